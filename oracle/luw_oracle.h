@@ -1,0 +1,71 @@
+/* TEST INFRASTRUCTURE -- CPU oracle for the LatticeUrbanWind LBM time step.
+ *
+ * This is a plain-C restatement of the algorithm in the reference's OpenCL-C device code
+ * (FX = /root/reference/core/cfd_core/FluidX3D/src): FX/kernel.cpp:833-1113 (indexing, codecs, f_eq, rho/u, Guo forcing),
+ * :1338-1351 (Esoteric-Pull load/store), :1370-1452 (initialize), :1475-1780 (stream_collide), :1938-2028 (update_fields),
+ * :2188-2310 (halo extract/insert), :2495-2571 (vk_inlet_apply).
+ *
+ * It is the CHECKER, never the product: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load it. The shipped CUDA path never links or calls anything in oracle/.
+ *
+ * PARITY PIN: the reference ships no golden vectors for this path. The oracle is instead pinned against the
+ * reference's OWN kernel text, compiled for host threads through oracle/ref_shim (oracle/_ref/libluwref_*.so), bit for bit:
+ * see tests/test_oracle_vs_reference.py and the committed fixtures in tests/golden/ produced by that build.
+ *
+ * Floating point: "as written" semantics. Compile with -ffp-contract=off; fused operations appear only where the
+ * reference writes fma(). Division and sqrt are IEEE correctly rounded.
+ */
+#ifndef LUW_ORACLE_H
+#define LUW_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { LUWO_FP32 = 0, LUWO_FP16S = 1, LUWO_FP16C = 2 };
+enum { /* compile-time switches of the reference (FX/defines.hpp:17-29) as run-time bits */
+	LUWO_UPDATE_FIELDS = 1u, LUWO_VOLUME_FORCE = 2u, LUWO_EQUILIBRIUM_BOUNDARIES = 4u, LUWO_SUBGRID = 8u,
+	LUWO_BUFFER_NUDGING = 16u, LUWO_TOP_SPONGE = 32u
+};
+
+typedef struct luwo_params { /* per-domain constants, FX/lbm.cpp:612-783 */
+	uint32_t Nx, Ny, Nz; /* local lattice incl. halo layers */
+	uint32_t Dx, Dy, Dz; /* domains per axis */
+	int32_t Ox, Oy, Oz; /* global coordinate of local cell 0 */
+	uint32_t precision; /* LUWO_FP32 / FP16S / FP16C */
+	uint32_t features; /* LUWO_* bits */
+	float w; /* def_w = 1/tau */
+	int32_t downstream_face; /* 0 none, 1 west, 2 east, 3 south, 4 north */
+	uint32_t buffer_N; float buffer_inv_tau; int32_t buffer_nudge_vertical;
+	uint32_t sponge_N; float sponge_inv_tau;
+} luwo_params;
+
+/* codecs (FX/kernel.cpp:864-875, FX/lbm.cpp:706-721) */
+float luwo_half_to_float(uint16_t h); /* IEEE binary16 -> binary32 */
+uint16_t luwo_float_to_half_rte(float f); /* IEEE binary32 -> binary16, round-to-nearest-even */
+float luwo_fp16c_to_float(uint16_t x);
+uint16_t luwo_float_to_fp16c(float x);
+
+void luwo_calculate_f_eq(float rho, float ux, float uy, float uz, float* feq);
+
+/* kernels: one call == one NDRange of the reference */
+void luwo_initialize(const luwo_params* p, void* fi, const float* rho, float* u, uint8_t* flags);
+void luwo_stream_collide(const luwo_params* p, void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t,
+	float fx, float fy, float fz, float omega_x, float omega_y, float omega_z);
+void luwo_update_fields(const luwo_params* p, const void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t,
+	float fx, float fy, float fz, float omega_x, float omega_y, float omega_z);
+void luwo_transfer_extract_fi(const luwo_params* p, uint32_t direction, uint64_t t, void* buf_p, void* buf_m, const void* fi);
+void luwo_transfer_insert_fi(const luwo_params* p, uint32_t direction, uint64_t t, const void* buf_p, const void* buf_m, void* fi);
+void luwo_transfer_extract_rho_u_flags(const luwo_params* p, uint32_t direction, char* buf_p, char* buf_m, const float* rho, const float* u, const uint8_t* flags);
+void luwo_transfer_insert_rho_u_flags(const luwo_params* p, uint32_t direction, const char* buf_p, const char* buf_m, float* rho, float* u, uint8_t* flags);
+void luwo_vk_inlet_apply(uint64_t N_cells, uint32_t use_interp, float t0, float t1, float alpha, uint64_t point_count, uint64_t mode_count, uint64_t mode_stride,
+	const uint64_t* point_cell, const uint8_t* point_face, const float* point_data, const float* mode_data, float* u);
+
+void luwo_set_threads(int n); /* 0 = all cores */
+int luwo_get_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
