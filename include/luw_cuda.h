@@ -1,0 +1,130 @@
+/* luw_cuda.h -- C ABI of the B200 (sm_100a) implementation of LatticeUrbanWind's LBM time step.
+ *
+ * This is the drop-in seam. In the reference the LBM host layer (FX/lbm.cpp, class LBM_Domain) reaches the device only through
+ * Device / Memory<T> / Kernel of FX/opencl.hpp:274-683 and the OpenCL-C program of FX/kernel.cpp. Every entry point below replaces
+ * one of those interactions; the citation next to it names the reference call it stands in for
+ * (FX = core/cfd_core/FluidX3D/src of hweifluids/LatticeUrbanWind).
+ *
+ * Conventions
+ *  - plain C types only; all pointers named `host_*` are host memory, `dev_*` are device memory of the domain's GPU;
+ *  - every function returns 0 on success, otherwise a luw_status code; luw_last_error_string() describes the last failure of the
+ *    calling thread. The reference prints and exit(1)s on any device error (FX/utilities.hpp:4370-4382, FX/opencl.hpp:613-618);
+ *    the C++ host layer (latticeurbanwind_b200/host/lbm.hpp) converts a non-zero status into the same print_error + exit(1);
+ *  - all work of a domain is enqueued on that domain's stream (luw_domain_set_stream) and is asynchronous unless stated;
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with LUW_ERR_NO_DEVICE.
+ *
+ * Memory layout (identical to the reference, FX/kernel.cpp:833-839,877-879): SoA, n = x + (y + z*Ny)*Nx over the LOCAL lattice
+ * including halo layers; fi[i*N + n] (i = 0..18, float / IEEE half scaled by 2^15 / custom 1-4-11 half), u[c*N + n], rho[n], flags[n].
+ */
+#ifndef LUW_CUDA_H
+#define LUW_CUDA_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum luw_status {
+	LUW_OK = 0,
+	LUW_ERR_INVALID = 1, /* bad argument / unsupported combination */
+	LUW_ERR_NO_DEVICE = 2, /* no CUDA device or driver */
+	LUW_ERR_OOM = 3, /* cudaMalloc failed (reference: predicted before allocation, FX/opencl.hpp:364-365) */
+	LUW_ERR_CUDA = 4 /* any other CUDA runtime error */
+} luw_status;
+
+/* DDF storage precision: compile-time FP16S / FP16C / (none) in FX/defines.hpp:13-14, `fpxx` in FX/defines.hpp:68-72 */
+enum { LUW_FP32 = 0, LUW_FP16S = 1, LUW_FP16C = 2 };
+/* extension switches: compile-time in the reference (FX/defines.hpp:17-29; BUFFER_NUDGING / TOP_SPONGE FX/lbm.cpp:770-782) */
+enum {
+	LUW_UPDATE_FIELDS = 1u, LUW_VOLUME_FORCE = 2u, LUW_EQUILIBRIUM_BOUNDARIES = 4u, LUW_SUBGRID = 8u,
+	LUW_BUFFER_NUDGING = 16u, LUW_TOP_SPONGE = 32u
+};
+/* arithmetic policy of the step kernels */
+enum {
+	LUW_ARITH_STRICT = 0, /* "as written": fused only where the reference writes fma(), IEEE div/sqrt -> bit-identical to oracle/ */
+	LUW_ARITH_FAST = 1 /* mul+add contraction and approximate reciprocals allowed (what -cl-mad-enable licenses, FX/opencl.hpp:305) */
+};
+enum { LUW_FIELD_RHO = 0, LUW_FIELD_U = 1, LUW_FIELD_FLAGS = 2, LUW_FIELD_FI = 3 };
+/* halo payloads: enum_transfer_field of FX/lbm.hpp:24 (fi: 5 DDFs per face cell; rho_u_flags: 17 bytes per face cell) */
+enum { LUW_HALO_FI = 0, LUW_HALO_RHO_U_FLAGS = 1 };
+
+typedef struct luw_device_info { /* subset of Device_Info, FX/opencl.hpp:89-188, used by device selection and the info printout */
+	char name[256];
+	uint64_t memory_bytes;
+	uint32_t compute_units; /* SMs */
+	uint32_t clock_mhz;
+	uint32_t cc_major, cc_minor;
+} luw_device_info;
+
+typedef struct luw_domain_params { /* LBM_Domain ctor arguments (FX/lbm.cpp:235-281) + the def_* constants of FX/lbm.cpp:612-783 */
+	uint32_t Nx, Ny, Nz; /* local lattice incl. halo layers */
+	uint32_t Dx, Dy, Dz; /* domains per axis (halo layers exist on axes with D>1) */
+	int32_t Ox, Oy, Oz; /* global coordinate of local cell 0 */
+	uint32_t precision; /* LUW_FP32 / LUW_FP16S / LUW_FP16C */
+	uint32_t features; /* LUW_* extension bits */
+	uint32_t arith; /* LUW_ARITH_STRICT / LUW_ARITH_FAST */
+	float w; /* def_w = 1/tau as the kernel sees it */
+	int32_t downstream_face; /* def_downstream_face: 0 none, 1 west, 2 east, 3 south, 4 north */
+	uint32_t buffer_N; float buffer_inv_tau; int32_t buffer_nudge_vertical; /* BUFFER_NUDGING constants */
+	uint32_t sponge_N; float sponge_inv_tau; /* TOP_SPONGE constants (sponge_ref_mode 0) */
+	int32_t device; /* CUDA device ordinal */
+} luw_domain_params;
+
+typedef struct luw_domain luw_domain; /* opaque: stands for one LBM_Domain's device side (Device + Memory<> + Kernel objects) */
+typedef struct luw_vk_inlet luw_vk_inlet; /* opaque: device buffers + kernel of VonKarmanInletUpdater (FX/setup.cpp:1034-1086) */
+
+const char* luw_last_error_string(void);
+
+/* get_devices() / Device_Info, FX/opencl.hpp:212-242 */
+int luw_device_count(int* count);
+int luw_get_device_info(int device, luw_device_info* info);
+
+/* LBM_Domain::LBM_Domain + allocate(): FX/lbm.cpp:235-338 (Memory<> ctors allocate and zero-fill, FX/opencl.hpp:383-391) */
+int luw_domain_create(const luw_domain_params* params, luw_domain** out);
+int luw_domain_destroy(luw_domain* dom); /* ~LBM_Domain / Memory<> dtors */
+/* use an existing CUDA stream (cudaStream_t passed as void*) for everything the domain enqueues; NULL restores the domain's own stream */
+int luw_domain_set_stream(luw_domain* dom, void* cuda_stream);
+int luw_domain_bytes(const luw_domain* dom, uint64_t* device_bytes); /* Device_Info::memory_used, FX/info.cpp:233-241 */
+
+/* Memory<T>::enqueue_write_to_device / enqueue_read_from_device(offset,length): FX/opencl.hpp:481-512. offset/count in ELEMENTS of the field
+ * (rho: N floats, u: 3N floats, flags: N bytes, fi: 19N fpxx). Host pointers may be pageable or pinned; copies are stream-ordered. */
+int luw_upload(luw_domain* dom, int field, const void* host_src, uint64_t offset, uint64_t count);
+int luw_download(luw_domain* dom, int field, void* host_dst, uint64_t offset, uint64_t count);
+int luw_device_ptr(luw_domain* dom, int field, void** dev_ptr); /* raw device pointer of a field (for peer / NCCL plumbing) */
+
+/* kernel "initialize", FX/kernel.cpp:1370-1452, enqueued by LBM_Domain::enqueue_initialize FX/lbm.cpp:340-343 (slot parity t=1 baked in) */
+int luw_initialize(luw_domain* dom);
+/* kernel "stream_collide", FX/kernel.cpp:1475-1780, enqueued by LBM_Domain::enqueue_stream_collide FX/lbm.cpp:344-346 with (t,fx,fy,fz,omega) */
+int luw_stream_collide(luw_domain* dom, uint64_t t, float fx, float fy, float fz, float omega_x, float omega_y, float omega_z);
+/* kernel "update_fields", FX/kernel.cpp:1938-2028, enqueued by LBM_Domain::enqueue_update_fields FX/lbm.cpp:348-355 */
+int luw_update_fields(luw_domain* dom, uint64_t t, float fx, float fy, float fz, float omega_x, float omega_y, float omega_z);
+/* k consecutive single-domain steps t0..t0+k-1 without host round trips: the body of LBM::run for D==1 (FX/lbm.cpp:1262-1312) minus its per-step finish() */
+int luw_run_steps(luw_domain* dom, uint64_t t0, uint64_t k, float fx, float fy, float fz, float omega_x, float omega_y, float omega_z);
+
+/* kernels "transfer_extract_*" / "transfer__insert_*", FX/kernel.cpp:2241-2310, enqueued by enqueue_transfer_extract/insert_field FX/lbm.cpp:1895-1906.
+ * axis 0/1/2 = x/y/z. dev_buf_p / dev_buf_m are DEVICE buffers of luw_halo_bytes() bytes each, laid out [b*A + a] like the reference's transfer buffers;
+ * who moves them between domains (peer copy, NCCL) is the caller's business -- that replaces the host-staged swap of FX/lbm.cpp:1907-1935. */
+int luw_halo_bytes(const luw_domain* dom, int payload, uint32_t axis, uint64_t* bytes);
+int luw_halo_extract(luw_domain* dom, int payload, uint32_t axis, uint64_t t, void* dev_buf_p, void* dev_buf_m);
+int luw_halo_insert(luw_domain* dom, int payload, uint32_t axis, uint64_t t, const void* dev_buf_p, const void* dev_buf_m);
+
+/* kernel "vk_inlet_apply", FX/kernel.cpp:2495-2571; buffers as packed by VonKarmanInletUpdater (FX/setup.cpp:886-1116):
+ * point_cell[P] u64 local cell index, point_face[P] u8, point_data[7*P] f32 SoA (px,py,pz,ubx,uby,ubz,sigma), mode_data[10*V] f32 SoA */
+int luw_vk_inlet_create(luw_domain* dom, uint64_t point_count, uint64_t mode_count, uint64_t mode_stride,
+	const uint64_t* host_point_cell, const uint8_t* host_point_face, const float* host_point_data, const float* host_mode_data, luw_vk_inlet** out);
+int luw_vk_inlet_apply(luw_vk_inlet* vk, uint32_t use_interp, float t0, float t1, float alpha);
+int luw_vk_inlet_destroy(luw_vk_inlet* vk);
+
+/* Device::finish_queue, FX/opencl.hpp:323 */
+int luw_sync(luw_domain* dom);
+
+/* timing helper for harnesses: CUDA events recorded on the domain's stream around whatever is enqueued between begin and end */
+int luw_timer_begin(luw_domain* dom);
+int luw_timer_end(luw_domain* dom, float* milliseconds); /* synchronises on the end event */
+/* number of kernels this library has launched on behalf of `dom` since creation */
+int luw_launch_count(const luw_domain* dom, uint64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LUW_CUDA_H */

@@ -1,0 +1,3 @@
+// Contraction allowed (-fmad=true): what the reference's OpenCL build flags license (-cl-mad-enable, FX/opencl.hpp:305).
+#define LUW_KERNELSET_FN kernels_fast
+#include "lbm_launch.inc"

@@ -1,0 +1,18 @@
+// Host-side launch interface between the C ABI (luw_cabi.cu) and the two arithmetic builds of the kernels.
+#pragma once
+#include "lbm_common.cuh"
+
+namespace luw {
+struct KernelSet { // one per arithmetic mode; every function enqueues exactly one kernel on `s` and returns the CUDA launch status
+	cudaError_t (*initialize)(const DomainConst& c, cudaStream_t s);
+	cudaError_t (*stream_collide)(const DomainConst& c, const StepArgs& a, cudaStream_t s);
+	cudaError_t (*update_fields)(const DomainConst& c, const StepArgs& a, cudaStream_t s);
+	cudaError_t (*halo_fi)(const DomainConst& c, int precision, uint32_t axis, uint32_t odd, bool insert, void* buf_p, void* buf_m, cudaStream_t s);
+	cudaError_t (*halo_rho_u_flags)(const DomainConst& c, uint32_t axis, bool insert, void* buf_p, void* buf_m, cudaStream_t s);
+	cudaError_t (*vk_inlet_apply)(uint64_t Ncells, uint32_t use_interp, float t0, float t1, float alpha, uint64_t P, uint64_t M, uint64_t V,
+		const uint64_t* point_cell, const uint8_t* point_face, const float* pd, const float* md, float* u, cudaStream_t s);
+	bool (*supported)(int precision, uint32_t features);
+};
+const KernelSet& kernels_strict(); // lbm_strict.cu: -fmad=false
+const KernelSet& kernels_fast(); // lbm_fast.cu: contraction allowed
+} // namespace luw

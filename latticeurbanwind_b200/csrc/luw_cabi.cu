@@ -1,0 +1,354 @@
+// C ABI of the B200 LBM step (include/luw_cuda.h): domain objects, device memory, stream-ordered copies and kernel enqueues.
+// Replaces the Device / Memory<T> / Kernel layer of the reference (FX/opencl.hpp:274-683) for LBM_Domain (FX/lbm.cpp:246-433).
+#include "../../include/luw_cuda.h"
+#include "lbm_launch.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(const int code, const std::string& msg) { g_error = msg; return code; }
+int cuda_fail(const cudaError_t e, const char* what) {
+	const int code = e==cudaErrorMemoryAllocation ? LUW_ERR_OOM : (e==cudaErrorNoDevice||e==cudaErrorInsufficientDriver||e==cudaErrorInitializationError) ? LUW_ERR_NO_DEVICE : LUW_ERR_CUDA;
+	return fail(code, std::string(what)+": "+cudaGetErrorName(e)+" ("+cudaGetErrorString(e)+")");
+}
+#define CU(call) do { const cudaError_t e_ = (call); if(e_!=cudaSuccess) return cuda_fail(e_, #call); } while(0)
+
+struct DeviceGuard { // every entry point may be called with any current device; restore it on exit
+	int prev = -1;
+	cudaError_t err;
+	explicit DeviceGuard(const int dev) { err = cudaGetDevice(&prev); if(err==cudaSuccess&&prev!=dev) err = cudaSetDevice(dev); }
+	~DeviceGuard() { if(prev>=0) cudaSetDevice(prev); }
+};
+
+} // namespace
+
+struct luw_domain {
+	luw_domain_params p;
+	luw::DomainConst c;
+	const luw::KernelSet* ks = nullptr;
+	cudaStream_t own_stream = nullptr, stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	float* wbuf = nullptr; float* sigma = nullptr;
+	uint64_t bytes = 0ull, launches = 0ull;
+	size_t ddf_size = 4u;
+};
+struct luw_vk_inlet {
+	luw_domain* dom;
+	uint64_t P, M, V;
+	uint64_t* point_cell; uint8_t* point_face; float* point_data; float* mode_data;
+};
+
+namespace {
+
+int field_info(const luw_domain* d, const int field, void** base, size_t* elem, uint64_t* count) {
+	const uint64_t N = d->c.N;
+	switch(field) {
+		case LUW_FIELD_RHO: *base = d->c.rho; *elem = 4u; *count = N; return LUW_OK;
+		case LUW_FIELD_U: *base = d->c.u; *elem = 4u; *count = 3ull*N; return LUW_OK;
+		case LUW_FIELD_FLAGS: *base = d->c.flags; *elem = 1u; *count = N; return LUW_OK;
+		case LUW_FIELD_FI: *base = d->c.fi; *elem = d->ddf_size; *count = 19ull*N; return LUW_OK;
+		default: return fail(LUW_ERR_INVALID, "unknown field id");
+	}
+}
+uint64_t face_area(const luw::DomainConst& c, const uint32_t axis) {
+	return axis==0u ? (uint64_t)c.Ny*c.Nz : axis==1u ? (uint64_t)c.Nz*c.Nx : (uint64_t)c.Nx*c.Ny;
+}
+template<typename T> int dev_alloc(luw_domain* d, T** ptr, const uint64_t count) {
+	const cudaError_t e = cudaMalloc((void**)ptr, count*sizeof(T));
+	if(e!=cudaSuccess) { *ptr = nullptr; return cuda_fail(e, "cudaMalloc"); }
+	d->bytes += count*sizeof(T);
+	return LUW_OK;
+}
+__global__ void k_fill_f32(float* p, const uint64_t n, const float v) {
+	for(uint64_t i=(uint64_t)blockIdx.x*blockDim.x+threadIdx.x; i<n; i+=(uint64_t)gridDim.x*blockDim.x) p[i] = v;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* luw_last_error_string(void) { return g_error.c_str(); }
+
+int luw_device_count(int* count) {
+	if(!count) return fail(LUW_ERR_INVALID, "count is null");
+	*count = 0;
+	const cudaError_t e = cudaGetDeviceCount(count);
+	if(e!=cudaSuccess) { *count = 0; return cuda_fail(e, "cudaGetDeviceCount"); }
+	return LUW_OK;
+}
+int luw_get_device_info(int device, luw_device_info* info) {
+	if(!info) return fail(LUW_ERR_INVALID, "info is null");
+	cudaDeviceProp pr;
+	CU(cudaGetDeviceProperties(&pr, device));
+	memset(info, 0, sizeof(*info));
+	strncpy(info->name, pr.name, sizeof(info->name)-1u);
+	info->memory_bytes = (uint64_t)pr.totalGlobalMem;
+	info->compute_units = (uint32_t)pr.multiProcessorCount;
+	int khz = 0;
+	cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+	info->clock_mhz = (uint32_t)(khz/1000);
+	info->cc_major = (uint32_t)pr.major; info->cc_minor = (uint32_t)pr.minor;
+	return LUW_OK;
+}
+
+int luw_domain_create(const luw_domain_params* p, luw_domain** out) {
+	if(!p||!out) return fail(LUW_ERR_INVALID, "null argument");
+	*out = nullptr;
+	if(p->Nx==0u||p->Ny==0u||p->Nz==0u||p->Dx==0u||p->Dy==0u||p->Dz==0u) return fail(LUW_ERR_INVALID, "lattice and domain counts must be positive");
+	if((p->Dx>1u&&p->Nx<4u)||(p->Dy>1u&&p->Ny<4u)||(p->Dz>1u&&p->Nz<4u)) return fail(LUW_ERR_INVALID, "a decomposed axis needs at least 2 cells plus 2 halo layers");
+	if(p->precision>2u) return fail(LUW_ERR_INVALID, "precision must be LUW_FP32, LUW_FP16S or LUW_FP16C");
+	if(p->arith>1u) return fail(LUW_ERR_INVALID, "arith must be LUW_ARITH_STRICT or LUW_ARITH_FAST");
+	if(p->Ny>65535u||p->Nz>65535u) return fail(LUW_ERR_INVALID, "Ny and Nz are limited to 65535 by the launch grid");
+	const uint64_t N = (uint64_t)p->Nx*p->Ny*p->Nz;
+	if(N>0xFFFFFFFFull) return fail(LUW_ERR_INVALID, "more than 2^32-1 cells per domain"); // the reference switches to 64-bit cell indices here (FX/lbm.cpp:631)
+	if((p->features&LUW_BUFFER_NUDGING)&&p->buffer_N==0u) return fail(LUW_ERR_INVALID, "buffer_N must be positive with BUFFER_NUDGING");
+	if((p->features&LUW_TOP_SPONGE)&&p->sponge_N==0u) return fail(LUW_ERR_INVALID, "sponge_N must be positive with TOP_SPONGE");
+	int ndev = 0;
+	{ const cudaError_t e = cudaGetDeviceCount(&ndev); if(e!=cudaSuccess||ndev==0) return e!=cudaSuccess ? cuda_fail(e, "cudaGetDeviceCount") : fail(LUW_ERR_NO_DEVICE, "no CUDA device"); }
+	if(p->device<0||p->device>=ndev) return fail(LUW_ERR_INVALID, "device ordinal out of range");
+	DeviceGuard guard(p->device);
+	if(guard.err!=cudaSuccess) return cuda_fail(guard.err, "cudaSetDevice");
+
+	luw_domain* d = new(std::nothrow) luw_domain();
+	if(!d) return fail(LUW_ERR_OOM, "host allocation failed");
+	d->p = *p;
+	d->ks = p->arith==LUW_ARITH_STRICT ? &luw::kernels_strict() : &luw::kernels_fast();
+	d->ddf_size = p->precision==LUW_FP32 ? 4u : 2u;
+	luw::DomainConst& c = d->c;
+	memset(&c, 0, sizeof(c));
+	c.Nx = p->Nx; c.Ny = p->Ny; c.Nz = p->Nz; c.N = N;
+	c.Dx = p->Dx; c.Dy = p->Dy; c.Dz = p->Dz; c.Ox = p->Ox; c.Oy = p->Oy; c.Oz = p->Oz;
+	c.Nxg = (p->Nx-2u*(p->Dx>1u))*p->Dx; c.Nyg = (p->Ny-2u*(p->Dy>1u))*p->Dy; c.Nzg = (p->Nz-2u*(p->Dz>1u))*p->Dz; // FX/lbm.cpp:613-627
+	c.wx = -p->Ox; c.ex = (int)c.Nxg-1-p->Ox; c.sy = -p->Oy; c.ny = (int)c.Nyg-1-p->Oy; c.tz = (int)c.Nzg-1-p->Oz;
+	c.has_w = c.wx>=0&&c.wx<(int)c.Nx; c.has_e = c.ex>=0&&c.ex<(int)c.Nx;
+	c.has_s = c.sy>=0&&c.sy<(int)c.Ny; c.has_n = c.ny>=0&&c.ny<(int)c.Ny; c.has_t = c.tz>=0&&c.tz<(int)c.Nz;
+	c.w = p->w; c.precision = (int)p->precision; c.features = p->features;
+	c.downstream_face = p->downstream_face;
+	c.buffer_N = p->buffer_N; c.buffer_inv_tau = p->buffer_inv_tau; c.nudge_vertical = p->buffer_nudge_vertical;
+	c.sponge_N = p->sponge_N;
+
+	int rc = LUW_OK;
+	cudaError_t e = cudaStreamCreateWithFlags(&d->own_stream, cudaStreamNonBlocking);
+	if(e==cudaSuccess) e = cudaEventCreate(&d->ev0);
+	if(e==cudaSuccess) e = cudaEventCreate(&d->ev1);
+	if(e!=cudaSuccess) rc = cuda_fail(e, "stream/event creation");
+	d->stream = d->own_stream;
+	if(rc==LUW_OK) rc = dev_alloc(d, (uint8_t**)&c.fi, 19ull*N*d->ddf_size);
+	if(rc==LUW_OK) rc = dev_alloc(d, &c.rho, N);
+	if(rc==LUW_OK) rc = dev_alloc(d, &c.u, 3ull*N);
+	if(rc==LUW_OK) rc = dev_alloc(d, &c.flags, N);
+	if(rc==LUW_OK) { // Memory<> zero-fills; rho starts at 1 (FX/lbm.cpp:283-288)
+		e = cudaMemsetAsync(c.fi, 0, 19ull*N*d->ddf_size, d->stream);
+		if(e==cudaSuccess) e = cudaMemsetAsync(c.u, 0, 3ull*N*4ull, d->stream);
+		if(e==cudaSuccess) e = cudaMemsetAsync(c.flags, 0, N, d->stream);
+		if(e==cudaSuccess) { k_fill_f32<<<1184, 256, 0, d->stream>>>(c.rho, N, 1.0f); e = cudaGetLastError(); d->launches++; }
+		if(e!=cudaSuccess) rc = cuda_fail(e, "zero-fill");
+	}
+	if(rc==LUW_OK&&(p->features&LUW_BUFFER_NUDGING)) { // distance -> sin^2 ramp, float arithmetic as written in FX/kernel.cpp:1579-1581
+		std::vector<float> t(p->buffer_N+1u);
+		for(uint32_t k=0u; k<=p->buffer_N; k++) { const float xi = 1.0f-(float)k/(float)p->buffer_N; float wb = sinf(1.5707963267948966f*xi); wb *= wb; t[k] = wb; }
+		rc = dev_alloc(d, &d->wbuf, t.size());
+		if(rc==LUW_OK) { e = cudaMemcpyAsync(d->wbuf, t.data(), t.size()*4u, cudaMemcpyHostToDevice, d->stream); if(e==cudaSuccess) e = cudaStreamSynchronize(d->stream); if(e!=cudaSuccess) rc = cuda_fail(e, "upload nudging table"); }
+	}
+	if(rc==LUW_OK&&(p->features&LUW_TOP_SPONGE)) { // depth -> inv_tau*sin^2 ramp, FX/kernel.cpp:1602-1605
+		std::vector<float> t(p->sponge_N);
+		const int Ns = (int)p->sponge_N;
+		for(int k=0; k<Ns; k++) { const float xi = Ns>1 ? 1.0f-(float)k/(float)(Ns-1) : 1.0f; float sg = sinf(1.5707963267948966f*xi); sg = p->sponge_inv_tau*sg*sg; t[(size_t)k] = sg; }
+		rc = dev_alloc(d, &d->sigma, t.size());
+		if(rc==LUW_OK) { e = cudaMemcpyAsync(d->sigma, t.data(), t.size()*4u, cudaMemcpyHostToDevice, d->stream); if(e==cudaSuccess) e = cudaStreamSynchronize(d->stream); if(e!=cudaSuccess) rc = cuda_fail(e, "upload sponge table"); }
+	}
+	c.wbuf = d->wbuf; c.sigma = d->sigma;
+	if(rc!=LUW_OK) { const std::string keep = g_error; luw_domain_destroy(d); g_error = keep; return rc; }
+	*out = d;
+	return LUW_OK;
+}
+
+int luw_domain_destroy(luw_domain* d) {
+	if(!d) return LUW_OK;
+	DeviceGuard guard(d->p.device);
+	if(d->own_stream) cudaStreamSynchronize(d->own_stream);
+	cudaFree(d->c.fi); cudaFree(d->c.rho); cudaFree(d->c.u); cudaFree(d->c.flags); cudaFree(d->wbuf); cudaFree(d->sigma);
+	if(d->ev0) cudaEventDestroy(d->ev0);
+	if(d->ev1) cudaEventDestroy(d->ev1);
+	if(d->own_stream) cudaStreamDestroy(d->own_stream);
+	delete d;
+	return LUW_OK;
+}
+
+int luw_domain_set_stream(luw_domain* d, void* cuda_stream) {
+	if(!d) return fail(LUW_ERR_INVALID, "null domain");
+	DeviceGuard guard(d->p.device);
+	CU(cudaStreamSynchronize(d->stream)); // work already enqueued on the old stream must not be overtaken
+	d->stream = cuda_stream ? (cudaStream_t)cuda_stream : d->own_stream;
+	return LUW_OK;
+}
+int luw_domain_bytes(const luw_domain* d, uint64_t* device_bytes) {
+	if(!d||!device_bytes) return fail(LUW_ERR_INVALID, "null argument");
+	*device_bytes = d->bytes;
+	return LUW_OK;
+}
+
+int luw_upload(luw_domain* d, int field, const void* host_src, uint64_t offset, uint64_t count) {
+	if(!d||!host_src) return fail(LUW_ERR_INVALID, "null argument");
+	void* base; size_t elem; uint64_t total;
+	if(const int rc = field_info(d, field, &base, &elem, &total)) return rc;
+	if(offset>total||count>total-offset) return fail(LUW_ERR_INVALID, "upload range exceeds the field");
+	DeviceGuard guard(d->p.device);
+	CU(cudaMemcpyAsync((char*)base+offset*elem, host_src, count*elem, cudaMemcpyHostToDevice, d->stream));
+	return LUW_OK;
+}
+int luw_download(luw_domain* d, int field, void* host_dst, uint64_t offset, uint64_t count) {
+	if(!d||!host_dst) return fail(LUW_ERR_INVALID, "null argument");
+	void* base; size_t elem; uint64_t total;
+	if(const int rc = field_info(d, field, &base, &elem, &total)) return rc;
+	if(offset>total||count>total-offset) return fail(LUW_ERR_INVALID, "download range exceeds the field");
+	DeviceGuard guard(d->p.device);
+	CU(cudaMemcpyAsync(host_dst, (const char*)base+offset*elem, count*elem, cudaMemcpyDeviceToHost, d->stream));
+	return LUW_OK;
+}
+int luw_device_ptr(luw_domain* d, int field, void** dev_ptr) {
+	if(!d||!dev_ptr) return fail(LUW_ERR_INVALID, "null argument");
+	size_t elem; uint64_t total;
+	return field_info(d, field, dev_ptr, &elem, &total);
+}
+
+int luw_initialize(luw_domain* d) {
+	if(!d) return fail(LUW_ERR_INVALID, "null domain");
+	DeviceGuard guard(d->p.device);
+	CU(d->ks->initialize(d->c, d->stream));
+	d->launches++;
+	return LUW_OK;
+}
+int luw_stream_collide(luw_domain* d, uint64_t t, float fx, float fy, float fz, float ox, float oy, float oz) {
+	if(!d) return fail(LUW_ERR_INVALID, "null domain");
+	DeviceGuard guard(d->p.device);
+	const luw::StepArgs a = { t, fx, fy, fz, ox, oy, oz };
+	CU(d->ks->stream_collide(d->c, a, d->stream));
+	d->launches++;
+	return LUW_OK;
+}
+int luw_update_fields(luw_domain* d, uint64_t t, float fx, float fy, float fz, float ox, float oy, float oz) {
+	if(!d) return fail(LUW_ERR_INVALID, "null domain");
+	DeviceGuard guard(d->p.device);
+	const luw::StepArgs a = { t, fx, fy, fz, ox, oy, oz };
+	CU(d->ks->update_fields(d->c, a, d->stream));
+	d->launches++;
+	return LUW_OK;
+}
+int luw_run_steps(luw_domain* d, uint64_t t0, uint64_t k, float fx, float fy, float fz, float ox, float oy, float oz) {
+	if(!d) return fail(LUW_ERR_INVALID, "null domain");
+	if(d->c.Dx*d->c.Dy*d->c.Dz!=1u) return fail(LUW_ERR_INVALID, "luw_run_steps is the single-domain fast path; decomposed runs need a halo exchange between steps");
+	DeviceGuard guard(d->p.device);
+	for(uint64_t s=0ull; s<k; s++) {
+		const luw::StepArgs a = { t0+s, fx, fy, fz, ox, oy, oz };
+		CU(d->ks->stream_collide(d->c, a, d->stream));
+		d->launches++;
+	}
+	return LUW_OK;
+}
+
+int luw_halo_bytes(const luw_domain* d, int payload, uint32_t axis, uint64_t* bytes) {
+	if(!d||!bytes||axis>2u) return fail(LUW_ERR_INVALID, "bad argument");
+	const uint64_t A = face_area(d->c, axis);
+	if(payload==LUW_HALO_FI) *bytes = 5ull*A*d->ddf_size; // transfers*sizeof(fpxx), FX/lbm.cpp:1937-1939
+	else if(payload==LUW_HALO_RHO_U_FLAGS) *bytes = 17ull*A; // FX/lbm.cpp:1940-1942
+	else return fail(LUW_ERR_INVALID, "unknown halo payload");
+	return LUW_OK;
+}
+static int halo(luw_domain* d, int payload, uint32_t axis, uint64_t t, void* bp, void* bm, const bool insert) {
+	if(!d||!bp||!bm||axis>2u) return fail(LUW_ERR_INVALID, "bad argument");
+	const uint32_t D = axis==0u ? d->c.Dx : axis==1u ? d->c.Dy : d->c.Dz;
+	if(D<2u) return fail(LUW_ERR_INVALID, "axis is not decomposed: it has no halo layers");
+	DeviceGuard guard(d->p.device);
+	if(payload==LUW_HALO_FI) CU(d->ks->halo_fi(d->c, d->c.precision, axis, (uint32_t)(t&1ull), insert, bp, bm, d->stream));
+	else if(payload==LUW_HALO_RHO_U_FLAGS) CU(d->ks->halo_rho_u_flags(d->c, axis, insert, bp, bm, d->stream));
+	else return fail(LUW_ERR_INVALID, "unknown halo payload");
+	d->launches++;
+	return LUW_OK;
+}
+int luw_halo_extract(luw_domain* d, int payload, uint32_t axis, uint64_t t, void* bp, void* bm) { return halo(d, payload, axis, t, bp, bm, false); }
+int luw_halo_insert(luw_domain* d, int payload, uint32_t axis, uint64_t t, const void* bp, const void* bm) { return halo(d, payload, axis, t, (void*)bp, (void*)bm, true); }
+
+int luw_vk_inlet_create(luw_domain* d, uint64_t P, uint64_t M, uint64_t V, const uint64_t* pc, const uint8_t* pf, const float* pd, const float* md, luw_vk_inlet** out) {
+	if(!d||!out||(P>0ull&&(!pc||!pf||!pd))||(V>0ull&&!md)) return fail(LUW_ERR_INVALID, "null argument");
+	*out = nullptr;
+	for(uint64_t i=0ull; i<P; i++) if(pc[i]>=d->c.N) return fail(LUW_ERR_INVALID, "inlet point outside the domain");
+	DeviceGuard guard(d->p.device);
+	luw_vk_inlet* v = new(std::nothrow) luw_vk_inlet();
+	if(!v) return fail(LUW_ERR_OOM, "host allocation failed");
+	memset(v, 0, sizeof(*v));
+	v->dom = d; v->P = P; v->M = M; v->V = V;
+	int rc = LUW_OK;
+	if(P>0ull) {
+		rc = dev_alloc(d, &v->point_cell, P);
+		if(rc==LUW_OK) rc = dev_alloc(d, &v->point_face, P);
+		if(rc==LUW_OK) rc = dev_alloc(d, &v->point_data, 7ull*P);
+	}
+	if(rc==LUW_OK&&V>0ull) rc = dev_alloc(d, &v->mode_data, 10ull*V);
+	if(rc==LUW_OK) {
+		cudaError_t e = cudaSuccess;
+		if(P>0ull) {
+			e = cudaMemcpyAsync(v->point_cell, pc, P*8ull, cudaMemcpyHostToDevice, d->stream);
+			if(e==cudaSuccess) e = cudaMemcpyAsync(v->point_face, pf, P, cudaMemcpyHostToDevice, d->stream);
+			if(e==cudaSuccess) e = cudaMemcpyAsync(v->point_data, pd, 7ull*P*4ull, cudaMemcpyHostToDevice, d->stream);
+		}
+		if(e==cudaSuccess&&V>0ull) e = cudaMemcpyAsync(v->mode_data, md, 10ull*V*4ull, cudaMemcpyHostToDevice, d->stream);
+		if(e==cudaSuccess) e = cudaStreamSynchronize(d->stream); // host arrays may be freed by the caller afterwards
+		if(e!=cudaSuccess) rc = cuda_fail(e, "upload inlet buffers");
+	}
+	if(rc!=LUW_OK) { const std::string keep = g_error; luw_vk_inlet_destroy(v); g_error = keep; return rc; }
+	*out = v;
+	return LUW_OK;
+}
+int luw_vk_inlet_apply(luw_vk_inlet* v, uint32_t use_interp, float t0, float t1, float alpha) {
+	if(!v) return fail(LUW_ERR_INVALID, "null inlet");
+	luw_domain* d = v->dom;
+	DeviceGuard guard(d->p.device);
+	CU(d->ks->vk_inlet_apply(d->c.N, use_interp, t0, t1, alpha, v->P, v->M, v->V, v->point_cell, v->point_face, v->point_data, v->mode_data, d->c.u, d->stream));
+	if(v->P>0ull) d->launches++;
+	return LUW_OK;
+}
+int luw_vk_inlet_destroy(luw_vk_inlet* v) {
+	if(!v) return LUW_OK;
+	DeviceGuard guard(v->dom->p.device);
+	cudaStreamSynchronize(v->dom->stream);
+	cudaFree(v->point_cell); cudaFree(v->point_face); cudaFree(v->point_data); cudaFree(v->mode_data);
+	delete v;
+	return LUW_OK;
+}
+
+int luw_sync(luw_domain* d) {
+	if(!d) return fail(LUW_ERR_INVALID, "null domain");
+	DeviceGuard guard(d->p.device);
+	CU(cudaStreamSynchronize(d->stream));
+	return LUW_OK;
+}
+int luw_timer_begin(luw_domain* d) {
+	if(!d) return fail(LUW_ERR_INVALID, "null domain");
+	DeviceGuard guard(d->p.device);
+	CU(cudaEventRecord(d->ev0, d->stream));
+	return LUW_OK;
+}
+int luw_timer_end(luw_domain* d, float* ms) {
+	if(!d||!ms) return fail(LUW_ERR_INVALID, "null argument");
+	DeviceGuard guard(d->p.device);
+	CU(cudaEventRecord(d->ev1, d->stream));
+	CU(cudaEventSynchronize(d->ev1));
+	CU(cudaEventElapsedTime(ms, d->ev0, d->ev1));
+	return LUW_OK;
+}
+int luw_launch_count(const luw_domain* d, uint64_t* launches) {
+	if(!d||!launches) return fail(LUW_ERR_INVALID, "null argument");
+	*launches = d->launches;
+	return LUW_OK;
+}
+
+} // extern "C"

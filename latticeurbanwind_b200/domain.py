@@ -1,0 +1,173 @@
+"""Host-side mirror of the reference's `LBM_Domain` (FX/lbm.hpp:26-221, FX/lbm.cpp:246-433) over the C ABI.
+
+One Domain = one block of the lattice on one GPU: host mirrors of rho / u / flags (numpy, like Memory<T>'s host side,
+FX/opencl.hpp:331-603), device buffers owned by the C library, and the enqueue_* calls of the reference under the same names.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi as A
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Domain:
+    def __init__(self, Nx, Ny, Nz, D=(1, 1, 1), O=(0, 0, 0), precision=A.FP32, features=0, w=1.0, arith=A.ARITH_STRICT, device=0,
+                 downstream_face=0, buffer_N=1, buffer_inv_tau=0.0, buffer_nudge_vertical=0, sponge_N=1, sponge_inv_tau=0.0):
+        self.params = A.DomainParams(Nx, Ny, Nz, D[0], D[1], D[2], O[0], O[1], O[2], precision, features, arith, np.float32(w),
+                                     downstream_face, buffer_N, np.float32(buffer_inv_tau), buffer_nudge_vertical, sponge_N,
+                                     np.float32(sponge_inv_tau), device)
+        self.Nx, self.Ny, self.Nz = Nx, Ny, Nz
+        self.N = Nx * Ny * Nz
+        self.precision = precision
+        self.ddf_dtype = np.float32 if precision == A.FP32 else np.uint16
+        self.t = 0
+        self.f = (0.0, 0.0, 0.0)
+        self.omega = (0.0, 0.0, 0.0)
+        self._h = C.c_void_p()
+        A.check(A.lib().luw_domain_create(C.byref(self.params), C.byref(self._h)))
+        # host mirrors, initialised like the reference's Memory<> objects (rho=1, u=0, flags=0; FX/lbm.cpp:283-288)
+        self.rho = np.ones(self.N, np.float32)
+        self.u = np.zeros(3 * self.N, np.float32)
+        self.flags = np.zeros(self.N, np.uint8)
+
+    # ---- lifetime
+    def close(self):
+        if self._h:
+            A.lib().luw_domain_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- Memory<T>::enqueue_write_to_device / enqueue_read_from_device
+    def _field(self, field):
+        return {A.FIELD_RHO: self.rho, A.FIELD_U: self.u, A.FIELD_FLAGS: self.flags}[field]
+
+    def write_to_device(self, field, offset=0, count=None):
+        host = self._field(field)
+        count = host.size - offset if count is None else count
+        A.check(A.lib().luw_upload(self._h, field, _ptr(host[offset:offset + count]), offset, count))
+
+    def read_from_device(self, field, offset=0, count=None):
+        host = self._field(field)
+        count = host.size - offset if count is None else count
+        A.check(A.lib().luw_download(self._h, field, _ptr(host[offset:offset + count]), offset, count))
+
+    def upload_all(self):
+        for f in (A.FIELD_RHO, A.FIELD_U, A.FIELD_FLAGS):
+            self.write_to_device(f)
+
+    def download_all(self):
+        for f in (A.FIELD_RHO, A.FIELD_U, A.FIELD_FLAGS):
+            self.read_from_device(f)
+        self.finish_queue()
+
+    def read_fi(self):
+        """Raw DDF image (device-only buffer in the reference; exposed for parity tests)."""
+        out = np.empty(19 * self.N, self.ddf_dtype)
+        A.check(A.lib().luw_download(self._h, A.FIELD_FI, _ptr(out), 0, out.size))
+        self.finish_queue()
+        return out
+
+    def write_fi(self, fi):
+        fi = np.ascontiguousarray(fi, self.ddf_dtype)
+        assert fi.size == 19 * self.N
+        A.check(A.lib().luw_upload(self._h, A.FIELD_FI, _ptr(fi), 0, fi.size))
+        self.finish_queue()
+
+    def device_ptr(self, field):
+        p = C.c_void_p()
+        A.check(A.lib().luw_device_ptr(self._h, field, C.byref(p)))
+        return p.value
+
+    # ---- kernels
+    def enqueue_initialize(self):
+        A.check(A.lib().luw_initialize(self._h))
+
+    def enqueue_stream_collide(self):
+        A.check(A.lib().luw_stream_collide(self._h, self.t, *map(float, self.f), *map(float, self.omega)))
+
+    def enqueue_update_fields(self):
+        A.check(A.lib().luw_update_fields(self._h, self.t, *map(float, self.f), *map(float, self.omega)))
+
+    def run_steps(self, k):
+        A.check(A.lib().luw_run_steps(self._h, self.t, k, *map(float, self.f), *map(float, self.omega)))
+        self.t += k
+
+    def increment_time_step(self, steps=1):
+        self.t += steps
+
+    def reset_time_step(self):
+        self.t = 0
+
+    def finish_queue(self):
+        A.check(A.lib().luw_sync(self._h))
+
+    def set_stream(self, cuda_stream):
+        A.check(A.lib().luw_domain_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    # ---- halo payloads (device buffers supplied by the caller as raw pointers)
+    def halo_bytes(self, payload, axis):
+        n = C.c_uint64()
+        A.check(A.lib().luw_halo_bytes(self._h, payload, axis, C.byref(n)))
+        return n.value
+
+    def halo_extract(self, payload, axis, buf_p, buf_m):
+        A.check(A.lib().luw_halo_extract(self._h, payload, axis, self.t, C.c_void_p(buf_p), C.c_void_p(buf_m)))
+
+    def halo_insert(self, payload, axis, buf_p, buf_m):
+        A.check(A.lib().luw_halo_insert(self._h, payload, axis, self.t, C.c_void_p(buf_p), C.c_void_p(buf_m)))
+
+    # ---- measurement helpers
+    def timer_begin(self):
+        A.check(A.lib().luw_timer_begin(self._h))
+
+    def timer_end(self):
+        ms = C.c_float()
+        A.check(A.lib().luw_timer_end(self._h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_uint64()
+        A.check(A.lib().luw_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def device_bytes(self):
+        n = C.c_uint64()
+        A.check(A.lib().luw_domain_bytes(self._h, C.byref(n)))
+        return n.value
+
+
+class VkInlet:
+    """Device side of VonKarmanInletUpdater (FX/setup.cpp:1034-1086, kernel FX/kernel.cpp:2495-2571)."""
+
+    def __init__(self, domain, point_cell, point_face, point_data, mode_data, mode_count, mode_stride):
+        self.domain = domain
+        self._h = C.c_void_p()
+        pc = np.ascontiguousarray(point_cell, np.uint64)
+        pf = np.ascontiguousarray(point_face, np.uint8)
+        pd = np.ascontiguousarray(point_data, np.float32)
+        md = np.ascontiguousarray(mode_data, np.float32)
+        assert pd.size == 7 * pc.size and md.size == 10 * mode_stride
+        A.check(A.lib().luw_vk_inlet_create(domain._h, pc.size, mode_count, mode_stride, _ptr(pc), _ptr(pf), _ptr(pd), _ptr(md), C.byref(self._h)))
+
+    def apply(self, use_interp, t0, t1, alpha):
+        A.check(A.lib().luw_vk_inlet_apply(self._h, int(use_interp), float(t0), float(t1), float(alpha)))
+
+    def close(self):
+        if self._h:
+            A.lib().luw_vk_inlet_destroy(self._h)
+            self._h = C.c_void_p()
