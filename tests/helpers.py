@@ -61,3 +61,112 @@ def decode(O, engine_or_none, fi, precision):
 
 def rel_l2(a, b):
     return float(np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) / max(np.linalg.norm(b.astype(np.float64)), 1e-300))
+
+
+# ---------------------------------------------------------------------------------------------------------------- golden fixtures
+GOLDEN_SHAPE, GOLDEN_STEPS = (24, 20, 16), 10
+TINY_SHAPE, TINY_STEPS = (12, 10, 8), 6
+HALO_SHAPE = (14, 12, 10)  # local lattice of one block of a 2x2x2 decomposition (halo layer on every axis)
+VK_SHAPE = (16, 12, 10)
+
+
+def golden_case(shape):
+    return cases.urban(*shape, seed=4321, edge=3, pitch=6)
+
+
+def golden_run(engine, O, precision, fset, shape=GOLDEN_SHAPE, steps=GOLDEN_STEPS):
+    flags, rho, u = golden_case(shape)
+    zones = dict(downstream_face=2, buffer_N=4, buffer_inv_tau=0.01, buffer_nudge_vertical=1, sponge_N=5, sponge_inv_tau=0.02)
+    return run_cpu(engine, O, shape, precision, O.FEATURE_SETS[fset], flags, rho, u, steps, cases.relaxation_rate(1e-6), zones=zones)
+
+
+def halo_params(O, precision, features=None):
+    zones = dict(downstream_face=2, buffer_N=4, buffer_inv_tau=0.01, buffer_nudge_vertical=1, sponge_N=5, sponge_inv_tau=0.02)
+    feat = O.FEATURE_SETS["luw"] if features is None else features
+    return O.make_params(*HALO_SHAPE, precision, feat, w=cases.relaxation_rate(1e-6), D=(2, 2, 2), O=(-1, -1, -1), **zones)
+
+
+def cut_block(shape_global, D, d, flags, rho, u):
+    """Host images of block d=(dx,dy,dz) of a D-decomposition incl. its halo layers, periodic at the global edges
+    (the index stitching of FX/lbm.hpp:274-297 / FX/lbm.cpp:1057-1073). Returns (local shape, offset O, flags, rho, u)."""
+    Ng = np.array(shape_global)
+    D = np.array(D)
+    H_ = (D > 1).astype(int)
+    Nl = Ng // D + 2 * H_
+    Ov = np.array(d) * (Ng // D) - H_
+    idx = [np.mod(np.arange(Nl[a]) + Ov[a], Ng[a]) for a in range(3)]
+    take = lambda a: a.reshape(Ng[2], Ng[1], Ng[0])[np.ix_(idx[2], idx[1], idx[0])].reshape(-1)
+    Ncell = int(np.prod(Ng))
+    ul = np.concatenate([take(u[c * Ncell:(c + 1) * Ncell]) for c in range(3)])
+    return tuple(int(v) for v in Nl), tuple(int(v) for v in Ov), take(flags).copy(), take(rho).copy(), ul
+
+
+def golden_halo(engine, O, precision):
+    """Block (0,0,0) of a 2x2x2 decomposition of the GOLDEN_SHAPE case: 3 steps, and every halo payload the step path moves, at both
+    slot parities (exchanged with itself, which is what a periodic 1-block-per-axis neighbourhood would do)."""
+    flags, rho, u = golden_case(GOLDEN_SHAPE)
+    shape, Ov, flags, rho, u = cut_block(GOLDEN_SHAPE, (2, 2, 2), (0, 0, 0), flags, rho, u)
+    assert shape == HALO_SHAPE and Ov == (-1, -1, -1)
+    p = halo_params(O, precision)
+    fi = np.zeros(19 * p.N, O.ddf_dtype(precision))
+    engine.bind(p)
+    engine.initialize(fi, rho, u, flags)
+    out = {}
+    name = O.PREC_NAME[precision]
+    for t in range(3):
+        engine.stream_collide(fi, rho, u, flags, t, FORCE, OMEGA)
+        for axis in range(3):
+            A = (p.Ny * p.Nz, p.Nz * p.Nx, p.Nx * p.Ny)[axis]
+            bp, bm = np.zeros(5 * A, fi.dtype), np.zeros(5 * A, fi.dtype)
+            engine.extract_fi(axis, t, bp, bm, fi)
+            out[f"halo_{name}_t{t}_axis{axis}_p"], out[f"halo_{name}_t{t}_axis{axis}_m"] = bp.copy(), bm.copy()
+            engine.insert_fi(axis, t, bm, bp, fi)
+        out[f"halo_{name}_t{t}_fi"] = fi.copy()
+    for axis in range(3):
+        A = (p.Ny * p.Nz, p.Nz * p.Nx, p.Nx * p.Ny)[axis]
+        bp, bm = np.zeros(17 * A, np.uint8), np.zeros(17 * A, np.uint8)
+        engine.extract_rho_u_flags(axis, bp, bm, rho, u, flags)
+        out[f"halo_{name}_ruf_axis{axis}_p"], out[f"halo_{name}_ruf_axis{axis}_m"] = bp.copy(), bm.copy()
+        engine.insert_rho_u_flags(axis, bm, bp, rho, u, flags)
+    out[f"halo_{name}_ruf_rho"], out[f"halo_{name}_ruf_u"], out[f"halo_{name}_ruf_flags"] = rho.copy(), u.copy(), flags.copy()
+    return out
+
+
+def codec_sweep():
+    """Floats covering the FP16C range (+-2), its subnormals, ties, and out-of-range values."""
+    rng = np.random.default_rng(99)
+    parts = [np.float32(s) * np.exp2(rng.uniform(-30, 2, 20000)).astype(np.float32) for s in (1.0, -1.0)]
+    bits = rng.integers(0, 2 ** 32, 20000, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    bits = bits[np.isfinite(bits)]
+    edge = np.array([0.0, -0.0, 1.0, -1.0, 1.9990234, 2.0, 3.0, 6.1035156e-5, 3.0517578e-5, 2.9802322e-8, 5.9604645e-8, 1e-9], np.float32)
+    return np.concatenate(parts + [bits, edge]).astype(np.float32)
+
+
+def vk_case(seed=7):
+    """Packed inlet buffers like VonKarmanInletUpdater's (FX/setup.cpp:886-1116): west-face points of a VK_SHAPE lattice, 2 faces x 24 modes."""
+    Nx, Ny, Nz = VK_SHAPE
+    N = Nx * Ny * Nz
+    rng = np.random.default_rng(seed)
+    ys, zs = np.meshgrid(np.arange(Ny), np.arange(1, Nz), indexing="ij")
+    cells_w = (0 + (ys + zs * Ny) * Nx).reshape(-1)
+    cells_s = (np.arange(1, Nx)[:, None] + (0 + np.arange(1, Nz)[None, :] * Ny) * Nx).reshape(-1)
+    pc = np.concatenate([cells_w, cells_s]).astype(np.uint64)
+    P = pc.size
+    pf = np.concatenate([np.zeros(cells_w.size, np.uint8), np.full(cells_s.size, 2, np.uint8)])
+    pf[::17] = 7  # "no synthesis" marker: base velocity only
+    pd = np.zeros(7 * P, np.float32)
+    pd[0 * P:1 * P] = (pc % Nx).astype(np.float32)
+    pd[1 * P:2 * P] = ((pc // Nx) % Ny).astype(np.float32)
+    pd[2 * P:3 * P] = (pc // (Nx * Ny)).astype(np.float32)
+    pd[3 * P:4 * P] = 0.08 + 0.01 * rng.random(P, dtype=np.float32)
+    pd[4 * P:5 * P] = 0.01 * (rng.random(P, dtype=np.float32) - 0.5)
+    pd[6 * P:7 * P] = 0.004 * rng.random(P, dtype=np.float32)
+    pd[6 * P + 3:7 * P:11] = 0.0  # sigma == 0 -> base velocity only
+    M, faces = 24, 5
+    V = faces * M
+    md = np.zeros(10 * V, np.float32)
+    md[0:3 * V] = rng.normal(0, 0.3, 3 * V).astype(np.float32)
+    md[3 * V:4 * V] = rng.normal(0, 0.05, V).astype(np.float32)
+    md[4 * V:7 * V] = rng.normal(0, 1.0, 3 * V).astype(np.float32)
+    md[7 * V:10 * V] = rng.uniform(0, 2 * np.pi, 3 * V).astype(np.float32)
+    return pc, pf, pd, md, M, V, N
