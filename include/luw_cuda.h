@@ -85,6 +85,9 @@ int luw_domain_destroy(luw_domain* dom); /* ~LBM_Domain / Memory<> dtors */
 /* use an existing CUDA stream (cudaStream_t passed as void*) for everything the domain enqueues; NULL restores the domain's own stream */
 int luw_domain_set_stream(luw_domain* dom, void* cuda_stream);
 int luw_domain_bytes(const luw_domain* dom, uint64_t* device_bytes); /* Device_Info::memory_used, FX/info.cpp:233-241 */
+/* which stream_collide implementation the domain runs: 1 = TMA-tiled persistent kernel (lattices whose x extent is a multiple of 16 and at least one
+ * tile wide), 0 = one-cell-per-thread kernel (any lattice). Same results; the reference has a single kernel (FX/kernel.cpp:1475). */
+int luw_domain_step_kernel(const luw_domain* dom, int* tiled);
 
 /* Memory<T>::enqueue_write_to_device / enqueue_read_from_device(offset,length): FX/opencl.hpp:481-512. offset/count in ELEMENTS of the field
  * (rho: N floats, u: 3N floats, flags: N bytes, fi: 19N fpxx). Host pointers may be pageable or pinned; copies are stream-ordered. */

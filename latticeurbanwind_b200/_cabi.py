@@ -43,6 +43,7 @@ EXPORTS = {  # name -> argtypes; every symbol include/luw_cuda.h declares
     "luw_domain_destroy": [C.c_void_p],
     "luw_domain_set_stream": [C.c_void_p, C.c_void_p],
     "luw_domain_bytes": [C.c_void_p, C.POINTER(C.c_uint64)],
+    "luw_domain_step_kernel": [C.c_void_p, C.POINTER(C.c_int)],
     "luw_upload": [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64],
     "luw_download": [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64],
     "luw_device_ptr": [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)],

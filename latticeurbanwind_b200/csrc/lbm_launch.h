@@ -1,8 +1,11 @@
 // Host-side launch interface between the C ABI (luw_cabi.cu) and the two arithmetic builds of the kernels.
 #pragma once
+#include <cuda.h>
 #include "lbm_common.cuh"
 
 namespace luw {
+struct TileMaps { CUtensorMap fi, flags; }; // TMA descriptors of the DDF array (4-D: x, y, z, slot) and the flag array (3-D) with the tile as box
+struct TileShape { int tx, ty, tz; };
 struct KernelSet { // one per arithmetic mode; every function enqueues exactly one kernel on `s` and returns the CUDA launch status
 	cudaError_t (*initialize)(const DomainConst& c, cudaStream_t s);
 	cudaError_t (*stream_collide)(const DomainConst& c, const StepArgs& a, cudaStream_t s);
@@ -12,6 +15,9 @@ struct KernelSet { // one per arithmetic mode; every function enqueues exactly o
 	cudaError_t (*vk_inlet_apply)(uint64_t Ncells, uint32_t use_interp, float t0, float t1, float alpha, uint64_t P, uint64_t M, uint64_t V,
 		const uint64_t* point_cell, const uint8_t* point_face, const float* pd, const float* md, float* u, cudaStream_t s);
 	bool (*supported)(int precision, uint32_t features);
+	// TMA-tiled stream_collide (lbm_tile.cuh): box shape of tile variant `variant` for this precision / feature set, false if there is none
+	bool (*tile_shape)(int precision, uint32_t features, int variant, TileShape* shape);
+	cudaError_t (*stream_collide_tile)(const DomainConst& c, const StepArgs& a, const TileMaps& maps, int variant, int sm_count, cudaStream_t s);
 };
 const KernelSet& kernels_strict(); // lbm_strict.cu: -fmad=false
 const KernelSet& kernels_fast(); // lbm_fast.cu: contraction allowed

@@ -1,0 +1,293 @@
+// Cell arithmetic of the LBM step on sm_100a's packed FP32 datapath.
+//
+// Blackwell issues FADD2 / FMUL2 / FFMA2: two IEEE-rounded FP32 operations per lane per instruction (64-bit register pairs). The
+// step kernel updates TWO x-adjacent cells per thread, so every add / multiply / fma of the collision is one packed instruction for
+// both cells. `f2` wraps that; each lane is rounded exactly like the scalar operation, so the STRICT formulation below (operations in
+// the reference's order, fused only where the reference writes fma(), FX/kernel.cpp:1016-1113,1686-1748) is bit-identical to the oracle.
+// The FAST formulation is an algebraically regrouped collision (pair sums / differences of opposite directions shared between
+// moments, equilibrium, Smagorinsky tensor and Guo forcing; approximate reciprocal and square root) for the tolerance-checked mode.
+//
+// All operations are explicit intrinsics, so the result does not depend on the translation unit's -fmad setting.
+#pragma once
+#include "lbm_common.cuh"
+
+namespace luw {
+namespace {
+
+struct f2 { float2 v; };
+__device__ __forceinline__ f2 mk2(const float a, const float b) { f2 r; r.v = make_float2(a, b); return r; }
+__device__ __forceinline__ f2 bc(const float a) { return mk2(a, a); }
+__device__ __forceinline__ f2 operator+(const f2 a, const f2 b) { f2 r; r.v = __fadd2_rn(a.v, b.v); return r; }
+__device__ __forceinline__ f2 operator-(const f2 a, const f2 b) { f2 r; r.v = __fadd2_rn(a.v, make_float2(-b.v.x, -b.v.y)); return r; }
+__device__ __forceinline__ f2 operator*(const f2 a, const f2 b) { f2 r; r.v = __fmul2_rn(a.v, b.v); return r; }
+__device__ __forceinline__ f2 operator*(const float a, const f2 b) { f2 r; r.v = __fmul2_rn(make_float2(a, a), b.v); return r; }
+__device__ __forceinline__ f2 operator-(const f2 a) { return mk2(-a.v.x, -a.v.y); }
+__device__ __forceinline__ f2 fma2(const f2 a, const f2 b, const f2 c) { f2 r; r.v = __ffma2_rn(a.v, b.v, c.v); return r; }
+__device__ __forceinline__ f2 fma2(const float a, const f2 b, const f2 c) { f2 r; r.v = __ffma2_rn(make_float2(a, a), b.v, c.v); return r; }
+__device__ __forceinline__ f2 fma2(const f2 a, const float b, const f2 c) { f2 r; r.v = __ffma2_rn(a.v, make_float2(b, b), c.v); return r; }
+__device__ __forceinline__ f2 fma2(const f2 a, const f2 b, const float c) { f2 r; r.v = __ffma2_rn(a.v, b.v, make_float2(c, c)); return r; }
+__device__ __forceinline__ f2 div_rn2(const f2 a, const f2 b) { return mk2(__fdiv_rn(a.v.x, b.v.x), __fdiv_rn(a.v.y, b.v.y)); }
+__device__ __forceinline__ f2 div_rn2(const float a, const f2 b) { return mk2(__fdiv_rn(a, b.v.x), __fdiv_rn(a, b.v.y)); }
+__device__ __forceinline__ f2 sqrt_rn2(const f2 a) { return mk2(__fsqrt_rn(a.v.x), __fsqrt_rn(a.v.y)); }
+__device__ __forceinline__ f2 clampc2(const f2 a) { return mk2(fminf(fmaxf(a.v.x, -LAT_C), LAT_C), fminf(fmaxf(a.v.y, -LAT_C), LAT_C)); }
+__device__ __forceinline__ float rcp_approx(const float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sqrt_approx(const float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ f2 rcp2(const f2 a) { return mk2(rcp_approx(a.v.x), rcp_approx(a.v.y)); }
+__device__ __forceinline__ f2 sqrt2(const f2 a) { return mk2(sqrt_approx(a.v.x), sqrt_approx(a.v.y)); }
+__device__ __forceinline__ f2 sel2(const bool c0, const bool c1, const f2 a, const f2 b) { return mk2(c0 ? a.v.x : b.v.x, c1 ? a.v.y : b.v.y); }
+
+struct PairIn { // what the step needs to know about the two cells besides their DDFs
+	bool e0, e1; // TYPE_E cell (with EQUILIBRIUM_BOUNDARIES): rho/u are boundary data
+	f2 rho_e, ux_e, uy_e, uz_e; // stored rho/u of TYPE_E lanes (unused lanes: anything finite)
+	bool zones; // run the relaxation-zone test for these cells
+	uint32_t x, y, z; // coordinates of the first cell (second: x+1)
+	uint32_t bo0, bo1; // flags & TYPE_BO
+};
+struct PairOut { f2 rho, ux, uy, uz; }; // the rho/u the reference writes with UPDATE_FIELDS (for non-TYPE_E cells)
+
+// nudging + sponge contribution for one cell, added in the reference's order (FX/kernel.cpp:1523-1614); scalar: zone cells are a thin shell
+__device__ __forceinline__ void zone_force(const DomainConst& c, const uint32_t x, const uint32_t y, const uint32_t z,
+	const float rho, const float ux, const float uy, const float uz, float& fxn, float& fyn, float& fzn) {
+	const uint64_t row = c.Nx, plane = (uint64_t)c.Nx*c.Ny;
+	if(c.features&F_NUDGING) {
+		const int xg = (int)x+c.Ox, yg = (int)y+c.Oy, zg = (int)z+c.Oz, Nb = (int)c.buffer_N;
+		const int dw = xg, de = (int)(c.Nxg-1u)-xg, ds = yg, dn = (int)(c.Nyg-1u)-yg, dt = (int)(c.Nzg-1u)-zg;
+		const bool in_w = c.downstream_face!=1&&c.has_w&&dw>=0&&dw<=Nb;
+		const bool in_e = c.downstream_face!=2&&c.has_e&&de>=0&&de<=Nb;
+		const bool in_s = c.downstream_face!=3&&c.has_s&&ds>=0&&ds<=Nb;
+		const bool in_n = c.downstream_face!=4&&c.has_n&&dn>=0&&dn<=Nb;
+		const bool in_t = c.has_t&&dt>=0&&dt<=Nb;
+		if(in_w||in_e||in_s||in_n||in_t) {
+			uint32_t dmin = c.buffer_N+1u;
+			uint64_t nref = 0ull;
+			if(in_w&&(uint32_t)dw<dmin) { dmin = (uint32_t)dw; nref = (uint64_t)c.wx+y*row+z*plane; }
+			if(in_e&&(uint32_t)de<dmin) { dmin = (uint32_t)de; nref = (uint64_t)c.ex+y*row+z*plane; }
+			if(in_s&&(uint32_t)ds<dmin) { dmin = (uint32_t)ds; nref = x+(uint64_t)c.sy*row+z*plane; }
+			if(in_n&&(uint32_t)dn<dmin) { dmin = (uint32_t)dn; nref = x+(uint64_t)c.ny*row+z*plane; }
+			if(in_t&&(uint32_t)dt<dmin) { dmin = (uint32_t)dt; nref = x+y*row+(uint64_t)c.tz*plane; }
+			const float k = __fmul_rn(__ldg(c.wbuf+dmin), c.buffer_inv_tau);
+			const float ax = __fmul_rn(k, __fadd_rn(__ldg(c.u+nref), -ux));
+			const float ay = __fmul_rn(k, __fadd_rn(__ldg(c.u+c.N+nref), -uy));
+			const float az = c.nudge_vertical==1 ? __fmul_rn(k, __fadd_rn(__ldg(c.u+2ull*c.N+nref), -uz)) : 0.0f;
+			fxn = __fadd_rn(fxn, __fmul_rn(rho, ax)); fyn = __fadd_rn(fyn, __fmul_rn(rho, ay)); fzn = __fadd_rn(fzn, __fmul_rn(rho, az));
+		}
+	}
+	if((c.features&F_SPONGE)&&c.has_t) {
+		const int dt = (int)(c.Nzg-2u)-((int)z+c.Oz);
+		if(dt>=0&&dt<(int)c.sponge_N) {
+			const float s = __ldg(c.sigma+dt);
+			const uint64_t nref = x+y*row+(uint64_t)c.tz*plane;
+			const float rs = __fmul_rn(rho, s);
+			fxn = __fadd_rn(fxn, __fmul_rn(rs, __fadd_rn(__ldg(c.u+nref), -ux)));
+			fyn = __fadd_rn(fyn, __fmul_rn(rs, __fadd_rn(__ldg(c.u+c.N+nref), -uy)));
+			fzn = __fadd_rn(fzn, __fmul_rn(rs, __fadd_rn(__ldg(c.u+2ull*c.N+nref), -uz)));
+		}
+	}
+}
+__device__ __forceinline__ void zone_force2(const DomainConst& c, const PairIn& in, const f2 rho, const f2 ux, const f2 uy, const f2 uz, f2& Fx, f2& Fy, f2& Fz) {
+	if(in.bo0!=TYPE_E) zone_force(c, in.x, in.y, in.z, rho.v.x, ux.v.x, uy.v.x, uz.v.x, Fx.v.x, Fy.v.x, Fz.v.x);
+	if(in.bo1!=TYPE_E) zone_force(c, in.x+1u, in.y, in.z, rho.v.y, ux.v.y, uy.v.y, uz.v.y, Fx.v.y, Fy.v.y, Fz.v.y);
+}
+
+// =================================================================== STRICT: the reference's operations, in its order
+// ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with -fmad=false (measured, CUDA 12.9); products that must be rounded on
+// their own are therefore formed with scalar FMULs (sm), which are never contracted; sums and explicit fmas stay packed.
+__device__ __forceinline__ f2 sm(const f2 a, const f2 b) { return mk2(__fmul_rn(a.v.x, b.v.x), __fmul_rn(a.v.y, b.v.y)); }
+__device__ __forceinline__ f2 sm(const float a, const f2 b) { return mk2(__fmul_rn(a, b.v.x), __fmul_rn(a, b.v.y)); }
+
+__device__ __forceinline__ void feq_strict2(const f2 rho, f2 ux, f2 uy, f2 uz, f2* feq) { // FX/kernel.cpp:1016-1073 (D3Q19 branch)
+	const f2 rhom1 = rho-bc(1.0f);
+	const f2 c3 = sm(-3.0f, (sm(ux, ux)+sm(uy, uy))+sm(uz, uz));
+	uz = sm(3.0f, uz); ux = sm(3.0f, ux); uy = sm(3.0f, uy);
+	feq[0] = sm(W0, fma2(rho, sm(0.5f, c3), rhom1));
+	const f2 u0 = ux+uy, u1 = ux+uz, u2 = uy+uz, u3 = ux-uy, u4 = ux-uz, u5 = uy-uz;
+	const f2 rhos = sm(WS, rho), rhoe = sm(WE, rho), rhom1s = sm(WS, rhom1), rhom1e = sm(WE, rhom1);
+#define LUW_FEQ2(i, a, r, r1) { const f2 q_ = fma2(a, a, c3); feq[i] = fma2(r, fma2(0.5f, q_, a), r1); feq[i+1] = fma2(r, fma2(0.5f, q_, -(a)), r1); }
+	LUW_FEQ2( 1, ux, rhos, rhom1s) LUW_FEQ2( 3, uy, rhos, rhom1s) LUW_FEQ2( 5, uz, rhos, rhom1s)
+	LUW_FEQ2( 7, u0, rhoe, rhom1e) LUW_FEQ2( 9, u1, rhoe, rhom1e) LUW_FEQ2(11, u2, rhoe, rhom1e)
+	LUW_FEQ2(13, u3, rhoe, rhom1e) LUW_FEQ2(15, u4, rhoe, rhom1e) LUW_FEQ2(17, u5, rhoe, rhom1e)
+#undef LUW_FEQ2
+}
+__device__ __forceinline__ void rho_u_strict2(const f2* f, f2& rho, f2& ux, f2& uy, f2& uz) { // FX/kernel.cpp:1075-1100
+	f2 r = f[0];
+#pragma unroll
+	for(int i=1; i<Q; i++) r = r+f[i];
+	r = r+bc(1.0f);
+	const f2 mx = ((((((((f[ 1]-f[ 2])+f[ 7])-f[ 8])+f[ 9])-f[10])+f[13])-f[14])+f[15])-f[16];
+	const f2 my = ((((((((f[ 3]-f[ 4])+f[ 7])-f[ 8])+f[11])-f[12])+f[14])-f[13])+f[17])-f[18];
+	const f2 mz = ((((((((f[ 5]-f[ 6])+f[ 9])-f[10])+f[11])-f[12])+f[16])-f[15])+f[18])-f[17];
+	rho = r; ux = div_rn2(mx, r); uy = div_rn2(my, r); uz = div_rn2(mz, r);
+}
+__device__ __forceinline__ void forcing_strict2(const f2 ux, const f2 uy, const f2 uz, const f2 fx, const f2 fy, const f2 fz, f2* Fin) { // FX/kernel.cpp:1103-1113
+	const f2 uF = sm(-0.33333334f, fma2(ux, fx, fma2(uy, fy, sm(uz, fz))));
+	const float t3 = 0.33333334f;
+	Fin[0] = sm(9.0f*W0, uF);
+	const float ks = 9.0f*WS, ke = 9.0f*WE;
+#define LUW_FIN2(i, k, cf, cu) { const f2 cf_ = (cf), cu_ = (cu); Fin[i] = sm(k, fma2(cf_, cu_+bc(t3), uF)); Fin[i+1] = sm(k, fma2(-cf_, (-cu_)+bc(t3), uF)); }
+	LUW_FIN2( 1, ks, fx, ux) LUW_FIN2( 3, ks, fy, uy) LUW_FIN2( 5, ks, fz, uz)
+	LUW_FIN2( 7, ke, fx+fy, ux+uy) LUW_FIN2( 9, ke, fx+fz, ux+uz) LUW_FIN2(11, ke, fy+fz, uy+uz)
+	LUW_FIN2(13, ke, fx-fy, ux-uy) LUW_FIN2(15, ke, fx-fz, ux-uz) LUW_FIN2(17, ke, fy-fz, uy-uz)
+#undef LUW_FIN2
+}
+__device__ __forceinline__ f2 smagorinsky_strict2(const float w0, const f2* f, const f2* feq, const f2 rho) { // FX/kernel.cpp:1723-1736
+	f2 n[Q];
+#pragma unroll
+	for(int i=1; i<Q; i++) n[i] = f[i]-feq[i];
+	const f2 Hxx = ((((((((n[1]+n[2])+n[7])+n[8])+n[9])+n[10])+n[13])+n[14])+n[15])+n[16];
+	const f2 Hyy = ((((((((n[3]+n[4])+n[7])+n[8])+n[11])+n[12])+n[13])+n[14])+n[17])+n[18];
+	const f2 Hzz = ((((((((n[5]+n[6])+n[9])+n[10])+n[11])+n[12])+n[15])+n[16])+n[17])+n[18];
+	const f2 Hxy = ((n[7]+n[8])-n[13])-n[14];
+	const f2 Hxz = ((n[9]+n[10])-n[15])-n[16];
+	const f2 Hyz = ((n[11]+n[12])-n[17])-n[18];
+	const float tau0 = __fdiv_rn(1.0f, w0);
+	const f2 Qn = ((sm(Hxx, Hxx)+sm(Hyy, Hyy))+sm(Hzz, Hzz))+sm(2.0f, (sm(Hxy, Hxy)+sm(Hxz, Hxz))+sm(Hyz, Hyz));
+	return div_rn2(2.0f, bc(tau0)+sqrt_rn2(bc(__fmul_rn(tau0, tau0))+div_rn2(sm(0.76421222f, sqrt_rn2(Qn)), rho)));
+}
+
+// f[19] (physical units): streamed DDFs in, post-collision DDFs out
+template<uint32_t FEAT> __device__ __forceinline__ void collide_strict2(const DomainConst& c, const StepArgs& a, const PairIn& in, f2* f, PairOut& out) {
+	constexpr bool VF = (FEAT&F_VOLUME_FORCE)!=0u, SG = (FEAT&F_SUBGRID)!=0u;
+	f2 rho, ux, uy, uz;
+	rho_u_strict2(f, rho, ux, uy, uz);
+	if(in.e0||in.e1) { rho = sel2(in.e0, in.e1, in.rho_e, rho); ux = sel2(in.e0, in.e1, in.ux_e, ux); uy = sel2(in.e0, in.e1, in.uy_e, uy); uz = sel2(in.e0, in.e1, in.uz_e, uz); }
+	f2 Fin[Q];
+	if(VF) {
+		const f2 m2rho = sm(-2.0f, rho);
+		f2 Fx = bc(a.fx)+sm(m2rho, sm(a.oy, uz)-sm(a.oz, uy));
+		f2 Fy = bc(a.fy)+sm(m2rho, sm(a.oz, ux)-sm(a.ox, uz));
+		f2 Fz = bc(a.fz)+sm(m2rho, sm(a.ox, uy)-sm(a.oy, ux));
+		if(in.zones) zone_force2(c, in, rho, ux, uy, uz, Fx, Fy, Fz);
+		const f2 rho2 = div_rn2(0.5f, rho);
+		ux = clampc2(fma2(Fx, rho2, ux)); uy = clampc2(fma2(Fy, rho2, uy)); uz = clampc2(fma2(Fz, rho2, uz));
+		forcing_strict2(ux, uy, uz, Fx, Fy, Fz, Fin);
+	} else {
+		ux = clampc2(ux); uy = clampc2(uy); uz = clampc2(uz);
+	}
+	out.rho = rho; out.ux = ux; out.uy = uy; out.uz = uz;
+	f2 feq[Q];
+	feq_strict2(rho, ux, uy, uz, feq);
+	f2 w = bc(c.w);
+	if(SG) w = smagorinsky_strict2(c.w, f, feq, rho);
+	const f2 omw = bc(1.0f)-w;
+	if(VF) {
+		const f2 c_tau = fma2(w, -0.5f, bc(1.0f));
+#pragma unroll
+		for(int i=0; i<Q; i++) f[i] = fma2(omw, f[i], fma2(w, feq[i], sm(Fin[i], c_tau)));
+	} else {
+#pragma unroll
+		for(int i=0; i<Q; i++) f[i] = fma2(omw, f[i], fma2(w, feq[i], bc(0.0f)));
+	}
+	if(in.e0||in.e1) {
+#pragma unroll
+		for(int i=0; i<Q; i++) f[i] = sel2(in.e0, in.e1, feq[i], f[i]);
+	}
+}
+
+// =================================================================== FAST: regrouped collision, tolerance-checked
+// g[19] = S*f (S = `scale`: 2^15 for FP16S so that the stored half is used as is; 1 otherwise), `inv` = 1/S. In and out in scaled units.
+// For each pair of opposite directions (i, i+1), i odd, with a = 3 c_i.u, A = c_i.F, r = w_i*rho:
+//   feq_i + feq_i+1 = e = r*(a^2 - 3u^2) + 2 w_i (rho-1)     feq_i - feq_i+1 = 2 r a
+//   the Smagorinsky tensor only needs n = (f_i + f_i+1) - e  (c_i c_i is the same for both members)
+//   post-collision: f_i' = (1-w) f_i + U + V,  f_i+1' = (1-w) f_i+1 + U - V,  U = w e/2 + kc (A a/3 + uF),  V = w r a + kc A/3,  kc = 9 w_i (1 - w/2)
+template<uint32_t FEAT> __device__ __forceinline__ void collide_fast2(const DomainConst& c, const StepArgs& a, const PairIn& in, f2* g, const float scale, const float inv, PairOut& out) {
+	constexpr bool VF = (FEAT&F_VOLUME_FORCE)!=0u, SG = (FEAT&F_SUBGRID)!=0u;
+	f2 s[9], d[9]; // pair sums / differences, k = (i-1)/2
+#pragma unroll
+	for(int k=0; k<9; k++) { s[k] = g[2*k+1]+g[2*k+2]; d[k] = g[2*k+1]-g[2*k+2]; }
+	const f2 R = (((g[0]+s[0])+(s[1]+s[2]))+((s[3]+s[4])+(s[5]+s[6])))+(s[7]+s[8]);
+	f2 rhom1 = inv*R;
+	f2 rho = rhom1+bc(1.0f);
+	// pairs: 0:(+x) 1:(+y) 2:(+z) 3:(+x+y) 4:(+x+z) 5:(+y+z) 6:(+x-y) 7:(+x-z) 8:(+y-z)
+	const f2 mx = ((d[0]+d[3])+(d[4]+d[6]))+d[7];
+	const f2 my = ((d[1]+d[3])+(d[5]-d[6]))+d[8];
+	const f2 mz = ((d[2]+d[4])+(d[5]-d[7]))-d[8];
+	f2 ir = rcp2(rho);
+	ir = fma2(ir, fma2(-rho, ir, bc(1.0f)), ir); // one Newton step: full single precision
+	const f2 iri = inv*ir;
+	f2 ux = mx*iri, uy = my*iri, uz = mz*iri;
+	if(in.e0||in.e1) {
+		rho = sel2(in.e0, in.e1, in.rho_e, rho); ux = sel2(in.e0, in.e1, in.ux_e, ux); uy = sel2(in.e0, in.e1, in.uy_e, uy); uz = sel2(in.e0, in.e1, in.uz_e, uz);
+		rhom1 = rho-bc(1.0f);
+		ir = rcp2(rho); ir = fma2(ir, fma2(-rho, ir, bc(1.0f)), ir);
+	}
+	f2 Fx, Fy, Fz, uF3;
+	if(VF) {
+		const f2 m2rho = -2.0f*rho;
+		Fx = fma2(m2rho, fma2(a.oy, uz, -(a.oz*uy)), bc(a.fx));
+		Fy = fma2(m2rho, fma2(a.oz, ux, -(a.ox*uz)), bc(a.fy));
+		Fz = fma2(m2rho, fma2(a.ox, uy, -(a.oy*ux)), bc(a.fz));
+		if(in.zones) zone_force2(c, in, rho, ux, uy, uz, Fx, Fy, Fz);
+		const f2 rho2 = 0.5f*ir;
+		ux = clampc2(fma2(Fx, rho2, ux)); uy = clampc2(fma2(Fy, rho2, uy)); uz = clampc2(fma2(Fz, rho2, uz));
+		uF3 = -(fma2(ux, Fx, fma2(uy, Fy, uz*Fz))); // = 3*uF = -(u.F)
+	} else {
+		ux = clampc2(ux); uy = clampc2(uy); uz = clampc2(uz);
+	}
+	out.rho = rho; out.ux = ux; out.uy = uy; out.uz = uz;
+	const f2 c3 = -3.0f*fma2(ux, ux, fma2(uy, uy, uz*uz));
+	const f2 ax = 3.0f*ux, ay = 3.0f*uy, az = 3.0f*uz;
+	f2 av[9] = { ax, ay, az, ax+ay, ax+az, ay+az, ax-ay, ax-az, ay-az };
+	const f2 rs = WS*rho, re = WE*rho, r1s = (2.0f*WS)*rhom1, r1e = (2.0f*WE)*rhom1;
+	f2 e[9]; // feq pair sums
+#pragma unroll
+	for(int k=0; k<9; k++) e[k] = fma2(k<3 ? rs : re, fma2(av[k], av[k], c3), k<3 ? r1s : r1e);
+	const f2 feq0 = W0*fma2(rho, 0.5f*c3, rhom1);
+	f2 w = bc(c.w);
+	if(SG) {
+		f2 n[9];
+#pragma unroll
+		for(int k=0; k<9; k++) n[k] = fma2(s[k], inv, -e[k]);
+		const f2 Hxx = ((n[0]+n[3])+(n[4]+n[6]))+n[7];
+		const f2 Hyy = ((n[1]+n[3])+(n[5]+n[6]))+n[8];
+		const f2 Hzz = ((n[2]+n[4])+(n[5]+n[7]))+n[8];
+		const f2 Hxy = n[3]-n[6], Hxz = n[4]-n[7], Hyz = n[5]-n[8];
+		const f2 Qn = fma2(Hxx, Hxx, fma2(Hyy, Hyy, Hzz*Hzz))+2.0f*fma2(Hxy, Hxy, fma2(Hxz, Hxz, Hyz*Hyz));
+		const float tau0 = __fdiv_rn(1.0f, c.w);
+		const f2 den = bc(tau0)+sqrt2(fma2(0.76421222f*sqrt2(Qn), ir, bc(__fmul_rn(tau0, tau0))));
+		f2 id = rcp2(den);
+		id = fma2(id, fma2(-den, id, bc(1.0f)), id);
+		w = 2.0f*id;
+	}
+	const f2 omw = bc(1.0f)-w;
+	const f2 hw = (0.5f*scale)*w; // S*w/2
+	if(VF) {
+		const f2 c_tau = fma2(w, -0.5f, bc(1.0f));
+		const f2 kcs = (9.0f*WS/3.0f*scale)*c_tau, kce = (9.0f*WE/3.0f*scale)*c_tau; // S*kc/3
+		const f2 Av[9] = { Fx, Fy, Fz, Fx+Fy, Fx+Fz, Fy+Fz, Fx-Fy, Fx-Fz, Fy-Fz };
+		const f2 wrs = (2.0f*hw)*rs, wre = (2.0f*hw)*re; // S*w*r
+#pragma unroll
+		for(int k=0; k<9; k++) {
+			const f2 kc = k<3 ? kcs : kce;
+			const f2 U = fma2(kc, fma2(Av[k], av[k], uF3), hw*e[k]);
+			const f2 V = fma2(k<3 ? wrs : wre, av[k], kc*Av[k]);
+			const f2 gi = g[2*k+1], gj = g[2*k+2];
+			g[2*k+1] = fma2(omw, gi, U+V);
+			g[2*k+2] = fma2(omw, gj, U-V);
+		}
+		g[0] = fma2(omw, g[0], fma2(2.0f*hw, feq0, ((9.0f*W0/3.0f*scale)*c_tau)*uF3));
+	} else {
+		const f2 wrs = (2.0f*hw)*rs, wre = (2.0f*hw)*re;
+#pragma unroll
+		for(int k=0; k<9; k++) {
+			const f2 U = hw*e[k];
+			const f2 V = (k<3 ? wrs : wre)*av[k];
+			const f2 gi = g[2*k+1], gj = g[2*k+2];
+			g[2*k+1] = fma2(omw, gi, U+V);
+			g[2*k+2] = fma2(omw, gj, U-V);
+		}
+		g[0] = fma2(omw, g[0], (2.0f*hw)*feq0);
+	}
+	if(in.e0||in.e1) { // TYPE_E: f := feq (FX/kernel.cpp:1747)
+		const f2 hs = bc(0.5f*scale);
+#pragma unroll
+		for(int k=0; k<9; k++) {
+			const f2 U = hs*e[k], V = (scale*(k<3 ? rs : re))*av[k];
+			g[2*k+1] = sel2(in.e0, in.e1, U+V, g[2*k+1]);
+			g[2*k+2] = sel2(in.e0, in.e1, U-V, g[2*k+2]);
+		}
+		g[0] = sel2(in.e0, in.e1, scale*feq0, g[0]);
+	}
+}
+
+} // anonymous namespace
+} // namespace luw

@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -39,6 +40,9 @@ struct luw_domain {
 	float* wbuf = nullptr; float* sigma = nullptr;
 	uint64_t bytes = 0ull, launches = 0ull;
 	size_t ddf_size = 4u;
+	luw::TileMaps maps; // TMA descriptors for the tiled step
+	bool tiled = false; // the tiled step is usable for this domain
+	int tile_variant = 0, sm_count = 0;
 };
 struct luw_vk_inlet {
 	luw_domain* dom;
@@ -67,6 +71,50 @@ template<typename T> int dev_alloc(luw_domain* d, T** ptr, const uint64_t count)
 	d->bytes += count*sizeof(T);
 	return LUW_OK;
 }
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+	CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+encode_tiled_fn get_encode_tiled() {
+	static encode_tiled_fn fn = nullptr;
+	if(!fn) {
+		void* p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q)==cudaSuccess&&q==cudaDriverEntryPointSuccess) fn = (encode_tiled_fn)p;
+	}
+	return fn;
+}
+// Build the TMA descriptors of a domain for the tile shape of the selected variant. Leaves d->tiled false when the lattice cannot be
+// described (row pitch not a multiple of 16 bytes for every array) -- the per-cell kernels are used then.
+void setup_tiles(luw_domain* d) {
+	d->tiled = false;
+	const char* off = getenv("LUW_NO_TILE");
+	if(off&&off[0]=='1') return;
+	const char* var = getenv("LUW_TILE_VARIANT");
+	d->tile_variant = var ? atoi(var) : 0;
+	luw::TileShape sh;
+	if(!d->ks->tile_shape(d->c.precision, d->c.features, d->tile_variant, &sh)) return;
+	const luw::DomainConst& c = d->c;
+	if(c.Nx%16u!=0u||c.Nx<(uint32_t)sh.tx) return;
+	encode_tiled_fn enc = get_encode_tiled();
+	if(!enc) return;
+	const cuuint64_t es = d->ddf_size;
+	const cuuint64_t dims4[4] = { c.Nx, c.Ny, c.Nz, 19u };
+	const cuuint64_t str4[3] = { c.Nx*es, (cuuint64_t)c.Nx*c.Ny*es, c.N*es };
+	const cuuint32_t box4[4] = { (cuuint32_t)sh.tx, (cuuint32_t)sh.ty, (cuuint32_t)sh.tz, 1u };
+	const cuuint32_t one4[4] = { 1u, 1u, 1u, 1u };
+	if(enc(&d->maps.fi, es==4u ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 4u, c.fi, dims4, str4, box4, one4,
+		CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)!=CUDA_SUCCESS) return;
+	const cuuint64_t dims3[3] = { c.Nx, c.Ny, c.Nz };
+	const cuuint64_t str3[2] = { c.Nx, (cuuint64_t)c.Nx*c.Ny };
+	if(enc(&d->maps.flags, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3u, c.flags, dims3, str3, box4, one4,
+		CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)!=CUDA_SUCCESS) return;
+	d->tiled = true;
+}
+cudaError_t enqueue_step(luw_domain* d, const luw::StepArgs& a) {
+	if(d->tiled) return d->ks->stream_collide_tile(d->c, a, d->maps, d->tile_variant, d->sm_count, d->stream);
+	return d->ks->stream_collide(d->c, a, d->stream);
+}
+
 __global__ void k_fill_f32(float* p, const uint64_t n, const float v) {
 	for(uint64_t i=(uint64_t)blockIdx.x*blockDim.x+threadIdx.x; i<n; i+=(uint64_t)gridDim.x*blockDim.x) p[i] = v;
 }
@@ -166,6 +214,10 @@ int luw_domain_create(const luw_domain_params* p, luw_domain** out) {
 		if(rc==LUW_OK) { e = cudaMemcpyAsync(d->sigma, t.data(), t.size()*4u, cudaMemcpyHostToDevice, d->stream); if(e==cudaSuccess) e = cudaStreamSynchronize(d->stream); if(e!=cudaSuccess) rc = cuda_fail(e, "upload sponge table"); }
 	}
 	c.wbuf = d->wbuf; c.sigma = d->sigma;
+	if(rc==LUW_OK) {
+		cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, p->device);
+		setup_tiles(d);
+	}
 	if(rc!=LUW_OK) { const std::string keep = g_error; luw_domain_destroy(d); g_error = keep; return rc; }
 	*out = d;
 	return LUW_OK;
@@ -193,6 +245,12 @@ int luw_domain_set_stream(luw_domain* d, void* cuda_stream) {
 int luw_domain_bytes(const luw_domain* d, uint64_t* device_bytes) {
 	if(!d||!device_bytes) return fail(LUW_ERR_INVALID, "null argument");
 	*device_bytes = d->bytes;
+	return LUW_OK;
+}
+
+int luw_domain_step_kernel(const luw_domain* d, int* tiled) {
+	if(!d||!tiled) return fail(LUW_ERR_INVALID, "null argument");
+	*tiled = d->tiled ? 1 : 0;
 	return LUW_OK;
 }
 
@@ -231,7 +289,7 @@ int luw_stream_collide(luw_domain* d, uint64_t t, float fx, float fy, float fz, 
 	if(!d) return fail(LUW_ERR_INVALID, "null domain");
 	DeviceGuard guard(d->p.device);
 	const luw::StepArgs a = { t, fx, fy, fz, ox, oy, oz };
-	CU(d->ks->stream_collide(d->c, a, d->stream));
+	CU(enqueue_step(d, a));
 	d->launches++;
 	return LUW_OK;
 }
@@ -249,7 +307,7 @@ int luw_run_steps(luw_domain* d, uint64_t t0, uint64_t k, float fx, float fy, fl
 	DeviceGuard guard(d->p.device);
 	for(uint64_t s=0ull; s<k; s++) {
 		const luw::StepArgs a = { t0+s, fx, fy, fz, ox, oy, oz };
-		CU(d->ks->stream_collide(d->c, a, d->stream));
+		CU(enqueue_step(d, a));
 		d->launches++;
 	}
 	return LUW_OK;

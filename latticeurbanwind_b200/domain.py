@@ -145,6 +145,11 @@ class Domain:
         A.check(A.lib().luw_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def uses_tiles(self):
+        n = C.c_int()
+        A.check(A.lib().luw_domain_step_kernel(self._h, C.byref(n)))
+        return bool(n.value)
+
     def device_bytes(self):
         n = C.c_uint64()
         A.check(A.lib().luw_domain_bytes(self._h, C.byref(n)))

@@ -13,10 +13,11 @@ def small_urban(Nx=48, Ny=40, Nz=32, seed=1234):
     return cases.urban(Nx, Ny, Nz, seed=seed, edge=6, pitch=12)
 
 
-def run_cpu(engine, O, shape, precision, features, flags, rho, u, steps, w, f=FORCE, omega=OMEGA, zones=ZONES, update_at_end=False):
+def run_cpu(engine, O, shape, precision, features, flags, rho, u, steps, w, f=FORCE, omega=OMEGA, zones=ZONES, update_at_end=False,
+            D=(1, 1, 1), Ov=(0, 0, 0)):
     """engine: oracle.Oracle() or oracle.Reference(...). Returns (fi, rho, u) after `steps` stream_collide calls."""
     Nx, Ny, Nz = shape
-    p = O.make_params(Nx, Ny, Nz, precision, features, w=w, **zones)
+    p = O.make_params(Nx, Ny, Nz, precision, features, w=w, D=D, O=Ov, **zones)
     fi = np.zeros(19 * p.N, O.ddf_dtype(precision))
     flags, rho, u = flags.copy(), rho.copy(), u.copy()
     engine.bind(p)
@@ -28,10 +29,13 @@ def run_cpu(engine, O, shape, precision, features, flags, rho, u, steps, w, f=FO
     return fi, rho, u
 
 
-def run_cuda(shape, precision, features, flags, rho, u, steps, w, arith, f=FORCE, omega=OMEGA, zones=ZONES, update_at_end=False, batched=False):
+def run_cuda(shape, precision, features, flags, rho, u, steps, w, arith, f=FORCE, omega=OMEGA, zones=ZONES, update_at_end=False, batched=False,
+             D=(1, 1, 1), O=(0, 0, 0), expect_tiles=None):
     from latticeurbanwind_b200.domain import Domain
     Nx, Ny, Nz = shape
-    with Domain(Nx, Ny, Nz, precision=precision, features=features, w=w, arith=arith, **zones) as d:
+    with Domain(Nx, Ny, Nz, D=D, O=O, precision=precision, features=features, w=w, arith=arith, **zones) as d:
+        if expect_tiles is not None:
+            assert d.uses_tiles() == expect_tiles, "unexpected stream_collide implementation"
         d.rho[:], d.u[:], d.flags[:] = rho, u, flags
         d.f, d.omega = f, omega
         d.upload_all()

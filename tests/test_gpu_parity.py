@@ -59,3 +59,71 @@ def test_update_fields_on_demand(oracle_lib):
         ref = H.run_cpu(O.Oracle(), O, shape, precision, feat, flags, rho, u, 7, w, update_at_end=True)
         got = H.run_cuda(shape, precision, feat, flags, rho, u, 7, w, arith=0, update_at_end=True, batched=True)
         assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+
+
+# ---------------------------------------------------------------------------------------------- the TMA-tiled step kernel
+TILED_SHAPES = [(64, 8, 4), (128, 20, 12), (80, 10, 7), (192, 9, 5)]  # exact tiles, several tiles, partial tiles in x / y / z
+
+
+@pytest.mark.parametrize("precision", [0, 1, 2], ids=["fp32", "fp16s", "fp16c"])
+@pytest.mark.parametrize("fset", ["bench", "plain", "luw", "luwnf"])
+@pytest.mark.parametrize("shape", TILED_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_tiled_strict_equals_oracle(oracle_lib, precision, fset, shape):
+    O = oracle_lib
+    flags, rho, u = cases.urban(*shape, seed=77, edge=3, pitch=6)
+    w = cases.relaxation_rate(1e-6)
+    feat = H.FEATURE_SETS[fset]
+    zones = dict(downstream_face=2, buffer_N=3, buffer_inv_tau=0.01, buffer_nudge_vertical=1, sponge_N=2, sponge_inv_tau=0.02)
+    ref = H.run_cpu(O.Oracle(), O, shape, precision, feat, flags, rho, u, 9, w, zones=zones)
+    got = H.run_cuda(shape, precision, feat, flags, rho, u, 9, w, arith=0, zones=zones, expect_tiles=True)
+    assert np.array_equal(H.decode(O, None, got[0], precision), H.decode(O, None, ref[0], precision)), "DDFs differ"
+    assert np.array_equal(got[1], ref[1]), "rho differs"
+    assert np.array_equal(got[2], ref[2]), "u differs"
+
+
+@pytest.mark.parametrize("precision", [0, 1], ids=["fp32", "fp16s"])
+def test_tiled_periodic_box_equals_oracle(oracle_lib, precision):
+    """Fully periodic lattice (upstream BENCHMARK protocol): every wrapped neighbour goes through the tile kernel's boundary patch."""
+    O = oracle_lib
+    shape = (128, 12, 6)
+    flags, rho, u = cases.periodic_box(*shape, seed=5, amp=1e-2)
+    w = cases.relaxation_rate(1.0 / 6.0)
+    ref = H.run_cpu(O.Oracle(), O, shape, precision, 0, flags, rho, u, 11, w)
+    got = H.run_cuda(shape, precision, 0, flags, rho, u, 11, w, arith=0, expect_tiles=True)
+    assert np.array_equal(H.decode(O, None, got[0], precision), H.decode(O, None, ref[0], precision))
+
+
+@pytest.mark.parametrize("precision", [0, 1], ids=["fp32", "fp16s"])
+def test_tiled_decomposed_block_equals_oracle(oracle_lib, precision):
+    """One block of a 2x2x2 decomposition: halo cells must not execute, their slots must survive the tile write-back unchanged."""
+    O = oracle_lib
+    glob = (124, 20, 12)
+    flags, rho, u = cases.urban(*glob, seed=3, edge=3, pitch=6)
+    shape, Ov, flags, rho, u = H.cut_block(glob, (2, 2, 2), (1, 0, 1), flags, rho, u)
+    assert shape == (64, 12, 8)
+    w = cases.relaxation_rate(1e-6)
+    feat = H.FEATURE_SETS["luw"]
+    zones = dict(downstream_face=2, buffer_N=3, buffer_inv_tau=0.01, buffer_nudge_vertical=1, sponge_N=2, sponge_inv_tau=0.02)
+    ref = H.run_cpu(O.Oracle(), O, shape, precision, feat, flags, rho, u, 5, w, zones=zones, D=(2, 2, 2), Ov=Ov)
+    got = H.run_cuda(shape, precision, feat, flags, rho, u, 5, w, arith=0, zones=zones, D=(2, 2, 2), O=Ov, expect_tiles=True)
+    assert np.array_equal(H.decode(O, None, got[0], precision), H.decode(O, None, ref[0], precision))
+    assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+
+
+TOL_TILED_FAST = {0: dict(rel_l2_u=2e-5, max_abs_u=3e-6, rel_l2_rho=1e-6), 1: dict(rel_l2_u=2e-3, max_abs_u=4e-4, rel_l2_rho=1e-4), 2: dict(rel_l2_u=1e-3, max_abs_u=2e-4, rel_l2_rho=1e-4)}
+
+
+@pytest.mark.parametrize("precision", [0, 1, 2], ids=["fp32", "fp16s", "fp16c"])
+@pytest.mark.parametrize("fset", ["bench", "luw"])
+def test_tiled_fast_within_tolerance(oracle_lib, precision, fset):
+    O = oracle_lib
+    shape = (128, 40, 24)
+    flags, rho, u = cases.urban(*shape, seed=11, edge=6, pitch=12)
+    w = cases.relaxation_rate(1e-6)
+    feat = H.FEATURE_SETS[fset]
+    ref = H.run_cpu(O.Oracle(), O, shape, precision, feat, flags, rho, u, STEPS, w, update_at_end=(fset == "bench"))
+    got = H.run_cuda(shape, precision, feat, flags, rho, u, STEPS, w, arith=1, update_at_end=(fset == "bench"), expect_tiles=True)
+    tol = TOL_TILED_FAST[precision]
+    assert H.rel_l2(got[2], ref[2]) <= tol["rel_l2_u"]
+    assert float(np.abs(got[2] - ref[2]).max()) <= tol["max_abs_u"]
+    assert H.rel_l2(got[1], ref[1]) <= tol["rel_l2_rho"]
