@@ -37,8 +37,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrie
 __device__ __forceinline__ void mbar_wait(uint64_t* b, const uint32_t parity) {
 	uint32_t done = 0u, spins = 0u;
 	while(!done) {
-		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
-		if(!done&&++spins>(1u<<26)) __trap(); // a lost arrival must abort the launch, not hang the device
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(b)), "r"(parity), "r"(1000000u) : "memory"); // suspend-time hint [ns]
+		if(!done&&++spins>(1u<<24)) __trap(); // a lost arrival must abort the launch, not hang the device
 	}
 }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, const int c0, const int c1, const int c2, const int c3) {
@@ -143,7 +143,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 	constexpr bool UF = (FEAT&F_UPDATE_FIELDS)!=0u, EQ = (FEAT&F_EQUILIBRIUM)!=0u, VF = (FEAT&F_VOLUME_FORCE)!=0u;
 
 	extern __shared__ uint8_t smem_raw[];
-	uint8_t* stage0 = (uint8_t*)(((uintptr_t)smem_raw+127u)&~(uintptr_t)127u);
+	uint8_t* stage0 = smem_raw+((128u-(smem_u32(smem_raw)&127u))&127u); // 128 B aligned; derived from the __shared__ symbol so that LDS/STS are emitted
 	uint64_t* bar_full = (uint64_t*)(stage0+(size_t)S*CFG::STAGE_BYTES);
 	uint64_t* bar_done = bar_full+S;
 	uint64_t* bar_empty = bar_done+S;
@@ -212,17 +212,21 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 	const float scale = (FAST&&P==P_FP16S) ? 32768.0f : 1.0f, inv = (FAST&&P==P_FP16S) ? 3.0517578E-5f : 1.0f;
 	const uint64_t rowN = c.Nx, planeN = (uint64_t)c.Nx*c.Ny;
 	const uint32_t xskip = c.Dx>1u ? 0xFFFFFFFFu : c.Nx-1u; // the column left to k_stream_collide_xcol
+	const bool has_zones = VF&&(c.features&(F_NUDGING|F_SPONGE))!=0u;
+	const int Nb = (c.features&F_NUDGING) ? (int)c.buffer_N : -1, Ns = (c.features&F_SPONGE) ? (int)c.sponge_N : 0;
+	// walk: strip = blockIdx.x, blockIdx.x+gridDim.x, ...; inside a strip xt = 0..tiles_x-1; ring slot s and its phase advance with every tile
+	uint32_t strip = blockIdx.x, xt = 0u, s = 0u, ph = 0u;
+	int y0 = (int)(strip%tiles_y)*TY, z0 = (int)(strip/tiles_y)*TZ;
 	for(uint32_t q=0u; q<my_tiles; q++) {
-		const int s = (int)(q%(uint32_t)S), s1 = (int)((q+1u)%(uint32_t)S);
-		const uint32_t strip = blockIdx.x+(q/tiles_x)*gridDim.x, xt = q%tiles_x;
-		const int x0 = (int)xt*TX, y0 = (int)(strip%tiles_y)*TY, z0 = (int)(strip/tiles_y)*TZ;
-		uint8_t* st = stage0+(size_t)s*CFG::STAGE_BYTES;
-		uint8_t* st1 = stage0+(size_t)s1*CFG::STAGE_BYTES;
+		const uint32_t s1 = s+1u==(uint32_t)S ? 0u : s+1u, ph1 = s+1u==(uint32_t)S ? ph^1u : ph;
+		const int x0 = (int)xt*TX;
+		uint8_t* const st = stage0+(size_t)s*CFG::STAGE_BYTES;
+		uint8_t* const st1 = stage0+(size_t)s1*CFG::STAGE_BYTES;
 		const bool has_next = xt+1u<tiles_x; // the next tile of the strip holds the +x slots of this tile's last column
 		const bool bnd_yz = y0==0||y0+TY>=(int)c.Ny||z0==0||z0+TZ>=(int)c.Nz; // strip touches the y/z boundary (uniform)
 		const bool edge = bnd_yz||x0==0||x0+TX>=(int)c.Nx;
-		if(xt==0u) { mbar_wait(bar_full+s, (q/(uint32_t)S)&1u); if(bnd_yz) patch_yz<CFG, true>(c, st, x0, y0, z0, odd, tid); }
-		if(has_next) { mbar_wait(bar_full+s1, ((q+1u)/(uint32_t)S)&1u); if(bnd_yz) patch_yz<CFG, true>(c, st1, x0+TX, y0, z0, odd, tid); }
+		if(xt==0u) { mbar_wait(bar_full+s, ph); if(bnd_yz) patch_yz<CFG, true>(c, st, x0, y0, z0, odd, tid); }
+		if(has_next) { mbar_wait(bar_full+s1, ph1); if(bnd_yz) patch_yz<CFG, true>(c, st1, x0+TX, y0, z0, odd, tid); }
 		if(bnd_yz) consumer_bar((uint32_t)NC);
 
 		const uint32_t x = (uint32_t)x0+lx, y = (uint32_t)y0+ly, z = (uint32_t)z0+lz;
@@ -239,58 +243,60 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 			// element right of the pair's word in an x-shifted box: the next word of the row, or column 0 of the same row in the next stage
 			uint8_t* const nxt = last_in_row ? (has_next ? st1+(size_t)row*TX*CFG::ES : (uint8_t*)box) : (uint8_t*)(box+1);
 			PairIn in;
-			in.x = x; in.y = y; in.z = z; in.bo0 = fl0&TYPE_BO; in.bo1 = fl1&TYPE_BO;
-			in.e0 = EQ&&run0&&in.bo0==TYPE_E; in.e1 = EQ&&run1&&in.bo1==TYPE_E;
+			const uint32_t bo0 = fl0&TYPE_BO, bo1 = fl1&TYPE_BO;
+			in.e0 = EQ&&run0&&bo0==TYPE_E; in.e1 = EQ&&run1&&bo1==TYPE_E;
 			const uint64_t n = (uint64_t)x+(uint64_t)y*rowN+(uint64_t)z*planeN;
+			in.zones = false;
+			if(has_zones) { // tile-uniform pre-test: does the tile reach into a relaxation zone? then gather the per-cell zone data now
+				const int xg0 = x0+c.Ox, yg0 = y0+c.Oy, zg1 = z0+TZ-1+c.Oz;
+				if(xg0<=Nb||xg0+TX-1>=(int)c.Nxg-1-Nb||yg0<=Nb||yg0+TY-1>=(int)c.Nyg-1-Nb||zg1>=(int)c.Nzg-1-Nb||zg1>=(int)c.Nzg-2-Ns) {
+					in.nudge_vertical = c.nudge_vertical;
+					in.zr0 = zone_prefetch(c, x, y, z, run0&&bo0!=TYPE_E);
+					in.zr1 = zone_prefetch(c, x+1u, y, z, run1&&bo1!=TYPE_E);
+					in.zones = in.zr0.nudge||in.zr0.sponge||in.zr1.nudge||in.zr1.sponge;
+				}
+			}
 			if(in.e0||in.e1) {
 				in.rho_e = mk2(in.e0 ? c.rho[n] : 1.0f, in.e1 ? c.rho[n+1ull] : 1.0f);
 				in.ux_e = mk2(in.e0 ? c.u[n] : 0.0f, in.e1 ? c.u[n+1ull] : 0.0f);
 				in.uy_e = mk2(in.e0 ? c.u[c.N+n] : 0.0f, in.e1 ? c.u[c.N+n+1ull] : 0.0f);
 				in.uz_e = mk2(in.e0 ? c.u[2ull*c.N+n] : 0.0f, in.e1 ? c.u[2ull*c.N+n+1ull] : 0.0f);
 			}
-			in.zones = false;
-			if(VF&&(c.features&(F_NUDGING|F_SPONGE))) { // tile-uniform pre-test: does the tile reach into a relaxation zone?
-				const int Nb = (c.features&F_NUDGING) ? (int)c.buffer_N : -1, Ns = (c.features&F_SPONGE) ? (int)c.sponge_N : 0;
-				const int xg0 = x0+c.Ox, yg0 = y0+c.Oy, zg1 = z0+TZ-1+c.Oz;
-				in.zones = xg0<=Nb||xg0+TX-1>=(int)c.Nxg-1-Nb||yg0<=Nb||yg0+TY-1>=(int)c.Nyg-1-Nb||zg1>=(int)c.Nzg-1-Nb||zg1>=(int)c.Nzg-2-Ns;
-			}
 			// load_f: box 0 -> f0, box 1+2k -> f_(2k+1), box 2+2k -> f_(2k+2); pairs 0,3,4,6,7 have c_x = +1
-			R raw[Q];
+			f2 f[Q];
 #pragma unroll
 			for(int b=0; b<Q; b++) {
-				const R w0 = box[b*(TILE/2)];
-				const bool xs = b==2||b==8||b==10||b==14||b==16;
-				raw[b] = xs ? PC::shift_in(w0, nxt+(size_t)b*CFG::BOX_BYTES) : w0;
+				R w = box[b*(TILE/2)];
+				if(b==2||b==8||b==10||b==14||b==16) w = PC::shift_in(w, nxt+(size_t)b*CFG::BOX_BYTES);
+				if(FAST&&P==P_FP16S) f[b] = PairCodec<P_FP16S>::dec_raw(*(const uint32_t*)&w); else f[b] = PC::dec(w);
 			}
-			f2 f[Q];
 			PairOut out;
-			if(FAST&&P==P_FP16S) {
-#pragma unroll
-				for(int b=0; b<Q; b++) f[b] = PairCodec<P_FP16S>::dec_raw(*(const uint32_t*)&raw[b]);
-				collide_fast2<FEAT>(c, a, in, f, scale, inv, out);
-			} else {
-#pragma unroll
-				for(int b=0; b<Q; b++) f[b] = PC::dec(raw[b]);
-				if(FAST) collide_fast2<FEAT>(c, a, in, f, 1.0f, 1.0f, out);
-				else collide_strict2<FEAT>(c, a, in, f, out);
-			}
+			if(FAST) collide_fast2<FEAT>(c, a, in, f, scale, inv, out);
+			else collide_strict2<FEAT>(c, a, in, f, out);
 			// store_f: f_i' goes to slot B (box 2+2k), f_i+1' to slot A (box 1+2k)
 			R nw[Q];
-			if(FAST&&P==P_FP16S) {
 #pragma unroll
-				for(int b=0; b<Q; b++) { const uint32_t r_ = PairCodec<P_FP16S>::enc_raw(f[b]); nw[b] = *(const R*)&r_; }
-			} else {
-#pragma unroll
-				for(int b=0; b<Q; b++) nw[b] = PC::enc(f[b]);
+			for(int b=0; b<Q; b++) {
+				if(FAST&&P==P_FP16S) { const uint32_t r_ = PairCodec<P_FP16S>::enc_raw(f[b]); nw[b] = *(const R*)&r_; } else nw[b] = PC::enc(f[b]);
 			}
-			const bool both = run0&&run1;
-			box[0] = both ? nw[0] : PC::mix(run0, run1, nw[0], box[0]);
+			if(run0&&run1) {
+				box[0] = nw[0];
 #pragma unroll
-			for(int k=0; k<9; k++) {
-				const int bA = 1+2*k, bB = 2+2*k;
-				box[bA*(TILE/2)] = both ? nw[bB] : PC::mix(run0, run1, nw[bB], box[bA*(TILE/2)]);
-				if(k==0||k==3||k==4||k==6||k==7) PC::shift_out((uint8_t*)(box+bB*(TILE/2)), nxt+(size_t)bB*CFG::BOX_BYTES, nw[bA], run0, run1);
-				else box[bB*(TILE/2)] = both ? nw[bA] : PC::mix(run0, run1, nw[bA], box[bB*(TILE/2)]);
+				for(int k=0; k<9; k++) {
+					const int bA = 1+2*k, bB = 2+2*k;
+					box[bA*(TILE/2)] = nw[bB];
+					if(k==0||k==3||k==4||k==6||k==7) PC::shift_out((uint8_t*)(box+bB*(TILE/2)), nxt+(size_t)bB*CFG::BOX_BYTES, nw[bA], true, true);
+					else box[bB*(TILE/2)] = nw[bA];
+				}
+			} else {
+				box[0] = PC::mix(run0, run1, nw[0], box[0]);
+#pragma unroll
+				for(int k=0; k<9; k++) {
+					const int bA = 1+2*k, bB = 2+2*k;
+					box[bA*(TILE/2)] = PC::mix(run0, run1, nw[bB], box[bA*(TILE/2)]);
+					if(k==0||k==3||k==4||k==6||k==7) PC::shift_out((uint8_t*)(box+bB*(TILE/2)), nxt+(size_t)bB*CFG::BOX_BYTES, nw[bA], run0, run1);
+					else box[bB*(TILE/2)] = PC::mix(run0, run1, nw[bA], box[bB*(TILE/2)]);
+				}
 			}
 			if(UF) {
 				const bool w0 = run0&&!in.e0, w1 = run1&&!in.e1;
@@ -309,6 +315,8 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 		}
 		fence_async_smem(); // make this thread's shared-memory writes visible to the TMA store
 		mbar_arrive(bar_done+s);
+		s = s1; ph = ph1;
+		if(++xt==tiles_x) { xt = 0u; strip += gridDim.x; y0 = (int)(strip%tiles_y)*TY; z0 = (int)(strip/tiles_y)*TZ; }
 	}
 }
 

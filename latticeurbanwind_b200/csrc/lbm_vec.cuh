@@ -36,18 +36,17 @@ __device__ __forceinline__ f2 rcp2(const f2 a) { return mk2(rcp_approx(a.v.x), r
 __device__ __forceinline__ f2 sqrt2(const f2 a) { return mk2(sqrt_approx(a.v.x), sqrt_approx(a.v.y)); }
 __device__ __forceinline__ f2 sel2(const bool c0, const bool c1, const f2 a, const f2 b) { return mk2(c0 ? a.v.x : b.v.x, c1 ? a.v.y : b.v.y); }
 
-struct PairIn { // what the step needs to know about the two cells besides their DDFs
-	bool e0, e1; // TYPE_E cell (with EQUILIBRIUM_BOUNDARIES): rho/u are boundary data
-	f2 rho_e, ux_e, uy_e, uz_e; // stored rho/u of TYPE_E lanes (unused lanes: anything finite)
-	bool zones; // run the relaxation-zone test for these cells
-	uint32_t x, y, z; // coordinates of the first cell (second: x+1)
-	uint32_t bo0, bo1; // flags & TYPE_BO
+// relaxation-zone data of one cell (FX/kernel.cpp:1523-1614): gathered BEFORE the DDFs are read so that the dependent global loads
+// (reference velocity at the boundary face / top plane) are in flight while the moments are computed
+struct ZoneRef {
+	bool nudge, sponge; // cell lies in the buffer-nudging shell / in the top sponge (and is not TYPE_E)
+	float kn, unx, uny, unz; // nudging: w_buf*inv_tau and the target velocity u[n_ref]
+	float ks, usx, usy, usz; // sponge: sigma and the reference velocity at the top plane
 };
-struct PairOut { f2 rho, ux, uy, uz; }; // the rho/u the reference writes with UPDATE_FIELDS (for non-TYPE_E cells)
-
-// nudging + sponge contribution for one cell, added in the reference's order (FX/kernel.cpp:1523-1614); scalar: zone cells are a thin shell
-__device__ __forceinline__ void zone_force(const DomainConst& c, const uint32_t x, const uint32_t y, const uint32_t z,
-	const float rho, const float ux, const float uy, const float uz, float& fxn, float& fyn, float& fzn) {
+__device__ __forceinline__ ZoneRef zone_prefetch(const DomainConst& c, const uint32_t x, const uint32_t y, const uint32_t z, const bool active) {
+	ZoneRef r;
+	r.nudge = false; r.sponge = false; r.kn = 0.0f; r.unx = r.uny = r.unz = 0.0f; r.ks = 0.0f; r.usx = r.usy = r.usz = 0.0f;
+	if(!active) return r;
 	const uint64_t row = c.Nx, plane = (uint64_t)c.Nx*c.Ny;
 	if(c.features&F_NUDGING) {
 		const int xg = (int)x+c.Ox, yg = (int)y+c.Oy, zg = (int)z+c.Oz, Nb = (int)c.buffer_N;
@@ -65,28 +64,50 @@ __device__ __forceinline__ void zone_force(const DomainConst& c, const uint32_t 
 			if(in_s&&(uint32_t)ds<dmin) { dmin = (uint32_t)ds; nref = x+(uint64_t)c.sy*row+z*plane; }
 			if(in_n&&(uint32_t)dn<dmin) { dmin = (uint32_t)dn; nref = x+(uint64_t)c.ny*row+z*plane; }
 			if(in_t&&(uint32_t)dt<dmin) { dmin = (uint32_t)dt; nref = x+y*row+(uint64_t)c.tz*plane; }
-			const float k = __fmul_rn(__ldg(c.wbuf+dmin), c.buffer_inv_tau);
-			const float ax = __fmul_rn(k, __fadd_rn(__ldg(c.u+nref), -ux));
-			const float ay = __fmul_rn(k, __fadd_rn(__ldg(c.u+c.N+nref), -uy));
-			const float az = c.nudge_vertical==1 ? __fmul_rn(k, __fadd_rn(__ldg(c.u+2ull*c.N+nref), -uz)) : 0.0f;
-			fxn = __fadd_rn(fxn, __fmul_rn(rho, ax)); fyn = __fadd_rn(fyn, __fmul_rn(rho, ay)); fzn = __fadd_rn(fzn, __fmul_rn(rho, az));
+			r.nudge = true;
+			r.kn = __fmul_rn(__ldg(c.wbuf+dmin), c.buffer_inv_tau);
+			r.unx = __ldg(c.u+nref); r.uny = __ldg(c.u+c.N+nref); r.unz = __ldg(c.u+2ull*c.N+nref);
 		}
 	}
 	if((c.features&F_SPONGE)&&c.has_t) {
 		const int dt = (int)(c.Nzg-2u)-((int)z+c.Oz);
 		if(dt>=0&&dt<(int)c.sponge_N) {
-			const float s = __ldg(c.sigma+dt);
 			const uint64_t nref = x+y*row+(uint64_t)c.tz*plane;
-			const float rs = __fmul_rn(rho, s);
-			fxn = __fadd_rn(fxn, __fmul_rn(rs, __fadd_rn(__ldg(c.u+nref), -ux)));
-			fyn = __fadd_rn(fyn, __fmul_rn(rs, __fadd_rn(__ldg(c.u+c.N+nref), -uy)));
-			fzn = __fadd_rn(fzn, __fmul_rn(rs, __fadd_rn(__ldg(c.u+2ull*c.N+nref), -uz)));
+			r.sponge = true;
+			r.ks = __ldg(c.sigma+dt);
+			r.usx = __ldg(c.u+nref); r.usy = __ldg(c.u+c.N+nref); r.usz = __ldg(c.u+2ull*c.N+nref);
 		}
 	}
+	return r;
 }
-__device__ __forceinline__ void zone_force2(const DomainConst& c, const PairIn& in, const f2 rho, const f2 ux, const f2 uy, const f2 uz, f2& Fx, f2& Fy, f2& Fz) {
-	if(in.bo0!=TYPE_E) zone_force(c, in.x, in.y, in.z, rho.v.x, ux.v.x, uy.v.x, uz.v.x, Fx.v.x, Fy.v.x, Fz.v.x);
-	if(in.bo1!=TYPE_E) zone_force(c, in.x+1u, in.y, in.z, rho.v.y, ux.v.y, uy.v.y, uz.v.y, Fx.v.y, Fy.v.y, Fz.v.y);
+// the two contributions, added in the reference's order and with its roundings
+__device__ __forceinline__ void zone_apply(const ZoneRef& r, const int nudge_vertical, const float rho, const float ux, const float uy, const float uz, float& fxn, float& fyn, float& fzn) {
+	if(r.nudge) {
+		const float ax = __fmul_rn(r.kn, __fadd_rn(r.unx, -ux));
+		const float ay = __fmul_rn(r.kn, __fadd_rn(r.uny, -uy));
+		const float az = nudge_vertical==1 ? __fmul_rn(r.kn, __fadd_rn(r.unz, -uz)) : 0.0f;
+		fxn = __fadd_rn(fxn, __fmul_rn(rho, ax)); fyn = __fadd_rn(fyn, __fmul_rn(rho, ay)); fzn = __fadd_rn(fzn, __fmul_rn(rho, az));
+	}
+	if(r.sponge) {
+		const float rs = __fmul_rn(rho, r.ks);
+		fxn = __fadd_rn(fxn, __fmul_rn(rs, __fadd_rn(r.usx, -ux)));
+		fyn = __fadd_rn(fyn, __fmul_rn(rs, __fadd_rn(r.usy, -uy)));
+		fzn = __fadd_rn(fzn, __fmul_rn(rs, __fadd_rn(r.usz, -uz)));
+	}
+}
+
+struct PairIn { // what the step needs to know about the two cells besides their DDFs
+	bool e0, e1; // TYPE_E cell (with EQUILIBRIUM_BOUNDARIES): rho/u are boundary data
+	f2 rho_e, ux_e, uy_e, uz_e; // stored rho/u of TYPE_E lanes (unused lanes: anything finite)
+	bool zones; // some lane lies in a relaxation zone
+	int nudge_vertical;
+	ZoneRef zr0, zr1;
+};
+struct PairOut { f2 rho, ux, uy, uz; }; // the rho/u the reference writes with UPDATE_FIELDS (for non-TYPE_E cells)
+
+__device__ __forceinline__ void zone_force2(const PairIn& in, const f2 rho, const f2 ux, const f2 uy, const f2 uz, f2& Fx, f2& Fy, f2& Fz) {
+	zone_apply(in.zr0, in.nudge_vertical, rho.v.x, ux.v.x, uy.v.x, uz.v.x, Fx.v.x, Fy.v.x, Fz.v.x);
+	zone_apply(in.zr1, in.nudge_vertical, rho.v.y, ux.v.y, uy.v.y, uz.v.y, Fx.v.y, Fy.v.y, Fz.v.y);
 }
 
 // =================================================================== STRICT: the reference's operations, in its order
@@ -156,7 +177,7 @@ template<uint32_t FEAT> __device__ __forceinline__ void collide_strict2(const Do
 		f2 Fx = bc(a.fx)+sm(m2rho, sm(a.oy, uz)-sm(a.oz, uy));
 		f2 Fy = bc(a.fy)+sm(m2rho, sm(a.oz, ux)-sm(a.ox, uz));
 		f2 Fz = bc(a.fz)+sm(m2rho, sm(a.ox, uy)-sm(a.oy, ux));
-		if(in.zones) zone_force2(c, in, rho, ux, uy, uz, Fx, Fy, Fz);
+		if(in.zones) zone_force2(in, rho, ux, uy, uz, Fx, Fy, Fz);
 		const f2 rho2 = div_rn2(0.5f, rho);
 		ux = clampc2(fma2(Fx, rho2, ux)); uy = clampc2(fma2(Fy, rho2, uy)); uz = clampc2(fma2(Fz, rho2, uz));
 		forcing_strict2(ux, uy, uz, Fx, Fy, Fz, Fin);
@@ -189,58 +210,72 @@ template<uint32_t FEAT> __device__ __forceinline__ void collide_strict2(const Do
 //   feq_i + feq_i+1 = e = r*(a^2 - 3u^2) + 2 w_i (rho-1)     feq_i - feq_i+1 = 2 r a
 //   the Smagorinsky tensor only needs n = (f_i + f_i+1) - e  (c_i c_i is the same for both members)
 //   post-collision: f_i' = (1-w) f_i + U + V,  f_i+1' = (1-w) f_i+1 + U - V,  U = w e/2 + kc (A a/3 + uF),  V = w r a + kc A/3,  kc = 9 w_i (1 - w/2)
+// Per-pair quantities (a, A, e) are recomputed where they are used instead of being kept in registers: the kernel is register-bound.
+struct Proj { f2 x, y, z; }; // a vector whose projections on the 9 pair directions are needed
+__device__ __forceinline__ f2 proj(const Proj& v, const int k) { // pairs: 0:+x 1:+y 2:+z 3:+x+y 4:+x+z 5:+y+z 6:+x-y 7:+x-z 8:+y-z
+	switch(k) {
+		case 0: return v.x; case 1: return v.y; case 2: return v.z;
+		case 3: return v.x+v.y; case 4: return v.x+v.z; case 5: return v.y+v.z;
+		case 6: return v.x-v.y; case 7: return v.x-v.z; default: return v.y-v.z;
+	}
+}
 template<uint32_t FEAT> __device__ __forceinline__ void collide_fast2(const DomainConst& c, const StepArgs& a, const PairIn& in, f2* g, const float scale, const float inv, PairOut& out) {
 	constexpr bool VF = (FEAT&F_VOLUME_FORCE)!=0u, SG = (FEAT&F_SUBGRID)!=0u;
-	f2 s[9], d[9]; // pair sums / differences, k = (i-1)/2
-#pragma unroll
-	for(int k=0; k<9; k++) { s[k] = g[2*k+1]+g[2*k+2]; d[k] = g[2*k+1]-g[2*k+2]; }
-	const f2 R = (((g[0]+s[0])+(s[1]+s[2]))+((s[3]+s[4])+(s[5]+s[6])))+(s[7]+s[8]);
-	f2 rhom1 = inv*R;
-	f2 rho = rhom1+bc(1.0f);
-	// pairs: 0:(+x) 1:(+y) 2:(+z) 3:(+x+y) 4:(+x+z) 5:(+y+z) 6:(+x-y) 7:(+x-z) 8:(+y-z)
-	const f2 mx = ((d[0]+d[3])+(d[4]+d[6]))+d[7];
-	const f2 my = ((d[1]+d[3])+(d[5]-d[6]))+d[8];
-	const f2 mz = ((d[2]+d[4])+(d[5]-d[7]))-d[8];
-	f2 ir = rcp2(rho);
-	ir = fma2(ir, fma2(-rho, ir, bc(1.0f)), ir); // one Newton step: full single precision
-	const f2 iri = inv*ir;
-	f2 ux = mx*iri, uy = my*iri, uz = mz*iri;
+	f2 rho, rhom1, ir, ux, uy, uz;
+	{ // moments from pair sums and differences
+		f2 R = g[0], mx, my, mz;
+		{ const f2 d0 = g[1]-g[2], d3 = g[7]-g[8], d4 = g[9]-g[10], d6 = g[13]-g[14], d7 = g[15]-g[16];
+		  const f2 d1 = g[3]-g[4], d5 = g[11]-g[12], d8 = g[17]-g[18], d2 = g[5]-g[6];
+		  mx = ((d0+d3)+(d4+d6))+d7; my = ((d1+d3)+(d5-d6))+d8; mz = ((d2+d4)+(d5-d7))-d8; }
+		R = ((R+(g[1]+g[2]))+((g[3]+g[4])+(g[5]+g[6])))+(((g[7]+g[8])+(g[9]+g[10]))+((g[11]+g[12])+(g[13]+g[14])))+((g[15]+g[16])+(g[17]+g[18]));
+		rhom1 = inv*R;
+		rho = rhom1+bc(1.0f);
+		ir = rcp2(rho);
+		ir = fma2(ir, fma2(-rho, ir, bc(1.0f)), ir); // one Newton step: full single precision
+		const f2 iri = inv*ir;
+		ux = mx*iri; uy = my*iri; uz = mz*iri;
+	}
 	if(in.e0||in.e1) {
 		rho = sel2(in.e0, in.e1, in.rho_e, rho); ux = sel2(in.e0, in.e1, in.ux_e, ux); uy = sel2(in.e0, in.e1, in.uy_e, uy); uz = sel2(in.e0, in.e1, in.uz_e, uz);
 		rhom1 = rho-bc(1.0f);
 		ir = rcp2(rho); ir = fma2(ir, fma2(-rho, ir, bc(1.0f)), ir);
 	}
-	f2 Fx, Fy, Fz, uF3;
+	Proj F; f2 uF3 = bc(0.0f);
 	if(VF) {
 		const f2 m2rho = -2.0f*rho;
-		Fx = fma2(m2rho, fma2(a.oy, uz, -(a.oz*uy)), bc(a.fx));
-		Fy = fma2(m2rho, fma2(a.oz, ux, -(a.ox*uz)), bc(a.fy));
-		Fz = fma2(m2rho, fma2(a.ox, uy, -(a.oy*ux)), bc(a.fz));
-		if(in.zones) zone_force2(c, in, rho, ux, uy, uz, Fx, Fy, Fz);
+		F.x = fma2(m2rho, fma2(a.oy, uz, -(a.oz*uy)), bc(a.fx));
+		F.y = fma2(m2rho, fma2(a.oz, ux, -(a.ox*uz)), bc(a.fy));
+		F.z = fma2(m2rho, fma2(a.ox, uy, -(a.oy*ux)), bc(a.fz));
+		if(in.zones) zone_force2(in, rho, ux, uy, uz, F.x, F.y, F.z);
 		const f2 rho2 = 0.5f*ir;
-		ux = clampc2(fma2(Fx, rho2, ux)); uy = clampc2(fma2(Fy, rho2, uy)); uz = clampc2(fma2(Fz, rho2, uz));
-		uF3 = -(fma2(ux, Fx, fma2(uy, Fy, uz*Fz))); // = 3*uF = -(u.F)
+		ux = clampc2(fma2(F.x, rho2, ux)); uy = clampc2(fma2(F.y, rho2, uy)); uz = clampc2(fma2(F.z, rho2, uz));
+		uF3 = -(fma2(ux, F.x, fma2(uy, F.y, uz*F.z))); // = 3*uF = -(u.F)
 	} else {
 		ux = clampc2(ux); uy = clampc2(uy); uz = clampc2(uz);
 	}
 	out.rho = rho; out.ux = ux; out.uy = uy; out.uz = uz;
 	const f2 c3 = -3.0f*fma2(ux, ux, fma2(uy, uy, uz*uz));
-	const f2 ax = 3.0f*ux, ay = 3.0f*uy, az = 3.0f*uz;
-	f2 av[9] = { ax, ay, az, ax+ay, ax+az, ay+az, ax-ay, ax-az, ay-az };
+	Proj A3; A3.x = 3.0f*ux; A3.y = 3.0f*uy; A3.z = 3.0f*uz; // a = 3 c.u
 	const f2 rs = WS*rho, re = WE*rho, r1s = (2.0f*WS)*rhom1, r1e = (2.0f*WE)*rhom1;
-	f2 e[9]; // feq pair sums
-#pragma unroll
-	for(int k=0; k<9; k++) e[k] = fma2(k<3 ? rs : re, fma2(av[k], av[k], c3), k<3 ? r1s : r1e);
 	const f2 feq0 = W0*fma2(rho, 0.5f*c3, rhom1);
 	f2 w = bc(c.w);
 	if(SG) {
-		f2 n[9];
+		f2 Hxx, Hyy, Hzz, Hxy, Hxz, Hyz;
 #pragma unroll
-		for(int k=0; k<9; k++) n[k] = fma2(s[k], inv, -e[k]);
-		const f2 Hxx = ((n[0]+n[3])+(n[4]+n[6]))+n[7];
-		const f2 Hyy = ((n[1]+n[3])+(n[5]+n[6]))+n[8];
-		const f2 Hzz = ((n[2]+n[4])+(n[5]+n[7]))+n[8];
-		const f2 Hxy = n[3]-n[6], Hxz = n[4]-n[7], Hyz = n[5]-n[8];
+		for(int k=0; k<9; k++) {
+			const f2 ak = proj(A3, k);
+			const f2 ek = fma2(k<3 ? rs : re, fma2(ak, ak, c3), k<3 ? r1s : r1e);
+			const f2 nk = fma2(g[2*k+1]+g[2*k+2], inv, -ek);
+			switch(k) {
+				case 0: Hxx = nk; break; case 1: Hyy = nk; break; case 2: Hzz = nk; break;
+				case 3: Hxx = Hxx+nk; Hyy = Hyy+nk; Hxy = nk; break;
+				case 4: Hxx = Hxx+nk; Hzz = Hzz+nk; Hxz = nk; break;
+				case 5: Hyy = Hyy+nk; Hzz = Hzz+nk; Hyz = nk; break;
+				case 6: Hxx = Hxx+nk; Hyy = Hyy+nk; Hxy = Hxy-nk; break;
+				case 7: Hxx = Hxx+nk; Hzz = Hzz+nk; Hxz = Hxz-nk; break;
+				default: Hyy = Hyy+nk; Hzz = Hzz+nk; Hyz = Hyz-nk; break;
+			}
+		}
 		const f2 Qn = fma2(Hxx, Hxx, fma2(Hyy, Hyy, Hzz*Hzz))+2.0f*fma2(Hxy, Hxy, fma2(Hxz, Hxz, Hyz*Hyz));
 		const float tau0 = __fdiv_rn(1.0f, c.w);
 		const f2 den = bc(tau0)+sqrt2(fma2(0.76421222f*sqrt2(Qn), ir, bc(__fmul_rn(tau0, tau0))));
@@ -250,43 +285,36 @@ template<uint32_t FEAT> __device__ __forceinline__ void collide_fast2(const Doma
 	}
 	const f2 omw = bc(1.0f)-w;
 	const f2 hw = (0.5f*scale)*w; // S*w/2
+	const f2 wrs = (2.0f*hw)*rs, wre = (2.0f*hw)*re; // S*w*r
+	const bool any_e = in.e0||in.e1;
+	const f2 hs = bc(0.5f*scale), srs = scale*rs, sre = scale*re;
 	if(VF) {
 		const f2 c_tau = fma2(w, -0.5f, bc(1.0f));
 		const f2 kcs = (9.0f*WS/3.0f*scale)*c_tau, kce = (9.0f*WE/3.0f*scale)*c_tau; // S*kc/3
-		const f2 Av[9] = { Fx, Fy, Fz, Fx+Fy, Fx+Fz, Fy+Fz, Fx-Fy, Fx-Fz, Fy-Fz };
-		const f2 wrs = (2.0f*hw)*rs, wre = (2.0f*hw)*re; // S*w*r
 #pragma unroll
 		for(int k=0; k<9; k++) {
-			const f2 kc = k<3 ? kcs : kce;
-			const f2 U = fma2(kc, fma2(Av[k], av[k], uF3), hw*e[k]);
-			const f2 V = fma2(k<3 ? wrs : wre, av[k], kc*Av[k]);
-			const f2 gi = g[2*k+1], gj = g[2*k+2];
-			g[2*k+1] = fma2(omw, gi, U+V);
-			g[2*k+2] = fma2(omw, gj, U-V);
+			const f2 ak = proj(A3, k), Ak = proj(F, k), kc = k<3 ? kcs : kce;
+			const f2 ek = fma2(k<3 ? rs : re, fma2(ak, ak, c3), k<3 ? r1s : r1e);
+			const f2 U = fma2(kc, fma2(Ak, ak, uF3), hw*ek);
+			const f2 V = fma2(k<3 ? wrs : wre, ak, kc*Ak);
+			f2 gi = fma2(omw, g[2*k+1], U+V), gj = fma2(omw, g[2*k+2], U-V);
+			if(any_e) { const f2 Ue = hs*ek, Ve = (k<3 ? srs : sre)*ak; gi = sel2(in.e0, in.e1, Ue+Ve, gi); gj = sel2(in.e0, in.e1, Ue-Ve, gj); } // TYPE_E: f := feq (FX/kernel.cpp:1747)
+			g[2*k+1] = gi; g[2*k+2] = gj;
 		}
 		g[0] = fma2(omw, g[0], fma2(2.0f*hw, feq0, ((9.0f*W0/3.0f*scale)*c_tau)*uF3));
 	} else {
-		const f2 wrs = (2.0f*hw)*rs, wre = (2.0f*hw)*re;
 #pragma unroll
 		for(int k=0; k<9; k++) {
-			const f2 U = hw*e[k];
-			const f2 V = (k<3 ? wrs : wre)*av[k];
-			const f2 gi = g[2*k+1], gj = g[2*k+2];
-			g[2*k+1] = fma2(omw, gi, U+V);
-			g[2*k+2] = fma2(omw, gj, U-V);
+			const f2 ak = proj(A3, k);
+			const f2 ek = fma2(k<3 ? rs : re, fma2(ak, ak, c3), k<3 ? r1s : r1e);
+			const f2 U = hw*ek, V = (k<3 ? wrs : wre)*ak;
+			f2 gi = fma2(omw, g[2*k+1], U+V), gj = fma2(omw, g[2*k+2], U-V);
+			if(any_e) { const f2 Ue = hs*ek, Ve = (k<3 ? srs : sre)*ak; gi = sel2(in.e0, in.e1, Ue+Ve, gi); gj = sel2(in.e0, in.e1, Ue-Ve, gj); }
+			g[2*k+1] = gi; g[2*k+2] = gj;
 		}
 		g[0] = fma2(omw, g[0], (2.0f*hw)*feq0);
 	}
-	if(in.e0||in.e1) { // TYPE_E: f := feq (FX/kernel.cpp:1747)
-		const f2 hs = bc(0.5f*scale);
-#pragma unroll
-		for(int k=0; k<9; k++) {
-			const f2 U = hs*e[k], V = (scale*(k<3 ? rs : re))*av[k];
-			g[2*k+1] = sel2(in.e0, in.e1, U+V, g[2*k+1]);
-			g[2*k+2] = sel2(in.e0, in.e1, U-V, g[2*k+2]);
-		}
-		g[0] = sel2(in.e0, in.e1, scale*feq0, g[0]);
-	}
+	if(any_e) g[0] = sel2(in.e0, in.e1, scale*feq0, g[0]);
 }
 
 } // anonymous namespace

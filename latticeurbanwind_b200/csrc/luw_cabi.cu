@@ -111,7 +111,8 @@ void setup_tiles(luw_domain* d) {
 	d->tiled = true;
 }
 cudaError_t enqueue_step(luw_domain* d, const luw::StepArgs& a) {
-	if(d->tiled) return d->ks->stream_collide_tile(d->c, a, d->maps, d->tile_variant, d->sm_count, d->stream);
+	if(d->tiled) { d->launches += d->c.Dx==1u ? 2ull : 1ull; return d->ks->stream_collide_tile(d->c, a, d->maps, d->tile_variant, d->sm_count, d->stream); } // tile kernel (+ x-column kernel)
+	d->launches++;
 	return d->ks->stream_collide(d->c, a, d->stream);
 }
 
@@ -290,7 +291,6 @@ int luw_stream_collide(luw_domain* d, uint64_t t, float fx, float fy, float fz, 
 	DeviceGuard guard(d->p.device);
 	const luw::StepArgs a = { t, fx, fy, fz, ox, oy, oz };
 	CU(enqueue_step(d, a));
-	d->launches++;
 	return LUW_OK;
 }
 int luw_update_fields(luw_domain* d, uint64_t t, float fx, float fy, float fz, float ox, float oy, float oz) {
@@ -308,7 +308,6 @@ int luw_run_steps(luw_domain* d, uint64_t t0, uint64_t k, float fx, float fy, fl
 	for(uint64_t s=0ull; s<k; s++) {
 		const luw::StepArgs a = { t0+s, fx, fy, fz, ox, oy, oz };
 		CU(enqueue_step(d, a));
-		d->launches++;
 	}
 	return LUW_OK;
 }

@@ -1,0 +1,299 @@
+"""Host-side mirror of the reference's `LBM` object (FX/lbm.hpp:223-633, FX/lbm.cpp:1057-1312) over the C ABI.
+
+    lbm = LBM((Nx, Ny, Nz), D=(Dx, Dy, Dz), nu=..., precision=..., features=...)
+    lbm.flags[...] / lbm.u[...] / lbm.rho[...]      global host images, reference layout n = x + (y + z*Ny)*Nx, u = [ux | uy | uz]
+    lbm.run(steps)                                   first call initialises (upload + `initialize` kernel + halo fill), then steps
+    lbm.read_from_device()                           device -> global host images
+
+Two drivers share the domain split and the step sequence of the reference (`do_time_step`: stream_collide on every domain, then
+`communicate_fi` axis by axis x -> y -> z):
+  * LBM             one process owns all Dx*Dy*Dz domains (any mix of devices; several domains may share one GPU, which is how
+                    decomposed runs are tested on a single B200). Halo payloads move device-to-device.
+  * DistributedLBM  one process per GPU (torch.distributed, NCCL): each rank owns ONE domain; halo payloads move with batched
+                    isend/irecv over NVLink. This replaces the host-staged exchange of FX/lbm.cpp:1907-1935.
+torch is used for device buffers, streams and the process group only; all LBM work is in the CUDA library behind the C ABI.
+"""
+import numpy as np
+
+from . import _cabi as A
+from . import cases
+from .domain import Domain
+
+AXES = (0, 1, 2)
+
+
+def split(shape, D):
+    """Domain split of FX/lbm.cpp:1057-1073: global N rounded down to multiples of D, local N/D + 2 halo layers on decomposed axes,
+    offset O = d*N/D - H. Returns (global shape, local shape, list of (d, O))."""
+    D = tuple(int(v) for v in D)
+    Ng = tuple((int(n) // d) * d for n, d in zip(shape, D))
+    H = tuple(1 if d > 1 else 0 for d in D)
+    Nl = tuple(n // d + 2 * h for n, d, h in zip(Ng, D, H))
+    doms = []
+    for dz in range(D[2]):
+        for dy in range(D[1]):
+            for dx in range(D[0]):
+                d = (dx, dy, dz)
+                doms.append((d, tuple(d[a] * (Ng[a] // D[a]) - H[a] for a in AXES)))
+    return Ng, Nl, doms
+
+
+def _local_index(Ng, Nl, O):
+    """Global linear indices of every local cell (periodic at the global edges), the stitching of FX/lbm.hpp:274-297."""
+    idx = [np.mod(np.arange(Nl[a]) + O[a], Ng[a]) for a in AXES]
+    g = idx[0][None, None, :] + Ng[0] * (idx[1][None, :, None] + Ng[1] * idx[2][:, None, None])
+    return g.reshape(-1)
+
+
+class _Base:
+    def __init__(self, shape, D=(1, 1, 1), nu=1.0 / 6.0, precision=A.FP32, features=A.UPDATE_FIELDS, arith=A.ARITH_FAST,
+                 f=(0.0, 0.0, 0.0), omega=(0.0, 0.0, 0.0), w=None, **zones):
+        self.D = tuple(int(v) for v in D)
+        self.Ng, self.Nl, self._split = split(shape, self.D)
+        self.N = int(np.prod(self.Ng))
+        self.precision, self.features, self.arith = precision, features, arith
+        self.w = cases.relaxation_rate(nu) if w is None else w
+        self.f, self.omega = tuple(f), tuple(omega)
+        self.zones = zones
+        self.t = 0
+        self.initialized = False
+
+    def _make_domain(self, d, O, device):
+        dom = Domain(*self.Nl, D=self.D, O=O, precision=self.precision, features=self.features, w=self.w, arith=self.arith,
+                     device=device, **self.zones)
+        dom.f, dom.omega = self.f, self.omega
+        return dom
+
+    def set_coriolis(self, ox, oy, oz):  # FX/lbm.hpp:496-498
+        self.omega = (ox, oy, oz)
+        for dom in self.domains:
+            dom.omega = self.omega
+
+    def get_N(self):
+        return self.N
+
+    def get_t(self):
+        return self.t
+
+
+class LBM(_Base):
+    """All domains in one process (reference: `LBM` with `lbm_domain[d]`, FX/lbm.hpp:426)."""
+
+    def __init__(self, shape, D=(1, 1, 1), devices=None, **kw):
+        super().__init__(shape, D, **kw)
+        import torch  # device buffers for the halo payloads
+        self._torch = torch
+        ndev = max(A.device_count(), 1)
+        self.devices = list(devices) if devices is not None else [i % ndev for i in range(len(self._split))]
+        self.domains = [self._make_domain(d, O, dev) for (d, O), dev in zip(self._split, self.devices)]
+        self.rho = np.ones(self.N, np.float32)
+        self.u = np.zeros(3 * self.N, np.float32)
+        self.flags = np.zeros(self.N, np.uint8)
+        self._gidx = [_local_index(self.Ng, self.Nl, O) for _, O in self._split]
+        self._bufs = {}
+
+    # ---- host <-> device (Memory_Container::write_to_device / read_from_device, FX/lbm.hpp:406-423)
+    def write_to_device(self):
+        for dom, g in zip(self.domains, self._gidx):
+            dom.rho[:] = self.rho[g]
+            dom.flags[:] = self.flags[g]
+            for c in range(3):
+                dom.u[c * dom.N:(c + 1) * dom.N] = self.u[c * self.N + g]
+            dom.upload_all()
+
+    def read_from_device(self):
+        H = tuple(1 if d > 1 else 0 for d in self.D)
+        for dom, g in zip(self.domains, self._gidx):
+            dom.download_all()
+            keep = np.ones(self.Nl[::-1], bool)
+            if H[0]: keep[:, :, 0] = keep[:, :, -1] = False
+            if H[1]: keep[:, 0, :] = keep[:, -1, :] = False
+            if H[2]: keep[0, :, :] = keep[-1, :, :] = False
+            k = keep.reshape(-1)
+            self.rho[g[k]] = dom.rho[k]
+            self.flags[g[k]] = dom.flags[k]
+            for c in range(3):
+                self.u[c * self.N + g[k]] = dom.u[c * dom.N:(c + 1) * dom.N][k]
+
+    # ---- halo exchange (FX/lbm.cpp:1895-1958)
+    def _buffers(self, i, payload, axis):
+        key = (i, payload, axis)
+        if key not in self._bufs:
+            torch = self._torch
+            n = self.domains[i].halo_bytes(payload, axis)
+            dev = torch.device("cuda", self.devices[i])
+            self._bufs[key] = tuple(torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(4))  # send_p, send_m, recv_p, recv_m
+        return self._bufs[key]
+
+    def _neighbour(self, i, axis, step):
+        d = list(self._split[i][0])
+        d[axis] = (d[axis] + step) % self.D[axis]
+        return d[0] + self.D[0] * (d[1] + self.D[1] * d[2])
+
+    def communicate(self, payload):
+        for axis in AXES:
+            if self.D[axis] < 2:
+                continue
+            for i, dom in enumerate(self.domains):
+                sp, sm, _, _ = self._buffers(i, payload, axis)
+                dom.halo_extract(payload, axis, sp.data_ptr(), sm.data_ptr())
+            for dom in self.domains:
+                dom.finish_queue()
+            for i in range(len(self.domains)):  # what left through + arrives in the - halo of the +neighbour, and vice versa
+                sp, sm, _, _ = self._buffers(i, payload, axis)
+                self._buffers(self._neighbour(i, axis, +1), payload, axis)[3].copy_(sp)
+                self._buffers(self._neighbour(i, axis, -1), payload, axis)[2].copy_(sm)
+            self._torch.cuda.synchronize()
+            for i, dom in enumerate(self.domains):
+                _, _, rp, rm = self._buffers(i, payload, axis)
+                dom.halo_insert(payload, axis, rp.data_ptr(), rm.data_ptr())
+
+    # ---- LBM::initialize / do_time_step / run (FX/lbm.cpp:1221-1312)
+    def initialize(self):
+        self.write_to_device()
+        for dom in self.domains:
+            dom.t = 1
+        self.communicate(A.HALO_RHO_U_FLAGS)
+        for dom in self.domains:
+            dom.enqueue_initialize()
+        self.communicate(A.HALO_RHO_U_FLAGS)
+        self.communicate(A.HALO_FI)
+        for dom in self.domains:
+            dom.finish_queue()
+            dom.t = 0
+        self.t = 0
+        self.initialized = True
+
+    def do_time_step(self):
+        for dom in self.domains:
+            dom.f, dom.omega = self.f, self.omega
+            dom.enqueue_stream_collide()
+        self.communicate(A.HALO_FI)
+        for dom in self.domains:
+            dom.increment_time_step()
+        self.t += 1
+
+    def run(self, steps=1):
+        if not self.initialized:
+            self.initialize()
+        if len(self.domains) == 1:
+            dom = self.domains[0]
+            dom.f, dom.omega = self.f, self.omega
+            dom.run_steps(steps)
+            self.t += steps
+        else:
+            for _ in range(steps):
+                self.do_time_step()
+        for dom in self.domains:
+            dom.finish_queue()
+
+    def update_fields(self):
+        for dom in self.domains:
+            dom.enqueue_update_fields()
+
+    def close(self):
+        for dom in self.domains:
+            dom.close()
+
+
+class DistributedLBM(_Base):
+    """One domain per rank (torch.distributed); rank r owns domain r of the split. Works with NCCL (GPU) and, for the host logic, with
+    gloo: `cpu_engine` then stands in for the device (tests only -- the product path has no CPU fallback)."""
+
+    def __init__(self, shape, D, group=None, device=0, cpu_engine=None, **kw):
+        super().__init__(shape, D, **kw)
+        import torch
+        import torch.distributed as dist
+        self._torch, self._dist = torch, dist
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        assert self.world == len(self._split), "one rank per domain"
+        self.d, self.O = self._split[self.rank]
+        self.cpu_engine = cpu_engine
+        self.device = device
+        self.gidx = _local_index(self.Ng, self.Nl, self.O)
+        if cpu_engine is None:
+            self.domain = self._make_domain(self.d, self.O, device)
+            self.domains = [self.domain]
+            self._stream = torch.cuda.current_stream(device)
+            self.domain.set_stream(self._stream.cuda_stream)  # one stream orders kernels, copies and the NCCL calls
+        else:
+            self.domain, self.domains = None, []
+        self._bufs = {}
+
+    def rank_of(self, axis, step):
+        d = list(self.d)
+        d[axis] = (d[axis] + step) % self.D[axis]
+        return d[0] + self.D[0] * (d[1] + self.D[1] * d[2])
+
+    def halo_bytes(self, payload, axis):
+        A_ = (self.Nl[1] * self.Nl[2], self.Nl[2] * self.Nl[0], self.Nl[0] * self.Nl[1])[axis]
+        per = 17 if payload == A.HALO_RHO_U_FLAGS else 5 * (4 if self.precision == A.FP32 else 2)
+        return per * A_
+
+    def _buffers(self, payload, axis):
+        key = (payload, axis)
+        if key not in self._bufs:
+            torch = self._torch
+            dev = torch.device("cpu") if self.cpu_engine is not None else torch.device("cuda", self.device)
+            self._bufs[key] = tuple(torch.empty(self.halo_bytes(payload, axis), dtype=torch.uint8, device=dev) for _ in range(4))
+        return self._bufs[key]
+
+    def exchange(self, axis, sp, sm, rp, rm):
+        """send_p -> (+) neighbour's recv_m, send_m -> (-) neighbour's recv_p. With 2 ranks on an axis both neighbours are the same rank."""
+        dist = self._dist
+        up, dn = self.rank_of(axis, +1), self.rank_of(axis, -1)
+        if up == self.rank:  # a single domain on this axis never gets here; kept for completeness
+            rm.copy_(sp); rp.copy_(sm)
+            return
+        ops = [dist.P2POp(dist.isend, sp, up, self.group, tag=2 * axis), dist.P2POp(dist.isend, sm, dn, self.group, tag=2 * axis + 1),
+               dist.P2POp(dist.irecv, rm, dn, self.group, tag=2 * axis), dist.P2POp(dist.irecv, rp, up, self.group, tag=2 * axis + 1)]
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+
+    def communicate(self, payload, extract, insert):
+        for axis in AXES:
+            if self.D[axis] < 2:
+                continue
+            sp, sm, rp, rm = self._buffers(payload, axis)
+            extract(payload, axis, sp, sm)
+            self.exchange(axis, sp, sm, rp, rm)
+            insert(payload, axis, rp, rm)
+
+    # device-side callbacks
+    def _extract(self, payload, axis, sp, sm):
+        self.domain.halo_extract(payload, axis, sp.data_ptr(), sm.data_ptr())
+
+    def _insert(self, payload, axis, rp, rm):
+        self.domain.halo_insert(payload, axis, rp.data_ptr(), rm.data_ptr())
+
+    def initialize(self, flags, rho, u):
+        """flags / rho / u: LOCAL host images of this rank's domain (halo layers included)."""
+        dom = self.domain
+        dom.rho[:], dom.u[:], dom.flags[:] = rho, u, flags
+        dom.f, dom.omega = self.f, self.omega
+        dom.upload_all()
+        dom.t = 1
+        self.communicate(A.HALO_RHO_U_FLAGS, self._extract, self._insert)
+        dom.enqueue_initialize()
+        self.communicate(A.HALO_RHO_U_FLAGS, self._extract, self._insert)
+        self.communicate(A.HALO_FI, self._extract, self._insert)
+        dom.finish_queue()
+        dom.t = 0
+        self.t = 0
+        self.initialized = True
+
+    def do_time_step(self):
+        dom = self.domain
+        dom.enqueue_stream_collide()
+        self.communicate(A.HALO_FI, self._extract, self._insert)
+        dom.increment_time_step()
+        self.t += 1
+
+    def run(self, steps=1):
+        for _ in range(steps):
+            self.do_time_step()
+
+    def close(self):
+        if self.domain is not None:
+            self.domain.close()

@@ -127,3 +127,24 @@ def test_tiled_fast_within_tolerance(oracle_lib, precision, fset):
     assert H.rel_l2(got[2], ref[2]) <= tol["rel_l2_u"]
     assert float(np.abs(got[2] - ref[2]).max()) <= tol["max_abs_u"]
     assert H.rel_l2(got[1], ref[1]) <= tol["rel_l2_rho"]
+
+
+# ---------------------------------------------------------------------------------------------- decomposed runs (several domains on ONE GPU)
+@pytest.mark.parametrize("D,arith", [((2, 2, 2), 0), ((1, 2, 2), 0), ((1, 2, 2), 1), ((1, 1, 4), 1)], ids=["2x2x2-strict", "1x2x2-strict", "1x2x2-fast", "1x1x4-fast"])
+@pytest.mark.parametrize("precision", [0, 1], ids=["fp32", "fp16s"])
+def test_decomposed_equals_single_domain(D, arith, precision):
+    """D domains with halo exchange reproduce the single-domain run bit for bit (same kernels on both sides of the comparison)."""
+    from latticeurbanwind_b200.lbm import LBM
+    shape = (128, 24, 16)
+    flags, rho, u = cases.urban(*shape, seed=21, edge=4, pitch=8)
+    zones = dict(downstream_face=2, buffer_N=3, buffer_inv_tau=0.01, buffer_nudge_vertical=1, sponge_N=3, sponge_inv_tau=0.02)
+    res = []
+    for dd in ((1, 1, 1), D):
+        lbm = LBM(shape, D=dd, nu=1e-6, precision=precision, features=H.FEATURE_SETS["luw"], arith=arith, f=H.FORCE, omega=H.OMEGA, **zones)
+        lbm.flags[:], lbm.rho[:], lbm.u[:] = flags, rho, u
+        lbm.run(7)
+        lbm.read_from_device()
+        res.append((lbm.rho.copy(), lbm.u.copy()))
+        lbm.close()
+    assert np.array_equal(res[0][0], res[1][0]), "rho differs between D=1 and the decomposed run"
+    assert np.array_equal(res[0][1], res[1][1]), "u differs between D=1 and the decomposed run"
