@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Benchmark of the LBM time step (BASELINE.json metric: D3Q19 MLUP/s at 1/2/4/8 B200 and % of the HBM-bandwidth roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+One "step" = one LBM time step (stream_collide on every cell of the lattice, plus the halo exchange when N > 1).
+MLUP/s = cells of the GLOBAL lattice (solids included, halo layers excluded) x steps / seconds / 1e6, the reference's own definition
+(FX/info.cpp:66, FX/lbm.cpp:1393).
+
+Workloads (BASELINE.json configs; the per-GPU block is fixed -> weak scaling):
+  channel512_fp16s   configs[1]: empty channel 512^3, TYPE_E on the x faces, TYPE_S walls, FP16S DDFs, nu = 1/6      (default)
+  channel512_fp32    configs[1], FP32 DDFs
+  urban_fp16s        configs[2]: staggered cube array 1024x1024x256, TYPE_E inflow, bounce-back cubes, Coriolis, nudging, sponge, Smagorinsky, FP16S
+  urban_fp16s_uf     the same with UPDATE_FIELDS (rho/u stored every step, +16 B/cell), LUW's shipped semantics
+N > 1 (torchrun, one rank per GPU): the lattice is decomposed like the reference's published multi-GPU runs (2x1x1, 2x2x1, 2x2x2); every rank owns
+one block of the same local size (halo layers included), halo DDFs move over NVLink.
+
+The JSON line carries, besides the contract keys: `roofline` (dominant kernel, algorithmic bytes per launch / CUDA-event duration against
+MEASURED_PEAKS.json), `cpu_baseline` (the reference's kernel text compiled for host threads -- oracle/_ref -- or the C oracle, on a bounded sample),
+`e2e` (the same steps driven through the host API one step at a time, each with a pinned-memory upload of that step's inflow boundary field
+and a read-back of a probe plane), `clocks`, `gpu_launches`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+F_UF, F_VF, F_EQ, F_SG, F_NUDGE, F_SPONGE = 1, 2, 4, 8, 16, 32
+WORKLOADS = {
+    # name: (case, local block shape incl. halos, precision, features, oracle feature-set name, nu, description)
+    "channel512_fp16s": ("channel", (512, 512, 512), 1, F_EQ, "chan", 1.0 / 6.0, "C2 empty channel 512^3 FP16S (TYPE_E x faces, TYPE_S walls), SRT nu=1/6"),
+    "channel512_fp32": ("channel", (512, 512, 512), 0, F_EQ, "chan", 1.0 / 6.0, "C2 empty channel 512^3 FP32 (TYPE_E x faces, TYPE_S walls), SRT nu=1/6"),
+    "urban_fp16s": ("urban", (1024, 1024, 256), 1, F_VF | F_EQ | F_SG | F_NUDGE | F_SPONGE, "luwnf", 1e-6,
+                    "C3 staggered cube array 1024x1024x256 FP16S, TYPE_E inflow, bounce-back, Coriolis, nudging N=16, sponge N=20, Smagorinsky; rho/u on demand"),
+    "urban_fp16s_uf": ("urban", (1024, 1024, 256), 1, F_UF | F_VF | F_EQ | F_SG | F_NUDGE | F_SPONGE, "luw", 1e-6,
+                       "C3 staggered cube array 1024x1024x256 FP16S, full LUW step with UPDATE_FIELDS (+16 B/cell rho/u stores)"),
+}
+ZONES = dict(downstream_face=2, buffer_N=16, buffer_inv_tau=0.01, buffer_nudge_vertical=1, sponge_N=20, sponge_inv_tau=0.02)
+OMEGA = (0.0, 5.6e-6, 4.7e-6)  # Omega_lbm of SURVEY.md 8d (7.292e-5 * (cos 40, sin 40) * dt)
+B_ALG = {0: 153, 1: 77, 2: 77}  # algorithmic bytes per cell-step: 19 DDF loads + 19 stores + 1 flag byte (FX/lbm.cpp:121-122)
+DTYPE = {0: "f32 arithmetic, f32 DDF storage", 1: "f32 arithmetic, FP16S DDF storage", 2: "f32 arithmetic, FP16C DDF storage"}
+DECOMP = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}  # the reference's published multi-GPU layouts (FluidX3D README)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        try:
+            for line in open(self.path):
+                c = [v.strip() for v in line.split(",")]
+                if len(c) < 8:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------------- CPU arms
+def cpu_engine(precision, fset):
+    """The CPU implementation timed beside the GPU: the reference's own kernel text built for host threads if oracle/_ref travelled, else our C port."""
+    from oracle import oracle as O
+    if O.ref_available(precision, fset):
+        return O, O.Reference(precision, fset), "reference"
+    return O, O.Oracle(), "port"
+
+
+def cpu_run(workload, steps, warmup, budget_s=20.0):
+    """Time `steps` stream_collide calls of the workload's step on a bounded sample: an x-y-complete slab of the same case, Nz cut so that one
+    step takes a fraction of a second. Returns (MLUP/s, cores, kind, sample description, ms per step)."""
+    case, shape, precision, features, fset, nu, _ = WORKLOADS[workload]
+    from latticeurbanwind_b200 import cases
+    O, eng, kind = cpu_engine(precision, fset)
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    Nx, Ny = min(shape[0], 512), min(shape[1], 512)
+    Nz = 64 if case == "urban" else 32  # urban: keeps ground, cubes (<= 48 cells high), the nudging shell and the sponge in the sample
+    Ng = (Nx, Ny, Nz)
+    flags, rho, u = cases.block_case(case, Ng)
+    zones = ZONES if features & (F_NUDGE | F_SPONGE) else {}
+    p = O.make_params(Nx, Ny, Nz, precision, features, w=cases.relaxation_rate(nu), **zones)
+    fi = np.zeros(19 * p.N, O.ddf_dtype(precision))
+    eng.bind(p)
+    eng.initialize(fi, rho, u, flags)
+    t = 0
+    t0 = time.perf_counter()
+    eng.stream_collide(fi, rho, u, flags, t, (0, 0, 0), OMEGA); t += 1
+    one = time.perf_counter() - t0
+    steps = max(1, min(steps, int(budget_s / max(one, 1e-3))))
+    for _ in range(max(0, min(warmup, 2))):
+        eng.stream_collide(fi, rho, u, flags, t, (0, 0, 0), OMEGA); t += 1
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        eng.stream_collide(fi, rho, u, flags, t, (0, 0, 0), OMEGA); t += 1
+    dt = time.perf_counter() - t0
+    mlups = p.N * steps / dt / 1e6
+    sample = f"{Nx}x{Ny}x{Nz} block of the workload's case ({p.N / 1e6:.1f} M cells), {steps} steps, OpenMP over z-planes on {cores} host threads"
+    return mlups, cores, kind, sample, dt / steps * 1e3, steps
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    case, shape, precision, features, fset, nu, desc = WORKLOADS[args.workload]
+    mlups, cores, kind, sample, ms, steps = cpu_run(args.workload, args.steps, args.warmup, budget_s=60.0)
+    line = {"impl": "reference", "metric": "D3Q19 MLUP/s", "value": mlups, "unit": "MLUP/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[precision], "data": "synthetic",
+            "config": {"workload": desc, "name": args.workload, "features": features},
+            "cpu_baseline": {"value": mlups, "unit": "MLUP/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": mlups, "unit": "MLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference stream_collide (FX/kernel.cpp text compiled for host threads through oracle/ref_shim) on the box's CPU cores; "
+                    "the reference's OpenCL runtime itself needs an OpenCL platform, absent from this image" if kind == "reference" else
+                    "CPU restatement of FX/kernel.cpp (oracle/luw_oracle.c) on the box's CPU cores"}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--workload", default=os.environ.get("LUW_BENCH_WORKLOAD", "channel512_fp16s"), choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--arith", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--also", default="", help="comma-separated extra workloads measured after the headline one (N=1) and reported under `also`")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    from latticeurbanwind_b200 import _cabi as A, cases
+    from latticeurbanwind_b200.domain import Domain, CellSet, pinned_empty
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 bench.py --gpus N ...")
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if A.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the LBM step has no CPU fallback (use --impl reference for the CPU arm)")
+    arith = A.ARITH_FAST if args.arith == "fast" else A.ARITH_STRICT
+    peak, peak_src = measured_peaks()
+
+    if world == 1:
+        res = bench_single(args, args.workload, arith, A, cases, Domain, CellSet, pinned_empty, peak, peak_src, headline=True)
+        also = []
+        for name in [w for w in args.also.split(",") if w]:
+            r = bench_single(args, name, arith, A, cases, Domain, CellSet, pinned_empty, peak, peak_src, headline=False)
+            also.append({k: r[k] for k in ("config", "value", "unit", "ms_per_step", "dtype", "roofline", "e2e", "gpu_launches")})
+        if also:
+            res["also"] = also
+        print(json.dumps(res), flush=True)
+        return 0
+    return bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src)
+
+
+def build_domain(Domain, cases, workload, arith, device, D=(1, 1, 1), O=(0, 0, 0), Ng=None, pinned=None):
+    case, shape, precision, features, fset, nu, desc = WORKLOADS[workload]
+    zones = ZONES if features & (F_NUDGE | F_SPONGE) else {}
+    d = Domain(*shape, D=D, O=O, precision=precision, features=features, w=cases.relaxation_rate(nu), arith=arith, device=device, **zones)
+    if pinned is not None:  # host mirrors in page-locked memory
+        d.flags, d.rho, d.u = pinned(d.N, np.uint8), pinned(d.N, np.float32), pinned(3 * d.N, np.float32)
+    cases.block_case(case, shape if Ng is None else Ng, O, shape, out=(d.flags, d.rho, d.u))
+    d.omega = OMEGA if features & F_VF else (0.0, 0.0, 0.0)
+    return d
+
+
+def bench_single(args, workload, arith, A, cases, Domain, CellSet, pinned_empty, peak, peak_src, headline):
+    case, shape, precision, features, fset, nu, desc = WORKLOADS[workload]
+    Nx, Ny, Nz = shape
+    N = Nx * Ny * Nz
+    K, W = args.steps, args.warmup
+    d = build_domain(Domain, cases, workload, arith, 0, pinned=pinned_empty)
+    try:
+        # ---- whole job through the host API: upload of the host images, initialize, K steps, read-back of rho/u (reported as e2e.job)
+        t0 = time.perf_counter()
+        d.upload_all(); d.t = 1; d.enqueue_initialize(); d.t = 0
+        d.finish_queue()
+        t_up = time.perf_counter() - t0
+        d.run_steps(W); d.finish_queue()
+        # ---- value: K steps, state resident in HBM, CUDA events on the domain's stream
+        clk = ClockSampler(0); clk.start()
+        launches0 = d.launch_count()
+        d.timer_begin(); d.run_steps(K); ms = d.timer_end()
+        launches = d.launch_count() - launches0
+        # ---- roofline pass: the same K steps with an event pair around every main-kernel launch
+        d.kernel_timing(True); d.run_steps(K); kms, kn = d.kernel_timing_read(); d.kernel_timing(False)
+        clocks = clk.stop()
+        mlups = N * K / ms / 1e3
+        kern_ms = kms / max(kn, 1)
+        achieved = N * B_ALG[precision] / (kern_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "k_stream_collide_tile" if d.uses_tiles() else "k_stream_collide", "kernel_ms": kern_ms, "share_of_step": kern_ms / (ms / K),
+                "alg_bytes_per_cell": B_ALG[precision], "cells_per_launch": N, "peak_source": peak_src,
+                "frac_of_8000_datasheet": achieved / 8000.0}
+        traffic = os.path.join(ROOT, "profiles", f"traffic_{workload}.json")
+        if os.path.isfile(traffic):  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+            try:
+                roof["traffic"] = json.load(open(traffic))["dram_bytes_per_launch"]
+            except Exception:
+                pass
+        res = {"metric": "D3Q19 MLUP/s", "value": mlups, "unit": "MLUP/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[precision], "data": "synthetic",
+               "config": {"workload": desc, "name": workload, "lattice": list(shape), "features": features, "arith": args.arith, "decomposition": [1, 1, 1],
+                          "l2": "state (DDFs %.1f GB) is far larger than the 126 MB L2; no flush needed" % (19 * N * (4 if precision == 0 else 2) / 1e9)},
+               "roofline": roof, "clocks": clocks, "gpu_launches": int(launches)}
+        published = {"channel512_fp16s": 55609.0, "channel512_fp32": 42152.0}.get(workload)
+        if published:  # FluidX3D's own B200 number for this protocol (OpenCL) -- context, the driver computes its own ratios
+            res["config"]["published_reference_b200_mlups"] = published
+        # ---- e2e: one host-API call per step, with that step's boundary field going up and a probe plane coming back
+        if not args.no_e2e:
+            res["e2e"] = e2e_steps(d, CellSet, pinned_empty, A, shape, min(K, 100), t_up, N)
+        if headline and not args.no_cpu:
+            c_mlups, cores, kind, sample, c_ms, c_steps = cpu_run(workload, 8, 1, budget_s=15.0)
+            res["cpu_baseline"] = {"value": c_mlups, "unit": "MLUP/s", "cores": cores, "kind": kind, "sample": sample}
+        return res
+    finally:
+        d.close()
+
+
+def e2e_steps(d, CellSet, pinned_empty, A, shape, K, t_upload_init, N):
+    """Every step: H2D of the inflow face's velocity (pinned -> device, scattered into u of the TYPE_E cells of the x=0 face), one time step
+    through the same call the host layer makes (luw_stream_collide), D2H of rho/u on the outflow-side probe plane x = Nx-2, then finish_queue
+    -- the reference's D==1 loop also synchronises every step (FX/lbm.cpp:1288)."""
+    Nx, Ny, Nz = shape
+    yz = (np.arange(Ny, dtype=np.uint64)[None, :] + np.arange(Nz, dtype=np.uint64)[:, None] * np.uint64(Ny)).reshape(-1) * np.uint64(Nx)
+    inlet = yz[d.flags[yz.astype(np.int64)] == 2]  # TYPE_E cells of the x = 0 face
+    probe = yz + np.uint64(Nx - 2)
+    cin, cpr = CellSet(d, inlet), CellSet(d, probe)
+    uin = pinned_empty(3 * cin.count, np.float32)
+    for c in range(3):
+        uin[c * cin.count:(c + 1) * cin.count] = d.u[c * d.N + inlet.astype(np.int64)]
+    upr, rpr = pinned_empty(3 * cpr.count, np.float32), pinned_empty(cpr.count, np.float32)
+    def step():
+        cin.upload(A.FIELD_U, uin)
+        d.enqueue_stream_collide(); d.increment_time_step()
+        cpr.download(A.FIELD_U, upr); cpr.download(A.FIELD_RHO, rpr)
+        d.finish_queue()
+    for _ in range(3):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step()
+    dt = time.perf_counter() - t0
+    # whole job: upload + initialize (measured above) + K steps + full rho/u read-back
+    t1 = time.perf_counter()
+    d.read_from_device(A.FIELD_RHO); d.read_from_device(A.FIELD_U); d.finish_queue()
+    t_down = time.perf_counter() - t1
+    out = {"value": N * K / dt / 1e6, "unit": "MLUP/s", "h2d_bytes_per_step": int(uin.nbytes), "d2h_bytes_per_step": int(upr.nbytes + rpr.nbytes),
+           "steps": K, "ms_per_step": dt / K * 1e3, "timer": "host wall clock around K x (upload, step, read-back, sync)",
+           "probe_mean_ux": float(upr[:cpr.count].mean()),
+           "job": {"upload_init_s": t_upload_init, "h2d_bytes": int(17 * N), "readback_s": t_down, "d2h_bytes": int(16 * N),
+                   "note": "one-off per case: full rho/u/flags images up (17 B/cell, pinned), rho/u down (16 B/cell)"}}
+    cin.close(); cpr.close()
+    return out
+
+
+def bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src):
+    import torch
+    import torch.distributed as dist
+    from latticeurbanwind_b200.lbm import DistributedLBM
+    case, shape, precision, features, fset, nu, desc = WORKLOADS[args.workload]
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    D = DECOMP[world]
+    H = tuple(1 if v > 1 else 0 for v in D)
+    Ng = tuple((n - 2 * h) * v for n, h, v in zip(shape, H, D))  # global lattice whose blocks have exactly the workload's local size incl. halos
+    zones = ZONES if features & (F_NUDGE | F_SPONGE) else {}
+    lbm = DistributedLBM(Ng, D, device=local, nu=nu, precision=precision, features=features, arith=arith,
+                         omega=OMEGA if features & F_VF else (0.0, 0.0, 0.0), **zones)
+    assert tuple(lbm.Nl) == tuple(shape)
+    flags, rho, u = cases.block_case(case, Ng, lbm.O, shape)
+    lbm.initialize(flags, rho, u)
+    K, W = args.steps, args.warmup
+    lbm.run(W)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start()
+    launches0 = lbm.domain.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); lbm.run(K); e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.barrier(); torch.cuda.synchronize()
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = lbm.domain.launch_count() - launches0
+    # roofline pass for the step kernel of this rank
+    lbm.domain.kernel_timing(True); lbm.run(K); kms, kn = lbm.domain.kernel_timing_read(); lbm.domain.kernel_timing(False)
+    kern = torch.tensor([kms / max(kn, 1)], device="cuda")
+    dist.all_reduce(kern, op=dist.ReduceOp.MAX)
+    clocks = clk.stop() if rank == 0 else None
+    if rank == 0:
+        ms, kern_ms = float(ms.item()), float(kern.item())
+        Nglob = int(np.prod(Ng))
+        Nloc = int(np.prod(shape))
+        mlups = Nglob * K / ms / 1e3
+        achieved = Nloc * B_ALG[precision] / (kern_ms * 1e-3) / 1e9
+        halo_bytes = sum(2 * lbm.halo_bytes(A.HALO_FI, a) for a in range(3) if D[a] > 1)
+        res = {"metric": "D3Q19 MLUP/s", "value": mlups, "unit": "MLUP/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[precision], "data": "synthetic",
+               "config": {"workload": desc, "name": args.workload, "lattice": list(Ng), "block_per_gpu_incl_halo": list(shape), "features": features,
+                          "arith": args.arith, "decomposition": list(D), "l2": "state per GPU is far larger than the 126 MB L2; no flush needed"},
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                            "kernel": "k_stream_collide_tile", "kernel_ms": kern_ms, "share_of_step": kern_ms / (ms / K), "alg_bytes_per_cell": B_ALG[precision],
+                            "cells_per_launch": Nloc, "peak_source": peak_src},
+               "halo": {"nvlink_bytes_out_per_gpu_per_step": int(halo_bytes), "exposed_ms_per_step": ms / K - kern_ms},
+               "e2e": {"value": mlups, "unit": "MLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                       "note": "N>1: the multi-rank loop IS the host-API loop (DistributedLBM.run); per-step boundary upload / probe read-back are measured at N=1"},
+               "clocks": clocks, "gpu_launches": int(launches)}
+        print(json.dumps(res), flush=True)
+    lbm.close()
+    dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

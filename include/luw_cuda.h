@@ -118,12 +118,31 @@ int luw_vk_inlet_create(luw_domain* dom, uint64_t point_count, uint64_t mode_cou
 int luw_vk_inlet_apply(luw_vk_inlet* vk, uint32_t use_interp, float t0, float t1, float alpha);
 int luw_vk_inlet_destroy(luw_vk_inlet* vk);
 
+/* Boundary-field upload and probe read-back without moving whole fields. The reference writes boundary values into the full host mirrors and
+ * uploads / downloads ALL N cells (LBM::initialize FX/lbm.cpp:1226-1237; probes and sampling read the whole u field back, FX/setup.cpp:4411-4425,
+ * 4498-4509). A cell set is a fixed list of local cell indices (e.g. the TYPE_E inflow faces, a probe plane); upload scatters host values
+ * [c*count + k] (c = component: rho 1, u 3, flags 1) into the field, download gathers them. Host buffers may be pinned (luw_host_alloc). */
+typedef struct luw_cellset luw_cellset;
+int luw_cellset_create(luw_domain* dom, uint64_t count, const uint64_t* host_cell_index, luw_cellset** out);
+int luw_cellset_upload(luw_cellset* set, int field, const void* host_values);
+int luw_cellset_download(luw_cellset* set, int field, void* host_values);
+int luw_cellset_destroy(luw_cellset* set);
+
+/* page-locked host memory for the mirrors (the reference's Memory<T> owns pageable new[] buffers, FX/opencl.hpp:354) */
+int luw_host_alloc(void** host_ptr, uint64_t bytes);
+int luw_host_free(void* host_ptr);
+
 /* Device::finish_queue, FX/opencl.hpp:323 */
 int luw_sync(luw_domain* dom);
 
 /* timing helper for harnesses: CUDA events recorded on the domain's stream around whatever is enqueued between begin and end */
 int luw_timer_begin(luw_domain* dom);
 int luw_timer_end(luw_domain* dom, float* milliseconds); /* synchronises on the end event */
+/* per-kernel timing for harnesses: when enabled, every stream_collide enqueue is bracketed by CUDA events on the domain's stream
+ * (main step kernel only, not its x-column companion); luw_kernel_timing_read synchronises and returns the summed duration and the launch count
+ * since the last read. */
+int luw_kernel_timing(luw_domain* dom, int enable);
+int luw_kernel_timing_read(luw_domain* dom, float* milliseconds_total, uint64_t* launches);
 /* number of kernels this library has launched on behalf of `dom` since creation */
 int luw_launch_count(const luw_domain* dom, uint64_t* launches);
 

@@ -57,9 +57,17 @@ EXPORTS = {  # name -> argtypes; every symbol include/luw_cuda.h declares
     "luw_vk_inlet_create": [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)],
     "luw_vk_inlet_apply": [C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_float],
     "luw_vk_inlet_destroy": [C.c_void_p],
+    "luw_cellset_create": [C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p)],
+    "luw_cellset_upload": [C.c_void_p, C.c_int, C.c_void_p],
+    "luw_cellset_download": [C.c_void_p, C.c_int, C.c_void_p],
+    "luw_cellset_destroy": [C.c_void_p],
+    "luw_host_alloc": [C.POINTER(C.c_void_p), C.c_uint64],
+    "luw_host_free": [C.c_void_p],
     "luw_sync": [C.c_void_p],
     "luw_timer_begin": [C.c_void_p],
     "luw_timer_end": [C.c_void_p, C.POINTER(C.c_float)],
+    "luw_kernel_timing": [C.c_void_p, C.c_int],
+    "luw_kernel_timing_read": [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint64)],
     "luw_launch_count": [C.c_void_p, C.POINTER(C.c_uint64)],
 }
 

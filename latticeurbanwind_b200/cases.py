@@ -89,6 +89,69 @@ def urban(Nx, Ny, Nz, seed=1234, edge=16, pitch=32, footprint=0.75, u_ref=0.1, a
 CASES = {"periodic_box": periodic_box, "channel": channel, "urban": urban}
 
 
+def block_case(name, Ng, O=(0, 0, 0), Nl=None, seed=1234, amp=1e-3, u_ref=0.1, edge=16, pitch=32, footprint=0.75, out=None):
+    """The same three cases, built directly for ONE block of a decomposed lattice (local shape Nl incl. halo layers at global offset O,
+    periodic at the global edges) with broadcasting instead of full coordinate grids, so that 512^3 ... 1024x1024x256 blocks are cheap.
+    Geometry (flags, base profile) is a function of the GLOBAL coordinate, so neighbouring blocks agree on their shared layers; the
+    seeded perturbation of interior fluid cells is per block (seed + block offset). `out` = (flags, rho, u) arrays to fill (e.g. pinned)."""
+    Nl = tuple(Ng) if Nl is None else tuple(Nl)
+    Nx, Ny, Nz = Nl
+    N = Nx * Ny * Nz
+    xg, yg, zg = (np.mod(np.arange(Nl[a]) + O[a], Ng[a]) for a in range(3))
+    flags, rho, u = out if out is not None else (np.empty(N, np.uint8), np.empty(N, np.float32), np.empty(3 * N, np.float32))
+    f3 = flags.reshape(Nz, Ny, Nx)
+    f3[:] = 0
+    rho[:] = 1.0
+    u3 = u.reshape(3, Nz, Ny, Nx)
+    X, Y, Z = xg[None, None, :], yg[None, :, None], zg[:, None, None]
+    if name == "periodic_box":
+        base = np.full(Nz, 0.05, np.float32)
+    elif name == "channel":
+        f3[np.broadcast_to((X == 0) | (X == Ng[0] - 1), f3.shape)] = TYPE_E
+        f3[np.broadcast_to((Y == 0) | (Y == Ng[1] - 1) | (Z == 0) | (Z == Ng[2] - 1), f3.shape)] = TYPE_S
+        base = np.full(Nz, 0.05, np.float32)
+    elif name == "urban":
+        x0, x1 = int(Ng[0] * (1 - footprint) / 2), int(Ng[0] * (1 + footprint) / 2)
+        y0, y1 = int(Ng[1] * (1 - footprint) / 2), int(Ng[1] * (1 + footprint) / 2)
+        x2, y2 = xg[None, :], yg[:, None]
+        iy = (y2 - y0) // pitch
+        xs = x2 - x0 - (iy % 2) * (pitch // 2)
+        ix = xs // pitch
+        inside = (x2 >= x0) & (x2 < x1) & (y2 >= y0) & (y2 < y1) & (xs >= 0) & (xs % pitch < edge) & ((y2 - y0) % pitch < edge)
+        h = np.where(inside, np.minimum(cube_heights(np.maximum(ix, 0), np.maximum(iy, 0)), Ng[2] - 3), -1)
+        side2 = (x2 == 0) | (x2 == Ng[0] - 1) | (y2 == 0) | (y2 == Ng[1] - 1)
+        for k, z in enumerate(zg):
+            plane = f3[k]
+            if z == 0:
+                plane[:] = TYPE_S
+                continue
+            plane[h >= z] = TYPE_S
+            if z == Ng[2] - 1:
+                plane[:] = TYPE_E
+            else:
+                plane[np.broadcast_to(side2, plane.shape)] = TYPE_E
+        base = log_law(zg.astype(np.float32), Ng[2], u_ref)
+    else:
+        raise KeyError(name)
+    rng = np.random.default_rng([seed, O[0] & 0xFFFF, O[1] & 0xFFFF, O[2] & 0xFFFF])
+    for c in range(3):
+        uc = u3[c]
+        if amp > 0.0:
+            rng.random(out=uc.reshape(-1), dtype=np.float32)
+            uc *= np.float32(2.0 * amp)
+            uc -= np.float32(amp)
+        else:
+            uc[:] = 0.0
+        if c == 0:
+            uc += base[:, None, None]
+        if name != "periodic_box":  # boundary cells carry the clean profile; solids are at rest
+            for k in range(Nz):
+                pl, fl = uc[k], f3[k]
+                pl[fl == TYPE_E] = base[k] if c == 0 else 0.0
+                pl[fl == TYPE_S] = 0.0
+    return flags, rho, u
+
+
 def kernel_literal(x):
     """The float the reference's OpenCL JIT sees for a per-case constant: the host value printed by to_string(float) with
     8 decimals (FX/utilities.hpp:2603-2634, 2741-2750: float32 arithmetic, scientific form outside [1,10)) and parsed again."""

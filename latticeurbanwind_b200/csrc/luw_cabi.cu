@@ -43,6 +43,15 @@ struct luw_domain {
 	luw::TileMaps maps; // TMA descriptors for the tiled step
 	bool tiled = false; // the tiled step is usable for this domain
 	int tile_variant = 0, sm_count = 0;
+	bool ktiming = false; // bracket every main step kernel with events (luw_kernel_timing)
+	std::vector<cudaEvent_t> kev; // event pairs
+	size_t kev_used = 0u;
+};
+struct luw_cellset {
+	luw_domain* dom;
+	uint64_t count;
+	uint64_t* cell; // device: local cell indices
+	float* stage; // device staging: 4*count bytes per component, up to 3 components
 };
 struct luw_vk_inlet {
 	luw_domain* dom;
@@ -111,9 +120,32 @@ void setup_tiles(luw_domain* d) {
 	d->tiled = true;
 }
 cudaError_t enqueue_step(luw_domain* d, const luw::StepArgs& a) {
-	if(d->tiled) { d->launches += d->c.Dx==1u ? 2ull : 1ull; return d->ks->stream_collide_tile(d->c, a, d->maps, d->tile_variant, d->sm_count, d->stream); } // tile kernel (+ x-column kernel)
+	cudaError_t e = cudaSuccess;
+	if(d->ktiming) { // event pair around the main kernel
+		if(d->kev_used+2u>d->kev.size()) for(int k=0; k<2; k++) { cudaEvent_t ev; e = cudaEventCreate(&ev); if(e!=cudaSuccess) return e; d->kev.push_back(ev); }
+		e = cudaEventRecord(d->kev[d->kev_used], d->stream); if(e!=cudaSuccess) return e;
+	}
+	if(d->tiled) e = d->ks->stream_collide_tile(d->c, a, d->maps, d->tile_variant, d->sm_count, d->stream);
+	else e = d->ks->stream_collide(d->c, a, d->stream);
 	d->launches++;
-	return d->ks->stream_collide(d->c, a, d->stream);
+	if(e!=cudaSuccess) return e;
+	if(d->ktiming) { e = cudaEventRecord(d->kev[d->kev_used+1u], d->stream); if(e!=cudaSuccess) return e; d->kev_used += 2u; }
+	if(d->tiled&&d->c.Dx==1u) { e = d->ks->stream_collide_xcol(d->c, a, d->stream); d->launches++; } // the periodic column x = Nx-1
+	return e;
+}
+
+// scatter / gather between a staging buffer [c*count + k] and a field with `comps` components of stride N
+template<typename T> __global__ void __launch_bounds__(256) k_cellset_scatter(T* __restrict__ field, const uint64_t N, const uint32_t comps, const uint64_t count, const uint64_t* __restrict__ cell, const T* __restrict__ stage) {
+	const uint64_t k = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x;
+	if(k>=count) return;
+	const uint64_t n = cell[k];
+	for(uint32_t c=0u; c<comps; c++) field[(uint64_t)c*N+n] = stage[(uint64_t)c*count+k];
+}
+template<typename T> __global__ void __launch_bounds__(256) k_cellset_gather(const T* __restrict__ field, const uint64_t N, const uint32_t comps, const uint64_t count, const uint64_t* __restrict__ cell, T* __restrict__ stage) {
+	const uint64_t k = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x;
+	if(k>=count) return;
+	const uint64_t n = cell[k];
+	for(uint32_t c=0u; c<comps; c++) stage[(uint64_t)c*count+k] = field[(uint64_t)c*N+n];
 }
 
 __global__ void k_fill_f32(float* p, const uint64_t n, const float v) {
@@ -231,6 +263,7 @@ int luw_domain_destroy(luw_domain* d) {
 	cudaFree(d->c.fi); cudaFree(d->c.rho); cudaFree(d->c.u); cudaFree(d->c.flags); cudaFree(d->wbuf); cudaFree(d->sigma);
 	if(d->ev0) cudaEventDestroy(d->ev0);
 	if(d->ev1) cudaEventDestroy(d->ev1);
+	for(cudaEvent_t ev : d->kev) cudaEventDestroy(ev);
 	if(d->own_stream) cudaStreamDestroy(d->own_stream);
 	delete d;
 	return LUW_OK;
@@ -382,6 +415,74 @@ int luw_vk_inlet_destroy(luw_vk_inlet* v) {
 	return LUW_OK;
 }
 
+int luw_cellset_create(luw_domain* d, uint64_t count, const uint64_t* host_cell_index, luw_cellset** out) {
+	if(!d||!out||(count>0ull&&!host_cell_index)) return fail(LUW_ERR_INVALID, "null argument");
+	*out = nullptr;
+	for(uint64_t k=0ull; k<count; k++) if(host_cell_index[k]>=d->c.N) return fail(LUW_ERR_INVALID, "cell index outside the domain");
+	DeviceGuard guard(d->p.device);
+	luw_cellset* s = new(std::nothrow) luw_cellset();
+	if(!s) return fail(LUW_ERR_OOM, "host allocation failed");
+	s->dom = d; s->count = count; s->cell = nullptr; s->stage = nullptr;
+	int rc = LUW_OK;
+	if(count>0ull) {
+		rc = dev_alloc(d, &s->cell, count);
+		if(rc==LUW_OK) rc = dev_alloc(d, &s->stage, 3ull*count);
+		if(rc==LUW_OK) {
+			cudaError_t e = cudaMemcpyAsync(s->cell, host_cell_index, count*8ull, cudaMemcpyHostToDevice, d->stream);
+			if(e==cudaSuccess) e = cudaStreamSynchronize(d->stream);
+			if(e!=cudaSuccess) rc = cuda_fail(e, "upload cell set");
+		}
+	}
+	if(rc!=LUW_OK) { const std::string keep = g_error; luw_cellset_destroy(s); g_error = keep; return rc; }
+	*out = s;
+	return LUW_OK;
+}
+static int cellset_move(luw_cellset* s, int field, void* host, const bool up) {
+	if(!s||!host) return fail(LUW_ERR_INVALID, "null argument");
+	luw_domain* d = s->dom;
+	if(field!=LUW_FIELD_RHO&&field!=LUW_FIELD_U&&field!=LUW_FIELD_FLAGS) return fail(LUW_ERR_INVALID, "cell sets move rho, u or flags");
+	if(s->count==0ull) return LUW_OK;
+	DeviceGuard guard(d->p.device);
+	const uint32_t comps = field==LUW_FIELD_U ? 3u : 1u;
+	const size_t elem = field==LUW_FIELD_FLAGS ? 1u : 4u;
+	const unsigned blocks = (unsigned)((s->count+255ull)/256ull);
+	if(up) CU(cudaMemcpyAsync(s->stage, host, comps*s->count*elem, cudaMemcpyHostToDevice, d->stream));
+	if(field==LUW_FIELD_FLAGS) {
+		if(up) k_cellset_scatter<uint8_t><<<blocks, 256, 0, d->stream>>>(d->c.flags, d->c.N, 1u, s->count, s->cell, (const uint8_t*)s->stage);
+		else k_cellset_gather<uint8_t><<<blocks, 256, 0, d->stream>>>(d->c.flags, d->c.N, 1u, s->count, s->cell, (uint8_t*)s->stage);
+	} else {
+		float* f = field==LUW_FIELD_U ? d->c.u : d->c.rho;
+		if(up) k_cellset_scatter<float><<<blocks, 256, 0, d->stream>>>(f, d->c.N, comps, s->count, s->cell, s->stage);
+		else k_cellset_gather<float><<<blocks, 256, 0, d->stream>>>(f, d->c.N, comps, s->count, s->cell, s->stage);
+	}
+	CU(cudaGetLastError());
+	d->launches++;
+	if(!up) CU(cudaMemcpyAsync(host, s->stage, comps*s->count*elem, cudaMemcpyDeviceToHost, d->stream));
+	return LUW_OK;
+}
+int luw_cellset_upload(luw_cellset* s, int field, const void* host_values) { return cellset_move(s, field, (void*)host_values, true); }
+int luw_cellset_download(luw_cellset* s, int field, void* host_values) { return cellset_move(s, field, host_values, false); }
+int luw_cellset_destroy(luw_cellset* s) {
+	if(!s) return LUW_OK;
+	DeviceGuard guard(s->dom->p.device);
+	cudaStreamSynchronize(s->dom->stream);
+	cudaFree(s->cell); cudaFree(s->stage);
+	delete s;
+	return LUW_OK;
+}
+
+int luw_host_alloc(void** host_ptr, uint64_t bytes) {
+	if(!host_ptr) return fail(LUW_ERR_INVALID, "null argument");
+	*host_ptr = nullptr;
+	CU(cudaHostAlloc(host_ptr, bytes, cudaHostAllocPortable));
+	return LUW_OK;
+}
+int luw_host_free(void* host_ptr) {
+	if(!host_ptr) return LUW_OK;
+	CU(cudaFreeHost(host_ptr));
+	return LUW_OK;
+}
+
 int luw_sync(luw_domain* d) {
 	if(!d) return fail(LUW_ERR_INVALID, "null domain");
 	DeviceGuard guard(d->p.device);
@@ -400,6 +501,24 @@ int luw_timer_end(luw_domain* d, float* ms) {
 	CU(cudaEventRecord(d->ev1, d->stream));
 	CU(cudaEventSynchronize(d->ev1));
 	CU(cudaEventElapsedTime(ms, d->ev0, d->ev1));
+	return LUW_OK;
+}
+int luw_kernel_timing(luw_domain* d, int enable) {
+	if(!d) return fail(LUW_ERR_INVALID, "null domain");
+	DeviceGuard guard(d->p.device);
+	CU(cudaStreamSynchronize(d->stream));
+	d->ktiming = enable!=0;
+	d->kev_used = 0u;
+	return LUW_OK;
+}
+int luw_kernel_timing_read(luw_domain* d, float* ms_total, uint64_t* launches) {
+	if(!d||!ms_total||!launches) return fail(LUW_ERR_INVALID, "null argument");
+	DeviceGuard guard(d->p.device);
+	CU(cudaStreamSynchronize(d->stream));
+	float total = 0.0f;
+	for(size_t k=0u; k+1u<d->kev_used; k+=2u) { float ms = 0.0f; CU(cudaEventElapsedTime(&ms, d->kev[k], d->kev[k+1u])); total += ms; }
+	*ms_total = total; *launches = (uint64_t)(d->kev_used/2u);
+	d->kev_used = 0u;
 	return LUW_OK;
 }
 int luw_launch_count(const luw_domain* d, uint64_t* launches) {

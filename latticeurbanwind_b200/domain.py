@@ -150,6 +150,15 @@ class Domain:
         A.check(A.lib().luw_domain_step_kernel(self._h, C.byref(n)))
         return bool(n.value)
 
+    def kernel_timing(self, enable):
+        A.check(A.lib().luw_kernel_timing(self._h, int(bool(enable))))
+
+    def kernel_timing_read(self):
+        """(summed milliseconds, launches) of the main stream_collide kernel since the last read."""
+        ms, n = C.c_float(), C.c_uint64()
+        A.check(A.lib().luw_kernel_timing_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def device_bytes(self):
         n = C.c_uint64()
         A.check(A.lib().luw_domain_bytes(self._h, C.byref(n)))
@@ -176,3 +185,48 @@ class VkInlet:
         if self._h:
             A.lib().luw_vk_inlet_destroy(self._h)
             self._h = C.c_void_p()
+
+
+class CellSet:
+    """A fixed list of local cells whose rho / u / flags are uploaded or read back without moving the whole field (boundary-field upload,
+    probes). Values are SoA over the set: [c*count + k]."""
+
+    def __init__(self, domain, cells):
+        self.domain = domain
+        self.cells = np.ascontiguousarray(cells, np.uint64)
+        self.count = int(self.cells.size)
+        self._h = C.c_void_p()
+        A.check(A.lib().luw_cellset_create(domain._h, self.count, _ptr(self.cells), C.byref(self._h)))
+
+    def upload(self, field, values):
+        A.check(A.lib().luw_cellset_upload(self._h, field, _ptr(values)))
+
+    def download(self, field, values):
+        A.check(A.lib().luw_cellset_download(self._h, field, _ptr(values)))
+
+    def close(self):
+        if self._h:
+            A.lib().luw_cellset_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+def pinned_empty(count, dtype):
+    """numpy array over page-locked host memory (luw_host_alloc). The array keeps the allocation alive through its base object."""
+    dtype = np.dtype(dtype)
+    nbytes = int(count) * dtype.itemsize
+    p = C.c_void_p()
+    A.check(A.lib().luw_host_alloc(C.byref(p), max(nbytes, 1)))
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                A.lib().luw_host_free(self.ptr)
+            except Exception:
+                pass
+
+    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+    buf._owner = _Owner(p)  # the ctypes array accepts attributes; numpy keeps `buf` alive as the base of the returned array
+    return np.frombuffer(buf, dtype=dtype, count=int(count))

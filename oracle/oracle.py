@@ -20,6 +20,7 @@ PREC_NAME = {FP32: "fp32", FP16S: "fp16s", FP16C: "fp16c"}
 UPDATE_FIELDS, VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, SUBGRID, BUFFER_NUDGING, TOP_SPONGE = 1, 2, 4, 8, 16, 32
 FEATURE_SETS = {  # must match oracle/Makefile
     "bench": 0,
+    "chan": EQUILIBRIUM_BOUNDARIES,
     "plain": UPDATE_FIELDS | EQUILIBRIUM_BOUNDARIES,
     "core": UPDATE_FIELDS | VOLUME_FORCE | EQUILIBRIUM_BOUNDARIES | SUBGRID,
     "luw": UPDATE_FIELDS | VOLUME_FORCE | EQUILIBRIUM_BOUNDARIES | SUBGRID | BUFFER_NUDGING | TOP_SPONGE,

@@ -3,7 +3,7 @@ import numpy as np
 
 from latticeurbanwind_b200 import cases
 
-FEATURE_SETS = {"bench": 0, "plain": 1 | 4, "core": 1 | 2 | 4 | 8, "luw": 1 | 2 | 4 | 8 | 16 | 32, "luwnf": 2 | 4 | 8 | 16 | 32}
+FEATURE_SETS = {"bench": 0, "chan": 4, "plain": 1 | 4, "core": 1 | 2 | 4 | 8, "luw": 1 | 2 | 4 | 8 | 16 | 32, "luwnf": 2 | 4 | 8 | 16 | 32}
 FORCE = (1e-6, 0.0, -2e-6)
 OMEGA = (0.0, 5.6e-6, 4.7e-6)
 ZONES = dict(downstream_face=2, buffer_N=6, buffer_inv_tau=0.01, buffer_nudge_vertical=1, sponge_N=8, sponge_inv_tau=0.02)
