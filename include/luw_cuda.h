@@ -139,7 +139,7 @@ int luw_sync(luw_domain* dom);
 int luw_timer_begin(luw_domain* dom);
 int luw_timer_end(luw_domain* dom, float* milliseconds); /* synchronises on the end event */
 /* per-kernel timing for harnesses: when enabled, every stream_collide enqueue is bracketed by CUDA events on the domain's stream
- * (main step kernel only, not its x-column companion); luw_kernel_timing_read synchronises and returns the summed duration and the launch count
+ * (the step is a single kernel); luw_kernel_timing_read synchronises and returns the summed duration and the launch count
  * since the last read. */
 int luw_kernel_timing(luw_domain* dom, int enable);
 int luw_kernel_timing_read(luw_domain* dom, float* milliseconds_total, uint64_t* launches);

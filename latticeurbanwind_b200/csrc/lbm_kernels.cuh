@@ -80,24 +80,6 @@ template<int P, uint32_t FEAT> __global__ void __launch_bounds__(128) k_stream_c
 	store_f<P>((T*)c.fi, c.N, j, odd, f);
 }
 
-// the same step for the cells of the last lattice column x = Nx-1 only (threads run along y): companion of the tiled kernel (lbm_tile.cuh),
-// which cannot express the periodic +x neighbour of that column as a TMA box
-template<int P, uint32_t FEAT> __global__ void __launch_bounds__(128) k_stream_collide_xcol(const __grid_constant__ DomainConst c, const __grid_constant__ StepArgs a) {
-	typedef typename Ddf<P>::T T;
-	const uint32_t x = c.Nx-1u, y = blockIdx.x*blockDim.x+threadIdx.x, z = blockIdx.y;
-	if(y>=c.Ny||is_halo(c, x, y, z)) return;
-	uint64_t j[Q];
-	neighbors(c, x, y, z, j);
-	const uint64_t n = j[0];
-	const uint32_t fl = c.flags[n], bo = fl&TYPE_BO;
-	if(bo==TYPE_S||(fl&TYPE_SU)==TYPE_G) return;
-	const uint32_t odd = (uint32_t)(a.t&1ull);
-	float f[Q];
-	load_f<P>((const T*)c.fi, c.N, j, odd, f);
-	collide_cell<FEAT>(c, a, n, x, y, z, bo, f);
-	store_f<P>((T*)c.fi, c.N, j, odd, f);
-}
-
 // ------------------------------------------------------------------ kernel: initialize (FX/kernel.cpp:1370-1452)
 template<int P> __global__ void __launch_bounds__(128) k_initialize(const __grid_constant__ DomainConst c) {
 	typedef typename Ddf<P>::T T;

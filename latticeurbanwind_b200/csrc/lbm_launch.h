@@ -18,8 +18,6 @@ struct KernelSet { // one per arithmetic mode; every function enqueues exactly o
 	// TMA-tiled stream_collide (lbm_tile.cuh): box shape of tile variant `variant` for this precision / feature set, false if there is none
 	bool (*tile_shape)(int precision, uint32_t features, int variant, TileShape* shape);
 	cudaError_t (*stream_collide_tile)(const DomainConst& c, const StepArgs& a, const TileMaps& maps, int variant, int sm_count, cudaStream_t s);
-	// its companion when x is not decomposed: the cells of the periodic column x = Nx-1 (must follow the tiled kernel on the same stream)
-	cudaError_t (*stream_collide_xcol)(const DomainConst& c, const StepArgs& a, cudaStream_t s);
 };
 const KernelSet& kernels_strict(); // lbm_strict.cu: -fmad=false
 const KernelSet& kernels_fast(); // lbm_fast.cu: contraction allowed

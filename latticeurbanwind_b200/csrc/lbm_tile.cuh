@@ -9,15 +9,23 @@
 // global DDF access. The innermost TMA coordinate must be 16-byte aligned (measured: an odd x origin raises "illegal instruction" on
 // B200), so the five x+1 shifted streams are loaded at the tile's own x origin and read one element to the right; the element that
 // belongs to the tile's last column then sits in column 0 of the NEXT tile's box. A CTA therefore walks whole x-strips, tile after
-// tile, and finishes the last column of a tile inside the already prefetched next stage. The cells of the lattice's last column
-// x = Nx-1 (whose +x neighbour wraps to x = 0) are left to a separate per-cell launch (k_stream_collide_xcol).
+// tile, and finishes the last column of a tile inside the already prefetched next stage.
+// Periodic x (Dx == 1): the +x neighbour of the lattice's last column is column 0, i.e. column 0 of the strip's FIRST tile, which
+// has long been written back when the strip's last tile is processed. Its five elements per row are therefore parked in shared memory
+// when the first tile passes (pads behind the five shifted boxes of stage 0), read and updated there by the last tile, and written
+// to global memory with plain stores one strip later, after the producer has seen the first tile's TMA store complete.
 // Cells that do not execute (solid / gas / halo, FX/kernel.cpp:1486-1490) leave their slots untouched in shared memory, so the
 // write-back of the box is the identity for them -- legal because no other cell touches those slots.
 //
-// Pipeline. One CTA = TILE/2 consumer threads (two x-adjacent cells per thread, packed FP32x2 arithmetic, lbm_vec.cuh) + a loader warp
-// + a storer warp, over a ring of STAGES shared-memory stages with mbarriers:  loader: wait empty[s] -> expect_tx + 20 TMA loads ->
-// full[s];  consumers: wait full[s] -> collide in place -> fence.proxy.async -> arrive done[s];  storer: wait done[s] -> 19 TMA stores ->
-// commit -> wait_group.read -> arrive empty[s]. CTAs are persistent (grid = resident CTAs) and walk the tile list with stride gridDim.
+// Pipeline. One CTA = TILE/2 consumer threads (two x-adjacent cells per thread, packed FP32x2 arithmetic, lbm_vec.cuh) + one producer
+// warp, over a ring of STAGES shared-memory stages with mbarriers:  producer: expect_tx + 20 TMA loads -> full[s];  consumers: wait
+// full[s] -> collide in place -> fence.proxy.async -> arrive done[s];  producer: wait done[s] -> 19 TMA stores -> commit ->
+// wait_group.read -> refill the stage with the tile STAGES ahead. CTAs are persistent (grid = resident CTAs) and walk the strip list
+// with stride gridDim.
+//
+// TYPE_E cells (FX/kernel.cpp:1503-1515,1747) take their rho/u from the boundary fields and set f := feq; they do not depend on the
+// streamed DDFs at all. They are kept out of the packed main path: lanes that hold a TYPE_E cell are overwritten afterwards by a
+// scalar equilibrium, and their rho/u are prefetched into L2 one tile ahead.
 //
 // Periodic wrap in y / z. TMA zero-fills the part of a box that lies outside the lattice and clips it on the way back. In strips that
 // touch the y / z boundary the consumers patch those elements from / to their wrapped addresses (FX/kernel.cpp:920-931) with plain loads and stores.
@@ -34,12 +42,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* b, const uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(b)), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* b, const uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(b)), "r"(bytes) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory"); }
+__device__ __forceinline__ bool mbar_try(uint64_t* b, const uint32_t parity) {
+	uint32_t done;
+	asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(b)), "r"(parity), "r"(1000000u) : "memory"); // suspend-time hint [ns]
+	return done!=0u;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* b, const uint32_t parity) {
-	uint32_t done = 0u, spins = 0u;
-	while(!done) {
-		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(b)), "r"(parity), "r"(1000000u) : "memory"); // suspend-time hint [ns]
-		if(!done&&++spins>(1u<<24)) __trap(); // a lost arrival must abort the launch, not hang the device
-	}
+	if(mbar_try(b, parity)) return;
+	uint32_t spins = 0u;
+	while(!mbar_try(b, parity)) if(++spins>(1u<<24)) __trap(); // a lost arrival must abort the launch, not hang the device
 }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, const int c0, const int c1, const int c2, const int c3) {
 	asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -56,65 +67,84 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); } // all but the most recent group complete
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void consumer_bar(const uint32_t nthreads) { asm volatile("bar.sync 1, %0;" :: "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 // ------------------------------------------------------------------ geometry of a tile
+// shared-memory box order inside a stage: box 0 = f0; box 1+2k = slot A of pair k (own cell: holds f_i, receives f_i+1);
+// box 2+2k = slot B of pair k (neighbour n+c_i: holds f_i+1, receives f_i). Pairs 0,3,4,6,7 have c_x = +1: their B boxes (2,8,10,14,16)
+// are the x-shifted ones; each is followed by a 128-byte pad (stage 0's pads park the periodic-x column, see above).
+__host__ __device__ constexpr bool box_shifted(const int b) { return b==2||b==8||b==10||b==14||b==16; }
+__host__ __device__ constexpr int pads_before(const int b) { return (b>2)+(b>8)+(b>10)+(b>14)+(b>16); }
 template<int P_, int TX_, int TY_, int TZ_, int STAGES_, int CTAS_> struct TileCfg {
 	static constexpr int P = P_, TX = TX_, TY = TY_, TZ = TZ_, STAGES = STAGES_, CTAS_PER_SM = CTAS_;
-	static constexpr int TILE = TX*TY*TZ, CONSUMERS = TILE/2, THREADS = CONSUMERS+64;
+	static constexpr int TILE = TX*TY*TZ, ROWS = TY*TZ, CONSUMERS = TILE/2, THREADS = CONSUMERS+32;
 	static constexpr int ES = (P_==P_FP32) ? 4 : 2;
-	static constexpr int BOX_BYTES = TILE*ES;
-	static constexpr int STAGE_BYTES = Q*BOX_BYTES+TILE; // 19 DDF boxes + the flag box
-	static constexpr int SMEM_BYTES = STAGES*STAGE_BYTES+3*STAGES*8+128; // + mbarriers, + slack for 128 B alignment of the first stage
-	static_assert(CONSUMERS%32==0&&TX%2==0&&BOX_BYTES%128==0&&TILE%128==0, "tile shape");
+	static constexpr int BOX_BYTES = TILE*ES, PAD = 128;
+	static constexpr int FLAG_OFF = Q*BOX_BYTES+5*PAD;
+	static constexpr int STAGE_BYTES = FLAG_OFF+TILE; // 19 DDF boxes + 5 pads + the flag box
+	static constexpr int LOAD_BYTES = Q*BOX_BYTES+TILE; // what one stage's TMA loads deliver
+	static constexpr int SMEM_BYTES = STAGES*STAGE_BYTES+(2*STAGES+1)*8+128; // + mbarriers, + slack for 128 B alignment of the first stage
+	__host__ __device__ static constexpr int box_off(const int b) { return b*BOX_BYTES+PAD*pads_before(b); }
+	static_assert(TX==64, "one warp per tile row"); // the periodic-x parking relies on a row being handled by a single warp
+	static_assert(CONSUMERS%32==0&&BOX_BYTES%128==0&&TILE%128==0&&2*ROWS*ES<=PAD, "tile shape");
 };
 // pair k = (i-1)/2, i odd: c_i
 __device__ __forceinline__ void pair_shift(const int k, int& cx, int& cy, int& cz) {
 	const int CXv[9] = {1,0,0,1,1,0, 1, 1, 0}, CYv[9] = {0,1,0,1,0,1,-1, 0, 1}, CZv[9] = {0,0,1,0,1,1, 0,-1,-1};
 	cx = CXv[k]; cy = CYv[k]; cz = CZv[k];
 }
-// shared-memory box order inside a stage: box 0 = f0; box 1+2k = slot A of pair k (own cell: holds f_i, receives f_i+1);
-// box 2+2k = slot B of pair k (neighbour n+c_i: holds f_i+1, receives f_i)
 
 template<int P> struct PairCodec;
 template<> struct PairCodec<P_FP32> { // two floats
 	typedef float2 R;
+	typedef float E;
 	static __device__ __forceinline__ f2 dec(const R r) { f2 v; v.v = r; return v; }
 	static __device__ __forceinline__ R enc(const f2 v) { return v.v; }
 	static __device__ __forceinline__ R mix(const bool k0, const bool k1, const R n, const R o) { return make_float2(k0 ? n.x : o.x, k1 ? n.y : o.y); }
+	static __device__ __forceinline__ E low(const R w) { return w.x; }
 	// x+1 shifted stream: elements (lx+1, lx+2) from the thread's own word w0 = (lx, lx+1) and the element right of it
 	static __device__ __forceinline__ R shift_in(const R w0, const uint8_t* next) { return make_float2(w0.y, *(const float*)next); }
 	static __device__ __forceinline__ void shift_out(uint8_t* own, uint8_t* next, const R n, const bool k0, const bool k1) { if(k0) ((float*)own)[1] = n.x; if(k1) *(float*)next = n.y; }
+	static __device__ __forceinline__ void shift_out_both(uint8_t* own, uint8_t* next, const R n) { ((float*)own)[1] = n.x; *(float*)next = n.y; }
 };
 template<> struct PairCodec<P_FP16S> { // half2 holding 2^15 f; the 2^15 is folded into the FAST collision, applied in STRICT
 	typedef uint32_t R;
+	typedef uint16_t E;
 	static __device__ __forceinline__ f2 dec_raw(const R r) { f2 v; v.v = __half22float2(*reinterpret_cast<const __half2*>(&r)); return v; }
 	static __device__ __forceinline__ R enc_raw(const f2 v) { const __half2 h = __float22half2_rn(v.v); return *reinterpret_cast<const R*>(&h); }
 	static __device__ __forceinline__ f2 dec(const R r) { return sm(3.0517578E-5f, dec_raw(r)); } // exact scaling; scalar so that it is never fused into a later add
 	static __device__ __forceinline__ R enc(const f2 v) { return enc_raw(sm(32768.0f, v)); }
 	static __device__ __forceinline__ R mix(const bool k0, const bool k1, const R n, const R o) { return (k0 ? (n&0xFFFFu) : (o&0xFFFFu))|(k1 ? (n&0xFFFF0000u) : (o&0xFFFF0000u)); }
+	static __device__ __forceinline__ E low(const R w) { return (uint16_t)(w&0xFFFFu); }
 	static __device__ __forceinline__ R shift_in(const R w0, const uint8_t* next) { return __byte_perm(w0, (uint32_t)*(const uint16_t*)next, 0x5432); }
 	static __device__ __forceinline__ void shift_out(uint8_t* own, uint8_t* next, const R n, const bool k0, const bool k1) { if(k0) ((uint16_t*)own)[1] = (uint16_t)(n&0xFFFFu); if(k1) *(uint16_t*)next = (uint16_t)(n>>16); }
+	static __device__ __forceinline__ void shift_out_both(uint8_t* own, uint8_t* next, const R n) { ((uint16_t*)own)[1] = (uint16_t)(n&0xFFFFu); *(uint16_t*)next = (uint16_t)(n>>16); }
 };
 template<> struct PairCodec<P_FP16C> {
 	typedef uint32_t R;
+	typedef uint16_t E;
 	static __device__ __forceinline__ f2 dec(const R r) { return mk2(Ddf<P_FP16C>::dec((uint16_t)(r&0xFFFFu)), Ddf<P_FP16C>::dec((uint16_t)(r>>16))); }
 	static __device__ __forceinline__ R enc(const f2 v) { return (uint32_t)Ddf<P_FP16C>::enc(v.v.x)|((uint32_t)Ddf<P_FP16C>::enc(v.v.y)<<16); }
 	static __device__ __forceinline__ R mix(const bool k0, const bool k1, const R n, const R o) { return (k0 ? (n&0xFFFFu) : (o&0xFFFFu))|(k1 ? (n&0xFFFF0000u) : (o&0xFFFF0000u)); }
+	static __device__ __forceinline__ E low(const R w) { return (uint16_t)(w&0xFFFFu); }
 	static __device__ __forceinline__ R shift_in(const R w0, const uint8_t* next) { return __byte_perm(w0, (uint32_t)*(const uint16_t*)next, 0x5432); }
 	static __device__ __forceinline__ void shift_out(uint8_t* own, uint8_t* next, const R n, const bool k0, const bool k1) { if(k0) ((uint16_t*)own)[1] = (uint16_t)(n&0xFFFFu); if(k1) *(uint16_t*)next = (uint16_t)(n>>16); }
+	static __device__ __forceinline__ void shift_out_both(uint8_t* own, uint8_t* next, const R n) { ((uint16_t*)own)[1] = (uint16_t)(n&0xFFFFu); *(uint16_t*)next = (uint16_t)(n>>16); }
 };
 
-// ------------------------------------------------------------------ the kernel
+// ------------------------------------------------------------------ boundary helpers
 // Boxes the TMA store must not write: (a) negative origin (measured: illegal instruction for stores; loads zero-fill), (b) a row/plane
 // shifted by -1 in a partial tile, where the last lattice row/plane would be rewritten on behalf of cells that do not exist while its
 // real owners (row/plane 0, through the periodic wrap) update it from another strip. The consumers write such boxes back (patch_yz).
 template<class CFG> __device__ __forceinline__ bool box_by_threads(const DomainConst& c, const int cy, const int cz, const int y0, const int z0) {
 	return y0+cy<0||z0+cz<0||(cy<0&&y0+CFG::TY>(int)c.Ny)||(cz<0&&z0+CFG::TZ>(int)c.Nz);
 }
-// y/z-wrap patch of stage `st` (tile origin x0,y0,z0): IN = fill the zero-filled elements from their wrapped addresses, !IN = write them back
-template<class CFG, bool IN> __device__ __forceinline__ void patch_yz(const DomainConst& c, uint8_t* st, const int x0, const int y0, const int z0, const uint32_t odd, const uint32_t tid) {
+// y/z-wrap patch of stage `st` (tile origin x0,y0,z0): IN = fill the zero-filled elements from their wrapped addresses, !IN = write them back.
+// `skip_x0`: column x = 0 of the x-shifted boxes is written by the periodic-x flush instead (see the head comment).
+template<class CFG, bool IN> __device__ __noinline__ void patch_yz(const DomainConst& c, uint8_t* st, const int x0, const int y0, const int z0, const uint32_t odd, const uint32_t tid, const bool skip_x0) {
 	typedef typename Ddf<CFG::P>::T T;
 	constexpr int TX = CFG::TX, TY = CFG::TY;
 	T* const fi = (T*)c.fi;
@@ -122,35 +152,76 @@ template<class CFG, bool IN> __device__ __forceinline__ void patch_yz(const Doma
 	for(int k=1; k<9; k++) { // pair 0 (+x) has no y/z shift
 		int cx, cy, cz; pair_shift(k, cx, cy, cz);
 		const uint32_t slot = odd ? 2u*k+2u : 2u*k+1u;
-		T* box = (T*)(st+(2+2*k)*CFG::BOX_BYTES);
+		T* box = (T*)(st+CFG::box_off(2+2*k));
 		const bool whole = box_by_threads<CFG>(c, cy, cz, y0, z0); // loaded by TMA, but written back here in full
 		for(uint32_t e=tid; e<(uint32_t)CFG::TILE; e+=(uint32_t)CFG::CONSUMERS) {
 			const int x = x0+(int)(e%TX), y = y0+(int)((e/TX)%TY), z = z0+(int)(e/(TX*TY));
 			if(x>=(int)c.Nx||y>=(int)c.Ny||z>=(int)c.Nz) continue; // no cell owns this element
 			const int yn = y+cy, zn = z+cz;
 			if(yn>=0&&yn<(int)c.Ny&&zn>=0&&zn<(int)c.Nz&&(IN||!whole)) continue; // inside the lattice: TMA moves it
+			if(!IN&&skip_x0&&cx!=0&&x==0) continue;
 			const uint64_t nn = (uint64_t)x+(uint64_t)(yn<0 ? (int)c.Ny-1 : yn>=(int)c.Ny ? 0 : yn)*rowN+(uint64_t)(zn<0 ? (int)c.Nz-1 : zn>=(int)c.Nz ? 0 : zn)*planeN;
 			if(IN) box[e] = fi[(uint64_t)slot*c.N+nn]; else fi[(uint64_t)slot*c.N+nn] = box[e];
 		}
 	}
 }
+// periodic-x flush: the parked column-0 elements of the strip with tile origin (y0,z0) go to global memory (row `row` of the tile)
+template<class CFG> __device__ __noinline__ void flush_wrap(const DomainConst& c, const uint8_t* stage0, const uint32_t par, const uint32_t row, const int y0, const int z0, const uint32_t odd) {
+	typedef typename Ddf<CFG::P>::T T;
+	const int y = y0+(int)(row%(uint32_t)CFG::TY), z = z0+(int)(row/(uint32_t)CFG::TY);
+	if(y>=(int)c.Ny||z>=(int)c.Nz) return;
+	T* const fi = (T*)c.fi;
+	const uint64_t rowN = c.Nx, planeN = (uint64_t)c.Nx*c.Ny;
+	for(int k=0; k<9; k++) {
+		int cx, cy, cz; pair_shift(k, cx, cy, cz);
+		if(cx==0) continue;
+		const uint32_t slot = odd ? 2u*k+2u : 2u*k+1u;
+		const int yn = y+cy, zn = z+cz;
+		const uint64_t nn = (uint64_t)(yn<0 ? (int)c.Ny-1 : yn>=(int)c.Ny ? 0 : yn)*rowN+(uint64_t)(zn<0 ? (int)c.Nz-1 : zn>=(int)c.Nz ? 0 : zn)*planeN; // x = 0
+		fi[(uint64_t)slot*c.N+nn] = *(const T*)(stage0+CFG::box_off(2+2*k)+CFG::BOX_BYTES+(par*(uint32_t)CFG::ROWS+row)*(uint32_t)CFG::ES);
+	}
+}
 
+// TYPE_E cell: rho/u are boundary data; Coriolis shift, clamp, f := feq (FX/kernel.cpp:1503-1522,1686-1716,1747). Scalar, in the reference's
+// operation order (relaxation zones never apply to TYPE_E cells, FX/kernel.cpp:1524). Writes lane `lane` of f[] in units of `scale`.
+template<uint32_t FEAT> __device__ __forceinline__ void equilibrium_cell(const DomainConst& c, const StepArgs& a, const uint64_t n, const float scale, float* feq) {
+	constexpr bool VF = (FEAT&F_VOLUME_FORCE)!=0u;
+	const float rhon = c.rho[n];
+	float uxn = c.u[n], uyn = c.u[c.N+n], uzn = c.u[2ull*c.N+n];
+	if(VF) {
+		float fxn, fyn, fzn;
+		luw_force(c, a, 0u, 0u, 0u, TYPE_E, false, rhon, uxn, uyn, uzn, fxn, fyn, fzn);
+		const float rho2 = 0.5f/rhon;
+		uxn = clampc(fmaf(fxn, rho2, uxn)); uyn = clampc(fmaf(fyn, rho2, uyn)); uzn = clampc(fmaf(fzn, rho2, uzn));
+	} else {
+		uxn = clampc(uxn); uyn = clampc(uyn); uzn = clampc(uzn);
+	}
+	f_eq(rhon, uxn, uyn, uzn, feq);
+	if(scale!=1.0f) {
+#pragma unroll
+		for(int i=0; i<Q; i++) feq[i] *= scale; // exact (power of two)
+	}
+}
+
+// ------------------------------------------------------------------ the kernel
 template<class CFG, uint32_t FEAT, bool FAST> __global__ void __launch_bounds__(CFG::THREADS, CFG::CTAS_PER_SM)
 k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_constant__ StepArgs a, const __grid_constant__ TileMaps maps, const uint32_t tiles_x, const uint32_t tiles_y, const uint32_t tiles_z) {
 	constexpr int P = CFG::P, TX = CFG::TX, TY = CFG::TY, TZ = CFG::TZ, TILE = CFG::TILE, S = CFG::STAGES, NC = CFG::CONSUMERS;
 	typedef PairCodec<P> PC;
 	typedef typename PC::R R;
+	typedef typename PC::E E;
 	constexpr bool UF = (FEAT&F_UPDATE_FIELDS)!=0u, EQ = (FEAT&F_EQUILIBRIUM)!=0u, VF = (FEAT&F_VOLUME_FORCE)!=0u;
 
 	extern __shared__ uint8_t smem_raw[];
-	uint8_t* stage0 = smem_raw+((128u-(smem_u32(smem_raw)&127u))&127u); // 128 B aligned; derived from the __shared__ symbol so that LDS/STS are emitted
-	uint64_t* bar_full = (uint64_t*)(stage0+(size_t)S*CFG::STAGE_BYTES);
-	uint64_t* bar_done = bar_full+S;
-	uint64_t* bar_empty = bar_done+S;
+	uint8_t* const stage0 = smem_raw+((128u-(smem_u32(smem_raw)&127u))&127u); // 128 B aligned; derived from the __shared__ symbol so that LDS/STS are emitted
+	uint64_t* const bar_full = (uint64_t*)(stage0+(size_t)S*CFG::STAGE_BYTES);
+	uint64_t* const bar_done = bar_full+S;
+	uint64_t* const bar_head = bar_done+S;
 
 	const uint32_t tid = threadIdx.x;
 	if(tid==0u) {
-		for(int s=0; s<S; s++) { mbar_init(bar_full+s, 1u); mbar_init(bar_done+s, (uint32_t)NC); mbar_init(bar_empty+s, 1u); }
+		for(int s=0; s<S; s++) { mbar_init(bar_full+s, 1u); mbar_init(bar_done+s, (uint32_t)NC); }
+		mbar_init(bar_head, 1u);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
@@ -160,92 +231,117 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 	const uint32_t my_strips = blockIdx.x<nstrips ? (nstrips-blockIdx.x+gridDim.x-1u)/gridDim.x : 0u;
 	const uint32_t my_tiles = my_strips*tiles_x;
 	const uint32_t odd = (uint32_t)(a.t&1ull);
+	const bool wrap_x = c.Dx==1u; // the lattice is periodic in x inside this domain
+	const bool park = wrap_x&&tiles_x>=2u; // ... and the wrapped column lives in another tile than the last one
 
-	if(tid>=(uint32_t)NC) { // ---------------------------------------------------------------- producer warps
-		const uint32_t pw = (tid-(uint32_t)NC)>>5;
-		if((tid&31u)!=0u) return;
-		if(pw==0u) { // loader
-			for(uint32_t q=0u; q<my_tiles; q++) {
-				const int s = (int)(q%(uint32_t)S);
-				if(q>=(uint32_t)S) mbar_wait(bar_empty+s, ((q/(uint32_t)S)-1u)&1u);
-				const uint32_t strip = blockIdx.x+(q/tiles_x)*gridDim.x;
-				const int x0 = (int)(q%tiles_x)*TX, y0 = (int)(strip%tiles_y)*TY, z0 = (int)(strip/tiles_y)*TZ;
-				uint8_t* st = stage0+(size_t)s*CFG::STAGE_BYTES;
-				mbar_expect_tx(bar_full+s, (uint32_t)CFG::STAGE_BYTES);
-				tma_load_3d(st+Q*CFG::BOX_BYTES, &maps.flags, bar_full+s, x0, y0, z0);
-				tma_load_4d(st, &maps.fi, bar_full+s, x0, y0, z0, 0);
+	if(tid>=(uint32_t)NC) { // ---------------------------------------------------------------- producer warp: TMA loads and stores
+		if(tid!=(uint32_t)NC) return;
+		uint32_t lstrip = blockIdx.x, lxt = 0u; // tile the next load belongs to
+		const auto issue_loads = [&](const uint32_t q) {
+			const int s = (int)(q%(uint32_t)S);
+			const int x0 = (int)lxt*TX, y0 = (int)(lstrip%tiles_y)*TY, z0 = (int)(lstrip/tiles_y)*TZ;
+			uint8_t* st = stage0+(size_t)s*CFG::STAGE_BYTES;
+			mbar_expect_tx(bar_full+s, (uint32_t)CFG::LOAD_BYTES);
+			tma_load_3d(st+CFG::FLAG_OFF, &maps.flags, bar_full+s, x0, y0, z0);
+			tma_load_4d(st, &maps.fi, bar_full+s, x0, y0, z0, 0);
 #pragma unroll
-				for(int k=0; k<9; k++) {
-					int cx, cy, cz; pair_shift(k, cx, cy, cz);
-					const int i = 2*k+1;
-					tma_load_4d(st+(1+2*k)*CFG::BOX_BYTES, &maps.fi, bar_full+s, x0, y0, z0, odd ? i : i+1);
-					tma_load_4d(st+(2+2*k)*CFG::BOX_BYTES, &maps.fi, bar_full+s, x0, y0+cy, z0+cz, odd ? i+1 : i); // x shift applied by the readers
-				}
+			for(int k=0; k<9; k++) {
+				int cx, cy, cz; pair_shift(k, cx, cy, cz);
+				const int i = 2*k+1;
+				tma_load_4d(st+CFG::box_off(1+2*k), &maps.fi, bar_full+s, x0, y0, z0, odd ? i : i+1);
+				tma_load_4d(st+CFG::box_off(2+2*k), &maps.fi, bar_full+s, x0, y0+cy, z0+cz, odd ? i+1 : i); // x shift applied by the readers
 			}
-		} else { // storer
-			for(uint32_t q=0u; q<my_tiles; q++) {
-				const int s = (int)(q%(uint32_t)S);
-				mbar_wait(bar_done+s, (q/(uint32_t)S)&1u);
-				const uint32_t strip = blockIdx.x+(q/tiles_x)*gridDim.x;
-				const int x0 = (int)(q%tiles_x)*TX, y0 = (int)(strip%tiles_y)*TY, z0 = (int)(strip/tiles_y)*TZ;
-				const uint8_t* st = stage0+(size_t)s*CFG::STAGE_BYTES;
-				tma_store_4d(&maps.fi, st, x0, y0, z0, 0);
+			if(++lxt==tiles_x) { lxt = 0u; lstrip += gridDim.x; }
+		};
+		const uint32_t pro = my_tiles<(uint32_t)S ? my_tiles : (uint32_t)S;
+		for(uint32_t q=0u; q<pro; q++) issue_loads(q);
+		uint32_t sstrip = blockIdx.x, sxt = 0u; // tile the next store belongs to
+		for(uint32_t q=0u; q<my_tiles; q++) {
+			const int s = (int)(q%(uint32_t)S);
+			mbar_wait(bar_done+s, (q/(uint32_t)S)&1u);
+			const int x0 = (int)sxt*TX, y0 = (int)(sstrip%tiles_y)*TY, z0 = (int)(sstrip/tiles_y)*TZ;
+			const uint8_t* st = stage0+(size_t)s*CFG::STAGE_BYTES;
+			tma_store_4d(&maps.fi, st, x0, y0, z0, 0);
 #pragma unroll
-				for(int k=0; k<9; k++) {
-					int cx, cy, cz; pair_shift(k, cx, cy, cz);
-					const int i = 2*k+1;
-					tma_store_4d(&maps.fi, st+(1+2*k)*CFG::BOX_BYTES, x0, y0, z0, odd ? i : i+1);
-					if(!box_by_threads<CFG>(c, cy, cz, y0, z0)) tma_store_4d(&maps.fi, st+(2+2*k)*CFG::BOX_BYTES, x0, y0+cy, z0+cz, odd ? i+1 : i);
-				}
-				tma_commit();
-				tma_wait_read0(); // the stage may be refilled once TMA has read it
-				mbar_arrive(bar_empty+s);
+			for(int k=0; k<9; k++) {
+				int cx, cy, cz; pair_shift(k, cx, cy, cz);
+				const int i = 2*k+1;
+				tma_store_4d(&maps.fi, st+CFG::box_off(1+2*k), x0, y0, z0, odd ? i : i+1);
+				if(!box_by_threads<CFG>(c, cy, cz, y0, z0)) tma_store_4d(&maps.fi, st+CFG::box_off(2+2*k), x0, y0+cy, z0+cz, odd ? i+1 : i);
 			}
-			tma_wait_all0();
+			tma_commit();
+			if(q+(uint32_t)S<my_tiles) { tma_wait_read0(); issue_loads(q+(uint32_t)S); } // the stage may be refilled once TMA has read it
+			const bool last_of_strip = sxt+1u==tiles_x;
+			if(park&&last_of_strip) { tma_wait_all1(); mbar_arrive(bar_head); } // the strip's first tile is in global memory: its column 0 may be overwritten
+			if(last_of_strip) { sxt = 0u; sstrip += gridDim.x; } else sxt++;
 		}
+		tma_wait_all0();
 		return;
 	}
 
 	// ---------------------------------------------------------------------------------------- consumers: two cells per thread
 	const uint32_t row = tid/(uint32_t)(TX/2), lx = 2u*(tid%(uint32_t)(TX/2)), ly = row%(uint32_t)TY, lz = row/(uint32_t)TY;
-	const bool last_in_row = lx==(uint32_t)(TX-2);
 	const float scale = (FAST&&P==P_FP16S) ? 32768.0f : 1.0f, inv = (FAST&&P==P_FP16S) ? 3.0517578E-5f : 1.0f;
 	const uint64_t rowN = c.Nx, planeN = (uint64_t)c.Nx*c.Ny;
-	const uint32_t xskip = c.Dx>1u ? 0xFFFFFFFFu : c.Nx-1u; // the column left to k_stream_collide_xcol
 	const bool has_zones = VF&&(c.features&(F_NUDGING|F_SPONGE))!=0u;
 	const int Nb = (c.features&F_NUDGING) ? (int)c.buffer_N : -1, Ns = (c.features&F_SPONGE) ? (int)c.sponge_N : 0;
+	const uint32_t last_tx = c.Nx-(tiles_x-1u)*(uint32_t)TX; // cells of the last tile's rows that lie inside the lattice
 	// walk: strip = blockIdx.x, blockIdx.x+gridDim.x, ...; inside a strip xt = 0..tiles_x-1; ring slot s and its phase advance with every tile
-	uint32_t strip = blockIdx.x, xt = 0u, s = 0u, ph = 0u;
-	int y0 = (int)(strip%tiles_y)*TY, z0 = (int)(strip/tiles_y)*TZ;
+	uint32_t strip = blockIdx.x, xt = 0u, s = 0u, ph = 0u, kstrip = 0u;
+	int y0 = (int)(strip%tiles_y)*TY, z0 = (int)(strip/tiles_y)*TZ, py0 = 0, pz0 = 0;
 	for(uint32_t q=0u; q<my_tiles; q++) {
 		const uint32_t s1 = s+1u==(uint32_t)S ? 0u : s+1u, ph1 = s+1u==(uint32_t)S ? ph^1u : ph;
 		const int x0 = (int)xt*TX;
 		uint8_t* const st = stage0+(size_t)s*CFG::STAGE_BYTES;
 		uint8_t* const st1 = stage0+(size_t)s1*CFG::STAGE_BYTES;
-		const bool has_next = xt+1u<tiles_x; // the next tile of the strip holds the +x slots of this tile's last column
+		const bool first = xt==0u, last = xt+1u==tiles_x; // the next tile of the strip holds the +x slots of this tile's last column
 		const bool bnd_yz = y0==0||y0+TY>=(int)c.Ny||z0==0||z0+TZ>=(int)c.Nz; // strip touches the y/z boundary (uniform)
-		const bool edge = bnd_yz||x0==0||x0+TX>=(int)c.Nx;
-		if(xt==0u) { mbar_wait(bar_full+s, ph); if(bnd_yz) patch_yz<CFG, true>(c, st, x0, y0, z0, odd, tid); }
-		if(has_next) { mbar_wait(bar_full+s1, ph1); if(bnd_yz) patch_yz<CFG, true>(c, st1, x0+TX, y0, z0, odd, tid); }
+		const bool edge = bnd_yz||first||last;
+		if(first) { mbar_wait(bar_full+s, ph); if(bnd_yz) patch_yz<CFG, true>(c, st, x0, y0, z0, odd, tid, false); }
+		if(!last) { mbar_wait(bar_full+s1, ph1); if(bnd_yz) patch_yz<CFG, true>(c, st1, x0+TX, y0, z0, odd, tid, false); }
 		if(bnd_yz) consumer_bar((uint32_t)NC);
+		if(park&&kstrip>0u&&xt==1u) { // write the previous strip's periodic-x column
+			mbar_wait(bar_head, (kstrip-1u)&1u);
+			__syncwarp();
+			if(lx==0u) flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd);
+		}
 
 		const uint32_t x = (uint32_t)x0+lx, y = (uint32_t)y0+ly, z = (uint32_t)z0+lz;
-		const uint32_t fl2 = ((const uint16_t*)(st+Q*CFG::BOX_BYTES))[tid];
+		const uint64_t n = (uint64_t)x+(uint64_t)y*rowN+(uint64_t)z*planeN;
+		const uint32_t fl2 = ((const uint16_t*)(st+CFG::FLAG_OFF))[tid];
 		const uint32_t fl0 = fl2&0xFFu, fl1 = fl2>>8;
 		bool run0 = !((fl0&TYPE_BO)==TYPE_S||(fl0&TYPE_SU)==TYPE_G), run1 = !((fl1&TYPE_BO)==TYPE_S||(fl1&TYPE_SU)==TYPE_G);
 		if(edge) {
 			const bool in_yz = y<c.Ny&&z<c.Nz&&!((c.Dy>1u&&(y==0u||y>=c.Ny-1u))||(c.Dz>1u&&(z==0u||z>=c.Nz-1u)));
-			run0 = run0&&in_yz&&x<c.Nx&&x!=xskip&&!(c.Dx>1u&&(x==0u||x>=c.Nx-1u));
-			run1 = run1&&in_yz&&x+1u<c.Nx&&x+1u!=xskip&&!(c.Dx>1u&&(x+1u>=c.Nx-1u));
+			run0 = run0&&in_yz&&x<c.Nx&&!(c.Dx>1u&&(x==0u||x>=c.Nx-1u));
+			run1 = run1&&in_yz&&x+1u<c.Nx&&!(c.Dx>1u&&(x+1u>=c.Nx-1u));
 		}
+		if(EQ) { // rho/u of TYPE_E cells: into L2 one tile ahead
+			if(!last) {
+				const uint32_t fn = ((const uint16_t*)(st1+CFG::FLAG_OFF))[tid];
+				if((fn&0x0003u)==TYPE_E||(fn&0x0300u)==(TYPE_E<<8)) { const uint64_t m = n+(uint64_t)TX; prefetch_l2(c.rho+m); prefetch_l2(c.u+m); prefetch_l2(c.u+c.N+m); prefetch_l2(c.u+2ull*c.N+m); }
+			} else if(lx==0u) { // the next strip starts at the west face: its x = 0 cells
+				const uint32_t ns = strip+gridDim.x;
+				const uint64_t m = (uint64_t)((ns%tiles_y)*(uint32_t)TY+ly)*rowN+(uint64_t)((ns/tiles_y)*(uint32_t)TZ+lz)*planeN;
+				if(m<c.N) { prefetch_l2(c.rho+m); prefetch_l2(c.u+m); prefetch_l2(c.u+c.N+m); prefetch_l2(c.u+2ull*c.N+m); }
+			}
+		}
+		R* const box = (R*)st+tid; // the pair's word in box b is at byte offset box_off(b)
+		const uint32_t par = kstrip&1u;
+		uint8_t* const park_row = stage0+CFG::BOX_BYTES+(par*(uint32_t)CFG::ROWS+row)*(uint32_t)CFG::ES; // + box_off(b): this row's parked element of shifted box b
+		if(park&&first&&lx==0u) { // park column 0 of the x-shifted boxes (pre-collision values; only the strip's last tile touches them)
+#pragma unroll
+			for(int b=0; b<Q; b++) if(box_shifted(b)) *(E*)(park_row+CFG::box_off(b)) = PC::low(*(const R*)((const uint8_t*)box+CFG::box_off(b)));
+		}
+		if(park&&last) __syncwarp(); // the row-end lane reads what lane 0 parked
 		if(run0||run1) {
-			R* const box = (R*)st+tid; // the pair's word in box b is box[b*(TILE/2)]
-			// element right of the pair's word in an x-shifted box: the next word of the row, or column 0 of the same row in the next stage
-			uint8_t* const nxt = last_in_row ? (has_next ? st1+(size_t)row*TX*CFG::ES : (uint8_t*)box) : (uint8_t*)(box+1);
-			PairIn in;
+			// element right of the pair's word in an x-shifted box: the next word of the row, or column 0 of the same row in the next stage / the parked column
+			const uint32_t rowend_lx = last ? last_tx-2u : (uint32_t)(TX-2);
+			uint8_t* nxt = (uint8_t*)(box+1);
+			if(lx==rowend_lx) nxt = !last ? st1+(size_t)row*TX*CFG::ES : park ? park_row : wrap_x ? st+(size_t)row*TX*CFG::ES : (uint8_t*)box;
 			const uint32_t bo0 = fl0&TYPE_BO, bo1 = fl1&TYPE_BO;
-			in.e0 = EQ&&run0&&bo0==TYPE_E; in.e1 = EQ&&run1&&bo1==TYPE_E;
-			const uint64_t n = (uint64_t)x+(uint64_t)y*rowN+(uint64_t)z*planeN;
+			const bool e0 = EQ&&run0&&bo0==TYPE_E, e1 = EQ&&run1&&bo1==TYPE_E;
+			PairIn in;
 			in.zones = false;
 			if(has_zones) { // tile-uniform pre-test: does the tile reach into a relaxation zone? then gather the per-cell zone data now
 				const int xg0 = x0+c.Ox, yg0 = y0+c.Oy, zg1 = z0+TZ-1+c.Oz;
@@ -256,50 +352,55 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 					in.zones = in.zr0.nudge||in.zr0.sponge||in.zr1.nudge||in.zr1.sponge;
 				}
 			}
-			if(in.e0||in.e1) {
-				in.rho_e = mk2(in.e0 ? c.rho[n] : 1.0f, in.e1 ? c.rho[n+1ull] : 1.0f);
-				in.ux_e = mk2(in.e0 ? c.u[n] : 0.0f, in.e1 ? c.u[n+1ull] : 0.0f);
-				in.uy_e = mk2(in.e0 ? c.u[c.N+n] : 0.0f, in.e1 ? c.u[c.N+n+1ull] : 0.0f);
-				in.uz_e = mk2(in.e0 ? c.u[2ull*c.N+n] : 0.0f, in.e1 ? c.u[2ull*c.N+n+1ull] : 0.0f);
-			}
-			// load_f: box 0 -> f0, box 1+2k -> f_(2k+1), box 2+2k -> f_(2k+2); pairs 0,3,4,6,7 have c_x = +1
+			// load_f: box 0 -> f0, box 1+2k -> f_(2k+1), box 2+2k -> f_(2k+2)
 			f2 f[Q];
 #pragma unroll
 			for(int b=0; b<Q; b++) {
-				R w = box[b*(TILE/2)];
-				if(b==2||b==8||b==10||b==14||b==16) w = PC::shift_in(w, nxt+(size_t)b*CFG::BOX_BYTES);
+				R w = *(const R*)((const uint8_t*)box+CFG::box_off(b));
+				if(box_shifted(b)) w = PC::shift_in(w, nxt+CFG::box_off(b));
 				if(FAST&&P==P_FP16S) f[b] = PairCodec<P_FP16S>::dec_raw(*(const uint32_t*)&w); else f[b] = PC::dec(w);
 			}
 			PairOut out;
 			if(FAST) collide_fast2<FEAT>(c, a, in, f, scale, inv, out);
 			else collide_strict2<FEAT>(c, a, in, f, out);
+			if(e0||e1) { // TYPE_E lanes: f := feq(rho, u) of the boundary fields
+#pragma unroll 1
+				for(uint32_t l=0u; l<2u; l++) {
+					if(!(l==0u ? e0 : e1)) continue;
+					float feq[Q];
+					equilibrium_cell<FEAT>(c, a, n+(uint64_t)l, scale, feq);
+#pragma unroll
+					for(int b=0; b<Q; b++) { if(l==0u) f[b].v.x = feq[b]; else f[b].v.y = feq[b]; }
+				}
+			}
 			// store_f: f_i' goes to slot B (box 2+2k), f_i+1' to slot A (box 1+2k)
 			R nw[Q];
 #pragma unroll
 			for(int b=0; b<Q; b++) {
 				if(FAST&&P==P_FP16S) { const uint32_t r_ = PairCodec<P_FP16S>::enc_raw(f[b]); nw[b] = *(const R*)&r_; } else nw[b] = PC::enc(f[b]);
 			}
+			uint8_t* const bb = (uint8_t*)box;
 			if(run0&&run1) {
-				box[0] = nw[0];
+				*(R*)bb = nw[0];
 #pragma unroll
 				for(int k=0; k<9; k++) {
 					const int bA = 1+2*k, bB = 2+2*k;
-					box[bA*(TILE/2)] = nw[bB];
-					if(k==0||k==3||k==4||k==6||k==7) PC::shift_out((uint8_t*)(box+bB*(TILE/2)), nxt+(size_t)bB*CFG::BOX_BYTES, nw[bA], true, true);
-					else box[bB*(TILE/2)] = nw[bA];
+					*(R*)(bb+CFG::box_off(bA)) = nw[bB];
+					if(box_shifted(bB)) PC::shift_out_both(bb+CFG::box_off(bB), nxt+CFG::box_off(bB), nw[bA]);
+					else *(R*)(bb+CFG::box_off(bB)) = nw[bA];
 				}
 			} else {
-				box[0] = PC::mix(run0, run1, nw[0], box[0]);
+				*(R*)bb = PC::mix(run0, run1, nw[0], *(R*)bb);
 #pragma unroll
 				for(int k=0; k<9; k++) {
 					const int bA = 1+2*k, bB = 2+2*k;
-					box[bA*(TILE/2)] = PC::mix(run0, run1, nw[bB], box[bA*(TILE/2)]);
-					if(k==0||k==3||k==4||k==6||k==7) PC::shift_out((uint8_t*)(box+bB*(TILE/2)), nxt+(size_t)bB*CFG::BOX_BYTES, nw[bA], run0, run1);
-					else box[bB*(TILE/2)] = PC::mix(run0, run1, nw[bA], box[bB*(TILE/2)]);
+					*(R*)(bb+CFG::box_off(bA)) = PC::mix(run0, run1, nw[bB], *(R*)(bb+CFG::box_off(bA)));
+					if(box_shifted(bB)) PC::shift_out(bb+CFG::box_off(bB), nxt+CFG::box_off(bB), nw[bA], run0, run1);
+					else *(R*)(bb+CFG::box_off(bB)) = PC::mix(run0, run1, nw[bA], *(R*)(bb+CFG::box_off(bB)));
 				}
 			}
 			if(UF) {
-				const bool w0 = run0&&!in.e0, w1 = run1&&!in.e1;
+				const bool w0 = run0&&!e0, w1 = run1&&!e1;
 				if(w0&&w1) {
 					*(float2*)(c.rho+n) = out.rho.v; *(float2*)(c.u+n) = out.ux.v; *(float2*)(c.u+c.N+n) = out.uy.v; *(float2*)(c.u+2ull*c.N+n) = out.uz.v;
 				} else {
@@ -311,12 +412,17 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 
 		if(bnd_yz) { // write the wrapped elements back to their real addresses (TMA clips them)
 			consumer_bar((uint32_t)NC);
-			patch_yz<CFG, false>(c, st, x0, y0, z0, odd, tid);
+			patch_yz<CFG, false>(c, st, x0, y0, z0, odd, tid, park);
 		}
 		fence_async_smem(); // make this thread's shared-memory writes visible to the TMA store
 		mbar_arrive(bar_done+s);
 		s = s1; ph = ph1;
-		if(++xt==tiles_x) { xt = 0u; strip += gridDim.x; y0 = (int)(strip%tiles_y)*TY; z0 = (int)(strip/tiles_y)*TZ; }
+		if(last) { xt = 0u; py0 = y0; pz0 = z0; kstrip++; strip += gridDim.x; y0 = (int)(strip%tiles_y)*TY; z0 = (int)(strip/tiles_y)*TZ; } else xt++;
+	}
+	if(park&&kstrip>0u) { // the last strip's periodic-x column
+		mbar_wait(bar_head, (kstrip-1u)&1u);
+		__syncwarp();
+		if(lx==0u) flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd);
 	}
 }
 

@@ -96,9 +96,7 @@ __device__ __forceinline__ void zone_apply(const ZoneRef& r, const int nudge_ver
 	}
 }
 
-struct PairIn { // what the step needs to know about the two cells besides their DDFs
-	bool e0, e1; // TYPE_E cell (with EQUILIBRIUM_BOUNDARIES): rho/u are boundary data
-	f2 rho_e, ux_e, uy_e, uz_e; // stored rho/u of TYPE_E lanes (unused lanes: anything finite)
+struct PairIn { // what the step needs to know about the two cells besides their DDFs (TYPE_E lanes are redone by the caller, lbm_tile.cuh)
 	bool zones; // some lane lies in a relaxation zone
 	int nudge_vertical;
 	ZoneRef zr0, zr1;
@@ -170,7 +168,6 @@ template<uint32_t FEAT> __device__ __forceinline__ void collide_strict2(const Do
 	constexpr bool VF = (FEAT&F_VOLUME_FORCE)!=0u, SG = (FEAT&F_SUBGRID)!=0u;
 	f2 rho, ux, uy, uz;
 	rho_u_strict2(f, rho, ux, uy, uz);
-	if(in.e0||in.e1) { rho = sel2(in.e0, in.e1, in.rho_e, rho); ux = sel2(in.e0, in.e1, in.ux_e, ux); uy = sel2(in.e0, in.e1, in.uy_e, uy); uz = sel2(in.e0, in.e1, in.uz_e, uz); }
 	f2 Fin[Q];
 	if(VF) {
 		const f2 m2rho = sm(-2.0f, rho);
@@ -197,10 +194,6 @@ template<uint32_t FEAT> __device__ __forceinline__ void collide_strict2(const Do
 	} else {
 #pragma unroll
 		for(int i=0; i<Q; i++) f[i] = fma2(omw, f[i], fma2(w, feq[i], bc(0.0f)));
-	}
-	if(in.e0||in.e1) {
-#pragma unroll
-		for(int i=0; i<Q; i++) f[i] = sel2(in.e0, in.e1, feq[i], f[i]);
 	}
 }
 
@@ -234,11 +227,6 @@ template<uint32_t FEAT> __device__ __forceinline__ void collide_fast2(const Doma
 		ir = fma2(ir, fma2(-rho, ir, bc(1.0f)), ir); // one Newton step: full single precision
 		const f2 iri = inv*ir;
 		ux = mx*iri; uy = my*iri; uz = mz*iri;
-	}
-	if(in.e0||in.e1) {
-		rho = sel2(in.e0, in.e1, in.rho_e, rho); ux = sel2(in.e0, in.e1, in.ux_e, ux); uy = sel2(in.e0, in.e1, in.uy_e, uy); uz = sel2(in.e0, in.e1, in.uz_e, uz);
-		rhom1 = rho-bc(1.0f);
-		ir = rcp2(rho); ir = fma2(ir, fma2(-rho, ir, bc(1.0f)), ir);
 	}
 	Proj F; f2 uF3 = bc(0.0f);
 	if(VF) {
@@ -286,8 +274,6 @@ template<uint32_t FEAT> __device__ __forceinline__ void collide_fast2(const Doma
 	const f2 omw = bc(1.0f)-w;
 	const f2 hw = (0.5f*scale)*w; // S*w/2
 	const f2 wrs = (2.0f*hw)*rs, wre = (2.0f*hw)*re; // S*w*r
-	const bool any_e = in.e0||in.e1;
-	const f2 hs = bc(0.5f*scale), srs = scale*rs, sre = scale*re;
 	if(VF) {
 		const f2 c_tau = fma2(w, -0.5f, bc(1.0f));
 		const f2 kcs = (9.0f*WS/3.0f*scale)*c_tau, kce = (9.0f*WE/3.0f*scale)*c_tau; // S*kc/3
@@ -298,7 +284,6 @@ template<uint32_t FEAT> __device__ __forceinline__ void collide_fast2(const Doma
 			const f2 U = fma2(kc, fma2(Ak, ak, uF3), hw*ek);
 			const f2 V = fma2(k<3 ? wrs : wre, ak, kc*Ak);
 			f2 gi = fma2(omw, g[2*k+1], U+V), gj = fma2(omw, g[2*k+2], U-V);
-			if(any_e) { const f2 Ue = hs*ek, Ve = (k<3 ? srs : sre)*ak; gi = sel2(in.e0, in.e1, Ue+Ve, gi); gj = sel2(in.e0, in.e1, Ue-Ve, gj); } // TYPE_E: f := feq (FX/kernel.cpp:1747)
 			g[2*k+1] = gi; g[2*k+2] = gj;
 		}
 		g[0] = fma2(omw, g[0], fma2(2.0f*hw, feq0, ((9.0f*W0/3.0f*scale)*c_tau)*uF3));
@@ -309,12 +294,10 @@ template<uint32_t FEAT> __device__ __forceinline__ void collide_fast2(const Doma
 			const f2 ek = fma2(k<3 ? rs : re, fma2(ak, ak, c3), k<3 ? r1s : r1e);
 			const f2 U = hw*ek, V = (k<3 ? wrs : wre)*ak;
 			f2 gi = fma2(omw, g[2*k+1], U+V), gj = fma2(omw, g[2*k+2], U-V);
-			if(any_e) { const f2 Ue = hs*ek, Ve = (k<3 ? srs : sre)*ak; gi = sel2(in.e0, in.e1, Ue+Ve, gi); gj = sel2(in.e0, in.e1, Ue-Ve, gj); }
 			g[2*k+1] = gi; g[2*k+2] = gj;
 		}
 		g[0] = fma2(omw, g[0], (2.0f*hw)*feq0);
 	}
-	if(any_e) g[0] = sel2(in.e0, in.e1, scale*feq0, g[0]);
 }
 
 } // anonymous namespace

@@ -130,7 +130,6 @@ cudaError_t enqueue_step(luw_domain* d, const luw::StepArgs& a) {
 	d->launches++;
 	if(e!=cudaSuccess) return e;
 	if(d->ktiming) { e = cudaEventRecord(d->kev[d->kev_used+1u], d->stream); if(e!=cudaSuccess) return e; d->kev_used += 2u; }
-	if(d->tiled&&d->c.Dx==1u) { e = d->ks->stream_collide_xcol(d->c, a, d->stream); d->launches++; } // the periodic column x = Nx-1
 	return e;
 }
 
