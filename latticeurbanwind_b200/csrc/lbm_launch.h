@@ -4,7 +4,7 @@
 #include "lbm_common.cuh"
 
 namespace luw {
-struct TileMaps { CUtensorMap fi, flags; }; // TMA descriptors of the DDF array (4-D: x, y, z, slot) and the flag array (3-D) with the tile as box
+struct TileMaps { CUtensorMap fi, fiA, flags; }; // TMA descriptors: DDF array (4-D: x, y, z, slot) with one tile as box; the same with a box of nine slots at element stride 2; flag array (3-D)
 struct TileShape { int tx, ty, tz; };
 struct KernelSet { // one per arithmetic mode; every function enqueues exactly one kernel on `s` and returns the CUDA launch status
 	cudaError_t (*initialize)(const DomainConst& c, cudaStream_t s);

@@ -70,14 +70,28 @@ __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void tma_wait_all1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); } // all but the most recent group complete
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void consumer_bar(const uint32_t nthreads) { asm volatile("bar.sync 1, %0;" :: "r"(nthreads) : "memory"); }
+__device__ __forceinline__ bool elect_one() { // one lane of the (converged) warp
+	uint32_t p;
+	asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(p));
+	return p!=0u;
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
+#ifdef LUW_TRACE // development aid: per-tile timestamps of CTA `LUW_TRACE` (producer: done seen / stores committed / smem read / loads issued; consumer warp 0: start / end)
+__device__ long long g_trace[6][2048];
+#define TRACE(slot, q) do { if(blockIdx.x==(LUW_TRACE)&&(q)<2048u) g_trace[slot][q] = clock64(); } while(0)
+#else
+#define TRACE(slot, q) do {} while(0)
+#endif
+
 // ------------------------------------------------------------------ geometry of a tile
-// shared-memory box order inside a stage: box 0 = f0; box 1+2k = slot A of pair k (own cell: holds f_i, receives f_i+1);
-// box 2+2k = slot B of pair k (neighbour n+c_i: holds f_i+1, receives f_i). Pairs 0,3,4,6,7 have c_x = +1: their B boxes (2,8,10,14,16)
-// are the x-shifted ones; each is followed by a 128-byte pad (stage 0's pads park the periodic-x column, see above).
-__host__ __device__ constexpr bool box_shifted(const int b) { return b==2||b==8||b==10||b==14||b==16; }
-__host__ __device__ constexpr int pads_before(const int b) { return (b>2)+(b>8)+(b>10)+(b>14)+(b>16); }
+// Box b of a stage: b = 0 is f0; b = 1+2k is slot A of pair k (own cell: holds f_i, receives f_i+1); b = 2+2k is slot B of pair k
+// (neighbour n+c_i: holds f_i+1, receives f_i). In shared memory the nine A boxes are contiguous (they are moved by ONE TMA operation that
+// walks the slot dimension with element stride 2), followed by the nine B boxes. Pairs 0,3,4,6,7 have c_x = +1: their B boxes are the
+// x-shifted ones; each is followed by a 128-byte pad (stage 0's pads park the periodic-x column, see above).
+__host__ __device__ constexpr bool pair_shifted(const int k) { return k==0||k==3||k==4||k==6||k==7; }
+__host__ __device__ constexpr bool box_shifted(const int b) { return b>0&&(b&1)==0&&pair_shifted((b-2)/2); }
+__host__ __device__ constexpr int pads_before_pair(const int k) { return (k>0)+(k>3)+(k>4)+(k>6)+(k>7); }
 template<int P_, int TX_, int TY_, int TZ_, int STAGES_, int CTAS_> struct TileCfg {
 	static constexpr int P = P_, TX = TX_, TY = TY_, TZ = TZ_, STAGES = STAGES_, CTAS_PER_SM = CTAS_;
 	static constexpr int TILE = TX*TY*TZ, ROWS = TY*TZ, CONSUMERS = TILE/2, THREADS = CONSUMERS+32;
@@ -87,8 +101,10 @@ template<int P_, int TX_, int TY_, int TZ_, int STAGES_, int CTAS_> struct TileC
 	static constexpr int STAGE_BYTES = FLAG_OFF+TILE; // 19 DDF boxes + 5 pads + the flag box
 	static constexpr int LOAD_BYTES = Q*BOX_BYTES+TILE; // what one stage's TMA loads deliver
 	static constexpr int SMEM_BYTES = STAGES*STAGE_BYTES+(2*STAGES+1)*8+128; // + mbarriers, + slack for 128 B alignment of the first stage
-	__host__ __device__ static constexpr int box_off(const int b) { return b*BOX_BYTES+PAD*pads_before(b); }
-	static_assert(TX==64, "one warp per tile row"); // the periodic-x parking relies on a row being handled by a single warp
+	__host__ __device__ static constexpr int box_off(const int b) {
+		return b==0 ? 0 : (b&1) ? (1+(b-1)/2)*BOX_BYTES : (10+(b-2)/2)*BOX_BYTES+PAD*pads_before_pair((b-2)/2);
+	}
+	static_assert(TX%64==0&&TX<=256, "rows are whole warps; TMA boxes are at most 256 elements wide");
 	static_assert(CONSUMERS%32==0&&BOX_BYTES%128==0&&TILE%128==0&&2*ROWS*ES<=PAD, "tile shape");
 };
 // pair k = (i-1)/2, i odd: c_i
@@ -183,11 +199,9 @@ template<class CFG> __device__ __noinline__ void flush_wrap(const DomainConst& c
 }
 
 // TYPE_E cell: rho/u are boundary data; Coriolis shift, clamp, f := feq (FX/kernel.cpp:1503-1522,1686-1716,1747). Scalar, in the reference's
-// operation order (relaxation zones never apply to TYPE_E cells, FX/kernel.cpp:1524). Writes lane `lane` of f[] in units of `scale`.
-template<uint32_t FEAT> __device__ __forceinline__ void equilibrium_cell(const DomainConst& c, const StepArgs& a, const uint64_t n, const float scale, float* feq) {
+// operation order (relaxation zones never apply to TYPE_E cells, FX/kernel.cpp:1524). feq[] in units of `scale`.
+template<uint32_t FEAT> __device__ __forceinline__ void equilibrium_cell(const DomainConst& c, const StepArgs& a, const float rhon, float uxn, float uyn, float uzn, const float scale, float* feq) {
 	constexpr bool VF = (FEAT&F_VOLUME_FORCE)!=0u;
-	const float rhon = c.rho[n];
-	float uxn = c.u[n], uyn = c.u[c.N+n], uzn = c.u[2ull*c.N+n];
 	if(VF) {
 		float fxn, fyn, fzn;
 		luw_force(c, a, 0u, 0u, 0u, TYPE_E, false, rhon, uxn, uyn, uzn, fxn, fyn, fzn);
@@ -235,21 +249,24 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 	const bool park = wrap_x&&tiles_x>=2u; // ... and the wrapped column lives in another tile than the last one
 
 	if(tid>=(uint32_t)NC) { // ---------------------------------------------------------------- producer warp: TMA loads and stores
-		if(tid!=(uint32_t)NC) return;
+		// The whole warp walks the loops (uniform control flow keeps coordinates and addresses in uniform registers); one elected lane issues.
+		const bool leader = elect_one();
 		uint32_t lstrip = blockIdx.x, lxt = 0u; // tile the next load belongs to
 		const auto issue_loads = [&](const uint32_t q) {
 			const int s = (int)(q%(uint32_t)S);
 			const int x0 = (int)lxt*TX, y0 = (int)(lstrip%tiles_y)*TY, z0 = (int)(lstrip/tiles_y)*TZ;
 			uint8_t* st = stage0+(size_t)s*CFG::STAGE_BYTES;
-			mbar_expect_tx(bar_full+s, (uint32_t)CFG::LOAD_BYTES);
-			tma_load_3d(st+CFG::FLAG_OFF, &maps.flags, bar_full+s, x0, y0, z0);
-			tma_load_4d(st, &maps.fi, bar_full+s, x0, y0, z0, 0);
+			if(leader) {
+				mbar_expect_tx(bar_full+s, (uint32_t)CFG::LOAD_BYTES);
+				tma_load_3d(st+CFG::FLAG_OFF, &maps.flags, bar_full+s, x0, y0, z0);
+				tma_load_4d(st, &maps.fi, bar_full+s, x0, y0, z0, 0);
+				tma_load_4d(st+CFG::box_off(1), &maps.fiA, bar_full+s, x0, y0, z0, odd ? 1 : 2); // the nine A slots: odd ? 1,3,..,17 : 2,4,..,18
 #pragma unroll
-			for(int k=0; k<9; k++) {
-				int cx, cy, cz; pair_shift(k, cx, cy, cz);
-				const int i = 2*k+1;
-				tma_load_4d(st+CFG::box_off(1+2*k), &maps.fi, bar_full+s, x0, y0, z0, odd ? i : i+1);
-				tma_load_4d(st+CFG::box_off(2+2*k), &maps.fi, bar_full+s, x0, y0+cy, z0+cz, odd ? i+1 : i); // x shift applied by the readers
+				for(int k=0; k<9; k++) {
+					int cx, cy, cz; pair_shift(k, cx, cy, cz);
+					const int i = 2*k+1;
+					tma_load_4d(st+CFG::box_off(2+2*k), &maps.fi, bar_full+s, x0, y0+cy, z0+cz, odd ? i+1 : i); // x shift applied by the readers
+				}
 			}
 			if(++lxt==tiles_x) { lxt = 0u; lstrip += gridDim.x; }
 		};
@@ -259,23 +276,32 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 		for(uint32_t q=0u; q<my_tiles; q++) {
 			const int s = (int)(q%(uint32_t)S);
 			mbar_wait(bar_done+s, (q/(uint32_t)S)&1u);
+			if(leader) TRACE(0, q);
 			const int x0 = (int)sxt*TX, y0 = (int)(sstrip%tiles_y)*TY, z0 = (int)(sstrip/tiles_y)*TZ;
 			const uint8_t* st = stage0+(size_t)s*CFG::STAGE_BYTES;
-			tma_store_4d(&maps.fi, st, x0, y0, z0, 0);
-#pragma unroll
-			for(int k=0; k<9; k++) {
-				int cx, cy, cz; pair_shift(k, cx, cy, cz);
-				const int i = 2*k+1;
-				tma_store_4d(&maps.fi, st+CFG::box_off(1+2*k), x0, y0, z0, odd ? i : i+1);
-				if(!box_by_threads<CFG>(c, cy, cz, y0, z0)) tma_store_4d(&maps.fi, st+CFG::box_off(2+2*k), x0, y0+cy, z0+cz, odd ? i+1 : i);
-			}
-			tma_commit();
-			if(q+(uint32_t)S<my_tiles) { tma_wait_read0(); issue_loads(q+(uint32_t)S); } // the stage may be refilled once TMA has read it
+			const bool inner = y0>0&&z0>0&&y0+TY<=(int)c.Ny&&z0+TZ<=(int)c.Nz; // every box lies inside the lattice: all 19 go through TMA
 			const bool last_of_strip = sxt+1u==tiles_x;
-			if(park&&last_of_strip) { tma_wait_all1(); mbar_arrive(bar_head); } // the strip's first tile is in global memory: its column 0 may be overwritten
+			if(leader) {
+				tma_store_4d(&maps.fi, st, x0, y0, z0, 0);
+				tma_store_4d(&maps.fiA, st+CFG::box_off(1), x0, y0, z0, odd ? 1 : 2);
+#pragma unroll
+				for(int k=0; k<9; k++) {
+					int cx, cy, cz; pair_shift(k, cx, cy, cz);
+					const int i = 2*k+1;
+					if(inner||!box_by_threads<CFG>(c, cy, cz, y0, z0)) tma_store_4d(&maps.fi, st+CFG::box_off(2+2*k), x0, y0+cy, z0+cz, odd ? i+1 : i);
+				}
+				tma_commit();
+				TRACE(1, q);
+				if(q+(uint32_t)S<my_tiles) tma_wait_read0(); // the stage may be refilled once TMA has read it
+				TRACE(2, q);
+			}
+			__syncwarp();
+			if(q+(uint32_t)S<my_tiles) issue_loads(q+(uint32_t)S);
+			if(leader) TRACE(3, q);
+			if(park&&last_of_strip&&leader) { tma_wait_all1(); mbar_arrive(bar_head); } // the strip's first tile is in global memory: its column 0 may be overwritten
 			if(last_of_strip) { sxt = 0u; sstrip += gridDim.x; } else sxt++;
 		}
-		tma_wait_all0();
+		if(leader) tma_wait_all0();
 		return;
 	}
 
@@ -306,6 +332,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 			if(lx==0u) flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd);
 		}
 
+		if(tid==0u) TRACE(4, q);
 		const uint32_t x = (uint32_t)x0+lx, y = (uint32_t)y0+ly, z = (uint32_t)z0+lz;
 		const uint64_t n = (uint64_t)x+(uint64_t)y*rowN+(uint64_t)z*planeN;
 		const uint32_t fl2 = ((const uint16_t*)(st+CFG::FLAG_OFF))[tid];
@@ -333,7 +360,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 #pragma unroll
 			for(int b=0; b<Q; b++) if(box_shifted(b)) *(E*)(park_row+CFG::box_off(b)) = PC::low(*(const R*)((const uint8_t*)box+CFG::box_off(b)));
 		}
-		if(park&&last) __syncwarp(); // the row-end lane reads what lane 0 parked
+		if(park&&first) { if(TX==64) __syncwarp(); else consumer_bar((uint32_t)NC); } // the row-end lane (possibly in another warp) reads what the row's first lane parked
 		if(run0||run1) {
 			// element right of the pair's word in an x-shifted box: the next word of the row, or column 0 of the same row in the next stage / the parked column
 			const uint32_t rowend_lx = last ? last_tx-2u : (uint32_t)(TX-2);
@@ -352,6 +379,9 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 					in.zones = in.zr0.nudge||in.zr0.sponge||in.zr1.nudge||in.zr1.sponge;
 				}
 			}
+			float4 eb0 = make_float4(1.0f, 0.0f, 0.0f, 0.0f), eb1 = eb0; // boundary rho/u of TYPE_E lanes: requested before the DDFs are touched, used after the collision
+			if(e0) eb0 = make_float4(c.rho[n], c.u[n], c.u[c.N+n], c.u[2ull*c.N+n]);
+			if(e1) eb1 = make_float4(c.rho[n+1ull], c.u[n+1ull], c.u[c.N+n+1ull], c.u[2ull*c.N+n+1ull]);
 			// load_f: box 0 -> f0, box 1+2k -> f_(2k+1), box 2+2k -> f_(2k+2)
 			f2 f[Q];
 #pragma unroll
@@ -368,7 +398,8 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 				for(uint32_t l=0u; l<2u; l++) {
 					if(!(l==0u ? e0 : e1)) continue;
 					float feq[Q];
-					equilibrium_cell<FEAT>(c, a, n+(uint64_t)l, scale, feq);
+					const float4 eb = l==0u ? eb0 : eb1;
+					equilibrium_cell<FEAT>(c, a, eb.x, eb.y, eb.z, eb.w, scale, feq);
 #pragma unroll
 					for(int b=0; b<Q; b++) { if(l==0u) f[b].v.x = feq[b]; else f[b].v.y = feq[b]; }
 				}
@@ -415,14 +446,14 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 			patch_yz<CFG, false>(c, st, x0, y0, z0, odd, tid, park);
 		}
 		fence_async_smem(); // make this thread's shared-memory writes visible to the TMA store
+		if(tid==0u) TRACE(5, q);
 		mbar_arrive(bar_done+s);
 		s = s1; ph = ph1;
 		if(last) { xt = 0u; py0 = y0; pz0 = z0; kstrip++; strip += gridDim.x; y0 = (int)(strip%tiles_y)*TY; z0 = (int)(strip/tiles_y)*TZ; } else xt++;
 	}
 	if(park&&kstrip>0u) { // the last strip's periodic-x column
 		mbar_wait(bar_head, (kstrip-1u)&1u);
-		__syncwarp();
-		if(lx==0u) flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd);
+		if(lx==last_tx-2u) flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd);
 	}
 }
 

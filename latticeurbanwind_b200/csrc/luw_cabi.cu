@@ -99,19 +99,29 @@ void setup_tiles(luw_domain* d) {
 	const char* off = getenv("LUW_NO_TILE");
 	if(off&&off[0]=='1') return;
 	const char* var = getenv("LUW_TILE_VARIANT");
-	d->tile_variant = var ? atoi(var) : 0;
-	luw::TileShape sh;
-	if(!d->ks->tile_shape(d->c.precision, d->c.features, d->tile_variant, &sh)) return;
+	const int want = var ? atoi(var) : 0;
 	const luw::DomainConst& c = d->c;
-	if(c.Nx%16u!=0u||c.Nx<(uint32_t)sh.tx) return;
+	if(c.Nx%16u!=0u) return;
 	encode_tiled_fn enc = get_encode_tiled();
 	if(!enc) return;
+	luw::TileShape sh;
+	bool found = false;
+	for(int v : { want, 2, 0, 1 }) { // the requested variant, else one whose tile is not wider than the lattice
+		if(d->ks->tile_shape(c.precision, c.features, v, &sh)&&c.Nx>=(uint32_t)sh.tx) { d->tile_variant = v; found = true; break; }
+	}
+	if(!found) return;
 	const cuuint64_t es = d->ddf_size;
+	const CUtensorMapDataType dt = es==4u ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16;
 	const cuuint64_t dims4[4] = { c.Nx, c.Ny, c.Nz, 19u };
+	const cuuint64_t dims4A[4] = { c.Nx, c.Ny, c.Nz, 20u }; // slot 19 does not exist and is never traversed (stride 2 from slot 1 or 2 ends at 17 / 18)
 	const cuuint64_t str4[3] = { c.Nx*es, (cuuint64_t)c.Nx*c.Ny*es, c.N*es };
 	const cuuint32_t box4[4] = { (cuuint32_t)sh.tx, (cuuint32_t)sh.ty, (cuuint32_t)sh.tz, 1u };
+	const cuuint32_t box4A[4] = { (cuuint32_t)sh.tx, (cuuint32_t)sh.ty, (cuuint32_t)sh.tz, 18u }; // 9 slots at element stride 2
 	const cuuint32_t one4[4] = { 1u, 1u, 1u, 1u };
-	if(enc(&d->maps.fi, es==4u ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 4u, c.fi, dims4, str4, box4, one4,
+	const cuuint32_t strideA[4] = { 1u, 1u, 1u, 2u };
+	if(enc(&d->maps.fi, dt, 4u, c.fi, dims4, str4, box4, one4,
+		CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)!=CUDA_SUCCESS) return;
+	if(enc(&d->maps.fiA, dt, 4u, c.fi, dims4A, str4, box4A, strideA,
 		CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)!=CUDA_SUCCESS) return;
 	const cuuint64_t dims3[3] = { c.Nx, c.Ny, c.Nz };
 	const cuuint64_t str3[2] = { c.Nx, (cuuint64_t)c.Nx*c.Ny };
