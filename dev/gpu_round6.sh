@@ -1,0 +1,4 @@
+#!/bin/bash
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+for v in 0 2; do LUW_TILE_VARIANT=$v QB_PRECS=1 timeout 600 python tests/quickbench_dev.py 2>&1 | grep "arith=1\|variant"; done
+for w in channel512_fp16s urban_fp16s urban_fp16s_uf channel512_fp32; do timeout 300 python bench.py --no-cpu --no-e2e --steps 100 --workload $w | python -c "import json,sys; d=json.load(sys.stdin); print('$w', round(d['value']), round(d['ms_per_step'],3), round(d['roofline']['frac'],3), d['clocks'])"; done

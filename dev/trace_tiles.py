@@ -8,14 +8,19 @@ from latticeurbanwind_b200.domain import Domain
 prec = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 feat = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 Nx, Ny, Nz = 512, 512, 256
-with Domain(Nx, Ny, Nz, precision=prec, features=feat, w=cases.relaxation_rate(1 / 6), arith=1) as d:
-    d.rho[:] = 1; d.u[:] = 0; d.u[:Nx * Ny * Nz] = 0.05
+case = sys.argv[3] if len(sys.argv) > 3 else "periodic_box"
+zones = dict(downstream_face=2, buffer_N=16, buffer_inv_tau=0.01, buffer_nudge_vertical=1, sponge_N=20, sponge_inv_tau=0.02)
+with Domain(Nx, Ny, Nz, precision=prec, features=feat, w=cases.relaxation_rate(1e-6 if feat & 8 else 1 / 6), arith=1, **zones) as d:
+    cases.block_case(case, (Nx, Ny, Nz), out=(d.flags, d.rho, d.u))
+    d.omega = (0, 5.6e-6, 4.7e-6)
     d.upload_all(); d.t = 1; d.enqueue_initialize(); d.t = 0
     d.run_steps(5); d.finish_queue()
     d.timer_begin(); d.run_steps(1); ms = d.timer_end()
     buf = np.zeros((6, 2048), np.int64)
     rc = A.lib().luw_debug_trace(buf.ctypes.data_as(C.c_void_p))
     print("rc", rc, "step ms", ms)
+    ns, cyc = buf[2][2047] - buf[0][2047], buf[3][2047] - buf[1][2047]
+    print(f"traced CTA alive {ns/1e6:.4f} ms = {cyc} cycles -> SM clock {cyc/max(ns,1)*1e3:.0f} MHz")
     t0 = buf[4][0]
     n = int((buf[4] > 0).sum())
     print("tiles traced:", n)

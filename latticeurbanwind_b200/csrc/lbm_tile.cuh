@@ -52,6 +52,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, const uint32_t parity) {
 	uint32_t spins = 0u;
 	while(!mbar_try(b, parity)) if(++spins>(1u<<24)) __trap(); // a lost arrival must abort the launch, not hang the device
 }
+// producer-side wait: polls with a growing sleep in between, so that the idle warp does not take issue slots from the consumers
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* b, const uint32_t parity) {
+	uint32_t ns = 64u, spins = 0u;
+	while(!mbar_try(b, parity)) {
+		__nanosleep(ns);
+		if(ns<1024u) ns <<= 1;
+		if(++spins>(1u<<22)) __trap();
+	}
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, const int c0, const int c1, const int c2, const int c3) {
 	asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
 		:: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
@@ -67,7 +76,19 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_wait_all1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); } // all but the most recent group complete
+// all but the `n` most recent groups complete (the operand is an immediate; a smaller n than asked for only waits for more)
+__device__ __forceinline__ void tma_wait_all_but(const uint32_t n) {
+	switch(n<7u ? n : 7u) {
+		case 0u: asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); break;
+		case 1u: asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); break;
+		case 2u: asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); break;
+		case 3u: asm volatile("cp.async.bulk.wait_group 3;" ::: "memory"); break;
+		case 4u: asm volatile("cp.async.bulk.wait_group 4;" ::: "memory"); break;
+		case 5u: asm volatile("cp.async.bulk.wait_group 5;" ::: "memory"); break;
+		case 6u: asm volatile("cp.async.bulk.wait_group 6;" ::: "memory"); break;
+		default: asm volatile("cp.async.bulk.wait_group 7;" ::: "memory"); break;
+	}
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void consumer_bar(const uint32_t nthreads) { asm volatile("bar.sync 1, %0;" :: "r"(nthreads) : "memory"); }
 __device__ __forceinline__ bool elect_one() { // one lane of the (converged) warp
@@ -79,8 +100,11 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 
 #ifdef LUW_TRACE // development aid: per-tile timestamps of CTA `LUW_TRACE` (producer: done seen / stores committed / smem read / loads issued; consumer warp 0: start / end)
 __device__ long long g_trace[6][2048];
-#define TRACE(slot, q) do { if(blockIdx.x==(LUW_TRACE)&&(q)<2048u) g_trace[slot][q] = clock64(); } while(0)
+#define TRACE(slot, q) do { if(blockIdx.x==(LUW_TRACE)&&(q)<2040u) g_trace[slot][q] = clock64(); } while(0)
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TRACE_CLK(i) do { if(blockIdx.x==(LUW_TRACE)&&threadIdx.x==0u) { g_trace[i][2047] = gtimer(); g_trace[i+1][2047] = clock64(); } } while(0)
 #else
+#define TRACE_CLK(i) do {} while(0)
 #define TRACE(slot, q) do {} while(0)
 #endif
 
@@ -233,6 +257,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 	uint64_t* const bar_head = bar_done+S;
 
 	const uint32_t tid = threadIdx.x;
+	TRACE_CLK(0);
 	if(tid==0u) {
 		for(int s=0; s<S; s++) { mbar_init(bar_full+s, 1u); mbar_init(bar_done+s, (uint32_t)NC); }
 		mbar_init(bar_head, 1u);
@@ -275,7 +300,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 		uint32_t sstrip = blockIdx.x, sxt = 0u; // tile the next store belongs to
 		for(uint32_t q=0u; q<my_tiles; q++) {
 			const int s = (int)(q%(uint32_t)S);
-			mbar_wait(bar_done+s, (q/(uint32_t)S)&1u);
+			mbar_wait_backoff(bar_done+s, (q/(uint32_t)S)&1u);
 			if(leader) TRACE(0, q);
 			const int x0 = (int)sxt*TX, y0 = (int)(sstrip%tiles_y)*TY, z0 = (int)(sstrip/tiles_y)*TZ;
 			const uint8_t* st = stage0+(size_t)s*CFG::STAGE_BYTES;
@@ -298,7 +323,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 			__syncwarp();
 			if(q+(uint32_t)S<my_tiles) issue_loads(q+(uint32_t)S);
 			if(leader) TRACE(3, q);
-			if(park&&last_of_strip&&leader) { tma_wait_all1(); mbar_arrive(bar_head); } // the strip's first tile is in global memory: its column 0 may be overwritten
+			if(park&&last_of_strip&&leader) { tma_wait_all_but(tiles_x-1u); mbar_arrive(bar_head); } // the strip's first tile (tiles_x-1 groups ago) is in global memory: its column 0 may be overwritten
 			if(last_of_strip) { sxt = 0u; sstrip += gridDim.x; } else sxt++;
 		}
 		if(leader) tma_wait_all0();
@@ -379,9 +404,6 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 					in.zones = in.zr0.nudge||in.zr0.sponge||in.zr1.nudge||in.zr1.sponge;
 				}
 			}
-			float4 eb0 = make_float4(1.0f, 0.0f, 0.0f, 0.0f), eb1 = eb0; // boundary rho/u of TYPE_E lanes: requested before the DDFs are touched, used after the collision
-			if(e0) eb0 = make_float4(c.rho[n], c.u[n], c.u[c.N+n], c.u[2ull*c.N+n]);
-			if(e1) eb1 = make_float4(c.rho[n+1ull], c.u[n+1ull], c.u[c.N+n+1ull], c.u[2ull*c.N+n+1ull]);
 			// load_f: box 0 -> f0, box 1+2k -> f_(2k+1), box 2+2k -> f_(2k+2)
 			f2 f[Q];
 #pragma unroll
@@ -391,9 +413,24 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 				if(FAST&&P==P_FP16S) f[b] = PairCodec<P_FP16S>::dec_raw(*(const uint32_t*)&w); else f[b] = PC::dec(w);
 			}
 			PairOut out;
-			if(FAST) collide_fast2<FEAT>(c, a, in, f, scale, inv, out);
-			else collide_strict2<FEAT>(c, a, in, f, out);
-			if(e0||e1) { // TYPE_E lanes: f := feq(rho, u) of the boundary fields
+			float4 eb0 = make_float4(1.0f, 0.0f, 0.0f, 0.0f), eb1 = eb0; // boundary rho/u of TYPE_E lanes (prefetched into L2 one tile ago)
+			if(FAST) {
+				if(EQ&&__any_sync(__activemask(), e0||e1)) { // warp-uniform: the common path carries no TYPE_E code
+					if(e0) eb0 = make_float4(c.rho[n], c.u[n], c.u[c.N+n], c.u[2ull*c.N+n]);
+					if(e1) eb1 = make_float4(c.rho[n+1ull], c.u[n+1ull], c.u[c.N+n+1ull], c.u[2ull*c.N+n+1ull]);
+					in.e0 = e0; in.e1 = e1;
+					in.rho_e = mk2(eb0.x, eb1.x); in.ux_e = mk2(eb0.y, eb1.y); in.uy_e = mk2(eb0.z, eb1.z); in.uz_e = mk2(eb0.w, eb1.w);
+					collide_fast2<FEAT, true>(c, a, in, f, scale, inv, out);
+				} else {
+					in.e0 = false; in.e1 = false;
+					collide_fast2<FEAT, false>(c, a, in, f, scale, inv, out);
+				}
+			} else {
+				if(e0) eb0 = make_float4(c.rho[n], c.u[n], c.u[c.N+n], c.u[2ull*c.N+n]);
+				if(e1) eb1 = make_float4(c.rho[n+1ull], c.u[n+1ull], c.u[c.N+n+1ull], c.u[2ull*c.N+n+1ull]);
+				collide_strict2<FEAT>(c, a, in, f, out);
+			}
+			if(!FAST&&(e0||e1)) { // TYPE_E lanes, bit-exact path: f := feq(rho, u) of the boundary fields in scalar code
 #pragma unroll 1
 				for(uint32_t l=0u; l<2u; l++) {
 					if(!(l==0u ? e0 : e1)) continue;
@@ -451,6 +488,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 		s = s1; ph = ph1;
 		if(last) { xt = 0u; py0 = y0; pz0 = z0; kstrip++; strip += gridDim.x; y0 = (int)(strip%tiles_y)*TY; z0 = (int)(strip/tiles_y)*TZ; } else xt++;
 	}
+	TRACE_CLK(2);
 	if(park&&kstrip>0u) { // the last strip's periodic-x column
 		mbar_wait(bar_head, (kstrip-1u)&1u);
 		if(lx==last_tx-2u) flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd);

@@ -96,7 +96,9 @@ __device__ __forceinline__ void zone_apply(const ZoneRef& r, const int nudge_ver
 	}
 }
 
-struct PairIn { // what the step needs to know about the two cells besides their DDFs (TYPE_E lanes are redone by the caller, lbm_tile.cuh)
+struct PairIn { // what the step needs to know about the two cells besides their DDFs
+	bool e0, e1; // FAST only: lane holds a TYPE_E cell -> rho/u are the boundary values below and f := feq (STRICT redoes such lanes in scalar code, lbm_tile.cuh)
+	f2 rho_e, ux_e, uy_e, uz_e;
 	bool zones; // some lane lies in a relaxation zone
 	int nudge_vertical;
 	ZoneRef zr0, zr1;
@@ -201,9 +203,10 @@ template<uint32_t FEAT> __device__ __forceinline__ void collide_strict2(const Do
 // g[19] = S*f (S = `scale`: 2^15 for FP16S so that the stored half is used as is; 1 otherwise), `inv` = 1/S. In and out in scaled units.
 // For each pair of opposite directions (i, i+1), i odd, with a = 3 c_i.u, A = c_i.F, r = w_i*rho:
 //   feq_i + feq_i+1 = e = r*(a^2 - 3u^2) + 2 w_i (rho-1)     feq_i - feq_i+1 = 2 r a
-//   the Smagorinsky tensor only needs n = (f_i + f_i+1) - e  (c_i c_i is the same for both members)
 //   post-collision: f_i' = (1-w) f_i + U + V,  f_i+1' = (1-w) f_i+1 + U - V,  U = w e/2 + kc (A a/3 + uF),  V = w r a + kc A/3,  kc = 9 w_i (1 - w/2)
-// Per-pair quantities (a, A, e) are recomputed where they are used instead of being kept in registers: the kernel is register-bound.
+// The Smagorinsky tensor H = sum_i c_i c_i (f_i - feq_i) is taken from the second moments of the DDFs instead of from 18 differences:
+//   sum c c feq = rho (u u + 1/3)  exactly for this equilibrium, and the DDFs are stored shifted by -w_i (sum c c w = 1/3), hence
+//   H_ab = sum c_a c_b f_i  -  rho u_a u_b  -  (rho-1)/3 delta_ab.   Density, momentum and second moments are accumulated in one pass over the pairs.
 struct Proj { f2 x, y, z; }; // a vector whose projections on the 9 pair directions are needed
 __device__ __forceinline__ f2 proj(const Proj& v, const int k) { // pairs: 0:+x 1:+y 2:+z 3:+x+y 4:+x+z 5:+y+z 6:+x-y 7:+x-z 8:+y-z
 	switch(k) {
@@ -212,21 +215,41 @@ __device__ __forceinline__ f2 proj(const Proj& v, const int k) { // pairs: 0:+x 
 		case 6: return v.x-v.y; case 7: return v.x-v.z; default: return v.y-v.z;
 	}
 }
-template<uint32_t FEAT> __device__ __forceinline__ void collide_fast2(const DomainConst& c, const StepArgs& a, const PairIn& in, f2* g, const float scale, const float inv, PairOut& out) {
+// HAS_E: some lane of the warp holds a TYPE_E cell (the caller branches warp-uniformly, so that the common path carries no selects)
+template<uint32_t FEAT, bool HAS_E> __device__ __forceinline__ void collide_fast2(const DomainConst& c, const StepArgs& a, const PairIn& in, f2* g, const float scale, const float inv, PairOut& out) {
 	constexpr bool VF = (FEAT&F_VOLUME_FORCE)!=0u, SG = (FEAT&F_SUBGRID)!=0u;
 	f2 rho, rhom1, ir, ux, uy, uz;
-	{ // moments from pair sums and differences
+	f2 Pxx, Pyy, Pzz, Pxy, Pxz, Pyz; // second moments of the scaled, shifted DDFs (SG only)
+	{ // one pass over the pairs: s = f_i + f_i+1 feeds density and second moments, d = f_i - f_i+1 feeds momentum
 		f2 R = g[0], mx, my, mz;
-		{ const f2 d0 = g[1]-g[2], d3 = g[7]-g[8], d4 = g[9]-g[10], d6 = g[13]-g[14], d7 = g[15]-g[16];
-		  const f2 d1 = g[3]-g[4], d5 = g[11]-g[12], d8 = g[17]-g[18], d2 = g[5]-g[6];
-		  mx = ((d0+d3)+(d4+d6))+d7; my = ((d1+d3)+(d5-d6))+d8; mz = ((d2+d4)+(d5-d7))-d8; }
-		R = ((R+(g[1]+g[2]))+((g[3]+g[4])+(g[5]+g[6])))+(((g[7]+g[8])+(g[9]+g[10]))+((g[11]+g[12])+(g[13]+g[14])))+((g[15]+g[16])+(g[17]+g[18]));
+#pragma unroll
+		for(int k=0; k<9; k++) {
+			const f2 sk = g[2*k+1]+g[2*k+2], dk = g[2*k+1]-g[2*k+2];
+			R = R+sk;
+			switch(k) {
+				case 0: mx = dk; if(SG) Pxx = sk; break;
+				case 1: my = dk; if(SG) Pyy = sk; break;
+				case 2: mz = dk; if(SG) Pzz = sk; break;
+				case 3: mx = mx+dk; my = my+dk; if(SG) { Pxx = Pxx+sk; Pyy = Pyy+sk; Pxy = sk; } break;
+				case 4: mx = mx+dk; mz = mz+dk; if(SG) { Pxx = Pxx+sk; Pzz = Pzz+sk; Pxz = sk; } break;
+				case 5: my = my+dk; mz = mz+dk; if(SG) { Pyy = Pyy+sk; Pzz = Pzz+sk; Pyz = sk; } break;
+				case 6: mx = mx+dk; my = my-dk; if(SG) { Pxx = Pxx+sk; Pyy = Pyy+sk; Pxy = Pxy-sk; } break;
+				case 7: mx = mx+dk; mz = mz-dk; if(SG) { Pxx = Pxx+sk; Pzz = Pzz+sk; Pxz = Pxz-sk; } break;
+				default: my = my+dk; mz = mz-dk; if(SG) { Pyy = Pyy+sk; Pzz = Pzz+sk; Pyz = Pyz-sk; } break;
+			}
+		}
 		rhom1 = inv*R;
 		rho = rhom1+bc(1.0f);
 		ir = rcp2(rho);
 		ir = fma2(ir, fma2(-rho, ir, bc(1.0f)), ir); // one Newton step: full single precision
 		const f2 iri = inv*ir;
 		ux = mx*iri; uy = my*iri; uz = mz*iri;
+	}
+	const bool any_e = HAS_E&&(in.e0||in.e1);
+	if(any_e) { // TYPE_E lanes: rho/u come from the boundary fields (FX/kernel.cpp:1503-1515)
+		rho = sel2(in.e0, in.e1, in.rho_e, rho); ux = sel2(in.e0, in.e1, in.ux_e, ux); uy = sel2(in.e0, in.e1, in.uy_e, uy); uz = sel2(in.e0, in.e1, in.uz_e, uz);
+		rhom1 = rho-bc(1.0f);
+		ir = rcp2(rho); ir = fma2(ir, fma2(-rho, ir, bc(1.0f)), ir);
 	}
 	Proj F; f2 uF3 = bc(0.0f);
 	if(VF) {
@@ -242,28 +265,11 @@ template<uint32_t FEAT> __device__ __forceinline__ void collide_fast2(const Doma
 		ux = clampc2(ux); uy = clampc2(uy); uz = clampc2(uz);
 	}
 	out.rho = rho; out.ux = ux; out.uy = uy; out.uz = uz;
-	const f2 c3 = -3.0f*fma2(ux, ux, fma2(uy, uy, uz*uz));
-	Proj A3; A3.x = 3.0f*ux; A3.y = 3.0f*uy; A3.z = 3.0f*uz; // a = 3 c.u
-	const f2 rs = WS*rho, re = WE*rho, r1s = (2.0f*WS)*rhom1, r1e = (2.0f*WE)*rhom1;
-	const f2 feq0 = W0*fma2(rho, 0.5f*c3, rhom1);
 	f2 w = bc(c.w);
-	if(SG) {
-		f2 Hxx, Hyy, Hzz, Hxy, Hxz, Hyz;
-#pragma unroll
-		for(int k=0; k<9; k++) {
-			const f2 ak = proj(A3, k);
-			const f2 ek = fma2(k<3 ? rs : re, fma2(ak, ak, c3), k<3 ? r1s : r1e);
-			const f2 nk = fma2(g[2*k+1]+g[2*k+2], inv, -ek);
-			switch(k) {
-				case 0: Hxx = nk; break; case 1: Hyy = nk; break; case 2: Hzz = nk; break;
-				case 3: Hxx = Hxx+nk; Hyy = Hyy+nk; Hxy = nk; break;
-				case 4: Hxx = Hxx+nk; Hzz = Hzz+nk; Hxz = nk; break;
-				case 5: Hyy = Hyy+nk; Hzz = Hzz+nk; Hyz = nk; break;
-				case 6: Hxx = Hxx+nk; Hyy = Hyy+nk; Hxy = Hxy-nk; break;
-				case 7: Hxx = Hxx+nk; Hzz = Hzz+nk; Hxz = Hxz-nk; break;
-				default: Hyy = Hyy+nk; Hzz = Hzz+nk; Hyz = Hyz-nk; break;
-			}
-		}
+	if(SG) { // Smagorinsky-Lilly (FX/kernel.cpp:1723-1736) from the second moments
+		const f2 rux = rho*ux, ruy = rho*uy, ruz = rho*uz, r3 = 0.33333334f*rhom1;
+		const f2 Hxx = fma2(Pxx, inv, -fma2(rux, ux, r3)), Hyy = fma2(Pyy, inv, -fma2(ruy, uy, r3)), Hzz = fma2(Pzz, inv, -fma2(ruz, uz, r3));
+		const f2 Hxy = fma2(Pxy, inv, -(rux*uy)), Hxz = fma2(Pxz, inv, -(rux*uz)), Hyz = fma2(Pyz, inv, -(ruy*uz));
 		const f2 Qn = fma2(Hxx, Hxx, fma2(Hyy, Hyy, Hzz*Hzz))+2.0f*fma2(Hxy, Hxy, fma2(Hxz, Hxz, Hyz*Hyz));
 		const float tau0 = __fdiv_rn(1.0f, c.w);
 		const f2 den = bc(tau0)+sqrt2(fma2(0.76421222f*sqrt2(Qn), ir, bc(__fmul_rn(tau0, tau0))));
@@ -271,19 +277,27 @@ template<uint32_t FEAT> __device__ __forceinline__ void collide_fast2(const Doma
 		id = fma2(id, fma2(-den, id, bc(1.0f)), id);
 		w = 2.0f*id;
 	}
+	if(any_e) w = sel2(in.e0, in.e1, bc(1.0f), w); // ... and f := feq: relaxation rate 1, no forcing term (FX/kernel.cpp:1747)
+	const f2 c3 = -3.0f*fma2(ux, ux, fma2(uy, uy, uz*uz));
+	Proj A3; A3.x = 3.0f*ux; A3.y = 3.0f*uy; A3.z = 3.0f*uz; // a = 3 c.u
 	const f2 omw = bc(1.0f)-w;
 	const f2 hw = (0.5f*scale)*w; // S*w/2
-	const f2 wrs = (2.0f*hw)*rs, wre = (2.0f*hw)*re; // S*w*r
+	const f2 hwr = hw*rho; // S*w*rho/2
+	const f2 hws = WS*hwr, hwe = WE*hwr; // S*w*r/2 per weight class
+	const f2 wrs = 2.0f*hws, wre = 2.0f*hwe; // S*w*r
+	const f2 hw1 = hw*rhom1;
+	const f2 h1s = (2.0f*WS)*hw1, h1e = (2.0f*WE)*hw1; // S*w/2 * 2 w_i (rho-1)
+	const f2 feq0 = W0*fma2(rho, 0.5f*c3, rhom1);
 	if(VF) {
-		const f2 c_tau = fma2(w, -0.5f, bc(1.0f));
+		f2 c_tau = fma2(w, -0.5f, bc(1.0f));
+		if(any_e) c_tau = sel2(in.e0, in.e1, bc(0.0f), c_tau);
 		const f2 kcs = (9.0f*WS/3.0f*scale)*c_tau, kce = (9.0f*WE/3.0f*scale)*c_tau; // S*kc/3
 #pragma unroll
 		for(int k=0; k<9; k++) {
 			const f2 ak = proj(A3, k), Ak = proj(F, k), kc = k<3 ? kcs : kce;
-			const f2 ek = fma2(k<3 ? rs : re, fma2(ak, ak, c3), k<3 ? r1s : r1e);
-			const f2 U = fma2(kc, fma2(Ak, ak, uF3), hw*ek);
+			const f2 U = fma2(kc, fma2(Ak, ak, uF3), fma2(k<3 ? hws : hwe, fma2(ak, ak, c3), k<3 ? h1s : h1e));
 			const f2 V = fma2(k<3 ? wrs : wre, ak, kc*Ak);
-			f2 gi = fma2(omw, g[2*k+1], U+V), gj = fma2(omw, g[2*k+2], U-V);
+			const f2 gi = fma2(omw, g[2*k+1], U+V), gj = fma2(omw, g[2*k+2], U-V);
 			g[2*k+1] = gi; g[2*k+2] = gj;
 		}
 		g[0] = fma2(omw, g[0], fma2(2.0f*hw, feq0, ((9.0f*W0/3.0f*scale)*c_tau)*uF3));
@@ -291,9 +305,8 @@ template<uint32_t FEAT> __device__ __forceinline__ void collide_fast2(const Doma
 #pragma unroll
 		for(int k=0; k<9; k++) {
 			const f2 ak = proj(A3, k);
-			const f2 ek = fma2(k<3 ? rs : re, fma2(ak, ak, c3), k<3 ? r1s : r1e);
-			const f2 U = hw*ek, V = (k<3 ? wrs : wre)*ak;
-			f2 gi = fma2(omw, g[2*k+1], U+V), gj = fma2(omw, g[2*k+2], U-V);
+			const f2 U = fma2(k<3 ? hws : hwe, fma2(ak, ak, c3), k<3 ? h1s : h1e), V = (k<3 ? wrs : wre)*ak;
+			const f2 gi = fma2(omw, g[2*k+1], U+V), gj = fma2(omw, g[2*k+2], U-V);
 			g[2*k+1] = gi; g[2*k+2] = gj;
 		}
 		g[0] = fma2(omw, g[0], (2.0f*hw)*feq0);
