@@ -34,6 +34,7 @@ struct DomainConst { // the def_* constants of FX/lbm.cpp:612-783 as kernel para
 	const float* wbuf; // [buffer_N+1] sin^2 ramp by distance, built on the host (FX/kernel.cpp:1579-1581)
 	const float* sigma; // [sponge_N] inv_tau*sin^2 ramp by depth (FX/kernel.cpp:1603-1605)
 	void* fi; float* rho; float* u; uint8_t* flags;
+	uint32_t* sched; // strip counter of the tiled step (zeroed in-stream before every launch)
 };
 struct StepArgs { uint64_t t; float fx, fy, fz, ox, oy, oz; }; // per-step kernel arguments, FX/lbm.cpp:345
 

@@ -20,8 +20,9 @@
 // Pipeline. One CTA = TILE/2 consumer threads (two x-adjacent cells per thread, packed FP32x2 arithmetic, lbm_vec.cuh) + one producer
 // warp, over a ring of STAGES shared-memory stages with mbarriers:  producer: expect_tx + 20 TMA loads -> full[s];  consumers: wait
 // full[s] -> collide in place -> fence.proxy.async -> arrive done[s];  producer: wait done[s] -> 19 TMA stores -> commit ->
-// wait_group.read -> refill the stage with the tile STAGES ahead. CTAs are persistent (grid = resident CTAs) and walk the strip list
-// with stride gridDim.
+// wait_group.read -> refill the stage with the tile STAGES ahead. CTAs are persistent (grid = resident CTAs); strips are handed out
+// dynamically through an atomic counter (SMs do not all see the same memory bandwidth -- a static split leaves the fast ones idle at the end);
+// the producer publishes the strip id of every stage in shared memory, an END id tells the consumers to leave.
 //
 // TYPE_E cells (FX/kernel.cpp:1503-1515,1747) take their rho/u from the boundary fields and set f := feq; they do not depend on the
 // streamed DDFs at all. They are kept out of the packed main path: lanes that hold a TYPE_E cell are overwritten afterwards by a
@@ -124,7 +125,7 @@ template<int P_, int TX_, int TY_, int TZ_, int STAGES_, int CTAS_> struct TileC
 	static constexpr int FLAG_OFF = Q*BOX_BYTES+5*PAD;
 	static constexpr int STAGE_BYTES = FLAG_OFF+TILE; // 19 DDF boxes + 5 pads + the flag box
 	static constexpr int LOAD_BYTES = Q*BOX_BYTES+TILE; // what one stage's TMA loads deliver
-	static constexpr int SMEM_BYTES = STAGES*STAGE_BYTES+(2*STAGES+1)*8+128; // + mbarriers, + slack for 128 B alignment of the first stage
+	static constexpr int SMEM_BYTES = STAGES*STAGE_BYTES+(2*STAGES+1)*8+STAGES*4+4+128; // + mbarriers, + the strip id of every stage, + slack for 128 B alignment of the first stage
 	__host__ __device__ static constexpr int box_off(const int b) {
 		return b==0 ? 0 : (b&1) ? (1+(b-1)/2)*BOX_BYTES : (10+(b-2)/2)*BOX_BYTES+PAD*pads_before_pair((b-2)/2);
 	}
@@ -255,6 +256,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 	uint64_t* const bar_full = (uint64_t*)(stage0+(size_t)S*CFG::STAGE_BYTES);
 	uint64_t* const bar_done = bar_full+S;
 	uint64_t* const bar_head = bar_done+S;
+	volatile uint32_t* const tile_strip = (volatile uint32_t*)(bar_head+1); // strip id of the tile in each stage
 
 	const uint32_t tid = threadIdx.x;
 	TRACE_CLK(0);
@@ -265,23 +267,34 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 	}
 	__syncthreads();
 
-	// tile sequence of this CTA: strips (one (y,z) tile row each) blockIdx.x, blockIdx.x+gridDim.x, ...; inside a strip x ascending
+	// tile sequence of this CTA: strips (one (y,z) tile row each) drawn from the counter *c.sched (zeroed by the host before the launch); inside a strip x ascending
 	const uint32_t nstrips = tiles_y*tiles_z;
-	const uint32_t my_strips = blockIdx.x<nstrips ? (nstrips-blockIdx.x+gridDim.x-1u)/gridDim.x : 0u;
-	const uint32_t my_tiles = my_strips*tiles_x;
+	constexpr uint32_t END = 0xFFFFFFFFu;
 	const uint32_t odd = (uint32_t)(a.t&1ull);
 	const bool wrap_x = c.Dx==1u; // the lattice is periodic in x inside this domain
 	const bool park = wrap_x&&tiles_x>=2u; // ... and the wrapped column lives in another tile than the last one
 
 	if(tid>=(uint32_t)NC) { // ---------------------------------------------------------------- producer warp: TMA loads and stores
-		// The whole warp walks the loops (uniform control flow keeps coordinates and addresses in uniform registers); one elected lane issues.
-		const bool leader = elect_one();
-		uint32_t lstrip = blockIdx.x, lxt = 0u; // tile the next load belongs to
-		const auto issue_loads = [&](const uint32_t q) {
-			const int s = (int)(q%(uint32_t)S);
+		// The whole warp walks the loops (uniform control flow keeps coordinates and addresses in uniform registers); lane 0 issues.
+		const bool leader = (tid&31u)==0u;
+		uint32_t lstrip = 0u, lxt = 0u, issued = 0u; // tile the next load belongs to; tiles whose loads have been issued
+		bool ended = false;
+		const auto issue_loads = [&]() {
+			const int s = (int)(issued%(uint32_t)S);
+			if(lxt==0u) { // next strip
+				uint32_t v = 0u;
+				if(leader) v = atomicAdd(c.sched, 1u);
+				lstrip = __shfl_sync(0xFFFFFFFFu, v, 0);
+				if(lstrip>=nstrips) { // no more work: tell the consumers
+					ended = true;
+					if(leader) { tile_strip[s] = END; mbar_arrive(bar_full+s); }
+					return;
+				}
+			}
 			const int x0 = (int)lxt*TX, y0 = (int)(lstrip%tiles_y)*TY, z0 = (int)(lstrip/tiles_y)*TZ;
 			uint8_t* st = stage0+(size_t)s*CFG::STAGE_BYTES;
 			if(leader) {
+				tile_strip[s] = lstrip; // published by the barrier's release / acquire
 				mbar_expect_tx(bar_full+s, (uint32_t)CFG::LOAD_BYTES);
 				tma_load_3d(st+CFG::FLAG_OFF, &maps.flags, bar_full+s, x0, y0, z0);
 				tma_load_4d(st, &maps.fi, bar_full+s, x0, y0, z0, 0);
@@ -293,15 +306,16 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 					tma_load_4d(st+CFG::box_off(2+2*k), &maps.fi, bar_full+s, x0, y0+cy, z0+cz, odd ? i+1 : i); // x shift applied by the readers
 				}
 			}
-			if(++lxt==tiles_x) { lxt = 0u; lstrip += gridDim.x; }
+			if(++lxt==tiles_x) lxt = 0u;
+			issued++;
 		};
-		const uint32_t pro = my_tiles<(uint32_t)S ? my_tiles : (uint32_t)S;
-		for(uint32_t q=0u; q<pro; q++) issue_loads(q);
-		uint32_t sstrip = blockIdx.x, sxt = 0u; // tile the next store belongs to
-		for(uint32_t q=0u; q<my_tiles; q++) {
+		for(int i=0; i<S&&!ended; i++) issue_loads();
+		uint32_t sxt = 0u; // x tile of the next store
+		for(uint32_t q=0u; q<issued; q++) { // `issued` keeps growing until the strips run out
 			const int s = (int)(q%(uint32_t)S);
 			mbar_wait_backoff(bar_done+s, (q/(uint32_t)S)&1u);
 			if(leader) TRACE(0, q);
+			const uint32_t sstrip = tile_strip[s];
 			const int x0 = (int)sxt*TX, y0 = (int)(sstrip%tiles_y)*TY, z0 = (int)(sstrip/tiles_y)*TZ;
 			const uint8_t* st = stage0+(size_t)s*CFG::STAGE_BYTES;
 			const bool inner = y0>0&&z0>0&&y0+TY<=(int)c.Ny&&z0+TZ<=(int)c.Nz; // every box lies inside the lattice: all 19 go through TMA
@@ -317,14 +331,14 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 				}
 				tma_commit();
 				TRACE(1, q);
-				if(q+(uint32_t)S<my_tiles) tma_wait_read0(); // the stage may be refilled once TMA has read it
+				if(!ended) tma_wait_read0(); // the stage may be refilled once TMA has read it
 				TRACE(2, q);
 			}
 			__syncwarp();
-			if(q+(uint32_t)S<my_tiles) issue_loads(q+(uint32_t)S);
+			if(!ended) issue_loads();
 			if(leader) TRACE(3, q);
 			if(park&&last_of_strip&&leader) { tma_wait_all_but(tiles_x-1u); mbar_arrive(bar_head); } // the strip's first tile (tiles_x-1 groups ago) is in global memory: its column 0 may be overwritten
-			if(last_of_strip) { sxt = 0u; sstrip += gridDim.x; } else sxt++;
+			sxt = last_of_strip ? 0u : sxt+1u;
 		}
 		if(leader) tma_wait_all0();
 		return;
@@ -337,24 +351,30 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 	const bool has_zones = VF&&(c.features&(F_NUDGING|F_SPONGE))!=0u;
 	const int Nb = (c.features&F_NUDGING) ? (int)c.buffer_N : -1, Ns = (c.features&F_SPONGE) ? (int)c.sponge_N : 0;
 	const uint32_t last_tx = c.Nx-(tiles_x-1u)*(uint32_t)TX; // cells of the last tile's rows that lie inside the lattice
-	// walk: strip = blockIdx.x, blockIdx.x+gridDim.x, ...; inside a strip xt = 0..tiles_x-1; ring slot s and its phase advance with every tile
-	uint32_t strip = blockIdx.x, xt = 0u, s = 0u, ph = 0u, kstrip = 0u;
-	int y0 = (int)(strip%tiles_y)*TY, z0 = (int)(strip/tiles_y)*TZ, py0 = 0, pz0 = 0;
-	for(uint32_t q=0u; q<my_tiles; q++) {
+	// walk: strips as published by the producer; inside a strip xt = 0..tiles_x-1; ring slot s and its phase advance with every tile
+	uint32_t xt = 0u, s = 0u, ph = 0u, kstrip = 0u;
+	int y0 = 0, z0 = 0, py0 = 0, pz0 = 0;
+	for(uint32_t q=0u; ; q++) {
 		const uint32_t s1 = s+1u==(uint32_t)S ? 0u : s+1u, ph1 = s+1u==(uint32_t)S ? ph^1u : ph;
 		const int x0 = (int)xt*TX;
 		uint8_t* const st = stage0+(size_t)s*CFG::STAGE_BYTES;
 		uint8_t* const st1 = stage0+(size_t)s1*CFG::STAGE_BYTES;
 		const bool first = xt==0u, last = xt+1u==tiles_x; // the next tile of the strip holds the +x slots of this tile's last column
+		if(first) { // a new strip: which one?
+			mbar_wait(bar_full+s, ph);
+			const uint32_t strip = tile_strip[s];
+			if(strip==END) break;
+			y0 = (int)(strip%tiles_y)*TY; z0 = (int)(strip/tiles_y)*TZ;
+		}
 		const bool bnd_yz = y0==0||y0+TY>=(int)c.Ny||z0==0||z0+TZ>=(int)c.Nz; // strip touches the y/z boundary (uniform)
 		const bool edge = bnd_yz||first||last;
-		if(first) { mbar_wait(bar_full+s, ph); if(bnd_yz) patch_yz<CFG, true>(c, st, x0, y0, z0, odd, tid, false); }
+		if(first&&bnd_yz) patch_yz<CFG, true>(c, st, x0, y0, z0, odd, tid, false);
 		if(!last) { mbar_wait(bar_full+s1, ph1); if(bnd_yz) patch_yz<CFG, true>(c, st1, x0+TX, y0, z0, odd, tid, false); }
 		if(bnd_yz) consumer_bar((uint32_t)NC);
 		if(park&&kstrip>0u&&xt==1u) { // write the previous strip's periodic-x column
 			mbar_wait(bar_head, (kstrip-1u)&1u);
 			__syncwarp();
-			if(lx==0u) flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd);
+			if(lx==last_tx-2u) flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd); // the thread that wrote the parked elements last
 		}
 
 		if(tid==0u) TRACE(4, q);
@@ -372,10 +392,10 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 			if(!last) {
 				const uint32_t fn = ((const uint16_t*)(st1+CFG::FLAG_OFF))[tid];
 				if((fn&0x0003u)==TYPE_E||(fn&0x0300u)==(TYPE_E<<8)) { const uint64_t m = n+(uint64_t)TX; prefetch_l2(c.rho+m); prefetch_l2(c.u+m); prefetch_l2(c.u+c.N+m); prefetch_l2(c.u+2ull*c.N+m); }
-			} else if(lx==0u) { // the next strip starts at the west face: its x = 0 cells
-				const uint32_t ns = strip+gridDim.x;
+			} else if(lx==0u) { // the next strip starts at the west face: its x = 0 cells (the id may still be a stale one: this is only a hint)
+				const uint32_t ns = tile_strip[s1];
 				const uint64_t m = (uint64_t)((ns%tiles_y)*(uint32_t)TY+ly)*rowN+(uint64_t)((ns/tiles_y)*(uint32_t)TZ+lz)*planeN;
-				if(m<c.N) { prefetch_l2(c.rho+m); prefetch_l2(c.u+m); prefetch_l2(c.u+c.N+m); prefetch_l2(c.u+2ull*c.N+m); }
+				if(ns<nstrips&&m<c.N) { prefetch_l2(c.rho+m); prefetch_l2(c.u+m); prefetch_l2(c.u+c.N+m); prefetch_l2(c.u+2ull*c.N+m); }
 			}
 		}
 		R* const box = (R*)st+tid; // the pair's word in box b is at byte offset box_off(b)
@@ -486,7 +506,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 		if(tid==0u) TRACE(5, q);
 		mbar_arrive(bar_done+s);
 		s = s1; ph = ph1;
-		if(last) { xt = 0u; py0 = y0; pz0 = z0; kstrip++; strip += gridDim.x; y0 = (int)(strip%tiles_y)*TY; z0 = (int)(strip/tiles_y)*TZ; } else xt++;
+		if(last) { xt = 0u; py0 = y0; pz0 = z0; kstrip++; } else xt++;
 	}
 	TRACE_CLK(2);
 	if(park&&kstrip>0u) { // the last strip's periodic-x column

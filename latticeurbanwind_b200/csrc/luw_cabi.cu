@@ -131,6 +131,7 @@ void setup_tiles(luw_domain* d) {
 }
 cudaError_t enqueue_step(luw_domain* d, const luw::StepArgs& a) {
 	cudaError_t e = cudaSuccess;
+	if(d->tiled) { e = cudaMemsetAsync(d->c.sched, 0, 4u, d->stream); if(e!=cudaSuccess) return e; } // strip counter of the persistent kernel
 	if(d->ktiming) { // event pair around the main kernel
 		if(d->kev_used+2u>d->kev.size()) for(int k=0; k<2; k++) { cudaEvent_t ev; e = cudaEventCreate(&ev); if(e!=cudaSuccess) return e; d->kev.push_back(ev); }
 		e = cudaEventRecord(d->kev[d->kev_used], d->stream); if(e!=cudaSuccess) return e;
@@ -235,10 +236,12 @@ int luw_domain_create(const luw_domain_params* p, luw_domain** out) {
 	if(rc==LUW_OK) rc = dev_alloc(d, &c.rho, N);
 	if(rc==LUW_OK) rc = dev_alloc(d, &c.u, 3ull*N);
 	if(rc==LUW_OK) rc = dev_alloc(d, &c.flags, N);
+	if(rc==LUW_OK) rc = dev_alloc(d, &c.sched, 2u);
 	if(rc==LUW_OK) { // Memory<> zero-fills; rho starts at 1 (FX/lbm.cpp:283-288)
 		e = cudaMemsetAsync(c.fi, 0, 19ull*N*d->ddf_size, d->stream);
 		if(e==cudaSuccess) e = cudaMemsetAsync(c.u, 0, 3ull*N*4ull, d->stream);
 		if(e==cudaSuccess) e = cudaMemsetAsync(c.flags, 0, N, d->stream);
+		if(e==cudaSuccess) e = cudaMemsetAsync(c.sched, 0, 8u, d->stream);
 		if(e==cudaSuccess) { k_fill_f32<<<1184, 256, 0, d->stream>>>(c.rho, N, 1.0f); e = cudaGetLastError(); d->launches++; }
 		if(e!=cudaSuccess) rc = cuda_fail(e, "zero-fill");
 	}
@@ -269,7 +272,7 @@ int luw_domain_destroy(luw_domain* d) {
 	if(!d) return LUW_OK;
 	DeviceGuard guard(d->p.device);
 	if(d->own_stream) cudaStreamSynchronize(d->own_stream);
-	cudaFree(d->c.fi); cudaFree(d->c.rho); cudaFree(d->c.u); cudaFree(d->c.flags); cudaFree(d->wbuf); cudaFree(d->sigma);
+	cudaFree(d->c.fi); cudaFree(d->c.rho); cudaFree(d->c.u); cudaFree(d->c.flags); cudaFree(d->c.sched); cudaFree(d->wbuf); cudaFree(d->sigma);
 	if(d->ev0) cudaEventDestroy(d->ev0);
 	if(d->ev1) cudaEventDestroy(d->ev1);
 	for(cudaEvent_t ev : d->kev) cudaEventDestroy(ev);
