@@ -43,6 +43,12 @@ struct luw_domain {
 	luw::TileMaps maps; // TMA descriptors for the tiled step
 	bool tiled = false; // the tiled step is usable for this domain
 	int tile_variant = 0, sm_count = 0;
+	struct HaloAxis { // transfer buffers of one decomposed axis (reference: transfer_buffer_p / _m, FX/lbm.cpp:1864-1889) and the events that order their use
+		char* send_p = nullptr; char* send_m = nullptr; char* recv_p = nullptr; char* recv_m = nullptr;
+		uint64_t bytes = 0ull;
+		cudaEvent_t extracted = nullptr, taken_p = nullptr, taken_m = nullptr; // payloads ready / copied away by the (+) and (-) neighbour
+		bool in_use = false;
+	} halo[3];
 	bool ktiming = false; // bracket every main step kernel with events (luw_kernel_timing)
 	std::vector<cudaEvent_t> kev; // event pairs
 	size_t kev_used = 0u;
@@ -158,6 +164,18 @@ template<typename T> __global__ void __launch_bounds__(256) k_cellset_gather(con
 	for(uint32_t c=0u; c<comps; c++) stage[(uint64_t)c*count+k] = field[(uint64_t)c*N+n];
 }
 
+// NVLink peer access from `dev` to every other device of the process (once per ordered pair; a pair without P2P falls back to staged copies)
+void enable_peer_access(const int dev, const int ndev) {
+	static std::vector<char> done;
+	if(done.size()<(size_t)ndev*ndev) done.assign((size_t)ndev*ndev, 0);
+	for(int other=0; other<ndev; other++) {
+		if(other==dev||done[(size_t)dev*ndev+other]) continue;
+		done[(size_t)dev*ndev+other] = 1;
+		int can = 0;
+		if(cudaDeviceCanAccessPeer(&can, dev, other)==cudaSuccess&&can) { if(cudaDeviceEnablePeerAccess(other, 0)!=cudaSuccess) cudaGetLastError(); } // "already enabled" is fine
+	}
+}
+
 __global__ void k_fill_f32(float* p, const uint64_t n, const float v) {
 	for(uint64_t i=(uint64_t)blockIdx.x*blockDim.x+threadIdx.x; i<n; i+=(uint64_t)gridDim.x*blockDim.x) p[i] = v;
 }
@@ -208,6 +226,7 @@ int luw_domain_create(const luw_domain_params* p, luw_domain** out) {
 	DeviceGuard guard(p->device);
 	if(guard.err!=cudaSuccess) return cuda_fail(guard.err, "cudaSetDevice");
 
+	if(p->Dx*p->Dy*p->Dz>1u) enable_peer_access(p->device, ndev);
 	luw_domain* d = new(std::nothrow) luw_domain();
 	if(!d) return fail(LUW_ERR_OOM, "host allocation failed");
 	d->p = *p;
@@ -276,6 +295,13 @@ int luw_domain_destroy(luw_domain* d) {
 	if(d->ev0) cudaEventDestroy(d->ev0);
 	if(d->ev1) cudaEventDestroy(d->ev1);
 	for(cudaEvent_t ev : d->kev) cudaEventDestroy(ev);
+	for(int a=0; a<3; a++) {
+		luw_domain::HaloAxis& h = d->halo[a];
+		cudaFree(h.send_p); cudaFree(h.send_m); cudaFree(h.recv_p); cudaFree(h.recv_m);
+		if(h.extracted) cudaEventDestroy(h.extracted);
+		if(h.taken_p) cudaEventDestroy(h.taken_p);
+		if(h.taken_m) cudaEventDestroy(h.taken_m);
+	}
 	if(d->own_stream) cudaStreamDestroy(d->own_stream);
 	delete d;
 	return LUW_OK;
@@ -378,6 +404,75 @@ static int halo(luw_domain* d, int payload, uint32_t axis, uint64_t t, void* bp,
 }
 int luw_halo_extract(luw_domain* d, int payload, uint32_t axis, uint64_t t, void* bp, void* bm) { return halo(d, payload, axis, t, bp, bm, false); }
 int luw_halo_insert(luw_domain* d, int payload, uint32_t axis, uint64_t t, const void* bp, const void* bm) { return halo(d, payload, axis, t, (void*)bp, (void*)bm, true); }
+
+static int halo_axis_setup(luw_domain* d, const uint32_t axis) { // buffers sized for the larger payload (rho_u_flags: 17 B per face cell >= 5 fpxx for FP16; FP32: 20 B)
+	luw_domain::HaloAxis& h = d->halo[axis];
+	if(h.send_p) return LUW_OK;
+	DeviceGuard guard(d->p.device);
+	const uint64_t A = face_area(d->c, axis);
+	h.bytes = A*(d->ddf_size==4u ? 20ull : 17ull);
+	int rc = dev_alloc(d, &h.send_p, h.bytes);
+	if(rc==LUW_OK) rc = dev_alloc(d, &h.send_m, h.bytes);
+	if(rc==LUW_OK) rc = dev_alloc(d, &h.recv_p, h.bytes);
+	if(rc==LUW_OK) rc = dev_alloc(d, &h.recv_m, h.bytes);
+	if(rc!=LUW_OK) return rc;
+	CU(cudaEventCreateWithFlags(&h.extracted, cudaEventDisableTiming));
+	CU(cudaEventCreateWithFlags(&h.taken_p, cudaEventDisableTiming));
+	CU(cudaEventCreateWithFlags(&h.taken_m, cudaEventDisableTiming));
+	return LUW_OK;
+}
+int luw_halo_exchange(luw_domain* const* doms, uint32_t count, int payload, uint32_t axis, uint64_t t) {
+	if(!doms||count==0u||axis>2u) return fail(LUW_ERR_INVALID, "bad argument");
+	const luw::DomainConst& c0 = doms[0]->c;
+	if(count!=c0.Dx*c0.Dy*c0.Dz) return fail(LUW_ERR_INVALID, "luw_halo_exchange needs all Dx*Dy*Dz domains of the decomposition");
+	const uint32_t D[3] = { c0.Dx, c0.Dy, c0.Dz };
+	if(D[axis]<2u) return LUW_OK; // nothing to exchange on an undecomposed axis
+	if(payload!=LUW_HALO_FI&&payload!=LUW_HALO_RHO_U_FLAGS) return fail(LUW_ERR_INVALID, "unknown halo payload");
+	for(uint32_t i=0u; i<count; i++) { if(!doms[i]) return fail(LUW_ERR_INVALID, "null domain"); if(const int rc = halo_axis_setup(doms[i], axis)) return rc; }
+	uint64_t bytes = 0ull;
+	luw_halo_bytes(doms[0], payload, axis, &bytes);
+	// 1. every domain packs its two boundary layers (after its neighbours have taken the previous payloads out of the send buffers)
+	for(uint32_t i=0u; i<count; i++) {
+		luw_domain* d = doms[i];
+		luw_domain::HaloAxis& h = d->halo[axis];
+		DeviceGuard guard(d->p.device);
+		if(h.in_use) { CU(cudaStreamWaitEvent(d->stream, h.taken_p, 0)); CU(cudaStreamWaitEvent(d->stream, h.taken_m, 0)); }
+		if(payload==LUW_HALO_FI) CU(d->ks->halo_fi(d->c, d->c.precision, axis, (uint32_t)(t&1ull), false, h.send_p, h.send_m, d->stream));
+		else CU(d->ks->halo_rho_u_flags(d->c, axis, false, h.send_p, h.send_m, d->stream));
+		d->launches++;
+		CU(cudaEventRecord(h.extracted, d->stream));
+		h.in_use = true;
+	}
+	// 2. every domain pulls what its neighbours packed for it (peer copies on the RECEIVER's stream) and unpacks it into its halo layers
+	const uint32_t stride = axis==0u ? 1u : axis==1u ? D[0] : D[0]*D[1];
+	for(uint32_t i=0u; i<count; i++) {
+		luw_domain* d = doms[i];
+		const uint32_t di = (i/stride)%D[axis];
+		luw_domain* up = doms[i-di*stride+((di+1u)%D[axis])*stride]; // (+) neighbour, periodic
+		luw_domain* dn = doms[i-di*stride+((di+D[axis]-1u)%D[axis])*stride]; // (-) neighbour
+		luw_domain::HaloAxis& h = d->halo[axis];
+		DeviceGuard guard(d->p.device);
+		// what left the (-) neighbour through its + face arrives in my - halo layer, and vice versa
+		CU(cudaStreamWaitEvent(d->stream, dn->halo[axis].extracted, 0));
+		CU(cudaMemcpyPeerAsync(h.recv_m, d->p.device, dn->halo[axis].send_p, dn->p.device, bytes, d->stream));
+		CU(cudaEventRecord(dn->halo[axis].taken_p, d->stream));
+		CU(cudaStreamWaitEvent(d->stream, up->halo[axis].extracted, 0));
+		CU(cudaMemcpyPeerAsync(h.recv_p, d->p.device, up->halo[axis].send_m, up->p.device, bytes, d->stream));
+		CU(cudaEventRecord(up->halo[axis].taken_m, d->stream));
+		if(payload==LUW_HALO_FI) CU(d->ks->halo_fi(d->c, d->c.precision, axis, (uint32_t)(t&1ull), true, h.recv_p, h.recv_m, d->stream));
+		else CU(d->ks->halo_rho_u_flags(d->c, axis, true, h.recv_p, h.recv_m, d->stream));
+		d->launches++;
+	}
+	return LUW_OK;
+}
+int luw_run_steps_multi(luw_domain* const* doms, uint32_t count, uint64_t t0, uint64_t k, float fx, float fy, float fz, float ox, float oy, float oz) {
+	if(!doms||count==0u) return fail(LUW_ERR_INVALID, "bad argument");
+	for(uint64_t s=0ull; s<k; s++) {
+		for(uint32_t i=0u; i<count; i++) { if(const int rc = luw_stream_collide(doms[i], t0+s, fx, fy, fz, ox, oy, oz)) return rc; }
+		for(uint32_t axis=0u; axis<3u; axis++) { if(const int rc = luw_halo_exchange(doms, count, LUW_HALO_FI, axis, t0+s)) return rc; }
+	}
+	return LUW_OK;
+}
 
 int luw_vk_inlet_create(luw_domain* d, uint64_t P, uint64_t M, uint64_t V, const uint64_t* pc, const uint8_t* pf, const float* pd, const float* md, luw_vk_inlet** out) {
 	if(!d||!out||(P>0ull&&(!pc||!pf||!pd))||(V>0ull&&!md)) return fail(LUW_ERR_INVALID, "null argument");

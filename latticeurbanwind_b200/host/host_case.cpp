@@ -1,0 +1,48 @@
+// Command-line driver over the C++ host layer, used by the parity tests (tests/test_cpp_host.py): it does what a case driver does with the
+// reference's API (FX/setup.cpp:4931-6153 in miniature): construct LBM, write lbm.flags / lbm.rho / lbm.u through the global accessors,
+// set_coriolis, run(steps), read_from_device, and dump rho / u.
+//   luw_host_case Nx Ny Nz Dx Dy Dz precision features arith nu steps downstream bufN buf_inv_tau buf_vertical spongeN sponge_inv_tau fx fy fz ox oy oz in.bin out.bin
+//   in.bin : flags[N] u8, rho[N] f32, u[3N] f32 (global images, n = x+(y+z*Ny)*Nx);  out.bin : rho[N] f32, u[3N] f32
+#include "lbm.hpp"
+#include <fstream>
+
+int main(int argc, char** argv) {
+	if(argc!=26) { fprintf(stderr, "usage: see host_case.cpp\n"); return 2; }
+	int a = 1;
+	const uint Nx = (uint)atoi(argv[a++]), Ny = (uint)atoi(argv[a++]), Nz = (uint)atoi(argv[a++]);
+	const uint Dx = (uint)atoi(argv[a++]), Dy = (uint)atoi(argv[a++]), Dz = (uint)atoi(argv[a++]);
+	lbm_settings.precision = (uint)atoi(argv[a++]);
+	lbm_settings.features = (uint)atoi(argv[a++])&~(uint)(LUW_BUFFER_NUDGING|LUW_TOP_SPONGE);
+	const uint want = (uint)atoi(argv[a-1]);
+	lbm_settings.arith = (uint)atoi(argv[a++]);
+	const float nu = (float)atof(argv[a++]);
+	const ulong steps = (ulong)atoll(argv[a++]);
+	lbm_settings.downstream_face = atoi(argv[a++]);
+	const uint bufN = (uint)atoi(argv[a++]); const float buf_inv_tau = (float)atof(argv[a++]); const bool buf_vertical = atoi(argv[a++])!=0;
+	const uint spongeN = (uint)atoi(argv[a++]); const float sponge_inv_tau = (float)atof(argv[a++]);
+	if(want&LUW_BUFFER_NUDGING) lbm_settings.set_buffer_nudging(bufN, buf_inv_tau, buf_vertical);
+	if(want&LUW_TOP_SPONGE) lbm_settings.set_top_sponge(spongeN, sponge_inv_tau);
+	const float fx = (float)atof(argv[a++]), fy = (float)atof(argv[a++]), fz = (float)atof(argv[a++]);
+	const float ox = (float)atof(argv[a++]), oy = (float)atof(argv[a++]), oz = (float)atof(argv[a++]);
+	const char* in_path = argv[a++]; const char* out_path = argv[a++];
+
+	LBM lbm(uint3(Nx, Ny, Nz), Dx, Dy, Dz, nu, fx, fy, fz);
+	lbm.set_coriolis(ox, oy, oz);
+	const ulong N = lbm.get_N();
+	std::vector<uchar> flags(N); std::vector<float> rho(N), u(3ull*N);
+	std::ifstream in(in_path, std::ios::binary);
+	in.read((char*)flags.data(), (std::streamsize)N); in.read((char*)rho.data(), (std::streamsize)(4ull*N)); in.read((char*)u.data(), (std::streamsize)(12ull*N));
+	if(!in) print_error("cannot read the input images");
+	for(ulong n=0ull; n<N; n++) { // the way FX/setup.cpp writes boundary conditions: through the stitched global accessors
+		lbm.flags[n] = flags[n]; lbm.rho[n] = rho[n];
+		lbm.u.x[n] = u[n]; lbm.u.y[n] = u[N+n]; lbm.u.z[n] = u[2ull*N+n];
+	}
+	lbm.run(0ull); // initialise only (FX/setup.cpp:4852)
+	lbm.run(steps);
+	lbm.rho.read_from_device(); lbm.u.read_from_device();
+	for(ulong n=0ull; n<N; n++) { rho[n] = lbm.rho[n]; u[n] = lbm.u.x[n]; u[N+n] = lbm.u.y[n]; u[2ull*N+n] = lbm.u.z[n]; }
+	std::ofstream out(out_path, std::ios::binary);
+	out.write((const char*)rho.data(), (std::streamsize)(4ull*N)); out.write((const char*)u.data(), (std::streamsize)(12ull*N));
+	printf("luw_host_case: %llu cells, %u domain(s), %llu steps, t = %llu\n", (unsigned long long)N, lbm.get_D(), (unsigned long long)steps, (unsigned long long)lbm.get_t());
+	return 0;
+}

@@ -1,0 +1,113 @@
+// C++ host layer of the B200 LBM (see lbm.hpp): domain split, initialisation and time-step orchestration of the reference's LBM object
+// (FX/lbm.cpp:1057-1112, 1221-1312) on top of the C ABI. All device work is enqueued asynchronously by one host thread (FX/main.cpp:146-150).
+#include "lbm.hpp"
+
+LBM_Settings lbm_settings;
+
+float lbm_kernel_literal(const float x) { // what `to_string(float)` + the OpenCL compiler make of a constant (FX/utilities.hpp:2741-2750): 8 decimals, round-trip through text
+	if(!std::isfinite(x)) return x;
+	float v = std::fabs(x);
+	int e = 0;
+	if(v>=10.0f) { const float lim[6] = {1e32f,1e16f,1e8f,1e4f,1e2f,1e1f}, mul[6] = {1e-32f,1e-16f,1e-8f,1e-4f,1e-2f,1e-1f}; const int de[6] = {32,16,8,4,2,1};
+		for(int k=0; k<6; k++) if(v>=lim[k]) { v *= mul[k]; e += de[k]; } }
+	if(v>0.0f&&v<=1.0f) { const float lim[6] = {1e-31f,1e-15f,1e-7f,1e-3f,1e-1f,1e0f}, mul[6] = {1e32f,1e16f,1e8f,1e4f,1e2f,1e1f}; const int de[6] = {32,16,8,4,2,1};
+		for(int k=0; k<6; k++) if(v<lim[k]) { v *= mul[k]; e -= de[k]; } }
+	unsigned long long integral = (unsigned long long)v;
+	const float rem = (v-(float)integral)*1e8f;
+	unsigned long long dec = (unsigned long long)rem;
+	if(rem-(float)dec>=0.5f) { dec++; if(dec>=100000000ull) { dec = 0ull; integral++; if(integral>=10ull) { integral = 1ull; e++; } } }
+	char text[64];
+	if(e!=0) snprintf(text, sizeof(text), "%s%llu.%08lluE%d", x<0.0f ? "-" : "", integral, dec, e);
+	else snprintf(text, sizeof(text), "%s%llu.%08llu", x<0.0f ? "-" : "", integral, dec);
+	return strtof(text, nullptr);
+}
+
+static uint env_uint(const char* name, const uint fallback) { const char* v = getenv(name); return v&&*v ? (uint)strtoul(v, nullptr, 10) : fallback; }
+
+uint LBM_Domain::lbm_features() { return lbm_settings.features; }
+
+luw_domain* LBM_Domain::create_handle(const int device, const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const int Ox, const int Oy, const int Oz, const float nu) {
+	luw_domain_params p;
+	memset(&p, 0, sizeof(p));
+	p.Nx = Nx; p.Ny = Ny; p.Nz = Nz; p.Dx = Dx; p.Dy = Dy; p.Dz = Dz; p.Ox = Ox; p.Oy = Oy; p.Oz = Oz;
+	p.precision = env_uint("LUW_PRECISION", lbm_settings.precision);
+	p.features = lbm_settings.features;
+	p.arith = env_uint("LUW_ARITH", lbm_settings.arith);
+	p.w = lbm_kernel_literal(1.0f/(3.0f*nu+0.5f)); // def_w, FX/lbm.hpp:146 + FX/lbm.cpp:663
+	p.downstream_face = lbm_settings.downstream_face;
+	p.buffer_N = lbm_settings.buffer_N>0u ? lbm_settings.buffer_N : 1u; p.buffer_inv_tau = lbm_kernel_literal(lbm_settings.buffer_inv_tau); p.buffer_nudge_vertical = lbm_settings.buffer_nudge_vertical;
+	p.sponge_N = lbm_settings.sponge_N>0u ? lbm_settings.sponge_N : 1u; p.sponge_inv_tau = lbm_kernel_literal(lbm_settings.sponge_inv_tau);
+	p.device = device;
+	luw_domain* h = nullptr;
+	luw_check(luw_domain_create(&p, &h));
+	return h;
+}
+
+LBM_Domain::LBM_Domain(const int device, const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const int Ox, const int Oy, const int Oz,
+	const float nu, const float fx, const float fy, const float fz)
+	: Nx(Nx), Ny(Ny), Nz(Nz), Dx(Dx), Dy(Dy), Dz(Dz), Ox(Ox), Oy(Oy), Oz(Oz), nu(nu), fx(fx), fy(fy), fz(fz), device(device),
+	  handle(create_handle(device, Nx, Ny, Nz, Dx, Dy, Dz, Ox, Oy, Oz, nu)),
+	  rho(handle, LUW_FIELD_RHO, (ulong)Nx*Ny*Nz, 1u, 1.0f), u(handle, LUW_FIELD_U, (ulong)Nx*Ny*Nz, 3u, 0.0f), flags(handle, LUW_FIELD_FLAGS, (ulong)Nx*Ny*Nz, 1u, (uchar)0) {}
+
+LBM_Domain::~LBM_Domain() { luw_domain_destroy(handle); }
+
+// ---------------------------------------------------------------------------------------------------------------- LBM
+void LBM::construct(const uint Nx_, const uint Ny_, const uint Nz_, const uint Dx_, const uint Dy_, const uint Dz_, const float nu, const float fx, const float fy, const float fz) {
+	if(Dx_*Dy_*Dz_==0u) print_error("You specified 0 LBM grid domains. There has to be at least 1 domain in every direction.");
+	Dx = Dx_; Dy = Dy_; Dz = Dz_;
+	Nx = (Nx_/Dx)*Dx; Ny = (Ny_/Dy)*Dy; Nz = (Nz_/Dz)*Dz; // global size rounded down to multiples of the domain counts, FX/lbm.cpp:1058-1060
+	if(Nx*Ny*Nz==0u) print_error("Grid point number is 0.");
+	const uint D = Dx*Dy*Dz;
+	int ndev = 0;
+	luw_check(luw_device_count(&ndev));
+	if(ndev<1) print_error("No CUDA device is available; this build of the LBM has no CPU fallback.");
+	const uint Hx = Dx>1u, Hy = Dy>1u, Hz = Dz>1u; // halo offsets, FX/lbm.cpp:1062-1064
+	lbm_domain = new LBM_Domain*[D];
+	for(uint d=0u; d<D; d++) {
+		const uint x = (d%(Dx*Dy))%Dx, y = (d%(Dx*Dy))/Dx, z = d/(Dx*Dy); // d = x+(y+z*Dy)*Dx, FX/lbm.cpp:1066-1073
+		const int device = d<lbm_settings.devices.size() ? lbm_settings.devices[d] : (int)(d%(uint)ndev);
+		lbm_domain[d] = new LBM_Domain(device, Nx/Dx+2u*Hx, Ny/Dy+2u*Hy, Nz/Dz+2u*Hz, Dx, Dy, Dz, (int)(x*Nx/Dx)-(int)Hx, (int)(y*Ny/Dy)-(int)Hy, (int)(z*Nz/Dz)-(int)Hz, nu, fx, fy, fz);
+		handles.push_back(lbm_domain[d]->get_handle());
+		rho_buffers.push_back(&lbm_domain[d]->rho); u_buffers.push_back(&lbm_domain[d]->u); flags_buffers.push_back(&lbm_domain[d]->flags);
+	}
+	rho.bind(this, rho_buffers.data()); u.bind(this, u_buffers.data()); flags.bind(this, flags_buffers.data());
+}
+LBM::LBM(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const float nu, const float fx, const float fy, const float fz, const float, const float, const float) { construct(Nx, Ny, Nz, Dx, Dy, Dz, nu, fx, fy, fz); }
+LBM::LBM(const uint Nx, const uint Ny, const uint Nz, const float nu, const float fx, const float fy, const float fz, const float, const float, const float) { construct(Nx, Ny, Nz, 1u, 1u, 1u, nu, fx, fy, fz); }
+LBM::LBM(const uint3 N, const uint Dx, const uint Dy, const uint Dz, const float nu, const float fx, const float fy, const float fz, const float, const float, const float) { construct(N.x, N.y, N.z, Dx, Dy, Dz, nu, fx, fy, fz); }
+LBM::LBM(const uint3 N, const float nu, const float fx, const float fy, const float fz, const float, const float, const float) { construct(N.x, N.y, N.z, 1u, 1u, 1u, nu, fx, fy, fz); }
+LBM::~LBM() {
+	for(uint d=0u; d<get_D(); d++) delete lbm_domain[d];
+	delete[] lbm_domain;
+}
+
+void LBM::communicate(const int payload) { // FX/lbm.cpp:1907-1958: x, then y, then z
+	if(get_D()==1u) return;
+	for(uint axis=0u; axis<3u; axis++) luw_check(luw_halo_exchange(handles.data(), get_D(), payload, axis, lbm_domain[0]->get_t()));
+}
+void LBM::initialize() { // FX/lbm.cpp:1221-1260
+	const uint D = get_D();
+	for(uint d=0u; d<D; d++) { lbm_domain[d]->rho.enqueue_write_to_device(); lbm_domain[d]->u.enqueue_write_to_device(); lbm_domain[d]->flags.enqueue_write_to_device(); }
+	for(uint d=0u; d<D; d++) lbm_domain[d]->increment_time_step(); // slot parity t = 1 for the initial DDF layout
+	communicate(LUW_HALO_RHO_U_FLAGS);
+	for(uint d=0u; d<D; d++) lbm_domain[d]->enqueue_initialize();
+	communicate(LUW_HALO_RHO_U_FLAGS);
+	communicate(LUW_HALO_FI);
+	for(uint d=0u; d<D; d++) lbm_domain[d]->finish_queue();
+	for(uint d=0u; d<D; d++) lbm_domain[d]->reset_time_step();
+	initialized = true;
+}
+void LBM::do_time_step() { // FX/lbm.cpp:1262-1290 (GRAPHICS / TEMPERATURE exchanges and the per-step finish_queue are gone)
+	const uint D = get_D();
+	for(uint d=0u; d<D; d++) lbm_domain[d]->enqueue_stream_collide();
+	communicate(LUW_HALO_FI);
+	for(uint d=0u; d<D; d++) lbm_domain[d]->increment_time_step();
+}
+void LBM::run(const ulong steps, const ulong) { // FX/lbm.cpp:1292-1312; steps are enqueued back to back, one synchronisation at the end of the call
+	if(!initialized) initialize();
+	const ulong n = steps==max_ulong ? 0ull : steps; // the reference's "run forever" needs the interactive main loop; not part of this layer
+	for(ulong i=0ull; i<n; i++) do_time_step();
+	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->finish_queue();
+}
+void LBM::update_fields() { for(uint d=0u; d<get_D(); d++) lbm_domain[d]->enqueue_update_fields(); for(uint d=0u; d<get_D(); d++) lbm_domain[d]->finish_queue(); }
+void LBM::reset() { initialized = false; }

@@ -1,0 +1,258 @@
+// C++ host layer of the B200 LBM: the reference's `LBM` / `LBM_Domain` / `Memory<T>` surface (FX/lbm.hpp:26-633, FX/opencl.hpp:331-603) over the
+// C ABI of include/luw_cuda.h. FX = core/cfd_core/FluidX3D/src of hweifluids/LatticeUrbanWind.
+//
+// What is kept (so that FX/setup.cpp, FX/interpolation*.cpp, FX/fluxcorrection.cpp and FX/info.cpp compile against it unchanged):
+//   LBM(N, Dx,Dy,Dz, nu, fx,fy,fz, sigma, alpha, beta) and the shorter constructors, run(steps,total), reset(), update_fields(), set_coriolis(),
+//   set_fx/fy/fz/f, the getters, coordinates()/index()/position()/center()/size(), lbm.rho / lbm.u / lbm.flags with operator[], .x/.y/.z,
+//   length()/dimensions()/range(), read_from_device()/write_to_device(), lbm.lbm_domain[d]-> {rho,u,flags}.enqueue_read_from_device(),
+//   finish_queue(), get_Nx()... -- same names, same argument meaning, same error behaviour (print_error -> exit(1), FX/utilities.hpp:4370-4382).
+// What is different underneath: no OpenCL, no JIT. The compile-time switches of FX/defines.hpp and the per-case constants the reference bakes
+// into the kernel source (FX/lbm.cpp:612-783) are run-time settings (LBM_Settings below; the defaults are LUW's shipped build), the device side is
+// the sm_100a library, host mirrors are page-locked, and the halo exchange moves device-to-device (luw_halo_exchange) instead of through the host.
+//
+// Stand-alone build: this header carries the few types it needs (uint3, float3, ...). Inside the reference tree define LUW_USE_REFERENCE_UTILITIES
+// and include FX/utilities.hpp first; the guarded block below then disappears.
+#pragma once
+#include "../../include/luw_cuda.h"
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#ifndef LUW_USE_REFERENCE_UTILITIES
+typedef unsigned int uint;
+typedef unsigned char uchar;
+typedef uint64_t ulong;
+struct uint3 { uint x, y, z; uint3(const uint x=0u, const uint y=0u, const uint z=0u) : x(x), y(y), z(z) {} };
+struct float3 { float x, y, z; float3(const float x=0.0f, const float y=0.0f, const float z=0.0f) : x(x), y(y), z(z) {} };
+constexpr ulong max_ulong = 18446744073709551615ull;
+[[noreturn]] inline void print_error(const std::string& s) { // FX/utilities.hpp:4370-4382: boxed message, then exit(1)
+	fprintf(stderr, "+-----------------------------------------------------------------------------+\n| Error: %-68s |\n+-----------------------------------------------------------------------------+\n", s.c_str());
+	exit(1);
+}
+#define TYPE_S 0x01 // FX/defines.hpp:50-57
+#define TYPE_E 0x02
+#define TYPE_T 0x04
+#define TYPE_F 0x08
+#define TYPE_I 0x10
+#define TYPE_G 0x20
+#define TYPE_X 0x40
+#define TYPE_Y 0x80
+#endif // LUW_USE_REFERENCE_UTILITIES
+
+// Run-time replacement of FX/defines.hpp + the constants of FX/lbm.cpp:612-783. Set the global `lbm_settings` before constructing an LBM
+// (the case driver does that where the reference's update_coriolis / update_buffer_nudging / update_top_sponge set their globals, FX/setup.cpp:3800-3903).
+struct LBM_Settings {
+	uint precision = LUW_FP16C; // FX/defines.hpp:14 (LUW ships FP16C); LUW_FP32 / LUW_FP16S / LUW_FP16C; env LUW_PRECISION overrides
+	uint features = LUW_UPDATE_FIELDS|LUW_VOLUME_FORCE|LUW_EQUILIBRIUM_BOUNDARIES|LUW_SUBGRID; // FX/defines.hpp:17-24; nudging / sponge added by the setters below
+	uint arith = LUW_ARITH_FAST; // the reference builds with -cl-mad-enable (FX/opencl.hpp:305); LUW_ARITH_STRICT reproduces the CPU oracle bit for bit
+	int downstream_face = 0; // def_downstream_face
+	uint buffer_N = 0u; float buffer_inv_tau = 0.0f; int buffer_nudge_vertical = 0; // BUFFER_NUDGING (FX/lbm.cpp:770-776)
+	uint sponge_N = 0u; float sponge_inv_tau = 0.0f; // TOP_SPONGE (FX/lbm.cpp:777-782)
+	std::vector<int> devices; // CUDA ordinals, one per domain (empty: domain d -> device d % device_count; the reference insists on one card per domain, FX/lbm.cpp:961-979)
+	void set_buffer_nudging(const uint N, const float inv_tau, const bool vertical) { buffer_N = N; buffer_inv_tau = inv_tau; buffer_nudge_vertical = vertical ? 1 : 0; if(N>0u) features |= LUW_BUFFER_NUDGING; else features &= ~(uint)LUW_BUFFER_NUDGING; }
+	void set_top_sponge(const uint N, const float inv_tau) { sponge_N = N; sponge_inv_tau = inv_tau; if(N>0u) features |= LUW_TOP_SPONGE; else features &= ~(uint)LUW_TOP_SPONGE; }
+};
+extern LBM_Settings lbm_settings;
+
+float lbm_kernel_literal(const float x); // the float the reference's kernel sees for a constant printed by to_string(float) with 8 decimals (FX/utilities.hpp:2741-2750)
+inline void luw_check(const int rc) { if(rc!=LUW_OK) print_error(std::string("CUDA layer: ")+luw_last_error_string()); } // reference: any device error -> print_error (FX/opencl.hpp:613-618)
+
+// ---------------------------------------------------------------------------------------------------------------- Memory<T> (FX/opencl.hpp:331-603)
+// Host mirror (page-locked) + the device field of ONE domain. `d` dimensions, SoA: data()[n + c*N].
+template<typename T> class Memory {
+private:
+	luw_domain* dom = nullptr;
+	int field = 0;
+	ulong N = 0ull; uint d = 1u;
+	T* host = nullptr;
+public:
+	T* x = nullptr; T* y = nullptr; T* z = nullptr; // host pointers of the components (FX/opencl.hpp:343-349)
+	Memory() {}
+	Memory(luw_domain* dom, const int field, const ulong N, const uint dimensions, const T value) : dom(dom), field(field), N(N), d(dimensions) {
+		if(N*(ulong)d==0ull) print_error("Memory size must be larger than 0.");
+		void* p = nullptr;
+		luw_check(luw_host_alloc(&p, N*(ulong)d*sizeof(T)));
+		host = (T*)p;
+		x = host; if(d>1u) y = host+N; if(d>2u) z = host+2ull*N;
+		reset(value);
+	}
+	Memory(const Memory&) = delete;
+	Memory& operator=(const Memory&) = delete;
+	~Memory() { if(host) luw_host_free(host); }
+	void reset(const T value=(T)0) { for(ulong i=0ull; i<range(); i++) host[i] = value; }
+	ulong length() const { return N; }
+	uint dimensions() const { return d; }
+	ulong range() const { return N*(ulong)d; }
+	ulong capacity() const { return N*(ulong)d*sizeof(T); }
+	T* data() { return host; }
+	const T* data() const { return host; }
+	T& operator[](const ulong i) { return host[i]; }
+	const T& operator[](const ulong i) const { return host[i]; }
+	T operator()(const ulong i) const { return host[i]; }
+	T operator()(const ulong i, const uint dimension) const { return host[i+(ulong)dimension*N]; }
+	void enqueue_read_from_device() { luw_check(luw_download(dom, field, host, 0ull, range())); }
+	void enqueue_write_to_device() { luw_check(luw_upload(dom, field, host, 0ull, range())); }
+	void enqueue_read_from_device(const ulong offset, const ulong length) { luw_check(luw_download(dom, field, host+offset, offset, length)); }
+	void enqueue_write_to_device(const ulong offset, const ulong length) { luw_check(luw_upload(dom, field, host+offset, offset, length)); }
+	void finish_queue() { luw_check(luw_sync(dom)); }
+	void read_from_device() { enqueue_read_from_device(); finish_queue(); }
+	void write_to_device() { enqueue_write_to_device(); finish_queue(); }
+	void read_from_device(const ulong offset, const ulong length) { enqueue_read_from_device(offset, length); finish_queue(); }
+	void write_to_device(const ulong offset, const ulong length) { enqueue_write_to_device(offset, length); finish_queue(); }
+};
+
+// ---------------------------------------------------------------------------------------------------------------- LBM_Domain (FX/lbm.hpp:26-221)
+class LBM_Domain {
+private:
+	uint Nx=1u, Ny=1u, Nz=1u, Dx=1u, Dy=1u, Dz=1u; int Ox=0, Oy=0, Oz=0;
+	ulong t = 0ull;
+	float nu = 1.0f/6.0f, fx=0.0f, fy=0.0f, fz=0.0f, omega_x=0.0f, omega_y=0.0f, omega_z=0.0f;
+	int device = 0;
+	luw_domain* handle = nullptr; // declared before the buffers: they are built on it
+	ulong t_last_update_fields = max_ulong;
+	static luw_domain* create_handle(const int device, const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const int Ox, const int Oy, const int Oz, const float nu);
+public:
+	Memory<float> rho; Memory<float> u; Memory<uchar> flags; // host + device buffers of this domain (FX/lbm.hpp:60-63; rho starts at 1, u and flags at 0: FX/lbm.cpp:283-288)
+
+	LBM_Domain(const int device, const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const int Ox, const int Oy, const int Oz,
+		const float nu, const float fx, const float fy, const float fz);
+	~LBM_Domain();
+	LBM_Domain(const LBM_Domain&) = delete;
+	LBM_Domain& operator=(const LBM_Domain&) = delete;
+
+	void enqueue_initialize() { luw_check(luw_initialize(handle)); } // FX/lbm.cpp:340-343
+	void enqueue_stream_collide() { luw_check(luw_stream_collide(handle, t, fx, fy, fz, omega_x, omega_y, omega_z)); } // FX/lbm.cpp:344-346
+	void enqueue_update_fields() { // FX/lbm.cpp:348-355: only when UPDATE_FIELDS is off, and only once per time step
+		if(!(lbm_features()&LUW_UPDATE_FIELDS)&&t!=t_last_update_fields) { luw_check(luw_update_fields(handle, t, fx, fy, fz, omega_x, omega_y, omega_z)); t_last_update_fields = t; }
+	}
+	void increment_time_step(const uint steps=1u) { t += (ulong)steps; }
+	void reset_time_step() { t = 0ull; }
+	void finish_queue() { luw_check(luw_sync(handle)); }
+
+	uint get_Nx() const { return Nx; } uint get_Ny() const { return Ny; } uint get_Nz() const { return Nz; }
+	ulong get_N() const { return (ulong)Nx*(ulong)Ny*(ulong)Nz; }
+	uint get_Dx() const { return Dx; } uint get_Dy() const { return Dy; } uint get_Dz() const { return Dz; }
+	uint get_D() const { return Dx*Dy*Dz; }
+	int get_Ox() const { return Ox; } int get_Oy() const { return Oy; } int get_Oz() const { return Oz; }
+	float get_nu() const { return nu; } float get_fx() const { return fx; } float get_fy() const { return fy; } float get_fz() const { return fz; }
+	ulong get_t() const { return t; }
+	void set_fx(const float v) { fx = v; } void set_fy(const float v) { fy = v; } void set_fz(const float v) { fz = v; }
+	void set_f(const float x, const float y, const float z) { fx = x; fy = y; fz = z; }
+	void set_coriolis(const float x, const float y, const float z) { omega_x = x; omega_y = y; omega_z = z; } // FX/lbm.hpp:156-160
+	luw_domain* get_handle() const { return handle; } // reference: get_device() hands out the OpenCL Device; here the C-ABI handle
+	int get_device_ordinal() const { return device; }
+	ulong device_memory_used() const { uint64_t b = 0ull; luw_domain_bytes(handle, &b); return (ulong)b; } // Device_Info::memory_used (FX/info.cpp:233-241)
+	static uint lbm_features();
+};
+
+// ---------------------------------------------------------------------------------------------------------------- LBM (FX/lbm.hpp:223-633)
+class LBM {
+private:
+	uint Nx=1u, Ny=1u, Nz=1u, Dx=1u, Dy=1u, Dz=1u;
+	bool initialized = false;
+	std::vector<luw_domain*> handles;
+	void construct(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const float nu, const float fx, const float fy, const float fz);
+	void initialize(); // FX/lbm.cpp:1221-1260
+	void do_time_step(); // FX/lbm.cpp:1262-1290
+	void communicate(const int payload);
+public:
+	template<typename T> class Memory_Container { // FX/lbm.hpp:252-423: holds no data, stitches the domains' host mirrors into one global array
+	private:
+		ulong N = 0ull; uint d = 1u;
+		LBM* lbm = nullptr;
+		Memory<T>** buffers = nullptr;
+		uint Nx=1u, Ny=1u, Nz=1u, Dx=1u, Dy=1u, Dz=1u, D=1u, NxDx=1u, NyDy=1u, NzDz=1u, Hx=0u, Hy=0u, Hz=0u;
+		ulong NxNy=1ull, local_Nx=1ull, local_Ny=1ull, local_Nz=1ull, local_N=1ull;
+		T& reference(const ulong i, const uint dimension) { // FX/lbm.hpp:274-297: global index -> (domain, local index with halo offsets)
+			if(D==1u) return buffers[0]->data()[i%N+(ulong)std::max((ulong)dimension, i/N)*N];
+			const ulong global_i = i%N, tt = global_i%NxNy;
+			const uint x = (uint)(tt%(ulong)Nx), y = (uint)(tt/(ulong)Nx), z = (uint)(global_i/NxNy);
+			const uint px = x%NxDx, py = y%NyDy, pz = z%NzDz, dx = x/NxDx, dy = y/NyDy, dz = z/NzDz, domain = dx+(dy+dz*Dy)*Dx;
+			const ulong local_i = (ulong)(px+Hx)+((ulong)(py+Hy)+(ulong)(pz+Hz)*local_Ny)*local_Nx;
+			return buffers[domain]->data()[local_i+std::max(i/N, (ulong)dimension)*local_N];
+		}
+	public:
+		class Pointer {
+			Memory_Container* memory = nullptr; uint dimension = 0u;
+		public:
+			Pointer() {}
+			Pointer(Memory_Container* memory, const uint dimension) : memory(memory), dimension(dimension) {}
+			T& operator[](const ulong i) { return memory->reference(i, dimension); }
+			const T& operator[](const ulong i) const { return memory->reference(i, dimension); }
+		};
+		Pointer x, y, z;
+		Memory_Container() {}
+		Memory_Container(LBM* lbm, Memory<T>** buffers) { bind(lbm, buffers); }
+		void bind(LBM* lbm_, Memory<T>** buffers_) {
+			lbm = lbm_; buffers = buffers_;
+			N = lbm->get_N(); d = buffers[0]->dimensions();
+			Nx = lbm->get_Nx(); Ny = lbm->get_Ny(); Nz = lbm->get_Nz(); Dx = lbm->get_Dx(); Dy = lbm->get_Dy(); Dz = lbm->get_Dz(); D = Dx*Dy*Dz;
+			NxNy = (ulong)Nx*(ulong)Ny; NxDx = Nx/Dx; NyDy = Ny/Dy; NzDz = Nz/Dz; Hx = Dx>1u; Hy = Dy>1u; Hz = Dz>1u;
+			local_Nx = (ulong)(NxDx+2u*Hx); local_Ny = (ulong)(NyDy+2u*Hy); local_Nz = (ulong)(NzDz+2u*Hz); local_N = local_Nx*local_Ny*local_Nz;
+			x = Pointer(this, 0u); if(d>1u) y = Pointer(this, 1u); if(d>2u) z = Pointer(this, 2u);
+		}
+		void reset(const T value=(T)0) { for(uint i=0u; i<D; i++) buffers[i]->reset(value); }
+		ulong length() const { return N; }
+		uint dimensions() const { return d; }
+		ulong range() const { return N*(ulong)d; }
+		ulong capacity() const { return N*(ulong)d*sizeof(T); }
+		T& operator[](const ulong i) { return reference(i, 0u); }
+		const T& operator[](const ulong i) const { return const_cast<Memory_Container*>(this)->reference(i, 0u); }
+		T operator()(const ulong i) const { return const_cast<Memory_Container*>(this)->reference(i, 0u); }
+		T operator()(const ulong i, const uint dimension) const { return const_cast<Memory_Container*>(this)->reference(i, dimension); }
+		void read_from_device() { // FX/lbm.hpp:406-412
+			for(uint i=0u; i<D; i++) lbm->lbm_domain[i]->enqueue_update_fields();
+			for(uint i=0u; i<D; i++) buffers[i]->enqueue_read_from_device();
+			for(uint i=0u; i<D; i++) buffers[i]->finish_queue();
+		}
+		void write_to_device() { // FX/lbm.hpp:413-416
+			for(uint i=0u; i<D; i++) buffers[i]->enqueue_write_to_device();
+			for(uint i=0u; i<D; i++) buffers[i]->finish_queue();
+		}
+	};
+
+	LBM_Domain** lbm_domain = nullptr; // one LBM domain per GPU
+	Memory_Container<float> rho, u;
+	Memory_Container<uchar> flags;
+
+	LBM(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const float nu, const float fx=0.0f, const float fy=0.0f, const float fz=0.0f, const float sigma=0.0f, const float alpha=0.0f, const float beta=0.0f);
+	LBM(const uint Nx, const uint Ny, const uint Nz, const float nu, const float fx=0.0f, const float fy=0.0f, const float fz=0.0f, const float sigma=0.0f, const float alpha=0.0f, const float beta=0.0f);
+	LBM(const uint3 N, const uint Dx, const uint Dy, const uint Dz, const float nu, const float fx=0.0f, const float fy=0.0f, const float fz=0.0f, const float sigma=0.0f, const float alpha=0.0f, const float beta=0.0f);
+	LBM(const uint3 N, const float nu, const float fx=0.0f, const float fy=0.0f, const float fz=0.0f, const float sigma=0.0f, const float alpha=0.0f, const float beta=0.0f);
+	~LBM();
+	LBM(const LBM&) = delete;
+	LBM& operator=(const LBM&) = delete;
+
+	void run(const ulong steps=max_ulong, const ulong total_steps=max_ulong); // FX/lbm.cpp:1292-1312; run(0) = initialise only
+	void update_fields(); // FX/lbm.cpp:1314-1317
+	void reset(); // FX/lbm.cpp:1319-1321
+
+	uint get_Nx() const { return Nx; } uint get_Ny() const { return Ny; } uint get_Nz() const { return Nz; }
+	ulong get_N() const { return (ulong)Nx*(ulong)Ny*(ulong)Nz; }
+	uint get_Dx() const { return Dx; } uint get_Dy() const { return Dy; } uint get_Dz() const { return Dz; }
+	uint get_D() const { return Dx*Dy*Dz; }
+	float get_nu() const { return lbm_domain[0]->get_nu(); }
+	float get_tau() const { return 3.0f*get_nu()+0.5f; }
+	float get_fx() const { return lbm_domain[0]->get_fx(); } float get_fy() const { return lbm_domain[0]->get_fy(); } float get_fz() const { return lbm_domain[0]->get_fz(); }
+	ulong get_t() const { return lbm_domain[0]->get_t(); }
+	void set_fx(const float fx) { for(uint d=0u; d<get_D(); d++) lbm_domain[d]->set_fx(fx); }
+	void set_fy(const float fy) { for(uint d=0u; d<get_D(); d++) lbm_domain[d]->set_fy(fy); }
+	void set_fz(const float fz) { for(uint d=0u; d<get_D(); d++) lbm_domain[d]->set_fz(fz); }
+	void set_f(const float fx, const float fy, const float fz) { for(uint d=0u; d<get_D(); d++) lbm_domain[d]->set_f(fx, fy, fz); }
+	void set_coriolis(const float omega_x, const float omega_y, const float omega_z) { for(uint d=0u; d<get_D(); d++) lbm_domain[d]->set_coriolis(omega_x, omega_y, omega_z); } // FX/lbm.hpp:496-498
+
+	void coordinates(const ulong n, uint& x, uint& y, uint& z) const { const ulong t = n%((ulong)Nx*(ulong)Ny); x = (uint)(t%(ulong)Nx); y = (uint)(t/(ulong)Nx); z = (uint)(n/((ulong)Nx*(ulong)Ny)); } // FX/lbm.hpp:500-505
+	ulong index(const uint x, const uint y, const uint z) const { return (ulong)x+((ulong)y+(ulong)z*(ulong)Ny)*(ulong)Nx; }
+	float3 position(const uint x, const uint y, const uint z) const { return float3((float)x-0.5f*(float)Nx+0.5f, (float)y-0.5f*(float)Ny+0.5f, (float)z-0.5f*(float)Nz+0.5f); }
+	float3 position(const ulong n) const { uint x, y, z; coordinates(n, x, y, z); return position(x, y, z); }
+	float3 size() const { return float3((float)Nx, (float)Ny, (float)Nz); }
+	float3 center() const { return float3(0.5f*(float)Nx-0.5f, 0.5f*(float)Ny-0.5f, 0.5f*(float)Nz-0.5f); }
+private:
+	std::vector<Memory<float>*> rho_buffers, u_buffers;
+	std::vector<Memory<uchar>*> flags_buffers;
+};

@@ -81,8 +81,6 @@ class LBM(_Base):
 
     def __init__(self, shape, D=(1, 1, 1), devices=None, **kw):
         super().__init__(shape, D, **kw)
-        import torch  # device buffers for the halo payloads
-        self._torch = torch
         ndev = max(A.device_count(), 1)
         self.devices = list(devices) if devices is not None else [i % ndev for i in range(len(self._split))]
         self.domains = [self._make_domain(d, O, dev) for (d, O), dev in zip(self._split, self.devices)]
@@ -90,7 +88,6 @@ class LBM(_Base):
         self.u = np.zeros(3 * self.N, np.float32)
         self.flags = np.zeros(self.N, np.uint8)
         self._gidx = [_local_index(self.Ng, self.Nl, O) for _, O in self._split]
-        self._bufs = {}
 
     # ---- host <-> device (Memory_Container::write_to_device / read_from_device, FX/lbm.hpp:406-423)
     def write_to_device(self):
@@ -115,38 +112,17 @@ class LBM(_Base):
             for c in range(3):
                 self.u[c * self.N + g[k]] = dom.u[c * dom.N:(c + 1) * dom.N][k]
 
-    # ---- halo exchange (FX/lbm.cpp:1895-1958)
-    def _buffers(self, i, payload, axis):
-        key = (i, payload, axis)
-        if key not in self._bufs:
-            torch = self._torch
-            n = self.domains[i].halo_bytes(payload, axis)
-            dev = torch.device("cuda", self.devices[i])
-            self._bufs[key] = tuple(torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(4))  # send_p, send_m, recv_p, recv_m
-        return self._bufs[key]
-
-    def _neighbour(self, i, axis, step):
-        d = list(self._split[i][0])
-        d[axis] = (d[axis] + step) % self.D[axis]
-        return d[0] + self.D[0] * (d[1] + self.D[1] * d[2])
+    # ---- halo exchange (FX/lbm.cpp:1895-1958): extract, peer copies and insert are enqueued by the library, stream-ordered
+    def _handles(self):
+        import ctypes as C
+        if not hasattr(self, "_harr"):
+            self._harr = (C.c_void_p * len(self.domains))(*[dom._h for dom in self.domains])
+        return self._harr
 
     def communicate(self, payload):
+        t = self.domains[0].t
         for axis in AXES:
-            if self.D[axis] < 2:
-                continue
-            for i, dom in enumerate(self.domains):
-                sp, sm, _, _ = self._buffers(i, payload, axis)
-                dom.halo_extract(payload, axis, sp.data_ptr(), sm.data_ptr())
-            for dom in self.domains:
-                dom.finish_queue()
-            for i in range(len(self.domains)):  # what left through + arrives in the - halo of the +neighbour, and vice versa
-                sp, sm, _, _ = self._buffers(i, payload, axis)
-                self._buffers(self._neighbour(i, axis, +1), payload, axis)[3].copy_(sp)
-                self._buffers(self._neighbour(i, axis, -1), payload, axis)[2].copy_(sm)
-            self._torch.cuda.synchronize()
-            for i, dom in enumerate(self.domains):
-                _, _, rp, rm = self._buffers(i, payload, axis)
-                dom.halo_insert(payload, axis, rp.data_ptr(), rm.data_ptr())
+            A.check(A.lib().luw_halo_exchange(self._handles(), len(self.domains), payload, axis, t))
 
     # ---- LBM::initialize / do_time_step / run (FX/lbm.cpp:1221-1312)
     def initialize(self):
@@ -182,8 +158,10 @@ class LBM(_Base):
             dom.run_steps(steps)
             self.t += steps
         else:
-            for _ in range(steps):
-                self.do_time_step()
+            A.check(A.lib().luw_run_steps_multi(self._handles(), len(self.domains), self.t, steps, *map(float, self.f), *map(float, self.omega)))
+            for dom in self.domains:
+                dom.increment_time_step(steps)
+            self.t += steps
         for dom in self.domains:
             dom.finish_queue()
 

@@ -1,0 +1,94 @@
+"""The C++ host layer (latticeurbanwind_b200/host: the reference's LBM / LBM_Domain / Memory<T> API over the C ABI), driven through its
+command-line case driver luw_host_case."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from latticeurbanwind_b200 import cases
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "latticeurbanwind_b200", "lib")
+DRIVER = os.path.join(LIB, "luw_host_case")
+ZONES = dict(downstream_face=2, buffer_N=3, buffer_inv_tau=0.01, buffer_nudge_vertical=1, sponge_N=3, sponge_inv_tau=0.02)
+
+
+def build():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "latticeurbanwind_b200", "csrc"), "-j4"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "latticeurbanwind_b200", "host")], stdout=subprocess.DEVNULL)
+
+
+def run_driver(tmp_path, shape, D, precision, features, arith, nu, steps, flags, rho, u, f=H.FORCE, omega=H.OMEGA, zones=ZONES, check=True):
+    inp, out = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(inp, "wb") as fh:
+        fh.write(flags.tobytes()); fh.write(rho.tobytes()); fh.write(u.tobytes())
+    args = [DRIVER, *map(str, shape), *map(str, D), str(precision), str(features), str(arith), repr(float(nu)), str(steps), str(zones["downstream_face"]),
+            str(zones["buffer_N"]), repr(zones["buffer_inv_tau"]), str(zones["buffer_nudge_vertical"]), str(zones["sponge_N"]), repr(zones["sponge_inv_tau"]),
+            *[repr(float(v)) for v in f], *[repr(float(v)) for v in omega], inp, out]
+    r = subprocess.run(args, capture_output=True, text=True)
+    if check:
+        assert r.returncode == 0, r.stderr
+        N = int(np.prod(shape))
+        raw = np.fromfile(out, np.float32)
+        return raw[:N].copy(), raw[N:].copy()
+    return r
+
+
+def test_host_layer_builds_and_exports_the_reference_api():
+    build()
+    syms = subprocess.check_output(["nm", "-DC", os.path.join(LIB, "libluw_host.so")], text=True)
+    for name in ("LBM::run(", "LBM::reset()", "LBM::update_fields()", "LBM::LBM(uint3", "LBM_Domain::LBM_Domain(", "lbm_settings", "lbm_kernel_literal"):
+        assert name in syms, name
+
+
+def test_kernel_literal_matches_the_python_twin():
+    """def_w as the kernel sees it: C++ lbm_kernel_literal == cases.kernel_literal (both restate FX/utilities.hpp:2741-2750)."""
+    import ctypes as C
+    build()
+    L = C.CDLL(os.path.join(LIB, "libluw_host.so"))
+    fn = getattr(L, "_Z18lbm_kernel_literalf")
+    fn.restype, fn.argtypes = C.c_float, [C.c_float]
+    rng = np.random.default_rng(3)
+    vals = np.concatenate([np.exp(rng.uniform(-20, 20, 400)), [1.0, 1.9999992, 0.5, 1e-7, 3.3333334e-3, 12345.678]]).astype(np.float32)
+    for v in vals:
+        assert np.float32(fn(float(v))) == cases.kernel_literal(v), v
+
+
+def test_no_device_is_a_boxed_error_and_exit_1(tmp_path):
+    """Reference error convention (FX/utilities.hpp:4370-4382): print a boxed message, exit(1). Without a GPU the product path must fail loudly."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    build()
+    shape = (16, 8, 8)
+    flags, rho, u = cases.periodic_box(*shape)
+    r = run_driver(tmp_path, shape, (1, 1, 1), 0, 0, 0, 1 / 6, 1, flags, rho, u, check=False)
+    assert r.returncode == 1 and "Error" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", [0, 1], ids=["fp32", "fp16s"])
+def test_cpp_lbm_equals_oracle(oracle_lib, tmp_path, precision):
+    """LBM(N, nu) + flags/rho/u through the accessors + run(steps) + read_from_device == the oracle, bit for bit (STRICT arithmetic)."""
+    O = oracle_lib
+    shape = (128, 20, 12)
+    flags, rho, u = cases.urban(*shape, seed=5, edge=4, pitch=8)
+    nu = 1e-6
+    feat = H.FEATURE_SETS["luw"]
+    ref = H.run_cpu(O.Oracle(), O, shape, precision, feat, flags, rho, u, 6, cases.relaxation_rate(nu), zones=ZONES)
+    got_rho, got_u = run_driver(tmp_path, shape, (1, 1, 1), precision, feat, 0, nu, 6, flags, rho, u)
+    assert np.array_equal(got_rho, ref[1]) and np.array_equal(got_u, ref[2])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D", [(2, 1, 1), (1, 2, 2), (2, 2, 2)], ids=["2x1x1", "1x2x2", "2x2x2"])
+def test_cpp_decomposed_equals_single_domain(tmp_path, D):
+    """n_gpu = [Dx,Dy,Dz] through the C++ layer (domains share the GPUs that exist): identical fields to the single-domain run."""
+    shape = (128, 24, 16)
+    flags, rho, u = cases.urban(*shape, seed=21, edge=4, pitch=8)
+    feat = H.FEATURE_SETS["luw"]
+    one = run_driver(tmp_path, shape, (1, 1, 1), 1, feat, 1, 1e-6, 7, flags, rho, u)
+    dec = run_driver(tmp_path, shape, D, 1, feat, 1, 1e-6, 7, flags, rho, u)
+    assert np.array_equal(one[0], dec[0]) and np.array_equal(one[1], dec[1])
