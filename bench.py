@@ -41,6 +41,8 @@ WORKLOADS = {
     "channel512_fp32": ("channel", (512, 512, 512), 0, F_EQ, "chan", 1.0 / 6.0, "C2 empty channel 512^3 FP32 (TYPE_E x faces, TYPE_S walls), SRT nu=1/6"),
     "urban_fp16s": ("urban", (1024, 1024, 256), 1, F_VF | F_EQ | F_SG | F_NUDGE | F_SPONGE, "luwnf", 1e-6,
                     "C3 staggered cube array 1024x1024x256 FP16S, TYPE_E inflow, bounce-back, Coriolis, nudging N=16, sponge N=20, Smagorinsky; rho/u on demand"),
+    "urban_fp16s_nz": ("urban", (1024, 1024, 256), 1, F_VF | F_EQ | F_SG, "core", 1e-6,
+                       "C3 staggered cube array 1024x1024x256 FP16S without the relaxation zones (cost attribution only)"),
     "urban_fp16s_uf": ("urban", (1024, 1024, 256), 1, F_UF | F_VF | F_EQ | F_SG | F_NUDGE | F_SPONGE, "luw", 1e-6,
                        "C3 staggered cube array 1024x1024x256 FP16S, full LUW step with UPDATE_FIELDS (+16 B/cell rho/u stores)"),
 }

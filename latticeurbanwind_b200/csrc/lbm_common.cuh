@@ -26,6 +26,7 @@ struct DomainConst { // the def_* constants of FX/lbm.cpp:612-783 as kernel para
 	int wx, ex, sy, ny, tz; // local index of the global west/east/south/north/top boundary plane
 	int has_w, has_e, has_s, has_n, has_t;
 	float w; // def_w
+	float tau0, tau0sq; // 1/def_w and its square (IEEE single, as the Smagorinsky term forms them: FX/kernel.cpp:1735)
 	int precision; // P_FP32 / P_FP16S / P_FP16C
 	uint32_t features;
 	int downstream_face;

@@ -92,6 +92,12 @@ __device__ __forceinline__ void tma_wait_all_but(const uint32_t n) {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void consumer_bar(const uint32_t nthreads) { asm volatile("bar.sync 1, %0;" :: "r"(nthreads) : "memory"); }
+// LUW_PRODUCER_NAMED_BARRIER (experiment, off): named barriers 2 .. 2+STAGES-1 carry "stage s has been collided": the consumers arrive (non-blocking), the
+// producer warp syncs (blocks in hardware without taking issue slots; polling an mbarrier costs the producer ~12 % of all issued instructions,
+// profiles/r1_ncu_urban_fp16s.md). Measured slower than polling on the channel case (61.9 vs 68.0 GLUP/s with the single-pass kernel): BAR.ARV drains the
+// consumers' pending shared-memory stores, and the dynamic barrier id makes ptxas reserve all 16 barriers.
+__device__ __forceinline__ void bar_arrive_id(const uint32_t id, const uint32_t nthreads) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bar_sync_id(const uint32_t id, const uint32_t nthreads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ bool elect_one() { // one lane of the (converged) warp
 	uint32_t p;
 	asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(p));
@@ -117,8 +123,9 @@ __device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u
 __host__ __device__ constexpr bool pair_shifted(const int k) { return k==0||k==3||k==4||k==6||k==7; }
 __host__ __device__ constexpr bool box_shifted(const int b) { return b>0&&(b&1)==0&&pair_shifted((b-2)/2); }
 __host__ __device__ constexpr int pads_before_pair(const int k) { return (k>0)+(k>3)+(k>4)+(k>6)+(k>7); }
-template<int P_, int TX_, int TY_, int TZ_, int STAGES_, int CTAS_> struct TileCfg {
+template<int P_, int TX_, int TY_, int TZ_, int STAGES_, int CTAS_, bool TWOPASS_ = false> struct TileCfg {
 	static constexpr int P = P_, TX = TX_, TY = TY_, TZ = TZ_, STAGES = STAGES_, CTAS_PER_SM = CTAS_;
+	static constexpr bool TWOPASS = TWOPASS_; // FAST arithmetic only: collide in two passes over the shared-memory boxes (fewer registers, more resident CTAs)
 	static constexpr int TILE = TX*TY*TZ, ROWS = TY*TZ, CONSUMERS = TILE/2, THREADS = CONSUMERS+32;
 	static constexpr int ES = (P_==P_FP32) ? 4 : 2;
 	static constexpr int BOX_BYTES = TILE*ES, PAD = 128;
@@ -131,7 +138,12 @@ template<int P_, int TX_, int TY_, int TZ_, int STAGES_, int CTAS_> struct TileC
 	}
 	static_assert(TX%64==0&&TX<=256, "rows are whole warps; TMA boxes are at most 256 elements wide");
 	static_assert(CONSUMERS%32==0&&BOX_BYTES%128==0&&TILE%128==0&&2*ROWS*ES<=PAD, "tile shape");
+	static_assert(STAGES<=14, "one named barrier per stage (ids 2..15)");
 };
+// register budget per thread for `ctas` resident CTAs of `warps` warps: the register file is partitioned per SM sub-partition (4 x 16384), a CTA's warps are
+// dealt round-robin to the four, so ceil(warps*ctas/4) warps must fit into 16384 registers, in units of 8 per thread (measured: 5 CTAs x 5 warps at 80
+// registers gave 4 resident CTAs, 3 x 5 at 136 gave 2)
+__host__ __device__ constexpr int tile_max_regs(const int warps, const int ctas) { const int r = (16384/((warps*ctas+3)/4))/32/8*8; return r>128 ? 128 : r; }
 // pair k = (i-1)/2, i odd: c_i
 __device__ __forceinline__ void pair_shift(const int k, int& cx, int& cy, int& cz) {
 	const int CXv[9] = {1,0,0,1,1,0, 1, 1, 0}, CYv[9] = {0,1,0,1,0,1,-1, 0, 1}, CZv[9] = {0,0,1,0,1,1, 0,-1,-1};
@@ -150,6 +162,9 @@ template<> struct PairCodec<P_FP32> { // two floats
 	static __device__ __forceinline__ R shift_in(const R w0, const uint8_t* next) { return make_float2(w0.y, *(const float*)next); }
 	static __device__ __forceinline__ void shift_out(uint8_t* own, uint8_t* next, const R n, const bool k0, const bool k1) { if(k0) ((float*)own)[1] = n.x; if(k1) *(float*)next = n.y; }
 	static __device__ __forceinline__ void shift_out_both(uint8_t* own, uint8_t* next, const R n) { ((float*)own)[1] = n.x; *(float*)next = n.y; }
+	typedef uint32_t M; // lane mask of a pair: bit 0 / bit 1 = cell 0 / 1 takes the new value
+	static __device__ __forceinline__ M mask(const bool k0, const bool k1) { return (k0 ? 1u : 0u)|(k1 ? 2u : 0u); }
+	static __device__ __forceinline__ R mixm(const M m, const R n, const R o) { return make_float2((m&1u) ? n.x : o.x, (m&2u) ? n.y : o.y); }
 };
 template<> struct PairCodec<P_FP16S> { // half2 holding 2^15 f; the 2^15 is folded into the FAST collision, applied in STRICT
 	typedef uint32_t R;
@@ -163,6 +178,9 @@ template<> struct PairCodec<P_FP16S> { // half2 holding 2^15 f; the 2^15 is fold
 	static __device__ __forceinline__ R shift_in(const R w0, const uint8_t* next) { return __byte_perm(w0, (uint32_t)*(const uint16_t*)next, 0x5432); }
 	static __device__ __forceinline__ void shift_out(uint8_t* own, uint8_t* next, const R n, const bool k0, const bool k1) { if(k0) ((uint16_t*)own)[1] = (uint16_t)(n&0xFFFFu); if(k1) *(uint16_t*)next = (uint16_t)(n>>16); }
 	static __device__ __forceinline__ void shift_out_both(uint8_t* own, uint8_t* next, const R n) { ((uint16_t*)own)[1] = (uint16_t)(n&0xFFFFu); *(uint16_t*)next = (uint16_t)(n>>16); }
+	typedef uint32_t M; // bit mask of a pair: the halves that take the new value
+	static __device__ __forceinline__ M mask(const bool k0, const bool k1) { return (k0 ? 0x0000FFFFu : 0u)|(k1 ? 0xFFFF0000u : 0u); }
+	static __device__ __forceinline__ R mixm(const M m, const R n, const R o) { return (n&m)|(o&~m); }
 };
 template<> struct PairCodec<P_FP16C> {
 	typedef uint32_t R;
@@ -174,6 +192,9 @@ template<> struct PairCodec<P_FP16C> {
 	static __device__ __forceinline__ R shift_in(const R w0, const uint8_t* next) { return __byte_perm(w0, (uint32_t)*(const uint16_t*)next, 0x5432); }
 	static __device__ __forceinline__ void shift_out(uint8_t* own, uint8_t* next, const R n, const bool k0, const bool k1) { if(k0) ((uint16_t*)own)[1] = (uint16_t)(n&0xFFFFu); if(k1) *(uint16_t*)next = (uint16_t)(n>>16); }
 	static __device__ __forceinline__ void shift_out_both(uint8_t* own, uint8_t* next, const R n) { ((uint16_t*)own)[1] = (uint16_t)(n&0xFFFFu); *(uint16_t*)next = (uint16_t)(n>>16); }
+	typedef uint32_t M; // bit mask of a pair: the halves that take the new value
+	static __device__ __forceinline__ M mask(const bool k0, const bool k1) { return (k0 ? 0x0000FFFFu : 0u)|(k1 ? 0xFFFF0000u : 0u); }
+	static __device__ __forceinline__ R mixm(const M m, const R n, const R o) { return (n&m)|(o&~m); }
 };
 
 // ------------------------------------------------------------------ boundary helpers
@@ -242,8 +263,35 @@ template<uint32_t FEAT> __device__ __forceinline__ void equilibrium_cell(const D
 	}
 }
 
+// Two-pass FAST path: TYPE_E lanes run through the packed collision like any other cell and are overwritten afterwards, element by element, with
+// f := feq(boundary rho, u) (FX/kernel.cpp:1503-1515,1747). Out of line: it runs in the few warps that touch an open face, and keeping it (and a
+// second, select-carrying copy of the collision) out of the loop body keeps the loop inside the instruction cache (profiles/r1_ncu_urban_fp16s.md).
+// `raw16`: FP16S values are stored as the half of the already scaled number (scale = 2^15).
+template<class CFG, uint32_t FEAT> __device__ __noinline__ void fix_equilibrium(const DomainConst& c, const StepArgs& a, const uint64_t n, const bool e0, const bool e1, const float scale, uint8_t* bb, uint8_t* nxt) {
+	typedef typename PairCodec<CFG::P>::E E;
+	const auto enc1 = [&](const float v) -> E {
+		if constexpr (CFG::P==P_FP32) return v;
+		else if constexpr (CFG::P==P_FP16S) return __half_as_ushort(__float2half_rn(v)); // v carries the 2^15
+		else return Ddf<P_FP16C>::enc(v);
+	};
+#pragma unroll 1
+	for(uint32_t l=0u; l<2u; l++) {
+		if(!(l==0u ? e0 : e1)) continue;
+		const uint64_t m = n+(uint64_t)l;
+		float feq[Q];
+		equilibrium_cell<FEAT>(c, a, c.rho[m], c.u[m], c.u[c.N+m], c.u[2ull*c.N+m], scale, feq);
+		((E*)bb)[l] = enc1(feq[0]);
+#pragma unroll
+		for(int k=0; k<9; k++) {
+			((E*)(bb+CFG::box_off(1+2*k)))[l] = enc1(feq[2*k+2]); // slot A receives f_i+1
+			if(pair_shifted(k)) { if(l==0u) ((E*)(bb+CFG::box_off(2+2*k)))[1] = enc1(feq[2*k+1]); else *(E*)(nxt+CFG::box_off(2+2*k)) = enc1(feq[2*k+1]); }
+			else ((E*)(bb+CFG::box_off(2+2*k)))[l] = enc1(feq[2*k+1]); // slot B receives f_i
+		}
+	}
+}
+
 // ------------------------------------------------------------------ the kernel
-template<class CFG, uint32_t FEAT, bool FAST> __global__ void __launch_bounds__(CFG::THREADS, CFG::CTAS_PER_SM)
+template<class CFG, uint32_t FEAT, bool FAST> __global__ void __maxnreg__(((FAST&&CFG::TWOPASS) ? tile_max_regs(CFG::THREADS/32, CFG::CTAS_PER_SM) : 128)) // the single-pass paths hold all 19 DDF pairs: 128 registers, residency as it comes
 k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_constant__ StepArgs a, const __grid_constant__ TileMaps maps, const uint32_t tiles_x, const uint32_t tiles_y, const uint32_t tiles_z) {
 	constexpr int P = CFG::P, TX = CFG::TX, TY = CFG::TY, TZ = CFG::TZ, TILE = CFG::TILE, S = CFG::STAGES, NC = CFG::CONSUMERS;
 	typedef PairCodec<P> PC;
@@ -313,7 +361,11 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 		uint32_t sxt = 0u; // x tile of the next store
 		for(uint32_t q=0u; q<issued; q++) { // `issued` keeps growing until the strips run out
 			const int s = (int)(q%(uint32_t)S);
+#ifndef LUW_PRODUCER_NAMED_BARRIER
 			mbar_wait_backoff(bar_done+s, (q/(uint32_t)S)&1u);
+#else
+			bar_sync_id(2u+(uint32_t)s, (uint32_t)CFG::THREADS); // all consumers have arrived: stage s is collided and fenced for the async proxy
+#endif
 			if(leader) TRACE(0, q);
 			const uint32_t sstrip = tile_strip[s];
 			const int x0 = (int)sxt*TX, y0 = (int)(sstrip%tiles_y)*TY, z0 = (int)(sstrip/tiles_y)*TZ;
@@ -354,6 +406,8 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 	// walk: strips as published by the producer; inside a strip xt = 0..tiles_x-1; ring slot s and its phase advance with every tile
 	uint32_t xt = 0u, s = 0u, ph = 0u, kstrip = 0u;
 	int y0 = 0, z0 = 0, py0 = 0, pz0 = 0;
+	bool zone_yz = false; // this thread's row lies in a relaxation zone through its y / z position (decided once per strip)
+	const int zone_xe = Nb>=0 ? (int)c.Nxg-1-Nb-63-c.Ox : 0x7FFFFFFF; // a warp (64 x-consecutive cells from local x = xw) reaches the east shell iff xw >= zone_xe, the west shell iff xw + Ox <= Nb
 	for(uint32_t q=0u; ; q++) {
 		const uint32_t s1 = s+1u==(uint32_t)S ? 0u : s+1u, ph1 = s+1u==(uint32_t)S ? ph^1u : ph;
 		const int x0 = (int)xt*TX;
@@ -365,6 +419,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 			const uint32_t strip = tile_strip[s];
 			if(strip==END) break;
 			y0 = (int)(strip%tiles_y)*TY; z0 = (int)(strip/tiles_y)*TZ;
+			if(has_zones) { const int yg = y0+(int)ly+c.Oy, zg = z0+(int)lz+c.Oz; zone_yz = yg<=Nb||yg>=(int)c.Nyg-1-Nb||zg>=(int)c.Nzg-1-Nb||zg>=(int)c.Nzg-2-Ns; }
 		}
 		const bool bnd_yz = y0==0||y0+TY>=(int)c.Ny||z0==0||z0+TZ>=(int)c.Nz; // strip touches the y/z boundary (uniform)
 		const bool edge = bnd_yz||first||last;
@@ -415,15 +470,63 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 			const bool e0 = EQ&&run0&&bo0==TYPE_E, e1 = EQ&&run1&&bo1==TYPE_E;
 			PairIn in;
 			in.zones = false;
-			if(has_zones) { // tile-uniform pre-test: does the tile reach into a relaxation zone? then gather the per-cell zone data now
-				const int xg0 = x0+c.Ox, yg0 = y0+c.Oy, zg1 = z0+TZ-1+c.Oz;
-				if(xg0<=Nb||xg0+TX-1>=(int)c.Nxg-1-Nb||yg0<=Nb||yg0+TY-1>=(int)c.Nyg-1-Nb||zg1>=(int)c.Nzg-1-Nb||zg1>=(int)c.Nzg-2-Ns) {
+			if(has_zones) { // warp-uniform pre-test (a warp holds 64 x-consecutive cells of one row): does it reach into a relaxation zone? then gather the per-cell zone data now
+				const int xw = x0+(int)(lx&~63u);
+				if(zone_yz||xw+c.Ox<=Nb||xw>=zone_xe) {
 					in.nudge_vertical = c.nudge_vertical;
 					in.zr0 = zone_prefetch(c, x, y, z, run0&&bo0!=TYPE_E);
 					in.zr1 = zone_prefetch(c, x+1u, y, z, run1&&bo1!=TYPE_E);
 					in.zones = in.zr0.nudge||in.zr0.sponge||in.zr1.nudge||in.zr1.sponge;
 				}
 			}
+			const auto store_fields = [&](const PairOut& o) { // rho / u of the non-TYPE_E cells (UPDATE_FIELDS, FX/kernel.cpp:1709-1715)
+				if(UF) {
+					const bool w0 = run0&&!e0, w1 = run1&&!e1;
+					if(w0&&w1) {
+						*(float2*)(c.rho+n) = o.rho.v; *(float2*)(c.u+n) = o.ux.v; *(float2*)(c.u+c.N+n) = o.uy.v; *(float2*)(c.u+2ull*c.N+n) = o.uz.v;
+					} else {
+						if(w0) { c.rho[n] = o.rho.v.x; c.u[n] = o.ux.v.x; c.u[c.N+n] = o.uy.v.x; c.u[2ull*c.N+n] = o.uz.v.x; }
+						if(w1) { c.rho[n+1ull] = o.rho.v.y; c.u[n+1ull] = o.ux.v.y; c.u[c.N+n+1ull] = o.uy.v.y; c.u[2ull*c.N+n+1ull] = o.uz.v.y; }
+					}
+				}
+			};
+			PairOut out;
+			if constexpr (FAST&&CFG::TWOPASS) { // ---- two passes over the shared-memory boxes: moments, then relax + store (see lbm_vec.cuh)
+				constexpr bool SG = (FEAT&F_SUBGRID)!=0u;
+				uint8_t* const bb = (uint8_t*)box;
+				const auto dec_in = [](const R w) -> f2 { if constexpr (P==P_FP16S) return PairCodec<P_FP16S>::dec_raw(w); else return PC::dec(w); };
+				const auto enc_out = [](const f2 v) -> R { if constexpr (P==P_FP16S) return PairCodec<P_FP16S>::enc_raw(v); else return PC::enc(v); };
+				Moments M;
+				const f2 g0 = dec_in(*(const R*)bb);
+				M.R = g0;
+#pragma unroll
+				for(int k=0; k<9; k++) {
+					const R wa = *(const R*)(bb+CFG::box_off(1+2*k));
+					R wb = *(const R*)(bb+CFG::box_off(2+2*k));
+					if(pair_shifted(k)) wb = PC::shift_in(wb, nxt+CFG::box_off(2+2*k));
+					mom_add<SG>(M, k, dec_in(wa), dec_in(wb));
+				}
+				FastK K;
+				fast_prepare<FEAT>(c, a, in, M, scale, inv, K, out);
+				store_fields(out); // now: rho / u need not stay live through pass 2
+				asm volatile("" ::: "memory"); // pass 2 re-reads the boxes: the DDFs must not stay in registers
+				const typename PC::M msk = PC::mask(run0, run1);
+				*(R*)bb = PC::mixm(msk, enc_out(fma2(K.omw, g0, K.g0add)), *(const R*)bb);
+#pragma unroll
+				for(int k=0; k<9; k++) {
+					const int bA = 1+2*k, bB = 2+2*k;
+					const R wa = *(const R*)(bb+CFG::box_off(bA)), wb0 = *(const R*)(bb+CFG::box_off(bB));
+					R wb = wb0;
+					if(pair_shifted(k)) wb = PC::shift_in(wb0, nxt+CFG::box_off(bB));
+					f2 gi = dec_in(wa), gj = dec_in(wb);
+					fast_relax<FEAT>(K, k, gi, gj);
+					const R ni = enc_out(gi), nj = enc_out(gj); // f_i' goes to slot B, f_i+1' to slot A
+					*(R*)(bb+CFG::box_off(bA)) = PC::mixm(msk, nj, wa);
+					if(pair_shifted(k)) PC::shift_out(bb+CFG::box_off(bB), nxt+CFG::box_off(bB), ni, run0, run1);
+					else *(R*)(bb+CFG::box_off(bB)) = PC::mixm(msk, ni, wb0);
+				}
+				if(EQ&&(e0||e1)) fix_equilibrium<CFG, FEAT>(c, a, n, e0, e1, scale, bb, nxt);
+			} else {
 			// load_f: box 0 -> f0, box 1+2k -> f_(2k+1), box 2+2k -> f_(2k+2)
 			f2 f[Q];
 #pragma unroll
@@ -432,7 +535,6 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 				if(box_shifted(b)) w = PC::shift_in(w, nxt+CFG::box_off(b));
 				if(FAST&&P==P_FP16S) f[b] = PairCodec<P_FP16S>::dec_raw(*(const uint32_t*)&w); else f[b] = PC::dec(w);
 			}
-			PairOut out;
 			float4 eb0 = make_float4(1.0f, 0.0f, 0.0f, 0.0f), eb1 = eb0; // boundary rho/u of TYPE_E lanes (prefetched into L2 one tile ago)
 			if(FAST) {
 				if(EQ&&__any_sync(__activemask(), e0||e1)) { // warp-uniform: the common path carries no TYPE_E code
@@ -487,14 +589,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 					else *(R*)(bb+CFG::box_off(bB)) = PC::mix(run0, run1, nw[bA], *(R*)(bb+CFG::box_off(bB)));
 				}
 			}
-			if(UF) {
-				const bool w0 = run0&&!e0, w1 = run1&&!e1;
-				if(w0&&w1) {
-					*(float2*)(c.rho+n) = out.rho.v; *(float2*)(c.u+n) = out.ux.v; *(float2*)(c.u+c.N+n) = out.uy.v; *(float2*)(c.u+2ull*c.N+n) = out.uz.v;
-				} else {
-					if(w0) { c.rho[n] = out.rho.v.x; c.u[n] = out.ux.v.x; c.u[c.N+n] = out.uy.v.x; c.u[2ull*c.N+n] = out.uz.v.x; }
-					if(w1) { c.rho[n+1ull] = out.rho.v.y; c.u[n+1ull] = out.ux.v.y; c.u[c.N+n+1ull] = out.uy.v.y; c.u[2ull*c.N+n+1ull] = out.uz.v.y; }
-				}
+			store_fields(out);
 			}
 		}
 
@@ -504,7 +599,11 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 		}
 		fence_async_smem(); // make this thread's shared-memory writes visible to the TMA store
 		if(tid==0u) TRACE(5, q);
+#ifndef LUW_PRODUCER_NAMED_BARRIER
 		mbar_arrive(bar_done+s);
+#else
+		bar_arrive_id(2u+s, (uint32_t)CFG::THREADS);
+#endif
 		s = s1; ph = ph1;
 		if(last) { xt = 0u; py0 = y0; pz0 = z0; kstrip++; } else xt++;
 	}

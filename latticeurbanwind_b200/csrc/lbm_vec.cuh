@@ -30,8 +30,8 @@ __device__ __forceinline__ f2 div_rn2(const f2 a, const f2 b) { return mk2(__fdi
 __device__ __forceinline__ f2 div_rn2(const float a, const f2 b) { return mk2(__fdiv_rn(a, b.v.x), __fdiv_rn(a, b.v.y)); }
 __device__ __forceinline__ f2 sqrt_rn2(const f2 a) { return mk2(__fsqrt_rn(a.v.x), __fsqrt_rn(a.v.y)); }
 __device__ __forceinline__ f2 clampc2(const f2 a) { return mk2(fminf(fmaxf(a.v.x, -LAT_C), LAT_C), fminf(fmaxf(a.v.y, -LAT_C), LAT_C)); }
-__device__ __forceinline__ float rcp_approx(const float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float sqrt_approx(const float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_approx(const float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sqrt_approx(const float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ f2 rcp2(const f2 a) { return mk2(rcp_approx(a.v.x), rcp_approx(a.v.y)); }
 __device__ __forceinline__ f2 sqrt2(const f2 a) { return mk2(sqrt_approx(a.v.x), sqrt_approx(a.v.y)); }
 __device__ __forceinline__ f2 sel2(const bool c0, const bool c1, const f2 a, const f2 b) { return mk2(c0 ? a.v.x : b.v.x, c1 ? a.v.y : b.v.y); }
@@ -271,8 +271,7 @@ template<uint32_t FEAT, bool HAS_E> __device__ __forceinline__ void collide_fast
 		const f2 Hxx = fma2(Pxx, inv, -fma2(rux, ux, r3)), Hyy = fma2(Pyy, inv, -fma2(ruy, uy, r3)), Hzz = fma2(Pzz, inv, -fma2(ruz, uz, r3));
 		const f2 Hxy = fma2(Pxy, inv, -(rux*uy)), Hxz = fma2(Pxz, inv, -(rux*uz)), Hyz = fma2(Pyz, inv, -(ruy*uz));
 		const f2 Qn = fma2(Hxx, Hxx, fma2(Hyy, Hyy, Hzz*Hzz))+2.0f*fma2(Hxy, Hxy, fma2(Hxz, Hxz, Hyz*Hyz));
-		const float tau0 = __fdiv_rn(1.0f, c.w);
-		const f2 den = bc(tau0)+sqrt2(fma2(0.76421222f*sqrt2(Qn), ir, bc(__fmul_rn(tau0, tau0))));
+		const f2 den = bc(c.tau0)+sqrt2(fma2(0.76421222f*sqrt2(Qn), ir, bc(c.tau0sq))); // tau0 = 1/def_w and its square, rounded like the kernel would (host, luw_cabi.cu)
 		f2 id = rcp2(den);
 		id = fma2(id, fma2(-den, id, bc(1.0f)), id);
 		w = 2.0f*id;
@@ -311,6 +310,94 @@ template<uint32_t FEAT, bool HAS_E> __device__ __forceinline__ void collide_fast
 		}
 		g[0] = fma2(omw, g[0], (2.0f*hw)*feq0);
 	}
+}
+
+// ------------------------------------------------------------------- FAST, two passes over the DDFs (low register footprint)
+// The same regrouped collision as collide_fast2, split so that the 19 DDF pairs never have to be live at once: pass 1 accumulates density,
+// momentum and second moments pair by pair (mom_add), fast_prepare turns them into the per-cell constants of the relaxation, pass 2 re-reads
+// each pair from shared memory and relaxes it (fast_relax). TYPE_E lanes are not handled here (the tile kernel overwrites them afterwards).
+struct Moments { f2 R, mx, my, mz, Pxx, Pyy, Pzz, Pxy, Pxz, Pyz; };
+template<bool SG> __device__ __forceinline__ void mom_add(Moments& M, const int k, const f2 gi, const f2 gj) {
+	const f2 sk = gi+gj, dk = gi-gj;
+	M.R = M.R+sk;
+	switch(k) {
+		case 0: M.mx = dk; if(SG) M.Pxx = sk; break;
+		case 1: M.my = dk; if(SG) M.Pyy = sk; break;
+		case 2: M.mz = dk; if(SG) M.Pzz = sk; break;
+		case 3: M.mx = M.mx+dk; M.my = M.my+dk; if(SG) { M.Pxx = M.Pxx+sk; M.Pyy = M.Pyy+sk; M.Pxy = sk; } break;
+		case 4: M.mx = M.mx+dk; M.mz = M.mz+dk; if(SG) { M.Pxx = M.Pxx+sk; M.Pzz = M.Pzz+sk; M.Pxz = sk; } break;
+		case 5: M.my = M.my+dk; M.mz = M.mz+dk; if(SG) { M.Pyy = M.Pyy+sk; M.Pzz = M.Pzz+sk; M.Pyz = sk; } break;
+		case 6: M.mx = M.mx+dk; M.my = M.my-dk; if(SG) { M.Pxx = M.Pxx+sk; M.Pyy = M.Pyy+sk; M.Pxy = M.Pxy-sk; } break;
+		case 7: M.mx = M.mx+dk; M.mz = M.mz-dk; if(SG) { M.Pxx = M.Pxx+sk; M.Pzz = M.Pzz+sk; M.Pxz = M.Pxz-sk; } break;
+		default: M.my = M.my+dk; M.mz = M.mz-dk; if(SG) { M.Pyy = M.Pyy+sk; M.Pzz = M.Pzz+sk; M.Pyz = M.Pyz-sk; } break;
+	}
+}
+struct FastK { f2 omw, hws, hwe, wrs, wre, h1s, h1e, kcs, kce, c3, uF3, g0add; Proj A3, F; }; // see the derivation above collide_fast2
+template<uint32_t FEAT> __device__ __forceinline__ void fast_prepare(const DomainConst& c, const StepArgs& a, const PairIn& in, const Moments& M, const float scale, const float inv, FastK& K, PairOut& out) {
+	constexpr bool VF = (FEAT&F_VOLUME_FORCE)!=0u, SG = (FEAT&F_SUBGRID)!=0u;
+	const f2 rhom1 = inv*M.R;
+	const f2 rho = rhom1+bc(1.0f);
+	f2 ir = rcp2(rho);
+	ir = fma2(ir, fma2(-rho, ir, bc(1.0f)), ir); // one Newton step: full single precision
+	const f2 iri = inv*ir;
+	f2 ux = M.mx*iri, uy = M.my*iri, uz = M.mz*iri;
+	K.uF3 = bc(0.0f);
+	if(VF) {
+		const f2 m2rho = -2.0f*rho;
+		K.F.x = fma2(m2rho, fma2(a.oy, uz, -(a.oz*uy)), bc(a.fx));
+		K.F.y = fma2(m2rho, fma2(a.oz, ux, -(a.ox*uz)), bc(a.fy));
+		K.F.z = fma2(m2rho, fma2(a.ox, uy, -(a.oy*ux)), bc(a.fz));
+		if(in.zones) zone_force2(in, rho, ux, uy, uz, K.F.x, K.F.y, K.F.z);
+		const f2 rho2 = 0.5f*ir;
+		ux = clampc2(fma2(K.F.x, rho2, ux)); uy = clampc2(fma2(K.F.y, rho2, uy)); uz = clampc2(fma2(K.F.z, rho2, uz));
+		K.uF3 = -(fma2(ux, K.F.x, fma2(uy, K.F.y, uz*K.F.z))); // = 3*uF = -(u.F)
+	} else {
+		ux = clampc2(ux); uy = clampc2(uy); uz = clampc2(uz);
+	}
+	out.rho = rho; out.ux = ux; out.uy = uy; out.uz = uz;
+	f2 w = bc(c.w);
+	if(SG) { // Smagorinsky-Lilly (FX/kernel.cpp:1723-1736) from the second moments
+		const f2 rux = rho*ux, ruy = rho*uy, ruz = rho*uz, r3 = 0.33333334f*rhom1;
+		const f2 Hxx = fma2(M.Pxx, inv, -fma2(rux, ux, r3)), Hyy = fma2(M.Pyy, inv, -fma2(ruy, uy, r3)), Hzz = fma2(M.Pzz, inv, -fma2(ruz, uz, r3));
+		const f2 Hxy = fma2(M.Pxy, inv, -(rux*uy)), Hxz = fma2(M.Pxz, inv, -(rux*uz)), Hyz = fma2(M.Pyz, inv, -(ruy*uz));
+		const f2 Qn = fma2(Hxx, Hxx, fma2(Hyy, Hyy, Hzz*Hzz))+2.0f*fma2(Hxy, Hxy, fma2(Hxz, Hxz, Hyz*Hyz));
+		const f2 den = bc(c.tau0)+sqrt2(fma2(0.76421222f*sqrt2(Qn), ir, bc(c.tau0sq))); // tau0 = 1/def_w and its square, rounded like the kernel would (host, luw_cabi.cu)
+		f2 id = rcp2(den);
+		id = fma2(id, fma2(-den, id, bc(1.0f)), id);
+		w = 2.0f*id;
+	}
+	K.c3 = -3.0f*fma2(ux, ux, fma2(uy, uy, uz*uz));
+	K.A3.x = 3.0f*ux; K.A3.y = 3.0f*uy; K.A3.z = 3.0f*uz; // a = 3 c.u
+	K.omw = bc(1.0f)-w;
+	const f2 hw = (0.5f*scale)*w; // S*w/2
+	const f2 hwr = hw*rho; // S*w*rho/2
+	K.hws = WS*hwr; K.hwe = WE*hwr; // S*w*r/2 per weight class
+	K.wrs = 2.0f*K.hws; K.wre = 2.0f*K.hwe; // S*w*r
+	const f2 hw1 = hw*rhom1;
+	K.h1s = (2.0f*WS)*hw1; K.h1e = (2.0f*WE)*hw1; // S*w/2 * 2 w_i (rho-1)
+	const f2 feq0 = W0*fma2(rho, 0.5f*K.c3, rhom1);
+	if(VF) {
+		const f2 c_tau = fma2(w, -0.5f, bc(1.0f));
+		K.kcs = (9.0f*WS/3.0f*scale)*c_tau; K.kce = (9.0f*WE/3.0f*scale)*c_tau; // S*kc/3
+		K.g0add = fma2(2.0f*hw, feq0, ((9.0f*W0/3.0f*scale)*c_tau)*K.uF3);
+	} else {
+		K.kcs = K.kce = bc(0.0f);
+		K.g0add = (2.0f*hw)*feq0;
+	}
+}
+template<uint32_t FEAT> __device__ __forceinline__ void fast_relax(const FastK& K, const int k, f2& gi, f2& gj) {
+	constexpr bool VF = (FEAT&F_VOLUME_FORCE)!=0u;
+	const f2 ak = proj(K.A3, k);
+	f2 U, V;
+	if(VF) {
+		const f2 Ak = proj(K.F, k), kc = k<3 ? K.kcs : K.kce;
+		U = fma2(kc, fma2(Ak, ak, K.uF3), fma2(k<3 ? K.hws : K.hwe, fma2(ak, ak, K.c3), k<3 ? K.h1s : K.h1e));
+		V = fma2(k<3 ? K.wrs : K.wre, ak, kc*Ak);
+	} else {
+		U = fma2(k<3 ? K.hws : K.hwe, fma2(ak, ak, K.c3), k<3 ? K.h1s : K.h1e);
+		V = (k<3 ? K.wrs : K.wre)*ak;
+	}
+	gi = fma2(K.omw, gi, U+V); gj = fma2(K.omw, gj, U-V);
 }
 
 } // anonymous namespace

@@ -105,14 +105,15 @@ void setup_tiles(luw_domain* d) {
 	const char* off = getenv("LUW_NO_TILE");
 	if(off&&off[0]=='1') return;
 	const char* var = getenv("LUW_TILE_VARIANT");
-	const int want = var ? atoi(var) : 0;
+	// default: two-pass kernel; 5 CTAs/SM where the collision fits 72 registers (no LES), else 128x4 tiles with 8 consumer warps per producer (measured, profiles/)
+	const int want = var ? atoi(var) : (d->c.precision!=luw::P_FP32&&(d->c.features&luw::F_SUBGRID)) ? 4 : 0;
 	const luw::DomainConst& c = d->c;
 	if(c.Nx%16u!=0u) return;
 	encode_tiled_fn enc = get_encode_tiled();
 	if(!enc) return;
 	luw::TileShape sh;
 	bool found = false;
-	for(int v : { want, 2, 0, 1 }) { // the requested variant, else one whose tile is not wider than the lattice
+	for(int v : { want, 0, 2 }) { // the requested variant, else one whose tile is not wider than the lattice
 		if(d->ks->tile_shape(c.precision, c.features, v, &sh)&&c.Nx>=(uint32_t)sh.tx) { d->tile_variant = v; found = true; break; }
 	}
 	if(!found) return;
@@ -240,7 +241,7 @@ int luw_domain_create(const luw_domain_params* p, luw_domain** out) {
 	c.wx = -p->Ox; c.ex = (int)c.Nxg-1-p->Ox; c.sy = -p->Oy; c.ny = (int)c.Nyg-1-p->Oy; c.tz = (int)c.Nzg-1-p->Oz;
 	c.has_w = c.wx>=0&&c.wx<(int)c.Nx; c.has_e = c.ex>=0&&c.ex<(int)c.Nx;
 	c.has_s = c.sy>=0&&c.sy<(int)c.Ny; c.has_n = c.ny>=0&&c.ny<(int)c.Ny; c.has_t = c.tz>=0&&c.tz<(int)c.Nz;
-	c.w = p->w; c.precision = (int)p->precision; c.features = p->features;
+	c.w = p->w; c.tau0 = 1.0f/p->w; c.tau0sq = c.tau0*c.tau0; c.precision = (int)p->precision; c.features = p->features;
 	c.downstream_face = p->downstream_face;
 	c.buffer_N = p->buffer_N; c.buffer_inv_tau = p->buffer_inv_tau; c.nudge_vertical = p->buffer_nudge_vertical;
 	c.sponge_N = p->sponge_N;
