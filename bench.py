@@ -12,7 +12,7 @@ Workloads (BASELINE.json configs; the per-GPU block is fixed -> weak scaling):
   channel512_fp32    configs[1], FP32 DDFs
   urban_fp16s        configs[2]: staggered cube array 1024x1024x256, TYPE_E inflow, bounce-back cubes, Coriolis, nudging, sponge, Smagorinsky, FP16S
   urban_fp16s_uf     the same with UPDATE_FIELDS (rho/u stored every step, +16 B/cell), LUW's shipped semantics
-N > 1 (torchrun, one rank per GPU): the lattice is decomposed like the reference's published multi-GPU runs (2x1x1, 2x2x1, 2x2x2); every rank owns
+N > 1 (torchrun, one rank per GPU): the lattice is decomposed along z and y first (--decomp for other layouts, see DECOMP); every rank owns
 one block of the same local size (halo layers included), halo DDFs move over NVLink.
 
 The JSON line carries, besides the contract keys: `roofline` (dominant kernel, algorithmic bytes per launch / CUDA-event duration against
@@ -50,7 +50,11 @@ ZONES = dict(downstream_face=2, buffer_N=16, buffer_inv_tau=0.01, buffer_nudge_v
 OMEGA = (0.0, 5.6e-6, 4.7e-6)  # Omega_lbm of SURVEY.md 8d (7.292e-5 * (cos 40, sin 40) * dt)
 B_ALG = {0: 153, 1: 77, 2: 77}  # algorithmic bytes per cell-step: 19 DDF loads + 19 stores + 1 flag byte (FX/lbm.cpp:121-122)
 DTYPE = {0: "f32 arithmetic, f32 DDF storage", 1: "f32 arithmetic, FP16S DDF storage", 2: "f32 arithmetic, FP16C DDF storage"}
-DECOMP = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}  # the reference's published multi-GPU layouts (FluidX3D README)
+# Decomposition per GPU count (the deck's n_gpu). Faces normal to x are the expensive ones in this memory layout (every face cell is a 2-byte element in
+# its own 1 KB row: measured 39 + 60 us to extract + insert a 131 k-cell x face against 9 + 9 us for a z face, profiles/), so the defaults split z and y
+# first, like a deck author would; --decomp selects any other layout, e.g. the reference README's 2,1,1 / 2,2,1 / 2,2,2.
+DECOMP = {"channel": {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (1, 2, 4)},
+          "urban": {1: (1, 1, 1), 2: (1, 2, 1), 4: (1, 4, 1), 8: (1, 8, 1)}}
 
 
 def measured_peaks():
@@ -181,6 +185,8 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("LUW_BENCH_WORKLOAD", "channel512_fp16s"), choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--arith", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--transport", default="ipc", choices=["ipc", "nccl"], help="N>1: halo payload by remote stores into IPC-mapped peer memory (default) or NCCL send/recv")
+    ap.add_argument("--decomp", default="", help="N>1: Dx,Dy,Dz (product = N); default: see DECOMP")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--also", default="", help="comma-separated extra workloads measured after the headline one (N=1) and reported under `also`")
@@ -321,13 +327,16 @@ def bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src):
     from latticeurbanwind_b200.lbm import DistributedLBM
     case, shape, precision, features, fset, nu, desc = WORKLOADS[args.workload]
     torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # NCCL would print its version banner on stdout, in front of the JSON line
+        os.environ["NCCL_DEBUG"] = "WARN"
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    D = DECOMP[world]
+    D = tuple(int(v) for v in args.decomp.split(",")) if args.decomp else DECOMP[case][world]
+    assert len(D) == 3 and D[0] * D[1] * D[2] == world, "--decomp must multiply to the number of ranks"
     H = tuple(1 if v > 1 else 0 for v in D)
     Ng = tuple((n - 2 * h) * v for n, h, v in zip(shape, H, D))  # global lattice whose blocks have exactly the workload's local size incl. halos
     zones = ZONES if features & (F_NUDGE | F_SPONGE) else {}
     lbm = DistributedLBM(Ng, D, device=local, nu=nu, precision=precision, features=features, arith=arith,
-                         omega=OMEGA if features & F_VF else (0.0, 0.0, 0.0), **zones)
+                         omega=OMEGA if features & F_VF else (0.0, 0.0, 0.0), transport=args.transport, **zones)
     assert tuple(lbm.Nl) == tuple(shape)
     flags, rho, u = cases.block_case(case, Ng, lbm.O, shape)
     lbm.initialize(flags, rho, u)
@@ -339,7 +348,7 @@ def bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src):
         clk.start()
     launches0 = lbm.domain.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); lbm.run(K); e1.record()
+    e0.record(lbm._stream); lbm.run(K); e1.record(lbm._stream)  # on the stream the step and the halo exchange are enqueued on
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
     dist.barrier(); torch.cuda.synchronize()
@@ -360,7 +369,7 @@ def bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src):
         res = {"metric": "D3Q19 MLUP/s", "value": mlups, "unit": "MLUP/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[precision], "data": "synthetic",
                "config": {"workload": desc, "name": args.workload, "lattice": list(Ng), "block_per_gpu_incl_halo": list(shape), "features": features,
-                          "arith": args.arith, "decomposition": list(D), "l2": "state per GPU is far larger than the 126 MB L2; no flush needed"},
+                          "arith": args.arith, "decomposition": list(D), "halo_transport": args.transport, "l2": "state per GPU is far larger than the 126 MB L2; no flush needed"},
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                             "kernel": "k_stream_collide_tile", "kernel_ms": kern_ms, "share_of_step": kern_ms / (ms / K), "alg_bytes_per_cell": B_ALG[precision],
                             "cells_per_launch": Nloc, "peak_source": peak_src},

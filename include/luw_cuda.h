@@ -116,6 +116,18 @@ int luw_halo_insert(luw_domain* dom, int payload, uint32_t axis, uint64_t t, con
  * (d +- 1) % D, insert on every domain -- all asynchronous on the domains' streams, ordered by events; no host staging, no host synchronisation.
  * Axes must be exchanged in the order x, y, z (edge / corner DDFs travel through two hops, like in the reference). */
 int luw_halo_exchange(luw_domain* const* doms, uint32_t count, int payload, uint32_t axis, uint64_t t);
+/* LBM::communicate_field, FX/lbm.cpp:1907-1935, for the one-process-per-GPU driver (every rank owns ONE domain of the decomposition; all ranks on one
+ * NVLink / NVSwitch node). The receive buffers of a domain are exported with CUDA IPC; a neighbour maps them and its extract kernel stores the face payload
+ * straight into them over NVLink (no staging copy, no NCCL call on the step path), then raises a sequence flag in the same mapping; the receiver's stream
+ * waits for the flags of both neighbours and runs the insert kernel. Two buffer sets alternate, which is enough because a rank cannot start exchange s+2
+ * on an axis before its neighbours have finished inserting exchange s (their exchange s+1, which this rank waits for, is enqueued after it).
+ *   export:   allocates the axis' receive block and writes its 64-byte cudaIpcMemHandle_t to `handle_out`;
+ *   connect:  maps the blocks of the (+) and the (-) neighbour rank (the two handles are equal when the axis has two domains);
+ *   exchange: extract -> remote stores -> signal -> wait -> insert, all enqueued on the domain's stream; every rank must issue the same sequence of
+ *             exchanges per axis (payloads may alternate: rho_u_flags at initialisation, fi every step). Axes in the order x, y, z. */
+int luw_halo_ipc_export(luw_domain* dom, uint32_t axis, void* handle_out);
+int luw_halo_ipc_connect(luw_domain* dom, uint32_t axis, const void* handle_up, const void* handle_dn);
+int luw_halo_ipc_exchange(luw_domain* dom, int payload, uint32_t axis, uint64_t t);
 /* LBM::do_time_step for `k` steps t0..t0+k-1 on all domains of a decomposition (FX/lbm.cpp:1262-1290): stream_collide on every domain, then
  * luw_halo_exchange(HALO_FI) for x, y, z. The reference's per-step finish_queue / barriers are gone: everything is stream-ordered. */
 int luw_run_steps_multi(luw_domain* const* doms, uint32_t count, uint64_t t0, uint64_t k, float fx, float fy, float fz, float omega_x, float omega_y, float omega_z);

@@ -124,21 +124,24 @@ template<int P, uint32_t FEAT> __global__ void __launch_bounds__(128) k_update_f
 __constant__ uint8_t XFER[6][5] = { // index_transfer(), D3Q19: the 5 DDFs that cross each face
 	{1, 7,13, 9,15}, {2, 8,14,10,16}, {3, 7,14,11,17}, {4, 8,13,12,18}, {5, 9,16,11,18}, {6,10,15,12,17}
 };
-// face cell a of axis d on layer `layer` -> (x,y,z); a runs like index_extract_p/m: x: a=y+z*Ny, y: a=z+x*Nz, z: a=x+y*Nx
-__device__ __forceinline__ void face_xyz(const DomainConst& c, const uint32_t d, const uint32_t a, const uint32_t layer, uint32_t& x, uint32_t& y, uint32_t& z) {
-	if(d==0u) { x = layer; y = a%c.Ny; z = a/c.Ny; }
-	else if(d==1u) { x = a/c.Nz; y = layer; z = a%c.Nz; }
-	else { x = a%c.Nx; y = a/c.Nx; z = layer; }
+// thread index t of a face of axis d on layer `layer` -> cell (x,y,z) and payload index a. The reference numbers face cells like index_extract_p/m
+// (FX/kernel.cpp:2192-2207): x: a=y+z*Ny, y: a=z+x*Nz, z: a=x+y*Nx. Threads always run x-fastest where the face has an x extent, so that lattice
+// accesses coalesce (the reference's y-face order walks z fastest: a stride of Nx*Ny elements per thread, measured 2.4x slower than a z face of the same area);
+// `xfast` also lays the payload out in thread order -- for buffers that only this library reads (in-process and IPC exchanges).
+__device__ __forceinline__ void face_xyz(const DomainConst& c, const uint32_t d, const uint32_t t, const uint32_t layer, const bool xfast, uint32_t& x, uint32_t& y, uint32_t& z, uint32_t& a) {
+	if(d==0u) { x = layer; y = t%c.Ny; z = t/c.Ny; a = t; }
+	else if(d==1u) { x = t%c.Nx; y = layer; z = t/c.Nx; a = xfast ? t : z+x*c.Nz; }
+	else { x = t%c.Nx; y = t/c.Nx; z = layer; a = t; }
 }
 __device__ __forceinline__ uint32_t axis_len(const DomainConst& c, const uint32_t d) { return d==0u ? c.Nx : d==1u ? c.Ny : c.Nz; }
 
 // one thread per (face cell, side); raw fpxx copies, no conversion
-template<typename T, bool INSERT> __global__ void __launch_bounds__(128) k_halo_fi(const __grid_constant__ DomainConst c, const uint32_t d, const uint32_t A, const uint32_t odd, T* __restrict__ buf_p, T* __restrict__ buf_m) {
-	const uint32_t a = blockIdx.x*blockDim.x+threadIdx.x, side = blockIdx.y;
-	if(a>=A) return;
+template<typename T, bool INSERT> __global__ void __launch_bounds__(128) k_halo_fi(const __grid_constant__ DomainConst c, const uint32_t d, const uint32_t A, const uint32_t odd, const bool xfast, T* __restrict__ buf_p, T* __restrict__ buf_m) {
+	const uint32_t t = blockIdx.x*blockDim.x+threadIdx.x, side = blockIdx.y;
+	if(t>=A) return;
 	const uint32_t L = axis_len(c, d);
-	uint32_t x, y, z;
-	face_xyz(c, d, a, INSERT ? (side==0u ? L-1u : 0u) : (side==0u ? L-2u : 1u), x, y, z);
+	uint32_t x, y, z, a;
+	face_xyz(c, d, t, INSERT ? (side==0u ? L-1u : 0u) : (side==0u ? L-2u : 1u), xfast, x, y, z, a);
 	uint64_t j[Q];
 	neighbors(c, x, y, z, j);
 	T* fi = (T*)c.fi;
@@ -157,12 +160,12 @@ template<typename T, bool INSERT> __global__ void __launch_bounds__(128) k_halo_
 		}
 	}
 }
-template<bool INSERT> __global__ void __launch_bounds__(128) k_halo_rho_u_flags(const __grid_constant__ DomainConst c, const uint32_t d, const uint32_t A, char* __restrict__ buf_p, char* __restrict__ buf_m) {
-	const uint32_t a = blockIdx.x*blockDim.x+threadIdx.x, side = blockIdx.y;
-	if(a>=A) return;
+template<bool INSERT> __global__ void __launch_bounds__(128) k_halo_rho_u_flags(const __grid_constant__ DomainConst c, const uint32_t d, const uint32_t A, const bool xfast, char* __restrict__ buf_p, char* __restrict__ buf_m) {
+	const uint32_t t = blockIdx.x*blockDim.x+threadIdx.x, side = blockIdx.y;
+	if(t>=A) return;
 	const uint32_t L = axis_len(c, d);
-	uint32_t x, y, z;
-	face_xyz(c, d, a, INSERT ? (side==0u ? L-1u : 0u) : (side==0u ? L-2u : 1u), x, y, z);
+	uint32_t x, y, z, a;
+	face_xyz(c, d, t, INSERT ? (side==0u ? L-1u : 0u) : (side==0u ? L-2u : 1u), xfast, x, y, z, a);
 	const uint64_t n = x+((uint64_t)y+(uint64_t)z*c.Ny)*c.Nx;
 	char* buf = side==0u ? buf_p : buf_m;
 	float* bf = (float*)buf;

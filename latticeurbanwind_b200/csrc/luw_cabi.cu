@@ -46,9 +46,16 @@ struct luw_domain {
 	struct HaloAxis { // transfer buffers of one decomposed axis (reference: transfer_buffer_p / _m, FX/lbm.cpp:1864-1889) and the events that order their use
 		char* send_p = nullptr; char* send_m = nullptr; char* recv_p = nullptr; char* recv_m = nullptr;
 		uint64_t bytes = 0ull;
-		cudaEvent_t extracted = nullptr, taken_p = nullptr, taken_m = nullptr; // payloads ready / copied away by the (+) and (-) neighbour
+		cudaEvent_t extracted = nullptr, got_p = nullptr, got_m = nullptr; // my payloads are packed / I have copied the (+) and the (-) neighbour's payload out of ITS send buffer
+		// (an event can only be recorded on a stream of its own device: every event here is recorded by its owner and waited for by the neighbours)
 		bool in_use = false;
 	} halo[3];
+	struct HaloIpc { // peer-mapped receive block of one axis (luw_halo_ipc_*): [flag_p @0 | flag_m @64 | recv_p[0] recv_m[0] recv_p[1] recv_m[1] @256]
+		char* block = nullptr; char* up = nullptr; char* dn = nullptr; // mine, and the mapped blocks of the (+) / (-) neighbour
+		uint64_t buf_bytes = 0ull; // one receive buffer, rounded up to 256 B
+		uint32_t seq = 0u; // exchanges issued on this axis
+		bool same = false; // up and dn are one mapping
+	} ipc[3];
 	bool ktiming = false; // bracket every main step kernel with events (luw_kernel_timing)
 	std::vector<cudaEvent_t> kev; // event pairs
 	size_t kev_used = 0u;
@@ -177,6 +184,26 @@ void enable_peer_access(const int dev, const int ndev) {
 	}
 }
 
+// flags of the IPC halo exchange: sequence numbers written into the neighbours' blocks after the payload (system-scope release) ...
+__global__ void k_halo_signal(uint32_t* flag_a, uint32_t* flag_b, const uint32_t value) {
+	__threadfence_system(); // the extract kernel before this one (same stream) has completed: its remote stores are ordered before the flags
+	asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flag_a), "r"(value) : "memory");
+	asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flag_b), "r"(value) : "memory");
+}
+// ... and awaited by the receiver before its insert kernel. Bounded: a lost neighbour aborts the launch instead of hanging the device.
+__global__ void k_halo_wait(const uint32_t* flag_p, const uint32_t* flag_m, const uint32_t value) {
+	const long long t0 = clock64();
+	for(int k=0; k<2; k++) {
+		const uint32_t* f = k==0 ? flag_p : flag_m;
+		uint32_t v;
+		for(;;) {
+			asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+			if((int32_t)(v-value)>=0) break;
+			__nanosleep(200u);
+			if(clock64()-t0>40000000000ll) __trap(); // ~20 s
+		}
+	}
+}
 __global__ void k_fill_f32(float* p, const uint64_t n, const float v) {
 	for(uint64_t i=(uint64_t)blockIdx.x*blockDim.x+threadIdx.x; i<n; i+=(uint64_t)gridDim.x*blockDim.x) p[i] = v;
 }
@@ -300,8 +327,14 @@ int luw_domain_destroy(luw_domain* d) {
 		luw_domain::HaloAxis& h = d->halo[a];
 		cudaFree(h.send_p); cudaFree(h.send_m); cudaFree(h.recv_p); cudaFree(h.recv_m);
 		if(h.extracted) cudaEventDestroy(h.extracted);
-		if(h.taken_p) cudaEventDestroy(h.taken_p);
-		if(h.taken_m) cudaEventDestroy(h.taken_m);
+		if(h.got_p) cudaEventDestroy(h.got_p);
+		if(h.got_m) cudaEventDestroy(h.got_m);
+	}
+	for(int a=0; a<3; a++) {
+		luw_domain::HaloIpc& h = d->ipc[a];
+		if(h.up) cudaIpcCloseMemHandle(h.up);
+		if(h.dn&&!h.same) cudaIpcCloseMemHandle(h.dn);
+		cudaFree(h.block);
 	}
 	if(d->own_stream) cudaStreamDestroy(d->own_stream);
 	delete d;
@@ -397,8 +430,8 @@ static int halo(luw_domain* d, int payload, uint32_t axis, uint64_t t, void* bp,
 	const uint32_t D = axis==0u ? d->c.Dx : axis==1u ? d->c.Dy : d->c.Dz;
 	if(D<2u) return fail(LUW_ERR_INVALID, "axis is not decomposed: it has no halo layers");
 	DeviceGuard guard(d->p.device);
-	if(payload==LUW_HALO_FI) CU(d->ks->halo_fi(d->c, d->c.precision, axis, (uint32_t)(t&1ull), insert, bp, bm, d->stream));
-	else if(payload==LUW_HALO_RHO_U_FLAGS) CU(d->ks->halo_rho_u_flags(d->c, axis, insert, bp, bm, d->stream));
+	if(payload==LUW_HALO_FI) CU(d->ks->halo_fi(d->c, d->c.precision, axis, (uint32_t)(t&1ull), insert, false, bp, bm, d->stream));
+	else if(payload==LUW_HALO_RHO_U_FLAGS) CU(d->ks->halo_rho_u_flags(d->c, axis, insert, false, bp, bm, d->stream));
 	else return fail(LUW_ERR_INVALID, "unknown halo payload");
 	d->launches++;
 	return LUW_OK;
@@ -418,8 +451,8 @@ static int halo_axis_setup(luw_domain* d, const uint32_t axis) { // buffers size
 	if(rc==LUW_OK) rc = dev_alloc(d, &h.recv_m, h.bytes);
 	if(rc!=LUW_OK) return rc;
 	CU(cudaEventCreateWithFlags(&h.extracted, cudaEventDisableTiming));
-	CU(cudaEventCreateWithFlags(&h.taken_p, cudaEventDisableTiming));
-	CU(cudaEventCreateWithFlags(&h.taken_m, cudaEventDisableTiming));
+	CU(cudaEventCreateWithFlags(&h.got_p, cudaEventDisableTiming));
+	CU(cudaEventCreateWithFlags(&h.got_m, cudaEventDisableTiming));
 	return LUW_OK;
 }
 int luw_halo_exchange(luw_domain* const* doms, uint32_t count, int payload, uint32_t axis, uint64_t t) {
@@ -432,38 +465,105 @@ int luw_halo_exchange(luw_domain* const* doms, uint32_t count, int payload, uint
 	for(uint32_t i=0u; i<count; i++) { if(!doms[i]) return fail(LUW_ERR_INVALID, "null domain"); if(const int rc = halo_axis_setup(doms[i], axis)) return rc; }
 	uint64_t bytes = 0ull;
 	luw_halo_bytes(doms[0], payload, axis, &bytes);
+	const uint32_t stride = axis==0u ? 1u : axis==1u ? D[0] : D[0]*D[1];
+	const auto neighbour = [&](const uint32_t i, const uint32_t step) { const uint32_t di = (i/stride)%D[axis]; return doms[i-di*stride+((di+step)%D[axis])*stride]; }; // periodic
 	// 1. every domain packs its two boundary layers (after its neighbours have taken the previous payloads out of the send buffers)
 	for(uint32_t i=0u; i<count; i++) {
 		luw_domain* d = doms[i];
 		luw_domain::HaloAxis& h = d->halo[axis];
 		DeviceGuard guard(d->p.device);
-		if(h.in_use) { CU(cudaStreamWaitEvent(d->stream, h.taken_p, 0)); CU(cudaStreamWaitEvent(d->stream, h.taken_m, 0)); }
-		if(payload==LUW_HALO_FI) CU(d->ks->halo_fi(d->c, d->c.precision, axis, (uint32_t)(t&1ull), false, h.send_p, h.send_m, d->stream));
-		else CU(d->ks->halo_rho_u_flags(d->c, axis, false, h.send_p, h.send_m, d->stream));
+		if(h.in_use) { // send_p was read by the (+) neighbour into its - halo (its got_m), send_m by the (-) neighbour (its got_p)
+			CU(cudaStreamWaitEvent(d->stream, neighbour(i, 1u)->halo[axis].got_m, 0));
+			CU(cudaStreamWaitEvent(d->stream, neighbour(i, D[axis]-1u)->halo[axis].got_p, 0));
+		}
+		if(payload==LUW_HALO_FI) CU(d->ks->halo_fi(d->c, d->c.precision, axis, (uint32_t)(t&1ull), false, true, h.send_p, h.send_m, d->stream));
+		else CU(d->ks->halo_rho_u_flags(d->c, axis, false, true, h.send_p, h.send_m, d->stream));
 		d->launches++;
 		CU(cudaEventRecord(h.extracted, d->stream));
-		h.in_use = true;
 	}
-	// 2. every domain pulls what its neighbours packed for it (peer copies on the RECEIVER's stream) and unpacks it into its halo layers
-	const uint32_t stride = axis==0u ? 1u : axis==1u ? D[0] : D[0]*D[1];
+	// 2. every domain pulls what its neighbours packed for it (peer copies over NVLink on the RECEIVER's stream) and unpacks it into its halo layers
 	for(uint32_t i=0u; i<count; i++) {
 		luw_domain* d = doms[i];
-		const uint32_t di = (i/stride)%D[axis];
-		luw_domain* up = doms[i-di*stride+((di+1u)%D[axis])*stride]; // (+) neighbour, periodic
-		luw_domain* dn = doms[i-di*stride+((di+D[axis]-1u)%D[axis])*stride]; // (-) neighbour
+		luw_domain* up = neighbour(i, 1u); // (+) neighbour
+		luw_domain* dn = neighbour(i, D[axis]-1u); // (-) neighbour
 		luw_domain::HaloAxis& h = d->halo[axis];
 		DeviceGuard guard(d->p.device);
 		// what left the (-) neighbour through its + face arrives in my - halo layer, and vice versa
 		CU(cudaStreamWaitEvent(d->stream, dn->halo[axis].extracted, 0));
 		CU(cudaMemcpyPeerAsync(h.recv_m, d->p.device, dn->halo[axis].send_p, dn->p.device, bytes, d->stream));
-		CU(cudaEventRecord(dn->halo[axis].taken_p, d->stream));
+		CU(cudaEventRecord(h.got_m, d->stream));
 		CU(cudaStreamWaitEvent(d->stream, up->halo[axis].extracted, 0));
 		CU(cudaMemcpyPeerAsync(h.recv_p, d->p.device, up->halo[axis].send_m, up->p.device, bytes, d->stream));
-		CU(cudaEventRecord(up->halo[axis].taken_m, d->stream));
-		if(payload==LUW_HALO_FI) CU(d->ks->halo_fi(d->c, d->c.precision, axis, (uint32_t)(t&1ull), true, h.recv_p, h.recv_m, d->stream));
-		else CU(d->ks->halo_rho_u_flags(d->c, axis, true, h.recv_p, h.recv_m, d->stream));
+		CU(cudaEventRecord(h.got_p, d->stream));
+		h.in_use = true;
+		if(payload==LUW_HALO_FI) CU(d->ks->halo_fi(d->c, d->c.precision, axis, (uint32_t)(t&1ull), true, true, h.recv_p, h.recv_m, d->stream));
+		else CU(d->ks->halo_rho_u_flags(d->c, axis, true, true, h.recv_p, h.recv_m, d->stream));
 		d->launches++;
 	}
+	return LUW_OK;
+}
+static int halo_ipc_axis(luw_domain* d, const uint32_t axis, luw_domain::HaloIpc** out) {
+	if(!d||axis>2u) return fail(LUW_ERR_INVALID, "bad argument");
+	const uint32_t D = axis==0u ? d->c.Dx : axis==1u ? d->c.Dy : d->c.Dz;
+	if(D<2u) return fail(LUW_ERR_INVALID, "axis is not decomposed: it has no halo layers");
+	*out = &d->ipc[axis];
+	return LUW_OK;
+}
+int luw_halo_ipc_export(luw_domain* d, uint32_t axis, void* handle_out) {
+	luw_domain::HaloIpc* h;
+	if(const int rc = halo_ipc_axis(d, axis, &h)) return rc;
+	if(!handle_out) return fail(LUW_ERR_INVALID, "null handle");
+	DeviceGuard guard(d->p.device);
+	if(!h->block) {
+		const uint64_t A = face_area(d->c, axis);
+		h->buf_bytes = (A*(d->ddf_size==4u ? 20ull : 17ull)+255ull)&~255ull; // the larger payload: 5 fpxx or rho_u_flags (17 B) per face cell
+		const uint64_t bytes = 256ull+4ull*h->buf_bytes;
+		if(const int rc = dev_alloc(d, &h->block, bytes)) return rc;
+		CU(cudaMemsetAsync(h->block, 0, bytes, d->stream));
+		CU(cudaStreamSynchronize(d->stream));
+	}
+	cudaIpcMemHandle_t mh;
+	CU(cudaIpcGetMemHandle(&mh, h->block));
+	static_assert(sizeof(mh)==64, "cudaIpcMemHandle_t is 64 bytes");
+	memcpy(handle_out, &mh, sizeof(mh));
+	return LUW_OK;
+}
+int luw_halo_ipc_connect(luw_domain* d, uint32_t axis, const void* handle_up, const void* handle_dn) {
+	luw_domain::HaloIpc* h;
+	if(const int rc = halo_ipc_axis(d, axis, &h)) return rc;
+	if(!handle_up||!handle_dn) return fail(LUW_ERR_INVALID, "null handle");
+	if(!h->block) return fail(LUW_ERR_INVALID, "luw_halo_ipc_export must come first");
+	if(h->up) return fail(LUW_ERR_INVALID, "axis is already connected");
+	DeviceGuard guard(d->p.device);
+	cudaIpcMemHandle_t up, dn;
+	memcpy(&up, handle_up, sizeof(up)); memcpy(&dn, handle_dn, sizeof(dn));
+	CU(cudaIpcOpenMemHandle((void**)&h->up, up, cudaIpcMemLazyEnablePeerAccess));
+	h->same = memcmp(&up, &dn, sizeof(up))==0;
+	if(h->same) h->dn = h->up;
+	else CU(cudaIpcOpenMemHandle((void**)&h->dn, dn, cudaIpcMemLazyEnablePeerAccess));
+	return LUW_OK;
+}
+int luw_halo_ipc_exchange(luw_domain* d, int payload, uint32_t axis, uint64_t t) {
+	luw_domain::HaloIpc* h;
+	if(const int rc = halo_ipc_axis(d, axis, &h)) return rc;
+	if(!h->up||!h->dn) return fail(LUW_ERR_INVALID, "luw_halo_ipc_connect must come first");
+	if(payload!=LUW_HALO_FI&&payload!=LUW_HALO_RHO_U_FLAGS) return fail(LUW_ERR_INVALID, "unknown halo payload");
+	DeviceGuard guard(d->p.device);
+	const uint32_t seq = h->seq++, par = seq&1u;
+	const uint64_t bb = h->buf_bytes;
+	// my + face goes into the (+) neighbour's recv_m, my - face into the (-) neighbour's recv_p: remote stores of the extract kernel
+	char* const to_up = h->up+256ull+(2ull*par+1ull)*bb;
+	char* const to_dn = h->dn+256ull+(2ull*par+0ull)*bb;
+	if(payload==LUW_HALO_FI) CU(d->ks->halo_fi(d->c, d->c.precision, axis, (uint32_t)(t&1ull), false, true, to_up, to_dn, d->stream));
+	else CU(d->ks->halo_rho_u_flags(d->c, axis, false, true, to_up, to_dn, d->stream));
+	k_halo_signal<<<1, 1, 0, d->stream>>>((uint32_t*)(h->up+64), (uint32_t*)(h->dn+0), seq+1u); // the (+) neighbour's flag_m, the (-) neighbour's flag_p
+	k_halo_wait<<<1, 1, 0, d->stream>>>((const uint32_t*)(h->block+0), (const uint32_t*)(h->block+64), seq+1u);
+	CU(cudaGetLastError());
+	char* const recv_p = h->block+256ull+(2ull*par+0ull)*bb;
+	char* const recv_m = h->block+256ull+(2ull*par+1ull)*bb;
+	if(payload==LUW_HALO_FI) CU(d->ks->halo_fi(d->c, d->c.precision, axis, (uint32_t)(t&1ull), true, true, recv_p, recv_m, d->stream));
+	else CU(d->ks->halo_rho_u_flags(d->c, axis, true, true, recv_p, recv_m, d->stream));
+	d->launches += 4ull;
 	return LUW_OK;
 }
 int luw_run_steps_multi(luw_domain* const* doms, uint32_t count, uint64_t t0, uint64_t k, float fx, float fy, float fz, float ox, float oy, float oz) {

@@ -131,6 +131,18 @@ class Domain:
     def halo_insert(self, payload, axis, buf_p, buf_m):
         A.check(A.lib().luw_halo_insert(self._h, payload, axis, self.t, C.c_void_p(buf_p), C.c_void_p(buf_m)))
 
+    # ---- peer-mapped halo exchange of the one-process-per-GPU driver (CUDA IPC over NVLink)
+    def halo_ipc_export(self, axis):
+        h = C.create_string_buffer(64)
+        A.check(A.lib().luw_halo_ipc_export(self._h, axis, h))
+        return h.raw
+
+    def halo_ipc_connect(self, axis, handle_up, handle_dn):
+        A.check(A.lib().luw_halo_ipc_connect(self._h, axis, C.c_char_p(handle_up), C.c_char_p(handle_dn)))
+
+    def halo_ipc_exchange(self, payload, axis):
+        A.check(A.lib().luw_halo_ipc_exchange(self._h, payload, axis, self.t))
+
     # ---- measurement helpers
     def timer_begin(self):
         A.check(A.lib().luw_timer_begin(self._h))

@@ -178,7 +178,7 @@ class DistributedLBM(_Base):
     """One domain per rank (torch.distributed); rank r owns domain r of the split. Works with NCCL (GPU) and, for the host logic, with
     gloo: `cpu_engine` then stands in for the device (tests only -- the product path has no CPU fallback)."""
 
-    def __init__(self, shape, D, group=None, device=0, cpu_engine=None, **kw):
+    def __init__(self, shape, D, group=None, device=0, cpu_engine=None, transport="ipc", **kw):
         super().__init__(shape, D, **kw)
         import torch
         import torch.distributed as dist
@@ -193,11 +193,29 @@ class DistributedLBM(_Base):
         if cpu_engine is None:
             self.domain = self._make_domain(self.d, self.O, device)
             self.domains = [self.domain]
-            self._stream = torch.cuda.current_stream(device)
-            self.domain.set_stream(self._stream.cuda_stream)  # one stream orders kernels, copies and the NCCL calls
+            # one explicit stream orders the step kernels, the halo kernels and the NCCL calls (torch's default stream has handle 0, which the C ABI
+            # reads as "use the domain's own stream": kernels and NCCL would then run unordered on two streams)
+            self._stream = torch.cuda.Stream(device=device)
+            self.domain.set_stream(self._stream.cuda_stream)
+            self.transport = transport
+            if transport == "ipc":
+                self._connect_ipc()
         else:
             self.domain, self.domains = None, []
         self._bufs = {}
+
+    def _connect_ipc(self):
+        """Exchange the CUDA IPC handles of the receive blocks (once) and map the two neighbours' blocks per decomposed axis. After this the
+        step path makes no NCCL call: extract kernels store into the neighbours' memory over NVLink (luw_halo_ipc_exchange)."""
+        dist = self._dist
+        for axis in AXES:
+            if self.D[axis] < 2:
+                continue
+            mine = self.domain.halo_ipc_export(axis)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mine, group=self.group)
+            self.domain.halo_ipc_connect(axis, handles[self.rank_of(axis, +1)], handles[self.rank_of(axis, -1)])
+        dist.barrier(group=self.group)
 
     def rank_of(self, axis, step):
         d = list(self.d)
@@ -226,12 +244,20 @@ class DistributedLBM(_Base):
             return
         ops = [dist.P2POp(dist.isend, sp, up, self.group, tag=2 * axis), dist.P2POp(dist.isend, sm, dn, self.group, tag=2 * axis + 1),
                dist.P2POp(dist.irecv, rm, dn, self.group, tag=2 * axis), dist.P2POp(dist.irecv, rp, up, self.group, tag=2 * axis + 1)]
-        for r in dist.batch_isend_irecv(ops):
-            r.wait()
+        if self.cpu_engine is None:
+            with self._torch.cuda.stream(self._stream):  # NCCL enqueues on the current stream
+                for r in dist.batch_isend_irecv(ops):
+                    r.wait()
+        else:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
 
     def communicate(self, payload, extract, insert):
         for axis in AXES:
             if self.D[axis] < 2:
+                continue
+            if self.cpu_engine is None and self.transport == "ipc":
+                self.domain.halo_ipc_exchange(payload, axis)
                 continue
             sp, sm, rp, rm = self._buffers(payload, axis)
             extract(payload, axis, sp, sm)
