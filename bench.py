@@ -39,6 +39,7 @@ WORKLOADS = {
     # name: (case, local block shape incl. halos, precision, features, oracle feature-set name, nu, description)
     "channel512_fp16s": ("channel", (512, 512, 512), 1, F_EQ, "chan", 1.0 / 6.0, "C2 empty channel 512^3 FP16S (TYPE_E x faces, TYPE_S walls), SRT nu=1/6"),
     "channel512_fp32": ("channel", (512, 512, 512), 0, F_EQ, "chan", 1.0 / 6.0, "C2 empty channel 512^3 FP32 (TYPE_E x faces, TYPE_S walls), SRT nu=1/6"),
+    "channel512_fp16c": ("channel", (512, 512, 512), 2, F_EQ, "chan", 1.0 / 6.0, "C2 empty channel 512^3 FP16C (LUW's shipped DDF format), SRT nu=1/6"),
     "urban_fp16s": ("urban", (1024, 1024, 256), 1, F_VF | F_EQ | F_SG | F_NUDGE | F_SPONGE, "luwnf", 1e-6,
                     "C3 staggered cube array 1024x1024x256 FP16S, TYPE_E inflow, bounce-back, Coriolis, nudging N=16, sponge N=20, Smagorinsky; rho/u on demand"),
     "urban_fp16s_nz": ("urban", (1024, 1024, 256), 1, F_VF | F_EQ | F_SG, "core", 1e-6,
@@ -270,7 +271,7 @@ def bench_single(args, workload, arith, A, cases, Domain, CellSet, pinned_empty,
                "config": {"workload": desc, "name": workload, "lattice": list(shape), "features": features, "arith": args.arith, "decomposition": [1, 1, 1],
                           "l2": "state (DDFs %.1f GB) is far larger than the 126 MB L2; no flush needed" % (19 * N * (4 if precision == 0 else 2) / 1e9)},
                "roofline": roof, "clocks": clocks, "gpu_launches": int(launches)}
-        published = {"channel512_fp16s": 55609.0, "channel512_fp32": 42152.0}.get(workload)
+        published = {"channel512_fp16s": 55609.0, "channel512_fp32": 42152.0, "channel512_fp16c": 22695.0}.get(workload)
         if published:  # FluidX3D's own B200 number for this protocol (OpenCL) -- context, the driver computes its own ratios
             res["config"]["published_reference_b200_mlups"] = published
         # ---- e2e: one host-API call per step, with that step's boundary field going up and a probe plane coming back

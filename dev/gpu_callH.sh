@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -k "decomposed or nccl or halo" 2>&1 | tail -4 | tee gpurun_out/pytest_gpu_H.log
+run() { # workload decomp
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 10 --workload $1 $2 > gpurun_out/bench_n2_H.json 2> gpurun_out/bench_n2_H.err
+echo "exit=$?"; grep -v "^\*\|OMP_NUM" gpurun_out/bench_n2_H.err | tail -5
+python -c "import json; d=json.loads(open('gpurun_out/bench_n2_H.json').read().strip().splitlines()[-1]); print('N2 $1 $2', d['config']['decomposition'], round(d['value']), round(d['ms_per_step'],3), round(d['roofline']['kernel_ms'],3), d['halo'])" | tee -a gpurun_out/n2_H.txt
+}
+run channel512_fp16s ""
+run channel512_fp16s "--decomp 1,2,1"
+run channel512_fp16s "--decomp 2,1,1"
+run urban_fp16s ""
+cp gpurun_out/bench_n2_H.json gpurun_out/bench_n2_urban_default.json
+timeout 300 python bench.py --no-cpu --no-e2e --steps 100 --warmup 10 --workload channel512_fp16s | python -c "import json,sys; d=json.load(sys.stdin); print('N1 channel', round(d['value']), round(d['ms_per_step'],3))" | tee -a gpurun_out/n2_H.txt
+timeout 300 python bench.py --no-cpu --no-e2e --steps 100 --warmup 10 --workload urban_fp16s | python -c "import json,sys; d=json.load(sys.stdin); print('N1 urban', round(d['value']), round(d['ms_per_step'],3))" | tee -a gpurun_out/n2_H.txt

@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/pytest_gpu_K.log
+run() { LUW_TILE_VARIANT=$2 timeout 300 python bench.py --no-cpu --no-e2e --steps 60 --warmup 10 --workload $1 2>/dev/null | python -c "import json,sys; d=json.load(sys.stdin); print('$1 variant=$2', round(d['value']), round(d['ms_per_step'],3), round(d['roofline']['frac'],3))" | tee -a gpurun_out/misc_K.txt; }
+run channel512_fp16c ""
+run channel512_fp16c 3
+run channel512_fp16c 1
+run urban_fp16s ""
+run urban_fp16s_uf ""
+run channel512_fp16s ""

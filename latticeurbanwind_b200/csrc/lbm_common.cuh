@@ -55,13 +55,11 @@ template<> struct Ddf<P_FP16S> { // IEEE half holding 2^15 * f
 };
 template<> struct Ddf<P_FP16C> { // custom 1-4-11 format, bias 15, range +-2, with subnormals
 	typedef uint16_t T;
+	// decode (FX/kernel.cpp:864-869) without branches: the 15 magnitude bits, shifted into a float's exponent/mantissa fields, read as 2^-112 times the
+	// value -- for the subnormal codes (e = 0) too, because the float is then itself subnormal -- and one exact multiplication by 2^112 restores it.
 	static __device__ __forceinline__ float dec(const uint16_t h) {
-		const uint32_t x = h, e = (x&0x7800u)>>11, m = (x&0x07FFu)<<12;
-		const uint32_t v = 158u-(uint32_t)__clz((int)m); // == as_uint((float)m)>>23 for m!=0
-		uint32_t r = (x&0x8000u)<<16;
-		if(e!=0u) r |= ((e+112u)<<23)|m;
-		else if(m!=0u) r |= ((v-37u)<<23)|((m<<(150u-v))&0x007FF000u);
-		return __uint_as_float(r);
+		const uint32_t x = h;
+		return __uint_as_float(__float_as_uint(__fmul_rn(__uint_as_float((x&0x7FFFu)<<12), 5.192296858534828e33f))|((x&0x8000u)<<16));
 	}
 	static __device__ __forceinline__ uint16_t enc(const float f) {
 		const uint32_t b = __float_as_uint(f)+0x00000800u, e = (b&0x7F800000u)>>23, m = b&0x007FFFFFu;

@@ -113,14 +113,14 @@ void setup_tiles(luw_domain* d) {
 	if(off&&off[0]=='1') return;
 	const char* var = getenv("LUW_TILE_VARIANT");
 	// default: two-pass kernel; 5 CTAs/SM where the collision fits 72 registers (no LES), else 128x4 tiles with 8 consumer warps per producer (measured, profiles/)
-	const int want = var ? atoi(var) : (d->c.precision!=luw::P_FP32&&(d->c.features&luw::F_SUBGRID)) ? 4 : 0;
+	const int want = (var&&var[0]) ? atoi(var) : d->c.precision==luw::P_FP16C ? 3 : (d->c.precision==luw::P_FP16S&&(d->c.features&luw::F_SUBGRID)) ? 4 : 0; // FP16C: the software codec makes decoding twice dearer than the registers (single pass)
 	const luw::DomainConst& c = d->c;
 	if(c.Nx%16u!=0u) return;
 	encode_tiled_fn enc = get_encode_tiled();
 	if(!enc) return;
 	luw::TileShape sh;
 	bool found = false;
-	for(int v : { want, 0, 2 }) { // the requested variant, else one whose tile is not wider than the lattice
+	for(int v : { want, 0, 2 }) { // 2: 64-wide tiles for narrow lattices // the requested variant, else one whose tile is not wider than the lattice
 		if(d->ks->tile_shape(c.precision, c.features, v, &sh)&&c.Nx>=(uint32_t)sh.tx) { d->tile_variant = v; found = true; break; }
 	}
 	if(!found) return;

@@ -62,7 +62,7 @@ def test_update_fields_on_demand(oracle_lib):
 
 
 # ---------------------------------------------------------------------------------------------- the TMA-tiled step kernel
-TILED_SHAPES = [(64, 8, 4), (128, 20, 12), (80, 10, 7), (192, 9, 5)]  # exact tiles, several tiles, partial tiles in x / y / z
+TILED_SHAPES = [(64, 8, 4), (128, 20, 12), (80, 10, 7), (192, 9, 5), (768, 6, 4)]  # exact tiles, several tiles, partial tiles in x / y / z, strips longer than the stage ring
 
 
 @pytest.mark.parametrize("precision", [0, 1, 2], ids=["fp32", "fp16s", "fp16c"])
@@ -85,7 +85,7 @@ def test_tiled_strict_equals_oracle(oracle_lib, precision, fset, shape):
 def test_tiled_periodic_box_equals_oracle(oracle_lib, precision):
     """Fully periodic lattice (upstream BENCHMARK protocol): every wrapped neighbour goes through the tile kernel's boundary patch."""
     O = oracle_lib
-    shape = (128, 12, 6)
+    shape = (128, 12, 6) if precision == 0 else (768, 6, 4)  # one tile per strip / strips longer than the stage ring (parked column without the barrier)
     flags, rho, u = cases.periodic_box(*shape, seed=5, amp=1e-2)
     w = cases.relaxation_rate(1.0 / 6.0)
     ref = H.run_cpu(O.Oracle(), O, shape, precision, 0, flags, rho, u, 11, w)
