@@ -13,8 +13,11 @@
  *  - all work of a domain is enqueued on that domain's stream (luw_domain_set_stream) and is asynchronous unless stated;
  *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with LUW_ERR_NO_DEVICE.
  *
- * Memory layout (identical to the reference, FX/kernel.cpp:833-839,877-879): SoA, n = x + (y + z*Ny)*Nx over the LOCAL lattice
- * including halo layers; fi[i*N + n] (i = 0..18, float / IEEE half scaled by 2^15 / custom 1-4-11 half), u[c*N + n], rho[n], flags[n].
+ * Memory layout of every HOST image and of every element range / cell index that crosses this interface (identical to the reference,
+ * FX/kernel.cpp:833-839,877-879): SoA, n = x + (y + z*Ny)*Nx over the LOCAL lattice including halo layers; fi[i*N + n] (i = 0..18, float /
+ * IEEE half scaled by 2^15 / custom 1-4-11 half), u[c*N + n], rho[n], flags[n]. On the device the rows are padded to a multiple of 16
+ * elements (row pitch Px >= Nx, component stride Px*Ny*Nz) so that TMA can address any lattice, e.g. the Nx/Dx + 2 cells of an x-decomposed
+ * block; luw_upload / luw_download / cell sets / inlet points translate. Only luw_device_ptr exposes the pitched arrays.
  */
 #ifndef LUW_CUDA_H
 #define LUW_CUDA_H
@@ -85,15 +88,15 @@ int luw_domain_destroy(luw_domain* dom); /* ~LBM_Domain / Memory<> dtors */
 /* use an existing CUDA stream (cudaStream_t passed as void*) for everything the domain enqueues; NULL restores the domain's own stream */
 int luw_domain_set_stream(luw_domain* dom, void* cuda_stream);
 int luw_domain_bytes(const luw_domain* dom, uint64_t* device_bytes); /* Device_Info::memory_used, FX/info.cpp:233-241 */
-/* which stream_collide implementation the domain runs: 1 = TMA-tiled persistent kernel (lattices whose x extent is a multiple of 16 and at least one
- * tile wide), 0 = one-cell-per-thread kernel (any lattice). Same results; the reference has a single kernel (FX/kernel.cpp:1475). */
+/* which stream_collide implementation the domain runs: 1 = TMA-tiled persistent kernel (lattices with an even x extent of at least one 64-cell
+ * tile), 0 = one-cell-per-thread kernel (any lattice). Same results; the reference has a single kernel (FX/kernel.cpp:1475). */
 int luw_domain_step_kernel(const luw_domain* dom, int* tiled);
 
 /* Memory<T>::enqueue_write_to_device / enqueue_read_from_device(offset,length): FX/opencl.hpp:481-512. offset/count in ELEMENTS of the field
  * (rho: N floats, u: 3N floats, flags: N bytes, fi: 19N fpxx). Host pointers may be pageable or pinned; copies are stream-ordered. */
 int luw_upload(luw_domain* dom, int field, const void* host_src, uint64_t offset, uint64_t count);
 int luw_download(luw_domain* dom, int field, void* host_dst, uint64_t offset, uint64_t count);
-int luw_device_ptr(luw_domain* dom, int field, void** dev_ptr); /* raw device pointer of a field (for peer / NCCL plumbing) */
+int luw_device_ptr(luw_domain* dom, int field, void** dev_ptr); /* raw device pointer of a field (pitched rows, see above) */
 
 /* kernel "initialize", FX/kernel.cpp:1370-1452, enqueued by LBM_Domain::enqueue_initialize FX/lbm.cpp:340-343 (slot parity t=1 baked in) */
 int luw_initialize(luw_domain* dom);

@@ -19,7 +19,8 @@ enum : int { P_FP32 = 0, P_FP16S = 1, P_FP16C = 2 };
 
 struct DomainConst { // the def_* constants of FX/lbm.cpp:612-783 as kernel parameters
 	uint32_t Nx, Ny, Nz;
-	uint64_t N;
+	uint32_t Px; // row pitch in elements: Nx rounded up to a multiple of 16, so that every row of every array starts 16-byte aligned (TMA); host images stay dense
+	uint64_t N; // elements per component / DDF slot ON THE DEVICE: Px*Ny*Nz (the device index of cell (x,y,z) is x+(y+z*Ny)*Px)
 	uint32_t Dx, Dy, Dz;
 	int Ox, Oy, Oz;
 	uint32_t Nxg, Nyg, Nzg; // global lattice
@@ -133,7 +134,7 @@ __device__ __forceinline__ void luw_force(const DomainConst& c, const StepArgs& 
 	fyn += -2.0f*rho*(a.oz*ux-a.ox*uz);
 	fzn += -2.0f*rho*(a.ox*uy-a.oy*ux);
 	if(zones&&bo!=TYPE_E) {
-		const uint64_t row = c.Nx, plane = (uint64_t)c.Nx*c.Ny;
+		const uint64_t row = c.Px, plane = (uint64_t)c.Px*c.Ny;
 		if(c.features&F_NUDGING) {
 			const int xg = (int)x+c.Ox, yg = (int)y+c.Oy, zg = (int)z+c.Oz, Nb = (int)c.buffer_N;
 			const int dw = xg, de = (int)(c.Nxg-1u)-xg, ds = yg, dn = (int)(c.Nyg-1u)-yg, dt = (int)(c.Nzg-1u)-zg;
@@ -178,7 +179,7 @@ __device__ __forceinline__ bool is_halo(const DomainConst& c, const uint32_t x, 
 // linear offsets of the 9 "+" neighbours n+c_i (i odd) with periodic wrap, FX/kernel.cpp:920-958
 struct Nbr { uint64_t j[Q]; };
 __device__ __forceinline__ void neighbors(const DomainConst& c, const uint32_t x, const uint32_t y, const uint32_t z, uint64_t* j) {
-	const uint64_t row = c.Nx, plane = (uint64_t)c.Nx*c.Ny;
+	const uint64_t row = c.Px, plane = (uint64_t)c.Px*c.Ny;
 	const uint64_t x0 = x, xp = x+1u==c.Nx ? 0u : x+1u, xm = x==0u ? c.Nx-1u : x-1u;
 	const uint64_t y0 = y*row, yp = (y+1u==c.Ny ? 0u : y+1u)*row, ym = (y==0u ? c.Ny-1u : y-1u)*row;
 	const uint64_t z0 = z*plane, zp = (z+1u==c.Nz ? 0u : z+1u)*plane, zm = (z==0u ? c.Nz-1u : z-1u)*plane;

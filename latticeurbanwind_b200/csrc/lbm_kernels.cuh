@@ -166,7 +166,7 @@ template<bool INSERT> __global__ void __launch_bounds__(128) k_halo_rho_u_flags(
 	const uint32_t L = axis_len(c, d);
 	uint32_t x, y, z, a;
 	face_xyz(c, d, t, INSERT ? (side==0u ? L-1u : 0u) : (side==0u ? L-2u : 1u), xfast, x, y, z, a);
-	const uint64_t n = x+((uint64_t)y+(uint64_t)z*c.Ny)*c.Nx;
+	const uint64_t n = x+((uint64_t)y+(uint64_t)z*c.Ny)*c.Px;
 	char* buf = side==0u ? buf_p : buf_m;
 	float* bf = (float*)buf;
 	uint8_t* bb = (uint8_t*)buf+16ull*A;

@@ -214,7 +214,7 @@ template<class CFG, bool IN> __device__ __noinline__ void patch_yz(const DomainC
 	typedef typename Ddf<CFG::P>::T T;
 	constexpr int TX = CFG::TX, TY = CFG::TY;
 	T* const fi = (T*)c.fi;
-	const uint64_t rowN = c.Nx, planeN = (uint64_t)c.Nx*c.Ny;
+	const uint64_t rowN = c.Px, planeN = (uint64_t)c.Px*c.Ny;
 	for(int k=1; k<9; k++) { // pair 0 (+x) has no y/z shift
 		int cx, cy, cz; pair_shift(k, cx, cy, cz);
 		const uint32_t slot = odd ? 2u*k+2u : 2u*k+1u;
@@ -237,7 +237,7 @@ template<class CFG> __device__ __noinline__ void flush_wrap(const DomainConst& c
 	const int y = y0+(int)(row%(uint32_t)CFG::TY), z = z0+(int)(row/(uint32_t)CFG::TY);
 	if(y>=(int)c.Ny||z>=(int)c.Nz) return;
 	T* const fi = (T*)c.fi;
-	const uint64_t rowN = c.Nx, planeN = (uint64_t)c.Nx*c.Ny;
+	const uint64_t rowN = c.Px, planeN = (uint64_t)c.Px*c.Ny;
 	for(int k=0; k<9; k++) {
 		int cx, cy, cz; pair_shift(k, cx, cy, cz);
 		if(cx==0) continue;
@@ -403,7 +403,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 	// ---------------------------------------------------------------------------------------- consumers: two cells per thread
 	const uint32_t row = tid/(uint32_t)(TX/2), lx = 2u*(tid%(uint32_t)(TX/2)), ly = row%(uint32_t)TY, lz = row/(uint32_t)TY;
 	const float scale = (FAST&&P==P_FP16S) ? 32768.0f : 1.0f, inv = (FAST&&P==P_FP16S) ? 3.0517578E-5f : 1.0f;
-	const uint64_t rowN = c.Nx, planeN = (uint64_t)c.Nx*c.Ny;
+	const uint64_t rowN = c.Px, planeN = (uint64_t)c.Px*c.Ny;
 	const bool has_zones = VF&&(c.features&(F_NUDGING|F_SPONGE))!=0u;
 	const int Nb = (c.features&F_NUDGING) ? (int)c.buffer_N : -1, Ns = (c.features&F_SPONGE) ? (int)c.sponge_N : 0;
 	const uint32_t last_tx = c.Nx-(tiles_x-1u)*(uint32_t)TX; // cells of the last tile's rows that lie inside the lattice

@@ -47,7 +47,7 @@ __device__ __forceinline__ ZoneRef zone_prefetch(const DomainConst& c, const uin
 	ZoneRef r;
 	r.nudge = false; r.sponge = false; r.kn = 0.0f; r.unx = r.uny = r.unz = 0.0f; r.ks = 0.0f; r.usx = r.usy = r.usz = 0.0f;
 	if(!active) return r;
-	const uint64_t row = c.Nx, plane = (uint64_t)c.Nx*c.Ny;
+	const uint64_t row = c.Px, plane = (uint64_t)c.Px*c.Ny;
 	if(c.features&F_NUDGING) {
 		const int xg = (int)x+c.Ox, yg = (int)y+c.Oy, zg = (int)z+c.Oz, Nb = (int)c.buffer_N;
 		const int dw = xg, de = (int)(c.Nxg-1u)-xg, ds = yg, dn = (int)(c.Nyg-1u)-yg, dt = (int)(c.Nzg-1u)-zg;
@@ -248,7 +248,7 @@ template<uint32_t FEAT, bool HAS_E> __device__ __forceinline__ void collide_fast
 	const bool any_e = HAS_E&&(in.e0||in.e1);
 	if(any_e) { // TYPE_E lanes: rho/u come from the boundary fields (FX/kernel.cpp:1503-1515)
 		rho = sel2(in.e0, in.e1, in.rho_e, rho); ux = sel2(in.e0, in.e1, in.ux_e, ux); uy = sel2(in.e0, in.e1, in.uy_e, uy); uz = sel2(in.e0, in.e1, in.uz_e, uz);
-		rhom1 = rho-bc(1.0f);
+		rhom1 = sel2(in.e0, in.e1, rho-bc(1.0f), rhom1); // the non-TYPE_E partner of a mixed pair keeps its own rho-1: its result must not depend on who it is paired with
 		ir = rcp2(rho); ir = fma2(ir, fma2(-rho, ir, bc(1.0f)), ir);
 	}
 	Proj F; f2 uF3 = bc(0.0f);

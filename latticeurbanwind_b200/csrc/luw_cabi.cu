@@ -39,6 +39,7 @@ struct luw_domain {
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	float* wbuf = nullptr; float* sigma = nullptr;
 	uint64_t bytes = 0ull, launches = 0ull;
+	uint64_t ncells = 0ull; // Nx*Ny*Nz: cells of the lattice = elements per component of a HOST image (the device arrays have c.N = Px*Ny*Nz, see lbm_common.cuh)
 	size_t ddf_size = 4u;
 	luw::TileMaps maps; // TMA descriptors for the tiled step
 	bool tiled = false; // the tiled step is usable for this domain
@@ -74,8 +75,8 @@ struct luw_vk_inlet {
 
 namespace {
 
-int field_info(const luw_domain* d, const int field, void** base, size_t* elem, uint64_t* count) {
-	const uint64_t N = d->c.N;
+int field_info(const luw_domain* d, const int field, void** base, size_t* elem, uint64_t* count) { // count: elements of the dense (host-side) image
+	const uint64_t N = d->ncells;
 	switch(field) {
 		case LUW_FIELD_RHO: *base = d->c.rho; *elem = 4u; *count = N; return LUW_OK;
 		case LUW_FIELD_U: *base = d->c.u; *elem = 4u; *count = 3ull*N; return LUW_OK;
@@ -83,6 +84,41 @@ int field_info(const luw_domain* d, const int field, void** base, size_t* elem, 
 		case LUW_FIELD_FI: *base = d->c.fi; *elem = d->ddf_size; *count = 19ull*N; return LUW_OK;
 		default: return fail(LUW_ERR_INVALID, "unknown field id");
 	}
+}
+// device index of the cell with dense index n = x+(y+z*Ny)*Nx
+inline uint64_t device_index(const luw::DomainConst& c, const uint64_t n) { return c.Px==c.Nx ? n : (n%c.Nx)+(n/c.Nx)*(uint64_t)c.Px; }
+// Copy elements [offset, offset+count) of a dense host image to / from the pitched device array: whole rows with one 2-D copy per component,
+// partial rows at the two ends with 1-D copies. With Px == Nx this is the single 1-D copy of the reference (FX/opencl.hpp:481-512).
+cudaError_t copy_field(luw_domain* d, char* dev_base, const size_t elem, char* host, const uint64_t offset, const uint64_t count, const bool to_device) {
+	const luw::DomainConst& c = d->c;
+	const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+	if(count==0ull) return cudaSuccess;
+	if(c.Px==c.Nx) return to_device ? cudaMemcpyAsync(dev_base+offset*elem, host, count*elem, kind, d->stream) : cudaMemcpyAsync(host, dev_base+offset*elem, count*elem, kind, d->stream);
+	const uint64_t N = d->ncells, Nx = c.Nx, Px = c.Px;
+	uint64_t i = offset; const uint64_t end = offset+count;
+	while(i<end) {
+		const uint64_t comp = i/N, n0 = i%N, n1 = (end-comp*N<N) ? end-comp*N : N; // [n0, n1) inside this component
+		char* dv = dev_base+comp*c.N*elem;
+		char* hs = host+(i-offset)*elem;
+		uint64_t n = n0;
+		cudaError_t e = cudaSuccess;
+		const auto piece = [&](const uint64_t len) { // within one row
+			char* dp = dv+device_index(c, n)*elem;
+			e = to_device ? cudaMemcpyAsync(dp, hs, len*elem, kind, d->stream) : cudaMemcpyAsync(hs, dp, len*elem, kind, d->stream);
+			n += len; hs += len*elem;
+		};
+		if(n%Nx!=0ull) { const uint64_t len = (Nx-n%Nx<n1-n) ? Nx-n%Nx : n1-n; piece(len); if(e!=cudaSuccess) return e; }
+		const uint64_t rows = (n1-n)/Nx;
+		if(rows>0ull) {
+			char* dp = dv+(n/Nx)*Px*elem;
+			e = to_device ? cudaMemcpy2DAsync(dp, Px*elem, hs, Nx*elem, Nx*elem, rows, kind, d->stream) : cudaMemcpy2DAsync(hs, Nx*elem, dp, Px*elem, Nx*elem, rows, kind, d->stream);
+			if(e!=cudaSuccess) return e;
+			n += rows*Nx; hs += rows*Nx*elem;
+		}
+		if(n<n1) { piece(n1-n); if(e!=cudaSuccess) return e; }
+		i = comp*N+n1;
+	}
+	return cudaSuccess;
 }
 uint64_t face_area(const luw::DomainConst& c, const uint32_t axis) {
 	return axis==0u ? (uint64_t)c.Ny*c.Nz : axis==1u ? (uint64_t)c.Nz*c.Nx : (uint64_t)c.Nx*c.Ny;
@@ -115,7 +151,7 @@ void setup_tiles(luw_domain* d) {
 	// default: two-pass kernel; 5 CTAs/SM where the collision fits 72 registers (no LES), else 128x4 tiles with 8 consumer warps per producer (measured, profiles/)
 	const int want = (var&&var[0]) ? atoi(var) : d->c.precision==luw::P_FP16C ? 3 : (d->c.precision==luw::P_FP16S&&(d->c.features&luw::F_SUBGRID)) ? 4 : 0; // FP16C: the software codec makes decoding twice dearer than the registers (single pass)
 	const luw::DomainConst& c = d->c;
-	if(c.Nx%16u!=0u) return;
+	if(c.Nx%2u!=0u) return; // two x-adjacent cells per thread
 	encode_tiled_fn enc = get_encode_tiled();
 	if(!enc) return;
 	luw::TileShape sh;
@@ -128,7 +164,7 @@ void setup_tiles(luw_domain* d) {
 	const CUtensorMapDataType dt = es==4u ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16;
 	const cuuint64_t dims4[4] = { c.Nx, c.Ny, c.Nz, 19u };
 	const cuuint64_t dims4A[4] = { c.Nx, c.Ny, c.Nz, 20u }; // slot 19 does not exist and is never traversed (stride 2 from slot 1 or 2 ends at 17 / 18)
-	const cuuint64_t str4[3] = { c.Nx*es, (cuuint64_t)c.Nx*c.Ny*es, c.N*es };
+	const cuuint64_t str4[3] = { c.Px*es, (cuuint64_t)c.Px*c.Ny*es, c.N*es }; // rows are Px elements apart (multiples of 16 bytes), boxes are clipped at Nx
 	const cuuint32_t box4[4] = { (cuuint32_t)sh.tx, (cuuint32_t)sh.ty, (cuuint32_t)sh.tz, 1u };
 	const cuuint32_t box4A[4] = { (cuuint32_t)sh.tx, (cuuint32_t)sh.ty, (cuuint32_t)sh.tz, 18u }; // 9 slots at element stride 2
 	const cuuint32_t one4[4] = { 1u, 1u, 1u, 1u };
@@ -138,7 +174,7 @@ void setup_tiles(luw_domain* d) {
 	if(enc(&d->maps.fiA, dt, 4u, c.fi, dims4A, str4, box4A, strideA,
 		CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)!=CUDA_SUCCESS) return;
 	const cuuint64_t dims3[3] = { c.Nx, c.Ny, c.Nz };
-	const cuuint64_t str3[2] = { c.Nx, (cuuint64_t)c.Nx*c.Ny };
+	const cuuint64_t str3[2] = { c.Px, (cuuint64_t)c.Px*c.Ny };
 	if(enc(&d->maps.flags, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3u, c.flags, dims3, str3, box4, one4,
 		CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)!=CUDA_SUCCESS) return;
 	d->tiled = true;
@@ -244,7 +280,8 @@ int luw_domain_create(const luw_domain_params* p, luw_domain** out) {
 	if(p->precision>2u) return fail(LUW_ERR_INVALID, "precision must be LUW_FP32, LUW_FP16S or LUW_FP16C");
 	if(p->arith>1u) return fail(LUW_ERR_INVALID, "arith must be LUW_ARITH_STRICT or LUW_ARITH_FAST");
 	if(p->Ny>65535u||p->Nz>65535u) return fail(LUW_ERR_INVALID, "Ny and Nz are limited to 65535 by the launch grid");
-	const uint64_t N = (uint64_t)p->Nx*p->Ny*p->Nz;
+	const uint64_t Px = ((uint64_t)p->Nx+15ull)&~15ull; // device row pitch
+	const uint64_t N = Px*p->Ny*p->Nz; // elements per component on the device
 	if(N>0xFFFFFFFFull) return fail(LUW_ERR_INVALID, "more than 2^32-1 cells per domain"); // the reference switches to 64-bit cell indices here (FX/lbm.cpp:631)
 	if((p->features&LUW_BUFFER_NUDGING)&&p->buffer_N==0u) return fail(LUW_ERR_INVALID, "buffer_N must be positive with BUFFER_NUDGING");
 	if((p->features&LUW_TOP_SPONGE)&&p->sponge_N==0u) return fail(LUW_ERR_INVALID, "sponge_N must be positive with TOP_SPONGE");
@@ -262,7 +299,8 @@ int luw_domain_create(const luw_domain_params* p, luw_domain** out) {
 	d->ddf_size = p->precision==LUW_FP32 ? 4u : 2u;
 	luw::DomainConst& c = d->c;
 	memset(&c, 0, sizeof(c));
-	c.Nx = p->Nx; c.Ny = p->Ny; c.Nz = p->Nz; c.N = N;
+	c.Nx = p->Nx; c.Ny = p->Ny; c.Nz = p->Nz; c.Px = (uint32_t)Px; c.N = N;
+	d->ncells = (uint64_t)p->Nx*p->Ny*p->Nz;
 	c.Dx = p->Dx; c.Dy = p->Dy; c.Dz = p->Dz; c.Ox = p->Ox; c.Oy = p->Oy; c.Oz = p->Oz;
 	c.Nxg = (p->Nx-2u*(p->Dx>1u))*p->Dx; c.Nyg = (p->Ny-2u*(p->Dy>1u))*p->Dy; c.Nzg = (p->Nz-2u*(p->Dz>1u))*p->Dz; // FX/lbm.cpp:613-627
 	c.wx = -p->Ox; c.ex = (int)c.Nxg-1-p->Ox; c.sy = -p->Oy; c.ny = (int)c.Nyg-1-p->Oy; c.tz = (int)c.Nzg-1-p->Oz;
@@ -366,7 +404,7 @@ int luw_upload(luw_domain* d, int field, const void* host_src, uint64_t offset, 
 	if(const int rc = field_info(d, field, &base, &elem, &total)) return rc;
 	if(offset>total||count>total-offset) return fail(LUW_ERR_INVALID, "upload range exceeds the field");
 	DeviceGuard guard(d->p.device);
-	CU(cudaMemcpyAsync((char*)base+offset*elem, host_src, count*elem, cudaMemcpyHostToDevice, d->stream));
+	CU(copy_field(d, (char*)base, elem, (char*)host_src, offset, count, true));
 	return LUW_OK;
 }
 int luw_download(luw_domain* d, int field, void* host_dst, uint64_t offset, uint64_t count) {
@@ -375,7 +413,7 @@ int luw_download(luw_domain* d, int field, void* host_dst, uint64_t offset, uint
 	if(const int rc = field_info(d, field, &base, &elem, &total)) return rc;
 	if(offset>total||count>total-offset) return fail(LUW_ERR_INVALID, "download range exceeds the field");
 	DeviceGuard guard(d->p.device);
-	CU(cudaMemcpyAsync(host_dst, (const char*)base+offset*elem, count*elem, cudaMemcpyDeviceToHost, d->stream));
+	CU(copy_field(d, (char*)base, elem, (char*)host_dst, offset, count, false));
 	return LUW_OK;
 }
 int luw_device_ptr(luw_domain* d, int field, void** dev_ptr) {
@@ -578,7 +616,9 @@ int luw_run_steps_multi(luw_domain* const* doms, uint32_t count, uint64_t t0, ui
 int luw_vk_inlet_create(luw_domain* d, uint64_t P, uint64_t M, uint64_t V, const uint64_t* pc, const uint8_t* pf, const float* pd, const float* md, luw_vk_inlet** out) {
 	if(!d||!out||(P>0ull&&(!pc||!pf||!pd))||(V>0ull&&!md)) return fail(LUW_ERR_INVALID, "null argument");
 	*out = nullptr;
-	for(uint64_t i=0ull; i<P; i++) if(pc[i]>=d->c.N) return fail(LUW_ERR_INVALID, "inlet point outside the domain");
+	for(uint64_t i=0ull; i<P; i++) if(pc[i]>=d->ncells) return fail(LUW_ERR_INVALID, "inlet point outside the domain");
+	std::vector<uint64_t> pcd(pc, pc+P); // device indices of the cells
+	for(uint64_t i=0ull; i<P; i++) pcd[i] = device_index(d->c, pc[i]);
 	DeviceGuard guard(d->p.device);
 	luw_vk_inlet* v = new(std::nothrow) luw_vk_inlet();
 	if(!v) return fail(LUW_ERR_OOM, "host allocation failed");
@@ -594,7 +634,7 @@ int luw_vk_inlet_create(luw_domain* d, uint64_t P, uint64_t M, uint64_t V, const
 	if(rc==LUW_OK) {
 		cudaError_t e = cudaSuccess;
 		if(P>0ull) {
-			e = cudaMemcpyAsync(v->point_cell, pc, P*8ull, cudaMemcpyHostToDevice, d->stream);
+			e = cudaMemcpyAsync(v->point_cell, pcd.data(), P*8ull, cudaMemcpyHostToDevice, d->stream);
 			if(e==cudaSuccess) e = cudaMemcpyAsync(v->point_face, pf, P, cudaMemcpyHostToDevice, d->stream);
 			if(e==cudaSuccess) e = cudaMemcpyAsync(v->point_data, pd, 7ull*P*4ull, cudaMemcpyHostToDevice, d->stream);
 		}
@@ -626,7 +666,9 @@ int luw_vk_inlet_destroy(luw_vk_inlet* v) {
 int luw_cellset_create(luw_domain* d, uint64_t count, const uint64_t* host_cell_index, luw_cellset** out) {
 	if(!d||!out||(count>0ull&&!host_cell_index)) return fail(LUW_ERR_INVALID, "null argument");
 	*out = nullptr;
-	for(uint64_t k=0ull; k<count; k++) if(host_cell_index[k]>=d->c.N) return fail(LUW_ERR_INVALID, "cell index outside the domain");
+	for(uint64_t k=0ull; k<count; k++) if(host_cell_index[k]>=d->ncells) return fail(LUW_ERR_INVALID, "cell index outside the domain");
+	std::vector<uint64_t> cd(host_cell_index, host_cell_index+count); // device indices
+	for(uint64_t k=0ull; k<count; k++) cd[k] = device_index(d->c, host_cell_index[k]);
 	DeviceGuard guard(d->p.device);
 	luw_cellset* s = new(std::nothrow) luw_cellset();
 	if(!s) return fail(LUW_ERR_OOM, "host allocation failed");
@@ -636,7 +678,7 @@ int luw_cellset_create(luw_domain* d, uint64_t count, const uint64_t* host_cell_
 		rc = dev_alloc(d, &s->cell, count);
 		if(rc==LUW_OK) rc = dev_alloc(d, &s->stage, 3ull*count);
 		if(rc==LUW_OK) {
-			cudaError_t e = cudaMemcpyAsync(s->cell, host_cell_index, count*8ull, cudaMemcpyHostToDevice, d->stream);
+			cudaError_t e = cudaMemcpyAsync(s->cell, cd.data(), count*8ull, cudaMemcpyHostToDevice, d->stream);
 			if(e==cudaSuccess) e = cudaStreamSynchronize(d->stream);
 			if(e!=cudaSuccess) rc = cuda_fail(e, "upload cell set");
 		}

@@ -83,11 +83,11 @@ def test_cpp_lbm_equals_oracle(oracle_lib, tmp_path, precision):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("D,arith", [((2, 1, 1), 0), ((1, 2, 2), 0), ((2, 2, 2), 0), ((1, 2, 2), 1)], ids=["2x1x1-strict", "1x2x2-strict", "2x2x2-strict", "1x2x2-fast"])
+@pytest.mark.parametrize("D,arith", [((2, 1, 1), 0), ((1, 2, 2), 0), ((2, 2, 2), 0), ((1, 2, 2), 1), ((2, 1, 1), 1)], ids=["2x1x1-strict", "1x2x2-strict", "2x2x2-strict", "1x2x2-fast", "2x1x1-fast"])
 def test_cpp_decomposed_equals_single_domain(tmp_path, D, arith):
     """n_gpu = [Dx,Dy,Dz] through the C++ layer (domains share the GPUs that exist): identical fields to the single-domain run.
-    STRICT arithmetic is bit-identical across the two step kernels (a block whose x extent incl. halos is not a multiple of 16 runs the
-    one-cell-per-thread kernel, the single domain the tiled one); FAST is only bit-identical kernel-for-kernel, so it is compared on a split that keeps x whole."""
+    STRICT arithmetic is bit-identical across all step kernels; FAST is bit-identical between the two-pass tile kernels of any tile shape (x-split blocks have
+    Nx/Dx + 2 cells per row and run the tile kernel through the padded device row pitch)."""
     shape = (128, 24, 16)
     flags, rho, u = cases.urban(*shape, seed=21, edge=4, pitch=8)
     feat = H.FEATURE_SETS["luw"]

@@ -62,7 +62,7 @@ def test_update_fields_on_demand(oracle_lib):
 
 
 # ---------------------------------------------------------------------------------------------- the TMA-tiled step kernel
-TILED_SHAPES = [(64, 8, 4), (128, 20, 12), (80, 10, 7), (192, 9, 5), (768, 6, 4)]  # exact tiles, several tiles, partial tiles in x / y / z, strips longer than the stage ring
+TILED_SHAPES = [(64, 8, 4), (128, 20, 12), (80, 10, 7), (192, 9, 5), (768, 6, 4), (66, 10, 6), (130, 7, 5), (202, 6, 4)]  # exact tiles, several tiles, partial tiles in x / y / z, strips longer than the stage ring, x extents that need a padded device row pitch (decomposed blocks: Nx/Dx + 2)
 
 
 @pytest.mark.parametrize("precision", [0, 1, 2], ids=["fp32", "fp16s", "fp16c"])
@@ -130,7 +130,7 @@ def test_tiled_fast_within_tolerance(oracle_lib, precision, fset):
 
 
 # ---------------------------------------------------------------------------------------------- decomposed runs (several domains on ONE GPU)
-@pytest.mark.parametrize("D,arith", [((2, 2, 2), 0), ((1, 2, 2), 0), ((1, 2, 2), 1), ((1, 1, 4), 1)], ids=["2x2x2-strict", "1x2x2-strict", "1x2x2-fast", "1x1x4-fast"])
+@pytest.mark.parametrize("D,arith", [((2, 2, 2), 0), ((1, 2, 2), 0), ((1, 2, 2), 1), ((1, 1, 4), 1), ((2, 2, 2), 1), ((2, 1, 1), 1)], ids=["2x2x2-strict", "1x2x2-strict", "1x2x2-fast", "1x1x4-fast", "2x2x2-fast", "2x1x1-fast"])
 @pytest.mark.parametrize("precision", [0, 1], ids=["fp32", "fp16s"])
 def test_decomposed_equals_single_domain(D, arith, precision):
     """D domains with halo exchange reproduce the single-domain run bit for bit (same kernels on both sides of the comparison)."""
@@ -148,3 +148,41 @@ def test_decomposed_equals_single_domain(D, arith, precision):
         lbm.close()
     assert np.array_equal(res[0][0], res[1][0]), "rho differs between D=1 and the decomposed run"
     assert np.array_equal(res[0][1], res[1][1]), "u differs between D=1 and the decomposed run"
+
+
+# ---------------------------------------------------------------------------------------------- dense host images <-> pitched device arrays
+@pytest.mark.parametrize("Nx", [66, 64, 37], ids=["66-padded", "64-dense", "37-padded"])
+def test_partial_uploads_and_downloads(Nx):
+    """Memory<T>::enqueue_write_to_device / enqueue_read_from_device(offset, length) (FX/opencl.hpp:481-512) on element ranges that start and end
+    inside rows and span components: the device rows are padded to multiples of 16 elements, host images are dense."""
+    from latticeurbanwind_b200 import _cabi as A
+    from latticeurbanwind_b200.domain import Domain
+    Ny, Nz = 5, 4
+    rng = np.random.default_rng(Nx)
+    with Domain(Nx, Ny, Nz, precision=1, features=0, w=1.0, arith=0) as d:
+        N = d.N
+        full = rng.standard_normal(3 * N).astype(np.float32)
+        d.u[:] = full
+        d.write_to_device(A.FIELD_U)
+        for off, cnt in [(0, 3 * N), (5, 7), (Nx - 3, 2 * Nx + 9), (N - 11, N + 30), (2 * N + Nx * 3, Nx * 4), (3 * N - 1, 1), (17, 0)]:
+            d.u[:] = -1.0
+            d.read_from_device(A.FIELD_U, off, cnt); d.finish_queue()
+            assert np.array_equal(d.u[off:off + cnt], full[off:off + cnt]), (off, cnt)
+            assert np.all(d.u[:off] == -1.0) and np.all(d.u[off + cnt:] == -1.0)
+        patch = rng.standard_normal(3 * N).astype(np.float32)
+        off, cnt = N - 2 * Nx - 5, 3 * Nx + 11  # crosses from ux into uy, ragged at both ends
+        d.u[:] = patch
+        d.write_to_device(A.FIELD_U, off, cnt)
+        expect = full.copy(); expect[off:off + cnt] = patch[off:off + cnt]
+        d.u[:] = 0.0
+        d.read_from_device(A.FIELD_U); d.finish_queue()
+        assert np.array_equal(d.u, expect)
+        flags = rng.integers(0, 255, N).astype(np.uint8)
+        d.flags[:] = flags
+        d.write_to_device(A.FIELD_FLAGS)
+        d.flags[:] = 0
+        d.read_from_device(A.FIELD_FLAGS, 3, N - 7); d.finish_queue()
+        assert np.array_equal(d.flags[3:N - 4], flags[3:N - 4])
+        fi = rng.integers(0, 65535, 19 * N).astype(np.uint16)
+        d.write_fi(fi)
+        assert np.array_equal(d.read_fi(), fi)
