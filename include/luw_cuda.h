@@ -152,6 +152,20 @@ int luw_cellset_upload(luw_cellset* set, int field, const void* host_values);
 int luw_cellset_download(luw_cellset* set, int field, void* host_values);
 int luw_cellset_destroy(luw_cellset* set);
 
+/* Device-side time averaging. The reference reads u and rho of ALL cells back every sample and updates running mean / M2 on host threads
+ * (process_post_step_samples -> enqueue_read_u_rho + accumulate_from_buffers, FX/setup.cpp:4411-4425, 4441-4488, 4510-4542). Here the accumulators live in
+ * HBM and one kernel applies the same per-cell Welford update (same operations, same roundings) to the fields where they are; only the finished
+ * statistics cross PCIe. accumulate: ++count, inv_n = 1/count, mean += (x-mean)*inv_n, M2 += (x-mean_old)*(x-mean_new) for ux, uy, uz; running mean of rho.
+ * The caller runs luw_update_fields first when the domain does not store rho/u every step, like the reference does (FX/setup.cpp:4412-4414).
+ * download: dense host arrays in the layout of `u` / `rho`: mean_u[c*N+n], m2_u[c*N+n] (c = 0..2), mean_rho[n]; any pointer may be NULL.
+ * (The reference keeps avg_u interleaved [3n+c] and M2 per component; the C++ host layer re-packs, latticeurbanwind_b200/host/lbm.hpp.) */
+typedef struct luw_stats luw_stats;
+int luw_stats_create(luw_domain* dom, luw_stats** out); /* accumulators zero-filled: avg_u.assign(.., 0.0f) ..., FX/setup.cpp:4258-4266 */
+int luw_stats_accumulate(luw_stats* st);
+int luw_stats_reset(luw_stats* st); /* std::fill(.., 0.0f), avg_count = 0: FX/setup.cpp:4556-4562 */
+int luw_stats_download(luw_stats* st, float* host_mean_u, float* host_m2_u, float* host_mean_rho, uint64_t* count);
+int luw_stats_destroy(luw_stats* st);
+
 /* page-locked host memory for the mirrors (the reference's Memory<T> owns pageable new[] buffers, FX/opencl.hpp:354) */
 int luw_host_alloc(void** host_ptr, uint64_t bytes);
 int luw_host_free(void* host_ptr);

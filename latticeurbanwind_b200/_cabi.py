@@ -66,6 +66,11 @@ EXPORTS = {  # name -> argtypes; every symbol include/luw_cuda.h declares
     "luw_cellset_upload": [C.c_void_p, C.c_int, C.c_void_p],
     "luw_cellset_download": [C.c_void_p, C.c_int, C.c_void_p],
     "luw_cellset_destroy": [C.c_void_p],
+    "luw_stats_create": [C.c_void_p, C.POINTER(C.c_void_p)],
+    "luw_stats_accumulate": [C.c_void_p],
+    "luw_stats_reset": [C.c_void_p],
+    "luw_stats_download": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)],
+    "luw_stats_destroy": [C.c_void_p],
     "luw_host_alloc": [C.POINTER(C.c_void_p), C.c_uint64],
     "luw_host_free": [C.c_void_p],
     "luw_sync": [C.c_void_p],

@@ -67,6 +67,11 @@ struct luw_cellset {
 	uint64_t* cell; // device: local cell indices
 	float* stage; // device staging: 4*count bytes per component, up to 3 components
 };
+struct luw_stats {
+	luw_domain* dom;
+	uint64_t count;
+	float* mean_u; float* m2_u; float* mean_rho; // device, pitched like u / rho: [c*c.N + n]
+};
 struct luw_vk_inlet {
 	luw_domain* dom;
 	uint64_t P, M, V;
@@ -238,6 +243,23 @@ __global__ void k_halo_wait(const uint32_t* flag_p, const uint32_t* flag_m, cons
 			__nanosleep(200u);
 			if(clock64()-t0>40000000000ll) __trap(); // ~20 s
 		}
+	}
+}
+// FX/setup.cpp:4441-4488 per cell, on the device arrays. Products and sums are rounded separately (explicit intrinsics), as in the reference's host build.
+__global__ void __launch_bounds__(256) k_stats_accumulate(const uint64_t N, const float inv_n, const float* __restrict__ rho, const float* __restrict__ u,
+	float* __restrict__ mean_u, float* __restrict__ m2_u, float* __restrict__ mean_rho) {
+	for(uint64_t n=(uint64_t)blockIdx.x*blockDim.x+threadIdx.x; n<N; n+=(uint64_t)gridDim.x*blockDim.x) {
+#pragma unroll
+		for(uint32_t c=0u; c<3u; c++) {
+			const float x = u[(uint64_t)c*N+n];
+			float mean = mean_u[(uint64_t)c*N+n];
+			const float delta = __fadd_rn(x, -mean);
+			mean = __fadd_rn(mean, __fmul_rn(delta, inv_n));
+			m2_u[(uint64_t)c*N+n] = __fadd_rn(m2_u[(uint64_t)c*N+n], __fmul_rn(delta, __fadd_rn(x, -mean)));
+			mean_u[(uint64_t)c*N+n] = mean;
+		}
+		const float r = mean_rho[n];
+		mean_rho[n] = __fadd_rn(r, __fmul_rn(__fadd_rn(rho[n], -r), inv_n));
 	}
 }
 __global__ void k_fill_f32(float* p, const uint64_t n, const float v) {
@@ -718,6 +740,62 @@ int luw_cellset_destroy(luw_cellset* s) {
 	cudaStreamSynchronize(s->dom->stream);
 	cudaFree(s->cell); cudaFree(s->stage);
 	delete s;
+	return LUW_OK;
+}
+
+int luw_stats_create(luw_domain* d, luw_stats** out) {
+	if(!d||!out) return fail(LUW_ERR_INVALID, "null argument");
+	*out = nullptr;
+	DeviceGuard guard(d->p.device);
+	luw_stats* st = new(std::nothrow) luw_stats();
+	if(!st) return fail(LUW_ERR_OOM, "host allocation failed");
+	st->dom = d; st->count = 0ull; st->mean_u = st->m2_u = st->mean_rho = nullptr;
+	int rc = dev_alloc(d, &st->mean_u, 3ull*d->c.N);
+	if(rc==LUW_OK) rc = dev_alloc(d, &st->m2_u, 3ull*d->c.N);
+	if(rc==LUW_OK) rc = dev_alloc(d, &st->mean_rho, d->c.N);
+	if(rc==LUW_OK) rc = luw_stats_reset(st);
+	if(rc!=LUW_OK) { const std::string keep = g_error; luw_stats_destroy(st); g_error = keep; return rc; }
+	*out = st;
+	return LUW_OK;
+}
+int luw_stats_reset(luw_stats* st) {
+	if(!st) return fail(LUW_ERR_INVALID, "null statistics object");
+	luw_domain* d = st->dom;
+	DeviceGuard guard(d->p.device);
+	CU(cudaMemsetAsync(st->mean_u, 0, 3ull*d->c.N*4ull, d->stream));
+	CU(cudaMemsetAsync(st->m2_u, 0, 3ull*d->c.N*4ull, d->stream));
+	CU(cudaMemsetAsync(st->mean_rho, 0, d->c.N*4ull, d->stream));
+	st->count = 0ull;
+	return LUW_OK;
+}
+int luw_stats_accumulate(luw_stats* st) {
+	if(!st) return fail(LUW_ERR_INVALID, "null statistics object");
+	luw_domain* d = st->dom;
+	DeviceGuard guard(d->p.device);
+	st->count++;
+	const float inv_n = 1.0f/(float)st->count;
+	k_stats_accumulate<<<(unsigned)(4*d->sm_count>0 ? 8*d->sm_count : 1184), 256, 0, d->stream>>>(d->c.N, inv_n, d->c.rho, d->c.u, st->mean_u, st->m2_u, st->mean_rho);
+	CU(cudaGetLastError());
+	d->launches++;
+	return LUW_OK;
+}
+int luw_stats_download(luw_stats* st, float* host_mean_u, float* host_m2_u, float* host_mean_rho, uint64_t* count) {
+	if(!st) return fail(LUW_ERR_INVALID, "null statistics object");
+	luw_domain* d = st->dom;
+	DeviceGuard guard(d->p.device);
+	if(host_mean_u) CU(copy_field(d, (char*)st->mean_u, 4u, (char*)host_mean_u, 0ull, 3ull*d->ncells, false));
+	if(host_m2_u) CU(copy_field(d, (char*)st->m2_u, 4u, (char*)host_m2_u, 0ull, 3ull*d->ncells, false));
+	if(host_mean_rho) CU(copy_field(d, (char*)st->mean_rho, 4u, (char*)host_mean_rho, 0ull, d->ncells, false));
+	CU(cudaStreamSynchronize(d->stream));
+	if(count) *count = st->count;
+	return LUW_OK;
+}
+int luw_stats_destroy(luw_stats* st) {
+	if(!st) return LUW_OK;
+	DeviceGuard guard(st->dom->p.device);
+	cudaStreamSynchronize(st->dom->stream);
+	cudaFree(st->mean_u); cudaFree(st->m2_u); cudaFree(st->mean_rho);
+	delete st;
 	return LUW_OK;
 }
 

@@ -222,6 +222,35 @@ class CellSet:
             self._h = C.c_void_p()
 
 
+class Stats:
+    """Device-side running mean / M2 of u and mean of rho (luw_stats_*): the reference's accumulate_from_buffers (FX/setup.cpp:4441-4488) without the
+    per-sample full-field read-back."""
+
+    def __init__(self, domain):
+        self.domain = domain
+        self._h = C.c_void_p()
+        A.check(A.lib().luw_stats_create(domain._h, C.byref(self._h)))
+
+    def accumulate(self):
+        A.check(A.lib().luw_stats_accumulate(self._h))
+
+    def reset(self):
+        A.check(A.lib().luw_stats_reset(self._h))
+
+    def download(self):
+        """-> (mean_u[3N] SoA, m2_u[3N] SoA, mean_rho[N], count)"""
+        N = self.domain.N
+        mean_u, m2_u, mean_rho = np.empty(3 * N, np.float32), np.empty(3 * N, np.float32), np.empty(N, np.float32)
+        n = C.c_uint64()
+        A.check(A.lib().luw_stats_download(self._h, _ptr(mean_u), _ptr(m2_u), _ptr(mean_rho), C.byref(n)))
+        return mean_u, m2_u, mean_rho, n.value
+
+    def close(self):
+        if self._h:
+            A.lib().luw_stats_destroy(self._h)
+            self._h = C.c_void_p()
+
+
 def pinned_empty(count, dtype):
     """numpy array over page-locked host memory (luw_host_alloc). The array keeps the allocation alive through its base object."""
     dtype = np.dtype(dtype)

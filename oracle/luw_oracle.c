@@ -477,3 +477,19 @@ void luwo_vk_inlet_apply(uint64_t Ncells, uint32_t use_interp, float t0, float t
 		u[n] = fmaf(sigma, qx, ubx); u[Ncells+n] = fmaf(sigma, qy, uby); u[2u*Ncells+n] = fmaf(sigma, qz, ubz);
 	}
 }
+
+/* FX/setup.cpp:4441-4488: ++avg_count; inv_n = 1/avg_count; per cell Welford update of the three velocity components and the running mean of rho */
+void luwo_stats_accumulate(uint64_t N, uint64_t count, const float* rho, const float* u, float* u_avg, float* rho_avg, float* m2_u, float* m2_v, float* m2_w) {
+	const float inv_n = 1.0f/(float)count;
+	const float* ux = u; const float* uy = u+N; const float* uz = u+2u*N;
+	int64_t n;
+#pragma omp parallel for schedule(static) num_threads(luwo_get_threads())
+	for(n=0; n<(int64_t)N; n++) {
+		const uint64_t i3 = 3ull*(uint64_t)n;
+		float mean_u = u_avg[i3], mean_v = u_avg[i3+1u], mean_w = u_avg[i3+2u];
+		const float delta_u = ux[n]-mean_u; mean_u += delta_u*inv_n; m2_u[n] += delta_u*(ux[n]-mean_u); u_avg[i3] = mean_u;
+		const float delta_v = uy[n]-mean_v; mean_v += delta_v*inv_n; m2_v[n] += delta_v*(uy[n]-mean_v); u_avg[i3+1u] = mean_v;
+		const float delta_w = uz[n]-mean_w; mean_w += delta_w*inv_n; m2_w[n] += delta_w*(uz[n]-mean_w); u_avg[i3+2u] = mean_w;
+		rho_avg[n] += (rho[n]-rho_avg[n])*inv_n;
+	}
+}

@@ -62,6 +62,10 @@ void luwo_transfer_insert_rho_u_flags(const luwo_params* p, uint32_t direction, 
 void luwo_vk_inlet_apply(uint64_t N_cells, uint32_t use_interp, float t0, float t1, float alpha, uint64_t point_count, uint64_t mode_count, uint64_t mode_stride,
 	const uint64_t* point_cell, const uint8_t* point_face, const float* point_data, const float* mode_data, float* u);
 
+/* running mean / M2 of the sampled fields: the host loop `accumulate_from_buffers` of the case driver, FX/setup.cpp:4441-4488 (Welford update per cell,
+ * u_avg interleaved [3n+c], products and sums rounded separately as the reference's g++ build does). `count` is the sample number AFTER the increment. */
+void luwo_stats_accumulate(uint64_t N, uint64_t count, const float* rho, const float* u, float* u_avg, float* rho_avg, float* m2_u, float* m2_v, float* m2_w);
+
 void luwo_set_threads(int n); /* 0 = all cores */
 int luwo_get_threads(void);
 

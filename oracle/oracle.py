@@ -149,6 +149,40 @@ class Oracle:
                                      _p(point_cell), _p(point_face), _p(point_data), _p(mode_data), _p(u))
 
 
+def stats_accumulate(lib_fn, count, rho, u, u_avg, rho_avg, m2_u, m2_v, m2_w):
+    lib_fn(C.c_uint64(rho.size), count, _p(rho), _p(u), _p(u_avg), _p(rho_avg), _p(m2_u), _p(m2_v), _p(m2_w))
+
+
+class RefStats:
+    """The reference's own averaging loop (FX/setup.cpp:4441-4488), text extracted by ref_shim/make_ref_stats.py and built into oracle/_ref/libluwref_stats.so."""
+    PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libluwref_stats.so")
+
+    @classmethod
+    def available(cls):
+        return os.path.isfile(cls.PATH)
+
+    def __init__(self):
+        self.lib = C.CDLL(self.PATH)
+        self.lib.luwref_stats_accumulate.restype = None
+        self.count = C.c_uint64(0)
+
+    def accumulate(self, rho, u, u_avg, rho_avg, m2_u, m2_v, m2_w):
+        stats_accumulate(self.lib.luwref_stats_accumulate, C.byref(self.count), rho, u, u_avg, rho_avg, m2_u, m2_v, m2_w)
+
+
+class OracleStats:
+    """C restatement (luwo_stats_accumulate)."""
+
+    def __init__(self):
+        self.lib = Oracle().lib
+        self.lib.luwo_stats_accumulate.restype = None
+        self.count = 0
+
+    def accumulate(self, rho, u, u_avg, rho_avg, m2_u, m2_v, m2_w):
+        self.count += 1
+        stats_accumulate(self.lib.luwo_stats_accumulate, C.c_uint64(self.count), rho, u, u_avg, rho_avg, m2_u, m2_v, m2_w)
+
+
 def ref_available(precision=FP32, feature_set="luw"):
     return os.path.isfile(os.path.join(HERE, "_ref", f"libluwref_{PREC_NAME[precision]}_{feature_set}.so"))
 

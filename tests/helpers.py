@@ -174,3 +174,28 @@ def vk_case(seed=7):
     md[4 * V:7 * V] = rng.normal(0, 1.0, 3 * V).astype(np.float32)
     md[7 * V:10 * V] = rng.uniform(0, 2 * np.pi, 3 * V).astype(np.float32)
     return pc, pf, pd, md, M, V, N
+
+
+# ---------------------------------------------------------------------------------------------- running statistics (FX/setup.cpp:4441-4488)
+STATS_N, STATS_SAMPLES = 5000, 6
+
+
+def stats_samples():
+    """Seeded sequence of (rho, u) samples, magnitudes like a turbulent LBM field (u ~ 0.05 +- 0.02, rho ~ 1 +- 1e-3)."""
+    rng = np.random.default_rng(2024)
+    out = []
+    for _ in range(STATS_SAMPLES):
+        rho = (1.0 + 1e-3 * rng.standard_normal(STATS_N)).astype(np.float32)
+        u = (np.array([0.05, 0.0, 0.01], np.float32)[:, None] + 0.02 * rng.standard_normal((3, STATS_N)).astype(np.float32)).reshape(-1).astype(np.float32)
+        out.append((rho, u))
+    return out
+
+
+def stats_run(engine):
+    """engine: oracle.OracleStats() / oracle.RefStats(). Returns (u_avg interleaved [3n+c], rho_avg, m2_u, m2_v, m2_w) after all samples."""
+    N = STATS_N
+    u_avg, rho_avg = np.zeros(3 * N, np.float32), np.zeros(N, np.float32)
+    m2 = [np.zeros(N, np.float32) for _ in range(3)]
+    for rho, u in stats_samples():
+        engine.accumulate(rho, u, u_avg, rho_avg, *m2)
+    return u_avg, rho_avg, m2[0], m2[1], m2[2]
