@@ -323,6 +323,24 @@ def e2e_steps(d, CellSet, pinned_empty, A, shape, K, t_upload_init, N):
            "job": {"upload_init_s": t_upload_init, "h2d_bytes": int(17 * N), "readback_s": t_down, "d2h_bytes": int(16 * N),
                    "note": "one-off per case: full rho/u/flags images up (17 B/cell, pinned), rho/u down (16 B/cell)"}}
     cin.close(); cpr.close()
+    try:  # von Karman inlet (on in every default deck): 256 modes on the TYPE_E cells of the x = 0 face, once per step in the reference's loop (FX/setup.cpp:538-558)
+        from latticeurbanwind_b200.domain import VkInlet
+        P, M = int(inlet.size), 256
+        rng = np.random.default_rng(5)
+        pdv = np.zeros(7 * P, np.float32)
+        pdv[0:P] = 0.0; pdv[P:2 * P] = ((inlet // np.uint64(Nx)) % np.uint64(Ny)).astype(np.float32); pdv[2 * P:3 * P] = (inlet // np.uint64(Nx * Ny)).astype(np.float32)
+        for c in range(3):
+            pdv[(3 + c) * P:(4 + c) * P] = d.u[c * d.N + inlet.astype(np.int64)]
+        pdv[6 * P:7 * P] = 0.004
+        V = 5 * M
+        mdv = np.concatenate([rng.normal(0, 0.3, 3 * V), rng.normal(0, 0.05, V), rng.normal(0, 1.0, 3 * V), rng.uniform(0, 2 * np.pi, 3 * V)]).astype(np.float32)
+        vk = VkInlet(d, inlet, np.zeros(P, np.uint8), pdv, mdv, M, V)
+        vk.apply(0, 100.0, 101.0, 0.0); d.finish_queue()
+        d.timer_begin(); vk.apply(0, 101.0, 102.0, 0.0); vk.apply(0, 102.0, 103.0, 0.0); vk.apply(0, 103.0, 104.0, 0.0); vms = d.timer_end() / 3.0
+        out["job"]["vk_inlet"] = {"points": P, "modes": M, "apply_ms": vms, "share_of_step": vms / (dt / K * 1e3)}
+        vk.close()
+    except Exception as exc:  # not part of the metric
+        out["job"]["vk_inlet"] = f"failed: {exc}"
     try:  # one sample of the device-side running statistics (mean / M2 of u, mean of rho: 72 B per cell) next to what it replaces: the read-back above
         from latticeurbanwind_b200.domain import Stats
         st = Stats(d)

@@ -204,5 +204,44 @@ __global__ void __launch_bounds__(128) k_vk_inlet_apply(const uint64_t Ncells, c
 	u[n] = fmaf(sigma, qx, ubx); u[Ncells+n] = fmaf(sigma, qy, uby); u[2ull*Ncells+n] = fmaf(sigma, qz, ubz);
 }
 
+// FAST variant: cos(phase + phi) = cos(phase) cos(phi) - sin(phase) sin(phi). The per-mode products A*cos(phi), A*sin(phi) come from a table built once on
+// the host (luw_vk_inlet_create); per point and mode ONE range-reduced hardware sine / cosine pair replaces three library cosines.
+// cs[6*V]: Ax cos(phix), Ax sin(phix), Ay cos(phiy), Ay sin(phiy), Az cos(phiz), Az sin(phiz). Absolute error per term ~1e-6 |A|. One difference in kind: the
+// reference rounds phase + phi to a float before the cosine (half an ulp of the phase: 1e-4 rad once omega*t reaches thousands of radians), the identity
+// does not -- late in a run the two agree to that rounding, not to 1e-6 (tests/test_gpu_parity.py states both tolerances).
+__device__ __forceinline__ void sincos_reduced(const float ph, float& s, float& c) {
+	const float k = rintf(ph*0.15915494309189535f); // phase / 2 pi
+	float r = fmaf(-k, 6.2831854820251465f, ph); // 2 pi split in two floats (Cody-Waite)
+	r = fmaf(-k, -1.7484555e-7f, r);
+	__sincosf(r, &s, &c);
+}
+__global__ void __launch_bounds__(128) k_vk_inlet_apply_fast(const uint64_t Ncells, const uint32_t use_interp, const float t0, const float t1, const float alpha,
+	const uint64_t P, const uint64_t M, const uint64_t V, const uint64_t* __restrict__ point_cell, const uint8_t* __restrict__ point_face,
+	const float* __restrict__ pd, const float* __restrict__ md, const float* __restrict__ cs, float* __restrict__ u) {
+	const uint64_t i = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x;
+	if(i>=P) return;
+	const uint64_t n = point_cell[i];
+	const uint64_t fid = point_face[i]&0x07u;
+	const float px = pd[i], py = pd[P+i], pz = pd[2ull*P+i];
+	const float ubx = pd[3ull*P+i], uby = pd[4ull*P+i], ubz = pd[5ull*P+i], sigma = pd[6ull*P+i];
+	if(fid>=5ull||!(sigma>0.0f)) { u[n] = ubx; u[Ncells+n] = uby; u[2ull*Ncells+n] = ubz; return; }
+	float qx = 0.0f, qy = 0.0f, qz = 0.0f;
+	for(uint64_t m=0ull; m<M; m++) {
+		const uint64_t k = fid*M+m;
+		const float kx = __ldg(md+k), ky = __ldg(md+V+k), kz = __ldg(md+2ull*V+k), om = __ldg(md+3ull*V+k);
+		const float axc = __ldg(cs+k), axs = __ldg(cs+V+k), ayc = __ldg(cs+2ull*V+k), ays = __ldg(cs+3ull*V+k), azc = __ldg(cs+4ull*V+k), azs = __ldg(cs+5ull*V+k);
+		float s, c;
+		sincos_reduced(fmaf(kx, px, fmaf(ky, py, fmaf(kz, pz, om*t0))), s, c); // the phase is formed exactly like the reference forms it
+		float vx = fmaf(c, axc, -s*axs), vy = fmaf(c, ayc, -s*ays), vz = fmaf(c, azc, -s*azs);
+		if(use_interp!=0u) {
+			sincos_reduced(fmaf(kx, px, fmaf(ky, py, fmaf(kz, pz, om*t1))), s, c);
+			const float vx1 = fmaf(c, axc, -s*axs), vy1 = fmaf(c, ayc, -s*ays), vz1 = fmaf(c, azc, -s*azs);
+			vx = fmaf(alpha, vx1-vx, vx); vy = fmaf(alpha, vy1-vy, vy); vz = fmaf(alpha, vz1-vz, vz);
+		}
+		qx += vx; qy += vy; qz += vz;
+	}
+	u[n] = fmaf(sigma, qx, ubx); u[Ncells+n] = fmaf(sigma, qy, uby); u[2ull*Ncells+n] = fmaf(sigma, qz, ubz);
+}
+
 } // anonymous namespace
 } // namespace luw

@@ -13,7 +13,7 @@ struct KernelSet { // one per arithmetic mode; every function enqueues exactly o
 	cudaError_t (*halo_fi)(const DomainConst& c, int precision, uint32_t axis, uint32_t odd, bool insert, bool xfast, void* buf_p, void* buf_m, cudaStream_t s); // xfast: payload in thread order (library-internal buffers) instead of the reference's face order
 	cudaError_t (*halo_rho_u_flags)(const DomainConst& c, uint32_t axis, bool insert, bool xfast, void* buf_p, void* buf_m, cudaStream_t s);
 	cudaError_t (*vk_inlet_apply)(uint64_t Ncells, uint32_t use_interp, float t0, float t1, float alpha, uint64_t P, uint64_t M, uint64_t V,
-		const uint64_t* point_cell, const uint8_t* point_face, const float* pd, const float* md, float* u, cudaStream_t s);
+		const uint64_t* point_cell, const uint8_t* point_face, const float* pd, const float* md, const float* cs, float* u, cudaStream_t s); // cs: A cos(phi), A sin(phi) table (FAST)
 	bool (*supported)(int precision, uint32_t features);
 	// TMA-tiled stream_collide (lbm_tile.cuh): box shape of tile variant `variant` for this precision / feature set, false if there is none
 	bool (*tile_shape)(int precision, uint32_t features, int variant, TileShape* shape);

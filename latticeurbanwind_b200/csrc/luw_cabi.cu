@@ -76,6 +76,7 @@ struct luw_vk_inlet {
 	luw_domain* dom;
 	uint64_t P, M, V;
 	uint64_t* point_cell; uint8_t* point_face; float* point_data; float* mode_data;
+	float* mode_cs; // [6*V]: A cos(phi), A sin(phi) per component, for the FAST kernel
 };
 
 namespace {
@@ -653,6 +654,12 @@ int luw_vk_inlet_create(luw_domain* d, uint64_t P, uint64_t M, uint64_t V, const
 		if(rc==LUW_OK) rc = dev_alloc(d, &v->point_data, 7ull*P);
 	}
 	if(rc==LUW_OK&&V>0ull) rc = dev_alloc(d, &v->mode_data, 10ull*V);
+	if(rc==LUW_OK&&V>0ull) rc = dev_alloc(d, &v->mode_cs, 6ull*V);
+	std::vector<float> cs(6ull*V);
+	for(uint64_t k=0ull; k<V; k++) for(uint32_t c=0u; c<3u; c++) { // amplitude (rows 4..6) times cos / sin of the phase (rows 7..9), in double, rounded once
+		const double A = md[(4ull+c)*V+k], ph = md[(7ull+c)*V+k];
+		cs[(2ull*c)*V+k] = (float)(A*cos(ph)); cs[(2ull*c+1ull)*V+k] = (float)(A*sin(ph));
+	}
 	if(rc==LUW_OK) {
 		cudaError_t e = cudaSuccess;
 		if(P>0ull) {
@@ -661,6 +668,7 @@ int luw_vk_inlet_create(luw_domain* d, uint64_t P, uint64_t M, uint64_t V, const
 			if(e==cudaSuccess) e = cudaMemcpyAsync(v->point_data, pd, 7ull*P*4ull, cudaMemcpyHostToDevice, d->stream);
 		}
 		if(e==cudaSuccess&&V>0ull) e = cudaMemcpyAsync(v->mode_data, md, 10ull*V*4ull, cudaMemcpyHostToDevice, d->stream);
+		if(e==cudaSuccess&&V>0ull) e = cudaMemcpyAsync(v->mode_cs, cs.data(), 6ull*V*4ull, cudaMemcpyHostToDevice, d->stream);
 		if(e==cudaSuccess) e = cudaStreamSynchronize(d->stream); // host arrays may be freed by the caller afterwards
 		if(e!=cudaSuccess) rc = cuda_fail(e, "upload inlet buffers");
 	}
@@ -672,7 +680,7 @@ int luw_vk_inlet_apply(luw_vk_inlet* v, uint32_t use_interp, float t0, float t1,
 	if(!v) return fail(LUW_ERR_INVALID, "null inlet");
 	luw_domain* d = v->dom;
 	DeviceGuard guard(d->p.device);
-	CU(d->ks->vk_inlet_apply(d->c.N, use_interp, t0, t1, alpha, v->P, v->M, v->V, v->point_cell, v->point_face, v->point_data, v->mode_data, d->c.u, d->stream));
+	CU(d->ks->vk_inlet_apply(d->c.N, use_interp, t0, t1, alpha, v->P, v->M, v->V, v->point_cell, v->point_face, v->point_data, v->mode_data, v->mode_cs, d->c.u, d->stream));
 	if(v->P>0ull) d->launches++;
 	return LUW_OK;
 }
@@ -680,7 +688,7 @@ int luw_vk_inlet_destroy(luw_vk_inlet* v) {
 	if(!v) return LUW_OK;
 	DeviceGuard guard(v->dom->p.device);
 	cudaStreamSynchronize(v->dom->stream);
-	cudaFree(v->point_cell); cudaFree(v->point_face); cudaFree(v->point_data); cudaFree(v->mode_data);
+	cudaFree(v->point_cell); cudaFree(v->point_face); cudaFree(v->point_data); cudaFree(v->mode_data); cudaFree(v->mode_cs);
 	delete v;
 	return LUW_OK;
 }

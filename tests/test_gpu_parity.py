@@ -186,3 +186,33 @@ def test_partial_uploads_and_downloads(Nx):
         fi = rng.integers(0, 65535, 19 * N).astype(np.uint16)
         d.write_fi(fi)
         assert np.array_equal(d.read_fi(), fi)
+
+
+# ---------------------------------------------------------------------------------------------- von Karman inlet (FX/kernel.cpp:2495-2571)
+@pytest.mark.parametrize("arith", [0, 1], ids=["strict", "fast"])
+@pytest.mark.parametrize("interp,t0,t1", [(0, 3.0, 4.0), (1, 3.0, 4.0), (1, 20000.0, 20001.0)], ids=["single", "interp", "interp-late"])
+def test_vk_inlet_matches_oracle(oracle_lib, arith, interp, t0, t1):
+    """u of the inlet cells = base + sigma * sum of modes. STRICT evaluates the reference's expression with CUDA's cosf (a few ulp from libm);
+    FAST uses cos(a+b) = cos a cos b - sin a sin b with one range-reduced hardware sincos per mode (absolute error ~1e-6 per unit amplitude).
+    Tolerance on u (lattice units, |u| ~ 0.1, sigma <= 0.004, 24 modes of amplitude ~1): 2e-7 STRICT, 1e-6 FAST; late in a run (phases of thousands of
+    radians) the reference's own rounding of phase + phi to a float (<= 1.2e-4 rad per term) is what separates the two: 2e-5 FAST."""
+    from latticeurbanwind_b200 import _cabi as A
+    from latticeurbanwind_b200.domain import Domain, VkInlet
+    O = oracle_lib
+    pc, pf, pd, md, M, V, N = H.vk_case()
+    orc = O.Oracle().bind(O.make_params(*H.VK_SHAPE, O.FP16C, O.FEATURE_SETS["luw"]))
+    ref = np.zeros(3 * N, np.float32)
+    orc.vk_inlet_apply(interp, t0, t1, 0.25, pc, pf, pd, md, M, V, ref)
+    with Domain(*H.VK_SHAPE, precision=2, features=H.FEATURE_SETS["luw"], w=1.0, arith=arith, **H.ZONES) as d:
+        d.u[:] = 0.0
+        d.write_to_device(A.FIELD_U)
+        vk = VkInlet(d, pc, pf, pd, md, M, V)
+        vk.apply(interp, t0, t1, 0.25)
+        d.read_from_device(A.FIELD_U); d.finish_queue()
+        vk.close()
+        err = float(np.abs(d.u - ref).max())
+        assert err <= (2e-7 if arith == 0 else 1e-6 if t0 < 1000.0 else 2e-5), err
+        untouched = np.ones(3 * N, bool)
+        for c in range(3):
+            untouched[c * N + pc.astype(np.int64)] = False
+        assert np.all(d.u[untouched] == 0.0)
