@@ -191,6 +191,17 @@ template<> struct PairCodec<P_FP16C> {
 		return mk2(__uint_as_float(__float_as_uint(m.v.x)|((r<<16)&0x80000000u)), __uint_as_float(__float_as_uint(m.v.y)|(r&0x80000000u)));
 	}
 	static __device__ __forceinline__ R enc(const f2 v) { return (uint32_t)Ddf<P_FP16C>::enc(v.v.x)|((uint32_t)Ddf<P_FP16C>::enc(v.v.y)<<16); }
+	// FAST encode: f * 2^-112 has the FP16C exponent in a float's exponent field, for subnormal codes too (the product is then a subnormal float); adding
+	// half an FP16C ulp (0x800) and dropping 12 bits is the reference's rounding (FX/kernel.cpp:870-875), including its wrap-around above the format's range.
+	// Differs from the exact encoder only through the multiplication's own rounding of subnormal results, 12 bits below the FP16C ulp (a double rounding
+	// that moves a result by one code when it lands exactly on a tie).
+	static __device__ __forceinline__ R enc_fast(const f2 v) {
+		const float2 g = __fmul2_rn(v.v, make_float2(1.925929944387236e-34f, 1.925929944387236e-34f)); // 2^-112
+		const uint32_t bx = __float_as_uint(g.x), by = __float_as_uint(g.y);
+		const uint32_t lo = (((bx+0x800u)>>12)&0x7FFFu)|((bx>>16)&0x8000u);
+		const uint32_t hi = (((by+0x800u)<<4)&0x7FFF0000u)|(by&0x80000000u);
+		return lo|hi;
+	}
 	static __device__ __forceinline__ R mix(const bool k0, const bool k1, const R n, const R o) { return (k0 ? (n&0xFFFFu) : (o&0xFFFFu))|(k1 ? (n&0xFFFF0000u) : (o&0xFFFF0000u)); }
 	static __device__ __forceinline__ E low(const R w) { return (uint16_t)(w&0xFFFFu); }
 	static __device__ __forceinline__ R shift_in(const R w0, const uint8_t* next) { return __byte_perm(w0, (uint32_t)*(const uint16_t*)next, 0x5432); }
@@ -501,7 +512,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 				constexpr bool SG = (FEAT&F_SUBGRID)!=0u;
 				uint8_t* const bb = (uint8_t*)box;
 				const auto dec_in = [](const R w) -> f2 { if constexpr (P==P_FP16S) return PairCodec<P_FP16S>::dec_raw(w); else return PC::dec(w); };
-				const auto enc_out = [](const f2 v) -> R { if constexpr (P==P_FP16S) return PairCodec<P_FP16S>::enc_raw(v); else return PC::enc(v); };
+				const auto enc_out = [](const f2 v) -> R { if constexpr (P==P_FP16S) return PairCodec<P_FP16S>::enc_raw(v); else if constexpr (P==P_FP16C) return PairCodec<P_FP16C>::enc_fast(v); else return PC::enc(v); };
 				Moments M;
 				const f2 g0 = dec_in(*(const R*)bb);
 				M.R = g0;
@@ -573,7 +584,9 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 			R nw[Q];
 #pragma unroll
 			for(int b=0; b<Q; b++) {
-				if(FAST&&P==P_FP16S) { const uint32_t r_ = PairCodec<P_FP16S>::enc_raw(f[b]); nw[b] = *(const R*)&r_; } else nw[b] = PC::enc(f[b]);
+				if(FAST&&P==P_FP16S) { const uint32_t r_ = PairCodec<P_FP16S>::enc_raw(f[b]); nw[b] = *(const R*)&r_; }
+				else if constexpr (FAST&&P==P_FP16C) nw[b] = PairCodec<P_FP16C>::enc_fast(f[b]);
+				else nw[b] = PC::enc(f[b]);
 			}
 			uint8_t* const bb = (uint8_t*)box;
 			if(run0&&run1) {
