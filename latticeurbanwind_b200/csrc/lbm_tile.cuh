@@ -324,13 +324,14 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 	const uint32_t tid = threadIdx.x;
 	TRACE_CLK(0);
 	if(tid==0u) {
+		if(blockIdx.x==0u) c.sched[(uint32_t)(a.t&1ull)^1u] = 0u; // strip counter of the NEXT step (steps alternate between two counters, so no memset node sits between launches)
 		for(int s=0; s<S; s++) { mbar_init(bar_full+s, 1u); mbar_init(bar_done+s, (uint32_t)NC); }
 		mbar_init(bar_head, 1u);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
 
-	// tile sequence of this CTA: strips (one (y,z) tile row each) drawn from the counter *c.sched (zeroed by the host before the launch); inside a strip x ascending
+	// tile sequence of this CTA: strips (one (y,z) tile row each) drawn from the counter c.sched[t&1] (zeroed by the previous step's launch, or by the host when the parity repeats); inside a strip x ascending
 	const uint32_t nstrips = tiles_y*tiles_z;
 	constexpr uint32_t END = 0xFFFFFFFFu;
 	const uint32_t odd = (uint32_t)(a.t&1ull);
@@ -346,7 +347,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 			const int s = (int)(issued%(uint32_t)S);
 			if(lxt==0u) { // next strip
 				uint32_t v = 0u;
-				if(leader) v = atomicAdd(c.sched, 1u);
+				if(leader) v = atomicAdd(c.sched+odd, 1u); // the counter of this step parity; the other one is being zeroed for the next step
 				lstrip = __shfl_sync(0xFFFFFFFFu, v, 0);
 				if(lstrip>=nstrips) { // no more work: tell the consumers
 					ended = true;

@@ -43,6 +43,7 @@ struct luw_domain {
 	size_t ddf_size = 4u;
 	luw::TileMaps maps; // TMA descriptors for the tiled step
 	bool tiled = false; // the tiled step is usable for this domain
+	int last_sched_parity = -1; // parity of the last tiled step enqueued (see enqueue_step)
 	int tile_variant = 0, sm_count = 0;
 	struct HaloAxis { // transfer buffers of one decomposed axis (reference: transfer_buffer_p / _m, FX/lbm.cpp:1864-1889) and the events that order their use
 		char* send_p = nullptr; char* send_m = nullptr; char* recv_p = nullptr; char* recv_m = nullptr;
@@ -187,7 +188,11 @@ void setup_tiles(luw_domain* d) {
 }
 cudaError_t enqueue_step(luw_domain* d, const luw::StepArgs& a) {
 	cudaError_t e = cudaSuccess;
-	if(d->tiled) { e = cudaMemsetAsync(d->c.sched, 0, 4u, d->stream); if(e!=cudaSuccess) return e; } // strip counter of the persistent kernel
+	if(d->tiled) { // strip counters of the persistent kernel: step parity p uses sched[p] and zeroes sched[p^1]; a memset is only needed when a parity repeats
+		const int par = (int)(a.t&1ull);
+		if(par==d->last_sched_parity||d->last_sched_parity<0) { e = cudaMemsetAsync(d->c.sched, 0, 8u, d->stream); if(e!=cudaSuccess) return e; }
+		d->last_sched_parity = par;
+	}
 	if(d->ktiming) { // event pair around the main kernel
 		if(d->kev_used+2u>d->kev.size()) for(int k=0; k<2; k++) { cudaEvent_t ev; e = cudaEventCreate(&ev); if(e!=cudaSuccess) return e; d->kev.push_back(ev); }
 		e = cudaEventRecord(d->kev[d->kev_used], d->stream); if(e!=cudaSuccess) return e;

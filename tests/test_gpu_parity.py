@@ -216,3 +216,37 @@ def test_vk_inlet_matches_oracle(oracle_lib, arith, interp, t0, t1):
         for c in range(3):
             untouched[c * N + pc.astype(np.int64)] = False
         assert np.all(d.u[untouched] == 0.0)
+
+
+# ---------------------------------------------------------------------------------------------- full-size properties (no oracle at these sizes)
+def test_full_size_decomposition_identity_and_fixed_point():
+    """At a bench-sized block (33.5 M cells, the urban case of BASELINE configs[2] at a quarter of its footprint) the oracle takes minutes, so parity is carried by
+    size-independent properties: (1) the 1x2x2 decomposition (four domains sharing the GPU, halo exchange in the library) reproduces the single-domain
+    FAST FP16S run bit for bit; (2) cells the step must not touch (TYPE_S buildings and ground) keep rho / u / flags; (3) u stays inside the clamp +-c."""
+    from latticeurbanwind_b200 import _cabi as A
+    from latticeurbanwind_b200.lbm import LBM
+    shape = (512, 512, 128)
+    flags, rho, u = cases.block_case("urban", shape)
+    zones = dict(downstream_face=2, buffer_N=16, buffer_inv_tau=0.01, buffer_nudge_vertical=1, sponge_N=20, sponge_inv_tau=0.02)
+    res = []
+    for D in ((1, 1, 1), (1, 2, 2)):
+        lbm = LBM(shape, D=D, nu=1e-6, precision=A.FP16S, features=H.FEATURE_SETS["luw"], arith=A.ARITH_FAST, omega=H.OMEGA, **zones)
+        lbm.flags[:], lbm.rho[:], lbm.u[:] = flags, rho, u
+        lbm.run(12)
+        lbm.read_from_device()
+        res.append((lbm.rho.copy(), lbm.u.copy(), lbm.flags.copy()))
+        lbm.close()
+    assert np.array_equal(res[0][0], res[1][0]), "rho differs between D=1 and 1x2x2"
+    assert np.array_equal(res[0][1], res[1][1]), "u differs between D=1 and 1x2x2"
+    r1, u1, f1 = res[0]
+    assert np.array_equal(f1, flags)
+    solid = (flags & 3) == 1
+    assert solid.sum() > 100000
+    N = flags.size
+    assert np.array_equal(r1[solid], rho[solid])
+    for c in range(3):
+        assert np.all(u1[c * N:(c + 1) * N][solid] == 0.0)  # initialize zeroes u in solids (FX/kernel.cpp:1379), the step never writes them
+    assert float(np.abs(u1).max()) <= 0.57735027 + 1e-7 and np.isfinite(r1).all()
+    fluid = ~solid & ((flags & 3) != 2)
+    lo, hi = float(r1[fluid].min()), float(r1[fluid].max())  # impulsive start against the cubes: a pressure wave of order rho*u/c_s = 0.17
+    assert 0.6 < lo and hi < 1.5, (lo, hi)
