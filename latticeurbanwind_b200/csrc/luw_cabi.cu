@@ -36,6 +36,7 @@ struct luw_domain {
 	luw::DomainConst c;
 	const luw::KernelSet* ks = nullptr;
 	cudaStream_t own_stream = nullptr, stream = nullptr;
+	cudaStream_t copy_stream = nullptr; // H2D / D2H of cell sets, overlapping the kernels on `stream`
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	float* wbuf = nullptr; float* sigma = nullptr;
 	uint64_t bytes = 0ull, launches = 0ull;
@@ -66,7 +67,12 @@ struct luw_cellset {
 	luw_domain* dom;
 	uint64_t count;
 	uint64_t* cell; // device: local cell indices
-	float* stage; // device staging: 4*count bytes per component, up to 3 components
+	// Copies run on the domain's copy stream so that they overlap the step kernel; only the small scatter / gather kernels sit on the domain's stream.
+	// Two staging slots per direction (4*count bytes per component, up to 3 components), handed round by events:
+	float* up[2]; float* dn[2];
+	cudaEvent_t staged[2], scattered[2]; // upload: H2D into up[k] finished / the scatter has read up[k]
+	cudaEvent_t gathered[2], drained[2]; // download: gather has filled dn[k] / D2H out of dn[k] finished
+	uint32_t up_seq, dn_seq;
 };
 struct luw_stats {
 	luw_domain* dom;
@@ -341,6 +347,7 @@ int luw_domain_create(const luw_domain_params* p, luw_domain** out) {
 
 	int rc = LUW_OK;
 	cudaError_t e = cudaStreamCreateWithFlags(&d->own_stream, cudaStreamNonBlocking);
+	if(e==cudaSuccess) e = cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking);
 	if(e==cudaSuccess) e = cudaEventCreate(&d->ev0);
 	if(e==cudaSuccess) e = cudaEventCreate(&d->ev1);
 	if(e!=cudaSuccess) rc = cuda_fail(e, "stream/event creation");
@@ -402,6 +409,7 @@ int luw_domain_destroy(luw_domain* d) {
 		if(h.dn&&!h.same) cudaIpcCloseMemHandle(h.dn);
 		cudaFree(h.block);
 	}
+	if(d->copy_stream) { cudaStreamSynchronize(d->copy_stream); cudaStreamDestroy(d->copy_stream); }
 	if(d->own_stream) cudaStreamDestroy(d->own_stream);
 	delete d;
 	return LUW_OK;
@@ -707,11 +715,19 @@ int luw_cellset_create(luw_domain* d, uint64_t count, const uint64_t* host_cell_
 	DeviceGuard guard(d->p.device);
 	luw_cellset* s = new(std::nothrow) luw_cellset();
 	if(!s) return fail(LUW_ERR_OOM, "host allocation failed");
-	s->dom = d; s->count = count; s->cell = nullptr; s->stage = nullptr;
+	memset(s, 0, sizeof(*s));
+	s->dom = d; s->count = count;
 	int rc = LUW_OK;
 	if(count>0ull) {
 		rc = dev_alloc(d, &s->cell, count);
-		if(rc==LUW_OK) rc = dev_alloc(d, &s->stage, 3ull*count);
+		for(int k=0; k<2&&rc==LUW_OK; k++) { rc = dev_alloc(d, &s->up[k], 3ull*count); if(rc==LUW_OK) rc = dev_alloc(d, &s->dn[k], 3ull*count); }
+		for(int k=0; k<2&&rc==LUW_OK; k++) {
+			cudaError_t e = cudaEventCreateWithFlags(&s->staged[k], cudaEventDisableTiming);
+			if(e==cudaSuccess) e = cudaEventCreateWithFlags(&s->scattered[k], cudaEventDisableTiming);
+			if(e==cudaSuccess) e = cudaEventCreateWithFlags(&s->gathered[k], cudaEventDisableTiming);
+			if(e==cudaSuccess) e = cudaEventCreateWithFlags(&s->drained[k], cudaEventDisableTiming);
+			if(e!=cudaSuccess) rc = cuda_fail(e, "cudaEventCreate");
+		}
 		if(rc==LUW_OK) {
 			cudaError_t e = cudaMemcpyAsync(s->cell, cd.data(), count*8ull, cudaMemcpyHostToDevice, d->stream);
 			if(e==cudaSuccess) e = cudaStreamSynchronize(d->stream);
@@ -731,18 +747,29 @@ static int cellset_move(luw_cellset* s, int field, void* host, const bool up) {
 	const uint32_t comps = field==LUW_FIELD_U ? 3u : 1u;
 	const size_t elem = field==LUW_FIELD_FLAGS ? 1u : 4u;
 	const unsigned blocks = (unsigned)((s->count+255ull)/256ull);
-	if(up) CU(cudaMemcpyAsync(s->stage, host, comps*s->count*elem, cudaMemcpyHostToDevice, d->stream));
-	if(field==LUW_FIELD_FLAGS) {
-		if(up) k_cellset_scatter<uint8_t><<<blocks, 256, 0, d->stream>>>(d->c.flags, d->c.N, 1u, s->count, s->cell, (const uint8_t*)s->stage);
-		else k_cellset_gather<uint8_t><<<blocks, 256, 0, d->stream>>>(d->c.flags, d->c.N, 1u, s->count, s->cell, (uint8_t*)s->stage);
-	} else {
-		float* f = field==LUW_FIELD_U ? d->c.u : d->c.rho;
-		if(up) k_cellset_scatter<float><<<blocks, 256, 0, d->stream>>>(f, d->c.N, comps, s->count, s->cell, s->stage);
-		else k_cellset_gather<float><<<blocks, 256, 0, d->stream>>>(f, d->c.N, comps, s->count, s->cell, s->stage);
+	const size_t bytes = comps*s->count*elem;
+	if(up) { // copy stream: wait until the slot's last scatter has read it, H2D; domain stream: wait for the copy, scatter
+		const uint32_t k = s->up_seq++&1u;
+		CU(cudaStreamWaitEvent(d->copy_stream, s->scattered[k], 0));
+		CU(cudaMemcpyAsync(s->up[k], host, bytes, cudaMemcpyHostToDevice, d->copy_stream));
+		CU(cudaEventRecord(s->staged[k], d->copy_stream));
+		CU(cudaStreamWaitEvent(d->stream, s->staged[k], 0));
+		if(field==LUW_FIELD_FLAGS) k_cellset_scatter<uint8_t><<<blocks, 256, 0, d->stream>>>(d->c.flags, d->c.N, 1u, s->count, s->cell, (const uint8_t*)s->up[k]);
+		else k_cellset_scatter<float><<<blocks, 256, 0, d->stream>>>(field==LUW_FIELD_U ? d->c.u : d->c.rho, d->c.N, comps, s->count, s->cell, s->up[k]);
+		CU(cudaGetLastError());
+		CU(cudaEventRecord(s->scattered[k], d->stream));
+	} else { // domain stream: wait until the slot's last D2H has drained it, gather; copy stream: wait for the gather, D2H
+		const uint32_t k = s->dn_seq++&1u;
+		CU(cudaStreamWaitEvent(d->stream, s->drained[k], 0));
+		if(field==LUW_FIELD_FLAGS) k_cellset_gather<uint8_t><<<blocks, 256, 0, d->stream>>>(d->c.flags, d->c.N, 1u, s->count, s->cell, (uint8_t*)s->dn[k]);
+		else k_cellset_gather<float><<<blocks, 256, 0, d->stream>>>(field==LUW_FIELD_U ? d->c.u : d->c.rho, d->c.N, comps, s->count, s->cell, s->dn[k]);
+		CU(cudaGetLastError());
+		CU(cudaEventRecord(s->gathered[k], d->stream));
+		CU(cudaStreamWaitEvent(d->copy_stream, s->gathered[k], 0));
+		CU(cudaMemcpyAsync(host, s->dn[k], bytes, cudaMemcpyDeviceToHost, d->copy_stream));
+		CU(cudaEventRecord(s->drained[k], d->copy_stream));
 	}
-	CU(cudaGetLastError());
 	d->launches++;
-	if(!up) CU(cudaMemcpyAsync(host, s->stage, comps*s->count*elem, cudaMemcpyDeviceToHost, d->stream));
 	return LUW_OK;
 }
 int luw_cellset_upload(luw_cellset* s, int field, const void* host_values) { return cellset_move(s, field, (void*)host_values, true); }
@@ -750,8 +777,15 @@ int luw_cellset_download(luw_cellset* s, int field, void* host_values) { return 
 int luw_cellset_destroy(luw_cellset* s) {
 	if(!s) return LUW_OK;
 	DeviceGuard guard(s->dom->p.device);
-	cudaStreamSynchronize(s->dom->stream);
-	cudaFree(s->cell); cudaFree(s->stage);
+	cudaStreamSynchronize(s->dom->stream); cudaStreamSynchronize(s->dom->copy_stream);
+	cudaFree(s->cell);
+	for(int k=0; k<2; k++) {
+		cudaFree(s->up[k]); cudaFree(s->dn[k]);
+		if(s->staged[k]) cudaEventDestroy(s->staged[k]);
+		if(s->scattered[k]) cudaEventDestroy(s->scattered[k]);
+		if(s->gathered[k]) cudaEventDestroy(s->gathered[k]);
+		if(s->drained[k]) cudaEventDestroy(s->drained[k]);
+	}
 	delete s;
 	return LUW_OK;
 }
@@ -828,6 +862,7 @@ int luw_sync(luw_domain* d) {
 	if(!d) return fail(LUW_ERR_INVALID, "null domain");
 	DeviceGuard guard(d->p.device);
 	CU(cudaStreamSynchronize(d->stream));
+	CU(cudaStreamSynchronize(d->copy_stream)); // cell-set read-backs finish on the copy stream
 	return LUW_OK;
 }
 int luw_timer_begin(luw_domain* d) {

@@ -250,3 +250,39 @@ def test_full_size_decomposition_identity_and_fixed_point():
     fluid = ~solid & ((flags & 3) != 2)
     lo, hi = float(r1[fluid].min()), float(r1[fluid].max())  # impulsive start against the cubes: a pressure wave of order rho*u/c_s = 0.17
     assert 0.6 < lo and hi < 1.5, (lo, hi)
+
+
+def test_cell_sets_move_boundary_data_without_whole_fields():
+    """luw_cellset_upload / _download (boundary-field upload and probe read-back): several uploads and read-backs in flight on the copy
+    stream, staging slots reused, results equal to plain whole-field transfers."""
+    from latticeurbanwind_b200 import _cabi as A
+    from latticeurbanwind_b200.domain import CellSet, Domain, pinned_empty
+    Nx, Ny, Nz = 66, 9, 7
+    rng = np.random.default_rng(11)
+    with Domain(Nx, Ny, Nz, precision=1, features=0, w=1.0, arith=0) as d:
+        N = d.N
+        base = rng.standard_normal(3 * N).astype(np.float32)
+        d.u[:] = base
+        d.rho[:] = rng.standard_normal(N).astype(np.float32)
+        rho0 = d.rho.copy()
+        d.upload_all()
+        cells = rng.choice(N, 500, replace=False).astype(np.uint64)
+        cs = CellSet(d, cells)
+        want = base.copy()
+        bufs = []
+        for k in range(5):  # five uploads back to back: the last one wins, none may be torn
+            b = pinned_empty(3 * cs.count, np.float32)
+            b[:] = rng.standard_normal(3 * cs.count).astype(np.float32)
+            bufs.append(b)
+            cs.upload(A.FIELD_U, b)
+        for c in range(3):
+            want[c * N + cells.astype(np.int64)] = bufs[-1][c * cs.count:(c + 1) * cs.count]
+        outs = [(pinned_empty(3 * cs.count, np.float32), pinned_empty(cs.count, np.float32)) for _ in range(3)]
+        for ou, orr in outs:  # three read-back pairs in flight
+            cs.download(A.FIELD_U, ou); cs.download(A.FIELD_RHO, orr)
+        d.finish_queue()
+        for ou, orr in outs:
+            assert np.array_equal(ou, bufs[-1]) and np.array_equal(orr, rho0[cells.astype(np.int64)])
+        d.read_from_device(A.FIELD_U); d.finish_queue()
+        assert np.array_equal(d.u, want)
+        cs.close()
