@@ -142,6 +142,14 @@ int luw_vk_inlet_create(luw_domain* dom, uint64_t point_count, uint64_t mode_cou
 int luw_vk_inlet_apply(luw_vk_inlet* vk, uint32_t use_interp, float t0, float t1, float alpha);
 int luw_vk_inlet_destroy(luw_vk_inlet* vk);
 
+/* kernel "voxelize_mesh", FX/kernel.cpp:2381-2471, as launched by LBM_Domain::voxelize_mesh_on_device -> run_voxelize_pass (FX/lbm.cpp:494-560): rays along
+ * `direction` (0/1/2 = x/y/z; LUW voxelises TYPE_S geometry along z, FX/lbm.cpp:585-587) through every column of the domain, flags of the cells inside the
+ * closed triangle mesh get `flag`, previously solid cells outside are released. host_p0/p1/p2: 3 floats per triangle in lattice coordinates (the mesh as
+ * FX/setup.cpp:4084-4087 leaves it); host_bbu: the 16 floats of `bounding_box_and_velocity` (FX/lbm.cpp:529-549: triangle count as float bits, bounding
+ * box -+ 2 cells, rotation centre, linear and rotational velocity). Only resting geometry (velocities 0, the only way LUW calls it) is supported:
+ * otherwise LUW_ERR_INVALID. Works on the device flags / u in place (upload the host images first if they were edited); bit-exact with the reference. */
+int luw_voxelize_mesh(luw_domain* dom, uint32_t direction, uint8_t flag, const float* host_p0, const float* host_p1, const float* host_p2, uint32_t triangle_count, const float* host_bbu);
+
 /* Boundary-field upload and probe read-back without moving whole fields. The reference writes boundary values into the full host mirrors and
  * uploads / downloads ALL N cells (LBM::initialize FX/lbm.cpp:1226-1237; probes and sampling read the whole u field back, FX/setup.cpp:4411-4425,
  * 4498-4509). A cell set is a fixed list of local cell indices (e.g. the TYPE_E inflow faces, a probe plane); upload scatters host values

@@ -204,6 +204,73 @@ __global__ void __launch_bounds__(128) k_vk_inlet_apply(const uint64_t Ncells, c
 	u[n] = fmaf(sigma, qx, ubx); u[Ncells+n] = fmaf(sigma, qy, uby); u[2ull*Ncells+n] = fmaf(sigma, qz, ubz);
 }
 
+// ------------------------------------------------------------------ kernel: voxelize_mesh (FX/kernel.cpp:2381-2471), resting geometry
+// One thread per column of the face normal to `direction`; the triangles are staged through shared memory in chunks that the whole block walks
+// (the reference reads all of them from global memory per work-item). Ray/triangle arithmetic in the reference's operation order; this kernel is always
+// taken from the STRICT translation unit (-fmad=false, IEEE division), because the flags must be bit-exact and a contracted product flips grazing rays.
+struct VoxBox { uint32_t ntri; float x0, y0, z0, x1, y1, z1; };
+__global__ void __launch_bounds__(128) k_voxelize_mesh(const __grid_constant__ DomainConst c, const uint32_t direction, const uint32_t A, const uint8_t flag, const VoxBox bb,
+	const float* __restrict__ p0, const float* __restrict__ p1, const float* __restrict__ p2) {
+	__shared__ float tri[128][9];
+	const uint32_t a = blockIdx.x*blockDim.x+threadIdx.x;
+	const int Nx = (int)c.Nx, Ny = (int)c.Ny, Nz = (int)c.Nz;
+	const auto clampi = [](const int x, const int lo, const int hi) { return x<lo ? lo : (x>hi ? hi : x); };
+	uint32_t X = 0u, Y = 0u, Z = 0u;
+	if(direction==0u) { X = (uint32_t)clampi((int)bb.x0-c.Ox, 0, Nx-1); Y = a%c.Ny; Z = a/c.Ny; }
+	else if(direction==1u) { X = a/c.Nz; Y = (uint32_t)clampi((int)bb.y0-c.Oy, 0, Ny-1); Z = a%c.Nz; }
+	else { X = a%c.Nx; Y = a/c.Nx; Z = (uint32_t)clampi((int)bb.z0-c.Oz, 0, Nz-1); }
+	const float offx = 0.5f*(float)(Nx+2*c.Ox)-0.5f, offy = 0.5f*(float)(Ny+2*c.Oy)-0.5f, offz = 0.5f*(float)(Nz+2*c.Oz)-0.5f;
+	const float rox = ((float)X+0.5f-0.5f*(float)Nx)+offx, roy = ((float)Y+0.5f-0.5f*(float)Ny)+offy, roz = ((float)Z+0.5f-0.5f*(float)Nz)+offz;
+	const float dx = (float)(direction==0u), dy = (float)(direction==1u), dz = (float)(direction==2u);
+	const bool out_of_box = direction==0u ? (roy<bb.y0||roz<bb.z0||roy>=bb.y1||roz>=bb.z1) : direction==1u ? (rox<bb.x0||roz<bb.z0||rox>=bb.x1||roz>=bb.z1) : (rox<bb.x0||roy<bb.y0||rox>=bb.x1||roy>=bb.y1);
+	const bool active = a<A&&!out_of_box;
+	uint32_t intersections = 0u, intersections_check = 0u;
+	uint16_t distances[64];
+	for(uint32_t base=0u; base<bb.ntri; base+=128u) {
+		__syncthreads();
+		const uint32_t i = base+threadIdx.x;
+		if(i<bb.ntri) {
+#pragma unroll
+			for(int k=0; k<3; k++) { tri[threadIdx.x][k] = p0[3u*i+k]; tri[threadIdx.x][3+k] = p1[3u*i+k]; tri[threadIdx.x][6+k] = p2[3u*i+k]; }
+		}
+		__syncthreads();
+		if(!active) continue;
+		const uint32_t cnt = bb.ntri-base<128u ? bb.ntri-base : 128u;
+		for(uint32_t k=0u; k<cnt; k++) {
+			const float ax = tri[k][0], ay = tri[k][1], az = tri[k][2];
+			const float ux = tri[k][3]-ax, uy = tri[k][4]-ay, uz = tri[k][5]-az;
+			const float vx = tri[k][6]-ax, vy = tri[k][7]-ay, vz = tri[k][8]-az;
+			const float wx = rox-ax, wy = roy-ay, wz = roz-az;
+			const float hx = dy*vz-dz*vy, hy = dz*vx-dx*vz, hz = dx*vy-dy*vx; // cross(r_direction, v)
+			const float qx = wy*uz-wz*uy, qy = wz*ux-wx*uz, qz = wx*uy-wy*ux; // cross(w, u)
+			const float g = ux*hx+uy*hy+uz*hz, f = 1.0f/g, s = f*(wx*hx+wy*hy+wz*hz), t = f*(dx*qx+dy*qy+dz*qz), d = f*(vx*qx+vy*qy+vz*qz);
+			if(g!=0.0f&&s>=0.0f&&s<1.0f&&t>=0.0f&&s+t<1.0f) {
+				if(d>0.0f) { if(intersections<64u&&d<65536.0f) distances[intersections] = (uint16_t)d; intersections++; }
+				else intersections_check++;
+			}
+		}
+	}
+	if(!active) return;
+	const uint32_t nsort = intersections<64u ? intersections : 64u;
+	for(uint32_t i=1u; i<nsort; i++) { const uint16_t t = distances[i]; int j = (int)i-1; while(j>=0&&distances[j]>t) { distances[j+1] = distances[j]; j--; } distances[j+1] = t; }
+	bool inside = (intersections%2u)&&(intersections_check%2u);
+	uint32_t intersection = intersections%2u!=intersections_check%2u;
+	const uint32_t h0 = direction==0u ? X : direction==1u ? Y : Z;
+	const uint32_t hmax = direction==0u ? (uint32_t)clampi((int)bb.x1-c.Ox, 0, Nx) : direction==1u ? (uint32_t)clampi((int)bb.y1-c.Oy, 0, Ny) : (uint32_t)clampi((int)bb.z1-c.Oz, 0, Nz);
+	const uint32_t hmesh = h0+(uint32_t)(intersections>0u ? distances[intersections-1u<63u ? intersections-1u : 63u] : 0u);
+	for(uint32_t h=h0; h<hmax; h++) {
+		while(intersection<intersections&&h>h0+(uint32_t)distances[intersection<63u ? intersection : 63u]) { inside = !inside; intersection++; }
+		inside = inside&&(intersection<intersections&&h<hmesh);
+		const uint64_t n = (uint64_t)(direction==0u ? h : X)+((uint64_t)(direction==1u ? h : Y)+(uint64_t)(direction==2u ? h : Z)*c.Ny)*c.Px;
+		uint8_t fl = c.flags[n];
+		if(inside) fl = (uint8_t)((fl&~TYPE_BO)|flag);
+		else if((fl&TYPE_BO)==TYPE_S) { // previously solid, outside now: released if it carries the geometry's velocity (0 for resting geometry)
+			if(c.u[n]==0.0f&&c.u[c.N+n]==0.0f&&c.u[2ull*c.N+n]==0.0f) fl = (uint8_t)(fl&~flag);
+		}
+		c.flags[n] = fl;
+	}
+}
+
 // FAST variant: cos(phase + phi) = cos(phase) cos(phi) - sin(phase) sin(phi). The per-mode products A*cos(phi), A*sin(phi) come from a table built once on
 // the host (luw_vk_inlet_create); per point and mode ONE range-reduced hardware sine / cosine pair replaces three library cosines.
 // cs[6*V]: Ax cos(phix), Ax sin(phix), Ay cos(phiy), Ay sin(phiy), Az cos(phiz), Az sin(phiz). Absolute error per term ~1e-6 |A|. One difference in kind: the

@@ -18,6 +18,7 @@ struct KernelSet { // one per arithmetic mode; every function enqueues exactly o
 	// TMA-tiled stream_collide (lbm_tile.cuh): box shape of tile variant `variant` for this precision / feature set, false if there is none
 	bool (*tile_shape)(int precision, uint32_t features, int variant, TileShape* shape);
 	cudaError_t (*stream_collide_tile)(const DomainConst& c, const StepArgs& a, const TileMaps& maps, int variant, int sm_count, cudaStream_t s);
+	cudaError_t (*voxelize)(const DomainConst& c, uint32_t direction, uint8_t flag, uint32_t ntri, const float* box6, const float* p0, const float* p1, const float* p2, cudaStream_t s); // p0..p2: device
 };
 const KernelSet& kernels_strict(); // lbm_strict.cu: -fmad=false
 const KernelSet& kernels_fast(); // lbm_fast.cu: contraction allowed

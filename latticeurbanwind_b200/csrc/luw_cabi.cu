@@ -706,6 +706,23 @@ int luw_vk_inlet_destroy(luw_vk_inlet* v) {
 	return LUW_OK;
 }
 
+int luw_voxelize_mesh(luw_domain* d, uint32_t direction, uint8_t flag, const float* p0, const float* p1, const float* p2, uint32_t ntri, const float* bbu) {
+	if(!d||!bbu||(ntri>0u&&(!p0||!p1||!p2))||direction>2u) return fail(LUW_ERR_INVALID, "bad argument");
+	for(int k=10; k<16; k++) if(bbu[k]!=0.0f) return fail(LUW_ERR_INVALID, "moving geometry (non-zero linear / rotational velocity) is not supported: LUW voxelises resting meshes only");
+	if(ntri==0u) return LUW_OK; // run_voxelize_pass returns early, FX/lbm.cpp:505
+	DeviceGuard guard(d->p.device);
+	float* tri = nullptr;
+	CU(cudaMalloc((void**)&tri, 9ull*ntri*sizeof(float))); // Memory<float3> p0, p1, p2 of FX/lbm.cpp:525-527: live for this call only
+	cudaError_t e = cudaMemcpyAsync(tri, p0, 3ull*ntri*4ull, cudaMemcpyHostToDevice, d->stream);
+	if(e==cudaSuccess) e = cudaMemcpyAsync(tri+3ull*ntri, p1, 3ull*ntri*4ull, cudaMemcpyHostToDevice, d->stream);
+	if(e==cudaSuccess) e = cudaMemcpyAsync(tri+6ull*ntri, p2, 3ull*ntri*4ull, cudaMemcpyHostToDevice, d->stream);
+	if(e==cudaSuccess) e = luw::kernels_strict().voxelize(d->c, direction, flag, ntri, bbu+1, tri, tri+3ull*ntri, tri+6ull*ntri, d->stream); // always the as-written arithmetic: flags are bit-exact
+	if(e==cudaSuccess) { d->launches++; e = cudaStreamSynchronize(d->stream); } // kernel.run() is synchronous in the reference, and the triangle buffers are released below
+	cudaFree(tri);
+	if(e!=cudaSuccess) return cuda_fail(e, "voxelize_mesh");
+	return LUW_OK;
+}
+
 int luw_cellset_create(luw_domain* d, uint64_t count, const uint64_t* host_cell_index, luw_cellset** out) {
 	if(!d||!out||(count>0ull&&!host_cell_index)) return fail(LUW_ERR_INVALID, "null argument");
 	*out = nullptr;

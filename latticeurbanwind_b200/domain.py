@@ -131,6 +131,11 @@ class Domain:
     def halo_insert(self, payload, axis, buf_p, buf_m):
         A.check(A.lib().luw_halo_insert(self._h, payload, axis, self.t, C.c_void_p(buf_p), C.c_void_p(buf_m)))
 
+    def voxelize_mesh(self, direction, flag, p0, p1, p2, bbu):
+        """LBM_Domain::voxelize_mesh_on_device -> run_voxelize_pass (FX/lbm.cpp:494-560) on the device flags / u; p0/p1/p2: 3 floats per triangle."""
+        p0, p1, p2, bbu = (np.ascontiguousarray(a, np.float32) for a in (p0, p1, p2, bbu))
+        A.check(A.lib().luw_voxelize_mesh(self._h, direction, flag, _ptr(p0), _ptr(p1), _ptr(p2), p0.size // 3, _ptr(bbu)))
+
     # ---- peer-mapped halo exchange of the one-process-per-GPU driver (CUDA IPC over NVLink)
     def halo_ipc_export(self, axis):
         h = C.create_string_buffer(64)

@@ -493,3 +493,62 @@ void luwo_stats_accumulate(uint64_t N, uint64_t count, const float* rho, const f
 		rho_avg[n] += (rho[n]-rho_avg[n])*inv_n;
 	}
 }
+
+/* FX/kernel.cpp:2381-2471. Vector helpers written out in the reference's operation order (cross: a.y*b.z-a.z*b.y, ...; dot: left to right). */
+static int clampi(int x, int lo, int hi) { return x<lo ? lo : (x>hi ? hi : x); }
+void luwo_voxelize_mesh(const luwo_params* p, uint32_t direction, const float* u, uint8_t* flags, uint8_t flag, const float* p0, const float* p1, const float* p2, const float* bbu) {
+	const uint32_t Nx = p->Nx, Ny = p->Ny, Nz = p->Nz;
+	const uint64_t N = (uint64_t)Nx*Ny*Nz;
+	const int Ox = p->Ox, Oy = p->Oy, Oz = p->Oz;
+	const uint32_t A = direction==0u ? Ny*Nz : direction==1u ? Nz*Nx : Nx*Ny;
+	uint32_t triangle_number; memcpy(&triangle_number, bbu, 4);
+	const float x0 = bbu[1], y0 = bbu[2], z0 = bbu[3], x1 = bbu[4], y1 = bbu[5], z1 = bbu[6];
+	const float offx = 0.5f*(float)((int)Nx+2*Ox)-0.5f, offy = 0.5f*(float)((int)Ny+2*Oy)-0.5f, offz = 0.5f*(float)((int)Nz+2*Oz)-0.5f;
+	const float dx = (float)(direction==0u), dy = (float)(direction==1u), dz = (float)(direction==2u);
+	int64_t ai;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(luwo_get_threads())
+	for(ai=0; ai<(int64_t)A; ai++) {
+		const uint32_t a = (uint32_t)ai;
+		uint32_t X, Y, Z;
+		if(direction==0u) { X = (uint32_t)clampi((int)x0-Ox, 0, (int)Nx-1); Y = a%Ny; Z = a/Ny; }
+		else if(direction==1u) { X = a/Nz; Y = (uint32_t)clampi((int)y0-Oy, 0, (int)Ny-1); Z = a%Nz; }
+		else { X = a%Nx; Y = a/Nx; Z = (uint32_t)clampi((int)z0-Oz, 0, (int)Nz-1); }
+		const float rox = ((float)X+0.5f-0.5f*(float)Nx)+offx, roy = ((float)Y+0.5f-0.5f*(float)Ny)+offy, roz = ((float)Z+0.5f-0.5f*(float)Nz)+offz;
+		const int out_of_box = direction==0u ? (roy<y0||roz<z0||roy>=y1||roz>=z1) : direction==1u ? (rox<x0||roz<z0||rox>=x1||roz>=z1) : (rox<x0||roy<y0||rox>=x1||roy>=y1);
+		if(out_of_box) continue;
+		uint32_t intersections = 0u, intersections_check = 0u;
+		uint16_t distances[64];
+		for(uint32_t i=0u; i<triangle_number; i++) {
+			const float ax = p0[3u*i], ay = p0[3u*i+1u], az = p0[3u*i+2u];
+			const float ux_ = p1[3u*i]-ax, uy_ = p1[3u*i+1u]-ay, uz_ = p1[3u*i+2u]-az;
+			const float vx = p2[3u*i]-ax, vy = p2[3u*i+1u]-ay, vz = p2[3u*i+2u]-az;
+			const float wx = rox-ax, wy = roy-ay, wz = roz-az;
+			const float hx = dy*vz-dz*vy, hy = dz*vx-dx*vz, hz = dx*vy-dy*vx; /* cross(r_direction, v) */
+			const float qx = wy*uz_-wz*uy_, qy = wz*ux_-wx*uz_, qz = wx*uy_-wy*ux_; /* cross(w, u) */
+			const float g = ux_*hx+uy_*hy+uz_*hz, f = 1.0f/g, s = f*(wx*hx+wy*hy+wz*hz), t = f*(dx*qx+dy*qy+dz*qz), d = f*(vx*qx+vy*qy+vz*qz);
+			if(g!=0.0f&&s>=0.0f&&s<1.0f&&t>=0.0f&&s+t<1.0f) {
+				if(d>0.0f) { if(intersections<64u&&d<65536.0f) distances[intersections] = (uint16_t)d; intersections++; }
+				else intersections_check++;
+			}
+		}
+		const uint32_t nsort = intersections<64u ? intersections : 64u;
+		for(uint32_t i=1u; i<nsort; i++) { const uint16_t t = distances[i]; int j = (int)i-1; while(j>=0&&distances[j]>t) { distances[j+1] = distances[j]; j--; } distances[j+1] = t; }
+		int inside = (intersections%2u)&&(intersections_check%2u);
+		uint32_t intersection = intersections%2u!=intersections_check%2u;
+		const uint32_t h0 = direction==0u ? X : direction==1u ? Y : Z;
+		const uint32_t hmax = direction==0u ? (uint32_t)clampi((int)x1-Ox, 0, (int)Nx) : direction==1u ? (uint32_t)clampi((int)y1-Oy, 0, (int)Ny) : (uint32_t)clampi((int)z1-Oz, 0, (int)Nz);
+		const uint32_t last = intersections-1u<63u ? intersections-1u : 63u; /* min(intersections-1u, 63u) with unsigned wrap for 0 */
+		const uint32_t hmesh = h0+(uint32_t)(intersections>0u ? distances[last] : 0u); /* intersections == 0: the reference reads an uninitialised slot, but `inside` is false then and stays false */
+		for(uint32_t h=h0; h<hmax; h++) {
+			while(intersection<intersections&&h>h0+(uint32_t)distances[intersection<63u ? intersection : 63u]) { inside = !inside; intersection++; }
+			inside = inside&&(intersection<intersections&&h<hmesh);
+			const uint64_t n = (uint64_t)(direction==0u ? h : X)+((uint64_t)(direction==1u ? h : Y)+(uint64_t)(direction==2u ? h : Z)*Ny)*Nx;
+			uint8_t fl = flags[n];
+			if(inside) fl = (uint8_t)((fl&~TYPE_BO)|flag);
+			else if((fl&TYPE_BO)==TYPE_S) {
+				if(u[n]==0.0f&&u[N+n]==0.0f&&u[2u*N+n]==0.0f) fl = (fl&TYPE_BO)==TYPE_BO ? (uint8_t)(fl&~TYPE_BO) : (uint8_t)(fl&~flag); /* u_set == 0 for resting geometry; TYPE_MS == TYPE_BO == 0x03 */
+			}
+			flags[n] = fl;
+		}
+	}
+}

@@ -62,6 +62,11 @@ void luwo_transfer_insert_rho_u_flags(const luwo_params* p, uint32_t direction, 
 void luwo_vk_inlet_apply(uint64_t N_cells, uint32_t use_interp, float t0, float t1, float alpha, uint64_t point_count, uint64_t mode_count, uint64_t mode_stride,
 	const uint64_t* point_cell, const uint8_t* point_face, const float* point_data, const float* mode_data, float* u);
 
+/* kernel voxelize_mesh, FX/kernel.cpp:2381-2471, for resting geometry (bbu[10..15] == 0, the only way LUW calls it: FX/setup.cpp passes no velocities):
+ * one ray per column of the face normal to `direction`, Moeller-Trumbore against all triangles, up to 64 sorted crossings, inside/outside walk along the
+ * column with the reference's error corrections. p0/p1/p2: 3 floats per triangle; bbu[16] as packed by LBM_Domain::voxelize_mesh_on_device (FX/lbm.cpp:529-549). */
+void luwo_voxelize_mesh(const luwo_params* p, uint32_t direction, const float* u, uint8_t* flags, uint8_t flag, const float* p0, const float* p1, const float* p2, const float* bbu);
+
 /* running mean / M2 of the sampled fields: the host loop `accumulate_from_buffers` of the case driver, FX/setup.cpp:4441-4488 (Welford update per cell,
  * u_avg interleaved [3n+c], products and sums rounded separately as the reference's g++ build does). `count` is the sample number AFTER the increment. */
 void luwo_stats_accumulate(uint64_t N, uint64_t count, const float* rho, const float* u, float* u_avg, float* rho_avg, float* m2_u, float* m2_v, float* m2_w);

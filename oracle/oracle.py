@@ -143,6 +143,10 @@ class Oracle:
     def insert_rho_u_flags(self, direction, bp, bm, rho, u, flags):
         self.lib.luwo_transfer_insert_rho_u_flags(C.byref(self.p), direction, _p(bp), _p(bm), _p(rho), _p(u), _p(flags))
 
+    def voxelize_mesh(self, direction, u, flags, flag, p0, p1, p2, bbu):
+        self.lib.luwo_voxelize_mesh.restype = None
+        self.lib.luwo_voxelize_mesh(C.byref(self.p), C.c_uint32(direction), _p(u), _p(flags), C.c_uint8(flag), _p(p0), _p(p1), _p(p2), _p(bbu))
+
     def vk_inlet_apply(self, use_interp, t0, t1, alpha, point_cell, point_face, point_data, mode_data, mode_count, mode_stride, u):
         P = point_cell.shape[0]
         self.lib.luwo_vk_inlet_apply(self.p.N, int(use_interp), float(t0), float(t1), float(alpha), P, int(mode_count), int(mode_stride),
@@ -212,6 +216,7 @@ class Reference:
         L.luwref_half_to_float_custom.restype = C.c_float; L.luwref_half_to_float_custom.argtypes = [C.c_uint16]
         L.luwref_float_to_half_custom.restype = C.c_uint16; L.luwref_float_to_half_custom.argtypes = [C.c_float]
         L.luwref_calculate_f_eq.argtypes = [C.c_float] * 4 + [C.c_void_p]
+        L.luwref_voxelize_mesh.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint8] + [C.c_void_p] * 4
 
     def bind(self, params):
         assert params.precision == self.precision and params.features == FEATURE_SETS[self.feature_set]
@@ -251,6 +256,10 @@ class Reference:
 
     def insert_rho_u_flags(self, direction, bp, bm, rho, u, flags):
         self.lib.luwref_transfer_insert_rho_u_flags(direction, 0, _p(bp), _p(bm), _p(rho), _p(u), _p(flags))
+
+    def voxelize_mesh(self, direction, u, flags, flag, p0, p1, p2, bbu, t=1):
+        fi = np.zeros(19 * self.p.N, ddf_dtype(self.precision))  # only touched for moving geometry
+        self.lib.luwref_voxelize_mesh(direction, _p(fi), _p(u), _p(flags), int(t), int(flag), _p(p0), _p(p1), _p(p2), _p(bbu))
 
     def vk_inlet_apply(self, use_interp, t0, t1, alpha, point_cell, point_face, point_data, mode_data, mode_count, mode_stride, u):
         P = point_cell.shape[0]

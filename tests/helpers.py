@@ -199,3 +199,44 @@ def stats_run(engine):
     for rho, u in stats_samples():
         engine.accumulate(rho, u, u_avg, rho_avg, *m2)
     return u_avg, rho_avg, m2[0], m2[1], m2[2]
+
+
+# ---------------------------------------------------------------------------------------------- mesh voxelisation (FX/kernel.cpp:2381-2471)
+VOX_SHAPE = (40, 36, 28)
+
+
+def _box_tris(lo, hi):
+    x0, y0, z0 = lo; x1, y1, z1 = hi
+    v = np.array([[x0, y0, z0], [x1, y0, z0], [x1, y1, z0], [x0, y1, z0], [x0, y0, z1], [x1, y0, z1], [x1, y1, z1], [x0, y1, z1]], np.float32)
+    quads = [(0, 3, 2, 1), (4, 5, 6, 7), (0, 1, 5, 4), (2, 3, 7, 6), (1, 2, 6, 5), (0, 4, 7, 3)]
+    tris = []
+    for a, b, c, d in quads:
+        tris += [(v[a], v[b], v[c]), (v[a], v[c], v[d])]
+    return tris
+
+
+def vox_mesh(seed=3):
+    """A small 'city' like luwvox produces: a base slab, extruded boxes at fractional positions, one tilted tetrahedron (rays graze its edges), in lattice
+    coordinates of a VOX_SHAPE domain (mesh already translated like FX/setup.cpp:4084-4087). Returns p0, p1, p2 (3 floats per triangle) and pmin, pmax."""
+    rng = np.random.default_rng(seed)
+    Nx, Ny, Nz = VOX_SHAPE
+    tris = _box_tris((1.0, 1.0, 1.0), (Nx - 1.0, Ny - 1.0, 2.3))
+    for _ in range(7):
+        cx, cy = rng.uniform(6, Nx - 6), rng.uniform(6, Ny - 6)
+        w, d, h = rng.uniform(2.2, 6.5), rng.uniform(2.2, 6.5), rng.uniform(4.0, Nz - 6.0)
+        tris += _box_tris((cx - w / 2, cy - d / 2, 1.7), (cx + w / 2, cy + d / 2, 1.7 + h))
+    t = np.array([[20.2, 8.1, 2.0], [27.9, 9.3, 2.0], [23.5, 15.7, 2.0], [24.1, 11.2, 17.4]], np.float32)
+    for a, b, c in [(0, 2, 1), (0, 1, 3), (1, 2, 3), (2, 0, 3)]:
+        tris.append((t[a], t[b], t[c]))
+    P = np.array(tris, np.float32)  # [T, 3 vertices, 3]
+    p0, p1, p2 = (np.ascontiguousarray(P[:, k, :]).reshape(-1) for k in range(3))
+    return p0, p1, p2, P.reshape(-1, 3).min(0), P.reshape(-1, 3).max(0)
+
+
+def vox_bbu(ntri, pmin, pmax):
+    """bounding_box_and_velocity[16] of LBM_Domain::voxelize_mesh_on_device (FX/lbm.cpp:497,529-549): triangle count as float bits, bbox -+ 2 cells, resting geometry."""
+    bbu = np.zeros(16, np.float32)
+    bbu[:1].view(np.uint32)[0] = ntri
+    bbu[1:4] = pmin - np.float32(2.0)
+    bbu[4:7] = pmax + np.float32(2.0)
+    return bbu
