@@ -135,17 +135,16 @@ __device__ __forceinline__ void face_xyz(const DomainConst& c, const uint32_t d,
 }
 __device__ __forceinline__ uint32_t axis_len(const DomainConst& c, const uint32_t d) { return d==0u ? c.Nx : d==1u ? c.Ny : c.Nz; }
 
-// one thread per (face cell, side); raw fpxx copies, no conversion
-template<typename T, bool INSERT> __global__ void __launch_bounds__(128) k_halo_fi(const __grid_constant__ DomainConst c, const uint32_t d, const uint32_t A, const uint32_t odd, const bool xfast, T* __restrict__ buf_p, T* __restrict__ buf_m) {
-	const uint32_t t = blockIdx.x*blockDim.x+threadIdx.x, side = blockIdx.y;
-	if(t>=A) return;
+// raw fpxx copies, no conversion. Faces normal to y / z: one thread per (face cell, side), blockIdx.y = side. Faces normal to x: one thread per face cell does
+// BOTH sides -- the two face cells of a row (x = 1 / Nx-2, or 0 / Nx-1) lie in the same 1 KB lattice row of every slot, and touching them back to back lets
+// the second access find the DRAM page the first one opened (every x-face element is a 2-byte access in its own row otherwise).
+template<typename T, bool INSERT> __device__ __forceinline__ void halo_fi_cell(const DomainConst& c, const uint32_t d, const uint32_t A, const uint32_t odd, const bool xfast, const uint32_t t, const uint32_t side, T* __restrict__ buf) {
 	const uint32_t L = axis_len(c, d);
 	uint32_t x, y, z, a;
 	face_xyz(c, d, t, INSERT ? (side==0u ? L-1u : 0u) : (side==0u ? L-2u : 1u), xfast, x, y, z, a);
 	uint64_t j[Q];
 	neighbors(c, x, y, z, j);
 	T* fi = (T*)c.fi;
-	T* buf = side==0u ? buf_p : buf_m;
 #pragma unroll
 	for(uint32_t b=0u; b<5u; b++) {
 		const uint32_t i = XFER[2u*d+side][b];
@@ -160,18 +159,27 @@ template<typename T, bool INSERT> __global__ void __launch_bounds__(128) k_halo_
 		}
 	}
 }
-template<bool INSERT> __global__ void __launch_bounds__(128) k_halo_rho_u_flags(const __grid_constant__ DomainConst c, const uint32_t d, const uint32_t A, const bool xfast, char* __restrict__ buf_p, char* __restrict__ buf_m) {
-	const uint32_t t = blockIdx.x*blockDim.x+threadIdx.x, side = blockIdx.y;
+template<typename T, bool INSERT> __global__ void __launch_bounds__(128) k_halo_fi(const __grid_constant__ DomainConst c, const uint32_t d, const uint32_t A, const uint32_t odd, const bool xfast, T* __restrict__ buf_p, T* __restrict__ buf_m) {
+	const uint32_t t = blockIdx.x*blockDim.x+threadIdx.x;
 	if(t>=A) return;
+	if(gridDim.y==1u) { halo_fi_cell<T, INSERT>(c, d, A, odd, xfast, t, 0u, buf_p); halo_fi_cell<T, INSERT>(c, d, A, odd, xfast, t, 1u, buf_m); }
+	else halo_fi_cell<T, INSERT>(c, d, A, odd, xfast, t, blockIdx.y, blockIdx.y==0u ? buf_p : buf_m);
+}
+template<bool INSERT> __device__ __forceinline__ void halo_ruf_cell(const DomainConst& c, const uint32_t d, const uint32_t A, const bool xfast, const uint32_t t, const uint32_t side, char* __restrict__ buf) {
 	const uint32_t L = axis_len(c, d);
 	uint32_t x, y, z, a;
 	face_xyz(c, d, t, INSERT ? (side==0u ? L-1u : 0u) : (side==0u ? L-2u : 1u), xfast, x, y, z, a);
 	const uint64_t n = x+((uint64_t)y+(uint64_t)z*c.Ny)*c.Px;
-	char* buf = side==0u ? buf_p : buf_m;
 	float* bf = (float*)buf;
 	uint8_t* bb = (uint8_t*)buf+16ull*A;
 	if(INSERT) { c.rho[n] = bf[a]; c.u[n] = bf[(uint64_t)A+a]; c.u[c.N+n] = bf[2ull*A+a]; c.u[2ull*c.N+n] = bf[3ull*A+a]; c.flags[n] = bb[a]; }
 	else { bf[a] = c.rho[n]; bf[(uint64_t)A+a] = c.u[n]; bf[2ull*A+a] = c.u[c.N+n]; bf[3ull*A+a] = c.u[2ull*c.N+n]; bb[a] = c.flags[n]; }
+}
+template<bool INSERT> __global__ void __launch_bounds__(128) k_halo_rho_u_flags(const __grid_constant__ DomainConst c, const uint32_t d, const uint32_t A, const bool xfast, char* __restrict__ buf_p, char* __restrict__ buf_m) {
+	const uint32_t t = blockIdx.x*blockDim.x+threadIdx.x;
+	if(t>=A) return;
+	if(gridDim.y==1u) { halo_ruf_cell<INSERT>(c, d, A, xfast, t, 0u, buf_p); halo_ruf_cell<INSERT>(c, d, A, xfast, t, 1u, buf_m); }
+	else halo_ruf_cell<INSERT>(c, d, A, xfast, t, blockIdx.y, blockIdx.y==0u ? buf_p : buf_m);
 }
 
 // ------------------------------------------------------------------ kernel: vk_inlet_apply (FX/kernel.cpp:2495-2571)

@@ -286,3 +286,20 @@ def test_cell_sets_move_boundary_data_without_whole_fields():
         d.read_from_device(A.FIELD_U); d.finish_queue()
         assert np.array_equal(d.u, want)
         cs.close()
+
+
+def test_c1_sized_case_equals_oracle(oracle_lib):
+    """BASELINE configs[0] scale (256 x 256 x 128 = 8.4 M cells, FP32, SRT + Smagorinsky, equilibrium inflow on five faces, bounce-back cubes, Coriolis,
+    nudging, sponge -- the profile case's physics on the synthetic block array): 10 steps, STRICT arithmetic, every rho / u value equal to the oracle's."""
+    O = oracle_lib
+    shape = (256, 256, 128)
+    flags, rho, u = cases.block_case("urban", shape)
+    w = cases.relaxation_rate(1e-6)
+    feat = H.FEATURE_SETS["luw"]
+    zones = dict(downstream_face=2, buffer_N=16, buffer_inv_tau=0.01, buffer_nudge_vertical=1, sponge_N=20, sponge_inv_tau=0.02)
+    ref = H.run_cpu(O.Oracle(), O, shape, 0, feat, flags, rho, u, 10, w, zones=zones)
+    got = H.run_cuda(shape, 0, feat, flags, rho, u, 10, w, arith=0, zones=zones, batched=True, expect_tiles=True)
+    assert np.array_equal(got[1], ref[1]), "rho differs"
+    assert np.array_equal(got[2], ref[2]), "u differs"
+    fast = H.run_cuda(shape, 0, feat, flags, rho, u, 10, w, arith=1, zones=zones, batched=True, expect_tiles=True)
+    assert H.rel_l2(fast[2], ref[2]) <= 1e-5 and float(np.abs(fast[2] - ref[2]).max()) <= 2e-6  # SURVEY 8c: FP32 rel-L2(u) <= 1e-5, max-abs(u) <= 2e-6
