@@ -132,7 +132,7 @@ template<int P_, int TX_, int TY_, int TZ_, int STAGES_, int CTAS_, bool TWOPASS
 	static constexpr int FLAG_OFF = Q*BOX_BYTES+5*PAD;
 	static constexpr int STAGE_BYTES = FLAG_OFF+TILE; // 19 DDF boxes + 5 pads + the flag box
 	static constexpr int LOAD_BYTES = Q*BOX_BYTES+TILE; // what one stage's TMA loads deliver
-	static constexpr int SMEM_BYTES = STAGES*STAGE_BYTES+(2*STAGES+1)*8+STAGES*4+4+128; // + mbarriers, + the strip id of every stage, + slack for 128 B alignment of the first stage
+	static constexpr int SMEM_BYTES = STAGES*STAGE_BYTES+(2*STAGES+1)*8+STAGES*12+4+128; // + mbarriers, + the strip id of every stage, + slack for 128 B alignment of the first stage
 	__host__ __device__ static constexpr int box_off(const int b) {
 		return b==0 ? 0 : (b&1) ? (1+(b-1)/2)*BOX_BYTES : (10+(b-2)/2)*BOX_BYTES+PAD*pads_before_pair((b-2)/2);
 	}
@@ -320,12 +320,13 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 	uint64_t* const bar_done = bar_full+S;
 	uint64_t* const bar_head = bar_done+S;
 	volatile uint32_t* const tile_strip = (volatile uint32_t*)(bar_head+1); // strip id of the tile in each stage
+	volatile int* const tile_yz = (volatile int*)(tile_strip+S); // its y0, z0 (producer only: saves the store side two integer divisions per tile)
 
 	const uint32_t tid = threadIdx.x;
 	TRACE_CLK(0);
 	if(tid==0u) {
 		if(blockIdx.x==0u) c.sched[(uint32_t)(a.t&1ull)^1u] = 0u; // strip counter of the NEXT step (steps alternate between two counters, so no memset node sits between launches)
-		for(int s=0; s<S; s++) { mbar_init(bar_full+s, 1u); mbar_init(bar_done+s, (uint32_t)NC); }
+		for(int s=0; s<S; s++) { mbar_init(bar_full+s, 1u); mbar_init(bar_done+s, (uint32_t)(NC/32)); } // done: one arrival per consumer WARP
 		mbar_init(bar_head, 1u);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
@@ -359,6 +360,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 			uint8_t* st = stage0+(size_t)s*CFG::STAGE_BYTES;
 			if(leader) {
 				tile_strip[s] = lstrip; // published by the barrier's release / acquire
+				tile_yz[2*s] = y0; tile_yz[2*s+1] = z0;
 				mbar_expect_tx(bar_full+s, (uint32_t)CFG::LOAD_BYTES);
 				tma_load_3d(st+CFG::FLAG_OFF, &maps.flags, bar_full+s, x0, y0, z0);
 				tma_load_4d(st, &maps.fi, bar_full+s, x0, y0, z0, 0);
@@ -383,8 +385,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 			bar_sync_id(2u+(uint32_t)s, (uint32_t)CFG::THREADS); // all consumers have arrived: stage s is collided and fenced for the async proxy
 #endif
 			if(leader) TRACE(0, q);
-			const uint32_t sstrip = tile_strip[s];
-			const int x0 = (int)sxt*TX, y0 = (int)(sstrip%tiles_y)*TY, z0 = (int)(sstrip/tiles_y)*TZ;
+			const int x0 = (int)sxt*TX, y0 = tile_yz[2*s], z0 = tile_yz[2*s+1];
 			const uint8_t* st = stage0+(size_t)s*CFG::STAGE_BYTES;
 			const bool inner = y0>0&&z0>0&&y0+TY<=(int)c.Ny&&z0+TZ<=(int)c.Nz; // every box lies inside the lattice: all 19 go through TMA
 			const bool last_of_strip = sxt+1u==tiles_x;
@@ -620,7 +621,11 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 		fence_async_smem(); // make this thread's shared-memory writes visible to the TMA store
 		if(tid==0u) TRACE(5, q);
 #ifndef LUW_PRODUCER_NAMED_BARRIER
-		mbar_arrive(bar_done+s);
+		// One arrival per warp: every lane has fenced its own shared-memory writes for the async proxy, __syncwarp orders them before lane 0's releasing arrive.
+		// (With one arrival per THREAD the producer's try_wait woke up ~94 times per tile -- once per arrival it could see -- and its polling was 15 % of all
+		// issued instructions on the channel case, profiles/r1c_ncu_channel512_fp16s.md.)
+		__syncwarp();
+		if((tid&31u)==0u) mbar_arrive(bar_done+s);
 #else
 		bar_arrive_id(2u+s, (uint32_t)CFG::THREADS);
 #endif
