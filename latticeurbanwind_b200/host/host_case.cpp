@@ -38,11 +38,22 @@ int main(int argc, char** argv) {
 		lbm.u.x[n] = u[n]; lbm.u.y[n] = u[N+n]; lbm.u.z[n] = u[2ull*N+n];
 	}
 	lbm.run(0ull); // initialise only (FX/setup.cpp:4852)
-	lbm.run(steps);
+	const ulong samples = getenv("LUW_CASE_STATS") ? (ulong)atoll(getenv("LUW_CASE_STATS")) : 0ull; // averaging window over the last `samples` steps (FX/setup.cpp:4510-4542)
+	LBM_Statistics* stats = samples>0ull ? new LBM_Statistics(lbm) : nullptr;
+	lbm.run(steps-(samples<steps ? samples : steps));
+	for(ulong k=0ull; k<(samples<steps ? samples : steps); k++) { lbm.run(1ull); stats->accumulate(); }
 	lbm.rho.read_from_device(); lbm.u.read_from_device();
 	for(ulong n=0ull; n<N; n++) { rho[n] = lbm.rho[n]; u[n] = lbm.u.x[n]; u[N+n] = lbm.u.y[n]; u[2ull*N+n] = lbm.u.z[n]; }
 	std::ofstream out(out_path, std::ios::binary);
 	out.write((const char*)rho.data(), (std::streamsize)(4ull*N)); out.write((const char*)u.data(), (std::streamsize)(12ull*N));
+	if(samples>0ull) { // avg_u[3N] interleaved, avg_rho[N], M2_u[N], M2_v[N], M2_w[N]
+		std::vector<float> avg_u, avg_rho, M2_u, M2_v, M2_w;
+		const ulong count = stats->download(avg_u, avg_rho, M2_u, M2_v, M2_w);
+		if(count!=(samples<steps ? samples : steps)) print_error("statistics sample count is off");
+		out.write((const char*)avg_u.data(), (std::streamsize)(12ull*N)); out.write((const char*)avg_rho.data(), (std::streamsize)(4ull*N));
+		out.write((const char*)M2_u.data(), (std::streamsize)(4ull*N)); out.write((const char*)M2_v.data(), (std::streamsize)(4ull*N)); out.write((const char*)M2_w.data(), (std::streamsize)(4ull*N));
+	}
+	delete stats;
 	printf("luw_host_case: %llu cells, %u domain(s), %llu steps, t = %llu\n", (unsigned long long)N, lbm.get_D(), (unsigned long long)steps, (unsigned long long)lbm.get_t());
 	return 0;
 }

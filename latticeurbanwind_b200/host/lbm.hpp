@@ -269,3 +269,45 @@ private:
 	std::vector<Memory<float>*> rho_buffers, u_buffers;
 	std::vector<Memory<uchar>*> flags_buffers;
 };
+
+// ---------------------------------------------------------------------------------------------------------------- running statistics (FX/setup.cpp:4441-4488)
+// The averaging window of the case driver without its per-sample read-back: accumulate() updates mean / M2 of u and the mean of rho of every domain on the
+// device (luw_stats_accumulate), download() returns them once, stitched over the global lattice in the reference's layout
+// (avg_u interleaved [3n+c], avg_rho[n], M2_u / M2_v / M2_w[n]; FX/setup.cpp:4252-4266), ready for write_avg_vtk.
+class LBM_Statistics {
+private:
+	LBM* lbm = nullptr;
+	std::vector<luw_stats*> st;
+public:
+	explicit LBM_Statistics(LBM& lbm_) : lbm(&lbm_) {
+		for(uint d=0u; d<lbm->get_D(); d++) { luw_stats* h = nullptr; luw_check(luw_stats_create(lbm->lbm_domain[d]->get_handle(), &h)); st.push_back(h); }
+	}
+	~LBM_Statistics() { for(luw_stats* h : st) luw_stats_destroy(h); }
+	LBM_Statistics(const LBM_Statistics&) = delete;
+	LBM_Statistics& operator=(const LBM_Statistics&) = delete;
+	void accumulate() { // FX/setup.cpp:4411-4425 + 4441-4488: update_fields first when rho / u are not stored every step
+		for(uint d=0u; d<lbm->get_D(); d++) lbm->lbm_domain[d]->enqueue_update_fields();
+		for(uint d=0u; d<lbm->get_D(); d++) luw_check(luw_stats_accumulate(st[d]));
+	}
+	void reset() { for(luw_stats* h : st) luw_check(luw_stats_reset(h)); } // FX/setup.cpp:4556-4562
+	ulong download(std::vector<float>& avg_u, std::vector<float>& avg_rho, std::vector<float>& M2_u, std::vector<float>& M2_v, std::vector<float>& M2_w) {
+		const ulong N = lbm->get_N();
+		avg_u.assign(3ull*N, 0.0f); avg_rho.assign(N, 0.0f); M2_u.assign(N, 0.0f); M2_v.assign(N, 0.0f); M2_w.assign(N, 0.0f);
+		const uint Dx = lbm->get_Dx(), Dy = lbm->get_Dy(), Dz = lbm->get_Dz(), Hx = Dx>1u, Hy = Dy>1u, Hz = Dz>1u;
+		uint64_t count = 0ull;
+		for(uint d=0u; d<lbm->get_D(); d++) {
+			const LBM_Domain* dom = lbm->lbm_domain[d];
+			const ulong Nl = dom->get_N();
+			std::vector<float> mu(3ull*Nl), m2(3ull*Nl), mr(Nl);
+			luw_check(luw_stats_download(st[d], mu.data(), m2.data(), mr.data(), &count));
+			for(uint z=Hz; z<dom->get_Nz()-Hz; z++) for(uint y=Hy; y<dom->get_Ny()-Hy; y++) for(uint x=Hx; x<dom->get_Nx()-Hx; x++) { // halo layers belong to the neighbours
+				const ulong l = (ulong)x+((ulong)y+(ulong)z*(ulong)dom->get_Ny())*(ulong)dom->get_Nx();
+				const ulong n = lbm->index((uint)((int)x+dom->get_Ox()), (uint)((int)y+dom->get_Oy()), (uint)((int)z+dom->get_Oz()));
+				avg_u[3ull*n] = mu[l]; avg_u[3ull*n+1ull] = mu[Nl+l]; avg_u[3ull*n+2ull] = mu[2ull*Nl+l];
+				M2_u[n] = m2[l]; M2_v[n] = m2[Nl+l]; M2_w[n] = m2[2ull*Nl+l];
+				avg_rho[n] = mr[l];
+			}
+		}
+		return (ulong)count;
+	}
+};

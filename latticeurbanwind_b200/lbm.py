@@ -300,4 +300,10 @@ class DistributedLBM(_Base):
 
     def close(self):
         if self.domain is not None:
+            self.domain.finish_queue()
+            try:  # the neighbours store into this rank's IPC-mapped receive blocks: nobody frees before everybody has drained its stream
+                self._dist.barrier(group=self.group)
+            except Exception:
+                pass
             self.domain.close()
+            self.domain = None

@@ -20,18 +20,22 @@ def build():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "latticeurbanwind_b200", "host")], stdout=subprocess.DEVNULL)
 
 
-def run_driver(tmp_path, shape, D, precision, features, arith, nu, steps, flags, rho, u, f=H.FORCE, omega=H.OMEGA, zones=ZONES, check=True):
+def run_driver(tmp_path, shape, D, precision, features, arith, nu, steps, flags, rho, u, f=H.FORCE, omega=H.OMEGA, zones=ZONES, check=True, stats=0):
     inp, out = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
     with open(inp, "wb") as fh:
         fh.write(flags.tobytes()); fh.write(rho.tobytes()); fh.write(u.tobytes())
     args = [DRIVER, *map(str, shape), *map(str, D), str(precision), str(features), str(arith), repr(float(nu)), str(steps), str(zones["downstream_face"]),
             str(zones["buffer_N"]), repr(zones["buffer_inv_tau"]), str(zones["buffer_nudge_vertical"]), str(zones["sponge_N"]), repr(zones["sponge_inv_tau"]),
             *[repr(float(v)) for v in f], *[repr(float(v)) for v in omega], inp, out]
-    r = subprocess.run(args, capture_output=True, text=True)
+    env = dict(os.environ, LUW_CASE_STATS=str(stats)) if stats else None
+    r = subprocess.run(args, capture_output=True, text=True, env=env)
     if check:
         assert r.returncode == 0, r.stderr
         N = int(np.prod(shape))
         raw = np.fromfile(out, np.float32)
+        if stats:  # rho, u, avg_u (interleaved), avg_rho, M2_u, M2_v, M2_w
+            assert raw.size == 11 * N
+            return raw[:N].copy(), raw[N:4 * N].copy(), raw[4 * N:7 * N].copy(), raw[7 * N:8 * N].copy(), raw[8 * N:9 * N].copy(), raw[9 * N:10 * N].copy(), raw[10 * N:].copy()
         return raw[:N].copy(), raw[N:].copy()
     return r
 
@@ -94,3 +98,27 @@ def test_cpp_decomposed_equals_single_domain(tmp_path, D, arith):
     one = run_driver(tmp_path, shape, (1, 1, 1), 1, feat, arith, 1e-6, 7, flags, rho, u)
     dec = run_driver(tmp_path, shape, D, 1, feat, arith, 1e-6, 7, flags, rho, u)
     assert np.array_equal(one[0], dec[0]) and np.array_equal(one[1], dec[1])
+
+
+@pytest.mark.gpu
+def test_cpp_statistics_match_the_oracle_loop(oracle_lib, tmp_path):
+    """LBM_Statistics (device-side Welford over the last 4 of 7 steps, all domains, stitched into the reference's avg_u / avg_rho / M2 layout):
+    (1) the 2x2x2 decomposition gives the same statistics as the single domain, bit for bit; (2) they equal the reference's host loop
+    (oracle restatement of FX/setup.cpp:4441-4488) applied to the per-step fields of the same STRICT run."""
+    O = oracle_lib
+    shape = (128, 24, 16)
+    N = int(np.prod(shape))
+    flags, rho, u = cases.urban(*shape, seed=21, edge=4, pitch=8)
+    feat = H.FEATURE_SETS["luw"]
+    one = run_driver(tmp_path, shape, (1, 1, 1), 1, feat, 0, 1e-6, 7, flags, rho, u, stats=4)
+    dec = run_driver(tmp_path, shape, (2, 2, 2), 1, feat, 0, 1e-6, 7, flags, rho, u, stats=4)
+    for a, b in zip(one, dec):
+        assert np.array_equal(a, b)
+    orc = O.OracleStats()
+    u_avg, rho_avg = np.zeros(3 * N, np.float32), np.zeros(N, np.float32)
+    m2 = [np.zeros(N, np.float32) for _ in range(3)]
+    for steps in (4, 5, 6, 7):  # the fields the host sees after each of the last four steps
+        ref = H.run_cpu(O.Oracle(), O, shape, 1, feat, flags, rho, u, steps, cases.relaxation_rate(1e-6), zones=ZONES)
+        orc.accumulate(ref[1], ref[2], u_avg, rho_avg, *m2)
+    assert np.array_equal(one[2], u_avg) and np.array_equal(one[3], rho_avg)
+    assert np.array_equal(one[4], m2[0]) and np.array_equal(one[5], m2[1]) and np.array_equal(one[6], m2[2])
