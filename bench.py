@@ -133,7 +133,15 @@ def cpu_run(workload, steps, warmup, budget_s=20.0):
         cores = len(os.sched_getaffinity(0))
     except Exception:
         pass
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    # all host threads, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 for its workers, which would make this arm 15x slower than it is)
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)  # the OpenMP runtime may have read the old value already
+    except OSError:
+        pass
+    if hasattr(eng, "set_threads"):
+        eng.set_threads(cores)
     Nx, Ny = min(shape[0], 512), min(shape[1], 512)
     Nz = 64 if case == "urban" else 32  # urban: keeps ground, cubes (<= 48 cells high), the nudging shell and the sponge in the sample
     Ng = (Nx, Ny, Nz)
