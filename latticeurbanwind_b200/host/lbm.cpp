@@ -3,6 +3,7 @@
 #include "lbm.hpp"
 
 LBM_Settings lbm_settings;
+static uint env_uint(const char* name, const uint fallback) { const char* v = getenv(name); return v&&*v ? (uint)strtoul(v, nullptr, 10) : fallback; }
 
 float lbm_kernel_literal(const float x) { // what `to_string(float)` + the OpenCL compiler make of a constant (FX/utilities.hpp:2741-2750): 8 decimals, round-trip through text
 	if(!std::isfinite(x)) return x;
@@ -22,7 +23,32 @@ float lbm_kernel_literal(const float x) { // what `to_string(float)` + the OpenC
 	return strtof(text, nullptr);
 }
 
-static uint env_uint(const char* name, const uint fallback) { const char* v = getenv(name); return v&&*v ? (uint)strtoul(v, nullptr, 10) : fallback; }
+#ifdef LUW_USE_REFERENCE_UTILITIES
+float3 vtk_origin_shift = float3(0.0f, 0.0f, 0.0f); // FX/lbm.cpp:18-20
+// Device memory of THIS build per domain: DDFs (19 fpxx) + rho, u (16 B) + flags (1 B) per cell of the padded local lattice, + halo buffers. The reference's
+// estimator (FX/lbm.cpp:143-232) counts its own buffer set (F, gi, T, graphics, transfer buffers): a deck with mesh_control="gpu_memory" therefore resolves to a
+// finer grid here than there for the same number of MB -- use mesh_control="cell_size" where the grid must be identical.
+uint vram_required_mb_per_device(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz) {
+	const ulong lx = (ulong)(Nx/Dx+2u*(Dx>1u)), ly = (ulong)(Ny/Dy+2u*(Dy>1u)), lz = (ulong)(Nz/Dz+2u*(Dz>1u));
+	const ulong px = (lx+15ull)&~15ull;
+	const ulong ddf = (env_uint("LUW_PRECISION", lbm_settings.precision)==LUW_FP32) ? 4ull : 2ull;
+	const ulong cells = px*ly*lz;
+	const ulong halo = 8ull*(ddf==4ull ? 20ull : 17ull)*((Dx>1u ? ly*lz : 0ull)+(Dy>1u ? lz*lx : 0ull)+(Dz>1u ? lx*ly : 0ull));
+	return (uint)((cells*(19ull*ddf+17ull)+halo)/1048576ull)+1u;
+}
+uint vram_required_mb_total(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz) { return Dx*Dy*Dz*vram_required_mb_per_device(Nx, Ny, Nz, Dx, Dy, Dz); }
+string default_filename(const string& path, const string& name, const string& extension, const ulong t) { // FX/lbm.cpp:235-239: <path or exe/export/><name>-<9-digit step><extension>
+	string time = "00000000"+to_string(t);
+	time = substring(time, length(time)-9u, 9u);
+	return (path=="" ? get_exe_path()+"export/" : path)+create_file_extension((name=="" ? "file" : name)+"-"+time, extension);
+}
+string default_filename(const string& name, const string& extension, const ulong t) { return default_filename("", name, extension, t); }
+// FX/lbm.cpp:95-142 for this build: host mirrors rho, u, flags; device the same + 19 DDFs; traffic per step = 19 loads + 19 stores + flags (+ rho, u stores with UPDATE_FIELDS)
+static uint ddf_bytes() { return env_uint("LUW_PRECISION", lbm_settings.precision)==LUW_FP32 ? 4u : 2u; }
+uint bytes_per_cell_host() { return 17u; }
+uint bytes_per_cell_device() { return 19u*ddf_bytes()+17u; }
+uint bandwidth_bytes_per_cell_device() { return 38u*ddf_bytes()+1u+((lbm_settings.features&LUW_UPDATE_FIELDS) ? 16u : 0u); }
+#endif // LUW_USE_REFERENCE_UTILITIES
 
 uint LBM_Domain::lbm_features() { return lbm_settings.features; }
 
@@ -70,7 +96,7 @@ void LBM::construct(const uint Nx_, const uint Ny_, const uint Nz_, const uint D
 		handles.push_back(lbm_domain[d]->get_handle());
 		rho_buffers.push_back(&lbm_domain[d]->rho); u_buffers.push_back(&lbm_domain[d]->u); flags_buffers.push_back(&lbm_domain[d]->flags);
 	}
-	rho.bind(this, rho_buffers.data()); u.bind(this, u_buffers.data()); flags.bind(this, flags_buffers.data());
+	rho.bind(this, rho_buffers.data(), "rho"); u.bind(this, u_buffers.data(), "u"); flags.bind(this, flags_buffers.data(), "flags");
 }
 LBM::LBM(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const float nu, const float fx, const float fy, const float fz, const float, const float, const float) { construct(Nx, Ny, Nz, Dx, Dy, Dz, nu, fx, fy, fz); }
 LBM::LBM(const uint Nx, const uint Ny, const uint Nz, const float nu, const float fx, const float fy, const float fz, const float, const float, const float) { construct(Nx, Ny, Nz, 1u, 1u, 1u, nu, fx, fy, fz); }

@@ -44,6 +44,24 @@ constexpr ulong max_ulong = 18446744073709551615ull;
 #define TYPE_Y 0x80
 #endif // LUW_USE_REFERENCE_UTILITIES
 
+#ifdef LUW_USE_REFERENCE_UTILITIES // inside the reference tree: the names FX/lbm.hpp:3-21 brings into every translation unit that includes it
+#include "defines.hpp" // TYPE_* flag bits, fpxx
+#include "units.hpp" // `units` (SI <-> lattice), used by the VTK writer
+#include "info.hpp" // `info` (console progress; FX/info.cpp reads the LBM through the getters below)
+#include <fstream>
+#include <thread>
+extern float3 vtk_origin_shift; // VTK origin shift in SI units (FX/lbm.hpp:10, set by the case driver FX/setup.cpp:4083)
+uint vram_required_mb_per_device(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz); // FX/lbm.hpp:17-18 -- for THIS build's buffers
+uint vram_required_mb_total(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz);
+string default_filename(const string& path, const string& name, const string& extension, const ulong t); // FX/lbm.cpp:235-242
+string default_filename(const string& name, const string& extension, const ulong t);
+uint bytes_per_cell_host(); // FX/lbm.hpp:13-15, for THIS build's buffers and the precision in use
+uint bytes_per_cell_device();
+uint bandwidth_bytes_per_cell_device();
+struct LBM_Device_Info { uint id = 0u; string name = ""; uint memory = 0u, memory_used = 0u; bool uses_ram = false; uint compute_units = 0u, clock_frequency = 0u; }; // the Device_Info fields FX/info.cpp:233-241 prints
+struct LBM_Device { LBM_Device_Info info; }; // what LBM_Domain::get_device() hands out (reference: the OpenCL Device, FX/opencl.hpp:274)
+#endif // LUW_USE_REFERENCE_UTILITIES
+
 // Run-time replacement of FX/defines.hpp + the constants of FX/lbm.cpp:612-783. Set the global `lbm_settings` before constructing an LBM
 // (the case driver does that where the reference's update_coriolis / update_buffer_nudging / update_top_sponge set their globals, FX/setup.cpp:3800-3903).
 struct LBM_Settings {
@@ -144,6 +162,8 @@ public:
 	void set_fx(const float v) { fx = v; } void set_fy(const float v) { fy = v; } void set_fz(const float v) { fz = v; }
 	void set_f(const float x, const float y, const float z) { fx = x; fy = y; fz = z; }
 	void set_coriolis(const float x, const float y, const float z) { omega_x = x; omega_y = y; omega_z = z; } // FX/lbm.hpp:156-160
+	float get_omega_x() const { return omega_x; } float get_omega_y() const { return omega_y; } float get_omega_z() const { return omega_z; } // FX/lbm.hpp:144-146
+	uint get_velocity_set() const { return 19u; } // D3Q19, FX/defines.hpp:7
 	// LBM_Domain::voxelize_mesh_on_device for TYPE_S geometry (FX/lbm.cpp:494-605: bounding box -+ 2 cells, rays along z unless overridden, resting mesh).
 	// p0/p1/p2: 3 floats per triangle in lattice coordinates (Mesh::p0/p1/p2 of FX/utilities.hpp are float3 arrays with exactly this memory layout).
 	// Works on the device images: upload edited host flags first; the host mirror of flags is refreshed afterwards, like the reference does (FX/lbm.cpp:562).
@@ -159,6 +179,15 @@ public:
 #endif
 	luw_domain* get_handle() const { return handle; } // reference: get_device() hands out the OpenCL Device; here the C-ABI handle
 	int get_device_ordinal() const { return device; }
+#ifdef LUW_USE_REFERENCE_UTILITIES
+	LBM_Device get_device() const { // FX/lbm.hpp:141; callers read .info only (FX/info.cpp:233-241, FX/setup.cpp:4415-4424)
+		LBM_Device dev; luw_device_info di;
+		luw_check(luw_get_device_info(device, &di));
+		dev.info.id = (uint)device; dev.info.name = di.name; dev.info.memory = (uint)(di.memory_bytes/1048576ull); dev.info.memory_used = (uint)(device_memory_used()/1048576ull);
+		dev.info.compute_units = di.compute_units; dev.info.clock_frequency = di.clock_mhz;
+		return dev;
+	}
+#endif
 	ulong device_memory_used() const { uint64_t b = 0ull; luw_domain_bytes(handle, &b); return (ulong)b; } // Device_Info::memory_used (FX/info.cpp:233-241)
 	static uint lbm_features();
 };
@@ -179,6 +208,7 @@ public:
 		ulong N = 0ull; uint d = 1u;
 		LBM* lbm = nullptr;
 		Memory<T>** buffers = nullptr;
+		std::string name = ""; // "rho" / "u" / "flags": file names and SI conversion of the VTK writer (FX/lbm.hpp:254)
 		uint Nx=1u, Ny=1u, Nz=1u, Dx=1u, Dy=1u, Dz=1u, D=1u, NxDx=1u, NyDy=1u, NzDz=1u, Hx=0u, Hy=0u, Hz=0u;
 		ulong NxNy=1ull, local_Nx=1ull, local_Ny=1ull, local_Nz=1ull, local_N=1ull;
 		T& reference(const ulong i, const uint dimension) { // FX/lbm.hpp:274-297: global index -> (domain, local index with halo offsets)
@@ -200,9 +230,9 @@ public:
 		};
 		Pointer x, y, z;
 		Memory_Container() {}
-		Memory_Container(LBM* lbm, Memory<T>** buffers) { bind(lbm, buffers); }
-		void bind(LBM* lbm_, Memory<T>** buffers_) {
-			lbm = lbm_; buffers = buffers_;
+		Memory_Container(LBM* lbm, Memory<T>** buffers, const std::string& name="") { bind(lbm, buffers, name); }
+		void bind(LBM* lbm_, Memory<T>** buffers_, const std::string& name_="") {
+			lbm = lbm_; buffers = buffers_; name = name_;
 			N = lbm->get_N(); d = buffers[0]->dimensions();
 			Nx = lbm->get_Nx(); Ny = lbm->get_Ny(); Nz = lbm->get_Nz(); Dx = lbm->get_Dx(); Dy = lbm->get_Dy(); Dz = lbm->get_Dz(); D = Dx*Dy*Dz;
 			NxNy = (ulong)Nx*(ulong)Ny; NxDx = Nx/Dx; NyDy = Ny/Dy; NzDz = Nz/Dz; Hx = Dx>1u; Hy = Dy>1u; Hz = Dz>1u;
@@ -227,6 +257,43 @@ public:
 			for(uint i=0u; i<D; i++) buffers[i]->enqueue_write_to_device();
 			for(uint i=0u; i<D; i++) buffers[i]->finish_queue();
 		}
+#ifdef LUW_USE_REFERENCE_UTILITIES
+		// Binary legacy-VTK export, byte-compatible with FX/lbm.hpp:307-356,417-423 (tools_core reads these files): STRUCTURED_POINTS header, then the field
+		// as big-endian array-of-structures in SI units, the lowest Nz_write layers only if asked for.
+		void write_host_to_vtk(const string& path="", const bool convert_to_si_units=true, const bool print_saved_message=true, const uint Nz_write=0u) {
+			const string filename = create_file_extension(default_filename(path, name, ".vtk", lbm->get_t()), ".vtk");
+			float spacing = 1.0f; T factor = (T)1;
+			if(convert_to_si_units) {
+				spacing = units.si_x(1.0f);
+				if(name=="rho") factor = (T)units.si_rho(1.0f);
+				if(name=="u") factor = (T)units.si_u(1.0f);
+			}
+			const uint Nz_out = (Nz_write>0u&&Nz_write<Nz) ? Nz_write : Nz;
+			const ulong points = (ulong)Nx*(ulong)Ny*(ulong)Nz_out;
+			float3 origin = spacing*float3(0.5f-0.5f*(float)Nx, 0.5f-0.5f*(float)Ny, 0.5f-0.5f*(float)Nz);
+			if(convert_to_si_units) origin += vtk_origin_shift;
+			const string type = sizeof(T)==1u ? "unsigned_char" : "float"; // the two element types of this build's fields (flags; rho, u)
+			const string header = "# vtk DataFile Version 3.0\nFluidX3D "+filename.substr(filename.rfind('/')+1)+"\nBINARY\nDATASET STRUCTURED_POINTS\n"
+				"DIMENSIONS "+to_string(Nx)+" "+to_string(Ny)+" "+to_string(Nz_out)+"\nORIGIN "+to_string(origin.x)+" "+to_string(origin.y)+" "+to_string(origin.z)+"\n"
+				"SPACING "+to_string(spacing)+" "+to_string(spacing)+" "+to_string(spacing)+"\nPOINT_DATA "+to_string(points)+"\nSCALARS data "+type+" "+to_string(d)+"\nLOOKUP_TABLE default\n";
+			create_folder(filename);
+			std::ofstream file(filename, std::ios::out|std::ios::binary);
+			file.write(header.c_str(), (std::streamsize)header.length());
+			const ulong chunk = 4194304ull; // points per write
+			std::vector<T> data(chunk*(ulong)d);
+			for(ulong p0=0ull; p0<points; p0+=chunk) {
+				const ulong np = points-p0<chunk ? points-p0 : chunk;
+				parallel_for(np, [&](ulong i) { for(uint c=0u; c<d; c++) data[i*(ulong)d+(ulong)c] = reverse_bytes((T)(factor*reference(p0+i, c))); });
+				file.write((const char*)data.data(), (std::streamsize)(np*(ulong)d*sizeof(T)));
+			}
+			file.close();
+			if(print_saved_message) { info.allow_printing.lock(); print_info("File \""+filename+"\" saved."); info.allow_printing.unlock(); }
+		}
+		void write_device_to_vtk(const string& path="", const bool convert_to_si_units=true, const bool print_saved_message=true, const uint Nz_write=0u) {
+			read_from_device();
+			write_host_to_vtk(path, convert_to_si_units, print_saved_message, Nz_write);
+		}
+#endif
 	};
 
 	LBM_Domain** lbm_domain = nullptr; // one LBM domain per GPU
@@ -253,6 +320,9 @@ public:
 	float get_tau() const { return 3.0f*get_nu()+0.5f; }
 	float get_fx() const { return lbm_domain[0]->get_fx(); } float get_fy() const { return lbm_domain[0]->get_fy(); } float get_fz() const { return lbm_domain[0]->get_fz(); }
 	ulong get_t() const { return lbm_domain[0]->get_t(); }
+	float get_Re_max() const { return 0.57735027f*sqrtf((float)Nx*(float)Nx+(float)Ny*(float)Ny+(float)Nz*(float)Nz)/get_nu(); } // Re < c*L_max/nu, FX/lbm.hpp:480
+	float get_omega_x() const { return lbm_domain[0]->get_omega_x(); } float get_omega_y() const { return lbm_domain[0]->get_omega_y(); } float get_omega_z() const { return lbm_domain[0]->get_omega_z(); }
+	uint get_velocity_set() const { return 19u; }
 	void set_fx(const float fx) { for(uint d=0u; d<get_D(); d++) lbm_domain[d]->set_fx(fx); }
 	void set_fy(const float fy) { for(uint d=0u; d<get_D(); d++) lbm_domain[d]->set_fy(fy); }
 	void set_fz(const float fz) { for(uint d=0u; d<get_D(); d++) lbm_domain[d]->set_fz(fz); }
@@ -261,6 +331,31 @@ public:
 
 	void coordinates(const ulong n, uint& x, uint& y, uint& z) const { const ulong t = n%((ulong)Nx*(ulong)Ny); x = (uint)(t%(ulong)Nx); y = (uint)(t/(ulong)Nx); z = (uint)(n/((ulong)Nx*(ulong)Ny)); } // FX/lbm.hpp:500-505
 	ulong index(const uint x, const uint y, const uint z) const { return (ulong)x+((ulong)y+(ulong)z*(ulong)Ny)*(ulong)Nx; }
+#ifdef LUW_USE_REFERENCE_UTILITIES
+	float3 mirror_position(const float3& p) const { // FX/lbm.hpp:531-537
+		return float3(sign(p.x)*(fmod(fabs(p.x)+0.5f*(float)Nx, (float)Nx)-0.5f*(float)Nx), sign(p.y)*(fmod(fabs(p.y)+0.5f*(float)Ny, (float)Ny)-0.5f*(float)Ny), sign(p.z)*(fmod(fabs(p.z)+0.5f*(float)Nz, (float)Nz)-0.5f*(float)Nz));
+	}
+	void coordinates(const float3& p, uint& x, uint& y, uint& z) const { // closest grid point of a position, FX/lbm.hpp:506-511
+		const float3 mp = mirror_position(p);
+		x = (uint)(mp.x+1.5f*(float)Nx)%Nx; y = (uint)(mp.y+1.5f*(float)Ny)%Ny; z = (uint)(mp.z+1.5f*(float)Nz)%Nz;
+	}
+	ulong index(const uint3 xyz) const { return index(xyz.x, xyz.y, xyz.z); }
+	// LBM::voxelize_mesh_on_device, FX/lbm.cpp:1411-1645, for resting geometry: every domain casts its rays against the whole mesh (the reference's per-domain triangle
+	// culling is an optimisation, not a semantic), TYPE_S along z; then the host mirrors are refreshed like FX/lbm.cpp:1641-1644 does before initialisation.
+	void voxelize_mesh_on_device(const Mesh* mesh, const uchar flag=TYPE_S, const float3& rotation_center=float3(0.0f), const float3& linear_velocity=float3(0.0f), const float3& rotational_velocity=float3(0.0f)) {
+		(void)rotation_center;
+		if(length(linear_velocity)>0.0f||length(rotational_velocity)>0.0f) print_error("voxelize_mesh_on_device: moving geometry is not part of this build (LUW voxelises resting meshes only).");
+		for(uint d=0u; d<get_D(); d++) lbm_domain[d]->voxelize_mesh_on_device(mesh, flag);
+		if(!initialized) { flags.read_from_device(); u.read_from_device(); }
+		if(flag==TYPE_S) { // FX/lbm.cpp:1626-1637
+			ulong solid = 0ull;
+			const ulong N = get_N();
+			for(ulong n=0ull; n<N; n++) if(flags[n]&TYPE_S) solid++;
+			print_info("Voxelized cells (whole domain global, no halos): solid = "+to_string(solid)+", fluid = "+to_string(N-solid)+", total = "+to_string(N)+".");
+		}
+	}
+	struct { int visualization_modes = 0; } graphics; // FX/setup.cpp:4125 sets it unconditionally; rendering is not part of this build
+#endif
 	float3 position(const uint x, const uint y, const uint z) const { return float3((float)x-0.5f*(float)Nx+0.5f, (float)y-0.5f*(float)Ny+0.5f, (float)z-0.5f*(float)Nz+0.5f); }
 	float3 position(const ulong n) const { uint x, y, z; coordinates(n, x, y, z); return position(x, y, z); }
 	float3 size() const { return float3((float)Nx, (float)Ny, (float)Nz); }

@@ -1,0 +1,50 @@
+"""CPU, build container only (needs /root/reference): the reference's own translation units that talk to the LBM -- setup.cpp (6 154 lines: deck parser, case
+drivers, run loop, VTK / probe output), interpolation.cpp, interpolation_hd.cpp, fluxcorrection.cpp, info.cpp -- are syntax-checked against THIS repo's
+host/lbm.hpp standing in for FX/lbm.hpp (with the reference's utilities.hpp / units.hpp / info.hpp / defines.hpp, GRAPHICS / TEMPERATURE / FORCE_FIELD off).
+Nothing of the reference is copied into the repository: the sources are compiled from a scratch directory.
+
+Allowed to fail: the von Karman inlet's direct use of the OpenCL objects Device / Kernel (FX/setup.cpp:554,620,1034-1086: the documented 10-line edit of
+INTEGRATION.md section 3.4) and `main_arguments` (a global of the reference's main.cpp / graphics.cpp, not of the LBM layer)."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FX = "/root/reference/core/cfd_core/FluidX3D/src"
+pytestmark = pytest.mark.skipif(not os.path.isfile(os.path.join(FX, "setup.cpp")), reason="reference tree not present")
+
+ALLOWED = re.compile(r"\bKernel\b|\bDevice\b|\bdevice\b|kernel_apply|main_arguments|setup\.cpp:1034:")
+
+
+def _scratch(tmp_path):
+    d = str(tmp_path)
+    for f in ("utilities.hpp", "units.hpp", "shapes.hpp", "setup.hpp", "info.hpp", "interpolation.hpp", "interpolation_hd.hpp", "fluxcorrection.hpp", "lodepng.hpp", "graphics.hpp",
+              "setup.cpp", "interpolation.cpp", "interpolation_hd.cpp", "fluxcorrection.cpp", "info.cpp"):
+        shutil.copy(os.path.join(FX, f), os.path.join(d, f))
+    defines = open(os.path.join(FX, "defines.hpp")).read()
+    for name in ("GRAPHICS", "TEMPERATURE", "FORCE_FIELD"):  # not part of this path
+        defines = re.sub(r"(?m)^#define %s\b" % name, "//#define %s" % name, defines)
+    open(os.path.join(d, "defines.hpp"), "w").write(defines)
+    open(os.path.join(d, "lbm.hpp"), "w").write('#pragma once\n#include "utilities.hpp"\n#define LUW_USE_REFERENCE_UTILITIES\n#include "%s/latticeurbanwind_b200/host/lbm.hpp"\n' % ROOT)
+    open(os.path.join(d, "our_lbm.cpp"), "w").write('#include "utilities.hpp"\n#define LUW_USE_REFERENCE_UTILITIES\n#include "%s/latticeurbanwind_b200/host/lbm.cpp"\n' % ROOT)
+    return d
+
+
+def _errors(d, src):
+    r = subprocess.run(["g++", "-std=c++17", "-O0", "-fsyntax-only", "-Wno-comment", "-I.", src], cwd=d, capture_output=True, text=True, env=dict(os.environ, LC_ALL="C"))
+    return [l for l in r.stderr.splitlines() if " error: " in l]
+
+
+@pytest.mark.parametrize("src", ["interpolation.cpp", "interpolation_hd.cpp", "fluxcorrection.cpp", "info.cpp", "our_lbm.cpp"])
+def test_reference_callers_compile_unchanged(tmp_path, src):
+    assert _errors(_scratch(tmp_path), src) == []
+
+
+def test_case_driver_compiles_up_to_the_documented_edits(tmp_path):
+    errs = _errors(_scratch(tmp_path), "setup.cpp")
+    other = [e for e in errs if not ALLOWED.search(e)]
+    assert other == [], "\n".join(other)
+    assert len(errs) <= 14
