@@ -24,6 +24,19 @@ float lbm_kernel_literal(const float x) { // what `to_string(float)` + the OpenC
 }
 
 #ifdef LUW_USE_REFERENCE_UTILITIES
+// Inside the reference tree this file stands in for FX/lbm.cpp: it defines the globals that one defines (FX/lbm.cpp:18-20) and reads the ones the case driver
+// sets before it constructs an LBM (FX/lbm.cpp:3-14; written by update_coriolis / update_buffer_nudging / update_top_sponge, FX/setup.cpp:3800-3903), which the
+// reference bakes into its kernel source (FX/lbm.cpp:770-782) -- so the case driver needs no edits for them.
+Units units; // for unit conversion
+float coriolis_f_lbmu = 0.0f;
+extern bool buffer_nudging_active; extern int buffer_n_cells; extern float buffer_inv_tau_lbmu; extern int buffer_nudge_vertical; extern int buffer_downstream_face_id;
+extern bool top_sponge_active; extern int sponge_n_cells; extern float sponge_inv_tau_lbmu; extern int sponge_ref_mode;
+static void settings_from_case_driver() {
+	lbm_settings.downstream_face = buffer_downstream_face_id; // def_downstream_face
+	lbm_settings.set_buffer_nudging(buffer_nudging_active&&buffer_n_cells>0 ? (uint)buffer_n_cells : 0u, buffer_inv_tau_lbmu, buffer_nudge_vertical!=0);
+	lbm_settings.set_top_sponge(top_sponge_active&&sponge_n_cells>0 ? (uint)sponge_n_cells : 0u, sponge_inv_tau_lbmu);
+	if(top_sponge_active&&sponge_ref_mode!=0) print_error("sponge_ref_mode "+to_string(sponge_ref_mode)+" is not implemented (the reference kernel implements mode 0 only, FX/kernel.cpp:1597).");
+}
 float3 vtk_origin_shift = float3(0.0f, 0.0f, 0.0f); // FX/lbm.cpp:18-20
 // Device memory of THIS build per domain: DDFs (19 fpxx) + rho, u (16 B) + flags (1 B) per cell of the padded local lattice, + halo buffers. The reference's
 // estimator (FX/lbm.cpp:143-232) counts its own buffer set (F, gi, T, graphics, transfer buffers): a deck with mesh_control="gpu_memory" therefore resolves to a
@@ -79,6 +92,9 @@ LBM_Domain::~LBM_Domain() { luw_domain_destroy(handle); }
 
 // ---------------------------------------------------------------------------------------------------------------- LBM
 void LBM::construct(const uint Nx_, const uint Ny_, const uint Nz_, const uint Dx_, const uint Dy_, const uint Dz_, const float nu, const float fx, const float fy, const float fz) {
+#ifdef LUW_USE_REFERENCE_UTILITIES
+	settings_from_case_driver();
+#endif
 	if(Dx_*Dy_*Dz_==0u) print_error("You specified 0 LBM grid domains. There has to be at least 1 domain in every direction.");
 	Dx = Dx_; Dy = Dy_; Dz = Dz_;
 	Nx = (Nx_/Dx)*Dx; Ny = (Ny_/Dy)*Dy; Nz = (Nz_/Dz)*Dz; // global size rounded down to multiples of the domain counts, FX/lbm.cpp:1058-1060

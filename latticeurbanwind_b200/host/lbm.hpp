@@ -47,6 +47,7 @@ constexpr ulong max_ulong = 18446744073709551615ull;
 #ifdef LUW_USE_REFERENCE_UTILITIES // inside the reference tree: the names FX/lbm.hpp:3-21 brings into every translation unit that includes it
 #include "defines.hpp" // TYPE_* flag bits, fpxx
 #include "units.hpp" // `units` (SI <-> lattice), used by the VTK writer
+#include "graphics.hpp" // main_arguments, running (FX/graphics.hpp:16-17; compiles to declarations only when GRAPHICS is off)
 #include "info.hpp" // `info` (console progress; FX/info.cpp reads the LBM through the getters below)
 #include <fstream>
 #include <thread>
@@ -59,7 +60,7 @@ uint bytes_per_cell_host(); // FX/lbm.hpp:13-15, for THIS build's buffers and th
 uint bytes_per_cell_device();
 uint bandwidth_bytes_per_cell_device();
 struct LBM_Device_Info { uint id = 0u; string name = ""; uint memory = 0u, memory_used = 0u; bool uses_ram = false; uint compute_units = 0u, clock_frequency = 0u; }; // the Device_Info fields FX/info.cpp:233-241 prints
-struct LBM_Device { LBM_Device_Info info; }; // what LBM_Domain::get_device() hands out (reference: the OpenCL Device, FX/opencl.hpp:274)
+struct Device { LBM_Device_Info info; luw_domain* dom = nullptr; }; // what LBM_Domain::get_device() hands out (reference: the OpenCL Device, FX/opencl.hpp:274): its info block + the C-ABI handle
 #endif // LUW_USE_REFERENCE_UTILITIES
 
 // Run-time replacement of FX/defines.hpp + the constants of FX/lbm.cpp:612-783. Set the global `lbm_settings` before constructing an LBM
@@ -88,6 +89,8 @@ private:
 	int field = 0;
 	ulong N = 0ull; uint d = 1u;
 	T* host = nullptr;
+	bool loose = false; // host-only buffer that is not a field of the lattice (see below)
+	void release() { if(host) { if(loose) delete[] host; else luw_host_free(host); } host = nullptr; }
 public:
 	T* x = nullptr; T* y = nullptr; T* z = nullptr; // host pointers of the components (FX/opencl.hpp:343-349)
 	Memory() {}
@@ -101,7 +104,23 @@ public:
 	}
 	Memory(const Memory&) = delete;
 	Memory& operator=(const Memory&) = delete;
-	~Memory() { if(host) luw_host_free(host); }
+	Memory(Memory&& o) noexcept { *this = std::move(o); }
+	Memory& operator=(Memory&& o) noexcept {
+		if(this!=&o) { release(); dom = o.dom; field = o.field; N = o.N; d = o.d; host = o.host; loose = o.loose; x = o.x; y = o.y; z = o.z; o.host = nullptr; o.x = o.y = o.z = nullptr; o.N = 0ull; }
+		return *this;
+	}
+	~Memory() { release(); }
+#ifdef LUW_USE_REFERENCE_UTILITIES
+	// Memory<T>(device, N, dimensions, allocate_host, allocate_device, value, external) of FX/opencl.hpp:383-391 for buffers that are NOT fields of the lattice: the case
+	// driver packs the von Karman inlet's point / mode tables into such objects (FX/setup.cpp:1040-1074). Host side only; the Kernel object below takes the contents.
+	Memory(Device& device, const ulong N, const uint dimensions=1u, const bool=true, const bool=true, const T value=(T)0, const bool=false) : N(N), d(dimensions), loose(true) {
+		(void)device;
+		if(N*(ulong)d==0ull) print_error("Memory size must be larger than 0.");
+		host = new T[N*(ulong)d];
+		x = host; if(d>1u) y = host+N; if(d>2u) z = host+2ull*N;
+		reset(value);
+	}
+#endif
 	void reset(const T value=(T)0) { for(ulong i=0ull; i<range(); i++) host[i] = value; }
 	ulong length() const { return N; }
 	uint dimensions() const { return d; }
@@ -113,16 +132,48 @@ public:
 	const T& operator[](const ulong i) const { return host[i]; }
 	T operator()(const ulong i) const { return host[i]; }
 	T operator()(const ulong i, const uint dimension) const { return host[i+(ulong)dimension*N]; }
-	void enqueue_read_from_device() { luw_check(luw_download(dom, field, host, 0ull, range())); }
-	void enqueue_write_to_device() { luw_check(luw_upload(dom, field, host, 0ull, range())); }
-	void enqueue_read_from_device(const ulong offset, const ulong length) { luw_check(luw_download(dom, field, host+offset, offset, length)); }
-	void enqueue_write_to_device(const ulong offset, const ulong length) { luw_check(luw_upload(dom, field, host+offset, offset, length)); }
-	void finish_queue() { luw_check(luw_sync(dom)); }
+	void enqueue_read_from_device() { if(!loose) luw_check(luw_download(dom, field, host, 0ull, range())); }
+	void enqueue_write_to_device() { if(!loose) luw_check(luw_upload(dom, field, host, 0ull, range())); }
+	void enqueue_read_from_device(const ulong offset, const ulong length) { if(!loose) luw_check(luw_download(dom, field, host+offset, offset, length)); }
+	void enqueue_write_to_device(const ulong offset, const ulong length) { if(!loose) luw_check(luw_upload(dom, field, host+offset, offset, length)); }
+	void finish_queue() { if(!loose) luw_check(luw_sync(dom)); }
 	void read_from_device() { enqueue_read_from_device(); finish_queue(); }
 	void write_to_device() { enqueue_write_to_device(); finish_queue(); }
 	void read_from_device(const ulong offset, const ulong length) { enqueue_read_from_device(offset, length); finish_queue(); }
 	void write_to_device(const ulong offset, const ulong length) { enqueue_write_to_device(offset, length); finish_queue(); }
 };
+
+#ifdef LUW_USE_REFERENCE_UTILITIES
+// The one Kernel object the case driver creates itself (FX/setup.cpp:1076-1086): Kernel(device, N, "vk_inlet_apply", use_interp, t0, t1, alpha, point_count, mode_count,
+// mode_stride, point_cell, point_face, point_data, mode_data, u) and, per step, set_parameters(0u, use_interp, t0, t1, alpha).enqueue_run() (FX/setup.cpp:553).
+// Here it owns a luw_vk_inlet built from the packed tables; any other kernel name is an error (there is no OpenCL program behind this layer).
+class Kernel {
+private:
+	luw_vk_inlet* vk = nullptr;
+	uint use_interp = 0u; float t0 = 0.0f, t1 = 0.0f, alpha = 0.0f;
+public:
+	Kernel() {}
+	Kernel(const Device& device, const ulong N, const string& name, const uint use_interp, const float t0, const float t1, const float alpha, const ulong point_count, const ulong mode_count, const ulong mode_stride,
+		Memory<ulong>& point_cell, Memory<uchar>& point_face, Memory<float>& point_data, Memory<float>& mode_data, Memory<float>& u) : use_interp(use_interp), t0(t0), t1(t1), alpha(alpha) {
+		(void)N; (void)u; // the velocity field is the domain's own
+		if(name!="vk_inlet_apply") print_error("Kernel \""+name+"\": only vk_inlet_apply can be created by the case driver in this build.");
+		static_assert(sizeof(ulong)==sizeof(uint64_t), "point_cell is an array of 64-bit cell indices");
+		luw_check(luw_vk_inlet_create(device.dom, point_count, mode_count, mode_stride, (const uint64_t*)point_cell.data(), point_face.data(), point_data.data(), mode_data.data(), &vk));
+	}
+	Kernel(const Kernel&) = delete;
+	Kernel& operator=(const Kernel&) = delete;
+	Kernel(Kernel&& o) noexcept { *this = std::move(o); }
+	Kernel& operator=(Kernel&& o) noexcept { if(this!=&o) { if(vk) luw_vk_inlet_destroy(vk); vk = o.vk; use_interp = o.use_interp; t0 = o.t0; t1 = o.t1; alpha = o.alpha; o.vk = nullptr; } return *this; }
+	~Kernel() { if(vk) luw_vk_inlet_destroy(vk); }
+	Kernel& set_parameters(const uint position, const uint use_interp_, const float t0_, const float t1_, const float alpha_) {
+		if(position!=0u) print_error("Kernel::set_parameters: vk_inlet_apply takes its per-step arguments from position 0.");
+		use_interp = use_interp_; t0 = t0_; t1 = t1_; alpha = alpha_;
+		return *this;
+	}
+	Kernel& enqueue_run() { if(vk) luw_check(luw_vk_inlet_apply(vk, use_interp, t0, t1, alpha)); return *this; }
+	Kernel& run() { return enqueue_run(); }
+};
+#endif // LUW_USE_REFERENCE_UTILITIES
 
 // ---------------------------------------------------------------------------------------------------------------- LBM_Domain (FX/lbm.hpp:26-221)
 class LBM_Domain {
@@ -180,13 +231,17 @@ public:
 	luw_domain* get_handle() const { return handle; } // reference: get_device() hands out the OpenCL Device; here the C-ABI handle
 	int get_device_ordinal() const { return device; }
 #ifdef LUW_USE_REFERENCE_UTILITIES
-	LBM_Device get_device() const { // FX/lbm.hpp:141; callers read .info only (FX/info.cpp:233-241, FX/setup.cpp:4415-4424)
-		LBM_Device dev; luw_device_info di;
+	const Device& get_device() const { // FX/lbm.hpp:141; callers read .info (FX/info.cpp:233-241, FX/setup.cpp:4415-4424) or pass it on to Memory / Kernel (FX/setup.cpp:1034)
+		luw_device_info di;
 		luw_check(luw_get_device_info(device, &di));
-		dev.info.id = (uint)device; dev.info.name = di.name; dev.info.memory = (uint)(di.memory_bytes/1048576ull); dev.info.memory_used = (uint)(device_memory_used()/1048576ull);
-		dev.info.compute_units = di.compute_units; dev.info.clock_frequency = di.clock_mhz;
-		return dev;
+		device_view.dom = handle;
+		device_view.info.id = (uint)device; device_view.info.name = di.name; device_view.info.memory = (uint)(di.memory_bytes/1048576ull); device_view.info.memory_used = (uint)(device_memory_used()/1048576ull);
+		device_view.info.compute_units = di.compute_units; device_view.info.clock_frequency = di.clock_mhz;
+		return device_view;
 	}
+private:
+	mutable Device device_view;
+public:
 #endif
 	ulong device_memory_used() const { uint64_t b = 0ull; luw_domain_bytes(handle, &b); return (ulong)b; } // Device_Info::memory_used (FX/info.cpp:233-241)
 	static uint lbm_features();
