@@ -119,6 +119,9 @@ LBM::LBM(const uint Nx, const uint Ny, const uint Nz, const float nu, const floa
 LBM::LBM(const uint3 N, const uint Dx, const uint Dy, const uint Dz, const float nu, const float fx, const float fy, const float fz, const float, const float, const float) { construct(N.x, N.y, N.z, Dx, Dy, Dz, nu, fx, fy, fz); }
 LBM::LBM(const uint3 N, const float nu, const float fx, const float fy, const float fz, const float, const float, const float) { construct(N.x, N.y, N.z, 1u, 1u, 1u, nu, fx, fy, fz); }
 LBM::~LBM() {
+#ifdef LUW_USE_REFERENCE_UTILITIES
+	info.print_finalize(); // FX/lbm.cpp: the console table is closed with the simulation
+#endif
 	for(uint d=0u; d<get_D(); d++) delete lbm_domain[d];
 	delete[] lbm_domain;
 }
@@ -145,11 +148,25 @@ void LBM::do_time_step() { // FX/lbm.cpp:1262-1290 (GRAPHICS / TEMPERATURE excha
 	communicate(LUW_HALO_FI);
 	for(uint d=0u; d<D; d++) lbm_domain[d]->increment_time_step();
 }
-void LBM::run(const ulong steps, const ulong) { // FX/lbm.cpp:1292-1312; steps are enqueued back to back, one synchronisation at the end of the call
+void LBM::run(const ulong steps, const ulong total_steps) { // FX/lbm.cpp:1292-1312
+#ifdef LUW_USE_REFERENCE_UTILITIES // inside the reference tree: feed the console table / ETA model exactly like FX/lbm.cpp does (FX/info.cpp reads it from another thread)
+	info.append(steps, total_steps, get_t());
+	if(!initialized) { initialize(); info.print_initialize(this); }
+	Clock clock;
+	const ulong n = steps==max_ulong ? 0ull : steps;
+	for(ulong i=0ull; i<n; i++) {
+		clock.start();
+		do_time_step();
+		for(uint d=0u; d<get_D(); d++) lbm_domain[d]->finish_queue(); // the step time shown on the console is the step's, not the enqueue's
+		info.update(clock.stop());
+	}
+#else // stand-alone: steps are enqueued back to back, one synchronisation at the end of the call
+	(void)total_steps;
 	if(!initialized) initialize();
 	const ulong n = steps==max_ulong ? 0ull : steps; // the reference's "run forever" needs the interactive main loop; not part of this layer
 	for(ulong i=0ull; i<n; i++) do_time_step();
 	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->finish_queue();
+#endif
 }
 void LBM::update_fields() { for(uint d=0u; d<get_D(); d++) lbm_domain[d]->enqueue_update_fields(); for(uint d=0u; d<get_D(); d++) lbm_domain[d]->finish_queue(); }
 void LBM::reset() { initialized = false; }
