@@ -380,8 +380,10 @@ def bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src):
     from latticeurbanwind_b200.lbm import DistributedLBM
     case, shape, precision, features, fset, nu, desc = WORKLOADS[args.workload]
     torch.cuda.set_device(local)
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # NCCL would print its version banner on stdout, in front of the JSON line
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # rank 0 prints ONE JSON line on stdout: whatever native libraries write there while the communicators come up (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     D = tuple(int(v) for v in args.decomp.split(",")) if args.decomp else DECOMP[case][world]
     assert len(D) == 3 and D[0] * D[1] * D[2] == world, "--decomp must multiply to the number of ranks"
@@ -430,7 +432,10 @@ def bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src):
                "e2e": {"value": mlups, "unit": "MLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                        "note": "N>1: the multi-rank loop IS the host-API loop (DistributedLBM.run); per-step boundary upload / probe read-back are measured at N=1"},
                "clocks": clocks, "gpu_launches": int(launches)}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(res), flush=True)
+        os.dup2(2, 1)
     lbm.close()
     dist.destroy_process_group()
     return 0
