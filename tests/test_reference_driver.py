@@ -13,8 +13,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DRIVER = os.path.join(ROOT, "baseline", "_ref", "luw_reference_driver")
 CASE = os.path.join(ROOT, "baseline", "_ref", "case_profile")
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not (os.path.isfile(DRIVER) and os.path.isdir(CASE)), reason="baseline/_ref was not built (needs /root/reference at build time)"),
-              pytest.mark.skipif(os.environ.get("LUW_RUN_REFERENCE_DRIVER", "0") != "1", reason="opt-in (LUW_RUN_REFERENCE_DRIVER=1) until the run has been observed on a B200")]
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not (os.path.isfile(DRIVER) and os.path.isdir(CASE)), reason="baseline/_ref was not built (needs /root/reference at build time)")]
 
 
 def read_vtk(path):
