@@ -1,0 +1,32 @@
+"""CPU: the parts of the bench.py contract that do not need a GPU -- the reference arm's JSON line and the loud failure of the GPU arm without a device."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "D3Q19 MLUP/s" and d["unit"] == "MLUP/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] >= 1 and d["vs_baseline"] is None
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "block" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "MLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["name"] == "channel512_fp16s"
+
+
+def test_gpu_arm_fails_loudly_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+    assert r.stdout.strip() == ""
