@@ -394,6 +394,7 @@ def bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src):
                          omega=OMEGA if features & F_VF else (0.0, 0.0, 0.0), transport=args.transport, **zones)
     assert tuple(lbm.Nl) == tuple(shape)
     flags, rho, u = cases.block_case(case, Ng, lbm.O, shape)
+    dist.barrier()  # host-side case generation takes seconds and not the same number on every rank: start the first halo exchange together
     lbm.initialize(flags, rho, u)
     K, W = args.steps, args.warmup
     lbm.run(W)

@@ -253,7 +253,7 @@ __global__ void k_halo_wait(const uint32_t* flag_p, const uint32_t* flag_m, cons
 			asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
 			if((int32_t)(v-value)>=0) break;
 			__nanosleep(200u);
-			if(clock64()-t0>40000000000ll) __trap(); // ~20 s
+			if(clock64()-t0>120000000000ll) __trap(); // ~60 s at 2 GHz: ranks may reach their first exchange seconds apart (host-side case generation)
 		}
 	}
 }
