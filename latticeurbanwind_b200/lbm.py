@@ -176,9 +176,11 @@ class LBM(_Base):
 
 class DistributedLBM(_Base):
     """One domain per rank (torch.distributed); rank r owns domain r of the split. Works with NCCL (GPU) and, for the host logic, with
-    gloo: `cpu_engine` then stands in for the device (tests only -- the product path has no CPU fallback)."""
+    gloo: with `routing_only=True` no device domain is created and the class only does what is host logic -- the domain split, neighbour ranks, the
+    x -> y -> z exchange order on host tensors -- while the caller supplies the extract / insert callbacks (the CPU tests plug the oracle in there).
+    There is no CPU fallback of the LBM itself: initialize() / run() need the device domain."""
 
-    def __init__(self, shape, D, group=None, device=0, cpu_engine=None, transport="ipc", **kw):
+    def __init__(self, shape, D, group=None, device=0, routing_only=False, transport="ipc", **kw):
         super().__init__(shape, D, **kw)
         import torch
         import torch.distributed as dist
@@ -187,10 +189,10 @@ class DistributedLBM(_Base):
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         assert self.world == len(self._split), "one rank per domain"
         self.d, self.O = self._split[self.rank]
-        self.cpu_engine = cpu_engine
+        self.routing_only = bool(routing_only)
         self.device = device
         self.gidx = _local_index(self.Ng, self.Nl, self.O)
-        if cpu_engine is None:
+        if not self.routing_only:
             self.domain = self._make_domain(self.d, self.O, device)
             self.domains = [self.domain]
             # one explicit stream orders the step kernels, the halo kernels and the NCCL calls (torch's default stream has handle 0, which the C ABI
@@ -231,7 +233,7 @@ class DistributedLBM(_Base):
         key = (payload, axis)
         if key not in self._bufs:
             torch = self._torch
-            dev = torch.device("cpu") if self.cpu_engine is not None else torch.device("cuda", self.device)
+            dev = torch.device("cpu") if self.routing_only else torch.device("cuda", self.device)
             self._bufs[key] = tuple(torch.empty(self.halo_bytes(payload, axis), dtype=torch.uint8, device=dev) for _ in range(4))
         return self._bufs[key]
 
@@ -244,7 +246,7 @@ class DistributedLBM(_Base):
             return
         ops = [dist.P2POp(dist.isend, sp, up, self.group, tag=2 * axis), dist.P2POp(dist.isend, sm, dn, self.group, tag=2 * axis + 1),
                dist.P2POp(dist.irecv, rm, dn, self.group, tag=2 * axis), dist.P2POp(dist.irecv, rp, up, self.group, tag=2 * axis + 1)]
-        if self.cpu_engine is None:
+        if not self.routing_only:
             with self._torch.cuda.stream(self._stream):  # NCCL enqueues on the current stream
                 for r in dist.batch_isend_irecv(ops):
                     r.wait()
@@ -256,7 +258,7 @@ class DistributedLBM(_Base):
         for axis in AXES:
             if self.D[axis] < 2:
                 continue
-            if self.cpu_engine is None and self.transport == "ipc":
+            if not self.routing_only and self.transport == "ipc":
                 self.domain.halo_ipc_exchange(payload, axis)
                 continue
             sp, sm, rp, rm = self._buffers(payload, axis)
@@ -273,6 +275,8 @@ class DistributedLBM(_Base):
 
     def initialize(self, flags, rho, u):
         """flags / rho / u: LOCAL host images of this rank's domain (halo layers included)."""
+        if self.domain is None:
+            raise RuntimeError("DistributedLBM(routing_only=True) has no device domain: the LBM step has no CPU fallback")
         dom = self.domain
         dom.rho[:], dom.u[:], dom.flags[:] = rho, u, flags
         dom.f, dom.omega = self.f, self.omega

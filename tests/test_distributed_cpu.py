@@ -33,7 +33,7 @@ def _worker(rank, world, port, D, precision, out):
         zones = dict(downstream_face=2, buffer_N=4, buffer_inv_tau=0.01, buffer_nudge_vertical=1, sponge_N=5, sponge_inv_tau=0.02)
         orc = O.Oracle()
         orc.set_threads(2)
-        lbm = DistributedLBM(SHAPE, D, cpu_engine=orc, precision=precision, features=feat, nu=1e-6, f=H.FORCE, omega=H.OMEGA, **zones)
+        lbm = DistributedLBM(SHAPE, D, routing_only=True, precision=precision, features=feat, nu=1e-6, f=H.FORCE, omega=H.OMEGA, **zones)
         shape, Ov, fl, rh, uu = H.cut_block(SHAPE, D, lbm.d, flags, rho, u)
         assert shape == lbm.Nl and Ov == lbm.O
         p = O.make_params(*shape, precision, feat, w=lbm.w, D=D, O=Ov, **zones)
