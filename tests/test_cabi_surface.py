@@ -49,3 +49,9 @@ def test_no_device_means_error_not_fallback():
     with pytest.raises(A.LuwError):
         A.check(rc)
     assert A.device_count() == 0
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: the header must compile as C99 on its own (no C++ or torch types in the signatures)."""
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", HEADER], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
