@@ -253,10 +253,88 @@ static void luw_force(const luwo_params* p, const frame_t* g, uint64_t n, uint32
 	*Fx = fxn; *Fy = fyn; *Fz = fzn;
 }
 
-/* ------------------------------------------------------------------ kernel: initialize, FX/kernel.cpp:1370-1452 */
-void luwo_initialize(const luwo_params* p, void* fi, const float* rho, float* u, uint8_t* flags) {
+/* ------------------------------------------------------------------ thermal D3Q7 (TEMPERATURE), FX/kernel.cpp:1306-1336 */
+#define TYPE_T 0x04u
+static void neighbors_temperature(const luwo_params* p, uint64_t n, uint64_t* j7) {
+	const xyz_t c = coords(p, n);
+	const uint64_t row = p->Nx, plane = (uint64_t)p->Nx*p->Ny;
+	const uint64_t x0 = c.x, xp = (c.x+1u)%p->Nx, xm = (c.x+p->Nx-1u)%p->Nx;
+	const uint64_t y0 = c.y*row, yp = ((c.y+1u)%p->Ny)*row, ym = ((c.y+p->Ny-1u)%p->Ny)*row;
+	const uint64_t z0 = c.z*plane, zp = ((c.z+1u)%p->Nz)*plane, zm = ((c.z+p->Nz-1u)%p->Nz)*plane;
+	j7[0] = n;
+	j7[1] = xp+y0+z0; j7[2] = xm+y0+z0;
+	j7[3] = x0+yp+z0; j7[4] = x0+ym+z0;
+	j7[5] = x0+y0+zp; j7[6] = x0+y0+zm;
+}
+void luwo_calculate_g_eq(float T, float ux, float uy, float uz, float* geq) { /* D3Q7, lattice speed of sound 1/2, DDF-shifted */
+	const float wsT4 = 0.5f*T, wsTm1 = 0.125f*(T-1.0f);
+	geq[0] = fmaf(0.25f, T, -0.25f);
+	geq[1] = fmaf(wsT4, ux, wsTm1); geq[2] = fmaf(wsT4, -ux, wsTm1);
+	geq[3] = fmaf(wsT4, uy, wsTm1); geq[4] = fmaf(wsT4, -uy, wsTm1);
+	geq[5] = fmaf(wsT4, uz, wsTm1); geq[6] = fmaf(wsT4, -uz, wsTm1);
+}
+static void load_g(const luwo_params* p, uint64_t n, float* g, const void* gi, const uint64_t* j7, uint64_t t) {
 	const uint64_t N = cells(p);
-	(void)flags;
+	const int odd = (int)(t&1u);
+	g[0] = ddf_load(p, gi, n);
+	for(uint32_t i=1u; i<7u; i+=2u) {
+		g[i   ] = ddf_load(p, gi, (uint64_t)(odd ? i    : i+1u)*N+n    );
+		g[i+1u] = ddf_load(p, gi, (uint64_t)(odd ? i+1u : i   )*N+j7[i]);
+	}
+}
+static void store_g(const luwo_params* p, uint64_t n, const float* g, void* gi, const uint64_t* j7, uint64_t t) {
+	const uint64_t N = cells(p);
+	const int odd = (int)(t&1u);
+	ddf_store(p, gi, n, g[0]);
+	for(uint32_t i=1u; i<7u; i+=2u) {
+		ddf_store(p, gi, (uint64_t)(odd ? i+1u : i   )*N+j7[i], g[i   ]);
+		ddf_store(p, gi, (uint64_t)(odd ? i    : i+1u)*N+n    , g[i+1u]);
+	}
+}
+/* the TEMPERATURE block of stream_collide (FX/kernel.cpp:1639-1684): stream g in, T from g (or the preset of a TYPE_T cell), relax T towards the top
+ * row inside the sponge (def_sponge_ref_mode == 0, the only mode LUW's build selects: clshim / FX/lbm.cpp:781), collide towards g_eq(T, u BEFORE the
+ * force half-step), stream out, buoyancy onto the force. NOTE: the sponge reads T of the top-row cell of the column while that cell may store its
+ * own T in the same NDRange unless it is TYPE_T; the reference has the same ordering freedom, so parity cases give the top row TYPE_T. */
+static void thermal_step(const luwo_params* p, const luwo_thermal* th, const frame_t* g, uint64_t n, uint32_t fl, uint32_t bo, void* gi, float* T, uint64_t t,
+	float uxn, float uyn, float uzn, float fx, float fy, float fz, float* fxn, float* fyn, float* fzn) {
+	uint64_t j7[7];
+	neighbors_temperature(p, n, j7);
+	float gh[7];
+	load_g(p, n, gh, gi, j7, t);
+	float Tn;
+	if(fl&TYPE_T) Tn = T[n];
+	else {
+		Tn = 0.0f;
+		for(int i=0; i<7; i++) Tn += gh[i];
+		Tn += 1.0f;
+	}
+	if((p->features&LUWO_TOP_SPONGE)&&!(fl&TYPE_T)&&bo!=TYPE_E&&g->has_t) {
+		const xyz_t c = coords(p, n);
+		const int dt = (int)(g->Nzg-2u)-((int)c.z+p->Oz);
+		const int Ns = (int)p->sponge_N;
+		if(dt>=0&&dt<Ns) {
+			const float xi = Ns>1 ? 1.0f-(float)dt/(float)(Ns-1) : 1.0f;
+			float sigma = sinf(1.5707963267948966f*xi);
+			sigma = p->sponge_inv_tau*sigma*sigma;
+			Tn = fmaf(sigma, T[lin(p, c.x, c.y, (uint32_t)g->tz)]-Tn, Tn);
+		}
+	}
+	float geq[7];
+	luwo_calculate_g_eq(Tn, uxn, uyn, uzn, geq);
+	if(fl&TYPE_T) { for(int i=0; i<7; i++) gh[i] = geq[i]; }
+	else {
+		if(p->features&LUWO_UPDATE_FIELDS) T[n] = Tn;
+		for(int i=0; i<7; i++) gh[i] = fmaf(1.0f-th->w_T, gh[i], th->w_T*geq[i]);
+	}
+	store_g(p, n, gh, gi, j7, t);
+	*fxn -= fx*th->beta*(Tn-th->T_avg);
+	*fyn -= fy*th->beta*(Tn-th->T_avg);
+	*fzn -= fz*th->beta*(Tn-th->T_avg);
+}
+
+/* ------------------------------------------------------------------ kernel: initialize, FX/kernel.cpp:1370-1452 */
+static void initialize_impl(const luwo_params* p, void* fi, const float* rho, float* u, uint8_t* flags, void* gi, const float* T) {
+	const uint64_t N = cells(p);
 	PAR_FOR
 	for(int64_t nn=0; nn<(int64_t)N; nn++) {
 		const uint64_t n = (uint64_t)nn;
@@ -266,13 +344,24 @@ void luwo_initialize(const luwo_params* p, void* fi, const float* rho, float* u,
 		if((flags[n]&TYPE_BO)==TYPE_S) { u[n] = 0.0f; u[N+n] = 0.0f; u[2u*N+n] = 0.0f; } /* MOVING_BOUNDARIES is off in LUW's build */
 		float feq[Q];
 		luwo_calculate_f_eq(rho[n], u[n], u[N+n], u[2u*N+n], feq);
+		if(gi) { /* FX/kernel.cpp:1442-1450 */
+			float geq[7];
+			luwo_calculate_g_eq(T[n], u[n], u[N+n], u[2u*N+n], geq);
+			uint64_t j7[7];
+			neighbors_temperature(p, n, j7);
+			store_g(p, n, geq, gi, j7, 1u);
+		}
 		store_f(p, n, feq, fi, j, 1u);
 	}
 }
+void luwo_initialize(const luwo_params* p, void* fi, const float* rho, float* u, uint8_t* flags) { initialize_impl(p, fi, rho, u, flags, 0, 0); }
+void luwo_initialize_thermal(const luwo_params* p, void* fi, const float* rho, float* u, uint8_t* flags, void* gi, const float* T) {
+	initialize_impl(p, fi, rho, u, flags, gi, T);
+}
 
 /* ------------------------------------------------------------------ kernel: stream_collide, FX/kernel.cpp:1475-1780 */
-void luwo_stream_collide(const luwo_params* p, void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t,
-	float fx, float fy, float fz, float ox, float oy, float oz) {
+static void stream_collide_impl(const luwo_params* p, const luwo_thermal* th, void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t,
+	float fx, float fy, float fz, float ox, float oy, float oz, void* gi, float* T) {
 	const uint64_t N = cells(p);
 	const frame_t g = frame(p);
 	const int eq_on = (p->features&LUWO_EQUILIBRIUM_BOUNDARIES)!=0u;
@@ -292,6 +381,7 @@ void luwo_stream_collide(const luwo_params* p, void* fi, float* rho, float* u, c
 		else rho_u(f, &rhon, &uxn, &uyn, &uzn);
 		float fxn, fyn, fzn;
 		luw_force(p, &g, n, bo, u, 1, rhon, uxn, uyn, uzn, fx, fy, fz, ox, oy, oz, &fxn, &fyn, &fzn);
+		if(gi) thermal_step(p, th, &g, n, fl, bo, gi, T, t, uxn, uyn, uzn, fx, fy, fz, &fxn, &fyn, &fzn);
 		float Fin[Q];
 		if(p->features&LUWO_VOLUME_FORCE) {
 			const float rho2 = 0.5f/rhon;
@@ -327,10 +417,18 @@ void luwo_stream_collide(const luwo_params* p, void* fi, float* rho, float* u, c
 		store_f(p, n, f, fi, j, t);
 	}
 }
+void luwo_stream_collide(const luwo_params* p, void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t,
+	float fx, float fy, float fz, float ox, float oy, float oz) {
+	stream_collide_impl(p, 0, fi, rho, u, flags, t, fx, fy, fz, ox, oy, oz, 0, 0);
+}
+void luwo_stream_collide_thermal(const luwo_params* p, const luwo_thermal* th, void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t,
+	float fx, float fy, float fz, float ox, float oy, float oz, void* gi, float* T) {
+	stream_collide_impl(p, th, fi, rho, u, flags, t, fx, fy, fz, ox, oy, oz, gi, T);
+}
 
 /* ------------------------------------------------------------------ kernel: update_fields, FX/kernel.cpp:1938-2028 */
-void luwo_update_fields(const luwo_params* p, const void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t,
-	float fx, float fy, float fz, float ox, float oy, float oz) {
+static void update_fields_impl(const luwo_params* p, const luwo_thermal* th, const void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t,
+	float fx, float fy, float fz, float ox, float oy, float oz, const void* gi, float* T) {
 	const uint64_t N = cells(p);
 	const frame_t g = frame(p);
 	const int eq_on = (p->features&LUWO_EQUILIBRIUM_BOUNDARIES)!=0u;
@@ -348,6 +446,23 @@ void luwo_update_fields(const luwo_params* p, const void* fi, float* rho, float*
 		rho_u(f, &rhon, &uxn, &uyn, &uzn);
 		float fxn, fyn, fzn;
 		luw_force(p, &g, n, bo, u, 0, rhon, uxn, uyn, uzn, fx, fy, fz, ox, oy, oz, &fxn, &fyn, &fzn); /* no nudging/sponge in this kernel */
+		if(gi) { /* FX/kernel.cpp:1981-2000: T from the streamed-in g (no sponge, no collision), buoyancy */
+			uint64_t j7[7];
+			neighbors_temperature(p, n, j7);
+			float gh[7];
+			load_g(p, n, gh, gi, j7, t);
+			float Tn;
+			if(fl&TYPE_T) Tn = T[n];
+			else {
+				Tn = 0.0f;
+				for(int i=0; i<7; i++) Tn += gh[i];
+				Tn += 1.0f;
+				T[n] = Tn;
+			}
+			fxn -= fx*th->beta*(Tn-th->T_avg);
+			fyn -= fy*th->beta*(Tn-th->T_avg);
+			fzn -= fz*th->beta*(Tn-th->T_avg);
+		}
 		if(p->features&LUWO_VOLUME_FORCE) {
 			const float rho2 = 0.5f/rhon;
 			uxn = clampf(fmaf(fxn, rho2, uxn), -LAT_C, LAT_C);
@@ -358,6 +473,14 @@ void luwo_update_fields(const luwo_params* p, const void* fi, float* rho, float*
 		}
 		if(!(eq_on&&bo==TYPE_E)) { rho[n] = rhon; u[n] = uxn; u[N+n] = uyn; u[2u*N+n] = uzn; }
 	}
+}
+void luwo_update_fields(const luwo_params* p, const void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t,
+	float fx, float fy, float fz, float ox, float oy, float oz) {
+	update_fields_impl(p, 0, fi, rho, u, flags, t, fx, fy, fz, ox, oy, oz, 0, 0);
+}
+void luwo_update_fields_thermal(const luwo_params* p, const luwo_thermal* th, const void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t,
+	float fx, float fy, float fz, float ox, float oy, float oz, const void* gi, float* T) {
+	update_fields_impl(p, th, fi, rho, u, flags, t, fx, fy, fz, ox, oy, oz, gi, T);
 }
 
 /* ------------------------------------------------------------------ halo kernels, FX/kernel.cpp:2188-2297 */
@@ -446,6 +569,64 @@ void luwo_transfer_insert_rho_u_flags(const luwo_params* p, uint32_t d, const ch
 			rho[n] = ((const float*)buf)[a]; u[n] = ((const float*)buf)[A+a]; u[N+n] = ((const float*)buf)[2u*A+a]; u[2u*N+n] = ((const float*)buf)[3u*A+a];
 			flags[n] = ((const uint8_t*)buf)[16u*A+a];
 		}
+	}
+}
+
+/* thermal halos, FX/kernel.cpp:2337-2377: one g DDF per face cell and side (i = 2*direction+1 towards +, 2*direction+2 towards -), and the T field */
+void luwo_transfer_extract_gi(const luwo_params* p, uint32_t d, uint64_t t, void* buf_p, void* buf_m, const void* gi) {
+	const uint64_t A = area(p, d), N = cells(p);
+	const uint32_t L = d==0u ? p->Nx : d==1u ? p->Ny : p->Nz;
+	const int odd = (int)(t&1u);
+	PAR_FOR
+	for(int64_t aa=0; aa<(int64_t)A; aa++) {
+		const uint32_t a = (uint32_t)aa;
+		for(int side=0; side<2; side++) {
+			const uint64_t n = face_cell(p, d, a, side==0 ? L-2u : 1u);
+			uint64_t j7[7];
+			neighbors_temperature(p, n, j7);
+			const uint32_t i = 2u*d+(uint32_t)side+1u;
+			const uint64_t cell = (i&1u) ? j7[i] : n;
+			const uint32_t slot = odd ? ((i&1u) ? i+1u : i-1u) : i;
+			copy_ddf(p, side==0 ? buf_p : buf_m, a, gi, (uint64_t)slot*N+cell);
+		}
+	}
+}
+void luwo_transfer_insert_gi(const luwo_params* p, uint32_t d, uint64_t t, const void* buf_p, const void* buf_m, void* gi) {
+	const uint64_t A = area(p, d), N = cells(p);
+	const uint32_t L = d==0u ? p->Nx : d==1u ? p->Ny : p->Nz;
+	const int odd = (int)(t&1u);
+	PAR_FOR
+	for(int64_t aa=0; aa<(int64_t)A; aa++) {
+		const uint32_t a = (uint32_t)aa;
+		for(int side=0; side<2; side++) {
+			const uint64_t n = face_cell(p, d, a, side==0 ? L-1u : 0u);
+			uint64_t j7[7];
+			neighbors_temperature(p, n, j7);
+			const uint32_t i = 2u*d+(uint32_t)side+1u;
+			const uint64_t cell = (i&1u) ? n : j7[i-1u];
+			const uint32_t slot = odd ? i : ((i&1u) ? i+1u : i-1u);
+			copy_ddf(p, gi, (uint64_t)slot*N+cell, side==0 ? buf_p : buf_m, a);
+		}
+	}
+}
+void luwo_transfer_extract_T(const luwo_params* p, uint32_t d, float* buf_p, float* buf_m, const float* T) {
+	const uint64_t A = area(p, d);
+	const uint32_t L = d==0u ? p->Nx : d==1u ? p->Ny : p->Nz;
+	PAR_FOR
+	for(int64_t aa=0; aa<(int64_t)A; aa++) {
+		const uint32_t a = (uint32_t)aa;
+		buf_p[a] = T[face_cell(p, d, a, L-2u)];
+		buf_m[a] = T[face_cell(p, d, a, 1u)];
+	}
+}
+void luwo_transfer_insert_T(const luwo_params* p, uint32_t d, const float* buf_p, const float* buf_m, float* T) {
+	const uint64_t A = area(p, d);
+	const uint32_t L = d==0u ? p->Nx : d==1u ? p->Ny : p->Nz;
+	PAR_FOR
+	for(int64_t aa=0; aa<(int64_t)A; aa++) {
+		const uint32_t a = (uint32_t)aa;
+		T[face_cell(p, d, a, L-1u)] = buf_p[a];
+		T[face_cell(p, d, a, 0u)] = buf_m[a];
 	}
 }
 

@@ -3,7 +3,7 @@
  * This is a plain-C restatement of the algorithm in the reference's OpenCL-C device code
  * (FX = /root/reference/core/cfd_core/FluidX3D/src): FX/kernel.cpp:833-1113 (indexing, codecs, f_eq, rho/u, Guo forcing),
  * :1338-1351 (Esoteric-Pull load/store), :1370-1452 (initialize), :1475-1780 (stream_collide), :1938-2028 (update_fields),
- * :2188-2310 (halo extract/insert), :2495-2571 (vk_inlet_apply).
+ * :2188-2310 (halo extract/insert), :2495-2571 (vk_inlet_apply); thermal D3Q7: :1306-1336, :1639-1684, :1981-2000, :2337-2377.
  *
  * It is the CHECKER, never the product: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load it. The shipped CUDA path never links or calls anything in oracle/.
@@ -28,6 +28,7 @@ enum { /* compile-time switches of the reference (FX/defines.hpp:17-29) as run-t
 	LUWO_UPDATE_FIELDS = 1u, LUWO_VOLUME_FORCE = 2u, LUWO_EQUILIBRIUM_BOUNDARIES = 4u, LUWO_SUBGRID = 8u,
 	LUWO_BUFFER_NUDGING = 16u, LUWO_TOP_SPONGE = 32u
 };
+/* the TEMPERATURE extension is selected per call: the *_thermal entry points take the D3Q7 DDFs `gi` and the field `T` (TYPE_T = flag bit 0x04) */
 
 typedef struct luwo_params { /* per-domain constants, FX/lbm.cpp:612-783 */
 	uint32_t Nx, Ny, Nz; /* local lattice incl. halo layers */
@@ -40,6 +41,12 @@ typedef struct luwo_params { /* per-domain constants, FX/lbm.cpp:612-783 */
 	uint32_t buffer_N; float buffer_inv_tau; int32_t buffer_nudge_vertical;
 	uint32_t sponge_N; float sponge_inv_tau;
 } luwo_params;
+
+typedef struct luwo_thermal { /* FX/lbm.cpp:750-752 */
+	float w_T; /* def_w_T = 1/(2 alpha + 1/2) */
+	float beta; /* def_beta: thermal expansion coefficient (buoyancy = -f * beta * (T - T_avg); LUW passes f = 0) */
+	float T_avg; /* def_T_avg */
+} luwo_thermal;
 
 /* codecs (FX/kernel.cpp:864-875, FX/lbm.cpp:706-721) */
 float luwo_half_to_float(uint16_t h); /* IEEE binary16 -> binary32 */
@@ -61,6 +68,20 @@ void luwo_transfer_extract_rho_u_flags(const luwo_params* p, uint32_t direction,
 void luwo_transfer_insert_rho_u_flags(const luwo_params* p, uint32_t direction, const char* buf_p, const char* buf_m, float* rho, float* u, uint8_t* flags);
 void luwo_vk_inlet_apply(uint64_t N_cells, uint32_t use_interp, float t0, float t1, float alpha, uint64_t point_count, uint64_t mode_count, uint64_t mode_stride,
 	const uint64_t* point_cell, const uint8_t* point_face, const float* point_data, const float* mode_data, float* u);
+
+/* thermal D3Q7 extension (TEMPERATURE): FX/kernel.cpp:1306-1336 (g_eq, Esoteric-Pull load_g / store_g), :1442-1450 (initialize), :1639-1684 (the block inside
+ * stream_collide: T, sponge on T, SRT collision of g, buoyancy), :1981-2000 (update_fields), :2337-2377 (halos of gi and T). gi: 7 x N DDFs in the same
+ * storage type as fi; T: N floats. The momentum part of these entry points is the code of the plain ones. */
+void luwo_calculate_g_eq(float T, float ux, float uy, float uz, float* geq);
+void luwo_initialize_thermal(const luwo_params* p, void* fi, const float* rho, float* u, uint8_t* flags, void* gi, const float* T);
+void luwo_stream_collide_thermal(const luwo_params* p, const luwo_thermal* th, void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t,
+	float fx, float fy, float fz, float omega_x, float omega_y, float omega_z, void* gi, float* T);
+void luwo_update_fields_thermal(const luwo_params* p, const luwo_thermal* th, const void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t,
+	float fx, float fy, float fz, float omega_x, float omega_y, float omega_z, const void* gi, float* T);
+void luwo_transfer_extract_gi(const luwo_params* p, uint32_t direction, uint64_t t, void* buf_p, void* buf_m, const void* gi);
+void luwo_transfer_insert_gi(const luwo_params* p, uint32_t direction, uint64_t t, const void* buf_p, const void* buf_m, void* gi);
+void luwo_transfer_extract_T(const luwo_params* p, uint32_t direction, float* buf_p, float* buf_m, const float* T);
+void luwo_transfer_insert_T(const luwo_params* p, uint32_t direction, const float* buf_p, const float* buf_m, float* T);
 
 /* kernel voxelize_mesh, FX/kernel.cpp:2381-2471, for resting geometry (bbu[10..15] == 0, the only way LUW calls it: FX/setup.cpp passes no velocities):
  * one ray per column of the face normal to `direction`, Moeller-Trumbore against all triangles, up to 64 sorted crossings, inside/outside walk along the

@@ -18,6 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 FP32, FP16S, FP16C = 0, 1, 2
 PREC_NAME = {FP32: "fp32", FP16S: "fp16s", FP16C: "fp16c"}
 UPDATE_FIELDS, VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, SUBGRID, BUFFER_NUDGING, TOP_SPONGE = 1, 2, 4, 8, 16, 32
+TEMPERATURE = 64  # thermal D3Q7: selects the *_thermal entry points (the C oracle takes gi / T per call and ignores the bit)
 FEATURE_SETS = {  # must match oracle/Makefile
     "bench": 0,
     "chan": EQUILIBRIUM_BOUNDARIES,
@@ -25,8 +26,15 @@ FEATURE_SETS = {  # must match oracle/Makefile
     "core": UPDATE_FIELDS | VOLUME_FORCE | EQUILIBRIUM_BOUNDARIES | SUBGRID,
     "luw": UPDATE_FIELDS | VOLUME_FORCE | EQUILIBRIUM_BOUNDARIES | SUBGRID | BUFFER_NUDGING | TOP_SPONGE,
     "luwnf": VOLUME_FORCE | EQUILIBRIUM_BOUNDARIES | SUBGRID | BUFFER_NUDGING | TOP_SPONGE,
+    "luwT": UPDATE_FIELDS | VOLUME_FORCE | EQUILIBRIUM_BOUNDARIES | SUBGRID | BUFFER_NUDGING | TOP_SPONGE | TEMPERATURE,
+    "chanT": VOLUME_FORCE | EQUILIBRIUM_BOUNDARIES | TEMPERATURE,
 }
-TYPE_S, TYPE_E = 0x01, 0x02
+TYPE_S, TYPE_E, TYPE_T = 0x01, 0x02, 0x04
+
+
+class Thermal(C.Structure):
+    """luwo_thermal -- def_w_T, def_beta, def_T_avg (FX/lbm.cpp:750-752)."""
+    _fields_ = [("w_T", C.c_float), ("beta", C.c_float), ("T_avg", C.c_float)]
 
 
 class Params(C.Structure):
@@ -100,6 +108,16 @@ class Oracle:
         L.luwo_vk_inlet_apply.argtypes = [C.c_uint64, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_uint64, C.c_uint64, C.c_uint64] + [C.c_void_p] * 5
         L.luwo_set_threads.argtypes = [C.c_int]
         L.luwo_get_threads.restype = C.c_int
+        PT = C.POINTER(Thermal)
+        L.luwo_calculate_g_eq.argtypes = [C.c_float] * 4 + [C.c_void_p]
+        L.luwo_initialize_thermal.argtypes = [PP] + [C.c_void_p] * 6
+        L.luwo_stream_collide_thermal.argtypes = [PP, PT] + [C.c_void_p] * 4 + [C.c_uint64] + f6 + [C.c_void_p] * 2
+        L.luwo_update_fields_thermal.argtypes = [PP, PT] + [C.c_void_p] * 4 + [C.c_uint64] + f6 + [C.c_void_p] * 2
+        L.luwo_transfer_extract_gi.argtypes = [PP, C.c_uint32, C.c_uint64] + [C.c_void_p] * 3
+        L.luwo_transfer_insert_gi.argtypes = [PP, C.c_uint32, C.c_uint64] + [C.c_void_p] * 3
+        L.luwo_transfer_extract_T.argtypes = [PP, C.c_uint32] + [C.c_void_p] * 3
+        L.luwo_transfer_insert_T.argtypes = [PP, C.c_uint32] + [C.c_void_p] * 3
+        self.th = Thermal(1.0, 0.0, 1.0)
 
     def set_threads(self, n):
         self.lib.luwo_set_threads(int(n))
@@ -142,6 +160,36 @@ class Oracle:
 
     def insert_rho_u_flags(self, direction, bp, bm, rho, u, flags):
         self.lib.luwo_transfer_insert_rho_u_flags(C.byref(self.p), direction, _p(bp), _p(bm), _p(rho), _p(u), _p(flags))
+
+    # thermal D3Q7 (gi: 7*N DDFs in the storage type of fi, T: N floats)
+    def set_thermal(self, w_T, beta=0.0, T_avg=1.0):
+        self.th = Thermal(np.float32(w_T), np.float32(beta), np.float32(T_avg))
+
+    def g_eq(self, T, ux, uy, uz):
+        out = np.zeros(7, np.float32)
+        self.lib.luwo_calculate_g_eq(float(T), float(ux), float(uy), float(uz), _p(out))
+        return out
+
+    def initialize_thermal(self, fi, rho, u, flags, gi, T):
+        self.lib.luwo_initialize_thermal(C.byref(self.p), _p(fi), _p(rho), _p(u), _p(flags), _p(gi), _p(T))
+
+    def stream_collide_thermal(self, fi, rho, u, flags, t, f, omega, gi, T):
+        self.lib.luwo_stream_collide_thermal(C.byref(self.p), C.byref(self.th), _p(fi), _p(rho), _p(u), _p(flags), int(t), *map(float, f), *map(float, omega), _p(gi), _p(T))
+
+    def update_fields_thermal(self, fi, rho, u, flags, t, f, omega, gi, T):
+        self.lib.luwo_update_fields_thermal(C.byref(self.p), C.byref(self.th), _p(fi), _p(rho), _p(u), _p(flags), int(t), *map(float, f), *map(float, omega), _p(gi), _p(T))
+
+    def extract_gi(self, direction, t, bp, bm, gi):
+        self.lib.luwo_transfer_extract_gi(C.byref(self.p), direction, int(t), _p(bp), _p(bm), _p(gi))
+
+    def insert_gi(self, direction, t, bp, bm, gi):
+        self.lib.luwo_transfer_insert_gi(C.byref(self.p), direction, int(t), _p(bp), _p(bm), _p(gi))
+
+    def extract_T(self, direction, bp, bm, T):
+        self.lib.luwo_transfer_extract_T(C.byref(self.p), direction, _p(bp), _p(bm), _p(T))
+
+    def insert_T(self, direction, bp, bm, T):
+        self.lib.luwo_transfer_insert_T(C.byref(self.p), direction, _p(bp), _p(bm), _p(T))
 
     def voxelize_mesh(self, direction, u, flags, flag, p0, p1, p2, bbu):
         self.lib.luwo_voxelize_mesh.restype = None
@@ -205,9 +253,17 @@ class Reference:
         assert L.luwref_sizeof_fpxx() == (4 if precision == FP32 else 2)
         f6 = [C.c_float] * 6
         L.luwref_set_params.argtypes = [C.POINTER(_RefParams)]
-        L.luwref_initialize.argtypes = [C.c_void_p] * 4
-        L.luwref_stream_collide.argtypes = [C.c_void_p] * 4 + [C.c_uint64] + f6
-        L.luwref_update_fields.argtypes = [C.c_void_p] * 4 + [C.c_uint64] + f6
+        if FEATURE_SETS[feature_set] & TEMPERATURE:  # built with -DTEMPERATURE: the kernels carry gi / T as trailing arguments
+            L.luwref_set_thermal.argtypes = [C.c_float] * 3
+            L.luwref_initialize_thermal.argtypes = [C.c_void_p] * 6
+            L.luwref_stream_collide_thermal.argtypes = [C.c_void_p] * 4 + [C.c_uint64] + f6 + [C.c_void_p] * 2
+            L.luwref_update_fields_thermal.argtypes = [C.c_void_p] * 4 + [C.c_uint64] + f6 + [C.c_void_p] * 2
+            for name in ("luwref_transfer_extract_gi", "luwref_transfer_insert_gi", "luwref_transfer_extract_T", "luwref_transfer_insert_T"):
+                getattr(L, name).argtypes = [C.c_uint32, C.c_uint64] + [C.c_void_p] * 3
+        else:
+            L.luwref_initialize.argtypes = [C.c_void_p] * 4
+            L.luwref_stream_collide.argtypes = [C.c_void_p] * 4 + [C.c_uint64] + f6
+            L.luwref_update_fields.argtypes = [C.c_void_p] * 4 + [C.c_uint64] + f6
         L.luwref_transfer_extract_fi.argtypes = [C.c_uint32, C.c_uint64] + [C.c_void_p] * 3
         L.luwref_transfer_insert_fi.argtypes = [C.c_uint32, C.c_uint64] + [C.c_void_p] * 3
         L.luwref_transfer_extract_rho_u_flags.argtypes = [C.c_uint32, C.c_uint64] + [C.c_void_p] * 5
@@ -256,6 +312,30 @@ class Reference:
 
     def insert_rho_u_flags(self, direction, bp, bm, rho, u, flags):
         self.lib.luwref_transfer_insert_rho_u_flags(direction, 0, _p(bp), _p(bm), _p(rho), _p(u), _p(flags))
+
+    def set_thermal(self, w_T, beta=0.0, T_avg=1.0):
+        self.lib.luwref_set_thermal(float(np.float32(w_T)), float(np.float32(beta)), float(np.float32(T_avg)))
+
+    def initialize_thermal(self, fi, rho, u, flags, gi, T):
+        self.lib.luwref_initialize_thermal(_p(fi), _p(rho), _p(u), _p(flags), _p(gi), _p(T))
+
+    def stream_collide_thermal(self, fi, rho, u, flags, t, f, omega, gi, T):
+        self.lib.luwref_stream_collide_thermal(_p(fi), _p(rho), _p(u), _p(flags), int(t), *map(float, f), *map(float, omega), _p(gi), _p(T))
+
+    def update_fields_thermal(self, fi, rho, u, flags, t, f, omega, gi, T):
+        self.lib.luwref_update_fields_thermal(_p(fi), _p(rho), _p(u), _p(flags), int(t), *map(float, f), *map(float, omega), _p(gi), _p(T))
+
+    def extract_gi(self, direction, t, bp, bm, gi):
+        self.lib.luwref_transfer_extract_gi(direction, int(t), _p(bp), _p(bm), _p(gi))
+
+    def insert_gi(self, direction, t, bp, bm, gi):
+        self.lib.luwref_transfer_insert_gi(direction, int(t), _p(bp), _p(bm), _p(gi))
+
+    def extract_T(self, direction, bp, bm, T):
+        self.lib.luwref_transfer_extract_T(direction, 0, _p(bp), _p(bm), _p(T))
+
+    def insert_T(self, direction, bp, bm, T):
+        self.lib.luwref_transfer_insert_T(direction, 0, _p(bp), _p(bm), _p(T))
 
     def voxelize_mesh(self, direction, u, flags, flag, p0, p1, p2, bbu, t=1):
         fi = np.zeros(19 * self.p.N, ddf_dtype(self.precision))  # only touched for moving geometry

@@ -63,11 +63,15 @@ uint32_t luwref_features() { // which compile-time switches this shared object w
 #ifdef TOP_SPONGE
 	f |= 32u;
 #endif
+#ifdef TEMPERATURE
+	f |= 64u;
+#endif
 	return f;
 }
 
 #define NDRANGE(count, call) { const long long cnt_ = (long long)(count); _Pragma("omp parallel for schedule(static)") for(long long i_=0; i_<cnt_; i_++) { cl_gid = (ulong)i_; call; } }
 
+#ifndef TEMPERATURE
 void luwref_initialize(fpxx* fi, const float* rho, float* u, uchar* flags) {
 	NDRANGE(g_N, refcl::initialize(fi, rho, u, flags));
 }
@@ -77,6 +81,18 @@ void luwref_stream_collide(fpxx* fi, float* rho, float* u, uchar* flags, const u
 void luwref_update_fields(const fpxx* fi, float* rho, float* u, const uchar* flags, const ulong t, const float fx, const float fy, const float fz, const float ox, const float oy, const float oz) {
 	NDRANGE(g_N, refcl::update_fields(fi, rho, u, flags, t, fx, fy, fz, ox, oy, oz));
 }
+#else // TEMPERATURE: the same kernels take the D3Q7 DDFs and the temperature field as trailing arguments (FX/kernel.cpp:1374-1376, 1482-1484, 1942-1944)
+void luwref_set_thermal(const float w_T, const float beta, const float T_avg) { g_w_T = w_T; g_beta = beta; g_T_avg = T_avg; } // def_w_T, def_beta, def_T_avg (FX/lbm.cpp:750-752)
+void luwref_initialize_thermal(fpxx* fi, const float* rho, float* u, uchar* flags, fpxx* gi, const float* T) {
+	NDRANGE(g_N, refcl::initialize(fi, rho, u, flags, gi, T));
+}
+void luwref_stream_collide_thermal(fpxx* fi, float* rho, float* u, uchar* flags, const ulong t, const float fx, const float fy, const float fz, const float ox, const float oy, const float oz, fpxx* gi, float* T) {
+	NDRANGE(g_N, refcl::stream_collide(fi, rho, u, flags, t, fx, fy, fz, ox, oy, oz, gi, T));
+}
+void luwref_update_fields_thermal(const fpxx* fi, float* rho, float* u, const uchar* flags, const ulong t, const float fx, const float fy, const float fz, const float ox, const float oy, const float oz, const fpxx* gi, float* T) {
+	NDRANGE(g_N, refcl::update_fields(fi, rho, u, flags, t, fx, fy, fz, ox, oy, oz, gi, T));
+}
+#endif
 static ulong area(const uint direction) { const ulong A[3] = {(ulong)g_Ny*g_Nz, (ulong)g_Nz*g_Nx, (ulong)g_Nx*g_Ny}; return A[direction]; }
 void luwref_transfer_extract_fi(const uint direction, const ulong t, fpxx_copy* bp, fpxx_copy* bm, const fpxx_copy* fi) {
 	NDRANGE(area(direction), refcl::transfer_extract_fi(direction, t, bp, bm, fi));
@@ -90,6 +106,20 @@ void luwref_transfer_extract_rho_u_flags(const uint direction, const ulong t, ch
 void luwref_transfer_insert_rho_u_flags(const uint direction, const ulong t, const char* bp, const char* bm, float* rho, float* u, uchar* flags) {
 	NDRANGE(area(direction), refcl::transfer__insert_rho_u_flags(direction, t, bp, bm, rho, u, flags));
 }
+#ifdef TEMPERATURE
+void luwref_transfer_extract_gi(const uint direction, const ulong t, fpxx_copy* bp, fpxx_copy* bm, const fpxx_copy* gi) {
+	NDRANGE(area(direction), refcl::transfer_extract_gi(direction, t, bp, bm, gi));
+}
+void luwref_transfer_insert_gi(const uint direction, const ulong t, const fpxx_copy* bp, const fpxx_copy* bm, fpxx_copy* gi) {
+	NDRANGE(area(direction), refcl::transfer__insert_gi(direction, t, bp, bm, gi));
+}
+void luwref_transfer_extract_T(const uint direction, const ulong t, float* bp, float* bm, const float* T) {
+	NDRANGE(area(direction), refcl::transfer_extract_T(direction, t, bp, bm, T));
+}
+void luwref_transfer_insert_T(const uint direction, const ulong t, const float* bp, const float* bm, float* T) {
+	NDRANGE(area(direction), refcl::transfer__insert_T(direction, t, bp, bm, T));
+}
+#endif
 void luwref_vk_inlet_apply(const uint use_interp, const float t0, const float t1, const float alpha, const ulong point_count, const ulong mode_count, const ulong mode_stride,
 	const ulong* point_cell, const uchar* point_face, const float* point_data, const float* mode_data, float* u) {
 	NDRANGE(point_count, refcl::vk_inlet_apply(use_interp, t0, t1, alpha, point_count, mode_count, mode_stride, point_cell, point_face, point_data, mode_data, u));

@@ -34,6 +34,8 @@ def main():
     tiny = {}
     for precision in (O.FP32, O.FP16S, O.FP16C):
         for fset in O.FEATURE_SETS:
+            if O.FEATURE_SETS[fset] & O.TEMPERATURE:
+                continue  # thermal sets: make_golden_thermal.py
             ref = O.Reference(precision, fset)
             fi, rho, u = H.golden_run(ref, O, precision, fset)
             out["cases"][f"{O.PREC_NAME[precision]}_{fset}"] = {"fi": sha(fi), "rho": sha(rho), "u": sha(u)}

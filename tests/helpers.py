@@ -3,7 +3,8 @@ import numpy as np
 
 from latticeurbanwind_b200 import cases
 
-FEATURE_SETS = {"bench": 0, "chan": 4, "plain": 1 | 4, "core": 1 | 2 | 4 | 8, "luw": 1 | 2 | 4 | 8 | 16 | 32, "luwnf": 2 | 4 | 8 | 16 | 32}
+FEATURE_SETS = {"bench": 0, "chan": 4, "plain": 1 | 4, "core": 1 | 2 | 4 | 8, "luw": 1 | 2 | 4 | 8 | 16 | 32, "luwnf": 2 | 4 | 8 | 16 | 32,
+                "luwT": 1 | 2 | 4 | 8 | 16 | 32 | 64, "chanT": 2 | 4 | 64}
 FORCE = (1e-6, 0.0, -2e-6)
 OMEGA = (0.0, 5.6e-6, 4.7e-6)
 ZONES = dict(downstream_face=2, buffer_N=6, buffer_inv_tau=0.01, buffer_nudge_vertical=1, sponge_N=8, sponge_inv_tau=0.02)
@@ -240,3 +241,74 @@ def vox_bbu(ntri, pmin, pmax):
     bbu[1:4] = pmin - np.float32(2.0)
     bbu[4:7] = pmax + np.float32(2.0)
     return bbu
+
+
+# ---------------------------------------------------------------------------------------------- thermal D3Q7 (FX/kernel.cpp:1306-1336,1639-1684)
+THERMAL = dict(w_T=1.0 / (2.0 * 2.0e-3 + 0.5), beta=0.4, T_avg=1.0)  # def_w_T = 1/(2 alpha + 1/2), FX/lbm.cpp:750
+THERMAL_SHAPE, THERMAL_STEPS = (20, 18, 14), 8
+
+
+def thermal_case(shape=THERMAL_SHAPE, seed=77):
+    """The urban case plus a temperature field: every TYPE_E cell also carries TYPE_T (what the case driver does for a WRF deck with a T column,
+    FX/setup.cpp:5268-5317 -- and what makes the T sponge's read of the top row independent of the work-item order), a few interior fluid cells are
+    heated TYPE_T sources, the rest starts from a stratified profile with seeded noise."""
+    Nx, Ny, Nz = shape
+    flags, rho, u = cases.urban(Nx, Ny, Nz, seed=seed, edge=3, pitch=6)
+    flags = flags.copy()
+    flags[(flags & 0x03) == 0x02] |= 0x04
+    rng = np.random.default_rng(seed)
+    z = (np.arange(Nx * Ny * Nz) // (Nx * Ny)).astype(np.float32)
+    T = (np.float32(1.0) + np.float32(0.02) * z / np.float32(Nz) + np.float32(1e-3) * rng.standard_normal(Nx * Ny * Nz).astype(np.float32)).astype(np.float32)
+    fluid = np.flatnonzero(flags == 0)
+    hot = fluid[rng.choice(fluid.size, size=max(4, fluid.size // 200), replace=False)]
+    flags[hot] |= 0x04
+    T[hot] = np.float32(1.05)
+    return flags, rho, u, T
+
+
+def run_cpu_thermal(engine, O, shape, precision, features, flags, rho, u, T, steps, w, f=FORCE, omega=OMEGA, zones=ZONES, thermal=THERMAL,
+                    update_at_end=False, D=(1, 1, 1), Ov=(0, 0, 0)):
+    """Like run_cpu with the TEMPERATURE extension: returns (fi, rho, u, gi, T)."""
+    Nx, Ny, Nz = shape
+    p = O.make_params(Nx, Ny, Nz, precision, features, w=w, D=D, O=Ov, **zones)
+    fi, gi = np.zeros(19 * p.N, O.ddf_dtype(precision)), np.zeros(7 * p.N, O.ddf_dtype(precision))
+    flags, rho, u, T = flags.copy(), rho.copy(), u.copy(), T.copy()
+    engine.bind(p)
+    engine.set_thermal(**thermal)
+    engine.initialize_thermal(fi, rho, u, flags, gi, T)
+    for t in range(steps):
+        engine.stream_collide_thermal(fi, rho, u, flags, t, f, omega, gi, T)
+    if update_at_end:
+        engine.update_fields_thermal(fi, rho, u, flags, steps, f, omega, gi, T)
+    return fi, rho, u, gi, T
+
+
+def golden_thermal_halo(engine, O, precision):
+    """Block (0,0,0) of a 2x2x2 decomposition of the thermal case: 3 steps with the gi / T halo payloads at both slot parities (exchanged with itself)."""
+    flags, rho, u, T = thermal_case(GOLDEN_SHAPE)
+    Ncell = int(np.prod(GOLDEN_SHAPE))
+    shape, Ov, fl, rh, ul = cut_block(GOLDEN_SHAPE, (2, 2, 2), (0, 0, 0), flags, rho, u)
+    Tl = cut_block(GOLDEN_SHAPE, (2, 2, 2), (0, 0, 0), flags, T, np.zeros(3 * Ncell, np.float32))[3]
+    p = halo_params(O, precision, O.FEATURE_SETS["luwT"])
+    fi, gi = np.zeros(19 * p.N, O.ddf_dtype(precision)), np.zeros(7 * p.N, O.ddf_dtype(precision))
+    engine.bind(p)
+    engine.set_thermal(**THERMAL)
+    engine.initialize_thermal(fi, rh, ul, fl, gi, Tl)
+    out, name = {}, O.PREC_NAME[precision]
+    for t in range(3):
+        engine.stream_collide_thermal(fi, rh, ul, fl, t, FORCE, OMEGA, gi, Tl)
+        for axis in range(3):
+            A = (p.Ny * p.Nz, p.Nz * p.Nx, p.Nx * p.Ny)[axis]
+            bp, bm = np.zeros(A, gi.dtype), np.zeros(A, gi.dtype)
+            engine.extract_gi(axis, t, bp, bm, gi)
+            out[f"thalo_{name}_t{t}_axis{axis}_p"], out[f"thalo_{name}_t{t}_axis{axis}_m"] = bp.copy(), bm.copy()
+            engine.insert_gi(axis, t, bm, bp, gi)
+        out[f"thalo_{name}_t{t}_gi"] = gi.copy()
+    for axis in range(3):
+        A = (p.Ny * p.Nz, p.Nz * p.Nx, p.Nx * p.Ny)[axis]
+        bp, bm = np.zeros(A, np.float32), np.zeros(A, np.float32)
+        engine.extract_T(axis, bp, bm, Tl)
+        out[f"thalo_{name}_T_axis{axis}_p"], out[f"thalo_{name}_T_axis{axis}_m"] = bp.copy(), bm.copy()
+        engine.insert_T(axis, bm, bp, Tl)
+    out[f"thalo_{name}_T"] = Tl.copy()
+    return out
