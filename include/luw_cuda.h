@@ -40,16 +40,17 @@ enum { LUW_FP32 = 0, LUW_FP16S = 1, LUW_FP16C = 2 };
 /* extension switches: compile-time in the reference (FX/defines.hpp:17-29; BUFFER_NUDGING / TOP_SPONGE FX/lbm.cpp:770-782) */
 enum {
 	LUW_UPDATE_FIELDS = 1u, LUW_VOLUME_FORCE = 2u, LUW_EQUILIBRIUM_BOUNDARIES = 4u, LUW_SUBGRID = 8u,
-	LUW_BUFFER_NUDGING = 16u, LUW_TOP_SPONGE = 32u
+	LUW_BUFFER_NUDGING = 16u, LUW_TOP_SPONGE = 32u,
+	LUW_TEMPERATURE = 64u /* thermal D3Q7 transport (FX/defines.hpp:23): allocates gi (7 fpxx per cell) and T (1 float per cell), see luw_thermal_params */
 };
 /* arithmetic policy of the step kernels */
 enum {
 	LUW_ARITH_STRICT = 0, /* "as written": fused only where the reference writes fma(), IEEE div/sqrt -> bit-identical to oracle/ */
 	LUW_ARITH_FAST = 1 /* mul+add contraction and approximate reciprocals allowed (what -cl-mad-enable licenses, FX/opencl.hpp:305) */
 };
-enum { LUW_FIELD_RHO = 0, LUW_FIELD_U = 1, LUW_FIELD_FLAGS = 2, LUW_FIELD_FI = 3 };
-/* halo payloads: enum_transfer_field of FX/lbm.hpp:24 (fi: 5 DDFs per face cell; rho_u_flags: 17 bytes per face cell) */
-enum { LUW_HALO_FI = 0, LUW_HALO_RHO_U_FLAGS = 1 };
+enum { LUW_FIELD_RHO = 0, LUW_FIELD_U = 1, LUW_FIELD_FLAGS = 2, LUW_FIELD_FI = 3, LUW_FIELD_T = 4, LUW_FIELD_GI = 5 /* T[n], gi[i*N+n] i = 0..6: LUW_TEMPERATURE domains */ };
+/* halo payloads: enum_transfer_field of FX/lbm.hpp:24 (fi: 5 DDFs per face cell; rho_u_flags: 17 bytes per face cell; gi: 1 DDF per face cell; T: 1 float) */
+enum { LUW_HALO_FI = 0, LUW_HALO_RHO_U_FLAGS = 1, LUW_HALO_GI = 2, LUW_HALO_T = 3 };
 
 typedef struct luw_device_info { /* subset of Device_Info, FX/opencl.hpp:89-188, used by device selection and the info printout */
 	char name[256];
@@ -97,6 +98,15 @@ int luw_domain_step_kernel(const luw_domain* dom, int* tiled);
 int luw_upload(luw_domain* dom, int field, const void* host_src, uint64_t offset, uint64_t count);
 int luw_download(luw_domain* dom, int field, void* host_dst, uint64_t offset, uint64_t count);
 int luw_device_ptr(luw_domain* dom, int field, void** dev_ptr); /* raw device pointer of a field (pitched rows, see above) */
+
+/* Thermal D3Q7 extension. A domain created with LUW_TEMPERATURE runs the reference's TEMPERATURE blocks inside initialize /
+ * stream_collide / update_fields (FX/kernel.cpp:1306-1336, 1442-1450, 1639-1684, 1981-2000): cells flagged TYPE_T (0x04) hold their preset T, every other
+ * fluid cell transports T with a D3Q7 SRT collision at rate w_T, relaxes it towards the top row inside the TOP_SPONGE zone, and (VOLUME_FORCE) feels the
+ * buoyancy -f*beta*(T-T_avg). Constants: def_w_T = 1/(2 alpha + 1/2), def_beta, def_T_avg of FX/lbm.cpp:750-752 (LBM ctor arguments alpha, beta;
+ * T_avg = 1). Defaults w_T = 1, beta = 0, T_avg = 1. T starts at 1 like Memory<float>(N, 1, .., 1.0f) (FX/lbm.cpp:323); upload it before luw_initialize.
+ * Decomposed runs exchange LUW_HALO_GI after LUW_HALO_FI every step and LUW_HALO_T + LUW_HALO_GI at the end of initialisation (FX/lbm.cpp LBM::initialize /
+ * do_time_step); luw_run_steps_multi does the per-step part. These domains use the one-cell-per-thread step kernel (luw_domain_step_kernel reports 0). */
+int luw_thermal_params(luw_domain* dom, float w_T, float beta, float T_avg);
 
 /* kernel "initialize", FX/kernel.cpp:1370-1452, enqueued by LBM_Domain::enqueue_initialize FX/lbm.cpp:340-343 (slot parity t=1 baked in) */
 int luw_initialize(luw_domain* dom);

@@ -12,9 +12,10 @@ LIB_PATH = os.environ.get("LUW_CUDA_LIB") or os.path.join(HERE, "lib", "libluw_c
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_OOM, ERR_CUDA = 0, 1, 2, 3, 4
 FP32, FP16S, FP16C = 0, 1, 2
 UPDATE_FIELDS, VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, SUBGRID, BUFFER_NUDGING, TOP_SPONGE = 1, 2, 4, 8, 16, 32
+TEMPERATURE = 64
 ARITH_STRICT, ARITH_FAST = 0, 1
-FIELD_RHO, FIELD_U, FIELD_FLAGS, FIELD_FI = 0, 1, 2, 3
-HALO_FI, HALO_RHO_U_FLAGS = 0, 1
+FIELD_RHO, FIELD_U, FIELD_FLAGS, FIELD_FI, FIELD_T, FIELD_GI = 0, 1, 2, 3, 4, 5
+HALO_FI, HALO_RHO_U_FLAGS, HALO_GI, HALO_T = 0, 1, 2, 3
 
 
 class LuwError(RuntimeError):
@@ -47,6 +48,7 @@ EXPORTS = {  # name -> argtypes; every symbol include/luw_cuda.h declares
     "luw_upload": [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64],
     "luw_download": [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64],
     "luw_device_ptr": [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)],
+    "luw_thermal_params": [C.c_void_p, C.c_float, C.c_float, C.c_float],
     "luw_initialize": [C.c_void_p],
     "luw_stream_collide": [C.c_void_p, C.c_uint64] + [C.c_float] * 6,
     "luw_update_fields": [C.c_void_p, C.c_uint64] + [C.c_float] * 6,

@@ -11,10 +11,11 @@ namespace luw {
 
 constexpr int Q = 19;
 constexpr uint32_t TYPE_S = 0x01u, TYPE_E = 0x02u, TYPE_BO = 0x03u, TYPE_G = 0x20u, TYPE_SU = 0x38u; // FX/defines.hpp:50-57, FX/lbm.cpp:689-694
+constexpr uint32_t TYPE_T = 0x04u; // temperature boundary, FX/defines.hpp:52
 constexpr float LAT_C = 0.57735027f; // def_c, FX/lbm.cpp:662
 constexpr float W0 = 1.0f/3.0f, WS = 1.0f/18.0f, WE = 1.0f/36.0f; // FX/lbm.cpp:672-674
 
-enum : uint32_t { F_UPDATE_FIELDS = 1u, F_VOLUME_FORCE = 2u, F_EQUILIBRIUM = 4u, F_SUBGRID = 8u, F_NUDGING = 16u, F_SPONGE = 32u };
+enum : uint32_t { F_UPDATE_FIELDS = 1u, F_VOLUME_FORCE = 2u, F_EQUILIBRIUM = 4u, F_SUBGRID = 8u, F_NUDGING = 16u, F_SPONGE = 32u, F_TEMPERATURE = 64u };
 enum : int { P_FP32 = 0, P_FP16S = 1, P_FP16C = 2 };
 
 struct DomainConst { // the def_* constants of FX/lbm.cpp:612-783 as kernel parameters
@@ -37,6 +38,9 @@ struct DomainConst { // the def_* constants of FX/lbm.cpp:612-783 as kernel para
 	const float* sigma; // [sponge_N] inv_tau*sin^2 ramp by depth (FX/kernel.cpp:1603-1605)
 	void* fi; float* rho; float* u; uint8_t* flags;
 	uint32_t* sched; // strip counter of the tiled step (zeroed in-stream before every launch)
+	// thermal D3Q7 extension (F_TEMPERATURE; FX/lbm.cpp:322-323, 750-752): 7 x N DDFs in the storage type of fi, N floats, def_w_T / def_beta / def_T_avg
+	void* gi; float* T;
+	float w_T, beta, T_avg;
 };
 struct StepArgs { uint64_t t; float fx, fy, fz, ox, oy, oz; }; // per-step kernel arguments, FX/lbm.cpp:345
 

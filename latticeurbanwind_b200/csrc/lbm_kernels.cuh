@@ -182,6 +182,212 @@ template<bool INSERT> __global__ void __launch_bounds__(128) k_halo_rho_u_flags(
 	else halo_ruf_cell<INSERT>(c, d, A, xfast, t, blockIdx.y, blockIdx.y==0u ? buf_p : buf_m);
 }
 
+// ================================================================== thermal D3Q7 extension (TEMPERATURE), SURVEY.md 8-f4
+// Correctness-first form: the one-cell-per-thread kernels with the reference's TEMPERATURE blocks fused in (the temperature collision needs the cell's velocity
+// BEFORE the force half-step, which is never stored, so the g update has to live inside the momentum kernel: FX/kernel.cpp:1639-1684). The first seven
+// entries of the D3Q19 neighbour list are exactly neighbors_temperature()'s j7 (FX/kernel.cpp:1307-1314).
+__device__ __forceinline__ void g_eq(const float T, const float ux, const float uy, const float uz, float* geq) { // FX/kernel.cpp:1315-1321
+	const float wsT4 = 0.5f*T, wsTm1 = 0.125f*(T-1.0f);
+	geq[0] = fmaf(0.25f, T, -0.25f);
+	geq[1] = fmaf(wsT4, ux, wsTm1); geq[2] = fmaf(wsT4, -ux, wsTm1);
+	geq[3] = fmaf(wsT4, uy, wsTm1); geq[4] = fmaf(wsT4, -uy, wsTm1);
+	geq[5] = fmaf(wsT4, uz, wsTm1); geq[6] = fmaf(wsT4, -uz, wsTm1);
+}
+template<int P> __device__ __forceinline__ void load_g(const typename Ddf<P>::T* gi, const uint64_t N, const uint64_t* j, const uint32_t odd, float* g) { // FX/kernel.cpp:1322-1328
+	g[0] = Ddf<P>::dec(gi[j[0]]);
+#pragma unroll
+	for(uint32_t i=1u; i<7u; i+=2u) {
+		g[i   ] = Ddf<P>::dec(gi[(uint64_t)(odd ? i    : i+1u)*N+j[0]]);
+		g[i+1u] = Ddf<P>::dec(gi[(uint64_t)(odd ? i+1u : i   )*N+j[i]]);
+	}
+}
+template<int P> __device__ __forceinline__ void store_g(typename Ddf<P>::T* gi, const uint64_t N, const uint64_t* j, const uint32_t odd, const float* g) { // FX/kernel.cpp:1329-1335
+	gi[j[0]] = Ddf<P>::enc(g[0]);
+#pragma unroll
+	for(uint32_t i=1u; i<7u; i+=2u) {
+		gi[(uint64_t)(odd ? i+1u : i   )*N+j[i]] = Ddf<P>::enc(g[i   ]);
+		gi[(uint64_t)(odd ? i    : i+1u)*N+j[0]] = Ddf<P>::enc(g[i+1u]);
+	}
+}
+// temperature of the cell from the streamed-in g (or the preset of a TYPE_T cell)
+__device__ __forceinline__ float temperature_of(const DomainConst& c, const uint64_t n, const bool is_t, const float* g) {
+	if(is_t) return c.T[n];
+	float Tn = 0.0f;
+#pragma unroll
+	for(int i=0; i<7; i++) Tn += g[i];
+	return Tn+1.0f; // 1 is added last (DDF shifting)
+}
+// stream_collide with the TEMPERATURE block: collide_cell's sequence (kept textually parallel to it) with the g update between the force assembly and
+// the force half-step. Returns the post-collision f; g is streamed out here.
+template<int P, uint32_t FEAT> __device__ __forceinline__ void collide_cell_thermal(const DomainConst& c, const StepArgs& a, const uint64_t* j,
+	const uint32_t x, const uint32_t y, const uint32_t z, const uint32_t fl, const uint32_t odd, float* f) {
+	typedef typename Ddf<P>::T S;
+	constexpr bool UF = (FEAT&F_UPDATE_FIELDS)!=0u, VF = (FEAT&F_VOLUME_FORCE)!=0u, EQ = (FEAT&F_EQUILIBRIUM)!=0u, SG = (FEAT&F_SUBGRID)!=0u;
+	const uint64_t n = j[0];
+	const uint32_t bo = fl&TYPE_BO;
+	const bool is_e = EQ&&bo==TYPE_E, is_t = (fl&TYPE_T)!=0u;
+	float rhon, uxn, uyn, uzn;
+	if(is_e) { rhon = c.rho[n]; uxn = c.u[n]; uyn = c.u[c.N+n]; uzn = c.u[2ull*c.N+n]; }
+	else rho_u(f, rhon, uxn, uyn, uzn);
+	// ---- TEMPERATURE block, FX/kernel.cpp:1639-1684
+	float g[7];
+	load_g<P>((const S*)c.gi, c.N, j, odd, g);
+	float Tn = temperature_of(c, n, is_t, g);
+	if((c.features&F_SPONGE)&&!is_t&&bo!=TYPE_E&&c.has_t) { // sponge on T towards the top row of the column (def_sponge_ref_mode 0)
+		const int dt = (int)(c.Nzg-2u)-((int)z+c.Oz);
+		if(dt>=0&&dt<(int)c.sponge_N) {
+			const float sg = __ldg(c.sigma+dt);
+			const uint64_t nref = (uint64_t)x+((uint64_t)y+(uint64_t)c.tz*c.Ny)*c.Px;
+			Tn = fmaf(sg, c.T[nref]-Tn, Tn); // plain load: T is written by this kernel (the top row itself is TYPE_T / TYPE_E in LUW's decks)
+		}
+	}
+	float geq[7];
+	g_eq(Tn, uxn, uyn, uzn, geq); // velocity BEFORE the force half-step
+	if(is_t) {
+#pragma unroll
+		for(int i=0; i<7; i++) g[i] = geq[i];
+	} else {
+		if(UF) c.T[n] = Tn;
+		const float omw_T = 1.0f-c.w_T;
+#pragma unroll
+		for(int i=0; i<7; i++) g[i] = fmaf(omw_T, g[i], c.w_T*geq[i]);
+	}
+	store_g<P>((S*)c.gi, c.N, j, odd, g);
+	// ---- momentum, as collide_cell
+	float Fin[Q];
+	if(VF) {
+		float fxn, fyn, fzn;
+		luw_force(c, a, x, y, z, bo, true, rhon, uxn, uyn, uzn, fxn, fyn, fzn);
+		const float dT = Tn-c.T_avg; // buoyancy (Boussinesq); LUW runs with f = 0
+		fxn -= a.fx*c.beta*dT; fyn -= a.fy*c.beta*dT; fzn -= a.fz*c.beta*dT;
+		const float rho2 = 0.5f/rhon;
+		uxn = clampc(fmaf(fxn, rho2, uxn)); uyn = clampc(fmaf(fyn, rho2, uyn)); uzn = clampc(fmaf(fzn, rho2, uzn));
+		forcing_terms(uxn, uyn, uzn, fxn, fyn, fzn, Fin);
+	} else {
+		uxn = clampc(uxn); uyn = clampc(uyn); uzn = clampc(uzn);
+	}
+	if(UF&&!is_e) { c.rho[n] = rhon; c.u[n] = uxn; c.u[c.N+n] = uyn; c.u[2ull*c.N+n] = uzn; }
+	float feq[Q];
+	f_eq(rhon, uxn, uyn, uzn, feq);
+	float w = c.w;
+	if(SG) w = smagorinsky_w(w, f, feq, rhon);
+	if(is_e) {
+#pragma unroll
+		for(int i=0; i<Q; i++) f[i] = feq[i];
+	} else if(VF) {
+		const float c_tau = fmaf(w, -0.5f, 1.0f), omw = 1.0f-w;
+#pragma unroll
+		for(int i=0; i<Q; i++) f[i] = fmaf(omw, f[i], fmaf(w, feq[i], Fin[i]*c_tau));
+	} else {
+		const float omw = 1.0f-w;
+#pragma unroll
+		for(int i=0; i<Q; i++) f[i] = fmaf(omw, f[i], fmaf(w, feq[i], 0.0f));
+	}
+}
+template<int P, uint32_t FEAT> __global__ void __launch_bounds__(128) k_stream_collide_thermal(const __grid_constant__ DomainConst c, const __grid_constant__ StepArgs a) {
+	typedef typename Ddf<P>::T T;
+	const uint32_t x = blockIdx.x*blockDim.x+threadIdx.x, y = blockIdx.y, z = blockIdx.z;
+	if(x>=c.Nx||is_halo(c, x, y, z)) return;
+	uint64_t j[Q];
+	neighbors(c, x, y, z, j);
+	const uint64_t n = j[0];
+	const uint32_t fl = c.flags[n], bo = fl&TYPE_BO;
+	if(bo==TYPE_S||(fl&TYPE_SU)==TYPE_G) return;
+	const uint32_t odd = (uint32_t)(a.t&1ull);
+	float f[Q];
+	load_f<P>((const T*)c.fi, c.N, j, odd, f);
+	collide_cell_thermal<P, FEAT>(c, a, j, x, y, z, fl, odd, f);
+	store_f<P>((T*)c.fi, c.N, j, odd, f);
+}
+// initialize with the TEMPERATURE block (FX/kernel.cpp:1442-1450): g starts at g_eq(T, u)
+template<int P> __global__ void __launch_bounds__(128) k_initialize_thermal(const __grid_constant__ DomainConst c) {
+	typedef typename Ddf<P>::T T;
+	const uint32_t x = blockIdx.x*blockDim.x+threadIdx.x, y = blockIdx.y, z = blockIdx.z;
+	if(x>=c.Nx||is_halo(c, x, y, z)) return;
+	uint64_t j[Q];
+	neighbors(c, x, y, z, j);
+	const uint64_t n = j[0];
+	if((c.flags[n]&TYPE_BO)==TYPE_S) { c.u[n] = 0.0f; c.u[c.N+n] = 0.0f; c.u[2ull*c.N+n] = 0.0f; }
+	const float uxn = c.u[n], uyn = c.u[c.N+n], uzn = c.u[2ull*c.N+n];
+	float feq[Q];
+	f_eq(c.rho[n], uxn, uyn, uzn, feq);
+	float geq[7];
+	g_eq(c.T[n], uxn, uyn, uzn, geq);
+	store_g<P>((T*)c.gi, c.N, j, 1u, geq);
+	store_f<P>((T*)c.fi, c.N, j, 1u, feq);
+}
+// update_fields with the TEMPERATURE block (FX/kernel.cpp:1981-2000): T from the streamed-in g, no sponge, no collision
+template<int P, uint32_t FEAT> __global__ void __launch_bounds__(128) k_update_fields_thermal(const __grid_constant__ DomainConst c, const __grid_constant__ StepArgs a) {
+	typedef typename Ddf<P>::T T;
+	constexpr bool VF = (FEAT&F_VOLUME_FORCE)!=0u, EQ = (FEAT&F_EQUILIBRIUM)!=0u;
+	const uint32_t x = blockIdx.x*blockDim.x+threadIdx.x, y = blockIdx.y, z = blockIdx.z;
+	if(x>=c.Nx||is_halo(c, x, y, z)) return;
+	uint64_t j[Q];
+	neighbors(c, x, y, z, j);
+	const uint64_t n = j[0];
+	const uint32_t fl = c.flags[n], bo = fl&TYPE_BO;
+	if(bo==TYPE_S||(fl&TYPE_SU)==TYPE_G) return;
+	const uint32_t odd = (uint32_t)(a.t&1ull);
+	float f[Q];
+	load_f<P>((const T*)c.fi, c.N, j, odd, f);
+	float rhon, uxn, uyn, uzn;
+	rho_u(f, rhon, uxn, uyn, uzn);
+	float g[7];
+	load_g<P>((const T*)c.gi, c.N, j, odd, g);
+	const bool is_t = (fl&TYPE_T)!=0u;
+	const float Tn = temperature_of(c, n, is_t, g);
+	if(!is_t) c.T[n] = Tn;
+	if(VF) {
+		float fxn, fyn, fzn;
+		luw_force(c, a, x, y, z, bo, false, rhon, uxn, uyn, uzn, fxn, fyn, fzn);
+		const float dT = Tn-c.T_avg;
+		fxn -= a.fx*c.beta*dT; fyn -= a.fy*c.beta*dT; fzn -= a.fz*c.beta*dT;
+		const float rho2 = 0.5f/rhon;
+		uxn = clampc(fmaf(fxn, rho2, uxn)); uyn = clampc(fmaf(fyn, rho2, uyn)); uzn = clampc(fmaf(fzn, rho2, uzn));
+	} else {
+		uxn = clampc(uxn); uyn = clampc(uyn); uzn = clampc(uzn);
+	}
+	if(!(EQ&&bo==TYPE_E)) { c.rho[n] = rhon; c.u[n] = uxn; c.u[c.N+n] = uyn; c.u[2ull*c.N+n] = uzn; }
+}
+// halos of gi (one DDF per face cell and side: i = 2*axis+1 leaves through the + face, 2*axis+2 through the - face) and of T, FX/kernel.cpp:2337-2377
+template<typename T, bool INSERT> __device__ __forceinline__ void halo_gi_cell(const DomainConst& c, const uint32_t d, const uint32_t odd, const bool xfast, const uint32_t t, const uint32_t side, T* __restrict__ buf) {
+	const uint32_t L = axis_len(c, d);
+	uint32_t x, y, z, a;
+	face_xyz(c, d, t, INSERT ? (side==0u ? L-1u : 0u) : (side==0u ? L-2u : 1u), xfast, x, y, z, a);
+	uint64_t j[Q];
+	neighbors(c, x, y, z, j);
+	T* gi = (T*)c.gi;
+	const uint32_t i = 2u*d+side+1u;
+	if(INSERT) {
+		const uint64_t cell = (i&1u) ? j[0] : j[i-1u];
+		const uint32_t slot = odd ? i : ((i&1u) ? i+1u : i-1u);
+		gi[(uint64_t)slot*c.N+cell] = buf[a];
+	} else {
+		const uint64_t cell = (i&1u) ? j[i] : j[0];
+		const uint32_t slot = odd ? ((i&1u) ? i+1u : i-1u) : i;
+		buf[a] = gi[(uint64_t)slot*c.N+cell];
+	}
+}
+template<typename T, bool INSERT> __global__ void __launch_bounds__(128) k_halo_gi(const __grid_constant__ DomainConst c, const uint32_t d, const uint32_t A, const uint32_t odd, const bool xfast, T* __restrict__ buf_p, T* __restrict__ buf_m) {
+	const uint32_t t = blockIdx.x*blockDim.x+threadIdx.x;
+	if(t>=A) return;
+	halo_gi_cell<T, INSERT>(c, d, odd, xfast, t, 0u, buf_p);
+	halo_gi_cell<T, INSERT>(c, d, odd, xfast, t, 1u, buf_m);
+}
+template<bool INSERT> __global__ void __launch_bounds__(128) k_halo_T(const __grid_constant__ DomainConst c, const uint32_t d, const uint32_t A, const bool xfast, float* __restrict__ buf_p, float* __restrict__ buf_m) {
+	const uint32_t t = blockIdx.x*blockDim.x+threadIdx.x;
+	if(t>=A) return;
+	const uint32_t L = axis_len(c, d);
+#pragma unroll
+	for(uint32_t side=0u; side<2u; side++) {
+		uint32_t x, y, z, a;
+		face_xyz(c, d, t, INSERT ? (side==0u ? L-1u : 0u) : (side==0u ? L-2u : 1u), xfast, x, y, z, a);
+		const uint64_t n = x+((uint64_t)y+(uint64_t)z*c.Ny)*c.Px;
+		float* buf = side==0u ? buf_p : buf_m;
+		if(INSERT) c.T[n] = buf[a]; else buf[a] = c.T[n];
+	}
+}
+
 // ------------------------------------------------------------------ kernel: vk_inlet_apply (FX/kernel.cpp:2495-2571)
 // one thread per inlet point; the mode table (10 x V floats) is shared by all points of a face and stays L1/L2 resident
 __global__ void __launch_bounds__(128) k_vk_inlet_apply(const uint64_t Ncells, const uint32_t use_interp, const float t0, const float t1, const float alpha,

@@ -19,6 +19,12 @@ struct KernelSet { // one per arithmetic mode; every function enqueues exactly o
 	bool (*tile_shape)(int precision, uint32_t features, int variant, TileShape* shape);
 	cudaError_t (*stream_collide_tile)(const DomainConst& c, const StepArgs& a, const TileMaps& maps, int variant, int sm_count, cudaStream_t s);
 	cudaError_t (*voxelize)(const DomainConst& c, uint32_t direction, uint8_t flag, uint32_t ntri, const float* box6, const float* p0, const float* p1, const float* p2, cudaStream_t s); // p0..p2: device
+	// thermal D3Q7 extension (domains created with LUW_TEMPERATURE): the three LBM kernels with the reference's TEMPERATURE blocks, halos of gi and T
+	cudaError_t (*initialize_thermal)(const DomainConst& c, cudaStream_t s);
+	cudaError_t (*stream_collide_thermal)(const DomainConst& c, const StepArgs& a, cudaStream_t s);
+	cudaError_t (*update_fields_thermal)(const DomainConst& c, const StepArgs& a, cudaStream_t s);
+	cudaError_t (*halo_gi)(const DomainConst& c, int precision, uint32_t axis, uint32_t odd, bool insert, bool xfast, void* buf_p, void* buf_m, cudaStream_t s);
+	cudaError_t (*halo_T)(const DomainConst& c, uint32_t axis, bool insert, bool xfast, void* buf_p, void* buf_m, cudaStream_t s);
 };
 const KernelSet& kernels_strict(); // lbm_strict.cu: -fmad=false
 const KernelSet& kernels_fast(); // lbm_fast.cu: contraction allowed

@@ -95,6 +95,8 @@ int field_info(const luw_domain* d, const int field, void** base, size_t* elem, 
 		case LUW_FIELD_U: *base = d->c.u; *elem = 4u; *count = 3ull*N; return LUW_OK;
 		case LUW_FIELD_FLAGS: *base = d->c.flags; *elem = 1u; *count = N; return LUW_OK;
 		case LUW_FIELD_FI: *base = d->c.fi; *elem = d->ddf_size; *count = 19ull*N; return LUW_OK;
+		case LUW_FIELD_T: if(!d->c.T) return fail(LUW_ERR_INVALID, "field T needs a domain created with LUW_TEMPERATURE"); *base = d->c.T; *elem = 4u; *count = N; return LUW_OK;
+		case LUW_FIELD_GI: if(!d->c.gi) return fail(LUW_ERR_INVALID, "field gi needs a domain created with LUW_TEMPERATURE"); *base = d->c.gi; *elem = d->ddf_size; *count = 7ull*N; return LUW_OK;
 		default: return fail(LUW_ERR_INVALID, "unknown field id");
 	}
 }
@@ -158,6 +160,7 @@ encode_tiled_fn get_encode_tiled() {
 // described (row pitch not a multiple of 16 bytes for every array) -- the per-cell kernels are used then.
 void setup_tiles(luw_domain* d) {
 	d->tiled = false;
+	if(d->c.features&luw::F_TEMPERATURE) return; // the TEMPERATURE blocks exist in the one-cell-per-thread kernels only
 	const char* off = getenv("LUW_NO_TILE");
 	if(off&&off[0]=='1') return;
 	const char* var = getenv("LUW_TILE_VARIANT");
@@ -204,6 +207,7 @@ cudaError_t enqueue_step(luw_domain* d, const luw::StepArgs& a) {
 		e = cudaEventRecord(d->kev[d->kev_used], d->stream); if(e!=cudaSuccess) return e;
 	}
 	if(d->tiled) e = d->ks->stream_collide_tile(d->c, a, d->maps, d->tile_variant, d->sm_count, d->stream);
+	else if(d->c.features&luw::F_TEMPERATURE) e = d->ks->stream_collide_thermal(d->c, a, d->stream);
 	else e = d->ks->stream_collide(d->c, a, d->stream);
 	d->launches++;
 	if(e!=cudaSuccess) return e;
@@ -344,6 +348,7 @@ int luw_domain_create(const luw_domain_params* p, luw_domain** out) {
 	c.downstream_face = p->downstream_face;
 	c.buffer_N = p->buffer_N; c.buffer_inv_tau = p->buffer_inv_tau; c.nudge_vertical = p->buffer_nudge_vertical;
 	c.sponge_N = p->sponge_N;
+	c.w_T = 1.0f; c.beta = 0.0f; c.T_avg = 1.0f; // luw_thermal_params
 
 	int rc = LUW_OK;
 	cudaError_t e = cudaStreamCreateWithFlags(&d->own_stream, cudaStreamNonBlocking);
@@ -357,12 +362,17 @@ int luw_domain_create(const luw_domain_params* p, luw_domain** out) {
 	if(rc==LUW_OK) rc = dev_alloc(d, &c.u, 3ull*N);
 	if(rc==LUW_OK) rc = dev_alloc(d, &c.flags, N);
 	if(rc==LUW_OK) rc = dev_alloc(d, &c.sched, 2u);
+	const bool thermal = (p->features&LUW_TEMPERATURE)!=0u;
+	if(rc==LUW_OK&&thermal) rc = dev_alloc(d, (uint8_t**)&c.gi, 7ull*N*d->ddf_size); // gi = Memory<fpxx>(N, 7), T = Memory<float>(N, 1, .., 1.0f): FX/lbm.cpp:322-323
+	if(rc==LUW_OK&&thermal) rc = dev_alloc(d, &c.T, N);
 	if(rc==LUW_OK) { // Memory<> zero-fills; rho starts at 1 (FX/lbm.cpp:283-288)
 		e = cudaMemsetAsync(c.fi, 0, 19ull*N*d->ddf_size, d->stream);
 		if(e==cudaSuccess) e = cudaMemsetAsync(c.u, 0, 3ull*N*4ull, d->stream);
 		if(e==cudaSuccess) e = cudaMemsetAsync(c.flags, 0, N, d->stream);
 		if(e==cudaSuccess) e = cudaMemsetAsync(c.sched, 0, 8u, d->stream);
 		if(e==cudaSuccess) { k_fill_f32<<<1184, 256, 0, d->stream>>>(c.rho, N, 1.0f); e = cudaGetLastError(); d->launches++; }
+		if(e==cudaSuccess&&thermal) e = cudaMemsetAsync(c.gi, 0, 7ull*N*d->ddf_size, d->stream);
+		if(e==cudaSuccess&&thermal) { k_fill_f32<<<1184, 256, 0, d->stream>>>(c.T, N, 1.0f); e = cudaGetLastError(); d->launches++; }
 		if(e!=cudaSuccess) rc = cuda_fail(e, "zero-fill");
 	}
 	if(rc==LUW_OK&&(p->features&LUW_BUFFER_NUDGING)) { // distance -> sin^2 ramp, float arithmetic as written in FX/kernel.cpp:1579-1581
@@ -392,7 +402,7 @@ int luw_domain_destroy(luw_domain* d) {
 	if(!d) return LUW_OK;
 	DeviceGuard guard(d->p.device);
 	if(d->own_stream) cudaStreamSynchronize(d->own_stream);
-	cudaFree(d->c.fi); cudaFree(d->c.rho); cudaFree(d->c.u); cudaFree(d->c.flags); cudaFree(d->c.sched); cudaFree(d->wbuf); cudaFree(d->sigma);
+	cudaFree(d->c.fi); cudaFree(d->c.rho); cudaFree(d->c.u); cudaFree(d->c.flags); cudaFree(d->c.sched); cudaFree(d->wbuf); cudaFree(d->sigma); cudaFree(d->c.gi); cudaFree(d->c.T);
 	if(d->ev0) cudaEventDestroy(d->ev0);
 	if(d->ev1) cudaEventDestroy(d->ev1);
 	for(cudaEvent_t ev : d->kev) cudaEventDestroy(ev);
@@ -458,10 +468,19 @@ int luw_device_ptr(luw_domain* d, int field, void** dev_ptr) {
 	return field_info(d, field, dev_ptr, &elem, &total);
 }
 
+int luw_thermal_params(luw_domain* d, float w_T, float beta, float T_avg) {
+	if(!d) return fail(LUW_ERR_INVALID, "null domain");
+	if(!(d->c.features&luw::F_TEMPERATURE)) return fail(LUW_ERR_INVALID, "the domain was created without LUW_TEMPERATURE");
+	if(!(w_T>0.0f)) return fail(LUW_ERR_INVALID, "w_T = 1/(2 alpha + 1/2) must be positive");
+	d->c.w_T = w_T; d->c.beta = beta; d->c.T_avg = T_avg; // kernel parameters of the launches that follow
+	return LUW_OK;
+}
+
 int luw_initialize(luw_domain* d) {
 	if(!d) return fail(LUW_ERR_INVALID, "null domain");
 	DeviceGuard guard(d->p.device);
-	CU(d->ks->initialize(d->c, d->stream));
+	if(d->c.features&luw::F_TEMPERATURE) CU(d->ks->initialize_thermal(d->c, d->stream));
+	else CU(d->ks->initialize(d->c, d->stream));
 	d->launches++;
 	return LUW_OK;
 }
@@ -476,7 +495,8 @@ int luw_update_fields(luw_domain* d, uint64_t t, float fx, float fy, float fz, f
 	if(!d) return fail(LUW_ERR_INVALID, "null domain");
 	DeviceGuard guard(d->p.device);
 	const luw::StepArgs a = { t, fx, fy, fz, ox, oy, oz };
-	CU(d->ks->update_fields(d->c, a, d->stream));
+	if(d->c.features&luw::F_TEMPERATURE) CU(d->ks->update_fields_thermal(d->c, a, d->stream));
+	else CU(d->ks->update_fields(d->c, a, d->stream));
 	d->launches++;
 	return LUW_OK;
 }
@@ -496,17 +516,31 @@ int luw_halo_bytes(const luw_domain* d, int payload, uint32_t axis, uint64_t* by
 	const uint64_t A = face_area(d->c, axis);
 	if(payload==LUW_HALO_FI) *bytes = 5ull*A*d->ddf_size; // transfers*sizeof(fpxx), FX/lbm.cpp:1937-1939
 	else if(payload==LUW_HALO_RHO_U_FLAGS) *bytes = 17ull*A; // FX/lbm.cpp:1940-1942
-	else return fail(LUW_ERR_INVALID, "unknown halo payload");
+	else if(payload==LUW_HALO_GI&&d->c.gi) *bytes = A*d->ddf_size; // one DDF per face cell: get_area*sizeof(fpxx), FX/lbm.cpp communicate_gi
+	else if(payload==LUW_HALO_T&&d->c.T) *bytes = 4ull*A;
+	else return fail(LUW_ERR_INVALID, "unknown halo payload (gi / T need a domain created with LUW_TEMPERATURE)");
 	return LUW_OK;
+}
+// one extract or insert kernel of any payload on the domain's stream
+static cudaError_t halo_kernel(luw_domain* d, const int payload, const uint32_t axis, const uint64_t t, const bool insert, const bool xfast, void* bp, void* bm) {
+	switch(payload) {
+		case LUW_HALO_FI: return d->ks->halo_fi(d->c, d->c.precision, axis, (uint32_t)(t&1ull), insert, xfast, bp, bm, d->stream);
+		case LUW_HALO_RHO_U_FLAGS: return d->ks->halo_rho_u_flags(d->c, axis, insert, xfast, bp, bm, d->stream);
+		case LUW_HALO_GI: return d->ks->halo_gi(d->c, d->c.precision, axis, (uint32_t)(t&1ull), insert, xfast, bp, bm, d->stream);
+		case LUW_HALO_T: return d->ks->halo_T(d->c, axis, insert, xfast, bp, bm, d->stream);
+		default: return cudaErrorInvalidValue;
+	}
+}
+static bool halo_payload_ok(const luw_domain* d, const int payload) {
+	return payload==LUW_HALO_FI||payload==LUW_HALO_RHO_U_FLAGS||((payload==LUW_HALO_GI||payload==LUW_HALO_T)&&d->c.gi&&d->c.T);
 }
 static int halo(luw_domain* d, int payload, uint32_t axis, uint64_t t, void* bp, void* bm, const bool insert) {
 	if(!d||!bp||!bm||axis>2u) return fail(LUW_ERR_INVALID, "bad argument");
 	const uint32_t D = axis==0u ? d->c.Dx : axis==1u ? d->c.Dy : d->c.Dz;
 	if(D<2u) return fail(LUW_ERR_INVALID, "axis is not decomposed: it has no halo layers");
+	if(!halo_payload_ok(d, payload)) return fail(LUW_ERR_INVALID, "unknown halo payload (gi / T need a domain created with LUW_TEMPERATURE)");
 	DeviceGuard guard(d->p.device);
-	if(payload==LUW_HALO_FI) CU(d->ks->halo_fi(d->c, d->c.precision, axis, (uint32_t)(t&1ull), insert, false, bp, bm, d->stream));
-	else if(payload==LUW_HALO_RHO_U_FLAGS) CU(d->ks->halo_rho_u_flags(d->c, axis, insert, false, bp, bm, d->stream));
-	else return fail(LUW_ERR_INVALID, "unknown halo payload");
+	CU(halo_kernel(d, payload, axis, t, insert, false, bp, bm));
 	d->launches++;
 	return LUW_OK;
 }
@@ -535,8 +569,11 @@ int luw_halo_exchange(luw_domain* const* doms, uint32_t count, int payload, uint
 	if(count!=c0.Dx*c0.Dy*c0.Dz) return fail(LUW_ERR_INVALID, "luw_halo_exchange needs all Dx*Dy*Dz domains of the decomposition");
 	const uint32_t D[3] = { c0.Dx, c0.Dy, c0.Dz };
 	if(D[axis]<2u) return LUW_OK; // nothing to exchange on an undecomposed axis
-	if(payload!=LUW_HALO_FI&&payload!=LUW_HALO_RHO_U_FLAGS) return fail(LUW_ERR_INVALID, "unknown halo payload");
-	for(uint32_t i=0u; i<count; i++) { if(!doms[i]) return fail(LUW_ERR_INVALID, "null domain"); if(const int rc = halo_axis_setup(doms[i], axis)) return rc; }
+	for(uint32_t i=0u; i<count; i++) {
+		if(!doms[i]) return fail(LUW_ERR_INVALID, "null domain");
+		if(!halo_payload_ok(doms[i], payload)) return fail(LUW_ERR_INVALID, "unknown halo payload (gi / T need domains created with LUW_TEMPERATURE)");
+		if(const int rc = halo_axis_setup(doms[i], axis)) return rc;
+	}
 	uint64_t bytes = 0ull;
 	luw_halo_bytes(doms[0], payload, axis, &bytes);
 	const uint32_t stride = axis==0u ? 1u : axis==1u ? D[0] : D[0]*D[1];
@@ -550,8 +587,7 @@ int luw_halo_exchange(luw_domain* const* doms, uint32_t count, int payload, uint
 			CU(cudaStreamWaitEvent(d->stream, neighbour(i, 1u)->halo[axis].got_m, 0));
 			CU(cudaStreamWaitEvent(d->stream, neighbour(i, D[axis]-1u)->halo[axis].got_p, 0));
 		}
-		if(payload==LUW_HALO_FI) CU(d->ks->halo_fi(d->c, d->c.precision, axis, (uint32_t)(t&1ull), false, true, h.send_p, h.send_m, d->stream));
-		else CU(d->ks->halo_rho_u_flags(d->c, axis, false, true, h.send_p, h.send_m, d->stream));
+		CU(halo_kernel(d, payload, axis, t, false, true, h.send_p, h.send_m));
 		d->launches++;
 		CU(cudaEventRecord(h.extracted, d->stream));
 	}
@@ -570,8 +606,7 @@ int luw_halo_exchange(luw_domain* const* doms, uint32_t count, int payload, uint
 		CU(cudaMemcpyPeerAsync(h.recv_p, d->p.device, up->halo[axis].send_m, up->p.device, bytes, d->stream));
 		CU(cudaEventRecord(h.got_p, d->stream));
 		h.in_use = true;
-		if(payload==LUW_HALO_FI) CU(d->ks->halo_fi(d->c, d->c.precision, axis, (uint32_t)(t&1ull), true, true, h.recv_p, h.recv_m, d->stream));
-		else CU(d->ks->halo_rho_u_flags(d->c, axis, true, true, h.recv_p, h.recv_m, d->stream));
+		CU(halo_kernel(d, payload, axis, t, true, true, h.recv_p, h.recv_m));
 		d->launches++;
 	}
 	return LUW_OK;
@@ -621,22 +656,20 @@ int luw_halo_ipc_exchange(luw_domain* d, int payload, uint32_t axis, uint64_t t)
 	luw_domain::HaloIpc* h;
 	if(const int rc = halo_ipc_axis(d, axis, &h)) return rc;
 	if(!h->up||!h->dn) return fail(LUW_ERR_INVALID, "luw_halo_ipc_connect must come first");
-	if(payload!=LUW_HALO_FI&&payload!=LUW_HALO_RHO_U_FLAGS) return fail(LUW_ERR_INVALID, "unknown halo payload");
+	if(!halo_payload_ok(d, payload)) return fail(LUW_ERR_INVALID, "unknown halo payload (gi / T need a domain created with LUW_TEMPERATURE)");
 	DeviceGuard guard(d->p.device);
 	const uint32_t seq = h->seq++, par = seq&1u;
 	const uint64_t bb = h->buf_bytes;
 	// my + face goes into the (+) neighbour's recv_m, my - face into the (-) neighbour's recv_p: remote stores of the extract kernel
 	char* const to_up = h->up+256ull+(2ull*par+1ull)*bb;
 	char* const to_dn = h->dn+256ull+(2ull*par+0ull)*bb;
-	if(payload==LUW_HALO_FI) CU(d->ks->halo_fi(d->c, d->c.precision, axis, (uint32_t)(t&1ull), false, true, to_up, to_dn, d->stream));
-	else CU(d->ks->halo_rho_u_flags(d->c, axis, false, true, to_up, to_dn, d->stream));
+	CU(halo_kernel(d, payload, axis, t, false, true, to_up, to_dn));
 	k_halo_signal<<<1, 1, 0, d->stream>>>((uint32_t*)(h->up+64), (uint32_t*)(h->dn+0), seq+1u); // the (+) neighbour's flag_m, the (-) neighbour's flag_p
 	k_halo_wait<<<1, 1, 0, d->stream>>>((const uint32_t*)(h->block+0), (const uint32_t*)(h->block+64), seq+1u);
 	CU(cudaGetLastError());
 	char* const recv_p = h->block+256ull+(2ull*par+0ull)*bb;
 	char* const recv_m = h->block+256ull+(2ull*par+1ull)*bb;
-	if(payload==LUW_HALO_FI) CU(d->ks->halo_fi(d->c, d->c.precision, axis, (uint32_t)(t&1ull), true, true, recv_p, recv_m, d->stream));
-	else CU(d->ks->halo_rho_u_flags(d->c, axis, true, true, recv_p, recv_m, d->stream));
+	CU(halo_kernel(d, payload, axis, t, true, true, recv_p, recv_m));
 	d->launches += 4ull;
 	return LUW_OK;
 }
@@ -645,6 +678,7 @@ int luw_run_steps_multi(luw_domain* const* doms, uint32_t count, uint64_t t0, ui
 	for(uint64_t s=0ull; s<k; s++) {
 		for(uint32_t i=0u; i<count; i++) { if(const int rc = luw_stream_collide(doms[i], t0+s, fx, fy, fz, ox, oy, oz)) return rc; }
 		for(uint32_t axis=0u; axis<3u; axis++) { if(const int rc = luw_halo_exchange(doms, count, LUW_HALO_FI, axis, t0+s)) return rc; }
+		if(doms[0]&&doms[0]->c.gi) for(uint32_t axis=0u; axis<3u; axis++) { if(const int rc = luw_halo_exchange(doms, count, LUW_HALO_GI, axis, t0+s)) return rc; } // communicate_gi follows communicate_fi, FX/lbm.cpp do_time_step
 	}
 	return LUW_OK;
 }
@@ -758,7 +792,7 @@ int luw_cellset_create(luw_domain* d, uint64_t count, const uint64_t* host_cell_
 static int cellset_move(luw_cellset* s, int field, void* host, const bool up) {
 	if(!s||!host) return fail(LUW_ERR_INVALID, "null argument");
 	luw_domain* d = s->dom;
-	if(field!=LUW_FIELD_RHO&&field!=LUW_FIELD_U&&field!=LUW_FIELD_FLAGS) return fail(LUW_ERR_INVALID, "cell sets move rho, u or flags");
+	if(field!=LUW_FIELD_RHO&&field!=LUW_FIELD_U&&field!=LUW_FIELD_FLAGS&&!(field==LUW_FIELD_T&&d->c.T)) return fail(LUW_ERR_INVALID, "cell sets move rho, u, flags or (LUW_TEMPERATURE domains) T");
 	if(s->count==0ull) return LUW_OK;
 	DeviceGuard guard(d->p.device);
 	const uint32_t comps = field==LUW_FIELD_U ? 3u : 1u;
@@ -772,14 +806,14 @@ static int cellset_move(luw_cellset* s, int field, void* host, const bool up) {
 		CU(cudaEventRecord(s->staged[k], d->copy_stream));
 		CU(cudaStreamWaitEvent(d->stream, s->staged[k], 0));
 		if(field==LUW_FIELD_FLAGS) k_cellset_scatter<uint8_t><<<blocks, 256, 0, d->stream>>>(d->c.flags, d->c.N, 1u, s->count, s->cell, (const uint8_t*)s->up[k]);
-		else k_cellset_scatter<float><<<blocks, 256, 0, d->stream>>>(field==LUW_FIELD_U ? d->c.u : d->c.rho, d->c.N, comps, s->count, s->cell, s->up[k]);
+		else k_cellset_scatter<float><<<blocks, 256, 0, d->stream>>>(field==LUW_FIELD_U ? d->c.u : field==LUW_FIELD_T ? d->c.T : d->c.rho, d->c.N, comps, s->count, s->cell, s->up[k]);
 		CU(cudaGetLastError());
 		CU(cudaEventRecord(s->scattered[k], d->stream));
 	} else { // domain stream: wait until the slot's last D2H has drained it, gather; copy stream: wait for the gather, D2H
 		const uint32_t k = s->dn_seq++&1u;
 		CU(cudaStreamWaitEvent(d->stream, s->drained[k], 0));
 		if(field==LUW_FIELD_FLAGS) k_cellset_gather<uint8_t><<<blocks, 256, 0, d->stream>>>(d->c.flags, d->c.N, 1u, s->count, s->cell, (uint8_t*)s->dn[k]);
-		else k_cellset_gather<float><<<blocks, 256, 0, d->stream>>>(field==LUW_FIELD_U ? d->c.u : d->c.rho, d->c.N, comps, s->count, s->cell, s->dn[k]);
+		else k_cellset_gather<float><<<blocks, 256, 0, d->stream>>>(field==LUW_FIELD_U ? d->c.u : field==LUW_FIELD_T ? d->c.T : d->c.rho, d->c.N, comps, s->count, s->cell, s->dn[k]);
 		CU(cudaGetLastError());
 		CU(cudaEventRecord(s->gathered[k], d->stream));
 		CU(cudaStreamWaitEvent(d->copy_stream, s->gathered[k], 0));

@@ -33,6 +33,20 @@ class Domain:
         self.rho = np.ones(self.N, np.float32)
         self.u = np.zeros(3 * self.N, np.float32)
         self.flags = np.zeros(self.N, np.uint8)
+        # thermal D3Q7 extension (features & TEMPERATURE): host mirror of T, 1 everywhere like Memory<float>(N, 1, .., 1.0f) (FX/lbm.cpp:323)
+        self.thermal = bool(features & A.TEMPERATURE)
+        self.T = np.ones(self.N, np.float32) if self.thermal else None
+
+    def set_thermal(self, w_T, beta=0.0, T_avg=1.0):
+        """def_w_T = 1/(2 alpha + 1/2), def_beta, def_T_avg (FX/lbm.cpp:750-752) for the launches that follow."""
+        A.check(A.lib().luw_thermal_params(self._h, float(np.float32(w_T)), float(np.float32(beta)), float(np.float32(T_avg))))
+
+    def read_gi(self):
+        """Raw D3Q7 DDF image gi[i*N+n] (device-only in the reference; exposed for parity tests)."""
+        out = np.empty(7 * self.N, self.ddf_dtype)
+        A.check(A.lib().luw_download(self._h, A.FIELD_GI, _ptr(out), 0, out.size))
+        self.finish_queue()
+        return out
 
     # ---- lifetime
     def close(self):
@@ -54,7 +68,7 @@ class Domain:
 
     # ---- Memory<T>::enqueue_write_to_device / enqueue_read_from_device
     def _field(self, field):
-        return {A.FIELD_RHO: self.rho, A.FIELD_U: self.u, A.FIELD_FLAGS: self.flags}[field]
+        return {A.FIELD_RHO: self.rho, A.FIELD_U: self.u, A.FIELD_FLAGS: self.flags, A.FIELD_T: self.T}[field]
 
     def write_to_device(self, field, offset=0, count=None):
         host = self._field(field)
@@ -66,12 +80,15 @@ class Domain:
         count = host.size - offset if count is None else count
         A.check(A.lib().luw_download(self._h, field, _ptr(host[offset:offset + count]), offset, count))
 
+    def _mirrored_fields(self):
+        return (A.FIELD_RHO, A.FIELD_U, A.FIELD_FLAGS) + ((A.FIELD_T,) if self.thermal else ())
+
     def upload_all(self):
-        for f in (A.FIELD_RHO, A.FIELD_U, A.FIELD_FLAGS):
+        for f in self._mirrored_fields():
             self.write_to_device(f)
 
     def download_all(self):
-        for f in (A.FIELD_RHO, A.FIELD_U, A.FIELD_FLAGS):
+        for f in self._mirrored_fields():
             self.read_from_device(f)
         self.finish_queue()
 

@@ -47,7 +47,7 @@ def _local_index(Ng, Nl, O):
 
 class _Base:
     def __init__(self, shape, D=(1, 1, 1), nu=1.0 / 6.0, precision=A.FP32, features=A.UPDATE_FIELDS, arith=A.ARITH_FAST,
-                 f=(0.0, 0.0, 0.0), omega=(0.0, 0.0, 0.0), w=None, **zones):
+                 f=(0.0, 0.0, 0.0), omega=(0.0, 0.0, 0.0), w=None, alpha=0.0, beta=0.0, T_avg=1.0, **zones):
         self.D = tuple(int(v) for v in D)
         self.Ng, self.Nl, self._split = split(shape, self.D)
         self.N = int(np.prod(self.Ng))
@@ -55,6 +55,11 @@ class _Base:
         self.w = cases.relaxation_rate(nu) if w is None else w
         self.f, self.omega = tuple(f), tuple(omega)
         self.zones = zones
+        # thermal D3Q7 extension (features & TEMPERATURE): LBM ctor arguments alpha (thermal diffusion coefficient) and beta (thermal expansion
+        # coefficient), FX/lbm.cpp:1040-1047; def_w_T = 1/(2 alpha + 1/2) in float arithmetic like FX/lbm.cpp:750
+        self.thermal = bool(features & A.TEMPERATURE)
+        self.w_T = float(np.float32(1.0) / (np.float32(2.0) * np.float32(alpha) + np.float32(0.5)))
+        self.beta, self.T_avg = float(beta), float(T_avg)
         self.t = 0
         self.initialized = False
 
@@ -62,6 +67,8 @@ class _Base:
         dom = Domain(*self.Nl, D=self.D, O=O, precision=self.precision, features=self.features, w=self.w, arith=self.arith,
                      device=device, **self.zones)
         dom.f, dom.omega = self.f, self.omega
+        if self.thermal:
+            dom.set_thermal(self.w_T, self.beta, self.T_avg)
         return dom
 
     def set_coriolis(self, ox, oy, oz):  # FX/lbm.hpp:496-498
@@ -87,6 +94,7 @@ class LBM(_Base):
         self.rho = np.ones(self.N, np.float32)
         self.u = np.zeros(3 * self.N, np.float32)
         self.flags = np.zeros(self.N, np.uint8)
+        self.T = np.ones(self.N, np.float32) if self.thermal else None
         self._gidx = [_local_index(self.Ng, self.Nl, O) for _, O in self._split]
 
     # ---- host <-> device (Memory_Container::write_to_device / read_from_device, FX/lbm.hpp:406-423)
@@ -96,6 +104,8 @@ class LBM(_Base):
             dom.flags[:] = self.flags[g]
             for c in range(3):
                 dom.u[c * dom.N:(c + 1) * dom.N] = self.u[c * self.N + g]
+            if self.thermal:
+                dom.T[:] = self.T[g]
             dom.upload_all()
 
     def read_from_device(self):
@@ -111,6 +121,8 @@ class LBM(_Base):
             self.flags[g[k]] = dom.flags[k]
             for c in range(3):
                 self.u[c * self.N + g[k]] = dom.u[c * dom.N:(c + 1) * dom.N][k]
+            if self.thermal:
+                self.T[g[k]] = dom.T[k]
 
     # ---- halo exchange (FX/lbm.cpp:1895-1958): extract, peer copies and insert are enqueued by the library, stream-ordered
     def _handles(self):
@@ -134,6 +146,9 @@ class LBM(_Base):
             dom.enqueue_initialize()
         self.communicate(A.HALO_RHO_U_FLAGS)
         self.communicate(A.HALO_FI)
+        if self.thermal:  # communicate_T(); communicate_gi(): FX/lbm.cpp LBM::initialize
+            self.communicate(A.HALO_T)
+            self.communicate(A.HALO_GI)
         for dom in self.domains:
             dom.finish_queue()
             dom.t = 0
@@ -145,6 +160,8 @@ class LBM(_Base):
             dom.f, dom.omega = self.f, self.omega
             dom.enqueue_stream_collide()
         self.communicate(A.HALO_FI)
+        if self.thermal:
+            self.communicate(A.HALO_GI)
         for dom in self.domains:
             dom.increment_time_step()
         self.t += 1
@@ -226,7 +243,8 @@ class DistributedLBM(_Base):
 
     def halo_bytes(self, payload, axis):
         A_ = (self.Nl[1] * self.Nl[2], self.Nl[2] * self.Nl[0], self.Nl[0] * self.Nl[1])[axis]
-        per = 17 if payload == A.HALO_RHO_U_FLAGS else 5 * (4 if self.precision == A.FP32 else 2)
+        ddf = 4 if self.precision == A.FP32 else 2
+        per = {A.HALO_RHO_U_FLAGS: 17, A.HALO_FI: 5 * ddf, A.HALO_GI: ddf, A.HALO_T: 4}[payload]
         return per * A_
 
     def _buffers(self, payload, axis):
@@ -273,12 +291,14 @@ class DistributedLBM(_Base):
     def _insert(self, payload, axis, rp, rm):
         self.domain.halo_insert(payload, axis, rp.data_ptr(), rm.data_ptr())
 
-    def initialize(self, flags, rho, u):
-        """flags / rho / u: LOCAL host images of this rank's domain (halo layers included)."""
+    def initialize(self, flags, rho, u, T=None):
+        """flags / rho / u (/ T with TEMPERATURE): LOCAL host images of this rank's domain (halo layers included)."""
         if self.domain is None:
             raise RuntimeError("DistributedLBM(routing_only=True) has no device domain: the LBM step has no CPU fallback")
         dom = self.domain
         dom.rho[:], dom.u[:], dom.flags[:] = rho, u, flags
+        if self.thermal and T is not None:
+            dom.T[:] = T
         dom.f, dom.omega = self.f, self.omega
         dom.upload_all()
         dom.t = 1
@@ -286,6 +306,9 @@ class DistributedLBM(_Base):
         dom.enqueue_initialize()
         self.communicate(A.HALO_RHO_U_FLAGS, self._extract, self._insert)
         self.communicate(A.HALO_FI, self._extract, self._insert)
+        if self.thermal:
+            self.communicate(A.HALO_T, self._extract, self._insert)
+            self.communicate(A.HALO_GI, self._extract, self._insert)
         dom.finish_queue()
         dom.t = 0
         self.t = 0
@@ -295,6 +318,8 @@ class DistributedLBM(_Base):
         dom = self.domain
         dom.enqueue_stream_collide()
         self.communicate(A.HALO_FI, self._extract, self._insert)
+        if self.thermal:
+            self.communicate(A.HALO_GI, self._extract, self._insert)
         dom.increment_time_step()
         self.t += 1
 

@@ -312,3 +312,29 @@ def golden_thermal_halo(engine, O, precision):
         engine.insert_T(axis, bm, bp, Tl)
     out[f"thalo_{name}_T"] = Tl.copy()
     return out
+
+
+def run_cuda_thermal(shape, precision, features, flags, rho, u, T, steps, w, arith, f=FORCE, omega=OMEGA, zones=ZONES, thermal=THERMAL, update_at_end=False,
+                     batched=False, D=(1, 1, 1), O=(0, 0, 0)):
+    """run_cpu_thermal's script on the CUDA path (Domain over the C ABI): returns (fi, rho, u, gi, T)."""
+    from latticeurbanwind_b200.domain import Domain
+    Nx, Ny, Nz = shape
+    with Domain(Nx, Ny, Nz, D=D, O=O, precision=precision, features=features, w=w, arith=arith, **zones) as d:
+        assert d.thermal and not d.uses_tiles()
+        d.set_thermal(**thermal)
+        d.rho[:], d.u[:], d.flags[:], d.T[:] = rho, u, flags, T
+        d.f, d.omega = f, omega
+        d.upload_all()
+        d.t = 1
+        d.enqueue_initialize()
+        d.t = 0
+        if batched:
+            d.run_steps(steps)
+        else:
+            for _ in range(steps):
+                d.enqueue_stream_collide()
+                d.increment_time_step()
+        if update_at_end:
+            d.enqueue_update_fields()
+        d.download_all()
+        return d.read_fi(), d.rho.copy(), d.u.copy(), d.read_gi(), d.T.copy()

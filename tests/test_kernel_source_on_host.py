@@ -1,0 +1,161 @@
+"""CPU: the package's CUDA kernel SOURCE (csrc/lbm_kernels.cuh), compiled with g++ behind a thin emulation of blockIdx / threadIdx / the few
+intrinsics it uses (tests/host_emulation/), run over the same launch grid on host threads, against the oracle -- bit for bit, in the device memory
+layout (padded row pitch). This is how kernel logic is checked in the container without a GPU: the thermal D3Q7 kernels were written
+after this round's GPU budget was spent, so this test -- not a B200 run -- is their parity evidence until tests/test_thermal_gpu.py has been observed
+on the device. The plain stream_collide (GPU-verified) runs through the same harness first, which validates the harness itself.
+Nothing in the package can load this library; it is test infrastructure like oracle/."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from latticeurbanwind_b200 import cases
+from oracle import oracle as O
+from tests import helpers as H
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emulation")
+pytestmark = pytest.mark.skipif(not os.path.isfile("/usr/local/cuda/include/cuda_fp16.h"), reason="CUDA headers not installed")
+PRECS = pytest.mark.parametrize("precision", [0, 1, 2], ids=["fp32", "fp16s", "fp16c"])
+
+
+class StepArgs(C.Structure):
+    _fields_ = [("t", C.c_uint64)] + [(n, C.c_float) for n in ("fx", "fy", "fz", "ox", "oy", "oz")]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.check_call(["make", "-C", HERE], stdout=subprocess.DEVNULL)
+    L = C.CDLL(os.path.join(HERE, "libluw_kernels_on_host.so"))
+    L.emu_sizeof_domain_const.restype = C.c_uint64
+    L.emu_make_domain.argtypes = [C.c_void_p] + [C.c_uint32] * 6 + [C.c_int] * 4 + [C.c_uint32, C.c_float, C.c_int, C.c_uint32, C.c_float, C.c_int, C.c_uint32] + \
+        [C.c_void_p] * 8 + [C.c_float] * 3
+    L.emu_zone_tables.argtypes = [C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p]
+    for name in ("emu_initialize", "emu_initialize_thermal"):
+        getattr(L, name).argtypes = [C.c_void_p]
+    for name in ("emu_stream_collide", "emu_stream_collide_thermal", "emu_update_fields_thermal"):
+        getattr(L, name).argtypes = [C.c_void_p, C.POINTER(StepArgs)]
+    L.emu_halo_gi.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.emu_halo_T.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class HostDomain:
+    """Device-layout arrays (rows padded to a multiple of 16 elements, like luw_domain_create) + the DomainConst the kernels take."""
+
+    def __init__(self, L, shape, precision, features, w, zones, D=(1, 1, 1), Ov=(0, 0, 0), thermal=None):
+        self.L, self.shape, self.precision = L, shape, precision
+        Nx, Ny, Nz = shape
+        self.Px = (Nx + 15) & ~15
+        self.Nd = self.Px * Ny * Nz
+        dt = O.ddf_dtype(precision)
+        self.fi, self.gi = np.zeros(19 * self.Nd, dt), np.zeros(7 * self.Nd, dt)
+        self.rho, self.u, self.flags, self.T = np.ones(self.Nd, np.float32), np.zeros(3 * self.Nd, np.float32), np.zeros(self.Nd, np.uint8), np.ones(self.Nd, np.float32)
+        self.wbuf, self.sigma = np.zeros(zones["buffer_N"] + 1, np.float32), np.zeros(zones["sponge_N"], np.float32)
+        L.emu_zone_tables(zones["buffer_N"], zones["sponge_N"], np.float32(zones["sponge_inv_tau"]), _p(self.wbuf), _p(self.sigma))
+        self.c = C.create_string_buffer(int(L.emu_sizeof_domain_const()))
+        th = thermal or dict(w_T=1.0, beta=0.0, T_avg=1.0)
+        rc = L.emu_make_domain(self.c, Nx, Ny, Nz, *D, *Ov, precision, features, np.float32(w), zones["downstream_face"], zones["buffer_N"],
+                               np.float32(zones["buffer_inv_tau"]), zones["buffer_nudge_vertical"], zones["sponge_N"], _p(self.wbuf), _p(self.sigma),
+                               _p(self.fi), _p(self.rho), _p(self.u), _p(self.flags), _p(self.gi), _p(self.T),
+                               np.float32(th["w_T"]), np.float32(th["beta"]), np.float32(th["T_avg"]))
+        assert rc == 0
+
+    def put(self, dev, dense, comps):
+        Nx, Ny, Nz = self.shape
+        dev.reshape(comps, Nz, Ny, self.Px)[..., :Nx] = dense.reshape(comps, Nz, Ny, Nx)
+
+    def get(self, dev, comps):
+        Nx, Ny, Nz = self.shape
+        return np.ascontiguousarray(dev.reshape(comps, Nz, Ny, self.Px)[..., :Nx]).reshape(-1)
+
+    def args(self, t, f, omega):
+        return StepArgs(t, *map(np.float32, f), *map(np.float32, omega))
+
+
+def test_harness_reproduces_the_gpu_verified_step(emu, oracle_lib):
+    """Validation of the harness: the plain (GPU-verified) stream_collide through it equals the oracle."""
+    shape = (20, 18, 14)
+    flags, rho, u = H.small_urban(*shape)
+    w = cases.relaxation_rate(1e-6)
+    feat = O.FEATURE_SETS["luw"]
+    for precision in (O.FP32, O.FP16S, O.FP16C):
+        want = H.run_cpu(O.Oracle(), O, shape, precision, feat, flags, rho, u, 6, w)
+        d = HostDomain(emu, shape, precision, feat, w, H.ZONES)
+        d.put(d.rho, rho, 1); d.put(d.u, u, 3); d.put(d.flags, flags, 1)
+        assert emu.emu_initialize(d.c) == 0
+        for t in range(6):
+            assert emu.emu_stream_collide(d.c, C.byref(d.args(t, H.FORCE, H.OMEGA))) == 0
+        for got, ref, name in zip((d.get(d.fi, 19), d.get(d.rho, 1), d.get(d.u, 3)), want, ("fi", "rho", "u")):
+            assert np.array_equal(got, ref), (precision, name)
+
+
+@PRECS
+@pytest.mark.parametrize("fset", ["luwT", "chanT"])
+def test_thermal_kernels_equal_the_oracle(emu, oracle_lib, precision, fset):
+    flags, rho, u, T = H.thermal_case()
+    w = cases.relaxation_rate(1e-6)
+    feat = O.FEATURE_SETS[fset]
+    steps = H.THERMAL_STEPS
+    want = H.run_cpu_thermal(O.Oracle(), O, H.THERMAL_SHAPE, precision, feat, flags, rho, u, T, steps, w, update_at_end=(fset == "chanT"))
+    d = HostDomain(emu, H.THERMAL_SHAPE, precision, feat, w, H.ZONES, thermal=H.THERMAL)
+    d.put(d.rho, rho, 1); d.put(d.u, u, 3); d.put(d.flags, flags, 1); d.put(d.T, T, 1)
+    assert emu.emu_initialize_thermal(d.c) == 0
+    for t in range(steps):
+        assert emu.emu_stream_collide_thermal(d.c, C.byref(d.args(t, H.FORCE, H.OMEGA))) == 0
+    if fset == "chanT":
+        assert emu.emu_update_fields_thermal(d.c, C.byref(d.args(steps, H.FORCE, H.OMEGA))) == 0
+    got = (d.get(d.fi, 19), d.get(d.rho, 1), d.get(d.u, 3), d.get(d.gi, 7), d.get(d.T, 1))
+    for g, r, name in zip(got, want, ("fi", "rho", "u", "gi", "T")):
+        assert np.array_equal(g, r), name
+
+
+@PRECS
+def test_thermal_halo_kernels_equal_the_oracle(emu, oracle_lib, precision):
+    """Block (0,0,0) of a 2x2x2 decomposition: gi / T payloads in the reference's face order (xfast = 0) and the lattice after inserting them."""
+    flags, rho, u, T = H.thermal_case(H.GOLDEN_SHAPE)
+    Ncell = int(np.prod(H.GOLDEN_SHAPE))
+    shape, Ov, fl, rh, ul = H.cut_block(H.GOLDEN_SHAPE, (2, 2, 2), (0, 0, 0), flags, rho, u)
+    Tl = H.cut_block(H.GOLDEN_SHAPE, (2, 2, 2), (0, 0, 0), flags, T, np.zeros(3 * Ncell, np.float32))[3]
+    zones = dict(downstream_face=2, buffer_N=4, buffer_inv_tau=0.01, buffer_nudge_vertical=1, sponge_N=5, sponge_inv_tau=0.02)
+    feat = O.FEATURE_SETS["luwT"]
+    w = cases.relaxation_rate(1e-6)
+    want = H.golden_thermal_halo(O.Oracle(), O, precision)
+    name = O.PREC_NAME[precision]
+    d = HostDomain(emu, shape, precision, feat, w, zones, D=(2, 2, 2), Ov=Ov, thermal=H.THERMAL)
+    d.put(d.rho, rh, 1); d.put(d.u, ul, 3); d.put(d.flags, fl, 1); d.put(d.T, Tl, 1)
+    assert emu.emu_initialize_thermal(d.c) == 0
+    Nx, Ny, Nz = shape
+    for t in range(3):
+        assert emu.emu_stream_collide_thermal(d.c, C.byref(d.args(t, H.FORCE, H.OMEGA))) == 0
+        for axis in range(3):
+            A = (Ny * Nz, Nz * Nx, Nx * Ny)[axis]
+            bp, bm = np.zeros(A, d.gi.dtype), np.zeros(A, d.gi.dtype)
+            assert emu.emu_halo_gi(d.c, axis, t & 1, 0, 0, _p(bp), _p(bm)) == 0
+            assert np.array_equal(bp, want[f"thalo_{name}_t{t}_axis{axis}_p"]) and np.array_equal(bm, want[f"thalo_{name}_t{t}_axis{axis}_m"]), (t, axis)
+            assert emu.emu_halo_gi(d.c, axis, t & 1, 1, 0, _p(bm), _p(bp)) == 0
+        assert np.array_equal(d.get(d.gi, 7), want[f"thalo_{name}_t{t}_gi"]), t
+    for axis in range(3):
+        A = (Ny * Nz, Nz * Nx, Nx * Ny)[axis]
+        bp, bm = np.zeros(A, np.float32), np.zeros(A, np.float32)
+        assert emu.emu_halo_T(d.c, axis, 0, 0, _p(bp), _p(bm)) == 0
+        assert np.array_equal(bp, want[f"thalo_{name}_T_axis{axis}_p"]) and np.array_equal(bm, want[f"thalo_{name}_T_axis{axis}_m"]), axis
+        assert emu.emu_halo_T(d.c, axis, 1, 0, _p(bm), _p(bp)) == 0
+    assert np.array_equal(d.get(d.T, 1), want[f"thalo_{name}_T"])
+    # xfast payload order (library-internal buffers): extract + insert with swapped buffers must give the same lattice as the reference order
+    g0 = d.gi.copy()
+    for order in (0, 1):
+        d.gi[:] = g0
+        for axis in range(3):
+            A = (Ny * Nz, Nz * Nx, Nx * Ny)[axis]
+            bp, bm = np.zeros(A, d.gi.dtype), np.zeros(A, d.gi.dtype)
+            emu.emu_halo_gi(d.c, axis, 1, 0, order, _p(bp), _p(bm))
+            emu.emu_halo_gi(d.c, axis, 1, 1, order, _p(bm), _p(bp))
+        if order == 0:
+            ref = d.gi.copy()
+    assert np.array_equal(d.gi, ref)

@@ -1,0 +1,108 @@
+"""GPU parity of the thermal D3Q7 extension through the C ABI: LUW_TEMPERATURE domains against the oracle, bit for bit (STRICT).
+
+STATUS: these kernels were written after this round's GPU budget was spent. Their source is checked bit for bit against the oracle by compiling it for
+the host (tests/test_kernel_source_on_host.py); the device build itself has NOT been observed on a B200 yet. Until it has, the tests are marked
+xfail(strict=False): a pass shows up as XPASS in the round-end run, a failure does not mask the rest of the suite (the file also sorts last, because
+a faulting kernel would poison the process's CUDA context). Remove the marker once an XPASS has been seen.
+"""
+import numpy as np
+import pytest
+
+from latticeurbanwind_b200 import cases
+from tests import helpers as H
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="thermal kernels not yet observed on a B200; host emulation of the same source is bit-exact", strict=False)]
+NAMES = ("fi", "rho", "u", "gi", "T")
+PRECS = pytest.mark.parametrize("precision", [0, 1, 2], ids=["fp32", "fp16s", "fp16c"])
+
+
+@PRECS
+@pytest.mark.parametrize("fset", ["luwT", "chanT"])
+def test_strict_equals_oracle(oracle_lib, precision, fset):
+    O = oracle_lib
+    flags, rho, u, T = H.thermal_case()
+    w = cases.relaxation_rate(1e-6)
+    kw = dict(update_at_end=(fset == "chanT"))
+    want = H.run_cpu_thermal(O.Oracle(), O, H.THERMAL_SHAPE, precision, O.FEATURE_SETS[fset], flags, rho, u, T, H.THERMAL_STEPS, w, **kw)
+    got = H.run_cuda_thermal(H.THERMAL_SHAPE, precision, H.FEATURE_SETS[fset], flags, rho, u, T, H.THERMAL_STEPS, w, 0, **kw)
+    for g, r, name in zip(got, want, NAMES):
+        assert np.array_equal(g, r), name
+
+
+def test_wide_lattice_and_batched_steps(oracle_lib):
+    """Rows wider than one thread block, padded pitch (Nx = 150 -> 160), luw_run_steps."""
+    O = oracle_lib
+    shape = (150, 12, 10)
+    flags, rho, u, T = H.thermal_case(shape, seed=9)
+    w = cases.relaxation_rate(1e-6)
+    want = H.run_cpu_thermal(O.Oracle(), O, shape, O.FP16S, O.FEATURE_SETS["luwT"], flags, rho, u, T, 5, w)
+    got = H.run_cuda_thermal(shape, O.FP16S, H.FEATURE_SETS["luwT"], flags, rho, u, T, 5, w, 0, batched=True)
+    for g, r, name in zip(got, want, NAMES):
+        assert np.array_equal(g, r), name
+
+
+def test_zero_gravity_leaves_the_flow_untouched():
+    """LUW runs with f = 0: the thermal domain's fi / rho / u equal the plain domain's (which takes the TMA-tiled kernel here) bit for bit."""
+    shape = (128, 16, 12)
+    flags, rho, u, T = H.thermal_case(shape, seed=3)
+    w = cases.relaxation_rate(1e-6)
+    zero = (0.0, 0.0, 0.0)
+    a = H.run_cuda_thermal(shape, 1, H.FEATURE_SETS["luwT"], flags, rho, u, T, 6, w, 0, f=zero)
+    b = H.run_cuda(shape, 1, H.FEATURE_SETS["luw"], flags, rho, u, 6, w, 0, f=zero)
+    for x, y, name in zip(a[:3], b, NAMES):
+        assert np.array_equal(x, y), name
+
+
+@pytest.mark.parametrize("D", [(2, 1, 1), (1, 2, 2), (2, 2, 2)], ids=["2x1x1", "1x2x2", "2x2x2"])
+def test_decomposed_equals_single_domain(D):
+    """Halo exchange of gi after fi every step, T + gi at initialisation (FX/lbm.cpp LBM::initialize / do_time_step): D domains == one domain."""
+    from latticeurbanwind_b200 import _cabi as A
+    from latticeurbanwind_b200.lbm import LBM
+    shape = (64, 24, 16)
+    flags, rho, u, T = H.thermal_case(shape, seed=21)
+    zones = dict(downstream_face=2, buffer_N=3, buffer_inv_tau=0.01, buffer_nudge_vertical=1, sponge_N=3, sponge_inv_tau=0.02)
+    res = []
+    for dd in ((1, 1, 1), D):
+        lbm = LBM(shape, D=dd, nu=1e-6, precision=A.FP16S, features=H.FEATURE_SETS["luwT"], arith=A.ARITH_STRICT, f=H.FORCE, omega=H.OMEGA,
+                  alpha=2.0e-3, beta=0.4, **zones)
+        lbm.flags[:], lbm.rho[:], lbm.u[:], lbm.T[:] = flags, rho, u, T
+        lbm.run(7)
+        lbm.read_from_device()
+        res.append((lbm.rho.copy(), lbm.u.copy(), lbm.T.copy()))
+        lbm.close()
+    for x, y, name in zip(res[0], res[1], ("rho", "u", "T")):
+        assert np.array_equal(x, y), name
+    assert not np.array_equal(res[0][2], T)
+
+
+def test_cell_set_moves_boundary_temperatures():
+    """Boundary-field upload for T (the case driver's TYPE_T cells, FX/setup.cpp:5268-5317) without moving the whole field."""
+    from latticeurbanwind_b200 import _cabi as A
+    from latticeurbanwind_b200.domain import CellSet, Domain
+    Nx, Ny, Nz = 37, 6, 5
+    rng = np.random.default_rng(1)
+    with Domain(Nx, Ny, Nz, precision=1, features=A.UPDATE_FIELDS | A.TEMPERATURE, w=1.0, arith=0) as d:
+        cells = np.sort(rng.choice(d.N, 50, replace=False)).astype(np.uint64)
+        vals = (1.0 + 0.1 * rng.standard_normal(50)).astype(np.float32)
+        cs = CellSet(d, cells)
+        cs.upload(A.FIELD_T, vals)
+        d.read_from_device(A.FIELD_T)
+        d.finish_queue()
+        want = np.ones(d.N, np.float32)
+        want[cells] = vals
+        assert np.array_equal(d.T, want)
+        back = np.zeros(50, np.float32)
+        cs.download(A.FIELD_T, back)
+        d.finish_queue()  # luw_sync also drains the copy stream the read-back runs on
+        cs.close()
+    assert np.array_equal(back, vals)
+
+
+def test_plain_domains_reject_thermal_calls():
+    from latticeurbanwind_b200 import _cabi as A
+    from latticeurbanwind_b200.domain import Domain
+    with Domain(16, 4, 4, precision=0, features=0, w=1.0, arith=0) as d:
+        with pytest.raises(A.LuwError):
+            d.set_thermal(1.0)
+        with pytest.raises(A.LuwError):
+            d.read_gi()
