@@ -3,6 +3,7 @@
 // set_coriolis, run(steps), read_from_device, and dump rho / u.
 //   luw_host_case Nx Ny Nz Dx Dy Dz precision features arith nu steps downstream bufN buf_inv_tau buf_vertical spongeN sponge_inv_tau fx fy fz ox oy oz in.bin out.bin
 //   in.bin : flags[N] u8, rho[N] f32, u[3N] f32 (global images, n = x+(y+z*Ny)*Nx);  out.bin : rho[N] f32, u[3N] f32
+//   with LUW_TEMPERATURE in `features`: in.bin carries T[N] f32 after u, out.bin ends with T[N] f32; alpha / beta of the LBM constructor from LUW_CASE_ALPHA / LUW_CASE_BETA
 #include "lbm.hpp"
 #include <fstream>
 
@@ -26,13 +27,18 @@ int main(int argc, char** argv) {
 	const float ox = (float)atof(argv[a++]), oy = (float)atof(argv[a++]), oz = (float)atof(argv[a++]);
 	const char* in_path = argv[a++]; const char* out_path = argv[a++];
 
-	LBM lbm(uint3(Nx, Ny, Nz), Dx, Dy, Dz, nu, fx, fy, fz);
+	const bool thermal = (want&LUW_TEMPERATURE)!=0u;
+	const float alpha = thermal&&getenv("LUW_CASE_ALPHA") ? (float)atof(getenv("LUW_CASE_ALPHA")) : 0.0f, beta = thermal&&getenv("LUW_CASE_BETA") ? (float)atof(getenv("LUW_CASE_BETA")) : 0.0f;
+	LBM lbm(uint3(Nx, Ny, Nz), Dx, Dy, Dz, nu, fx, fy, fz, 0.0f, alpha, beta);
 	lbm.set_coriolis(ox, oy, oz);
 	const ulong N = lbm.get_N();
 	std::vector<uchar> flags(N); std::vector<float> rho(N), u(3ull*N);
 	std::ifstream in(in_path, std::ios::binary);
 	in.read((char*)flags.data(), (std::streamsize)N); in.read((char*)rho.data(), (std::streamsize)(4ull*N)); in.read((char*)u.data(), (std::streamsize)(12ull*N));
+	std::vector<float> T(thermal ? N : 0ull);
+	if(thermal) in.read((char*)T.data(), (std::streamsize)(4ull*N));
 	if(!in) print_error("cannot read the input images");
+	if(thermal) for(ulong n=0ull; n<N; n++) lbm.T[n] = T[n]; // FX/setup.cpp:5268-5317 writes lbm.T the same way
 	for(ulong n=0ull; n<N; n++) { // the way FX/setup.cpp writes boundary conditions: through the stitched global accessors
 		lbm.flags[n] = flags[n]; lbm.rho[n] = rho[n];
 		lbm.u.x[n] = u[n]; lbm.u.y[n] = u[N+n]; lbm.u.z[n] = u[2ull*N+n];
@@ -52,6 +58,11 @@ int main(int argc, char** argv) {
 		if(count!=(samples<steps ? samples : steps)) print_error("statistics sample count is off");
 		out.write((const char*)avg_u.data(), (std::streamsize)(12ull*N)); out.write((const char*)avg_rho.data(), (std::streamsize)(4ull*N));
 		out.write((const char*)M2_u.data(), (std::streamsize)(4ull*N)); out.write((const char*)M2_v.data(), (std::streamsize)(4ull*N)); out.write((const char*)M2_w.data(), (std::streamsize)(4ull*N));
+	}
+	if(thermal) {
+		lbm.T.read_from_device();
+		for(ulong n=0ull; n<N; n++) T[n] = lbm.T[n];
+		out.write((const char*)T.data(), (std::streamsize)(4ull*N));
 	}
 	delete stats;
 	printf("luw_host_case: %llu cells, %u domain(s), %llu steps, t = %llu\n", (unsigned long long)N, lbm.get_D(), (unsigned long long)steps, (unsigned long long)lbm.get_t());

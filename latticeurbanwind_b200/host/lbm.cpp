@@ -47,7 +47,8 @@ uint vram_required_mb_per_device(const uint Nx, const uint Ny, const uint Nz, co
 	const ulong ddf = (env_uint("LUW_PRECISION", lbm_settings.precision)==LUW_FP32) ? 4ull : 2ull;
 	const ulong cells = px*ly*lz;
 	const ulong halo = 8ull*(ddf==4ull ? 20ull : 17ull)*((Dx>1u ? ly*lz : 0ull)+(Dy>1u ? lz*lx : 0ull)+(Dz>1u ? lx*ly : 0ull));
-	return (uint)((cells*(19ull*ddf+17ull)+halo)/1048576ull)+1u;
+	const ulong thermal = (lbm_settings.features&LUW_TEMPERATURE) ? 7ull*ddf+4ull : 0ull; // gi + T (FX/lbm.cpp:124-126)
+	return (uint)((cells*(19ull*ddf+17ull+thermal)+halo)/1048576ull)+1u;
 }
 uint vram_required_mb_total(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz) { return Dx*Dy*Dz*vram_required_mb_per_device(Nx, Ny, Nz, Dx, Dy, Dz); }
 string default_filename(const string& path, const string& name, const string& extension, const ulong t) { // FX/lbm.cpp:235-239: <path or exe/export/><name>-<9-digit step><extension>
@@ -58,14 +59,15 @@ string default_filename(const string& path, const string& name, const string& ex
 string default_filename(const string& name, const string& extension, const ulong t) { return default_filename("", name, extension, t); }
 // FX/lbm.cpp:95-142 for this build: host mirrors rho, u, flags; device the same + 19 DDFs; traffic per step = 19 loads + 19 stores + flags (+ rho, u stores with UPDATE_FIELDS)
 static uint ddf_bytes() { return env_uint("LUW_PRECISION", lbm_settings.precision)==LUW_FP32 ? 4u : 2u; }
-uint bytes_per_cell_host() { return 17u; }
-uint bytes_per_cell_device() { return 19u*ddf_bytes()+17u; }
-uint bandwidth_bytes_per_cell_device() { return 38u*ddf_bytes()+1u+((lbm_settings.features&LUW_UPDATE_FIELDS) ? 16u : 0u); }
+static bool thermal_on() { return (lbm_settings.features&LUW_TEMPERATURE)!=0u; }
+uint bytes_per_cell_host() { return 17u+(thermal_on() ? 4u : 0u); }
+uint bytes_per_cell_device() { return 19u*ddf_bytes()+17u+(thermal_on() ? 7u*ddf_bytes()+4u : 0u); }
+uint bandwidth_bytes_per_cell_device() { return 38u*ddf_bytes()+1u+((lbm_settings.features&LUW_UPDATE_FIELDS) ? 16u : 0u)+(thermal_on() ? 14u*ddf_bytes()+((lbm_settings.features&LUW_UPDATE_FIELDS) ? 4u : 0u) : 0u); } // + 7 g loads + 7 g stores (+ T), FX/lbm.cpp:127-128
 #endif // LUW_USE_REFERENCE_UTILITIES
 
 uint LBM_Domain::lbm_features() { return lbm_settings.features; }
 
-luw_domain* LBM_Domain::create_handle(const int device, const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const int Ox, const int Oy, const int Oz, const float nu) {
+luw_domain* LBM_Domain::create_handle(const int device, const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const int Ox, const int Oy, const int Oz, const float nu, const float alpha, const float beta) {
 	luw_domain_params p;
 	memset(&p, 0, sizeof(p));
 	p.Nx = Nx; p.Ny = Ny; p.Nz = Nz; p.Dx = Dx; p.Dy = Dy; p.Dz = Dz; p.Ox = Ox; p.Oy = Oy; p.Oz = Oz;
@@ -79,22 +81,27 @@ luw_domain* LBM_Domain::create_handle(const int device, const uint Nx, const uin
 	p.device = device;
 	luw_domain* h = nullptr;
 	luw_check(luw_domain_create(&p, &h));
+	if(p.features&LUW_TEMPERATURE) luw_check(luw_thermal_params(h, lbm_kernel_literal(1.0f/(2.0f*alpha+0.5f)), lbm_kernel_literal(beta), lbm_kernel_literal(1.0f))); // def_w_T, def_beta, def_T_avg: FX/lbm.cpp:750-752
 	return h;
 }
 
 LBM_Domain::LBM_Domain(const int device, const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const int Ox, const int Oy, const int Oz,
-	const float nu, const float fx, const float fy, const float fz)
-	: Nx(Nx), Ny(Ny), Nz(Nz), Dx(Dx), Dy(Dy), Dz(Dz), Ox(Ox), Oy(Oy), Oz(Oz), nu(nu), fx(fx), fy(fy), fz(fz), device(device),
-	  handle(create_handle(device, Nx, Ny, Nz, Dx, Dy, Dz, Ox, Oy, Oz, nu)),
-	  rho(handle, LUW_FIELD_RHO, (ulong)Nx*Ny*Nz, 1u, 1.0f), u(handle, LUW_FIELD_U, (ulong)Nx*Ny*Nz, 3u, 0.0f), flags(handle, LUW_FIELD_FLAGS, (ulong)Nx*Ny*Nz, 1u, (uchar)0) {}
+	const float nu, const float fx, const float fy, const float fz, const float alpha, const float beta)
+	: Nx(Nx), Ny(Ny), Nz(Nz), Dx(Dx), Dy(Dy), Dz(Dz), Ox(Ox), Oy(Oy), Oz(Oz), nu(nu), fx(fx), fy(fy), fz(fz), alpha(alpha), beta(beta), device(device),
+	  handle(create_handle(device, Nx, Ny, Nz, Dx, Dy, Dz, Ox, Oy, Oz, nu, alpha, beta)),
+	  rho(handle, LUW_FIELD_RHO, (ulong)Nx*Ny*Nz, 1u, 1.0f), u(handle, LUW_FIELD_U, (ulong)Nx*Ny*Nz, 3u, 0.0f), flags(handle, LUW_FIELD_FLAGS, (ulong)Nx*Ny*Nz, 1u, (uchar)0) {
+	if(thermal()) T = Memory<float>(handle, LUW_FIELD_T, (ulong)Nx*Ny*Nz, 1u, 1.0f); // FX/lbm.cpp:323
+}
 
 LBM_Domain::~LBM_Domain() { luw_domain_destroy(handle); }
 
 // ---------------------------------------------------------------------------------------------------------------- LBM
-void LBM::construct(const uint Nx_, const uint Ny_, const uint Nz_, const uint Dx_, const uint Dy_, const uint Dz_, const float nu, const float fx, const float fy, const float fz) {
+void LBM::construct(const uint Nx_, const uint Ny_, const uint Nz_, const uint Dx_, const uint Dy_, const uint Dz_, const float nu, const float fx, const float fy, const float fz, const float alpha, const float beta) {
 #ifdef LUW_USE_REFERENCE_UTILITIES
 	settings_from_case_driver();
 #endif
+	if(env_uint("LUW_TEMPERATURE", (lbm_settings.features&LUW_TEMPERATURE) ? 1u : 0u)) lbm_settings.features |= LUW_TEMPERATURE; else lbm_settings.features &= ~(uint)LUW_TEMPERATURE;
+	if(!(lbm_settings.features&LUW_TEMPERATURE)&&(alpha!=0.0f||beta!=0.0f)) print_error("Thermal diffusion/expansion coefficients are set in the LBM constructor, but TEMPERATURE is not enabled (lbm_settings.features |= LUW_TEMPERATURE)."); // FX/lbm.cpp:1162
 	if(Dx_*Dy_*Dz_==0u) print_error("You specified 0 LBM grid domains. There has to be at least 1 domain in every direction.");
 	Dx = Dx_; Dy = Dy_; Dz = Dz_;
 	Nx = (Nx_/Dx)*Dx; Ny = (Ny_/Dy)*Dy; Nz = (Nz_/Dz)*Dz; // global size rounded down to multiples of the domain counts, FX/lbm.cpp:1058-1060
@@ -108,16 +115,18 @@ void LBM::construct(const uint Nx_, const uint Ny_, const uint Nz_, const uint D
 	for(uint d=0u; d<D; d++) {
 		const uint x = (d%(Dx*Dy))%Dx, y = (d%(Dx*Dy))/Dx, z = d/(Dx*Dy); // d = x+(y+z*Dy)*Dx, FX/lbm.cpp:1066-1073
 		const int device = d<lbm_settings.devices.size() ? lbm_settings.devices[d] : (int)(d%(uint)ndev);
-		lbm_domain[d] = new LBM_Domain(device, Nx/Dx+2u*Hx, Ny/Dy+2u*Hy, Nz/Dz+2u*Hz, Dx, Dy, Dz, (int)(x*Nx/Dx)-(int)Hx, (int)(y*Ny/Dy)-(int)Hy, (int)(z*Nz/Dz)-(int)Hz, nu, fx, fy, fz);
+		lbm_domain[d] = new LBM_Domain(device, Nx/Dx+2u*Hx, Ny/Dy+2u*Hy, Nz/Dz+2u*Hz, Dx, Dy, Dz, (int)(x*Nx/Dx)-(int)Hx, (int)(y*Ny/Dy)-(int)Hy, (int)(z*Nz/Dz)-(int)Hz, nu, fx, fy, fz, alpha, beta);
 		handles.push_back(lbm_domain[d]->get_handle());
+		if(LBM_Domain::thermal()) T_buffers.push_back(&lbm_domain[d]->T);
 		rho_buffers.push_back(&lbm_domain[d]->rho); u_buffers.push_back(&lbm_domain[d]->u); flags_buffers.push_back(&lbm_domain[d]->flags);
 	}
 	rho.bind(this, rho_buffers.data(), "rho"); u.bind(this, u_buffers.data(), "u"); flags.bind(this, flags_buffers.data(), "flags");
+	if(LBM_Domain::thermal()) T.bind(this, T_buffers.data(), "T");
 }
-LBM::LBM(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const float nu, const float fx, const float fy, const float fz, const float, const float, const float) { construct(Nx, Ny, Nz, Dx, Dy, Dz, nu, fx, fy, fz); }
-LBM::LBM(const uint Nx, const uint Ny, const uint Nz, const float nu, const float fx, const float fy, const float fz, const float, const float, const float) { construct(Nx, Ny, Nz, 1u, 1u, 1u, nu, fx, fy, fz); }
-LBM::LBM(const uint3 N, const uint Dx, const uint Dy, const uint Dz, const float nu, const float fx, const float fy, const float fz, const float, const float, const float) { construct(N.x, N.y, N.z, Dx, Dy, Dz, nu, fx, fy, fz); }
-LBM::LBM(const uint3 N, const float nu, const float fx, const float fy, const float fz, const float, const float, const float) { construct(N.x, N.y, N.z, 1u, 1u, 1u, nu, fx, fy, fz); }
+LBM::LBM(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const float nu, const float fx, const float fy, const float fz, const float, const float alpha, const float beta) { construct(Nx, Ny, Nz, Dx, Dy, Dz, nu, fx, fy, fz, alpha, beta); }
+LBM::LBM(const uint Nx, const uint Ny, const uint Nz, const float nu, const float fx, const float fy, const float fz, const float, const float alpha, const float beta) { construct(Nx, Ny, Nz, 1u, 1u, 1u, nu, fx, fy, fz, alpha, beta); }
+LBM::LBM(const uint3 N, const uint Dx, const uint Dy, const uint Dz, const float nu, const float fx, const float fy, const float fz, const float, const float alpha, const float beta) { construct(N.x, N.y, N.z, Dx, Dy, Dz, nu, fx, fy, fz, alpha, beta); }
+LBM::LBM(const uint3 N, const float nu, const float fx, const float fy, const float fz, const float, const float alpha, const float beta) { construct(N.x, N.y, N.z, 1u, 1u, 1u, nu, fx, fy, fz, alpha, beta); }
 LBM::~LBM() {
 #ifdef LUW_USE_REFERENCE_UTILITIES
 	info.print_finalize(); // FX/lbm.cpp: the console table is closed with the simulation
@@ -133,19 +142,22 @@ void LBM::communicate(const int payload) { // FX/lbm.cpp:1907-1958: x, then y, t
 void LBM::initialize() { // FX/lbm.cpp:1221-1260
 	const uint D = get_D();
 	for(uint d=0u; d<D; d++) { lbm_domain[d]->rho.enqueue_write_to_device(); lbm_domain[d]->u.enqueue_write_to_device(); lbm_domain[d]->flags.enqueue_write_to_device(); }
+	if(LBM_Domain::thermal()) for(uint d=0u; d<D; d++) lbm_domain[d]->T.enqueue_write_to_device();
 	for(uint d=0u; d<D; d++) lbm_domain[d]->increment_time_step(); // slot parity t = 1 for the initial DDF layout
 	communicate(LUW_HALO_RHO_U_FLAGS);
 	for(uint d=0u; d<D; d++) lbm_domain[d]->enqueue_initialize();
 	communicate(LUW_HALO_RHO_U_FLAGS);
 	communicate(LUW_HALO_FI);
+	if(LBM_Domain::thermal()) { communicate(LUW_HALO_T); communicate(LUW_HALO_GI); } // communicate_T(); communicate_gi(); (time step must be odd here)
 	for(uint d=0u; d<D; d++) lbm_domain[d]->finish_queue();
 	for(uint d=0u; d<D; d++) lbm_domain[d]->reset_time_step();
 	initialized = true;
 }
-void LBM::do_time_step() { // FX/lbm.cpp:1262-1290 (GRAPHICS / TEMPERATURE exchanges and the per-step finish_queue are gone)
+void LBM::do_time_step() { // FX/lbm.cpp:1262-1290 (GRAPHICS exchanges and the per-step finish_queue are gone)
 	const uint D = get_D();
 	for(uint d=0u; d<D; d++) lbm_domain[d]->enqueue_stream_collide();
 	communicate(LUW_HALO_FI);
+	if(LBM_Domain::thermal()) communicate(LUW_HALO_GI); // communicate_gi()
 	for(uint d=0u; d<D; d++) lbm_domain[d]->increment_time_step();
 }
 void LBM::run(const ulong steps, const ulong total_steps) { // FX/lbm.cpp:1292-1312

@@ -67,7 +67,7 @@ struct Device { LBM_Device_Info info; luw_domain* dom = nullptr; }; // what LBM_
 // (the case driver does that where the reference's update_coriolis / update_buffer_nudging / update_top_sponge set their globals, FX/setup.cpp:3800-3903).
 struct LBM_Settings {
 	uint precision = LUW_FP16C; // FX/defines.hpp:14 (LUW ships FP16C); LUW_FP32 / LUW_FP16S / LUW_FP16C; env LUW_PRECISION overrides
-	uint features = LUW_UPDATE_FIELDS|LUW_VOLUME_FORCE|LUW_EQUILIBRIUM_BOUNDARIES|LUW_SUBGRID; // FX/defines.hpp:17-24; nudging / sponge added by the setters below
+	uint features = LUW_UPDATE_FIELDS|LUW_VOLUME_FORCE|LUW_EQUILIBRIUM_BOUNDARIES|LUW_SUBGRID; // FX/defines.hpp:17-24; nudging / sponge added by the setters below; |= LUW_TEMPERATURE for the thermal D3Q7 extension (FX/defines.hpp:23; env LUW_TEMPERATURE=1)
 	uint arith = LUW_ARITH_FAST; // the reference builds with -cl-mad-enable (FX/opencl.hpp:305); LUW_ARITH_STRICT reproduces the CPU oracle bit for bit
 	int downstream_face = 0; // def_downstream_face
 	uint buffer_N = 0u; float buffer_inv_tau = 0.0f; int buffer_nudge_vertical = 0; // BUFFER_NUDGING (FX/lbm.cpp:770-776)
@@ -181,15 +181,19 @@ private:
 	uint Nx=1u, Ny=1u, Nz=1u, Dx=1u, Dy=1u, Dz=1u; int Ox=0, Oy=0, Oz=0;
 	ulong t = 0ull;
 	float nu = 1.0f/6.0f, fx=0.0f, fy=0.0f, fz=0.0f, omega_x=0.0f, omega_y=0.0f, omega_z=0.0f;
+	float alpha = 0.0f, beta = 0.0f, T_avg = 1.0f; // thermal diffusion / expansion coefficients, average temperature (FX/lbm.hpp:37)
 	int device = 0;
 	luw_domain* handle = nullptr; // declared before the buffers: they are built on it
 	ulong t_last_update_fields = max_ulong;
-	static luw_domain* create_handle(const int device, const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const int Ox, const int Oy, const int Oz, const float nu);
+	static luw_domain* create_handle(const int device, const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const int Ox, const int Oy, const int Oz, const float nu, const float alpha, const float beta);
 public:
 	Memory<float> rho; Memory<float> u; Memory<uchar> flags; // host + device buffers of this domain (FX/lbm.hpp:60-63; rho starts at 1, u and flags at 0: FX/lbm.cpp:283-288)
+	Memory<float> T; // temperature (FX/lbm.hpp:77, starts at 1: FX/lbm.cpp:323); only allocated with LUW_TEMPERATURE (length() == 0 otherwise). gi stays device-only like in the reference
 
 	LBM_Domain(const int device, const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const int Ox, const int Oy, const int Oz,
-		const float nu, const float fx, const float fy, const float fz);
+		const float nu, const float fx, const float fy, const float fz, const float alpha=0.0f, const float beta=0.0f);
+	static bool thermal() { return (lbm_features()&LUW_TEMPERATURE)!=0u; }
+	float get_alpha() const { return alpha; } float get_beta() const { return beta; } float get_T_avg() const { return T_avg; } // FX/lbm.hpp:151-153
 	~LBM_Domain();
 	LBM_Domain(const LBM_Domain&) = delete;
 	LBM_Domain& operator=(const LBM_Domain&) = delete;
@@ -253,7 +257,7 @@ private:
 	uint Nx=1u, Ny=1u, Nz=1u, Dx=1u, Dy=1u, Dz=1u;
 	bool initialized = false;
 	std::vector<luw_domain*> handles;
-	void construct(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const float nu, const float fx, const float fy, const float fz);
+	void construct(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const float nu, const float fx, const float fy, const float fz, const float alpha, const float beta);
 	void initialize(); // FX/lbm.cpp:1221-1260
 	void do_time_step(); // FX/lbm.cpp:1262-1290
 	void communicate(const int payload);
@@ -354,6 +358,7 @@ public:
 	LBM_Domain** lbm_domain = nullptr; // one LBM domain per GPU
 	Memory_Container<float> rho, u;
 	Memory_Container<uchar> flags;
+	Memory_Container<float> T; // bound only with LUW_TEMPERATURE (FX/lbm.hpp:441, FX/lbm.cpp:1102)
 
 	LBM(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const float nu, const float fx=0.0f, const float fy=0.0f, const float fz=0.0f, const float sigma=0.0f, const float alpha=0.0f, const float beta=0.0f);
 	LBM(const uint Nx, const uint Ny, const uint Nz, const float nu, const float fx=0.0f, const float fy=0.0f, const float fz=0.0f, const float sigma=0.0f, const float alpha=0.0f, const float beta=0.0f);
@@ -373,6 +378,7 @@ public:
 	uint get_D() const { return Dx*Dy*Dz; }
 	float get_nu() const { return lbm_domain[0]->get_nu(); }
 	float get_tau() const { return 3.0f*get_nu()+0.5f; }
+	float get_alpha() const { return lbm_domain[0]->get_alpha(); } float get_beta() const { return lbm_domain[0]->get_beta(); } float get_T_avg() const { return lbm_domain[0]->get_T_avg(); } // FX/lbm.hpp:483-485
 	float get_fx() const { return lbm_domain[0]->get_fx(); } float get_fy() const { return lbm_domain[0]->get_fy(); } float get_fz() const { return lbm_domain[0]->get_fz(); }
 	ulong get_t() const { return lbm_domain[0]->get_t(); }
 	float get_Re_max() const { return 0.57735027f*sqrtf((float)Nx*(float)Nx+(float)Ny*(float)Ny+(float)Nz*(float)Nz)/get_nu(); } // Re < c*L_max/nu, FX/lbm.hpp:480
@@ -416,7 +422,7 @@ public:
 	float3 size() const { return float3((float)Nx, (float)Ny, (float)Nz); }
 	float3 center() const { return float3(0.5f*(float)Nx-0.5f, 0.5f*(float)Ny-0.5f, 0.5f*(float)Nz-0.5f); }
 private:
-	std::vector<Memory<float>*> rho_buffers, u_buffers;
+	std::vector<Memory<float>*> rho_buffers, u_buffers, T_buffers;
 	std::vector<Memory<uchar>*> flags_buffers;
 };
 

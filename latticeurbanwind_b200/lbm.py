@@ -58,8 +58,8 @@ class _Base:
         # thermal D3Q7 extension (features & TEMPERATURE): LBM ctor arguments alpha (thermal diffusion coefficient) and beta (thermal expansion
         # coefficient), FX/lbm.cpp:1040-1047; def_w_T = 1/(2 alpha + 1/2) in float arithmetic like FX/lbm.cpp:750
         self.thermal = bool(features & A.TEMPERATURE)
-        self.w_T = float(np.float32(1.0) / (np.float32(2.0) * np.float32(alpha) + np.float32(0.5)))
-        self.beta, self.T_avg = float(beta), float(T_avg)
+        self.w_T = float(cases.kernel_literal(np.float32(1.0) / (np.float32(2.0) * np.float32(alpha) + np.float32(0.5))))
+        self.beta, self.T_avg = float(cases.kernel_literal(beta)), float(cases.kernel_literal(T_avg))
         self.t = 0
         self.initialized = False
 

@@ -106,3 +106,42 @@ def test_plain_domains_reject_thermal_calls():
             d.set_thermal(1.0)
         with pytest.raises(A.LuwError):
             d.read_gi()
+
+
+# ---------------------------------------------------------------------------------------------- the C++ host layer (reference LBM API) with lbm.T
+def _run_cpp(tmp_path, shape, D, precision, steps, flags, rho, u, T, alpha, beta):
+    import os
+    import subprocess
+    from tests import test_cpp_host as CPP
+    CPP.build()
+    inp, out = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(inp, "wb") as fh:
+        fh.write(flags.tobytes()); fh.write(rho.tobytes()); fh.write(u.tobytes()); fh.write(T.tobytes())
+    z = CPP.ZONES
+    args = [CPP.DRIVER, *map(str, shape), *map(str, D), str(precision), str(H.FEATURE_SETS["luwT"]), "0", repr(1e-6), str(steps), str(z["downstream_face"]),
+            str(z["buffer_N"]), repr(z["buffer_inv_tau"]), str(z["buffer_nudge_vertical"]), str(z["sponge_N"]), repr(z["sponge_inv_tau"]),
+            *[repr(float(v)) for v in H.FORCE], *[repr(float(v)) for v in H.OMEGA], inp, out]
+    r = subprocess.run(args, capture_output=True, text=True, env=dict(os.environ, LUW_CASE_ALPHA=repr(alpha), LUW_CASE_BETA=repr(beta)))
+    assert r.returncode == 0, r.stderr
+    N = int(np.prod(shape))
+    raw = np.fromfile(out, np.float32)
+    assert raw.size == 5 * N
+    return raw[:N].copy(), raw[N:4 * N].copy(), raw[4 * N:].copy()
+
+
+def test_cpp_lbm_with_temperature_equals_oracle(oracle_lib, tmp_path):
+    """LBM(N, nu, f, sigma, alpha, beta) + lbm.T through the stitched accessor + run(steps): rho, u, T equal the oracle's (STRICT), and the
+    2x2x2 decomposition (communicate_T / communicate_gi) equals the single domain."""
+    from tests import test_cpp_host as CPP
+    O = oracle_lib
+    shape = (64, 20, 12)
+    flags, rho, u, T = H.thermal_case(shape, seed=5)
+    alpha, beta = 2.0e-3, 0.4
+    thermal = dict(w_T=cases.kernel_literal(np.float32(1.0) / (np.float32(2.0) * np.float32(alpha) + np.float32(0.5))), beta=cases.kernel_literal(beta), T_avg=1.0)
+    ref = H.run_cpu_thermal(O.Oracle(), O, shape, 1, O.FEATURE_SETS["luwT"], flags, rho, u, T, 6, cases.relaxation_rate(1e-6), zones=CPP.ZONES, thermal=thermal)
+    one = _run_cpp(tmp_path, shape, (1, 1, 1), 1, 6, flags, rho, u, T, alpha, beta)
+    for g, r, name in zip(one, (ref[1], ref[2], ref[4]), ("rho", "u", "T")):
+        assert np.array_equal(g, r), name
+    dec = _run_cpp(tmp_path, shape, (2, 2, 2), 1, 6, flags, rho, u, T, alpha, beta)
+    for g, r, name in zip(dec, one, ("rho", "u", "T")):
+        assert np.array_equal(g, r), name
