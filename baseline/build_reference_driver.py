@@ -36,7 +36,10 @@ def build(reference_root="/root/reference"):
                 continue
             os.symlink(os.path.join(fx, name), os.path.join(tmp, name))
         defines = open(os.path.join(fx, "defines.hpp")).read()
-        for flag in ("GRAPHICS", "TEMPERATURE", "FORCE_FIELD"):
+        # LUW_DROPIN_TEMPERATURE=1 leaves the reference's TEMPERATURE switch on: setup.cpp's 19 TEMPERATURE blocks then compile against lbm.T / alpha / beta of the host
+        # layer and the LBM runs LUW_TEMPERATURE domains. Off by default until the thermal kernels have been observed on a B200.
+        off = ("GRAPHICS", "FORCE_FIELD") if os.environ.get("LUW_DROPIN_TEMPERATURE") == "1" else ("GRAPHICS", "TEMPERATURE", "FORCE_FIELD")
+        for flag in off:
             defines = re.sub(r"(?m)^#define %s\b" % flag, "//#define %s" % flag, defines)
         open(os.path.join(tmp, "defines.hpp"), "w").write(defines)
         host = os.path.join(ROOT, "latticeurbanwind_b200", "host")

@@ -36,6 +36,9 @@ static void settings_from_case_driver() {
 	lbm_settings.set_buffer_nudging(buffer_nudging_active&&buffer_n_cells>0 ? (uint)buffer_n_cells : 0u, buffer_inv_tau_lbmu, buffer_nudge_vertical!=0);
 	lbm_settings.set_top_sponge(top_sponge_active&&sponge_n_cells>0 ? (uint)sponge_n_cells : 0u, sponge_inv_tau_lbmu);
 	if(top_sponge_active&&sponge_ref_mode!=0) print_error("sponge_ref_mode "+to_string(sponge_ref_mode)+" is not implemented (the reference kernel implements mode 0 only, FX/kernel.cpp:1597).");
+#ifdef TEMPERATURE // the reference's compile-time switch (FX/defines.hpp:23) left on in the tree this is built in: the case driver then writes lbm.T and passes alpha / beta
+	lbm_settings.features |= LUW_TEMPERATURE;
+#endif
 }
 float3 vtk_origin_shift = float3(0.0f, 0.0f, 0.0f); // FX/lbm.cpp:18-20
 // Device memory of THIS build per domain: DDFs (19 fpxx) + rho, u (16 B) + flags (1 B) per cell of the padded local lattice, + halo buffers. The reference's

@@ -19,13 +19,13 @@ pytestmark = pytest.mark.skipif(not os.path.isfile(os.path.join(FX, "setup.cpp")
 ALLOWED = re.compile(r"\bKernel\b|\bDevice\b|\bdevice\b|kernel_apply|main_arguments|setup\.cpp:1034:")
 
 
-def _scratch(tmp_path):
+def _scratch(tmp_path, off=("GRAPHICS", "TEMPERATURE", "FORCE_FIELD")):
     d = str(tmp_path)
     for f in ("utilities.hpp", "units.hpp", "shapes.hpp", "setup.hpp", "info.hpp", "interpolation.hpp", "interpolation_hd.hpp", "fluxcorrection.hpp", "lodepng.hpp", "graphics.hpp",
               "setup.cpp", "interpolation.cpp", "interpolation_hd.cpp", "fluxcorrection.cpp", "info.cpp"):
         shutil.copy(os.path.join(FX, f), os.path.join(d, f))
     defines = open(os.path.join(FX, "defines.hpp")).read()
-    for name in ("GRAPHICS", "TEMPERATURE", "FORCE_FIELD"):  # not part of this path
+    for name in off:  # not part of this path; TEMPERATURE can stay on, see the last test
         defines = re.sub(r"(?m)^#define %s\b" % name, "//#define %s" % name, defines)
     open(os.path.join(d, "defines.hpp"), "w").write(defines)
     open(os.path.join(d, "lbm.hpp"), "w").write('#pragma once\n#include "utilities.hpp"\n#define LUW_USE_REFERENCE_UTILITIES\n#include "%s/latticeurbanwind_b200/host/lbm.hpp"\n' % ROOT)
@@ -48,3 +48,13 @@ def test_case_driver_compiles_up_to_the_documented_edits(tmp_path):
     other = [e for e in errs if not ALLOWED.search(e)]
     assert other == [], "\n".join(other)
     assert len(errs) <= 14
+
+
+@pytest.mark.parametrize("src", ["setup.cpp", "info.cpp", "our_lbm.cpp"])
+def test_case_driver_compiles_with_temperature_on(tmp_path, src):
+    """The reference's shipped defines.hpp has TEMPERATURE on (FX/defines.hpp:23). With it left on, the case driver's TEMPERATURE blocks (lbm.T[n] = ...,
+    lbm.lbm_domain[d]->T.enqueue_read_from_device(), lbm.T.write_device_to_vtk(...), FX/setup.cpp:4420,4483,4773,5062,5300,5497,5583) and info.cpp's
+    get_alpha() / get_beta() compile against the host layer's thermal surface."""
+    errs = _errors(_scratch(tmp_path, off=("GRAPHICS", "FORCE_FIELD")), src)
+    other = [e for e in errs if not ALLOWED.search(e)]
+    assert other == [], "\n".join(other)
