@@ -34,7 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-F_UF, F_VF, F_EQ, F_SG, F_NUDGE, F_SPONGE = 1, 2, 4, 8, 16, 32
+F_UF, F_VF, F_EQ, F_SG, F_NUDGE, F_SPONGE, F_TEMPERATURE = 1, 2, 4, 8, 16, 32, 64
 WORKLOADS = {
     # name: (case, local block shape incl. halos, precision, features, oracle feature-set name, nu, description)
     "channel512_fp16s": ("channel", (512, 512, 512), 1, F_EQ, "chan", 1.0 / 6.0, "C2 empty channel 512^3 FP16S (TYPE_E x faces, TYPE_S walls), SRT nu=1/6"),
@@ -46,10 +46,32 @@ WORKLOADS = {
                        "C3 staggered cube array 1024x1024x256 FP16S without the relaxation zones (cost attribution only)"),
     "urban_fp16s_uf": ("urban", (1024, 1024, 256), 1, F_UF | F_VF | F_EQ | F_SG | F_NUDGE | F_SPONGE, "luw", 1e-6,
                        "C3 staggered cube array 1024x1024x256 FP16S, full LUW step with UPDATE_FIELDS (+16 B/cell rho/u stores)"),
+    # the reference's shipped build (TEMPERATURE on). Not a headline workload: one-cell-per-thread kernel, unobserved on a B200 in round 1
+    "urban_fp16s_thermal": ("urban", (1024, 1024, 256), 1, F_UF | F_VF | F_EQ | F_SG | F_NUDGE | F_SPONGE | F_TEMPERATURE, "luwT", 1e-6,
+                            "C3 staggered cube array 1024x1024x256 FP16S, full LUW step with UPDATE_FIELDS and thermal D3Q7 transport (TYPE_E cells carry TYPE_T, alpha = 2e-3)"),
 }
+THERMAL_ALPHA = 2.0e-3  # thermal diffusion coefficient of the thermal workload (lattice units); def_w_T = 1/(2 alpha + 1/2), beta = 0 (LUW runs without gravity)
 ZONES = dict(downstream_face=2, buffer_N=16, buffer_inv_tau=0.01, buffer_nudge_vertical=1, sponge_N=20, sponge_inv_tau=0.02)
 OMEGA = (0.0, 5.6e-6, 4.7e-6)  # Omega_lbm of SURVEY.md 8d (7.292e-5 * (cos 40, sin 40) * dt)
 B_ALG = {0: 153, 1: 77, 2: 77}  # algorithmic bytes per cell-step: 19 DDF loads + 19 stores + 1 flag byte (FX/lbm.cpp:121-122)
+
+
+def alg_bytes(precision, features):
+    """B_ALG, plus 7 g loads + 7 g stores per cell-step with the thermal extension (FX/lbm.cpp:127-128)."""
+    return B_ALG[precision] + (14 * (4 if precision == 0 else 2) if features & F_TEMPERATURE else 0)
+
+
+def thermal_fields(flags, shape):
+    """Temperature setup of the thermal workload, in place on a block's flags: every TYPE_E cell also gets TYPE_T (what the case driver does for a WRF deck
+    with a T column, FX/setup.cpp:5268-5317); returns T: a stable stratification 1 .. 1.02 over the block height."""
+    Nx, Ny, Nz = shape
+    flags[(flags & 0x03) == 0x02] |= 0x04
+    return np.repeat((np.float32(1.0) + np.float32(0.02) * np.arange(Nz, dtype=np.float32) / np.float32(Nz)).astype(np.float32), Nx * Ny)
+
+
+def thermal_w_T():
+    from latticeurbanwind_b200 import cases
+    return float(cases.kernel_literal(np.float32(1.0) / (np.float32(2.0) * np.float32(THERMAL_ALPHA) + np.float32(0.5))))
 DTYPE = {0: "f32 arithmetic, f32 DDF storage", 1: "f32 arithmetic, FP16S DDF storage", 2: "f32 arithmetic, FP16C DDF storage"}
 # Decomposition per GPU count (the deck's n_gpu). Faces normal to x are the expensive ones in this memory layout (every face cell is a 2-byte element in
 # its own 1 KB row: measured 39 + 60 us to extract + insert a 131 k-cell x face against 9 + 9 us for a z face, profiles/), so the defaults split z and y
@@ -150,17 +172,24 @@ def cpu_run(workload, steps, warmup, budget_s=20.0):
     p = O.make_params(Nx, Ny, Nz, precision, features, w=cases.relaxation_rate(nu), **zones)
     fi = np.zeros(19 * p.N, O.ddf_dtype(precision))
     eng.bind(p)
-    eng.initialize(fi, rho, u, flags)
+    if features & F_TEMPERATURE:
+        gi, T = np.zeros(7 * p.N, O.ddf_dtype(precision)), thermal_fields(flags, Ng)
+        eng.set_thermal(thermal_w_T(), 0.0, 1.0)
+        eng.initialize_thermal(fi, rho, u, flags, gi, T)
+        step = lambda t: eng.stream_collide_thermal(fi, rho, u, flags, t, (0, 0, 0), OMEGA, gi, T)
+    else:
+        eng.initialize(fi, rho, u, flags)
+        step = lambda t: eng.stream_collide(fi, rho, u, flags, t, (0, 0, 0), OMEGA)
     t = 0
     t0 = time.perf_counter()
-    eng.stream_collide(fi, rho, u, flags, t, (0, 0, 0), OMEGA); t += 1
+    step(t); t += 1
     one = time.perf_counter() - t0
     steps = max(1, min(steps, int(budget_s / max(one, 1e-3))))
     for _ in range(max(0, min(warmup, 2))):
-        eng.stream_collide(fi, rho, u, flags, t, (0, 0, 0), OMEGA); t += 1
+        step(t); t += 1
     t0 = time.perf_counter()
     for _ in range(steps):
-        eng.stream_collide(fi, rho, u, flags, t, (0, 0, 0), OMEGA); t += 1
+        step(t); t += 1
     dt = time.perf_counter() - t0
     mlups = p.N * steps / dt / 1e6
     sample = f"{Nx}x{Ny}x{Nz} block of the workload's case ({p.N / 1e6:.1f} M cells), {steps} steps, OpenMP over z-planes on {cores} host threads"
@@ -237,6 +266,11 @@ def build_domain(Domain, cases, workload, arith, device, D=(1, 1, 1), O=(0, 0, 0
         d.flags, d.rho, d.u = pinned(d.N, np.uint8), pinned(d.N, np.float32), pinned(3 * d.N, np.float32)
     cases.block_case(case, shape if Ng is None else Ng, O, shape, out=(d.flags, d.rho, d.u))
     d.omega = OMEGA if features & F_VF else (0.0, 0.0, 0.0)
+    if features & F_TEMPERATURE:
+        if pinned is not None:
+            d.T = pinned(d.N, np.float32)
+        d.T[:] = thermal_fields(d.flags, shape)
+        d.set_thermal(thermal_w_T(), 0.0, 1.0)
     return d
 
 
@@ -266,11 +300,12 @@ def bench_single(args, workload, arith, A, cases, Domain, CellSet, pinned_empty,
         # The second pass brackets every launch with its own event pair; that serialises the launches (no back-to-back overlap of tail and head) and is
         # reported as `kernel_ms_isolated` -- the two must agree to a few per cent.
         kern_ms = ms / K
-        achieved = N * B_ALG[precision] / (kern_ms * 1e-3) / 1e9
+        achieved = N * alg_bytes(precision, features) / (kern_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "k_stream_collide_tile" if d.uses_tiles() else "k_stream_collide", "kernel_ms": kern_ms, "kernel_ms_isolated": kms / max(kn, 1),
+                "kernel": "k_stream_collide_tile" if d.uses_tiles() else "k_stream_collide_thermal" if features & F_TEMPERATURE else "k_stream_collide",
+                "kernel_ms": kern_ms, "kernel_ms_isolated": kms / max(kn, 1),
                 "share_of_step": 1.0,
-                "alg_bytes_per_cell": B_ALG[precision], "cells_per_launch": N, "peak_source": peak_src,
+                "alg_bytes_per_cell": alg_bytes(precision, features), "cells_per_launch": N, "peak_source": peak_src,
                 "frac_of_8000_datasheet": achieved / 8000.0}
         traffic = os.path.join(ROOT, "profiles", f"traffic_{workload}.json")
         if os.path.isfile(traffic):  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
@@ -391,11 +426,13 @@ def bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src):
     Ng = tuple((n - 2 * h) * v for n, h, v in zip(shape, H, D))  # global lattice whose blocks have exactly the workload's local size incl. halos
     zones = ZONES if features & (F_NUDGE | F_SPONGE) else {}
     lbm = DistributedLBM(Ng, D, device=local, nu=nu, precision=precision, features=features, arith=arith,
-                         omega=OMEGA if features & F_VF else (0.0, 0.0, 0.0), transport=args.transport, **zones)
+                         omega=OMEGA if features & F_VF else (0.0, 0.0, 0.0), transport=args.transport,
+                         **(dict(alpha=THERMAL_ALPHA) if features & F_TEMPERATURE else {}), **zones)
     assert tuple(lbm.Nl) == tuple(shape)
     flags, rho, u = cases.block_case(case, Ng, lbm.O, shape)
+    T = thermal_fields(flags, shape) if features & F_TEMPERATURE else None  # per-block stratification: a benchmark input, not a physical profile across blocks
     dist.barrier()  # host-side case generation takes seconds and not the same number on every rank: start the first halo exchange together
-    lbm.initialize(flags, rho, u)
+    lbm.initialize(flags, rho, u, T)
     K, W = args.steps, args.warmup
     lbm.run(W)
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
@@ -420,14 +457,14 @@ def bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src):
         Nglob = int(np.prod(Ng))
         Nloc = int(np.prod(shape))
         mlups = Nglob * K / ms / 1e3
-        achieved = Nloc * B_ALG[precision] / (kern_ms * 1e-3) / 1e9
+        achieved = Nloc * alg_bytes(precision, features) / (kern_ms * 1e-3) / 1e9
         halo_bytes = sum(2 * lbm.halo_bytes(A.HALO_FI, a) for a in range(3) if D[a] > 1)
         res = {"metric": "D3Q19 MLUP/s", "value": mlups, "unit": "MLUP/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[precision], "data": "synthetic",
                "config": {"workload": desc, "name": args.workload, "lattice": list(Ng), "block_per_gpu_incl_halo": list(shape), "features": features,
                           "arith": args.arith, "decomposition": list(D), "halo_transport": args.transport, "l2": "state per GPU is far larger than the 126 MB L2; no flush needed"},
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                            "kernel": "k_stream_collide_tile", "kernel_ms": kern_ms, "share_of_step": kern_ms / (ms / K), "alg_bytes_per_cell": B_ALG[precision],
+                            "kernel": "k_stream_collide_thermal" if features & F_TEMPERATURE else "k_stream_collide_tile", "kernel_ms": kern_ms, "share_of_step": kern_ms / (ms / K), "alg_bytes_per_cell": alg_bytes(precision, features),
                             "cells_per_launch": Nloc, "peak_source": peak_src},
                "halo": {"nvlink_bytes_out_per_gpu_per_step": int(halo_bytes), "exposed_ms_per_step": ms / K - kern_ms},
                "e2e": {"value": mlups, "unit": "MLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
