@@ -3,6 +3,8 @@
 // set_coriolis, run(steps), read_from_device, and dump rho / u.
 //   luw_host_case Nx Ny Nz Dx Dy Dz precision features arith nu steps downstream bufN buf_inv_tau buf_vertical spongeN sponge_inv_tau fx fy fz ox oy oz in.bin out.bin
 //   in.bin : flags[N] u8, rho[N] f32, u[3N] f32 (global images, n = x+(y+z*Ny)*Nx);  out.bin : rho[N] f32, u[3N] f32
+//   LUW_CASE_TRIANGLES=<file> (u32 n, pmin[3], pmax[3], p0[3n], p1[3n], p2[3n] f32, lattice coordinates): the geometry is voxelised on the device first, through
+//   LBM::voxelize_triangles_on_device like FX/setup.cpp:4084-4125 does with the STL, the flags of in.bin are OR-ed on top, and out.bin ends with flags[N] u8
 //   with LUW_TEMPERATURE in `features`: in.bin carries T[N] f32 after u, out.bin ends with T[N] f32; alpha / beta of the LBM constructor from LUW_CASE_ALPHA / LUW_CASE_BETA
 #include "lbm.hpp"
 #include <fstream>
@@ -39,8 +41,20 @@ int main(int argc, char** argv) {
 	if(thermal) in.read((char*)T.data(), (std::streamsize)(4ull*N));
 	if(!in) print_error("cannot read the input images");
 	if(thermal) for(ulong n=0ull; n<N; n++) lbm.T[n] = T[n]; // FX/setup.cpp:5268-5317 writes lbm.T the same way
+	const char* tri_path = getenv("LUW_CASE_TRIANGLES");
+	if(tri_path) {
+		std::ifstream tf(tri_path, std::ios::binary);
+		uint ntri = 0u; float bb[6];
+		tf.read((char*)&ntri, 4); tf.read((char*)bb, 24);
+		std::vector<float> p0(3ull*ntri), p1(3ull*ntri), p2(3ull*ntri);
+		tf.read((char*)p0.data(), (std::streamsize)(12ull*ntri)); tf.read((char*)p1.data(), (std::streamsize)(12ull*ntri)); tf.read((char*)p2.data(), (std::streamsize)(12ull*ntri));
+		if(!tf) print_error("cannot read the triangle file");
+		const std::vector<uint> given = lbm.voxelize_triangles_on_device(p0.data(), p1.data(), p2.data(), ntri, float3(bb[0], bb[1], bb[2]), float3(bb[3], bb[4], bb[5]));
+		for(uint d=0u; d<lbm.get_D(); d++) printf("luw_host_case: domain %u voxelised %u of %u triangles\n", d, given[d], ntri);
+		lbm.flags.read_from_device(); // host mirrors of all domains, like FX/lbm.cpp:1641-1644
+	}
 	for(ulong n=0ull; n<N; n++) { // the way FX/setup.cpp writes boundary conditions: through the stitched global accessors
-		lbm.flags[n] = flags[n]; lbm.rho[n] = rho[n];
+		lbm.flags[n] = tri_path ? (uchar)(lbm.flags[n]|flags[n]) : flags[n]; lbm.rho[n] = rho[n];
 		lbm.u.x[n] = u[n]; lbm.u.y[n] = u[N+n]; lbm.u.z[n] = u[2ull*N+n];
 	}
 	lbm.run(0ull); // initialise only (FX/setup.cpp:4852)
@@ -63,6 +77,11 @@ int main(int argc, char** argv) {
 		lbm.T.read_from_device();
 		for(ulong n=0ull; n<N; n++) T[n] = lbm.T[n];
 		out.write((const char*)T.data(), (std::streamsize)(4ull*N));
+	}
+	if(tri_path) {
+		lbm.flags.read_from_device();
+		for(ulong n=0ull; n<N; n++) flags[n] = lbm.flags[n];
+		out.write((const char*)flags.data(), (std::streamsize)N);
 	}
 	delete stats;
 	printf("luw_host_case: %llu cells, %u domain(s), %llu steps, t = %llu\n", (unsigned long long)N, lbm.get_D(), (unsigned long long)steps, (unsigned long long)lbm.get_t());

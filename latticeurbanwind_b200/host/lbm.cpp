@@ -70,6 +70,34 @@ uint bandwidth_bytes_per_cell_device() { return 38u*ddf_bytes()+1u+((lbm_setting
 
 uint LBM_Domain::lbm_features() { return lbm_settings.features; }
 
+// FX/lbm.cpp:52-90 (triangle_aabb, make_projected_bounds, overlap_1d, overlaps_projected) and :1457-1483 (collect_domain_triangle_ids), pad 1 cell, eps 1e-4
+std::vector<uint> luw_cull_triangles(const float* p0, const float* p1, const float* p2, const uint triangle_number, const uint direction,
+	const int Ox, const int Oy, const int Oz, const uint local_Nx, const uint local_Ny, const uint local_Nz) {
+	const float lo[3] = { (float)Ox, (float)Oy, (float)Oz };
+	const float hi[3] = { (float)(Ox+(int)local_Nx-1), (float)(Oy+(int)local_Ny-1), (float)(Oz+(int)local_Nz-1) };
+	const uint a = direction==0u ? 1u : 0u, b = direction==2u ? 1u : 2u; // the two axes of the projection plane: yz, xz, xy
+	const float pad = 1.0f, eps = 1.0e-4f;
+	std::vector<uint> ids;
+	ids.reserve(triangle_number/4u+1u);
+	for(uint i=0u; i<triangle_number; i++) {
+		bool keep = true;
+		for(const uint axis : { a, b }) {
+			const float v0 = p0[3u*i+axis], v1 = p1[3u*i+axis], v2 = p2[3u*i+axis];
+			const float tmin = fmin(fmin(v0, v1), v2), tmax = fmax(fmax(v0, v1), v2);
+			keep = keep&&(tmax>=lo[axis]-pad-eps&&tmin<=hi[axis]+pad+eps);
+		}
+		if(keep) ids.push_back(i);
+	}
+	return ids;
+}
+// test hook (tests/test_voxelize.py, no device needed): ids_out has room for triangle_number entries; returns the count
+extern "C" uint luw_host_cull_triangles(const float* p0, const float* p1, const float* p2, const uint triangle_number, const uint direction,
+	const int Ox, const int Oy, const int Oz, const uint local_Nx, const uint local_Ny, const uint local_Nz, uint* ids_out) {
+	const std::vector<uint> ids = luw_cull_triangles(p0, p1, p2, triangle_number, direction, Ox, Oy, Oz, local_Nx, local_Ny, local_Nz);
+	for(size_t i=0u; i<ids.size(); i++) ids_out[i] = ids[i];
+	return (uint)ids.size();
+}
+
 luw_domain* LBM_Domain::create_handle(const int device, const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const int Ox, const int Oy, const int Oz, const float nu, const float alpha, const float beta) {
 	luw_domain_params p;
 	memset(&p, 0, sizeof(p));

@@ -175,6 +175,13 @@ public:
 };
 #endif // LUW_USE_REFERENCE_UTILITIES
 
+// Per-domain triangle culling of LBM::voxelize_mesh_on_device (FX/lbm.cpp:41-90, 1457-1495): the ids of the triangles whose bounding box, projected along the ray
+// direction, overlaps the projected extent [O, O+N-1] of the local lattice (halo layers included), padded by 1 cell + 1e-4. Rays of this domain's columns cannot hit
+// any other triangle, so the flags are those of the whole mesh -- except that a domain whose list is EMPTY is skipped altogether by the reference (FX/lbm.cpp:499),
+// i.e. previously solid cells inside the mesh's bounding box are not released there. p0/p1/p2: 3 floats per triangle in lattice coordinates.
+std::vector<uint> luw_cull_triangles(const float* p0, const float* p1, const float* p2, const uint triangle_number, const uint direction,
+	const int Ox, const int Oy, const int Oz, const uint local_Nx, const uint local_Ny, const uint local_Nz);
+
 // ---------------------------------------------------------------------------------------------------------------- LBM_Domain (FX/lbm.hpp:26-221)
 class LBM_Domain {
 private:
@@ -401,12 +408,18 @@ public:
 		x = (uint)(mp.x+1.5f*(float)Nx)%Nx; y = (uint)(mp.y+1.5f*(float)Ny)%Ny; z = (uint)(mp.z+1.5f*(float)Nz)%Nz;
 	}
 	ulong index(const uint3 xyz) const { return index(xyz.x, xyz.y, xyz.z); }
-	// LBM::voxelize_mesh_on_device, FX/lbm.cpp:1411-1645, for resting geometry: every domain casts its rays against the whole mesh (the reference's per-domain triangle
-	// culling is an optimisation, not a semantic), TYPE_S along z; then the host mirrors are refreshed like FX/lbm.cpp:1641-1644 does before initialisation.
+	// LBM::voxelize_mesh_on_device, FX/lbm.cpp:1411-1645, for resting geometry, TYPE_S along z: with several domains every domain casts its rays against ITS subset of
+	// the triangles (voxelize_triangles_on_device below: the reference's culling, including its skip of domains with an empty subset) inside the whole mesh's bounding
+	// box; then the host mirrors are refreshed like FX/lbm.cpp:1641-1644 does before initialisation.
 	void voxelize_mesh_on_device(const Mesh* mesh, const uchar flag=TYPE_S, const float3& rotation_center=float3(0.0f), const float3& linear_velocity=float3(0.0f), const float3& rotational_velocity=float3(0.0f)) {
 		(void)rotation_center;
 		if(length(linear_velocity)>0.0f||length(rotational_velocity)>0.0f) print_error("voxelize_mesh_on_device: moving geometry is not part of this build (LUW voxelises resting meshes only).");
-		for(uint d=0u; d<get_D(); d++) lbm_domain[d]->voxelize_mesh_on_device(mesh, flag);
+		const std::vector<uint> subset = voxelize_triangles_on_device((const float*)mesh->p0, (const float*)mesh->p1, (const float*)mesh->p2, mesh->triangle_number, mesh->pmin, mesh->pmax, flag);
+		if(get_D()>1u) { // FX/lbm.cpp:1604-1619
+			ulong sum = 0ull; uint lo = subset[0], hi = subset[0];
+			for(const uint n : subset) { sum += (ulong)n; lo = min(lo, n); hi = max(hi, n); }
+			print_info("Voxelize pass 2 triangle subsets: min="+to_string(lo)+", max="+to_string(hi)+", sum="+to_string(sum)+", d0="+to_string(subset[0])+", est peak MB/GPU="+to_string((float)hi*36.0f/1048576.0f, 2u));
+		}
 		if(!initialized) { flags.read_from_device(); u.read_from_device(); }
 		if(flag==TYPE_S) { // FX/lbm.cpp:1626-1637
 			ulong solid = 0ull;
@@ -417,6 +430,23 @@ public:
 	}
 	struct { int visualization_modes = 0; } graphics; // FX/setup.cpp:4125 sets it unconditionally; rendering is not part of this build
 #endif
+	// The stand-alone form of the above: triangles as 3 floats each, bounding box of the WHOLE mesh (the kernel's ray range, FX/lbm.cpp:497). Returns the number of
+	// triangles each domain was given (the whole mesh for a single domain, FX/lbm.cpp:1488-1491).
+	std::vector<uint> voxelize_triangles_on_device(const float* p0, const float* p1, const float* p2, const uint triangle_number, const float3& pmin, const float3& pmax, const uchar flag=TYPE_S, const uint direction=2u) {
+		std::vector<uint> given(get_D(), triangle_number);
+		if(get_D()==1u) { lbm_domain[0]->voxelize_triangles_on_device(p0, p1, p2, triangle_number, pmin, pmax, flag, direction); return given; }
+		for(uint d=0u; d<get_D(); d++) {
+			LBM_Domain* dom = lbm_domain[d];
+			const std::vector<uint> ids = luw_cull_triangles(p0, p1, p2, triangle_number, direction, dom->get_Ox(), dom->get_Oy(), dom->get_Oz(), dom->get_Nx(), dom->get_Ny(), dom->get_Nz());
+			given[d] = (uint)ids.size();
+			if(ids.empty()) continue; // FX/lbm.cpp:499: no pass at all for this domain
+			if(ids.size()==(size_t)triangle_number) { dom->voxelize_triangles_on_device(p0, p1, p2, triangle_number, pmin, pmax, flag, direction); continue; } // FX/lbm.cpp:1583
+			std::vector<float> q0(3u*ids.size()), q1(3u*ids.size()), q2(3u*ids.size()); // subset in mesh order, FX/lbm.cpp:510-522
+			for(size_t i=0u; i<ids.size(); i++) for(uint k=0u; k<3u; k++) { q0[3u*i+k] = p0[3u*ids[i]+k]; q1[3u*i+k] = p1[3u*ids[i]+k]; q2[3u*i+k] = p2[3u*ids[i]+k]; }
+			dom->voxelize_triangles_on_device(q0.data(), q1.data(), q2.data(), (uint)ids.size(), pmin, pmax, flag, direction);
+		}
+		return given;
+	}
 	float3 position(const uint x, const uint y, const uint z) const { return float3((float)x-0.5f*(float)Nx+0.5f, (float)y-0.5f*(float)Ny+0.5f, (float)z-0.5f*(float)Nz+0.5f); }
 	float3 position(const ulong n) const { uint x, y, z; coordinates(n, x, y, z); return position(x, y, z); }
 	float3 size() const { return float3((float)Nx, (float)Ny, (float)Nz); }
