@@ -159,3 +159,23 @@ def test_thermal_halo_kernels_equal_the_oracle(emu, oracle_lib, precision):
         if order == 0:
             ref = d.gi.copy()
     assert np.array_equal(d.gi, ref)
+
+
+def test_thermal_kernels_on_a_wide_padded_lattice(emu, oracle_lib):
+    """Rows wider than one thread block with a padded pitch (Nx = 150 -> Px = 160): the x >= Nx guard and the pitched neighbour / reference-cell indices."""
+    shape = (150, 12, 10)
+    flags, rho, u, T = H.thermal_case(shape, seed=9)
+    w = cases.relaxation_rate(1e-6)
+    feat = O.FEATURE_SETS["luwT"]
+    want = H.run_cpu_thermal(O.Oracle(), O, shape, O.FP16S, feat, flags, rho, u, T, 5, w)
+    d = HostDomain(emu, shape, O.FP16S, feat, w, H.ZONES, thermal=H.THERMAL)
+    assert d.Px == 160
+    d.put(d.rho, rho, 1); d.put(d.u, u, 3); d.put(d.flags, flags, 1); d.put(d.T, T, 1)
+    assert emu.emu_initialize_thermal(d.c) == 0
+    for t in range(5):
+        assert emu.emu_stream_collide_thermal(d.c, C.byref(d.args(t, H.FORCE, H.OMEGA))) == 0
+    got = (d.get(d.fi, 19), d.get(d.rho, 1), d.get(d.u, 3), d.get(d.gi, 7), d.get(d.T, 1))
+    for g, r, name in zip(got, want, ("fi", "rho", "u", "gi", "T")):
+        assert np.array_equal(g, r), name
+    pad = d.T.reshape(shape[2], shape[1], d.Px)[..., shape[0]:]
+    assert np.all(pad == 1.0)  # the padding columns are never written
