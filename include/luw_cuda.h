@@ -182,6 +182,8 @@ int luw_stats_create(luw_domain* dom, luw_stats** out); /* accumulators zero-fil
 int luw_stats_accumulate(luw_stats* st);
 int luw_stats_reset(luw_stats* st); /* std::fill(.., 0.0f), avg_count = 0: FX/setup.cpp:4556-4562 */
 int luw_stats_download(luw_stats* st, float* host_mean_u, float* host_m2_u, float* host_mean_rho, uint64_t* count);
+/* LUW_TEMPERATURE domains: accumulate also keeps the running mean of T (avg_T under `include_temperature_avg`, FX/setup.cpp:4449-4451, 4481-4486); dense host array [n] */
+int luw_stats_download_temperature(luw_stats* st, float* host_mean_T);
 int luw_stats_destroy(luw_stats* st);
 
 /* page-locked host memory for the mirrors (the reference's Memory<T> owns pageable new[] buffers, FX/opencl.hpp:354) */

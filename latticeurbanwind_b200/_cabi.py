@@ -73,6 +73,7 @@ EXPORTS = {  # name -> argtypes; every symbol include/luw_cuda.h declares
     "luw_stats_accumulate": [C.c_void_p],
     "luw_stats_reset": [C.c_void_p],
     "luw_stats_download": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)],
+    "luw_stats_download_temperature": [C.c_void_p, C.c_void_p],
     "luw_stats_destroy": [C.c_void_p],
     "luw_host_alloc": [C.POINTER(C.c_void_p), C.c_uint64],
     "luw_host_free": [C.c_void_p],

@@ -78,6 +78,7 @@ struct luw_stats {
 	luw_domain* dom;
 	uint64_t count;
 	float* mean_u; float* m2_u; float* mean_rho; // device, pitched like u / rho: [c*c.N + n]
+	float* mean_T; // LUW_TEMPERATURE domains: running mean of T (avg_T, FX/setup.cpp:4449-4451, 4481-4486); nullptr otherwise
 };
 struct luw_vk_inlet {
 	luw_domain* dom;
@@ -276,6 +277,13 @@ __global__ void __launch_bounds__(256) k_stats_accumulate(const uint64_t N, cons
 		}
 		const float r = mean_rho[n];
 		mean_rho[n] = __fadd_rn(r, __fmul_rn(__fadd_rn(rho[n], -r), inv_n));
+	}
+}
+// running mean of one scalar field, the avg_T line of the same loop (FX/setup.cpp:4483-4485): t_avg += (T - t_avg) * inv_n, rounded like the host build
+__global__ void __launch_bounds__(256) k_stats_mean(const uint64_t N, const float inv_n, const float* __restrict__ x, float* __restrict__ mean) {
+	for(uint64_t n=(uint64_t)blockIdx.x*blockDim.x+threadIdx.x; n<N; n+=(uint64_t)gridDim.x*blockDim.x) {
+		const float m = mean[n];
+		mean[n] = __fadd_rn(m, __fmul_rn(__fadd_rn(x[n], -m), inv_n));
 	}
 }
 __global__ void k_fill_f32(float* p, const uint64_t n, const float v) {
@@ -847,10 +855,11 @@ int luw_stats_create(luw_domain* d, luw_stats** out) {
 	DeviceGuard guard(d->p.device);
 	luw_stats* st = new(std::nothrow) luw_stats();
 	if(!st) return fail(LUW_ERR_OOM, "host allocation failed");
-	st->dom = d; st->count = 0ull; st->mean_u = st->m2_u = st->mean_rho = nullptr;
+	st->dom = d; st->count = 0ull; st->mean_u = st->m2_u = st->mean_rho = st->mean_T = nullptr;
 	int rc = dev_alloc(d, &st->mean_u, 3ull*d->c.N);
 	if(rc==LUW_OK) rc = dev_alloc(d, &st->m2_u, 3ull*d->c.N);
 	if(rc==LUW_OK) rc = dev_alloc(d, &st->mean_rho, d->c.N);
+	if(rc==LUW_OK&&d->c.T) rc = dev_alloc(d, &st->mean_T, d->c.N);
 	if(rc==LUW_OK) rc = luw_stats_reset(st);
 	if(rc!=LUW_OK) { const std::string keep = g_error; luw_stats_destroy(st); g_error = keep; return rc; }
 	*out = st;
@@ -863,6 +872,7 @@ int luw_stats_reset(luw_stats* st) {
 	CU(cudaMemsetAsync(st->mean_u, 0, 3ull*d->c.N*4ull, d->stream));
 	CU(cudaMemsetAsync(st->m2_u, 0, 3ull*d->c.N*4ull, d->stream));
 	CU(cudaMemsetAsync(st->mean_rho, 0, d->c.N*4ull, d->stream));
+	if(st->mean_T) CU(cudaMemsetAsync(st->mean_T, 0, d->c.N*4ull, d->stream));
 	st->count = 0ull;
 	return LUW_OK;
 }
@@ -875,6 +885,20 @@ int luw_stats_accumulate(luw_stats* st) {
 	k_stats_accumulate<<<(unsigned)(4*d->sm_count>0 ? 8*d->sm_count : 1184), 256, 0, d->stream>>>(d->c.N, inv_n, d->c.rho, d->c.u, st->mean_u, st->m2_u, st->mean_rho);
 	CU(cudaGetLastError());
 	d->launches++;
+	if(st->mean_T) {
+		k_stats_mean<<<(unsigned)(4*d->sm_count>0 ? 8*d->sm_count : 1184), 256, 0, d->stream>>>(d->c.N, inv_n, d->c.T, st->mean_T);
+		CU(cudaGetLastError());
+		d->launches++;
+	}
+	return LUW_OK;
+}
+int luw_stats_download_temperature(luw_stats* st, float* host_mean_T) {
+	if(!st||!host_mean_T) return fail(LUW_ERR_INVALID, "null argument");
+	if(!st->mean_T) return fail(LUW_ERR_INVALID, "the statistics object belongs to a domain without LUW_TEMPERATURE");
+	luw_domain* d = st->dom;
+	DeviceGuard guard(d->p.device);
+	CU(copy_field(d, (char*)st->mean_T, 4u, (char*)host_mean_T, 0ull, d->ncells, false));
+	CU(cudaStreamSynchronize(d->stream));
 	return LUW_OK;
 }
 int luw_stats_download(luw_stats* st, float* host_mean_u, float* host_m2_u, float* host_mean_rho, uint64_t* count) {
@@ -892,7 +916,7 @@ int luw_stats_destroy(luw_stats* st) {
 	if(!st) return LUW_OK;
 	DeviceGuard guard(st->dom->p.device);
 	cudaStreamSynchronize(st->dom->stream);
-	cudaFree(st->mean_u); cudaFree(st->m2_u); cudaFree(st->mean_rho);
+	cudaFree(st->mean_u); cudaFree(st->m2_u); cudaFree(st->mean_rho); cudaFree(st->mean_T);
 	delete st;
 	return LUW_OK;
 }

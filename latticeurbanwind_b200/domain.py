@@ -267,6 +267,12 @@ class Stats:
         A.check(A.lib().luw_stats_download(self._h, _ptr(mean_u), _ptr(m2_u), _ptr(mean_rho), C.byref(n)))
         return mean_u, m2_u, mean_rho, n.value
 
+    def download_T(self):
+        """-> mean_T[N] (LUW_TEMPERATURE domains: the reference's avg_T, FX/setup.cpp:4481-4486)"""
+        mean_T = np.empty(self.domain.N, np.float32)
+        A.check(A.lib().luw_stats_download_temperature(self._h, _ptr(mean_T)))
+        return mean_T
+
     def close(self):
         if self._h:
             A.lib().luw_stats_destroy(self._h)

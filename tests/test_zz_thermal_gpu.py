@@ -145,3 +145,23 @@ def test_cpp_lbm_with_temperature_equals_oracle(oracle_lib, tmp_path):
     dec = _run_cpp(tmp_path, shape, (2, 2, 2), 1, 6, flags, rho, u, T, alpha, beta)
     for g, r, name in zip(dec, one, ("rho", "u", "T")):
         assert np.array_equal(g, r), name
+
+
+def test_device_side_mean_temperature():
+    """luw_stats_accumulate on a LUW_TEMPERATURE domain also keeps avg_T (FX/setup.cpp:4481-4486: t_avg += (T - t_avg) * inv_n, products and sums rounded separately)."""
+    from latticeurbanwind_b200 import _cabi as A
+    from latticeurbanwind_b200.domain import Domain, Stats
+    Nx, Ny, Nz = 37, 6, 5
+    rng = np.random.default_rng(4)
+    with Domain(Nx, Ny, Nz, precision=1, features=A.UPDATE_FIELDS | A.TEMPERATURE, w=1.0, arith=0) as d:
+        st = Stats(d)
+        mean = np.zeros(d.N, np.float32)
+        for k in range(1, 5):
+            d.T[:] = (1.0 + 0.05 * rng.standard_normal(d.N)).astype(np.float32)
+            d.write_to_device(A.FIELD_T)
+            st.accumulate()
+            inv_n = np.float32(1.0) / np.float32(k)
+            mean = (mean + ((d.T - mean).astype(np.float32) * inv_n).astype(np.float32)).astype(np.float32)
+        got = st.download_T()
+        st.close()
+    assert np.array_equal(got, mean)
