@@ -496,4 +496,18 @@ public:
 		}
 		return (ulong)count;
 	}
+	void download_T(std::vector<float>& avg_T) { // the reference's avg_T (FX/setup.cpp:4262, 4481-4486), stitched like avg_rho; needs LUW_TEMPERATURE
+		const ulong N = lbm->get_N();
+		avg_T.assign(N, 0.0f);
+		const uint Hx = lbm->get_Dx()>1u, Hy = lbm->get_Dy()>1u, Hz = lbm->get_Dz()>1u;
+		for(uint d=0u; d<lbm->get_D(); d++) {
+			const LBM_Domain* dom = lbm->lbm_domain[d];
+			std::vector<float> mt(dom->get_N());
+			luw_check(luw_stats_download_temperature(st[d], mt.data()));
+			for(uint z=Hz; z<dom->get_Nz()-Hz; z++) for(uint y=Hy; y<dom->get_Ny()-Hy; y++) for(uint x=Hx; x<dom->get_Nx()-Hx; x++) {
+				const ulong l = (ulong)x+((ulong)y+(ulong)z*(ulong)dom->get_Ny())*(ulong)dom->get_Nx();
+				avg_T[lbm->index((uint)((int)x+dom->get_Ox()), (uint)((int)y+dom->get_Oy()), (uint)((int)z+dom->get_Oz()))] = mt[l];
+			}
+		}
+	}
 };
