@@ -354,16 +354,20 @@ template<typename T, bool INSERT> __device__ __forceinline__ void halo_gi_cell(c
 	const uint32_t L = axis_len(c, d);
 	uint32_t x, y, z, a;
 	face_xyz(c, d, t, INSERT ? (side==0u ? L-1u : 0u) : (side==0u ? L-2u : 1u), xfast, x, y, z, a);
-	uint64_t j[Q];
-	neighbors(c, x, y, z, j);
+	// the only neighbour either direction needs is the one a step along +axis (j7[2d+1]): extract reads it for the DDF leaving through the + face (odd i),
+	// insert writes it for the DDF arriving through the - face (even i, j7[i-1]); no neighbour table, hence no local-memory array
+	const uint64_t row = c.Px, plane = (uint64_t)c.Px*c.Ny;
+	const uint64_t n = (uint64_t)x+y*row+z*plane;
+	const uint32_t xp = d==0u ? (x+1u==c.Nx ? 0u : x+1u) : x, yp = d==1u ? (y+1u==c.Ny ? 0u : y+1u) : y, zp = d==2u ? (z+1u==c.Nz ? 0u : z+1u) : z;
+	const uint64_t np = (uint64_t)xp+yp*row+zp*plane;
 	T* gi = (T*)c.gi;
 	const uint32_t i = 2u*d+side+1u;
 	if(INSERT) {
-		const uint64_t cell = (i&1u) ? j[0] : j[i-1u];
+		const uint64_t cell = (i&1u) ? n : np;
 		const uint32_t slot = odd ? i : ((i&1u) ? i+1u : i-1u);
 		gi[(uint64_t)slot*c.N+cell] = buf[a];
 	} else {
-		const uint64_t cell = (i&1u) ? j[i] : j[0];
+		const uint64_t cell = (i&1u) ? np : n;
 		const uint32_t slot = odd ? ((i&1u) ? i+1u : i-1u) : i;
 		buf[a] = gi[(uint64_t)slot*c.N+cell];
 	}
