@@ -132,7 +132,8 @@ void LBM::construct(const uint Nx_, const uint Ny_, const uint Nz_, const uint D
 	settings_from_case_driver();
 #endif
 	if(env_uint("LUW_TEMPERATURE", (lbm_settings.features&LUW_TEMPERATURE) ? 1u : 0u)) lbm_settings.features |= LUW_TEMPERATURE; else lbm_settings.features &= ~(uint)LUW_TEMPERATURE;
-	if(!(lbm_settings.features&LUW_TEMPERATURE)&&(alpha!=0.0f||beta!=0.0f)) print_error("Thermal diffusion/expansion coefficients are set in the LBM constructor, but TEMPERATURE is not enabled (lbm_settings.features |= LUW_TEMPERATURE)."); // FX/lbm.cpp:1162
+	// Without LUW_TEMPERATURE alpha / beta are ignored, NOT an error as in FX/lbm.cpp:1162: the case driver passes units.alpha(si_alpha_air) to every LBM it builds
+	// (FX/setup.cpp:3740, 4935, 5720, 6018) whatever defines.hpp says, and the drop-in driver is built with TEMPERATURE off by default.
 	if(Dx_*Dy_*Dz_==0u) print_error("You specified 0 LBM grid domains. There has to be at least 1 domain in every direction.");
 	Dx = Dx_; Dy = Dy_; Dz = Dz_;
 	Nx = (Nx_/Dx)*Dx; Ny = (Ny_/Dy)*Dy; Nz = (Nz_/Dz)*Dz; // global size rounded down to multiples of the domain counts, FX/lbm.cpp:1058-1060
