@@ -8,10 +8,12 @@ MLUP/s = cells of the GLOBAL lattice (solids included, halo layers excluded) x s
 (FX/info.cpp:66, FX/lbm.cpp:1393).
 
 Workloads (BASELINE.json configs; the per-GPU block is fixed -> weak scaling):
-  channel512_fp16s   configs[1]: empty channel 512^3, TYPE_E on the x faces, TYPE_S walls, FP16S DDFs, nu = 1/6      (default)
-  channel512_fp32    configs[1], FP32 DDFs
-  urban_fp16s        configs[2]: staggered cube array 1024x1024x256, TYPE_E inflow, bounce-back cubes, Coriolis, nudging, sponge, Smagorinsky, FP16S
+  urban_fp16s        configs[2], the north-star's target step: staggered cube array 1024x1024x256, TYPE_E inflow, bounce-back cubes, Coriolis, nudging,
+                     sponge, Smagorinsky LES, FP16S                                                                     (default: the headline line)
   urban_fp16s_uf     the same with UPDATE_FIELDS (rho/u stored every step, +16 B/cell), LUW's shipped semantics
+  channel512_fp16s   configs[1]: empty channel 512^3, TYPE_E on the x faces, TYPE_S walls, FP16S DDFs, nu = 1/6 (the upstream README's protocol)
+  channel512_fp32 / channel512_fp16c    configs[1] with FP32 / FP16C DDFs
+At N = 1 the default run also measures urban_fp16s_uf and the three channel workloads and reports them under `also` (--also '' to skip).
 N > 1 (torchrun, one rank per GPU): the lattice is decomposed along z and y first (--decomp for other layouts, see DECOMP); every rank owns
 one block of the same local size (halo layers included), halo DDFs move over NVLink.
 
@@ -135,6 +137,14 @@ class ClockSampler:
         return out
 
 
+def config_of(workload, arith, D=(1, 1, 1), lattice=None):
+    """The `config` object of a JSON line -- the same for the B200 arm and the reference arm of a workload."""
+    case, shape, precision, features, fset, nu, desc = WORKLOADS[workload]
+    N = shape[0] * shape[1] * shape[2]
+    return {"workload": desc, "name": workload, "lattice": list(lattice if lattice is not None else shape), "features": features, "arith": arith, "decomposition": list(D),
+            "l2": "state (DDFs %.1f GB per GPU) is far larger than the 126 MB L2; no flush needed" % (19 * N * (4 if precision == 0 else 2) / 1e9)}
+
+
 # ---------------------------------------------------------------------------------------------------------------- CPU arms
 def cpu_engine(precision, fset):
     """The CPU implementation timed beside the GPU: the reference's own kernel text built for host threads if oracle/_ref travelled, else our C port."""
@@ -144,9 +154,10 @@ def cpu_engine(precision, fset):
     return O, O.Oracle(), "port"
 
 
-def cpu_run(workload, steps, warmup, budget_s=20.0):
+def cpu_run(workload, steps, warmup, budget_s=20.0, exact=False):
     """Time `steps` stream_collide calls of the workload's step on a bounded sample: an x-y-complete slab of the same case, Nz cut so that one
-    step takes a fraction of a second. Returns (MLUP/s, cores, kind, sample description, ms per step)."""
+    step takes a fraction of a second. `exact`: run exactly `steps` timed and `warmup` untimed steps (the reference arm's contract) and shrink the
+    sample instead of the step count until they fit the budget. Returns (MLUP/s, cores, kind, sample description, ms per step, steps)."""
     case, shape, precision, features, fset, nu, _ = WORKLOADS[workload]
     from latticeurbanwind_b200 import cases
     O, eng, kind = cpu_engine(precision, fset)
@@ -166,6 +177,9 @@ def cpu_run(workload, steps, warmup, budget_s=20.0):
         eng.set_threads(cores)
     Nx, Ny = min(shape[0], 512), min(shape[1], 512)
     Nz = 64 if case == "urban" else 32  # urban: keeps ground, cubes (<= 48 cells high), the nudging shell and the sponge in the sample
+    if exact:  # ~2.3 MLUP/s per host thread (measured, g++ build of the kernel text): keep (steps + warmup) steps inside the budget
+        while Nx * Ny * Nz * (steps + warmup) / (2.0e6 * cores) > budget_s and Nx > 128:
+            Nx, Ny = Nx // 2, Ny // 2
     Ng = (Nx, Ny, Nz)
     flags, rho, u = cases.block_case(case, Ng)
     zones = ZONES if features & (F_NUDGE | F_SPONGE) else {}
@@ -184,8 +198,10 @@ def cpu_run(workload, steps, warmup, budget_s=20.0):
     t0 = time.perf_counter()
     step(t); t += 1
     one = time.perf_counter() - t0
-    steps = max(1, min(steps, int(budget_s / max(one, 1e-3))))
-    for _ in range(max(0, min(warmup, 2))):
+    if not exact:
+        steps = max(1, min(steps, int(budget_s / max(one, 1e-3))))
+        warmup = min(warmup, 2)
+    for _ in range(max(0, warmup - 1)):  # the step above was the first warm-up step
         step(t); t += 1
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -201,10 +217,13 @@ def reference_arm(args):
     if rank != 0:
         return 0
     case, shape, precision, features, fset, nu, desc = WORKLOADS[args.workload]
-    mlups, cores, kind, sample, ms, steps = cpu_run(args.workload, args.steps, args.warmup, budget_s=60.0)
-    line = {"impl": "reference", "metric": "D3Q19 MLUP/s", "value": mlups, "unit": "MLUP/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2),
+    mlups, cores, kind, sample, ms, steps = cpu_run(args.workload, args.steps, args.warmup, budget_s=150.0, exact=True)
+    D = tuple(int(v) for v in args.decomp.split(",")) if args.decomp else DECOMP[case].get(args.gpus, (1, 1, 1))
+    H = tuple(1 if v > 1 else 0 for v in D)
+    Ng = tuple((n - 2 * h) * v for n, h, v in zip(shape, H, D))
+    line = {"impl": "reference", "metric": "D3Q19 MLUP/s", "value": mlups, "unit": "MLUP/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[precision], "data": "synthetic",
-            "config": {"workload": desc, "name": args.workload, "features": features},
+            "config": config_of(args.workload, args.arith, D, Ng),
             "cpu_baseline": {"value": mlups, "unit": "MLUP/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": mlups, "unit": "MLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference stream_collide (FX/kernel.cpp text compiled for host threads through oracle/ref_shim) on the box's CPU cores; "
@@ -220,18 +239,27 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--workload", default=os.environ.get("LUW_BENCH_WORKLOAD", "channel512_fp16s"), choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("LUW_BENCH_WORKLOAD", "urban_fp16s"), choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--arith", default="fast", choices=["fast", "strict"])
     ap.add_argument("--transport", default="ipc", choices=["ipc", "nccl"], help="N>1: halo payload by remote stores into IPC-mapped peer memory (default) or NCCL send/recv")
     ap.add_argument("--decomp", default="", help="N>1: Dx,Dy,Dz (product = N); default: see DECOMP")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--also", default="", help="comma-separated extra workloads measured after the headline one (N=1) and reported under `also`")
+    ap.add_argument("--also", default=None, help="comma-separated extra workloads measured after the headline one (N=1) and reported under `also`; "
+                                                 "default: urban_fp16s_uf and the channel workloads when the headline is the default one")
+    ap.add_argument("--sustain", type=float, default=2.0, help="seconds of back-to-back steps for the `sustained` figure (0: skip)")
+    ap.add_argument("--traffic", default="auto", choices=["auto", "live", "file", "off"],
+                    help="roofline.traffic: re-run one step under ncu (live), read the committed capture (file), auto = live when ncu is on PATH")
+    ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.also is None:
+        args.also = "urban_fp16s_uf,channel512_fp16s,channel512_fp32,channel512_fp16c" if args.workload == "urban_fp16s" and args.gpus == 1 else ""
     if args.impl == "reference":
         return reference_arm(args)
+    if args.traffic_child:
+        return traffic_child(args)
 
     from latticeurbanwind_b200 import _cabi as A, cases
     from latticeurbanwind_b200.domain import Domain, CellSet, pinned_empty
@@ -250,12 +278,61 @@ def main():
         also = []
         for name in [w for w in args.also.split(",") if w]:
             r = bench_single(args, name, arith, A, cases, Domain, CellSet, pinned_empty, peak, peak_src, headline=False)
-            also.append({k: r[k] for k in ("config", "value", "unit", "ms_per_step", "dtype", "roofline", "e2e", "gpu_launches")})
+            also.append({k: r[k] for k in ("config", "value", "unit", "ms_per_step", "dtype", "roofline", "e2e", "gpu_launches") if k in r})
         if also:
             res["also"] = also
         print(json.dumps(res), flush=True)
         return 0
     return bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src)
+
+
+def dram_traffic(args, workload):
+    """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel. `live`: this process starts `ncu` on a child copy of
+    itself that runs warm-up + one step of the same workload with the same library (so the figure cannot go stale when the kernel changes); `file`: the
+    committed capture profiles/traffic_<workload>.json. Returns (bytes or None, where it came from)."""
+    import shutil
+    mode = args.traffic
+    if mode == "off":
+        return None, "off"
+    ncu = shutil.which("ncu") or ("/usr/local/cuda/bin/ncu" if os.path.isfile("/usr/local/cuda/bin/ncu") else None)
+    if mode in ("auto", "live") and ncu:
+        cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:k_stream_collide", "--launch-skip", "3",
+               "--launch-count", "1", "--csv", sys.executable, os.path.abspath(__file__), "--workload", workload, "--arith", args.arith, "--traffic-child"]
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+            total, seen = 0.0, 0
+            import csv
+            for row in csv.reader(r.stdout.splitlines()):
+                if len(row) > 3 and any(c.startswith("dram__bytes_") for c in row):
+                    name = next(c for c in row if c.startswith("dram__bytes_"))
+                    unit, val = row[row.index(name) + 1], float(row[row.index(name) + 2].replace(",", ""))
+                    total += val * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(unit, 1.0)
+                    seen += 1
+            if seen == 2 and total > 0:
+                return total, "live: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum on one launch of this build (child process)"
+        except Exception:
+            pass
+        if mode == "live":
+            return None, "live capture failed"
+    path = os.path.join(ROOT, "profiles", f"traffic_{workload}.json")
+    if os.path.isfile(path):
+        try:
+            return json.load(open(path))["dram_bytes_per_launch"], f"file: profiles/traffic_{workload}.json (committed ncu capture; may predate the current kernel)"
+        except Exception:
+            pass
+    return None, "unavailable"
+
+
+def traffic_child(args):
+    """Child of dram_traffic(): warm-up + one step of the workload, nothing printed (runs under ncu)."""
+    from latticeurbanwind_b200 import _cabi as A, cases
+    from latticeurbanwind_b200.domain import Domain, pinned_empty
+    arith = A.ARITH_FAST if args.arith == "fast" else A.ARITH_STRICT
+    d = build_domain(Domain, cases, args.workload, arith, 0)
+    d.upload_all(); d.t = 1; d.enqueue_initialize(); d.t = 0
+    d.run_steps(5); d.finish_queue()
+    d.close()
+    return 0
 
 
 def build_domain(Domain, cases, workload, arith, device, D=(1, 1, 1), O=(0, 0, 0), Ng=None, pinned=None):
@@ -307,17 +384,23 @@ def bench_single(args, workload, arith, A, cases, Domain, CellSet, pinned_empty,
                 "share_of_step": 1.0,
                 "alg_bytes_per_cell": alg_bytes(precision, features), "cells_per_launch": N, "peak_source": peak_src,
                 "frac_of_8000_datasheet": achieved / 8000.0}
-        traffic = os.path.join(ROOT, "profiles", f"traffic_{workload}.json")
-        if os.path.isfile(traffic):  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-            try:
-                roof["traffic"] = json.load(open(traffic))["dram_bytes_per_launch"]
-            except Exception:
-                pass
+        # ---- sustained: the driver's K steps are a burst of tens of milliseconds at full boost; the same loop for >= args.sustain seconds shows what power capping leaves
+        sustained = None
+        if headline and args.sustain > 0:
+            n_s = max(K, int(args.sustain * 1e3 / (ms / K)) + 1)
+            clk2 = ClockSampler(0); clk2.start()
+            d.timer_begin(); d.run_steps(n_s); ms_s = d.timer_end()
+            c2 = clk2.stop()
+            sustained = {"value": N * n_s / ms_s / 1e3, "unit": "MLUP/s", "steps": n_s, "seconds": ms_s / 1e3, "ms_per_step": ms_s / n_s,
+                         "frac": N * alg_bytes(precision, features) / (ms_s / n_s * 1e-3) / 1e9 / peak, "clocks": c2}
+        if headline:
+            roof["traffic"], roof["traffic_source"] = dram_traffic(args, workload)
         res = {"metric": "D3Q19 MLUP/s", "value": mlups, "unit": "MLUP/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[precision], "data": "synthetic",
-               "config": {"workload": desc, "name": workload, "lattice": list(shape), "features": features, "arith": args.arith, "decomposition": [1, 1, 1],
-                          "l2": "state (DDFs %.1f GB) is far larger than the 126 MB L2; no flush needed" % (19 * N * (4 if precision == 0 else 2) / 1e9)},
+               "config": config_of(workload, args.arith),
                "roofline": roof, "clocks": clocks, "gpu_launches": int(launches)}
+        if sustained:
+            res["sustained"] = sustained
         published = {"channel512_fp16s": 55609.0, "channel512_fp32": 42152.0, "channel512_fp16c": 22695.0}.get(workload)
         if published:  # FluidX3D's own B200 number for this protocol (OpenCL) -- context, the driver computes its own ratios
             res["config"]["published_reference_b200_mlups"] = published
@@ -461,8 +544,7 @@ def bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src):
         halo_bytes = sum(2 * lbm.halo_bytes(A.HALO_FI, a) for a in range(3) if D[a] > 1)
         res = {"metric": "D3Q19 MLUP/s", "value": mlups, "unit": "MLUP/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[precision], "data": "synthetic",
-               "config": {"workload": desc, "name": args.workload, "lattice": list(Ng), "block_per_gpu_incl_halo": list(shape), "features": features,
-                          "arith": args.arith, "decomposition": list(D), "halo_transport": args.transport, "l2": "state per GPU is far larger than the 126 MB L2; no flush needed"},
+               "config": dict(config_of(args.workload, args.arith, D, Ng), block_per_gpu_incl_halo=list(shape), halo_transport=args.transport),
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                             "kernel": "k_stream_collide_thermal" if features & F_TEMPERATURE else "k_stream_collide_tile", "kernel_ms": kern_ms, "share_of_step": kern_ms / (ms / K), "alg_bytes_per_cell": alg_bytes(precision, features),
                             "cells_per_launch": Nloc, "peak_source": peak_src},

@@ -1,6 +1,6 @@
 // LBM kernels, generic one-cell-per-thread form (sm_100a). This file is compiled twice (lbm_strict.cu with -fmad=false,
 // lbm_fast.cu with contraction) -- see LUW_ARITH_* in include/luw_cuda.h. The generic kernels are the always-correct path for
-// every grid shape and flag pattern; lbm_pair.cuh adds the vectorised two-cells-per-thread fast path for interior rows.
+// every grid shape and flag pattern; lbm_tile.cuh / lbm_lean.cuh hold the TMA-staged two-cells-per-thread kernels that run wherever the lattice allows.
 #pragma once
 #include "lbm_common.cuh"
 

@@ -1,0 +1,456 @@
+// stream_collide, FAST arithmetic: the "lean loop" variant of the TMA-staged tile kernel (lbm_tile.cuh; re-implements FX/kernel.cpp:1475-1780).
+//
+// Same data movement, same shared-memory layout, same mbarrier protocol and the same per-cell arithmetic (mom_add / fast_prepare / fast_relax, lbm_vec.cuh)
+// as k_stream_collide_tile<.., FAST = true> with a two-pass configuration -- results are bit-identical to it. What differs is how a consumer warp spends its
+// issue slots. The round-1 kernel was issue-bound on the urban LES step (930 warp instructions per 64 cells, of which ~200 were per-tile control flow,
+// address arithmetic, flag decoding and store masks, ~95 relaxation-zone gathers and ~125 producer work and polling; profiles/r1c_ncu_urban_fp16s.md).
+// Here:
+//   * everything that depends only on the strip (row coordinates, halo / boundary classification, the y/z part of the relaxation zones) is computed once
+//     per strip, not per tile;
+//   * per tile a warp takes ONE warp-uniform decision: do all 64 cells carry flag 0 (plain fluid), outside every relaxation zone, in a tile that needs
+//     no edge handling?  Then it runs the fast body: no TYPE_E code, no zone code, no run masks -- pass 2 stores whole words unconditionally. Everything
+//     else (solid / TYPE_E / gas cells, zone shells, halo columns, partial tiles) goes through the general body, which is the round-1 logic;
+//   * the relaxation-zone gather is split into a per-strip part (nearest of the south / north / top faces, sponge depth) and a per-cell part (west / east);
+//   * the producer warp polls the "stage collided" barrier with a fixed sleep instead of a restarting exponential backoff.
+#pragma once
+#include "lbm_tile.cuh"
+
+namespace luw {
+namespace {
+
+// ------------------------------------------------------------------ relaxation zones, split by what depends on x (FX/kernel.cpp:1523-1614)
+struct ZoneRow { // of one lattice row (y, z): the part of zone_prefetch that does not depend on x
+	uint32_t d_yz; // distance to the nearest of the south / north / top faces in whose nudging shell the row lies (first minimum in the reference's order s, n, t); buffer_N+1 if none
+	uint64_t ref_yz; // that face's reference cell for x = 0
+	bool sponge; float ks; uint64_t ref_top; // top sponge: the row lies in it, its sigma, the top-plane reference cell for x = 0
+};
+__device__ __forceinline__ ZoneRow zone_row(const DomainConst& c, const uint32_t y, const uint32_t z) {
+	ZoneRow r;
+	const uint64_t row = c.Px, plane = (uint64_t)c.Px*c.Ny;
+	r.d_yz = c.buffer_N+1u; r.ref_yz = 0ull; r.sponge = false; r.ks = 0.0f; r.ref_top = (uint64_t)y*row+(uint64_t)c.tz*plane;
+	if(c.features&F_NUDGING) {
+		const int yg = (int)y+c.Oy, zg = (int)z+c.Oz, Nb = (int)c.buffer_N;
+		const int ds = yg, dn = (int)(c.Nyg-1u)-yg, dt = (int)(c.Nzg-1u)-zg;
+		if(c.downstream_face!=3&&c.has_s&&ds>=0&&ds<=Nb&&(uint32_t)ds<r.d_yz) { r.d_yz = (uint32_t)ds; r.ref_yz = (uint64_t)c.sy*row+(uint64_t)z*plane; }
+		if(c.downstream_face!=4&&c.has_n&&dn>=0&&dn<=Nb&&(uint32_t)dn<r.d_yz) { r.d_yz = (uint32_t)dn; r.ref_yz = (uint64_t)c.ny*row+(uint64_t)z*plane; }
+		if(c.has_t&&dt>=0&&dt<=Nb&&(uint32_t)dt<r.d_yz) { r.d_yz = (uint32_t)dt; r.ref_yz = r.ref_top; }
+	}
+	if((c.features&F_SPONGE)&&c.has_t) {
+		const int dt = (int)(c.Nzg-2u)-((int)z+c.Oz);
+		if(dt>=0&&dt<(int)c.sponge_N) { r.sponge = true; r.ks = __ldg(c.sigma+dt); }
+	}
+	return r;
+}
+// the per-cell part: west / east shells, then the loads. Produces exactly zone_prefetch's values (first minimum in the order w, e, s, n, t).
+__device__ __forceinline__ ZoneRef zone_cell(const DomainConst& c, const ZoneRow& zr, const uint32_t x, const uint64_t n_row, const bool active) {
+	ZoneRef r;
+	r.nudge = false; r.sponge = false; r.kn = 0.0f; r.unx = r.uny = r.unz = 0.0f; r.ks = 0.0f; r.usx = r.usy = r.usz = 0.0f;
+	if(!active) return r;
+	if(c.features&F_NUDGING) {
+		const int xg = (int)x+c.Ox, Nb = (int)c.buffer_N;
+		const int dw = xg, de = (int)(c.Nxg-1u)-xg;
+		uint32_t dmin = c.buffer_N+1u;
+		uint64_t nref = 0ull;
+		if(c.downstream_face!=1&&c.has_w&&dw>=0&&dw<=Nb) { dmin = (uint32_t)dw; nref = (uint64_t)c.wx+n_row; }
+		if(c.downstream_face!=2&&c.has_e&&de>=0&&de<=Nb&&(uint32_t)de<dmin) { dmin = (uint32_t)de; nref = (uint64_t)c.ex+n_row; }
+		if(zr.d_yz<dmin) { dmin = zr.d_yz; nref = (uint64_t)x+zr.ref_yz; }
+		if(dmin<=c.buffer_N) {
+			r.nudge = true;
+			r.kn = __fmul_rn(__ldg(c.wbuf+dmin), c.buffer_inv_tau);
+			r.unx = __ldg(c.u+nref); r.uny = __ldg(c.u+c.N+nref); r.unz = __ldg(c.u+2ull*c.N+nref);
+		}
+	}
+	if(zr.sponge) {
+		const uint64_t nref = (uint64_t)x+zr.ref_top;
+		r.sponge = true;
+		r.ks = zr.ks;
+		r.usx = __ldg(c.u+nref); r.usy = __ldg(c.u+c.N+nref); r.usz = __ldg(c.u+2ull*c.N+nref);
+	}
+	return r;
+}
+
+// does the row (y, z) lie in a relaxation zone through its y / z position? (the per-strip test of the lean loop: zone_row's two conditions without its loads)
+__device__ __forceinline__ bool zone_row_hit(const DomainConst& c, const uint32_t y, const uint32_t z) {
+	const int yg = (int)y+c.Oy, zg = (int)z+c.Oz, Nb = (int)c.buffer_N;
+	bool hit = false;
+	if(c.features&F_NUDGING) {
+		const int ds = yg, dn = (int)(c.Nyg-1u)-yg, dt = (int)(c.Nzg-1u)-zg;
+		hit = (c.downstream_face!=3&&c.has_s&&ds>=0&&ds<=Nb)||(c.downstream_face!=4&&c.has_n&&dn>=0&&dn<=Nb)||(c.has_t&&dt>=0&&dt<=Nb);
+	}
+	if((c.features&F_SPONGE)&&c.has_t) { const int dt = (int)(c.Nzg-2u)-zg; hit = hit||(dt>=0&&dt<(int)c.sponge_N); }
+	return hit;
+}
+
+// ------------------------------------------------------------------ shared memory by 32-bit shared-window address
+// (ptxas folds `address + constant` into the instruction's immediate offset, so one base register serves all boxes of a stage)
+__device__ __forceinline__ uint32_t lds_b32(const uint32_t a) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u16(const uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float lds_f32(const uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float2 lds_f32x2(const uint32_t a) { float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_b32(const uint32_t a, const uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_b16(const uint32_t a, const uint32_t v) { asm volatile("st.shared.b16 [%0], %1;" :: "r"(a), "r"(v) : "memory"); } // the low half of v
+__device__ __forceinline__ void sts_f32(const uint32_t a, const float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_f32x2(const uint32_t a, const float2 v) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"(a), "f"(v.x), "f"(v.y) : "memory"); }
+__device__ __forceinline__ bool mbar_try_a(const uint32_t bar, const uint32_t parity) {
+	uint32_t done;
+	asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
+	return done!=0u;
+}
+__device__ __forceinline__ void mbar_wait_a(const uint32_t bar, const uint32_t parity) {
+	if(mbar_try_a(bar, parity)) return;
+	uint32_t spins = 0u;
+	while(!mbar_try_a(bar, parity)) if(++spins>(1u<<24)) __trap(); // a lost arrival must abort the launch, not hang the device
+}
+__device__ __forceinline__ void mbar_arrive_a(const uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
+
+// the pair's word of a box (R), one element of it (E), and the FAST codecs (FP16S: the stored half IS the scaled value)
+template<int P> struct SmemPair;
+template<> struct SmemPair<P_FP32> {
+	typedef float2 R; typedef float E;
+	static __device__ __forceinline__ R ldw(const uint32_t a) { return lds_f32x2(a); }
+	static __device__ __forceinline__ E lde(const uint32_t a) { return lds_f32(a); }
+	static __device__ __forceinline__ void stw(const uint32_t a, const R w) { sts_f32x2(a, w); }
+	static __device__ __forceinline__ void ste(const uint32_t a, const E e) { sts_f32(a, e); }
+	static __device__ __forceinline__ E low(const R w) { return w.x; }
+	static __device__ __forceinline__ R shift_in(const R w0, const E next) { return make_float2(w0.y, next); }
+	static __device__ __forceinline__ void shift_out_both(const uint32_t own, const uint32_t next, const R n) { sts_f32(own+4u, n.x); sts_f32(next, n.y); }
+	static __device__ __forceinline__ f2 dec(const R w) { f2 v; v.v = w; return v; }
+	static __device__ __forceinline__ R enc(const f2 v) { return v.v; }
+};
+template<> struct SmemPair<P_FP16S> {
+	typedef uint32_t R; typedef uint32_t E; // an element travels in the low half of a 32-bit register
+	static __device__ __forceinline__ R ldw(const uint32_t a) { return lds_b32(a); }
+	static __device__ __forceinline__ E lde(const uint32_t a) { return lds_u16(a); }
+	static __device__ __forceinline__ void stw(const uint32_t a, const R w) { sts_b32(a, w); }
+	static __device__ __forceinline__ void ste(const uint32_t a, const E e) { sts_b16(a, e); }
+	static __device__ __forceinline__ E low(const R w) { return w; }
+	static __device__ __forceinline__ R shift_in(const R w0, const E next) { return __byte_perm(w0, next, 0x5432); }
+	static __device__ __forceinline__ void shift_out_both(const uint32_t own, const uint32_t next, const R n) { sts_b16(own+2u, n); sts_b16(next, n>>16); }
+	static __device__ __forceinline__ f2 dec(const R w) { return PairCodec<P_FP16S>::dec_raw(w); }
+	static __device__ __forceinline__ R enc(const f2 v) { return PairCodec<P_FP16S>::enc_raw(v); }
+};
+template<> struct SmemPair<P_FP16C> : SmemPair<P_FP16S> {
+	static __device__ __forceinline__ f2 dec(const R w) { return PairCodec<P_FP16C>::dec(w); }
+	static __device__ __forceinline__ R enc(const f2 v) { return PairCodec<P_FP16C>::enc_fast(v); }
+};
+
+// rho/u of TYPE_E cells: into L2 one tile ahead (`fn`: the pair's flags in the NEXT stage; `ns`: the strip id published for it, possibly a stale one -- this is only a hint)
+template<class CFG> __device__ __noinline__ void lean_prefetch_e(const DomainConst& c, const bool last, const uint32_t fn, const uint32_t ns, const uint32_t nstrips, const uint32_t tiles_y,
+	const uint32_t lx, const uint32_t ly, const uint32_t lz, const uint64_t n) {
+	if(!last) {
+		if((fn&0x0003u)==TYPE_E||(fn&0x0300u)==(TYPE_E<<8)) { const uint64_t m = n+(uint64_t)CFG::TX; prefetch_l2(c.rho+m); prefetch_l2(c.u+m); prefetch_l2(c.u+c.N+m); prefetch_l2(c.u+2ull*c.N+m); }
+	} else if(lx==0u) { // the next strip starts at the west face: its x = 0 cells
+		const uint64_t m = (uint64_t)((ns%tiles_y)*(uint32_t)CFG::TY+ly)*c.Px+(uint64_t)((ns/tiles_y)*(uint32_t)CFG::TZ+lz)*((uint64_t)c.Px*c.Ny);
+		if(ns<nstrips&&m<c.N) { prefetch_l2(c.rho+m); prefetch_l2(c.u+m); prefetch_l2(c.u+c.N+m); prefetch_l2(c.u+2ull*c.N+m); }
+	}
+}
+
+// The general body of the lean loop: run masks (solid / gas cells, halo columns, columns beyond the lattice), TYPE_E cells, relaxation zones. Out of line: about a
+// quarter of the warp-tiles of an urban case come here, and keeping it out of the loop keeps the loop's registers and instruction-cache footprint for the fast body.
+// Same arithmetic, in the same order, as the fast body (a cell's result must not depend on the path its warp takes). bb / nxt: shared-window addresses.
+template<class CFG, uint32_t FEAT> __device__ __noinline__ void lean_general_pair(const DomainConst& c, const StepArgs& a, const uint32_t bb, const uint32_t nxt, const uint32_t fl2,
+	const uint32_t x, const uint32_t y, const uint32_t z, const bool zone_warp) {
+	constexpr int P = CFG::P;
+	typedef SmemPair<P> SP;
+	typedef typename SP::R R;
+	typedef PairCodec<P> PC;
+	constexpr bool UF = (FEAT&F_UPDATE_FIELDS)!=0u, EQ = (FEAT&F_EQUILIBRIUM)!=0u, SG = (FEAT&F_SUBGRID)!=0u;
+	const float scale = (P==P_FP16S) ? 32768.0f : 1.0f, inv = (P==P_FP16S) ? 3.0517578E-5f : 1.0f;
+	const uint32_t fl0 = fl2&0xFFu, fl1 = fl2>>8;
+	bool run0 = !((fl0&TYPE_BO)==TYPE_S||(fl0&TYPE_SU)==TYPE_G), run1 = !((fl1&TYPE_BO)==TYPE_S||(fl1&TYPE_SU)==TYPE_G);
+	run0 = run0&&x<c.Nx&&!(c.Dx>1u&&(x==0u||x>=c.Nx-1u));
+	run1 = run1&&x+1u<c.Nx&&!(c.Dx>1u&&(x+1u>=c.Nx-1u));
+	if(!(run0||run1)) return;
+	const uint64_t n_row = (uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny), n = n_row+(uint64_t)x;
+	const uint32_t bo0 = fl0&TYPE_BO, bo1 = fl1&TYPE_BO;
+	const bool e0 = EQ&&run0&&bo0==TYPE_E, e1 = EQ&&run1&&bo1==TYPE_E;
+	PairIn in;
+	in.zones = false;
+	if(zone_warp) {
+		const ZoneRow zr = zone_row(c, y, z);
+		in.nudge_vertical = c.nudge_vertical;
+		in.zr0 = zone_cell(c, zr, x, n_row, run0&&bo0!=TYPE_E);
+		in.zr1 = zone_cell(c, zr, x+1u, n_row, run1&&bo1!=TYPE_E);
+		in.zones = in.zr0.nudge||in.zr0.sponge||in.zr1.nudge||in.zr1.sponge;
+	}
+	Moments M;
+	const f2 g0 = SP::dec(SP::ldw(bb));
+	M.R = g0;
+#pragma unroll
+	for(int k=0; k<9; k++) {
+		const R wa = SP::ldw(bb+(uint32_t)CFG::box_off(1+2*k));
+		R wb = SP::ldw(bb+(uint32_t)CFG::box_off(2+2*k));
+		if(pair_shifted(k)) wb = SP::shift_in(wb, SP::lde(nxt+(uint32_t)CFG::box_off(2+2*k)));
+		mom_add<SG>(M, k, SP::dec(wa), SP::dec(wb));
+	}
+	FastK K;
+	PairOut out;
+	fast_prepare<FEAT>(c, a, in, M, scale, inv, K, out);
+	if(UF) { // rho / u of the non-TYPE_E cells (UPDATE_FIELDS, FX/kernel.cpp:1709-1715)
+		const bool w0 = run0&&!e0, w1 = run1&&!e1;
+		if(w0&&w1) {
+			*(float2*)(c.rho+n) = out.rho.v; *(float2*)(c.u+n) = out.ux.v; *(float2*)(c.u+c.N+n) = out.uy.v; *(float2*)(c.u+2ull*c.N+n) = out.uz.v;
+		} else {
+			if(w0) { c.rho[n] = out.rho.v.x; c.u[n] = out.ux.v.x; c.u[c.N+n] = out.uy.v.x; c.u[2ull*c.N+n] = out.uz.v.x; }
+			if(w1) { c.rho[n+1ull] = out.rho.v.y; c.u[n+1ull] = out.ux.v.y; c.u[c.N+n+1ull] = out.uy.v.y; c.u[2ull*c.N+n+1ull] = out.uz.v.y; }
+		}
+	}
+	const auto mix = [&](const R nw, const R old) -> R { return PC::mix(run0, run1, nw, old); };
+	SP::stw(bb, mix(SP::enc(fma2(K.omw, g0, K.g0add)), SP::ldw(bb)));
+#pragma unroll
+	for(int k=0; k<9; k++) {
+		const int bA = 1+2*k, bB = 2+2*k;
+		const R wa = SP::ldw(bb+(uint32_t)CFG::box_off(bA)), wb0 = SP::ldw(bb+(uint32_t)CFG::box_off(bB));
+		R wb = wb0;
+		if(pair_shifted(k)) wb = SP::shift_in(wb0, SP::lde(nxt+(uint32_t)CFG::box_off(bB)));
+		f2 gi = SP::dec(wa), gj = SP::dec(wb);
+		fast_relax<FEAT>(K, k, gi, gj);
+		const R ni = SP::enc(gi), nj = SP::enc(gj); // f_i' goes to slot B, f_i+1' to slot A
+		SP::stw(bb+(uint32_t)CFG::box_off(bA), mix(nj, wa));
+		if(pair_shifted(k)) {
+			if(P==P_FP32) { if(run0) sts_f32(bb+(uint32_t)CFG::box_off(bB)+4u, SmemPair<P_FP32>::enc(gi).x); if(run1) sts_f32(nxt+(uint32_t)CFG::box_off(bB), SmemPair<P_FP32>::enc(gi).y); }
+			else { const uint32_t n16 = *(const uint32_t*)&ni; if(run0) sts_b16(bb+(uint32_t)CFG::box_off(bB)+2u, n16); if(run1) sts_b16(nxt+(uint32_t)CFG::box_off(bB), n16>>16); }
+		} else SP::stw(bb+(uint32_t)CFG::box_off(bB), mix(ni, wb0));
+	}
+	if(EQ&&(e0||e1)) { // generic pointers for the out-of-line equilibrium (shared with k_stream_collide_tile)
+		uint8_t* const gb = (uint8_t*)__cvta_shared_to_generic((size_t)bb);
+		uint8_t* const gn = (uint8_t*)__cvta_shared_to_generic((size_t)nxt);
+		fix_equilibrium<CFG, FEAT>(c, a, n, e0, e1, scale, gb, gn);
+	}
+}
+
+// ------------------------------------------------------------------ the kernel
+template<class CFG, uint32_t FEAT> __global__ void __maxnreg__(tile_max_regs(CFG::THREADS/32, CFG::CTAS_PER_SM))
+k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_constant__ StepArgs a, const __grid_constant__ TileMaps maps, const uint32_t tiles_x, const uint32_t tiles_y, const uint32_t tiles_z) {
+	constexpr int P = CFG::P, TX = CFG::TX, TY = CFG::TY, TZ = CFG::TZ, S = CFG::STAGES, NC = CFG::CONSUMERS;
+	typedef PairCodec<P> PC;
+	typedef typename PC::R R;
+	typedef typename PC::E E;
+	constexpr bool UF = (FEAT&F_UPDATE_FIELDS)!=0u, EQ = (FEAT&F_EQUILIBRIUM)!=0u, VF = (FEAT&F_VOLUME_FORCE)!=0u, SG = (FEAT&F_SUBGRID)!=0u;
+	static_assert(TX/2>=32, "a consumer warp must lie inside one lattice row");
+
+	extern __shared__ uint8_t smem_raw[];
+	uint8_t* const stage0 = smem_raw+((128u-(smem_u32(smem_raw)&127u))&127u);
+	uint64_t* const bar_full = (uint64_t*)(stage0+(size_t)S*CFG::STAGE_BYTES);
+	uint64_t* const bar_done = bar_full+S;
+	uint64_t* const bar_head = bar_done+S;
+	volatile uint32_t* const tile_strip = (volatile uint32_t*)(bar_head+1);
+	volatile int* const tile_yz = (volatile int*)(tile_strip+S);
+
+	const uint32_t tid = threadIdx.x;
+	if(tid==0u) {
+		if(blockIdx.x==0u) c.sched[(uint32_t)(a.t&1ull)^1u] = 0u; // strip counter of the NEXT step
+		for(int s=0; s<S; s++) { mbar_init(bar_full+s, 1u); mbar_init(bar_done+s, (uint32_t)(NC/32)); }
+		mbar_init(bar_head, 1u);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+
+	const uint32_t nstrips = tiles_y*tiles_z;
+	constexpr uint32_t END = 0xFFFFFFFFu;
+	const uint32_t odd = (uint32_t)(a.t&1ull);
+	const bool wrap_x = c.Dx==1u;
+	const bool park = wrap_x&&tiles_x>=2u;
+
+	if(tid>=(uint32_t)NC) { // ---------------------------------------------------------------- producer warp (protocol of k_stream_collide_tile)
+		const bool leader = (tid&31u)==0u;
+		uint32_t lstrip = 0u, lxt = 0u, issued = 0u;
+		bool ended = false;
+		const auto issue_loads = [&]() {
+			const int s = (int)(issued%(uint32_t)S);
+			if(lxt==0u) {
+				uint32_t v = 0u;
+				if(leader) v = atomicAdd(c.sched+odd, 1u);
+				lstrip = __shfl_sync(0xFFFFFFFFu, v, 0);
+				if(lstrip>=nstrips) {
+					ended = true;
+					if(leader) { tile_strip[s] = END; mbar_arrive(bar_full+s); }
+					return;
+				}
+			}
+			const int x0 = (int)lxt*TX, y0 = (int)(lstrip%tiles_y)*TY, z0 = (int)(lstrip/tiles_y)*TZ;
+			uint8_t* st = stage0+(size_t)s*CFG::STAGE_BYTES;
+			if(leader) {
+				tile_strip[s] = lstrip;
+				tile_yz[2*s] = y0; tile_yz[2*s+1] = z0;
+				mbar_expect_tx(bar_full+s, (uint32_t)CFG::LOAD_BYTES);
+				tma_load_3d(st+CFG::FLAG_OFF, &maps.flags, bar_full+s, x0, y0, z0);
+				tma_load_4d(st, &maps.fi, bar_full+s, x0, y0, z0, 0);
+				tma_load_4d(st+CFG::box_off(1), &maps.fiA, bar_full+s, x0, y0, z0, odd ? 1 : 2);
+#pragma unroll
+				for(int k=0; k<9; k++) {
+					int cx, cy, cz; pair_shift(k, cx, cy, cz);
+					const int i = 2*k+1;
+					tma_load_4d(st+CFG::box_off(2+2*k), &maps.fi, bar_full+s, x0, y0+cy, z0+cz, odd ? i+1 : i);
+				}
+			}
+			if(++lxt==tiles_x) lxt = 0u;
+			issued++;
+		};
+		for(int i=0; i<S&&!ended; i++) issue_loads();
+		uint32_t sxt = 0u;
+		for(uint32_t q=0u; q<issued; q++) {
+			const int s = (int)(q%(uint32_t)S);
+			{ // a tile takes the consumers a few microseconds and S-1 further stages are in flight: a fixed sleep of a fraction of that costs nothing and keeps the issue slots free
+				const uint32_t par = (q/(uint32_t)S)&1u;
+				uint32_t spins = 0u;
+				while(!mbar_try(bar_done+s, par)) { __nanosleep(400u); if(++spins>(1u<<22)) __trap(); }
+			}
+			const int x0 = (int)sxt*TX, y0 = tile_yz[2*s], z0 = tile_yz[2*s+1];
+			const uint8_t* st = stage0+(size_t)s*CFG::STAGE_BYTES;
+			const bool inner = y0>0&&z0>0&&y0+TY<=(int)c.Ny&&z0+TZ<=(int)c.Nz;
+			const bool last_of_strip = sxt+1u==tiles_x;
+			if(leader) {
+				tma_store_4d(&maps.fi, st, x0, y0, z0, 0);
+				tma_store_4d(&maps.fiA, st+CFG::box_off(1), x0, y0, z0, odd ? 1 : 2);
+				if(inner) {
+#pragma unroll
+					for(int k=0; k<9; k++) {
+						int cx, cy, cz; pair_shift(k, cx, cy, cz);
+						const int i = 2*k+1;
+						tma_store_4d(&maps.fi, st+CFG::box_off(2+2*k), x0, y0+cy, z0+cz, odd ? i+1 : i);
+					}
+				} else {
+#pragma unroll
+					for(int k=0; k<9; k++) {
+						int cx, cy, cz; pair_shift(k, cx, cy, cz);
+						const int i = 2*k+1;
+						if(!box_by_threads<CFG>(c, cy, cz, y0, z0)) tma_store_4d(&maps.fi, st+CFG::box_off(2+2*k), x0, y0+cy, z0+cz, odd ? i+1 : i);
+					}
+				}
+				tma_commit();
+				if(!ended) tma_wait_read0();
+			}
+			__syncwarp();
+			if(!ended) issue_loads();
+			if(park&&last_of_strip&&leader) { tma_wait_all_but(tiles_x-1u); mbar_arrive(bar_head); }
+			sxt = last_of_strip ? 0u : sxt+1u;
+		}
+		if(leader) tma_wait_all0();
+		return;
+	}
+
+	// ---------------------------------------------------------------------------------------- consumers: two cells per thread
+	// Shared memory is addressed through 32-bit shared-window addresses and explicit ld/st.shared (SmemPair): one base register per tile, every box at an
+	// immediate offset, no generic-pointer arithmetic in the loop.
+	typedef SmemPair<P> SP;
+	const uint32_t sm0 = smem_u32(stage0), bar0 = sm0+(uint32_t)(S*CFG::STAGE_BYTES); // full[s] at bar0 + 8 s, done[s] at bar0 + 8 (S + s), head at bar0 + 16 S
+	const uint32_t row = tid/(uint32_t)(TX/2), lx = 2u*(tid%(uint32_t)(TX/2)), ly = row%(uint32_t)TY, lz = row/(uint32_t)TY;
+	const float scale = (P==P_FP16S) ? 32768.0f : 1.0f, inv = (P==P_FP16S) ? 3.0517578E-5f : 1.0f;
+	const bool has_zones = VF&&(c.features&(F_NUDGING|F_SPONGE))!=0u;
+	const uint32_t last_tx = c.Nx-(tiles_x-1u)*(uint32_t)TX; // cells of the last tile's rows that lie inside the lattice
+	const bool edge_x_slow = c.Dx>1u||last_tx!=(uint32_t)TX; // the first / last tile of a strip holds halo columns, or columns beyond the lattice
+	// a warp (64 x-consecutive cells from local x = xw) reaches the west nudging shell iff xw + Ox <= Nb, the east one iff xw >= zone_xe
+	const bool west_shell = has_zones&&(c.features&F_NUDGING)&&c.downstream_face!=1&&c.has_w, east_shell = has_zones&&(c.features&F_NUDGING)&&c.downstream_face!=2&&c.has_e;
+	const int zone_xw = west_shell ? (int)c.buffer_N-c.Ox : -0x7FFFFFFF, zone_xe = east_shell ? (int)c.Nxg-1-(int)c.buffer_N-63-c.Ox : 0x7FFFFFFF;
+
+	uint32_t s = 0u, ph = 0u, kstrip = 0u, st = sm0; // ring slot, its phase, strips done, shared address of stage s
+	int py0 = 0, pz0 = 0;
+	for(;;) { // ---- strips, as published by the producer
+		mbar_wait_a(bar0+8u*s, ph);
+		const uint32_t strip = tile_strip[s];
+		if(strip==END) break;
+		const int y0 = (int)(strip%tiles_y)*TY, z0 = (int)(strip/tiles_y)*TZ;
+		const uint32_t y = (uint32_t)y0+ly, z = (uint32_t)z0+lz;
+		const bool bnd_yz = y0==0||y0+TY>=(int)c.Ny||z0==0||z0+TZ>=(int)c.Nz; // strip touches the y/z boundary (uniform in the CTA)
+		const bool in_yz = y<c.Ny&&z<c.Nz&&!((c.Dy>1u&&(y==0u||y>=c.Ny-1u))||(c.Dz>1u&&(z==0u||z>=c.Nz-1u))); // the cells of this row execute (uniform in the warp)
+		const bool zone_yz = has_zones&&zone_row_hit(c, y, z); // the row lies in a relaxation zone through its y / z position
+		const uint32_t park_off = (uint32_t)CFG::BOX_BYTES+((kstrip&1u)*(uint32_t)CFG::ROWS+row)*(uint32_t)CFG::ES; // in stage 0, + box_off(b): this row's parked element of shifted box b
+
+		for(uint32_t xt=0u; xt<tiles_x; xt++) { // ---- tiles of the strip, x ascending
+			const bool wrap = s+1u==(uint32_t)S;
+			const uint32_t s1 = wrap ? 0u : s+1u, ph1 = wrap ? ph^1u : ph, st1 = wrap ? sm0 : st+(uint32_t)CFG::STAGE_BYTES;
+			const bool first = xt==0u, last = xt+1u==tiles_x;
+			if(!last) mbar_wait_a(bar0+8u*s1, ph1);
+			if(bnd_yz||(park&&xt<2u)) { // ---- rare: y/z wrap patches, the parked periodic-x column
+				const int x0 = (int)xt*TX;
+				if(bnd_yz) {
+					if(first) patch_yz<CFG, true>(c, stage0+(size_t)s*CFG::STAGE_BYTES, x0, y0, z0, odd, tid, false);
+					if(!last) patch_yz<CFG, true>(c, stage0+(size_t)s1*CFG::STAGE_BYTES, x0+TX, y0, z0, odd, tid, false);
+					consumer_bar((uint32_t)NC);
+				}
+				if(park&&kstrip>0u&&xt==1u) { // write the previous strip's periodic-x column
+					mbar_wait_a(bar0+16u*(uint32_t)S, (kstrip-1u)&1u);
+					__syncwarp();
+					if(lx==last_tx-2u) flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd);
+				}
+				if(park&&first) {
+					if(lx==0u) { // park column 0 of the x-shifted boxes (pre-collision values; only the strip's last tile touches them)
+#pragma unroll
+						for(int b=0; b<Q; b++) if(box_shifted(b)) SP::ste(sm0+park_off+(uint32_t)CFG::box_off(b), SP::low(SP::ldw(st+tid*(uint32_t)sizeof(R)+(uint32_t)CFG::box_off(b))));
+					}
+					if(TX==64) __syncwarp(); else consumer_bar((uint32_t)NC); // the row-end lane (possibly in another warp) reads what the row's first lane parked
+				}
+			}
+			if(in_yz) {
+				const uint32_t bb = st+tid*(uint32_t)sizeof(R); // the pair's word in box b is at bb + box_off(b)
+				const uint32_t fl2 = lds_u16(st+(uint32_t)CFG::FLAG_OFF+2u*tid);
+				const int xw = (int)(xt*(uint32_t)TX+(lx&~63u));
+				// ONE warp-uniform decision per tile: plain fluid, no zone, no edge -> fast body
+				const bool slow = __any_sync(0xFFFFFFFFu, fl2!=0u)||zone_yz||((first||last)&&edge_x_slow)||xw<=zone_xw||xw>=zone_xe;
+				// element right of the pair's word in an x-shifted box: the next word of the row, or column 0 of the same row in the next stage / the parked column
+				uint32_t nxt = bb+(uint32_t)sizeof(R);
+				if(lx==(last ? last_tx-2u : (uint32_t)(TX-2))) nxt = !last ? st1+row*(uint32_t)(TX*CFG::ES) : park ? sm0+park_off : wrap_x ? st+row*(uint32_t)(TX*CFG::ES) : bb;
+				if(EQ&&(slow||xt+2u>=tiles_x)) lean_prefetch_e<CFG>(c, last, lds_u16(st1+(uint32_t)CFG::FLAG_OFF+2u*tid), tile_strip[s1], nstrips, tiles_y, lx, ly, lz,
+					(uint64_t)(xt*(uint32_t)TX+lx)+(uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny));
+				if(!slow) { // ---------------- fast body: 64 plain fluid cells
+					Moments M;
+					const f2 g0 = SP::dec(SP::ldw(bb));
+					M.R = g0;
+#pragma unroll
+					for(int k=0; k<9; k++) {
+						const R wa = SP::ldw(bb+(uint32_t)CFG::box_off(1+2*k));
+						R wb = SP::ldw(bb+(uint32_t)CFG::box_off(2+2*k));
+						if(pair_shifted(k)) wb = SP::shift_in(wb, SP::lde(nxt+(uint32_t)CFG::box_off(2+2*k)));
+						mom_add<SG>(M, k, SP::dec(wa), SP::dec(wb));
+					}
+					PairIn in;
+					in.zones = false;
+					FastK K;
+					PairOut out;
+					fast_prepare<FEAT>(c, a, in, M, scale, inv, K, out);
+					if(UF) {
+						const uint64_t n = (uint64_t)(xt*(uint32_t)TX+lx)+(uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny);
+						*(float2*)(c.rho+n) = out.rho.v; *(float2*)(c.u+n) = out.ux.v; *(float2*)(c.u+c.N+n) = out.uy.v; *(float2*)(c.u+2ull*c.N+n) = out.uz.v;
+					}
+					// pass 2 re-reads the boxes (volatile shared loads: the DDFs do not stay in registers); the next pair's words are fetched before this pair's are stored
+					SP::stw(bb, SP::enc(fma2(K.omw, g0, K.g0add)));
+					R wa = SP::ldw(bb+(uint32_t)CFG::box_off(1)), wb = SP::ldw(bb+(uint32_t)CFG::box_off(2));
+					E we = SP::lde(nxt+(uint32_t)CFG::box_off(2)); // pair 0 is x-shifted
+#pragma unroll
+					for(int k=0; k<9; k++) {
+						const int bA = 1+2*k, bB = 2+2*k;
+						R wa_n = wa, wb_n = wb; E we_n = we;
+						if(k<8) {
+							wa_n = SP::ldw(bb+(uint32_t)CFG::box_off(bA+2)); wb_n = SP::ldw(bb+(uint32_t)CFG::box_off(bB+2));
+							if(pair_shifted(k<8 ? k+1 : k)) we_n = SP::lde(nxt+(uint32_t)CFG::box_off(bB+2));
+						}
+						if(pair_shifted(k)) wb = SP::shift_in(wb, we);
+						f2 gi = SP::dec(wa), gj = SP::dec(wb);
+						fast_relax<FEAT>(K, k, gi, gj);
+						SP::stw(bb+(uint32_t)CFG::box_off(bA), SP::enc(gj)); // f_i+1' goes to slot A, f_i' to slot B
+						if(pair_shifted(k)) SP::shift_out_both(bb+(uint32_t)CFG::box_off(bB), nxt+(uint32_t)CFG::box_off(bB), SP::enc(gi));
+						else SP::stw(bb+(uint32_t)CFG::box_off(bB), SP::enc(gi));
+						wa = wa_n; wb = wb_n; we = we_n;
+					}
+				} else lean_general_pair<CFG, FEAT>(c, a, bb, nxt, fl2, xt*(uint32_t)TX+lx, y, z, zone_yz||xw<=zone_xw||xw>=zone_xe);
+			}
+			if(bnd_yz) { // write the wrapped elements back to their real addresses (TMA clips them)
+				consumer_bar((uint32_t)NC);
+				patch_yz<CFG, false>(c, stage0+(size_t)s*CFG::STAGE_BYTES, (int)xt*TX, y0, z0, odd, tid, park);
+			}
+			fence_async_smem(); // make this thread's shared-memory writes visible to the TMA store
+			__syncwarp();
+			if((tid&31u)==0u) mbar_arrive_a(bar0+8u*((uint32_t)S+s)); // one arrival per warp
+			s = s1; ph = ph1; st = st1;
+		}
+		py0 = y0; pz0 = z0; kstrip++;
+	}
+	if(park&&kstrip>0u) { // the last strip's periodic-x column
+		mbar_wait_a(bar0+16u*(uint32_t)S, (kstrip-1u)&1u);
+		if(lx==last_tx-2u) flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd);
+	}
+}
+
+} // anonymous namespace
+} // namespace luw

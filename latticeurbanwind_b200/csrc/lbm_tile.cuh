@@ -123,9 +123,10 @@ __device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u
 __host__ __device__ constexpr bool pair_shifted(const int k) { return k==0||k==3||k==4||k==6||k==7; }
 __host__ __device__ constexpr bool box_shifted(const int b) { return b>0&&(b&1)==0&&pair_shifted((b-2)/2); }
 __host__ __device__ constexpr int pads_before_pair(const int k) { return (k>0)+(k>3)+(k>4)+(k>6)+(k>7); }
-template<int P_, int TX_, int TY_, int TZ_, int STAGES_, int CTAS_, bool TWOPASS_ = false> struct TileCfg {
+template<int P_, int TX_, int TY_, int TZ_, int STAGES_, int CTAS_, bool TWOPASS_ = false, bool LEAN_ = false> struct TileCfg {
 	static constexpr int P = P_, TX = TX_, TY = TY_, TZ = TZ_, STAGES = STAGES_, CTAS_PER_SM = CTAS_;
 	static constexpr bool TWOPASS = TWOPASS_; // FAST arithmetic only: collide in two passes over the shared-memory boxes (fewer registers, more resident CTAs)
+	static constexpr bool LEAN = LEAN_; // FAST arithmetic only: k_stream_collide_lean (warp-uniform fast path for plain fluid cells) instead of k_stream_collide_tile
 	static constexpr int TILE = TX*TY*TZ, ROWS = TY*TZ, CONSUMERS = TILE/2, THREADS = CONSUMERS+32;
 	static constexpr int ES = (P_==P_FP32) ? 4 : 2;
 	static constexpr int BOX_BYTES = TILE*ES, PAD = 128;

@@ -64,6 +64,27 @@ def decode(O, engine_or_none, fi, precision):
     return table[fi]
 
 
+def report(name, **metrics):
+    """Measured parity errors: printed (pytest -s / -rA) and appended to gpurun_out/parity_measured.jsonl so that the margin against every written
+    tolerance is on record (profiles/ keeps the copy of the last GPU run)."""
+    import json
+    import os
+    line = json.dumps({"test": name, **{k: (float(v) if isinstance(v, (float, np.floating)) else v) for k, v in metrics.items()}})
+    print("[parity]", line)
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_measured.jsonl"), "a") as fh:
+            fh.write(line + "\n")
+    except OSError:
+        pass
+
+
+def errors(got, ref):
+    """(rel-L2(u), max-abs(u), rel-L2(rho)) of (fi, rho, u) triples."""
+    return rel_l2(got[2], ref[2]), float(np.abs(got[2] - ref[2]).max()), rel_l2(got[1], ref[1])
+
+
 def rel_l2(a, b):
     return float(np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) / max(np.linalg.norm(b.astype(np.float64)), 1e-300))
 

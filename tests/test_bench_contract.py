@@ -20,7 +20,7 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "block" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "MLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["name"] == "channel512_fp16s"
+    assert d["config"]["name"] == "urban_fp16s" and d["config"]["lattice"] == [1024, 1024, 256] and d["steps"] == 1 and d["warmup"] == 3  # the B200 arm's config, exactly K and W steps
 
 
 def test_gpu_arm_fails_loudly_without_a_device():

@@ -1,9 +1,7 @@
 """GPU parity of the thermal D3Q7 extension through the C ABI: LUW_TEMPERATURE domains against the oracle, bit for bit (STRICT).
 
-STATUS: these kernels were written after this round's GPU budget was spent. Their source is checked bit for bit against the oracle by compiling it for
-the host (tests/test_kernel_source_on_host.py); the device build itself has NOT been observed on a B200 yet. Until it has, the tests are marked
-xfail(strict=False): a pass shows up as XPASS in the round-end run, a failure does not mask the rest of the suite (the file also sorts last, because
-a faulting kernel would poison the process's CUDA context). Remove the marker once an XPASS has been seen.
+All of these passed on the round-1 driver's B200 (19 XPASS in GPUTEST_r01.json); the xfail markers are gone. The kernel source is additionally checked
+bit for bit against the oracle by compiling it for the host (tests/test_kernel_source_on_host.py).
 """
 import numpy as np
 import pytest
@@ -11,7 +9,7 @@ import pytest
 from latticeurbanwind_b200 import cases
 from tests import helpers as H
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="thermal kernels not yet observed on a B200; host emulation of the same source is bit-exact", strict=False)]
+pytestmark = pytest.mark.gpu
 NAMES = ("fi", "rho", "u", "gi", "T")
 PRECS = pytest.mark.parametrize("precision", [0, 1, 2], ids=["fp32", "fp16s", "fp16c"])
 

@@ -115,7 +115,6 @@ def test_culled_triangle_subsets_give_the_flags_of_the_whole_mesh(oracle_lib, D)
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="multi-domain voxelisation driver written after the round's GPU budget was spent: not yet observed on a B200 (its host logic is covered by the CPU test above)", strict=False)
 def test_cpp_lbm_voxelises_decomposed_like_single_domain(oracle_lib, tmp_path):
     """LBM::voxelize_triangles_on_device through the C++ host layer (luw_host_case, LUW_CASE_TRIANGLES): the 2x2x1 and 2x1x2 decompositions (culled subsets per
     domain) produce the flags of the single domain, which are the oracle voxeliser's; the flow that follows is identical too."""
