@@ -1,17 +1,22 @@
 // stream_collide, FAST arithmetic: the "lean loop" variant of the TMA-staged tile kernel (lbm_tile.cuh; re-implements FX/kernel.cpp:1475-1780).
 //
-// Same data movement, same shared-memory layout, same mbarrier protocol and the same per-cell arithmetic (mom_add / fast_prepare / fast_relax, lbm_vec.cuh)
+// Same data movement, same shared-memory layout, same mbarrier protocol and the same per-cell arithmetic (moments_of / fast_prepare / fast_relax_*, lbm_vec.cuh)
 // as k_stream_collide_tile<.., FAST = true> with a two-pass configuration -- results are bit-identical to it. What differs is how a consumer warp spends its
 // issue slots. The round-1 kernel was issue-bound on the urban LES step (930 warp instructions per 64 cells, of which ~200 were per-tile control flow,
 // address arithmetic, flag decoding and store masks, ~95 relaxation-zone gathers and ~125 producer work and polling; profiles/r1c_ncu_urban_fp16s.md).
-// Here:
-//   * everything that depends only on the strip (row coordinates, halo / boundary classification, the y/z part of the relaxation zones) is computed once
-//     per strip, not per tile;
-//   * per tile a warp takes ONE warp-uniform decision: do all 64 cells carry flag 0 (plain fluid), outside every relaxation zone, in a tile that needs
-//     no edge handling?  Then it runs the fast body: no TYPE_E code, no zone code, no run masks -- pass 2 stores whole words unconditionally. Everything
-//     else (solid / TYPE_E / gas cells, zone shells, halo columns, partial tiles) goes through the general body, which is the round-1 logic;
-//   * the relaxation-zone gather is split into a per-strip part (nearest of the south / north / top faces, sponge depth) and a per-cell part (west / east);
-//   * the producer warp polls the "stage collided" barrier with a fixed sleep instead of a restarting exponential backoff.
+// Here (profiles/r2a_ncu_urban_fp16s_v5.md is the first cut of this kernel, profiles/r2b_* the current one):
+//   * everything that depends only on the strip (row coordinates, halo / boundary classification, the y/z part of the relaxation zones) is computed when a
+//     strip starts, not per tile; shared memory is addressed through 32-bit shared-window addresses with immediate box offsets;
+//   * per tile a warp takes ONE warp-uniform decision: are all 64 cells plain fluid or TYPE_E (flag byte 0x00 / 0x02), in a tile without halo columns or
+//     columns beyond the lattice?  Then it runs the fast body: no run masks -- pass 2 stores whole words unconditionally; relaxation-zone data is gathered
+//     only by warps that reach into a zone (per-row part once, per-cell part for west / east), TYPE_E lanes are overwritten afterwards by the out-of-line
+//     equilibrium. Only warps that hold solid / gas cells, halo columns or a partial tile go through the general body (out of line), which is the round-1
+//     logic with the same arithmetic, so a cell's result does not depend on the path its warp takes;
+//   * the periodic-x column is parked by the thread that reads it back at the end of the strip (the row's last pair), so the consumers of a CTA never
+//     rendezvous (the round-1 kernel has a CTA-wide named barrier per strip for this: 5 % of all stall samples);
+//   * only the warp that holds a row's last pair waits for the NEXT stage before it collides (it reads column 0 of the next tile);
+//   * the producer warp blocks in mbarrier.try_wait (which suspends in hardware) without a software back-off or spin counter around it: a lost arrival is
+//     caught by the consumers' bounded waits.
 #pragma once
 #include "lbm_tile.cuh"
 
@@ -175,14 +180,13 @@ template<class CFG, uint32_t FEAT> __device__ __noinline__ void lean_general_pai
 	}
 	Moments M;
 	const f2 g0 = SP::dec(SP::ldw(bb));
-	M.R = g0;
-#pragma unroll
-	for(int k=0; k<9; k++) {
+	const auto ld1 = [&](const int k, f2& gi, f2& gj) {
 		const R wa = SP::ldw(bb+(uint32_t)CFG::box_off(1+2*k));
 		R wb = SP::ldw(bb+(uint32_t)CFG::box_off(2+2*k));
 		if(pair_shifted(k)) wb = SP::shift_in(wb, SP::lde(nxt+(uint32_t)CFG::box_off(2+2*k)));
-		mom_add<SG>(M, k, SP::dec(wa), SP::dec(wb));
-	}
+		gi = SP::dec(wa); gj = SP::dec(wb);
+	};
+	moments_of<SG>(g0, ld1, M);
 	FastK K;
 	PairOut out;
 	fast_prepare<FEAT>(c, a, in, M, scale, inv, K, out);
@@ -197,20 +201,35 @@ template<class CFG, uint32_t FEAT> __device__ __noinline__ void lean_general_pai
 	}
 	const auto mix = [&](const R nw, const R old) -> R { return PC::mix(run0, run1, nw, old); };
 	SP::stw(bb, mix(SP::enc(fma2(K.omw, g0, K.g0add)), SP::ldw(bb)));
-#pragma unroll
-	for(int k=0; k<9; k++) {
+	struct Raw { R wa, wb0; };
+	const auto ld2 = [&](const int k, Raw& r, f2& gi, f2& gj) {
+		r.wa = SP::ldw(bb+(uint32_t)CFG::box_off(1+2*k)); r.wb0 = SP::ldw(bb+(uint32_t)CFG::box_off(2+2*k));
+		R wb = r.wb0;
+		if(pair_shifted(k)) wb = SP::shift_in(r.wb0, SP::lde(nxt+(uint32_t)CFG::box_off(2+2*k)));
+		gi = SP::dec(r.wa); gj = SP::dec(wb);
+	};
+	const auto st2 = [&](const int k, const Raw& r, const f2 gi, const f2 gj) { // f_i' goes to slot B, f_i+1' to slot A
 		const int bA = 1+2*k, bB = 2+2*k;
-		const R wa = SP::ldw(bb+(uint32_t)CFG::box_off(bA)), wb0 = SP::ldw(bb+(uint32_t)CFG::box_off(bB));
-		R wb = wb0;
-		if(pair_shifted(k)) wb = SP::shift_in(wb0, SP::lde(nxt+(uint32_t)CFG::box_off(bB)));
-		f2 gi = SP::dec(wa), gj = SP::dec(wb);
-		fast_relax<FEAT>(K, k, gi, gj);
-		const R ni = SP::enc(gi), nj = SP::enc(gj); // f_i' goes to slot B, f_i+1' to slot A
-		SP::stw(bb+(uint32_t)CFG::box_off(bA), mix(nj, wa));
+		const R ni = SP::enc(gi), nj = SP::enc(gj);
+		SP::stw(bb+(uint32_t)CFG::box_off(bA), mix(nj, r.wa));
 		if(pair_shifted(k)) {
 			if(P==P_FP32) { if(run0) sts_f32(bb+(uint32_t)CFG::box_off(bB)+4u, SmemPair<P_FP32>::enc(gi).x); if(run1) sts_f32(nxt+(uint32_t)CFG::box_off(bB), SmemPair<P_FP32>::enc(gi).y); }
 			else { const uint32_t n16 = *(const uint32_t*)&ni; if(run0) sts_b16(bb+(uint32_t)CFG::box_off(bB)+2u, n16); if(run1) sts_b16(nxt+(uint32_t)CFG::box_off(bB), n16>>16); }
-		} else SP::stw(bb+(uint32_t)CFG::box_off(bB), mix(ni, wb0));
+		} else SP::stw(bb+(uint32_t)CFG::box_off(bB), mix(ni, r.wb0));
+	};
+#pragma unroll
+	for(int ax=0; ax<3; ax++) {
+		Raw r; f2 gi, gj;
+		ld2(ax, r, gi, gj);
+		fast_relax_axis(K, ax, gi, gj);
+		st2(ax, r, gi, gj);
+	}
+#pragma unroll
+	for(int pl=0; pl<3; pl++) {
+		Raw rp, rm; f2 gip, gjp, gim, gjm;
+		ld2(3+pl, rp, gip, gjp); ld2(6+pl, rm, gim, gjm);
+		fast_relax_diag(K, pl, gip, gjp, gim, gjm);
+		st2(3+pl, rp, gip, gjp); st2(6+pl, rm, gim, gjm);
 	}
 	if(EQ&&(e0||e1)) { // generic pointers for the out-of-line equilibrium (shared with k_stream_collide_tile)
 		uint8_t* const gb = (uint8_t*)__cvta_shared_to_generic((size_t)bb);
@@ -291,10 +310,10 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 		uint32_t sxt = 0u;
 		for(uint32_t q=0u; q<issued; q++) {
 			const int s = (int)(q%(uint32_t)S);
-			{ // a tile takes the consumers a few microseconds and S-1 further stages are in flight: a fixed sleep of a fraction of that costs nothing and keeps the issue slots free
+			{ // try_wait suspends the warp in hardware until the barrier sees traffic or the time hint expires (measured: __nanosleep around it returns at once and only
+				// costs issue slots). No spin counter here: if an arrival were lost, the consumers' bounded waits on `full` abort the launch.
 				const uint32_t par = (q/(uint32_t)S)&1u;
-				uint32_t spins = 0u;
-				while(!mbar_try(bar_done+s, par)) { __nanosleep(400u); if(++spins>(1u<<22)) __trap(); }
+				while(!mbar_try(bar_done+s, par)) { }
 			}
 			const int x0 = (int)sxt*TX, y0 = tile_yz[2*s], z0 = tile_yz[2*s+1];
 			const uint8_t* st = stage0+(size_t)s*CFG::STAGE_BYTES;
@@ -344,111 +363,139 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 	const bool west_shell = has_zones&&(c.features&F_NUDGING)&&c.downstream_face!=1&&c.has_w, east_shell = has_zones&&(c.features&F_NUDGING)&&c.downstream_face!=2&&c.has_e;
 	const int zone_xw = west_shell ? (int)c.buffer_N-c.Ox : -0x7FFFFFFF, zone_xe = east_shell ? (int)c.Nxg-1-(int)c.buffer_N-63-c.Ox : 0x7FFFFFFF;
 
-	uint32_t s = 0u, ph = 0u, kstrip = 0u, st = sm0; // ring slot, its phase, strips done, shared address of stage s
-	int py0 = 0, pz0 = 0;
-	for(;;) { // ---- strips, as published by the producer
-		mbar_wait_a(bar0+8u*s, ph);
-		const uint32_t strip = tile_strip[s];
-		if(strip==END) break;
-		const int y0 = (int)(strip%tiles_y)*TY, z0 = (int)(strip/tiles_y)*TZ;
-		const uint32_t y = (uint32_t)y0+ly, z = (uint32_t)z0+lz;
-		const bool bnd_yz = y0==0||y0+TY>=(int)c.Ny||z0==0||z0+TZ>=(int)c.Nz; // strip touches the y/z boundary (uniform in the CTA)
-		const bool in_yz = y<c.Ny&&z<c.Nz&&!((c.Dy>1u&&(y==0u||y>=c.Ny-1u))||(c.Dz>1u&&(z==0u||z>=c.Nz-1u))); // the cells of this row execute (uniform in the warp)
-		const bool zone_yz = has_zones&&zone_row_hit(c, y, z); // the row lies in a relaxation zone through its y / z position
-		const uint32_t park_off = (uint32_t)CFG::BOX_BYTES+((kstrip&1u)*(uint32_t)CFG::ROWS+row)*(uint32_t)CFG::ES; // in stage 0, + box_off(b): this row's parked element of shifted box b
+	const bool next_warp = (lx&~63u)==(uint32_t)(TX-64); // this warp holds the last pair of its row in a full tile: it reads column 0 of the NEXT tile
+	constexpr uint32_t E_BITS = TYPE_E|(TYPE_E<<8);
 
-		for(uint32_t xt=0u; xt<tiles_x; xt++) { // ---- tiles of the strip, x ascending
-			const bool wrap = s+1u==(uint32_t)S;
-			const uint32_t s1 = wrap ? 0u : s+1u, ph1 = wrap ? ph^1u : ph, st1 = wrap ? sm0 : st+(uint32_t)CFG::STAGE_BYTES;
-			const bool first = xt==0u, last = xt+1u==tiles_x;
-			if(!last) mbar_wait_a(bar0+8u*s1, ph1);
-			if(bnd_yz||(park&&xt<2u)) { // ---- rare: y/z wrap patches, the parked periodic-x column
-				const int x0 = (int)xt*TX;
-				if(bnd_yz) {
-					if(first) patch_yz<CFG, true>(c, stage0+(size_t)s*CFG::STAGE_BYTES, x0, y0, z0, odd, tid, false);
-					if(!last) patch_yz<CFG, true>(c, stage0+(size_t)s1*CFG::STAGE_BYTES, x0+TX, y0, z0, odd, tid, false);
-					consumer_bar((uint32_t)NC);
-				}
-				if(park&&kstrip>0u&&xt==1u) { // write the previous strip's periodic-x column
-					mbar_wait_a(bar0+16u*(uint32_t)S, (kstrip-1u)&1u);
-					__syncwarp();
-					if(lx==last_tx-2u) flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd);
-				}
-				if(park&&first) {
-					if(lx==0u) { // park column 0 of the x-shifted boxes (pre-collision values; only the strip's last tile touches them)
-#pragma unroll
-						for(int b=0; b<Q; b++) if(box_shifted(b)) SP::ste(sm0+park_off+(uint32_t)CFG::box_off(b), SP::low(SP::ldw(st+tid*(uint32_t)sizeof(R)+(uint32_t)CFG::box_off(b))));
-					}
-					if(TX==64) __syncwarp(); else consumer_bar((uint32_t)NC); // the row-end lane (possibly in another warp) reads what the row's first lane parked
-				}
-			}
-			if(in_yz) {
-				const uint32_t bb = st+tid*(uint32_t)sizeof(R); // the pair's word in box b is at bb + box_off(b)
-				const uint32_t fl2 = lds_u16(st+(uint32_t)CFG::FLAG_OFF+2u*tid);
-				const int xw = (int)(xt*(uint32_t)TX+(lx&~63u));
-				// ONE warp-uniform decision per tile: plain fluid, no zone, no edge -> fast body
-				const bool slow = __any_sync(0xFFFFFFFFu, fl2!=0u)||zone_yz||((first||last)&&edge_x_slow)||xw<=zone_xw||xw>=zone_xe;
-				// element right of the pair's word in an x-shifted box: the next word of the row, or column 0 of the same row in the next stage / the parked column
-				uint32_t nxt = bb+(uint32_t)sizeof(R);
-				if(lx==(last ? last_tx-2u : (uint32_t)(TX-2))) nxt = !last ? st1+row*(uint32_t)(TX*CFG::ES) : park ? sm0+park_off : wrap_x ? st+row*(uint32_t)(TX*CFG::ES) : bb;
-				if(EQ&&(slow||xt+2u>=tiles_x)) lean_prefetch_e<CFG>(c, last, lds_u16(st1+(uint32_t)CFG::FLAG_OFF+2u*tid), tile_strip[s1], nstrips, tiles_y, lx, ly, lz,
-					(uint64_t)(xt*(uint32_t)TX+lx)+(uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny));
-				if(!slow) { // ---------------- fast body: 64 plain fluid cells
-					Moments M;
-					const f2 g0 = SP::dec(SP::ldw(bb));
-					M.R = g0;
-#pragma unroll
-					for(int k=0; k<9; k++) {
-						const R wa = SP::ldw(bb+(uint32_t)CFG::box_off(1+2*k));
-						R wb = SP::ldw(bb+(uint32_t)CFG::box_off(2+2*k));
-						if(pair_shifted(k)) wb = SP::shift_in(wb, SP::lde(nxt+(uint32_t)CFG::box_off(2+2*k)));
-						mom_add<SG>(M, k, SP::dec(wa), SP::dec(wb));
-					}
-					PairIn in;
-					in.zones = false;
-					FastK K;
-					PairOut out;
-					fast_prepare<FEAT>(c, a, in, M, scale, inv, K, out);
-					if(UF) {
-						const uint64_t n = (uint64_t)(xt*(uint32_t)TX+lx)+(uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny);
-						*(float2*)(c.rho+n) = out.rho.v; *(float2*)(c.u+n) = out.ux.v; *(float2*)(c.u+c.N+n) = out.uy.v; *(float2*)(c.u+2ull*c.N+n) = out.uz.v;
-					}
-					// pass 2 re-reads the boxes (volatile shared loads: the DDFs do not stay in registers); the next pair's words are fetched before this pair's are stored
-					SP::stw(bb, SP::enc(fma2(K.omw, g0, K.g0add)));
-					R wa = SP::ldw(bb+(uint32_t)CFG::box_off(1)), wb = SP::ldw(bb+(uint32_t)CFG::box_off(2));
-					E we = SP::lde(nxt+(uint32_t)CFG::box_off(2)); // pair 0 is x-shifted
-#pragma unroll
-					for(int k=0; k<9; k++) {
-						const int bA = 1+2*k, bB = 2+2*k;
-						R wa_n = wa, wb_n = wb; E we_n = we;
-						if(k<8) {
-							wa_n = SP::ldw(bb+(uint32_t)CFG::box_off(bA+2)); wb_n = SP::ldw(bb+(uint32_t)CFG::box_off(bB+2));
-							if(pair_shifted(k<8 ? k+1 : k)) we_n = SP::lde(nxt+(uint32_t)CFG::box_off(bB+2));
-						}
-						if(pair_shifted(k)) wb = SP::shift_in(wb, we);
-						f2 gi = SP::dec(wa), gj = SP::dec(wb);
-						fast_relax<FEAT>(K, k, gi, gj);
-						SP::stw(bb+(uint32_t)CFG::box_off(bA), SP::enc(gj)); // f_i+1' goes to slot A, f_i' to slot B
-						if(pair_shifted(k)) SP::shift_out_both(bb+(uint32_t)CFG::box_off(bB), nxt+(uint32_t)CFG::box_off(bB), SP::enc(gi));
-						else SP::stw(bb+(uint32_t)CFG::box_off(bB), SP::enc(gi));
-						wa = wa_n; wb = wb_n; we = we_n;
-					}
-				} else lean_general_pair<CFG, FEAT>(c, a, bb, nxt, fl2, xt*(uint32_t)TX+lx, y, z, zone_yz||xw<=zone_xw||xw>=zone_xe);
-			}
-			if(bnd_yz) { // write the wrapped elements back to their real addresses (TMA clips them)
-				consumer_bar((uint32_t)NC);
-				patch_yz<CFG, false>(c, stage0+(size_t)s*CFG::STAGE_BYTES, (int)xt*TX, y0, z0, odd, tid, park);
-			}
-			fence_async_smem(); // make this thread's shared-memory writes visible to the TMA store
-			__syncwarp();
-			if((tid&31u)==0u) mbar_arrive_a(bar0+8u*((uint32_t)S+s)); // one arrival per warp
-			s = s1; ph = ph1; st = st1;
+	uint32_t s = 0u, ph = 0u, kstrip = 0u, st = sm0, xt = 0u; // ring slot, its phase, strips done, shared address of stage s, x tile inside the strip
+	int y0 = 0, z0 = 0, py0 = 0, pz0 = 0;
+	uint32_t y = 0u, z = 0u, park_off = 0u;
+	bool bnd_yz = false, in_yz = false, zone_yz = false;
+	for(;;) { // ---- tiles: strips as published by the producer, inside a strip x ascending
+		mbar_wait_a(bar0+8u*s, ph);
+		const bool first = xt==0u, last = xt+1u==tiles_x;
+		if(first) { // ---- a new strip
+			const uint32_t strip = tile_strip[s];
+			if(strip==END) break;
+			y0 = (int)(strip%tiles_y)*TY; z0 = (int)(strip/tiles_y)*TZ;
+			y = (uint32_t)y0+ly; z = (uint32_t)z0+lz;
+			bnd_yz = y0==0||y0+TY>=(int)c.Ny||z0==0||z0+TZ>=(int)c.Nz; // strip touches the y/z boundary (uniform in the CTA)
+			in_yz = y<c.Ny&&z<c.Nz&&!((c.Dy>1u&&(y==0u||y>=c.Ny-1u))||(c.Dz>1u&&(z==0u||z>=c.Nz-1u))); // the cells of this row execute (uniform in the warp)
+			zone_yz = has_zones&&zone_row_hit(c, y, z); // the row lies in a relaxation zone through its y / z position
+			park_off = (uint32_t)CFG::BOX_BYTES+((kstrip&1u)*(uint32_t)CFG::ROWS+row)*(uint32_t)CFG::ES; // in stage 0, + box_off(b): this row's parked element of shifted box b
 		}
-		py0 = y0; pz0 = z0; kstrip++;
+		const bool wrap = s+1u==(uint32_t)S;
+		const uint32_t s1 = wrap ? 0u : s+1u, ph1 = wrap ? ph^1u : ph, st1 = wrap ? sm0 : st+(uint32_t)CFG::STAGE_BYTES;
+		if(!last&&(next_warp||bnd_yz)) mbar_wait_a(bar0+8u*s1, ph1);
+		if(bnd_yz||(park&&xt<2u)) { // ---- rare: y/z wrap patches, the parked periodic-x column
+			const int x0 = (int)xt*TX;
+			if(bnd_yz) {
+				if(first) patch_yz<CFG, true>(c, stage0+(size_t)s*CFG::STAGE_BYTES, x0, y0, z0, odd, tid, false);
+				if(!last) patch_yz<CFG, true>(c, stage0+(size_t)s1*CFG::STAGE_BYTES, x0+TX, y0, z0, odd, tid, false);
+				consumer_bar((uint32_t)NC);
+			}
+			if(park&&lx==last_tx-2u) { // the thread that holds the row's last pair in the strip's last tile owns the periodic-x column of its row
+				if(kstrip>0u&&xt==1u) { // the previous strip's column goes to global memory (its first tile has been written back: bar_head)
+					mbar_wait_a(bar0+16u*(uint32_t)S, (kstrip-1u)&1u);
+					flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd);
+				}
+				if(first) { // park column 0 of the x-shifted boxes (pre-collision values; nothing else touches them before the strip's last tile)
+#pragma unroll
+					for(int b=0; b<Q; b++) if(box_shifted(b)) SP::ste(sm0+park_off+(uint32_t)CFG::box_off(b), SP::lde(st+row*(uint32_t)(TX*CFG::ES)+(uint32_t)CFG::box_off(b)));
+				}
+			}
+		}
+		if(in_yz) {
+			const uint32_t bb = st+tid*(uint32_t)sizeof(R); // the pair's word in box b is at bb + box_off(b)
+			const uint32_t fl2 = lds_u16(st+(uint32_t)CFG::FLAG_OFF+2u*tid);
+			const uint32_t x = xt*(uint32_t)TX+lx;
+			// ONE warp-uniform decision per tile: all 64 cells plain fluid or TYPE_E, no halo column, no column beyond the lattice -> fast body
+			const bool slow = __any_sync(0xFFFFFFFFu, (fl2&~E_BITS)!=0u)||((first||last)&&edge_x_slow);
+			const uint32_t e2 = EQ ? fl2&E_BITS : 0u; // TYPE_E lanes (fast body)
+			// element right of the pair's word in an x-shifted box: the next word of the row, or column 0 of the same row in the next stage / the parked column
+			uint32_t nxt = bb+(uint32_t)sizeof(R);
+			if(lx==(last ? last_tx-2u : (uint32_t)(TX-2))) nxt = !last ? st1+row*(uint32_t)(TX*CFG::ES) : park ? sm0+park_off : wrap_x ? st+row*(uint32_t)(TX*CFG::ES) : bb;
+			const int xw = (int)(xt*(uint32_t)TX+(lx&~63u));
+			const bool zone_warp = zone_yz||xw<=zone_xw||xw>=zone_xe;
+			if(EQ&&(xt+2u>=tiles_x||__any_sync(0xFFFFFFFFu, fl2!=0u))) lean_prefetch_e<CFG>(c, last, last ? 0u : lds_u16(st1+(uint32_t)CFG::FLAG_OFF+2u*tid), tile_strip[s1], nstrips, tiles_y, lx, ly, lz,
+				(uint64_t)x+(uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny));
+			if(!slow) { // ---------------- fast body: 64 cells that all execute
+				PairIn in;
+				in.zones = false;
+				if(zone_warp) { // relaxation-zone data first: its global loads are in flight while the moments are accumulated
+					const uint64_t n_row = (uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny);
+					const ZoneRow zr = zone_row(c, y, z);
+					in.nudge_vertical = c.nudge_vertical;
+					in.zr0 = zone_cell(c, zr, x, n_row, (fl2&0x00FFu)==0u); // not for TYPE_E cells (FX/kernel.cpp:1524); the fast body only sees flag bytes 0x00 / 0x02
+					in.zr1 = zone_cell(c, zr, x+1u, n_row, (fl2&0xFF00u)==0u);
+					in.zones = in.zr0.nudge||in.zr0.sponge||in.zr1.nudge||in.zr1.sponge;
+				}
+				Moments M;
+				const f2 g0 = SP::dec(SP::ldw(bb));
+				struct Raw { R wa, wb; E we; };
+				const auto fetch = [&](const int k) -> Raw { // the pair's words of box A and box B (+ the element to the right of it in an x-shifted box)
+					Raw r;
+					r.wa = SP::ldw(bb+(uint32_t)CFG::box_off(1+2*k)); r.wb = SP::ldw(bb+(uint32_t)CFG::box_off(2+2*k));
+					r.we = pair_shifted(k) ? SP::lde(nxt+(uint32_t)CFG::box_off(2+2*k)) : SP::low(r.wb);
+					return r;
+				};
+				const auto decode = [&](const int k, const Raw& r, f2& gi, f2& gj) { gi = SP::dec(r.wa); gj = SP::dec(pair_shifted(k) ? SP::shift_in(r.wb, r.we) : r.wb); };
+				moments_of<SG>(g0, [&](const int k, f2& gi, f2& gj) { decode(k, fetch(k), gi, gj); }, M);
+				FastK K;
+				PairOut out;
+				fast_prepare<FEAT>(c, a, in, M, scale, inv, K, out);
+				if(UF) { // rho / u of the non-TYPE_E cells (UPDATE_FIELDS, FX/kernel.cpp:1709-1715)
+					const uint64_t n = (uint64_t)x+(uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny);
+					if(e2==0u) {
+						*(float2*)(c.rho+n) = out.rho.v; *(float2*)(c.u+n) = out.ux.v; *(float2*)(c.u+c.N+n) = out.uy.v; *(float2*)(c.u+2ull*c.N+n) = out.uz.v;
+					} else {
+						if((e2&0x00FFu)==0u) { c.rho[n] = out.rho.v.x; c.u[n] = out.ux.v.x; c.u[c.N+n] = out.uy.v.x; c.u[2ull*c.N+n] = out.uz.v.x; }
+						if((e2&0xFF00u)==0u) { c.rho[n+1ull] = out.rho.v.y; c.u[n+1ull] = out.ux.v.y; c.u[c.N+n+1ull] = out.uy.v.y; c.u[2ull*c.N+n+1ull] = out.uz.v.y; }
+					}
+				}
+				// pass 2 re-reads the boxes (volatile shared loads: the DDFs do not stay in registers); the next group's words are fetched before this group's are stored
+				const auto store = [&](const int k, const f2 gi, const f2 gj) { // f_i+1' goes to slot A, f_i' to slot B; whole words, no masks
+					SP::stw(bb+(uint32_t)CFG::box_off(1+2*k), SP::enc(gj));
+					if(pair_shifted(k)) SP::shift_out_both(bb+(uint32_t)CFG::box_off(2+2*k), nxt+(uint32_t)CFG::box_off(2+2*k), SP::enc(gi));
+					else SP::stw(bb+(uint32_t)CFG::box_off(2+2*k), SP::enc(gi));
+				};
+				const auto axis = [&](const int ax, const Raw& r) { f2 gi, gj; decode(ax, r, gi, gj); fast_relax_axis(K, ax, gi, gj); store(ax, gi, gj); };
+				const auto diag = [&](const int pl, const Raw& rp, const Raw& rm) {
+					f2 gip, gjp, gim, gjm;
+					decode(3+pl, rp, gip, gjp); decode(6+pl, rm, gim, gjm);
+					fast_relax_diag(K, pl, gip, gjp, gim, gjm);
+					store(3+pl, gip, gjp); store(6+pl, gim, gjm);
+				};
+				SP::stw(bb, SP::enc(fma2(K.omw, g0, K.g0add)));
+				const Raw r0 = fetch(0), r1 = fetch(1);
+				axis(0, r0);
+				const Raw r2 = fetch(2);
+				axis(1, r1);
+				const Raw r3 = fetch(3), r6 = fetch(6);
+				axis(2, r2);
+				const Raw r4 = fetch(4), r7 = fetch(7);
+				diag(0, r3, r6);
+				const Raw r5 = fetch(5), r8 = fetch(8);
+				diag(1, r4, r7);
+				diag(2, r5, r8);
+				if(e2!=0u) { // TYPE_E lanes: f := feq of the boundary fields, element by element (out of line; generic pointers, shared with k_stream_collide_tile)
+					const uint64_t n = (uint64_t)x+(uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny);
+					fix_equilibrium<CFG, FEAT>(c, a, n, (e2&0x00FFu)!=0u, (e2&0xFF00u)!=0u, scale, (uint8_t*)__cvta_shared_to_generic((size_t)bb), (uint8_t*)__cvta_shared_to_generic((size_t)nxt));
+				}
+			} else lean_general_pair<CFG, FEAT>(c, a, bb, nxt, fl2, x, y, z, zone_warp);
+		}
+		if(bnd_yz) { // write the wrapped elements back to their real addresses (TMA clips them)
+			consumer_bar((uint32_t)NC);
+			patch_yz<CFG, false>(c, stage0+(size_t)s*CFG::STAGE_BYTES, (int)xt*TX, y0, z0, odd, tid, park);
+		}
+		fence_async_smem(); // make this thread's shared-memory writes visible to the TMA store
+		__syncwarp();
+		if((tid&31u)==0u) mbar_arrive_a(bar0+8u*((uint32_t)S+s)); // one arrival per warp
+		s = s1; ph = ph1; st = st1;
+		if(last) { xt = 0u; py0 = y0; pz0 = z0; kstrip++; } else xt++;
 	}
-	if(park&&kstrip>0u) { // the last strip's periodic-x column
+	if(park&&kstrip>0u&&lx==last_tx-2u) { // the last strip's periodic-x column
 		mbar_wait_a(bar0+16u*(uint32_t)S, (kstrip-1u)&1u);
-		if(lx==last_tx-2u) flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd);
+		flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd);
 	}
 }
 

@@ -518,32 +518,46 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 				const auto enc_out = [](const f2 v) -> R { if constexpr (P==P_FP16S) return PairCodec<P_FP16S>::enc_raw(v); else if constexpr (P==P_FP16C) return PairCodec<P_FP16C>::enc_fast(v); else return PC::enc(v); };
 				Moments M;
 				const f2 g0 = dec_in(*(const R*)bb);
-				M.R = g0;
-#pragma unroll
-				for(int k=0; k<9; k++) {
+				const auto ld1 = [&](const int k, f2& gi, f2& gj) {
 					const R wa = *(const R*)(bb+CFG::box_off(1+2*k));
 					R wb = *(const R*)(bb+CFG::box_off(2+2*k));
 					if(pair_shifted(k)) wb = PC::shift_in(wb, nxt+CFG::box_off(2+2*k));
-					mom_add<SG>(M, k, dec_in(wa), dec_in(wb));
-				}
+					gi = dec_in(wa); gj = dec_in(wb);
+				};
+				moments_of<SG>(g0, ld1, M);
 				FastK K;
 				fast_prepare<FEAT>(c, a, in, M, scale, inv, K, out);
 				store_fields(out); // now: rho / u need not stay live through pass 2
 				asm volatile("" ::: "memory"); // pass 2 re-reads the boxes: the DDFs must not stay in registers
 				const typename PC::M msk = PC::mask(run0, run1);
 				*(R*)bb = PC::mixm(msk, enc_out(fma2(K.omw, g0, K.g0add)), *(const R*)bb);
-#pragma unroll
-				for(int k=0; k<9; k++) {
+				struct Raw { R wa, wb0; };
+				const auto ld2 = [&](const int k, Raw& r, f2& gi, f2& gj) {
+					r.wa = *(const R*)(bb+CFG::box_off(1+2*k)); r.wb0 = *(const R*)(bb+CFG::box_off(2+2*k));
+					R wb = r.wb0;
+					if(pair_shifted(k)) wb = PC::shift_in(r.wb0, nxt+CFG::box_off(2+2*k));
+					gi = dec_in(r.wa); gj = dec_in(wb);
+				};
+				const auto st2 = [&](const int k, const Raw& r, const f2 gi, const f2 gj) { // f_i' goes to slot B, f_i+1' to slot A
 					const int bA = 1+2*k, bB = 2+2*k;
-					const R wa = *(const R*)(bb+CFG::box_off(bA)), wb0 = *(const R*)(bb+CFG::box_off(bB));
-					R wb = wb0;
-					if(pair_shifted(k)) wb = PC::shift_in(wb0, nxt+CFG::box_off(bB));
-					f2 gi = dec_in(wa), gj = dec_in(wb);
-					fast_relax<FEAT>(K, k, gi, gj);
-					const R ni = enc_out(gi), nj = enc_out(gj); // f_i' goes to slot B, f_i+1' to slot A
-					*(R*)(bb+CFG::box_off(bA)) = PC::mixm(msk, nj, wa);
+					const R ni = enc_out(gi), nj = enc_out(gj);
+					*(R*)(bb+CFG::box_off(bA)) = PC::mixm(msk, nj, r.wa);
 					if(pair_shifted(k)) PC::shift_out(bb+CFG::box_off(bB), nxt+CFG::box_off(bB), ni, run0, run1);
-					else *(R*)(bb+CFG::box_off(bB)) = PC::mixm(msk, ni, wb0);
+					else *(R*)(bb+CFG::box_off(bB)) = PC::mixm(msk, ni, r.wb0);
+				};
+#pragma unroll
+				for(int ax=0; ax<3; ax++) {
+					Raw r; f2 gi, gj;
+					ld2(ax, r, gi, gj);
+					fast_relax_axis(K, ax, gi, gj);
+					st2(ax, r, gi, gj);
+				}
+#pragma unroll
+				for(int pl=0; pl<3; pl++) {
+					Raw rp, rm; f2 gip, gjp, gim, gjm;
+					ld2(3+pl, rp, gip, gjp); ld2(6+pl, rm, gim, gjm);
+					fast_relax_diag(K, pl, gip, gjp, gim, gjm);
+					st2(3+pl, rp, gip, gjp); st2(6+pl, rm, gim, gjm);
 				}
 				if(EQ&&(e0||e1)) fix_equilibrium<CFG, FEAT>(c, a, n, e0, e1, scale, bb, nxt);
 			} else {

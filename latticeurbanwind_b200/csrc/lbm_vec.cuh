@@ -30,8 +30,13 @@ __device__ __forceinline__ f2 div_rn2(const f2 a, const f2 b) { return mk2(__fdi
 __device__ __forceinline__ f2 div_rn2(const float a, const f2 b) { return mk2(__fdiv_rn(a, b.v.x), __fdiv_rn(a, b.v.y)); }
 __device__ __forceinline__ f2 sqrt_rn2(const f2 a) { return mk2(__fsqrt_rn(a.v.x), __fsqrt_rn(a.v.y)); }
 __device__ __forceinline__ f2 clampc2(const f2 a) { return mk2(fminf(fmaxf(a.v.x, -LAT_C), LAT_C), fminf(fmaxf(a.v.y, -LAT_C), LAT_C)); }
+#ifndef LUW_HOST_EMULATION
 __device__ __forceinline__ float rcp_approx(const float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float sqrt_approx(const float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#else // tests/host_emulation: the algebra of the FAST formulation is checked on the host against the as-written one
+__device__ __forceinline__ float rcp_approx(const float x) { return 1.0f/x; }
+__device__ __forceinline__ float sqrt_approx(const float x) { return sqrtf(x); }
+#endif
 __device__ __forceinline__ f2 rcp2(const f2 a) { return mk2(rcp_approx(a.v.x), rcp_approx(a.v.y)); }
 __device__ __forceinline__ f2 sqrt2(const f2 a) { return mk2(sqrt_approx(a.v.x), sqrt_approx(a.v.y)); }
 __device__ __forceinline__ f2 sel2(const bool c0, const bool c1, const f2 a, const f2 b) { return mk2(c0 ? a.v.x : b.v.x, c1 ? a.v.y : b.v.y); }
@@ -313,26 +318,40 @@ template<uint32_t FEAT, bool HAS_E> __device__ __forceinline__ void collide_fast
 }
 
 // ------------------------------------------------------------------- FAST, two passes over the DDFs (low register footprint)
-// The same regrouped collision as collide_fast2, split so that the 19 DDF pairs never have to be live at once: pass 1 accumulates density,
-// momentum and second moments pair by pair (mom_add), fast_prepare turns them into the per-cell constants of the relaxation, pass 2 re-reads
-// each pair from shared memory and relaxes it (fast_relax). TYPE_E lanes are not handled here (the tile kernel overwrites them afterwards).
+// The regrouped collision split so that the 19 DDF pairs never have to be live at once: pass 1 accumulates density, momentum and second moments
+// (moments_of), fast_prepare turns them into the per-cell coefficients of the relaxation, pass 2 re-reads the pairs from shared memory and relaxes
+// them (fast_relax_axis / fast_relax_diag). TYPE_E lanes are not handled here (the tile kernels overwrite them afterwards).
+//
+// With G = w rho u + ct F, H = G + ct F (ct = 1 - w/2) the post-collision populations of the pair along c (weight w_i) are
+//   f_i'   = (1-w) f_i   + U + V,   f_i+1' = (1-w) f_i+1 + U - V,   U = w_i [ 9/2 (c.u)(c.H) + K0 ],   V = 3 w_i c.G,
+//   K0 = w rho (-3/2 u^2) + w (rho-1) - 3 ct u.F        (the same U, V as in collide_fast2, written as a quadratic form in c)
+// so that all 18 add terms come from 12 per-cell values: for the axis pairs U = 2 J_a + 2 K0', V = 2 B_a, and for the two diagonal pairs of a plane (a, b)
+//   U(a+b) = E_ab + X_ab,  U(a-b) = E_ab - X_ab,  V(a+-b) = B_a +- B_b,   J_a = 9/2 we u_a H_a,  E_ab = J_a + J_b + K0',  X_ab = 9/2 we (u_a H_b + u_b H_a),
+//   B_a = 3 we G_a,  K0' = we K0      (we = 1/36 = ws/2 = w0/12; everything in units of the DDF scale S).
 struct Moments { f2 R, mx, my, mz, Pxx, Pyy, Pzz, Pxy, Pxz, Pyz; };
-template<bool SG> __device__ __forceinline__ void mom_add(Moments& M, const int k, const f2 gi, const f2 gj) {
-	const f2 sk = gi+gj, dk = gi-gj;
-	M.R = M.R+sk;
-	switch(k) {
-		case 0: M.mx = dk; if(SG) M.Pxx = sk; break;
-		case 1: M.my = dk; if(SG) M.Pyy = sk; break;
-		case 2: M.mz = dk; if(SG) M.Pzz = sk; break;
-		case 3: M.mx = M.mx+dk; M.my = M.my+dk; if(SG) { M.Pxx = M.Pxx+sk; M.Pyy = M.Pyy+sk; M.Pxy = sk; } break;
-		case 4: M.mx = M.mx+dk; M.mz = M.mz+dk; if(SG) { M.Pxx = M.Pxx+sk; M.Pzz = M.Pzz+sk; M.Pxz = sk; } break;
-		case 5: M.my = M.my+dk; M.mz = M.mz+dk; if(SG) { M.Pyy = M.Pyy+sk; M.Pzz = M.Pzz+sk; M.Pyz = sk; } break;
-		case 6: M.mx = M.mx+dk; M.my = M.my-dk; if(SG) { M.Pxx = M.Pxx+sk; M.Pyy = M.Pyy+sk; M.Pxy = M.Pxy-sk; } break;
-		case 7: M.mx = M.mx+dk; M.mz = M.mz-dk; if(SG) { M.Pxx = M.Pxx+sk; M.Pzz = M.Pzz+sk; M.Pxz = M.Pxz-sk; } break;
-		default: M.my = M.my+dk; M.mz = M.mz-dk; if(SG) { M.Pyy = M.Pyy+sk; M.Pzz = M.Pzz+sk; M.Pyz = M.Pyz-sk; } break;
-	}
+// `ld(k, gi, gj)` delivers the decoded pair k (k = 0..8: +x +y +z +x+y +x+z +y+z +x-y +x-z +y-z); the two diagonal pairs of a plane are combined before they are accumulated
+template<bool SG, class LD> __device__ __forceinline__ void moments_of(const f2 g0, LD&& ld, Moments& M) {
+	f2 gi, gj;
+	ld(0, gi, gj); const f2 s0 = gi+gj, d0 = gi-gj;
+	ld(1, gi, gj); const f2 s1 = gi+gj, d1 = gi-gj;
+	ld(2, gi, gj); const f2 s2 = gi+gj, d2 = gi-gj;
+	ld(3, gi, gj); const f2 s3 = gi+gj, d3 = gi-gj;
+	ld(6, gi, gj); const f2 s6 = gi+gj, d6 = gi-gj;
+	const f2 Sxy = s3+s6, Dxyp = d3+d6, Dxym = d3-d6;
+	if(SG) M.Pxy = s3-s6;
+	ld(4, gi, gj); const f2 s4 = gi+gj, d4 = gi-gj;
+	ld(7, gi, gj); const f2 s7 = gi+gj, d7 = gi-gj;
+	const f2 Sxz = s4+s7, Dxzp = d4+d7, Dxzm = d4-d7;
+	if(SG) M.Pxz = s4-s7;
+	ld(5, gi, gj); const f2 s5 = gi+gj, d5 = gi-gj;
+	ld(8, gi, gj); const f2 s8 = gi+gj, d8 = gi-gj;
+	const f2 Syz = s5+s8, Dyzp = d5+d8, Dyzm = d5-d8;
+	if(SG) M.Pyz = s5-s8;
+	M.mx = (d0+Dxyp)+Dxzp; M.my = (d1+Dxym)+Dyzp; M.mz = (d2+Dxzm)+Dyzm;
+	M.R = (((g0+s0)+(s1+s2))+(Sxy+Sxz))+Syz;
+	if(SG) { M.Pxx = (s0+Sxy)+Sxz; M.Pyy = (s1+Sxy)+Syz; M.Pzz = (s2+Sxz)+Syz; }
 }
-struct FastK { f2 omw, hws, hwe, wrs, wre, h1s, h1e, kcs, kce, c3, uF3, g0add; Proj A3, F; }; // see the derivation above collide_fast2
+struct FastK { f2 omw, g0add, UA[3], B[3], E[3], X[3]; }; // see the derivation above; planes: 0 = (x,y), 1 = (x,z), 2 = (y,z)
 template<uint32_t FEAT> __device__ __forceinline__ void fast_prepare(const DomainConst& c, const StepArgs& a, const PairIn& in, const Moments& M, const float scale, const float inv, FastK& K, PairOut& out) {
 	constexpr bool VF = (FEAT&F_VOLUME_FORCE)!=0u, SG = (FEAT&F_SUBGRID)!=0u;
 	const f2 rhom1 = inv*M.R;
@@ -341,16 +360,17 @@ template<uint32_t FEAT> __device__ __forceinline__ void fast_prepare(const Domai
 	ir = fma2(ir, fma2(-rho, ir, bc(1.0f)), ir); // one Newton step: full single precision
 	const f2 iri = inv*ir;
 	f2 ux = M.mx*iri, uy = M.my*iri, uz = M.mz*iri;
-	K.uF3 = bc(0.0f);
+	Proj F; F.x = F.y = F.z = bc(0.0f);
+	f2 uF = bc(0.0f);
 	if(VF) {
 		const f2 m2rho = -2.0f*rho;
-		K.F.x = fma2(m2rho, fma2(a.oy, uz, -(a.oz*uy)), bc(a.fx));
-		K.F.y = fma2(m2rho, fma2(a.oz, ux, -(a.ox*uz)), bc(a.fy));
-		K.F.z = fma2(m2rho, fma2(a.ox, uy, -(a.oy*ux)), bc(a.fz));
-		if(in.zones) zone_force2(in, rho, ux, uy, uz, K.F.x, K.F.y, K.F.z);
+		F.x = fma2(m2rho, fma2(a.oy, uz, -(a.oz*uy)), bc(a.fx));
+		F.y = fma2(m2rho, fma2(a.oz, ux, -(a.ox*uz)), bc(a.fy));
+		F.z = fma2(m2rho, fma2(a.ox, uy, -(a.oy*ux)), bc(a.fz));
+		if(in.zones) zone_force2(in, rho, ux, uy, uz, F.x, F.y, F.z);
 		const f2 rho2 = 0.5f*ir;
-		ux = clampc2(fma2(K.F.x, rho2, ux)); uy = clampc2(fma2(K.F.y, rho2, uy)); uz = clampc2(fma2(K.F.z, rho2, uz));
-		K.uF3 = -(fma2(ux, K.F.x, fma2(uy, K.F.y, uz*K.F.z))); // = 3*uF = -(u.F)
+		ux = clampc2(fma2(F.x, rho2, ux)); uy = clampc2(fma2(F.y, rho2, uy)); uz = clampc2(fma2(F.z, rho2, uz));
+		uF = fma2(ux, F.x, fma2(uy, F.y, uz*F.z));
 	} else {
 		ux = clampc2(ux); uy = clampc2(uy); uz = clampc2(uz);
 	}
@@ -366,39 +386,46 @@ template<uint32_t FEAT> __device__ __forceinline__ void fast_prepare(const Domai
 		id = fma2(id, fma2(-den, id, bc(1.0f)), id);
 		w = 2.0f*id;
 	}
-	K.c3 = -3.0f*fma2(ux, ux, fma2(uy, uy, uz*uz));
-	K.A3.x = 3.0f*ux; K.A3.y = 3.0f*uy; K.A3.z = 3.0f*uz; // a = 3 c.u
 	K.omw = bc(1.0f)-w;
-	const f2 hw = (0.5f*scale)*w; // S*w/2
-	const f2 hwr = hw*rho; // S*w*rho/2
-	K.hws = WS*hwr; K.hwe = WE*hwr; // S*w*r/2 per weight class
-	K.wrs = 2.0f*K.hws; K.wre = 2.0f*K.hwe; // S*w*r
-	const f2 hw1 = hw*rhom1;
-	K.h1s = (2.0f*WS)*hw1; K.h1e = (2.0f*WE)*hw1; // S*w/2 * 2 w_i (rho-1)
-	const f2 feq0 = W0*fma2(rho, 0.5f*K.c3, rhom1);
+	const float swe = scale*WE;
+	const f2 wr = w*rho;
+	const f2 t1 = fma2(rho, -1.5f*fma2(ux, ux, fma2(uy, uy, uz*uz)), rhom1);
+	const f2 hw = swe*w;
+	Proj G, H;
+	f2 K0;
 	if(VF) {
-		const f2 c_tau = fma2(w, -0.5f, bc(1.0f));
-		K.kcs = (9.0f*WS/3.0f*scale)*c_tau; K.kce = (9.0f*WE/3.0f*scale)*c_tau; // S*kc/3
-		K.g0add = fma2(2.0f*hw, feq0, ((9.0f*W0/3.0f*scale)*c_tau)*K.uF3);
+		const f2 ct = fma2(w, -0.5f, bc(1.0f));
+		const f2 cfx = ct*F.x, cfy = ct*F.y, cfz = ct*F.z;
+		G.x = fma2(wr, ux, cfx); G.y = fma2(wr, uy, cfy); G.z = fma2(wr, uz, cfz);
+		H.x = G.x+cfx; H.y = G.y+cfy; H.z = G.z+cfz;
+		K0 = fma2(hw, t1, ((-3.0f*swe)*ct)*uF);
 	} else {
-		K.kcs = K.kce = bc(0.0f);
-		K.g0add = (2.0f*hw)*feq0;
+		G.x = wr*ux; G.y = wr*uy; G.z = wr*uz;
+		H = G;
+		K0 = hw*t1;
 	}
+	const f2 qx = (4.5f*swe)*ux, qy = (4.5f*swe)*uy, qz = (4.5f*swe)*uz;
+	const f2 Jx = qx*H.x, Jy = qy*H.y, Jz = qz*H.z;
+	K.X[0] = fma2(qx, H.y, qy*H.x); K.X[1] = fma2(qx, H.z, qz*H.x); K.X[2] = fma2(qy, H.z, qz*H.y);
+	K.E[0] = (Jx+Jy)+K0; K.E[1] = (Jx+Jz)+K0; K.E[2] = (Jy+Jz)+K0;
+	const f2 K02 = 2.0f*K0;
+	K.UA[0] = fma2(2.0f, Jx, K02); K.UA[1] = fma2(2.0f, Jy, K02); K.UA[2] = fma2(2.0f, Jz, K02);
+	K.B[0] = (3.0f*swe)*G.x; K.B[1] = (3.0f*swe)*G.y; K.B[2] = (3.0f*swe)*G.z;
+	K.g0add = 12.0f*K0;
 }
-template<uint32_t FEAT> __device__ __forceinline__ void fast_relax(const FastK& K, const int k, f2& gi, f2& gj) {
-	constexpr bool VF = (FEAT&F_VOLUME_FORCE)!=0u;
-	const f2 ak = proj(K.A3, k);
-	f2 U, V;
-	if(VF) {
-		const f2 Ak = proj(K.F, k), kc = k<3 ? K.kcs : K.kce;
-		U = fma2(kc, fma2(Ak, ak, K.uF3), fma2(k<3 ? K.hws : K.hwe, fma2(ak, ak, K.c3), k<3 ? K.h1s : K.h1e));
-		V = fma2(k<3 ? K.wrs : K.wre, ak, kc*Ak);
-	} else {
-		U = fma2(k<3 ? K.hws : K.hwe, fma2(ak, ak, K.c3), k<3 ? K.h1s : K.h1e);
-		V = (k<3 ? K.wrs : K.wre)*ak;
-	}
-	gi = fma2(K.omw, gi, U+V); gj = fma2(K.omw, gj, U-V);
+// axis pair ax (= pair index 0..2: +x, +y, +z)
+__device__ __forceinline__ void fast_relax_axis(const FastK& K, const int ax, f2& gi, f2& gj) {
+	gi = fma2(K.omw, gi, fma2(2.0f, K.B[ax], K.UA[ax])); gj = fma2(K.omw, gj, fma2(-2.0f, K.B[ax], K.UA[ax]));
 }
+// the two diagonal pairs of plane pl: (gip, gjp) along e_a + e_b (pair 3+pl), (gim, gjm) along e_a - e_b (pair 6+pl); (a, b) = (x,y), (x,z), (y,z)
+__device__ __forceinline__ void fast_relax_diag(const FastK& K, const int pl, f2& gip, f2& gjp, f2& gim, f2& gjm) {
+	const int ia = pl==2 ? 1 : 0, ib = pl==0 ? 1 : 2;
+	const f2 p = K.E[pl]+K.X[pl], q = K.E[pl]-K.X[pl], r = K.B[ia]+K.B[ib], s = K.B[ia]-K.B[ib];
+	gip = fma2(K.omw, gip, p+r); gjp = fma2(K.omw, gjp, p-r);
+	gim = fma2(K.omw, gim, q+s); gjm = fma2(K.omw, gjm, q-s);
+}
+// the order in which both passes visit the pairs: axis pairs, then the planes' diagonal pairs together
+__host__ __device__ constexpr int fast_pair_order(const int j) { return j<3 ? j : (j-3)%2==0 ? 3+(j-3)/2 : 6+(j-3)/2; } // 0 1 2 3 6 4 7 5 8
 
 } // anonymous namespace
 } // namespace luw
