@@ -118,6 +118,7 @@ template<> struct SmemPair<P_FP32> {
 	static __device__ __forceinline__ void ste(const uint32_t a, const E e) { sts_f32(a, e); }
 	static __device__ __forceinline__ E low(const R w) { return w.x; }
 	static __device__ __forceinline__ R shift_in(const R w0, const E next) { return make_float2(w0.y, next); }
+	static __device__ __forceinline__ R join(const E e0, const E e1) { return make_float2(e0, e1); }
 	static __device__ __forceinline__ void shift_out_both(const uint32_t own, const uint32_t next, const R n) { sts_f32(own+4u, n.x); sts_f32(next, n.y); }
 	static __device__ __forceinline__ f2 dec(const R w) { f2 v; v.v = w; return v; }
 	static __device__ __forceinline__ R enc(const f2 v) { return v.v; }
@@ -130,6 +131,7 @@ template<> struct SmemPair<P_FP16S> {
 	static __device__ __forceinline__ void ste(const uint32_t a, const E e) { sts_b16(a, e); }
 	static __device__ __forceinline__ E low(const R w) { return w; }
 	static __device__ __forceinline__ R shift_in(const R w0, const E next) { return __byte_perm(w0, next, 0x5432); }
+	static __device__ __forceinline__ R join(const E e0, const E e1) { return __byte_perm(e0, e1, 0x5410); }
 	static __device__ __forceinline__ void shift_out_both(const uint32_t own, const uint32_t next, const R n) { sts_b16(own+2u, n); sts_b16(next, n>>16); }
 	static __device__ __forceinline__ f2 dec(const R w) { return PairCodec<P_FP16S>::dec_raw(w); }
 	static __device__ __forceinline__ R enc(const f2 v) { return PairCodec<P_FP16S>::enc_raw(v); }
@@ -180,12 +182,11 @@ template<class CFG, uint32_t FEAT> __device__ __noinline__ void lean_general_pai
 	}
 	Moments M;
 	const f2 g0 = SP::dec(SP::ldw(bb));
-	const auto ld1 = [&](const int k, f2& gi, f2& gj) {
-		const R wa = SP::ldw(bb+(uint32_t)CFG::box_off(1+2*k));
-		R wb = SP::ldw(bb+(uint32_t)CFG::box_off(2+2*k));
-		if(pair_shifted(k)) wb = SP::shift_in(wb, SP::lde(nxt+(uint32_t)CFG::box_off(2+2*k)));
-		gi = SP::dec(wa); gj = SP::dec(wb);
+	const auto ldb = [&](const int k) -> R { // box B: the pair's word, or -- x-shifted -- the second element of its word and the element to the right of it
+		if(pair_shifted(k)) return SP::join(SP::lde(bb+(uint32_t)(CFG::box_off(2+2*k)+CFG::ES)), SP::lde(nxt+(uint32_t)CFG::box_off(2+2*k)));
+		return SP::ldw(bb+(uint32_t)CFG::box_off(2+2*k));
 	};
+	const auto ld1 = [&](const int k, f2& gi, f2& gj) { gi = SP::dec(SP::ldw(bb+(uint32_t)CFG::box_off(1+2*k))); gj = SP::dec(ldb(k)); };
 	moments_of<SG>(g0, ld1, M);
 	FastK K;
 	PairOut out;
@@ -203,10 +204,8 @@ template<class CFG, uint32_t FEAT> __device__ __noinline__ void lean_general_pai
 	SP::stw(bb, mix(SP::enc(fma2(K.omw, g0, K.g0add)), SP::ldw(bb)));
 	struct Raw { R wa, wb0; };
 	const auto ld2 = [&](const int k, Raw& r, f2& gi, f2& gj) {
-		r.wa = SP::ldw(bb+(uint32_t)CFG::box_off(1+2*k)); r.wb0 = SP::ldw(bb+(uint32_t)CFG::box_off(2+2*k));
-		R wb = r.wb0;
-		if(pair_shifted(k)) wb = SP::shift_in(r.wb0, SP::lde(nxt+(uint32_t)CFG::box_off(2+2*k)));
-		gi = SP::dec(r.wa); gj = SP::dec(wb);
+		r.wa = SP::ldw(bb+(uint32_t)CFG::box_off(1+2*k)); r.wb0 = ldb(k);
+		gi = SP::dec(r.wa); gj = SP::dec(r.wb0);
 	};
 	const auto st2 = [&](const int k, const Raw& r, const f2 gi, const f2 gj) { // f_i' goes to slot B, f_i+1' to slot A
 		const int bA = 1+2*k, bB = 2+2*k;
@@ -239,8 +238,36 @@ template<class CFG, uint32_t FEAT> __device__ __noinline__ void lean_general_pai
 }
 
 // ------------------------------------------------------------------ the kernel
+// Per-launch constants of the lean loop, derived on the host (lean_const): they reach the kernel through the constant bank, so the loop spends neither
+// registers nor instructions on them (the first cut kept them in registers and spilled four of them: 5 % of the stall samples were loads of those spills).
+struct LeanConst {
+	uint32_t tiles_x, tiles_y, tiles_z;
+	uint32_t last_tx; // cells of the last tile's rows that lie inside the lattice
+	uint32_t rowend_last; // local x of the pair that holds the last cell of a row, in the strip's last tile
+	int zone_xw, zone_xe; // a warp (64 x-consecutive cells from local x = xw) reaches the west nudging shell iff xw <= zone_xw, the east one iff xw >= zone_xe
+	uint32_t flags;
+};
+enum : uint32_t { LC_WRAP_X = 1u, LC_PARK = 2u, LC_EDGE_X_SLOW = 4u, LC_ZONES = 8u, LC_PREFETCH = 16u, LC_UF = 32u, LC_EQ = 64u };
+template<class CFG> inline LeanConst lean_const(const DomainConst& c, const bool prefetch) {
+	LeanConst l;
+	l.tiles_x = (c.Nx+CFG::TX-1u)/CFG::TX; l.tiles_y = (c.Ny+CFG::TY-1u)/CFG::TY; l.tiles_z = (c.Nz+CFG::TZ-1u)/CFG::TZ;
+	l.last_tx = c.Nx-(l.tiles_x-1u)*(uint32_t)CFG::TX;
+	l.rowend_last = (l.last_tx-1u)&~1u;
+	const bool vf = (c.features&F_VOLUME_FORCE)!=0u, zones = vf&&(c.features&(F_NUDGING|F_SPONGE))!=0u;
+	const bool west = zones&&(c.features&F_NUDGING)&&c.downstream_face!=1&&c.has_w, east = zones&&(c.features&F_NUDGING)&&c.downstream_face!=2&&c.has_e;
+	l.zone_xw = west ? (int)c.buffer_N-c.Ox : -0x7FFFFFFF;
+	l.zone_xe = east ? (int)c.Nxg-1-(int)c.buffer_N-63-c.Ox : 0x7FFFFFFF;
+	l.flags = (c.Dx==1u ? LC_WRAP_X : 0u)|((c.Dx==1u&&l.tiles_x>=2u) ? LC_PARK : 0u)|((c.Dx>1u||l.last_tx!=(uint32_t)CFG::TX) ? LC_EDGE_X_SLOW : 0u)|(zones ? LC_ZONES : 0u)|(prefetch ? LC_PREFETCH : 0u)
+		|((c.features&F_UPDATE_FIELDS) ? LC_UF : 0u)|((c.features&F_EQUILIBRIUM) ? LC_EQ : 0u);
+	return l;
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, const int c0, const int c1, const int c2, const int c3) {
+	asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" :: "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 template<class CFG, uint32_t FEAT> __global__ void __maxnreg__(tile_max_regs(CFG::THREADS/32, CFG::CTAS_PER_SM))
-k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_constant__ StepArgs a, const __grid_constant__ TileMaps maps, const uint32_t tiles_x, const uint32_t tiles_y, const uint32_t tiles_z) {
+k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_constant__ StepArgs a, const __grid_constant__ TileMaps maps, const __grid_constant__ LeanConst lc) {
+	const uint32_t tiles_x = lc.tiles_x, tiles_y = lc.tiles_y, tiles_z = lc.tiles_z;
 	constexpr int P = CFG::P, TX = CFG::TX, TY = CFG::TY, TZ = CFG::TZ, S = CFG::STAGES, NC = CFG::CONSUMERS;
 	typedef PairCodec<P> PC;
 	typedef typename PC::R R;
@@ -268,8 +295,8 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 	const uint32_t nstrips = tiles_y*tiles_z;
 	constexpr uint32_t END = 0xFFFFFFFFu;
 	const uint32_t odd = (uint32_t)(a.t&1ull);
-	const bool wrap_x = c.Dx==1u;
-	const bool park = wrap_x&&tiles_x>=2u;
+	const bool wrap_x = (lc.flags&LC_WRAP_X)!=0u;
+	const bool park = (lc.flags&LC_PARK)!=0u;
 
 	if(tid>=(uint32_t)NC) { // ---------------------------------------------------------------- producer warp (protocol of k_stream_collide_tile)
 		const bool leader = (tid&31u)==0u;
@@ -301,6 +328,17 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 					int cx, cy, cz; pair_shift(k, cx, cy, cz);
 					const int i = 2*k+1;
 					tma_load_4d(st+CFG::box_off(2+2*k), &maps.fi, bar_full+s, x0, y0+cy, z0+cz, odd ? i+1 : i);
+				}
+				if((lc.flags&LC_PREFETCH)&&lxt+1u<tiles_x) { // the strip's next tile into L2: its stage is still busy, so its loads will be issued a tile-time from now and then hit L2
+					const int x1 = x0+TX;
+					tma_prefetch_4d(&maps.fi, x1, y0, z0, 0);
+					tma_prefetch_4d(&maps.fiA, x1, y0, z0, odd ? 1 : 2);
+#pragma unroll
+					for(int k=0; k<9; k++) {
+						int cx, cy, cz; pair_shift(k, cx, cy, cz);
+						const int i = 2*k+1;
+						tma_prefetch_4d(&maps.fi, x1, y0+cy, z0+cz, odd ? i+1 : i);
+					}
 				}
 			}
 			if(++lxt==tiles_x) lxt = 0u;
@@ -356,20 +394,15 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 	const uint32_t sm0 = smem_u32(stage0), bar0 = sm0+(uint32_t)(S*CFG::STAGE_BYTES); // full[s] at bar0 + 8 s, done[s] at bar0 + 8 (S + s), head at bar0 + 16 S
 	const uint32_t row = tid/(uint32_t)(TX/2), lx = 2u*(tid%(uint32_t)(TX/2)), ly = row%(uint32_t)TY, lz = row/(uint32_t)TY;
 	const float scale = (P==P_FP16S) ? 32768.0f : 1.0f, inv = (P==P_FP16S) ? 3.0517578E-5f : 1.0f;
-	const bool has_zones = VF&&(c.features&(F_NUDGING|F_SPONGE))!=0u;
-	const uint32_t last_tx = c.Nx-(tiles_x-1u)*(uint32_t)TX; // cells of the last tile's rows that lie inside the lattice
-	const bool edge_x_slow = c.Dx>1u||last_tx!=(uint32_t)TX; // the first / last tile of a strip holds halo columns, or columns beyond the lattice
-	// a warp (64 x-consecutive cells from local x = xw) reaches the west nudging shell iff xw + Ox <= Nb, the east one iff xw >= zone_xe
-	const bool west_shell = has_zones&&(c.features&F_NUDGING)&&c.downstream_face!=1&&c.has_w, east_shell = has_zones&&(c.features&F_NUDGING)&&c.downstream_face!=2&&c.has_e;
-	const int zone_xw = west_shell ? (int)c.buffer_N-c.Ox : -0x7FFFFFFF, zone_xe = east_shell ? (int)c.Nxg-1-(int)c.buffer_N-63-c.Ox : 0x7FFFFFFF;
-
+	const bool has_zones = VF&&(lc.flags&LC_ZONES)!=0u;
 	const bool next_warp = (lx&~63u)==(uint32_t)(TX-64); // this warp holds the last pair of its row in a full tile: it reads column 0 of the NEXT tile
 	constexpr uint32_t E_BITS = TYPE_E|(TYPE_E<<8);
 
 	uint32_t s = 0u, ph = 0u, kstrip = 0u, st = sm0, xt = 0u; // ring slot, its phase, strips done, shared address of stage s, x tile inside the strip
 	int y0 = 0, z0 = 0, py0 = 0, pz0 = 0;
 	uint32_t y = 0u, z = 0u, park_off = 0u;
-	bool bnd_yz = false, in_yz = false, zone_yz = false;
+	uint32_t sf = 0u; // strip state in one register: the strip touches the y/z boundary (uniform in the CTA) | the cells of this row execute | the row lies in a relaxation zone through its y / z position (both uniform in the warp)
+	constexpr uint32_t SF_BND = 1u, SF_IN = 2u, SF_ZONE = 4u;
 	for(;;) { // ---- tiles: strips as published by the producer, inside a strip x ascending
 		mbar_wait_a(bar0+8u*s, ph);
 		const bool first = xt==0u, last = xt+1u==tiles_x;
@@ -378,11 +411,12 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 			if(strip==END) break;
 			y0 = (int)(strip%tiles_y)*TY; z0 = (int)(strip/tiles_y)*TZ;
 			y = (uint32_t)y0+ly; z = (uint32_t)z0+lz;
-			bnd_yz = y0==0||y0+TY>=(int)c.Ny||z0==0||z0+TZ>=(int)c.Nz; // strip touches the y/z boundary (uniform in the CTA)
-			in_yz = y<c.Ny&&z<c.Nz&&!((c.Dy>1u&&(y==0u||y>=c.Ny-1u))||(c.Dz>1u&&(z==0u||z>=c.Nz-1u))); // the cells of this row execute (uniform in the warp)
-			zone_yz = has_zones&&zone_row_hit(c, y, z); // the row lies in a relaxation zone through its y / z position
+			sf = (y0==0||y0+TY>=(int)c.Ny||z0==0||z0+TZ>=(int)c.Nz) ? SF_BND : 0u;
+			if(y<c.Ny&&z<c.Nz&&!((c.Dy>1u&&(y==0u||y>=c.Ny-1u))||(c.Dz>1u&&(z==0u||z>=c.Nz-1u)))) sf |= SF_IN;
+			if(has_zones&&zone_row_hit(c, y, z)) sf |= SF_ZONE;
 			park_off = (uint32_t)CFG::BOX_BYTES+((kstrip&1u)*(uint32_t)CFG::ROWS+row)*(uint32_t)CFG::ES; // in stage 0, + box_off(b): this row's parked element of shifted box b
 		}
+		const bool bnd_yz = (sf&SF_BND)!=0u, in_yz = (sf&SF_IN)!=0u, zone_yz = (sf&SF_ZONE)!=0u;
 		const bool wrap = s+1u==(uint32_t)S;
 		const uint32_t s1 = wrap ? 0u : s+1u, ph1 = wrap ? ph^1u : ph, st1 = wrap ? sm0 : st+(uint32_t)CFG::STAGE_BYTES;
 		if(!last&&(next_warp||bnd_yz)) mbar_wait_a(bar0+8u*s1, ph1);
@@ -393,7 +427,7 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 				if(!last) patch_yz<CFG, true>(c, stage0+(size_t)s1*CFG::STAGE_BYTES, x0+TX, y0, z0, odd, tid, false);
 				consumer_bar((uint32_t)NC);
 			}
-			if(park&&lx==last_tx-2u) { // the thread that holds the row's last pair in the strip's last tile owns the periodic-x column of its row
+			if(park&&lx==lc.rowend_last) { // the thread that holds the row's last pair in the strip's last tile owns the periodic-x column of its row
 				if(kstrip>0u&&xt==1u) { // the previous strip's column goes to global memory (its first tile has been written back: bar_head)
 					mbar_wait_a(bar0+16u*(uint32_t)S, (kstrip-1u)&1u);
 					flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd);
@@ -409,13 +443,13 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 			const uint32_t fl2 = lds_u16(st+(uint32_t)CFG::FLAG_OFF+2u*tid);
 			const uint32_t x = xt*(uint32_t)TX+lx;
 			// ONE warp-uniform decision per tile: all 64 cells plain fluid or TYPE_E, no halo column, no column beyond the lattice -> fast body
-			const bool slow = __any_sync(0xFFFFFFFFu, (fl2&~E_BITS)!=0u)||((first||last)&&edge_x_slow);
+			const bool slow = __any_sync(0xFFFFFFFFu, (fl2&~E_BITS)!=0u)||((first||last)&&(lc.flags&LC_EDGE_X_SLOW)!=0u);
 			const uint32_t e2 = EQ ? fl2&E_BITS : 0u; // TYPE_E lanes (fast body)
 			// element right of the pair's word in an x-shifted box: the next word of the row, or column 0 of the same row in the next stage / the parked column
 			uint32_t nxt = bb+(uint32_t)sizeof(R);
-			if(lx==(last ? last_tx-2u : (uint32_t)(TX-2))) nxt = !last ? st1+row*(uint32_t)(TX*CFG::ES) : park ? sm0+park_off : wrap_x ? st+row*(uint32_t)(TX*CFG::ES) : bb;
+			if(lx==(last ? lc.rowend_last : (uint32_t)(TX-2))) nxt = !last ? st1+row*(uint32_t)(TX*CFG::ES) : park ? sm0+park_off : wrap_x ? st+row*(uint32_t)(TX*CFG::ES) : bb;
 			const int xw = (int)(xt*(uint32_t)TX+(lx&~63u));
-			const bool zone_warp = zone_yz||xw<=zone_xw||xw>=zone_xe;
+			const bool zone_warp = zone_yz||xw<=lc.zone_xw||xw>=lc.zone_xe;
 			if(EQ&&(xt+2u>=tiles_x||__any_sync(0xFFFFFFFFu, fl2!=0u))) lean_prefetch_e<CFG>(c, last, last ? 0u : lds_u16(st1+(uint32_t)CFG::FLAG_OFF+2u*tid), tile_strip[s1], nstrips, tiles_y, lx, ly, lz,
 				(uint64_t)x+(uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny));
 			if(!slow) { // ---------------- fast body: 64 cells that all execute
@@ -431,14 +465,15 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 				}
 				Moments M;
 				const f2 g0 = SP::dec(SP::ldw(bb));
-				struct Raw { R wa, wb; E we; };
-				const auto fetch = [&](const int k) -> Raw { // the pair's words of box A and box B (+ the element to the right of it in an x-shifted box)
-					Raw r;
-					r.wa = SP::ldw(bb+(uint32_t)CFG::box_off(1+2*k)); r.wb = SP::ldw(bb+(uint32_t)CFG::box_off(2+2*k));
-					r.we = pair_shifted(k) ? SP::lde(nxt+(uint32_t)CFG::box_off(2+2*k)) : SP::low(r.wb);
+				struct Raw { R wa, wb; E e0, e1; };
+				const auto fetch = [&](const int k) -> Raw { // the pair's word of box A, and of box B -- or, in an x-shifted box B, the second element of its word and the element to the right of it
+					Raw r;                                     // (element loads: the first element of the word belongs to the pair on the left, which may be writing it)
+					r.wa = SP::ldw(bb+(uint32_t)CFG::box_off(1+2*k));
+					if(pair_shifted(k)) { r.e0 = SP::lde(bb+(uint32_t)(CFG::box_off(2+2*k)+CFG::ES)); r.e1 = SP::lde(nxt+(uint32_t)CFG::box_off(2+2*k)); r.wb = r.wa; }
+					else { r.wb = SP::ldw(bb+(uint32_t)CFG::box_off(2+2*k)); r.e0 = r.e1 = SP::low(r.wb); }
 					return r;
 				};
-				const auto decode = [&](const int k, const Raw& r, f2& gi, f2& gj) { gi = SP::dec(r.wa); gj = SP::dec(pair_shifted(k) ? SP::shift_in(r.wb, r.we) : r.wb); };
+				const auto decode = [&](const int k, const Raw& r, f2& gi, f2& gj) { gi = SP::dec(r.wa); gj = SP::dec(pair_shifted(k) ? SP::join(r.e0, r.e1) : r.wb); };
 				moments_of<SG>(g0, [&](const int k, f2& gi, f2& gj) { decode(k, fetch(k), gi, gj); }, M);
 				FastK K;
 				PairOut out;
@@ -493,7 +528,7 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 		s = s1; ph = ph1; st = st1;
 		if(last) { xt = 0u; py0 = y0; pz0 = z0; kstrip++; } else xt++;
 	}
-	if(park&&kstrip>0u&&lx==last_tx-2u) { // the last strip's periodic-x column
+	if(park&&kstrip>0u&&lx==lc.rowend_last) { // the last strip's periodic-x column
 		mbar_wait_a(bar0+16u*(uint32_t)S, (kstrip-1u)&1u);
 		flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd);
 	}

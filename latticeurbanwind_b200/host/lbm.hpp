@@ -347,9 +347,10 @@ public:
 			file.write(header.c_str(), (std::streamsize)header.length());
 			const ulong chunk = 4194304ull; // points per write
 			std::vector<T> data(chunk*(ulong)d);
+			const bool kelvin = convert_to_si_units&&name=="T"; // temperature is an affine map, not a factor: units.si_T(T) = T*unit_K + offset (FX/lbm.hpp:343)
 			for(ulong p0=0ull; p0<points; p0+=chunk) {
 				const ulong np = points-p0<chunk ? points-p0 : chunk;
-				parallel_for(np, [&](ulong i) { for(uint c=0u; c<d; c++) data[i*(ulong)d+(ulong)c] = reverse_bytes((T)(factor*reference(p0+i, c))); });
+				parallel_for(np, [&](ulong i) { for(uint c=0u; c<d; c++) { const T v = reference(p0+i, c); data[i*(ulong)d+(ulong)c] = reverse_bytes(kelvin ? (T)units.si_T((float)v) : (T)(factor*v)); } });
 				file.write((const char*)data.data(), (std::streamsize)(np*(ulong)d*sizeof(T)));
 			}
 			file.close();

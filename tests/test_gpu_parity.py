@@ -181,7 +181,7 @@ def test_bench_instantiation_fast_within_tolerance(oracle_lib, monkeypatch, prec
     assert e[0] <= tol["rel_l2_u"] and e[1] <= tol["max_abs_u"] and e[2] <= tol["rel_l2_rho"], e
 
 
-@pytest.mark.parametrize("variant", [0, 4, 5], ids=lambda v: f"V{v}")
+@pytest.mark.parametrize("variant", [0, 4, 5, 6, 7], ids=lambda v: f"V{v}")
 def test_fast_result_does_not_depend_on_the_tile_variant(monkeypatch, variant):
     """A cell's FAST result is a function of its own DDFs only: every two-pass variant -- tile shape, lean or general loop, masked or
     unmasked stores -- must produce the same bits. This is what makes decomposed FAST runs equal to single-domain ones."""
