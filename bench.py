@@ -51,6 +51,10 @@ WORKLOADS = {
     # the reference's shipped build (TEMPERATURE on). Not a headline workload: one-cell-per-thread kernel, unobserved on a B200 in round 1
     "urban_fp16s_thermal": ("urban", (1024, 1024, 256), 1, F_UF | F_VF | F_EQ | F_SG | F_NUDGE | F_SPONGE | F_TEMPERATURE, "luwT", 1e-6,
                             "C3 staggered cube array 1024x1024x256 FP16S, full LUW step with UPDATE_FIELDS and thermal D3Q7 transport (TYPE_E cells carry TYPE_T, alpha = 2e-3)"),
+    "urban_fp16c_thermal": ("urban", (1024, 1024, 256), 2, F_UF | F_VF | F_EQ | F_SG | F_NUDGE | F_SPONGE | F_TEMPERATURE, "luwT", 1e-6,
+                            "C3 staggered cube array 1024x1024x256 FP16C + UPDATE_FIELDS + TEMPERATURE: the switches LUW ships (FX/defines.hpp:14-24)"),
+    "urban_fp16c_uf": ("urban", (1024, 1024, 256), 2, F_UF | F_VF | F_EQ | F_SG | F_NUDGE | F_SPONGE, "luw", 1e-6,
+                       "C3 staggered cube array 1024x1024x256 FP16C, full LUW step with UPDATE_FIELDS"),
 }
 THERMAL_ALPHA = 2.0e-3  # thermal diffusion coefficient of the thermal workload (lattice units); def_w_T = 1/(2 alpha + 1/2), beta = 0 (LUW runs without gravity)
 ZONES = dict(downstream_face=2, buffer_N=16, buffer_inv_tau=0.01, buffer_nudge_vertical=1, sponge_N=20, sponge_inv_tau=0.02)

@@ -156,7 +156,7 @@ template<class CFG> __device__ __noinline__ void lean_prefetch_e(const DomainCon
 // quarter of the warp-tiles of an urban case come here, and keeping it out of the loop keeps the loop's registers and instruction-cache footprint for the fast body.
 // Same arithmetic, in the same order, as the fast body (a cell's result must not depend on the path its warp takes). bb / nxt: shared-window addresses.
 template<class CFG, uint32_t FEAT> __device__ __noinline__ void lean_general_pair(const DomainConst& c, const StepArgs& a, const uint32_t bb, const uint32_t nxt, const uint32_t fl2,
-	const uint32_t x, const uint32_t y, const uint32_t z, const bool zone_warp) {
+	const uint32_t x, const uint32_t y, const uint32_t z, const bool zone_warp, const bool odd_end) {
 	constexpr int P = CFG::P;
 	typedef SmemPair<P> SP;
 	typedef typename SP::R R;
@@ -182,8 +182,9 @@ template<class CFG, uint32_t FEAT> __device__ __noinline__ void lean_general_pai
 	}
 	Moments M;
 	const f2 g0 = SP::dec(SP::ldw(bb));
+	const uint32_t sh0 = odd_end ? nxt : bb+(uint32_t)CFG::ES; // cell 0's element of an x-shifted box (+ box_off): the second element of the pair's word -- or, odd Nx, the row's last pair: `nxt` (cell 0 IS the last column, cell 1 does not exist)
 	const auto ldb = [&](const int k) -> R { // box B: the pair's word, or -- x-shifted -- the second element of its word and the element to the right of it
-		if(pair_shifted(k)) return SP::join(SP::lde(bb+(uint32_t)(CFG::box_off(2+2*k)+CFG::ES)), SP::lde(nxt+(uint32_t)CFG::box_off(2+2*k)));
+		if(pair_shifted(k)) return SP::join(SP::lde(sh0+(uint32_t)CFG::box_off(2+2*k)), SP::lde(nxt+(uint32_t)CFG::box_off(2+2*k)));
 		return SP::ldw(bb+(uint32_t)CFG::box_off(2+2*k));
 	};
 	const auto ld1 = [&](const int k, f2& gi, f2& gj) { gi = SP::dec(SP::ldw(bb+(uint32_t)CFG::box_off(1+2*k))); gj = SP::dec(ldb(k)); };
@@ -212,8 +213,8 @@ template<class CFG, uint32_t FEAT> __device__ __noinline__ void lean_general_pai
 		const R ni = SP::enc(gi), nj = SP::enc(gj);
 		SP::stw(bb+(uint32_t)CFG::box_off(bA), mix(nj, r.wa));
 		if(pair_shifted(k)) {
-			if(P==P_FP32) { if(run0) sts_f32(bb+(uint32_t)CFG::box_off(bB)+4u, SmemPair<P_FP32>::enc(gi).x); if(run1) sts_f32(nxt+(uint32_t)CFG::box_off(bB), SmemPair<P_FP32>::enc(gi).y); }
-			else { const uint32_t n16 = *(const uint32_t*)&ni; if(run0) sts_b16(bb+(uint32_t)CFG::box_off(bB)+2u, n16); if(run1) sts_b16(nxt+(uint32_t)CFG::box_off(bB), n16>>16); }
+			if(P==P_FP32) { if(run0) sts_f32(sh0+(uint32_t)CFG::box_off(bB), SmemPair<P_FP32>::enc(gi).x); if(run1) sts_f32(nxt+(uint32_t)CFG::box_off(bB), SmemPair<P_FP32>::enc(gi).y); }
+			else { const uint32_t n16 = *(const uint32_t*)&ni; if(run0) sts_b16(sh0+(uint32_t)CFG::box_off(bB), n16); if(run1) sts_b16(nxt+(uint32_t)CFG::box_off(bB), n16>>16); }
 		} else SP::stw(bb+(uint32_t)CFG::box_off(bB), mix(ni, r.wb0));
 	};
 #pragma unroll
@@ -233,7 +234,7 @@ template<class CFG, uint32_t FEAT> __device__ __noinline__ void lean_general_pai
 	if(EQ&&(e0||e1)) { // generic pointers for the out-of-line equilibrium (shared with k_stream_collide_tile)
 		uint8_t* const gb = (uint8_t*)__cvta_shared_to_generic((size_t)bb);
 		uint8_t* const gn = (uint8_t*)__cvta_shared_to_generic((size_t)nxt);
-		fix_equilibrium<CFG, FEAT>(c, a, n, e0, e1, scale, gb, gn);
+		fix_equilibrium<CFG, FEAT>(c, a, n, e0, e1, scale, gb, gn, odd_end);
 	}
 }
 
@@ -247,8 +248,8 @@ struct LeanConst {
 	int zone_xw, zone_xe; // a warp (64 x-consecutive cells from local x = xw) reaches the west nudging shell iff xw <= zone_xw, the east one iff xw >= zone_xe
 	uint32_t flags;
 };
-enum : uint32_t { LC_WRAP_X = 1u, LC_PARK = 2u, LC_EDGE_X_SLOW = 4u, LC_ZONES = 8u, LC_PREFETCH = 16u, LC_UF = 32u, LC_EQ = 64u };
-template<class CFG> inline LeanConst lean_const(const DomainConst& c, const bool prefetch) {
+enum : uint32_t { LC_WRAP_X = 1u, LC_PARK = 2u, LC_EDGE_X_SLOW = 4u, LC_ZONES = 8u, LC_PREFETCH = 16u, LC_UF = 32u, LC_EQ = 64u, LC_LAG = 128u, LC_ODD_X = 256u };
+template<class CFG> inline LeanConst lean_const(const DomainConst& c, const bool prefetch, const bool lag) {
 	LeanConst l;
 	l.tiles_x = (c.Nx+CFG::TX-1u)/CFG::TX; l.tiles_y = (c.Ny+CFG::TY-1u)/CFG::TY; l.tiles_z = (c.Nz+CFG::TZ-1u)/CFG::TZ;
 	l.last_tx = c.Nx-(l.tiles_x-1u)*(uint32_t)CFG::TX;
@@ -258,7 +259,7 @@ template<class CFG> inline LeanConst lean_const(const DomainConst& c, const bool
 	l.zone_xw = west ? (int)c.buffer_N-c.Ox : -0x7FFFFFFF;
 	l.zone_xe = east ? (int)c.Nxg-1-(int)c.buffer_N-63-c.Ox : 0x7FFFFFFF;
 	l.flags = (c.Dx==1u ? LC_WRAP_X : 0u)|((c.Dx==1u&&l.tiles_x>=2u) ? LC_PARK : 0u)|((c.Dx>1u||l.last_tx!=(uint32_t)CFG::TX) ? LC_EDGE_X_SLOW : 0u)|(zones ? LC_ZONES : 0u)|(prefetch ? LC_PREFETCH : 0u)
-		|((c.features&F_UPDATE_FIELDS) ? LC_UF : 0u)|((c.features&F_EQUILIBRIUM) ? LC_EQ : 0u);
+		|((c.features&F_UPDATE_FIELDS) ? LC_UF : 0u)|((c.features&F_EQUILIBRIUM) ? LC_EQ : 0u)|((lag&&CFG::STAGES>=3) ? LC_LAG : 0u)|((c.Nx&1u) ? LC_ODD_X : 0u);
 	return l;
 }
 __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, const int c0, const int c1, const int c2, const int c3) {
@@ -302,6 +303,7 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 		const bool leader = (tid&31u)==0u;
 		uint32_t lstrip = 0u, lxt = 0u, issued = 0u;
 		bool ended = false;
+		const bool lag = (lc.flags&LC_LAG)!=0u;
 		const auto issue_loads = [&]() {
 			const int s = (int)(issued%(uint32_t)S);
 			if(lxt==0u) {
@@ -376,10 +378,12 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 					}
 				}
 				tma_commit();
-				if(!ended) tma_wait_read0();
+				// refill: the stage just stored may be overwritten once TMA has read it. LC_LAG: do not wait for that here -- refill the stage of the PREVIOUS tile instead, whose
+				// stores were committed a tile-time ago (the wait then returns at once; the ring is one tile shallower)
+				if(!ended) { if(lag) { if(q>0u) tma_wait_read1(); } else tma_wait_read0(); }
 			}
 			__syncwarp();
-			if(!ended) issue_loads();
+			if(!ended&&(!lag||q>0u)) issue_loads();
 			if(park&&last_of_strip&&leader) { tma_wait_all_but(tiles_x-1u); mbar_arrive(bar_head); }
 			sxt = last_of_strip ? 0u : sxt+1u;
 		}
@@ -516,7 +520,7 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 					const uint64_t n = (uint64_t)x+(uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny);
 					fix_equilibrium<CFG, FEAT>(c, a, n, (e2&0x00FFu)!=0u, (e2&0xFF00u)!=0u, scale, (uint8_t*)__cvta_shared_to_generic((size_t)bb), (uint8_t*)__cvta_shared_to_generic((size_t)nxt));
 				}
-			} else lean_general_pair<CFG, FEAT>(c, a, bb, nxt, fl2, x, y, z, zone_warp);
+			} else lean_general_pair<CFG, FEAT>(c, a, bb, nxt, fl2, x, y, z, zone_warp, last&&(lc.flags&LC_ODD_X)!=0u&&lx==lc.rowend_last);
 		}
 		if(bnd_yz) { // write the wrapped elements back to their real addresses (TMA clips them)
 			consumer_bar((uint32_t)NC);

@@ -76,6 +76,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); } // all but the most recent group have been read from shared memory
 __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // all but the `n` most recent groups complete (the operand is an immediate; a smaller n than asked for only waits for more)
 __device__ __forceinline__ void tma_wait_all_but(const uint32_t n) {
@@ -163,6 +164,9 @@ template<> struct PairCodec<P_FP32> { // two floats
 	static __device__ __forceinline__ R shift_in(const R w0, const uint8_t* next) { return make_float2(w0.y, *(const float*)next); }
 	static __device__ __forceinline__ void shift_out(uint8_t* own, uint8_t* next, const R n, const bool k0, const bool k1) { if(k0) ((float*)own)[1] = n.x; if(k1) *(float*)next = n.y; }
 	static __device__ __forceinline__ void shift_out_both(uint8_t* own, uint8_t* next, const R n) { ((float*)own)[1] = n.x; *(float*)next = n.y; }
+	// odd Nx, the row's last pair: cell 0 IS the last column (its +x element is `next`), cell 1 does not exist
+	static __device__ __forceinline__ R shift_in_odd(const uint8_t* next) { return make_float2(*(const float*)next, 0.0f); }
+	static __device__ __forceinline__ void shift_out_odd(uint8_t* next, const R n) { *(float*)next = n.x; }
 	typedef uint32_t M; // lane mask of a pair: bit 0 / bit 1 = cell 0 / 1 takes the new value
 	static __device__ __forceinline__ M mask(const bool k0, const bool k1) { return (k0 ? 1u : 0u)|(k1 ? 2u : 0u); }
 	static __device__ __forceinline__ R mixm(const M m, const R n, const R o) { return make_float2((m&1u) ? n.x : o.x, (m&2u) ? n.y : o.y); }
@@ -179,6 +183,8 @@ template<> struct PairCodec<P_FP16S> { // half2 holding 2^15 f; the 2^15 is fold
 	static __device__ __forceinline__ R shift_in(const R w0, const uint8_t* next) { return __byte_perm(w0, (uint32_t)*(const uint16_t*)next, 0x5432); }
 	static __device__ __forceinline__ void shift_out(uint8_t* own, uint8_t* next, const R n, const bool k0, const bool k1) { if(k0) ((uint16_t*)own)[1] = (uint16_t)(n&0xFFFFu); if(k1) *(uint16_t*)next = (uint16_t)(n>>16); }
 	static __device__ __forceinline__ void shift_out_both(uint8_t* own, uint8_t* next, const R n) { ((uint16_t*)own)[1] = (uint16_t)(n&0xFFFFu); *(uint16_t*)next = (uint16_t)(n>>16); }
+	static __device__ __forceinline__ R shift_in_odd(const uint8_t* next) { return (uint32_t)*(const uint16_t*)next; }
+	static __device__ __forceinline__ void shift_out_odd(uint8_t* next, const R n) { *(uint16_t*)next = (uint16_t)(n&0xFFFFu); }
 	typedef uint32_t M; // bit mask of a pair: the halves that take the new value
 	static __device__ __forceinline__ M mask(const bool k0, const bool k1) { return (k0 ? 0x0000FFFFu : 0u)|(k1 ? 0xFFFF0000u : 0u); }
 	static __device__ __forceinline__ R mixm(const M m, const R n, const R o) { return (n&m)|(o&~m); }
@@ -208,6 +214,8 @@ template<> struct PairCodec<P_FP16C> {
 	static __device__ __forceinline__ R shift_in(const R w0, const uint8_t* next) { return __byte_perm(w0, (uint32_t)*(const uint16_t*)next, 0x5432); }
 	static __device__ __forceinline__ void shift_out(uint8_t* own, uint8_t* next, const R n, const bool k0, const bool k1) { if(k0) ((uint16_t*)own)[1] = (uint16_t)(n&0xFFFFu); if(k1) *(uint16_t*)next = (uint16_t)(n>>16); }
 	static __device__ __forceinline__ void shift_out_both(uint8_t* own, uint8_t* next, const R n) { ((uint16_t*)own)[1] = (uint16_t)(n&0xFFFFu); *(uint16_t*)next = (uint16_t)(n>>16); }
+	static __device__ __forceinline__ R shift_in_odd(const uint8_t* next) { return (uint32_t)*(const uint16_t*)next; }
+	static __device__ __forceinline__ void shift_out_odd(uint8_t* next, const R n) { *(uint16_t*)next = (uint16_t)(n&0xFFFFu); }
 	typedef uint32_t M; // bit mask of a pair: the halves that take the new value
 	static __device__ __forceinline__ M mask(const bool k0, const bool k1) { return (k0 ? 0x0000FFFFu : 0u)|(k1 ? 0xFFFF0000u : 0u); }
 	static __device__ __forceinline__ R mixm(const M m, const R n, const R o) { return (n&m)|(o&~m); }
@@ -283,7 +291,8 @@ template<uint32_t FEAT> __device__ __forceinline__ void equilibrium_cell(const D
 // f := feq(boundary rho, u) (FX/kernel.cpp:1503-1515,1747). Out of line: it runs in the few warps that touch an open face, and keeping it (and a
 // second, select-carrying copy of the collision) out of the loop body keeps the loop inside the instruction cache (profiles/r1_ncu_urban_fp16s.md).
 // `raw16`: FP16S values are stored as the half of the already scaled number (scale = 2^15).
-template<class CFG, uint32_t FEAT> __device__ __noinline__ void fix_equilibrium(const DomainConst& c, const StepArgs& a, const uint64_t n, const bool e0, const bool e1, const float scale, uint8_t* bb, uint8_t* nxt) {
+// `odd_end`: odd Nx, the row's last pair -- cell 0's +x element is `nxt` (see PairCodec::shift_in_odd).
+template<class CFG, uint32_t FEAT> __device__ __noinline__ void fix_equilibrium(const DomainConst& c, const StepArgs& a, const uint64_t n, const bool e0, const bool e1, const float scale, uint8_t* bb, uint8_t* nxt, const bool odd_end = false) {
 	typedef typename PairCodec<CFG::P>::E E;
 	const auto enc1 = [&](const float v) -> E {
 		if constexpr (CFG::P==P_FP32) return v;
@@ -300,7 +309,7 @@ template<class CFG, uint32_t FEAT> __device__ __noinline__ void fix_equilibrium(
 #pragma unroll
 		for(int k=0; k<9; k++) {
 			((E*)(bb+CFG::box_off(1+2*k)))[l] = enc1(feq[2*k+2]); // slot A receives f_i+1
-			if(pair_shifted(k)) { if(l==0u) ((E*)(bb+CFG::box_off(2+2*k)))[1] = enc1(feq[2*k+1]); else *(E*)(nxt+CFG::box_off(2+2*k)) = enc1(feq[2*k+1]); }
+			if(pair_shifted(k)) { if(l==0u&&!odd_end) ((E*)(bb+CFG::box_off(2+2*k)))[1] = enc1(feq[2*k+1]); else *(E*)(nxt+CFG::box_off(2+2*k)) = enc1(feq[2*k+1]); }
 			else ((E*)(bb+CFG::box_off(2+2*k)))[l] = enc1(feq[2*k+1]); // slot B receives f_i
 		}
 	}
@@ -308,7 +317,7 @@ template<class CFG, uint32_t FEAT> __device__ __noinline__ void fix_equilibrium(
 
 // ------------------------------------------------------------------ the kernel
 template<class CFG, uint32_t FEAT, bool FAST> __global__ void __maxnreg__(((FAST&&CFG::TWOPASS) ? tile_max_regs(CFG::THREADS/32, CFG::CTAS_PER_SM) : 128)) // the single-pass paths hold all 19 DDF pairs: 128 registers, residency as it comes
-k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_constant__ StepArgs a, const __grid_constant__ TileMaps maps, const uint32_t tiles_x, const uint32_t tiles_y, const uint32_t tiles_z) {
+k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_constant__ StepArgs a, const __grid_constant__ TileMaps maps, const uint32_t tiles_x, const uint32_t tiles_y, const uint32_t tiles_z, const uint32_t opts) {
 	constexpr int P = CFG::P, TX = CFG::TX, TY = CFG::TY, TZ = CFG::TZ, TILE = CFG::TILE, S = CFG::STAGES, NC = CFG::CONSUMERS;
 	typedef PairCodec<P> PC;
 	typedef typename PC::R R;
@@ -345,6 +354,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 		const bool leader = (tid&31u)==0u;
 		uint32_t lstrip = 0u, lxt = 0u, issued = 0u; // tile the next load belongs to; tiles whose loads have been issued
 		bool ended = false;
+		const bool lag = (opts&1u)!=0u; // refill the stage of the PREVIOUS tile (its stores were committed a tile-time ago) instead of waiting for this tile's stores to be read
 		const auto issue_loads = [&]() {
 			const int s = (int)(issued%(uint32_t)S);
 			if(lxt==0u) { // next strip
@@ -401,11 +411,11 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 				}
 				tma_commit();
 				TRACE(1, q);
-				if(!ended) tma_wait_read0(); // the stage may be refilled once TMA has read it
+				if(!ended) { if(lag) { if(q>0u) tma_wait_read1(); } else tma_wait_read0(); } // the stage may be refilled once TMA has read it
 				TRACE(2, q);
 			}
 			__syncwarp();
-			if(!ended) issue_loads();
+			if(!ended&&(!lag||q>0u)) issue_loads();
 			if(leader) TRACE(3, q);
 			if(park&&last_of_strip&&leader) { tma_wait_all_but(tiles_x-1u); mbar_arrive(bar_head); } // the strip's first tile (tiles_x-1 groups ago) is in global memory: its column 0 may be overwritten
 			sxt = last_of_strip ? 0u : sxt+1u;
@@ -421,6 +431,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 	const bool has_zones = VF&&(c.features&(F_NUDGING|F_SPONGE))!=0u;
 	const int Nb = (c.features&F_NUDGING) ? (int)c.buffer_N : -1, Ns = (c.features&F_SPONGE) ? (int)c.sponge_N : 0;
 	const uint32_t last_tx = c.Nx-(tiles_x-1u)*(uint32_t)TX; // cells of the last tile's rows that lie inside the lattice
+	const uint32_t rowend_last = (last_tx-1u)&~1u; // local x of the pair that holds a row's last cell in the strip's last tile (odd Nx: that cell is the pair's cell 0)
 	// walk: strips as published by the producer; inside a strip xt = 0..tiles_x-1; ring slot s and its phase advance with every tile
 	uint32_t xt = 0u, s = 0u, ph = 0u, kstrip = 0u;
 	int y0 = 0, z0 = 0, py0 = 0, pz0 = 0;
@@ -447,7 +458,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 		if(park&&kstrip>0u&&xt==1u) { // write the previous strip's periodic-x column
 			mbar_wait(bar_head, (kstrip-1u)&1u);
 			__syncwarp();
-			if(lx==last_tx-2u) flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd); // the thread that wrote the parked elements last
+			if(lx==rowend_last) flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd); // the thread that wrote the parked elements last
 		}
 
 		if(tid==0u) TRACE(4, q);
@@ -483,9 +494,10 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 		if(park&&first) { if(TX==64) __syncwarp(); else consumer_bar((uint32_t)NC); }
 		if(run0||run1) {
 			// element right of the pair's word in an x-shifted box: the next word of the row, or column 0 of the same row in the next stage / the parked column
-			const uint32_t rowend_lx = last ? last_tx-2u : (uint32_t)(TX-2);
+			const uint32_t rowend_lx = last ? rowend_last : (uint32_t)(TX-2);
 			uint8_t* nxt = (uint8_t*)(box+1);
 			if(lx==rowend_lx) nxt = !last ? st1+(size_t)row*TX*CFG::ES : park ? park_row : wrap_x ? st+(size_t)row*TX*CFG::ES : (uint8_t*)box;
+			const bool odd_end = last&&(c.Nx&1u)!=0u&&lx==rowend_lx; // odd Nx: cell 0 of the row's last pair is the lattice's last column, its +x element is `nxt` (cell 1 does not exist: run1 is false)
 			const uint32_t bo0 = fl0&TYPE_BO, bo1 = fl1&TYPE_BO;
 			const bool e0 = EQ&&run0&&bo0==TYPE_E, e1 = EQ&&run1&&bo1==TYPE_E;
 			PairIn in;
@@ -521,7 +533,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 				const auto ld1 = [&](const int k, f2& gi, f2& gj) {
 					const R wa = *(const R*)(bb+CFG::box_off(1+2*k));
 					R wb = *(const R*)(bb+CFG::box_off(2+2*k));
-					if(pair_shifted(k)) wb = PC::shift_in(wb, nxt+CFG::box_off(2+2*k));
+					if(pair_shifted(k)) wb = odd_end ? PC::shift_in_odd(nxt+CFG::box_off(2+2*k)) : PC::shift_in(wb, nxt+CFG::box_off(2+2*k));
 					gi = dec_in(wa); gj = dec_in(wb);
 				};
 				moments_of<SG>(g0, ld1, M);
@@ -535,14 +547,14 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 				const auto ld2 = [&](const int k, Raw& r, f2& gi, f2& gj) {
 					r.wa = *(const R*)(bb+CFG::box_off(1+2*k)); r.wb0 = *(const R*)(bb+CFG::box_off(2+2*k));
 					R wb = r.wb0;
-					if(pair_shifted(k)) wb = PC::shift_in(r.wb0, nxt+CFG::box_off(2+2*k));
+					if(pair_shifted(k)) wb = odd_end ? PC::shift_in_odd(nxt+CFG::box_off(2+2*k)) : PC::shift_in(r.wb0, nxt+CFG::box_off(2+2*k));
 					gi = dec_in(r.wa); gj = dec_in(wb);
 				};
 				const auto st2 = [&](const int k, const Raw& r, const f2 gi, const f2 gj) { // f_i' goes to slot B, f_i+1' to slot A
 					const int bA = 1+2*k, bB = 2+2*k;
 					const R ni = enc_out(gi), nj = enc_out(gj);
 					*(R*)(bb+CFG::box_off(bA)) = PC::mixm(msk, nj, r.wa);
-					if(pair_shifted(k)) PC::shift_out(bb+CFG::box_off(bB), nxt+CFG::box_off(bB), ni, run0, run1);
+					if(pair_shifted(k)) { if(odd_end) { if(run0) PC::shift_out_odd(nxt+CFG::box_off(bB), ni); } else PC::shift_out(bb+CFG::box_off(bB), nxt+CFG::box_off(bB), ni, run0, run1); }
 					else *(R*)(bb+CFG::box_off(bB)) = PC::mixm(msk, ni, r.wb0);
 				};
 #pragma unroll
@@ -559,14 +571,14 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 					fast_relax_diag(K, pl, gip, gjp, gim, gjm);
 					st2(3+pl, rp, gip, gjp); st2(6+pl, rm, gim, gjm);
 				}
-				if(EQ&&(e0||e1)) fix_equilibrium<CFG, FEAT>(c, a, n, e0, e1, scale, bb, nxt);
+				if(EQ&&(e0||e1)) fix_equilibrium<CFG, FEAT>(c, a, n, e0, e1, scale, bb, nxt, odd_end);
 			} else {
 			// load_f: box 0 -> f0, box 1+2k -> f_(2k+1), box 2+2k -> f_(2k+2)
 			f2 f[Q];
 #pragma unroll
 			for(int b=0; b<Q; b++) {
 				R w = *(const R*)((const uint8_t*)box+CFG::box_off(b));
-				if(box_shifted(b)) w = PC::shift_in(w, nxt+CFG::box_off(b));
+				if(box_shifted(b)) w = odd_end ? PC::shift_in_odd(nxt+CFG::box_off(b)) : PC::shift_in(w, nxt+CFG::box_off(b));
 				if(FAST&&P==P_FP16S) f[b] = PairCodec<P_FP16S>::dec_raw(*(const uint32_t*)&w); else f[b] = PC::dec(w);
 			}
 			float4 eb0 = make_float4(1.0f, 0.0f, 0.0f, 0.0f), eb1 = eb0; // boundary rho/u of TYPE_E lanes (prefetched into L2 one tile ago)
@@ -621,7 +633,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 				for(int k=0; k<9; k++) {
 					const int bA = 1+2*k, bB = 2+2*k;
 					*(R*)(bb+CFG::box_off(bA)) = PC::mix(run0, run1, nw[bB], *(R*)(bb+CFG::box_off(bA)));
-					if(box_shifted(bB)) PC::shift_out(bb+CFG::box_off(bB), nxt+CFG::box_off(bB), nw[bA], run0, run1);
+					if(box_shifted(bB)) { if(odd_end) { if(run0) PC::shift_out_odd(nxt+CFG::box_off(bB), nw[bA]); } else PC::shift_out(bb+CFG::box_off(bB), nxt+CFG::box_off(bB), nw[bA], run0, run1); }
 					else *(R*)(bb+CFG::box_off(bB)) = PC::mix(run0, run1, nw[bA], *(R*)(bb+CFG::box_off(bB)));
 				}
 			}
@@ -650,7 +662,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 	TRACE_CLK(2);
 	if(park&&kstrip>0u) { // the last strip's periodic-x column
 		mbar_wait(bar_head, (kstrip-1u)&1u);
-		if(lx==last_tx-2u) flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd);
+		if(lx==rowend_last) flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd);
 	}
 }
 

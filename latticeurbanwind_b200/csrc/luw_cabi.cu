@@ -168,7 +168,7 @@ void setup_tiles(luw_domain* d) {
 	// default: two-pass kernel; 5 CTAs/SM where the collision fits 72 registers (no LES), else 128x4 tiles with 8 consumer warps per producer (measured, profiles/)
 	const int want = (var&&var[0]) ? atoi(var) : d->c.precision==luw::P_FP16C ? 3 : (d->c.precision==luw::P_FP16S&&(d->c.features&luw::F_SUBGRID)) ? 4 : 0; // FP16C: the software codec makes decoding twice dearer than the registers (single pass)
 	const luw::DomainConst& c = d->c;
-	if(c.Nx%2u!=0u) return; // two x-adjacent cells per thread
+	// odd Nx: the row's last pair holds one cell (rows are padded to Px, a multiple of 16 elements); lbm_tile.cuh `odd_end`
 	encode_tiled_fn enc = get_encode_tiled();
 	if(!enc) return;
 	luw::TileShape sh;

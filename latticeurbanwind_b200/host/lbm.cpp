@@ -98,6 +98,51 @@ extern "C" uint luw_host_cull_triangles(const float* p0, const float* p1, const 
 	return (uint)ids.size();
 }
 
+// ---------------------------------------------------------------------------------------------------------------- test hook: LUW_DUMP_DIR
+static const char* dump_dir() { static const char* d = getenv("LUW_DUMP_DIR"); return (d&&d[0]) ? d : nullptr; }
+bool luw_dump_enabled() { return dump_dir()!=nullptr; }
+void luw_dump_array(const char* name, const void* data, const ulong bytes) {
+	const std::string path = std::string(dump_dir())+"/"+name+".bin";
+	FILE* f = fopen(path.c_str(), "wb");
+	if(!f) return;
+	fwrite(data, 1u, (size_t)bytes, f);
+	fclose(f);
+}
+void luw_dump_voxelize_call(luw_domain* handle, const ulong N, const uint direction, const uchar flag, const float* p0, const float* p1, const float* p2, const uint triangle_number, const float* bbu) {
+	const uint head[4] = { triangle_number, direction, (uint)flag, 0u };
+	std::vector<float> tri; tri.reserve(16u+9u*(size_t)triangle_number);
+	tri.insert(tri.end(), bbu, bbu+16);
+	tri.insert(tri.end(), p0, p0+3u*(size_t)triangle_number); tri.insert(tri.end(), p1, p1+3u*(size_t)triangle_number); tri.insert(tri.end(), p2, p2+3u*(size_t)triangle_number);
+	luw_dump_array("vox_head", head, sizeof(head));
+	luw_dump_array("vox_tri", tri.data(), tri.size()*sizeof(float));
+	std::vector<uchar> fl((size_t)N); std::vector<float> u(3u*(size_t)N); // the device images the kernel works on
+	luw_check(luw_download(handle, LUW_FIELD_FLAGS, fl.data(), 0ull, N)); luw_check(luw_download(handle, LUW_FIELD_U, u.data(), 0ull, 3ull*N)); luw_check(luw_sync(handle));
+	luw_dump_array("vox_flags_before", fl.data(), N); luw_dump_array("vox_u_before", u.data(), 3ull*N*sizeof(float));
+}
+void LBM::dump_state(const char* tag) {
+	if(!luw_dump_enabled()||get_D()!=1u) return;
+	LBM_Domain* dm = lbm_domain[0];
+	const ulong N = dm->get_N();
+	const std::string t(tag);
+	if(t=="init") { // the host images initialize() uploads, and the constants the kernels were given
+		luw_dump_array("init_flags", dm->flags.data(), N); luw_dump_array("init_rho", dm->rho.data(), N*sizeof(float)); luw_dump_array("init_u", dm->u.data(), 3ull*N*sizeof(float));
+		const std::string path = std::string(dump_dir())+"/params.txt";
+		FILE* f = fopen(path.c_str(), "w");
+		if(f) {
+			fprintf(f, "Nx %u\nNy %u\nNz %u\nprecision %u\nfeatures %u\narith %u\n", dm->get_Nx(), dm->get_Ny(), dm->get_Nz(), env_uint("LUW_PRECISION", lbm_settings.precision), lbm_settings.features, env_uint("LUW_ARITH", lbm_settings.arith));
+			fprintf(f, "w %.9g\nfx %.9g\nfy %.9g\nfz %.9g\nomega_x %.9g\nomega_y %.9g\nomega_z %.9g\n", (double)lbm_kernel_literal(1.0f/(3.0f*dm->get_nu()+0.5f)), (double)dm->get_fx(), (double)dm->get_fy(), (double)dm->get_fz(), (double)dm->get_omega_x(), (double)dm->get_omega_y(), (double)dm->get_omega_z());
+			fprintf(f, "downstream_face %d\nbuffer_N %u\nbuffer_inv_tau %.9g\nbuffer_nudge_vertical %d\nsponge_N %u\nsponge_inv_tau %.9g\n", lbm_settings.downstream_face, lbm_settings.buffer_N>0u ? lbm_settings.buffer_N : 1u, (double)lbm_kernel_literal(lbm_settings.buffer_inv_tau),
+				lbm_settings.buffer_nudge_vertical, lbm_settings.sponge_N>0u ? lbm_settings.sponge_N : 1u, (double)lbm_kernel_literal(lbm_settings.sponge_inv_tau));
+			fclose(f);
+		}
+		return;
+	}
+	std::vector<float> r((size_t)N), u(3u*(size_t)N); // rho / u of the device, without touching the host mirrors the case driver works on
+	if(!(lbm_settings.features&LUW_UPDATE_FIELDS)) dm->enqueue_update_fields();
+	luw_check(luw_download(dm->get_handle(), LUW_FIELD_RHO, r.data(), 0ull, N)); luw_check(luw_download(dm->get_handle(), LUW_FIELD_U, u.data(), 0ull, 3ull*N)); luw_check(luw_sync(dm->get_handle()));
+	luw_dump_array((t+"_rho").c_str(), r.data(), N*sizeof(float)); luw_dump_array((t+"_u").c_str(), u.data(), 3ull*N*sizeof(float));
+}
+
 luw_domain* LBM_Domain::create_handle(const int device, const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const int Ox, const int Oy, const int Oz, const float nu, const float alpha, const float beta) {
 	luw_domain_params p;
 	memset(&p, 0, sizeof(p));
@@ -161,6 +206,7 @@ LBM::LBM(const uint3 N, const uint Dx, const uint Dy, const uint Dz, const float
 LBM::LBM(const uint3 N, const float nu, const float fx, const float fy, const float fz, const float, const float alpha, const float beta) { construct(N.x, N.y, N.z, 1u, 1u, 1u, nu, fx, fy, fz, alpha, beta); }
 LBM::~LBM() {
 #ifdef LUW_USE_REFERENCE_UTILITIES
+	flush_pending();
 	info.print_finalize(); // FX/lbm.cpp: the console table is closed with the simulation
 #endif
 	for(uint d=0u; d<get_D(); d++) delete lbm_domain[d];
@@ -173,6 +219,7 @@ void LBM::communicate(const int payload) { // FX/lbm.cpp:1907-1958: x, then y, t
 }
 void LBM::initialize() { // FX/lbm.cpp:1221-1260
 	const uint D = get_D();
+	dump_state("init");
 	for(uint d=0u; d<D; d++) { lbm_domain[d]->rho.enqueue_write_to_device(); lbm_domain[d]->u.enqueue_write_to_device(); lbm_domain[d]->flags.enqueue_write_to_device(); }
 	if(LBM_Domain::thermal()) for(uint d=0u; d<D; d++) lbm_domain[d]->T.enqueue_write_to_device();
 	for(uint d=0u; d<D; d++) lbm_domain[d]->increment_time_step(); // slot parity t = 1 for the initial DDF layout
@@ -191,18 +238,23 @@ void LBM::do_time_step() { // FX/lbm.cpp:1262-1290 (GRAPHICS exchanges and the p
 	communicate(LUW_HALO_FI);
 	if(LBM_Domain::thermal()) communicate(LUW_HALO_GI); // communicate_gi()
 	for(uint d=0u; d<D; d++) lbm_domain[d]->increment_time_step();
+	static const ulong dump_step = []{ const char* e = getenv("LUW_DUMP_STEP"); return e ? (ulong)atol(e) : 0ull; }();
+	if(dump_step>0ull&&get_t()==dump_step) dump_state("step");
 }
 void LBM::run(const ulong steps, const ulong total_steps) { // FX/lbm.cpp:1292-1312
 #ifdef LUW_USE_REFERENCE_UTILITIES // inside the reference tree: feed the console table / ETA model exactly like FX/lbm.cpp does (FX/info.cpp reads it from another thread)
 	info.append(steps, total_steps, get_t());
 	if(!initialized) { initialize(); info.print_initialize(this); }
-	Clock clock;
+	// The case driver calls run(1) once per step (FX/setup.cpp:4898). Synchronising after every step, as FX/lbm.cpp:1306 does, leaves the GPU idle while the host
+	// prepares the next step (14.8 GLUP/s on the console for the 3.7 M-cell example deck); here the steps stay enqueued and the queues are drained every
+	// LUW_SYNC_EVERY steps (default 16; 1 = the reference's behaviour). The elapsed time is credited to the drained steps in equal parts, so `info` still sees one
+	// update per step. Host reads in between (probes, averages, VTK) synchronise by themselves: they are ordered on the same streams.
+	static const ulong sync_every = []{ const char* e = getenv("LUW_SYNC_EVERY"); const long v = e ? atol(e) : 16l; return (ulong)(v<1l ? 1l : v); }();
 	const ulong n = steps==max_ulong ? 0ull : steps;
 	for(ulong i=0ull; i<n; i++) {
-		clock.start();
+		if(pending_steps==0ull) pending_t0 = std::chrono::high_resolution_clock::now();
 		do_time_step();
-		for(uint d=0u; d<get_D(); d++) lbm_domain[d]->finish_queue(); // the step time shown on the console is the step's, not the enqueue's
-		info.update(clock.stop());
+		if(++pending_steps>=sync_every) flush_pending();
 	}
 #else // stand-alone: steps are enqueued back to back, one synchronisation at the end of the call
 	(void)total_steps;
@@ -211,6 +263,15 @@ void LBM::run(const ulong steps, const ulong total_steps) { // FX/lbm.cpp:1292-1
 	for(ulong i=0ull; i<n; i++) do_time_step();
 	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->finish_queue();
 #endif
+}
+void LBM::flush_pending() {
+	if(pending_steps==0ull) return;
+	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->finish_queue();
+#ifdef LUW_USE_REFERENCE_UTILITIES
+	const double dt = std::chrono::duration_cast<std::chrono::duration<double>>(std::chrono::high_resolution_clock::now()-pending_t0).count()/(double)pending_steps;
+	for(ulong k=0ull; k<pending_steps; k++) info.update(dt);
+#endif
+	pending_steps = 0ull;
 }
 void LBM::update_fields() { for(uint d=0u; d<get_D(); d++) lbm_domain[d]->enqueue_update_fields(); for(uint d=0u; d<get_D(); d++) lbm_domain[d]->finish_queue(); }
 void LBM::reset() { initialized = false; }

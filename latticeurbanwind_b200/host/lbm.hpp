@@ -22,6 +22,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <chrono>
 
 #ifndef LUW_USE_REFERENCE_UTILITIES
 typedef unsigned int uint;
@@ -183,6 +184,13 @@ std::vector<uint> luw_cull_triangles(const float* p0, const float* p1, const flo
 	const int Ox, const int Oy, const int Oz, const uint local_Nx, const uint local_Ny, const uint local_Nz);
 
 // ---------------------------------------------------------------------------------------------------------------- LBM_Domain (FX/lbm.hpp:26-221)
+// Test hook (tests/test_reference_driver.py): with LUW_DUMP_DIR set, a single-domain LBM writes what it is given and what it computes as raw arrays -- the
+// triangles of every voxelisation call, the host images at initialize(), rho / u after step LUW_DUMP_STEP -- so that the deck-driven path through the
+// reference's unmodified case driver can be compared with the oracle bit for bit. Never on in production (one getenv at start-up).
+bool luw_dump_enabled();
+void luw_dump_array(const char* name, const void* data, const ulong bytes);
+void luw_dump_voxelize_call(luw_domain* handle, const ulong N, const uint direction, const uchar flag, const float* p0, const float* p1, const float* p2, const uint triangle_number, const float* bbu);
+
 class LBM_Domain {
 private:
 	uint Nx=1u, Ny=1u, Nz=1u, Dx=1u, Dy=1u, Dz=1u; int Ox=0, Oy=0, Oz=0;
@@ -233,8 +241,11 @@ public:
 		float bbu[16] = {0.0f};
 		memcpy(&bbu[0], &triangle_number, sizeof(uint));
 		bbu[1] = pmin.x-2.0f; bbu[2] = pmin.y-2.0f; bbu[3] = pmin.z-2.0f; bbu[4] = pmax.x+2.0f; bbu[5] = pmax.y+2.0f; bbu[6] = pmax.z+2.0f;
+		const bool dump = luw_dump_enabled();
+		if(dump) luw_dump_voxelize_call(handle, (ulong)Nx*Ny*Nz, direction, flag, p0, p1, p2, triangle_number, bbu); // test hook (LUW_DUMP_DIR): the call's inputs, for the oracle voxeliser
 		luw_check(luw_voxelize_mesh(handle, direction, flag, p0, p1, p2, triangle_number, bbu));
 		flags.read_from_device();
+		if(dump) luw_dump_array("vox_flags_after", flags.data(), (ulong)Nx*Ny*Nz);
 	}
 #ifdef LUW_USE_REFERENCE_UTILITIES
 	void voxelize_mesh_on_device(const Mesh* mesh, const uchar flag=TYPE_S) { voxelize_triangles_on_device((const float*)mesh->p0, (const float*)mesh->p1, (const float*)mesh->p2, mesh->triangle_number, mesh->pmin, mesh->pmax, flag); }
@@ -263,6 +274,10 @@ class LBM {
 private:
 	uint Nx=1u, Ny=1u, Nz=1u, Dx=1u, Dy=1u, Dz=1u;
 	bool initialized = false;
+	ulong pending_steps = 0ull; // reference-tree mode: steps enqueued since the last synchronisation (run() synchronises every LUW_SYNC_EVERY steps, not every step)
+	std::chrono::time_point<std::chrono::high_resolution_clock> pending_t0;
+	void dump_state(const char* tag); // test hook, see luw_dump_enabled
+	void flush_pending(); // synchronise and credit the elapsed time to the pending steps (info.update once per step, like FX/lbm.cpp:1292-1312)
 	std::vector<luw_domain*> handles;
 	void construct(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const float nu, const float fx, const float fy, const float fz, const float alpha, const float beta);
 	void initialize(); // FX/lbm.cpp:1221-1260

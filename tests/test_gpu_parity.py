@@ -64,7 +64,7 @@ def test_update_fields_on_demand(oracle_lib):
 
 
 # ---------------------------------------------------------------------------------------------- the TMA-tiled step kernel
-TILED_SHAPES = [(64, 8, 4), (128, 20, 12), (80, 10, 7), (192, 9, 5), (768, 6, 4), (66, 10, 6), (130, 7, 5), (202, 6, 4)]  # exact tiles, several tiles, partial tiles in x / y / z, strips longer than the stage ring, x extents that need a padded device row pitch (decomposed blocks: Nx/Dx + 2)
+TILED_SHAPES = [(64, 8, 4), (128, 20, 12), (80, 10, 7), (192, 9, 5), (768, 6, 4), (66, 10, 6), (130, 7, 5), (202, 6, 4), (65, 8, 4), (129, 7, 5), (253, 10, 7), (385, 5, 3)]  # the last four: odd Nx (the row's last pair holds one cell; real decks size Nx = round(si_x / cell), FX/setup.cpp:3552-3568); exact tiles, several tiles, partial tiles in x / y / z, strips longer than the stage ring, x extents that need a padded device row pitch (decomposed blocks: Nx/Dx + 2)
 
 
 @pytest.mark.parametrize("precision", [0, 1, 2], ids=["fp32", "fp16s", "fp16c"])
@@ -83,11 +83,15 @@ def test_tiled_strict_equals_oracle(oracle_lib, precision, fset, shape):
     assert np.array_equal(got[2], ref[2]), "u differs"
 
 
+@pytest.mark.parametrize("odd", [False, True], ids=["even", "oddNx"])
 @pytest.mark.parametrize("precision", [0, 1], ids=["fp32", "fp16s"])
-def test_tiled_periodic_box_equals_oracle(oracle_lib, precision):
-    """Fully periodic lattice (upstream BENCHMARK protocol): every wrapped neighbour goes through the tile kernel's boundary patch."""
+def test_tiled_periodic_box_equals_oracle(oracle_lib, precision, odd):
+    """Fully periodic lattice (upstream BENCHMARK protocol): every wrapped neighbour goes through the tile kernel's boundary patch. Odd Nx: the periodic-x
+    neighbour of the last column belongs to cell 0 of the row's last pair."""
     O = oracle_lib
     shape = (128, 12, 6) if precision == 0 else (768, 6, 4)  # one tile per strip / strips longer than the stage ring (parked column without the barrier)
+    if odd:
+        shape = (127, 12, 6) if precision == 0 else (771, 6, 4)  # wrap inside the only tile / through the parked column
     flags, rho, u = cases.periodic_box(*shape, seed=5, amp=1e-2)
     w = cases.relaxation_rate(1.0 / 6.0)
     ref = H.run_cpu(O.Oracle(), O, shape, precision, 0, flags, rho, u, 11, w)
@@ -181,11 +185,11 @@ def test_bench_instantiation_fast_within_tolerance(oracle_lib, monkeypatch, prec
     assert e[0] <= tol["rel_l2_u"] and e[1] <= tol["max_abs_u"] and e[2] <= tol["rel_l2_rho"], e
 
 
+@pytest.mark.parametrize("shape", [(256, 24, 12), (253, 12, 9)], ids=["256x24x12", "253x12x9-oddNx"])
 @pytest.mark.parametrize("variant", [0, 4, 5, 6, 7], ids=lambda v: f"V{v}")
-def test_fast_result_does_not_depend_on_the_tile_variant(monkeypatch, variant):
+def test_fast_result_does_not_depend_on_the_tile_variant(monkeypatch, variant, shape):
     """A cell's FAST result is a function of its own DDFs only: every two-pass variant -- tile shape, lean or general loop, masked or
     unmasked stores -- must produce the same bits. This is what makes decomposed FAST runs equal to single-domain ones."""
-    shape = (256, 24, 12)
     flags, rho, u, w = _bench_case("luw", shape)
     res = []
     for v in (1, variant):
@@ -398,6 +402,26 @@ def test_cell_sets_move_boundary_data_without_whole_fields():
         d.read_from_device(A.FIELD_U); d.finish_queue()
         assert np.array_equal(d.u, want)
         cs.close()
+
+
+@pytest.mark.parametrize("precision,arith", [(2, 0), (2, 1), (1, 1)], ids=["fp16c-strict", "fp16c-fast", "fp16s-fast"])
+def test_reference_example_lattice_runs_the_tile_kernel(oracle_lib, precision, arith):
+    """253 x 250 x 59 is the lattice of the reference's own example deck (examples/example_ProfileResearch_noDEM at its default cell size): odd Nx, partial tiles
+    in x, y and z. It must reach the TMA tile kernel (luw_domain_step_kernel == 1) and equal the oracle."""
+    O = oracle_lib
+    shape = (253, 250, 59)
+    flags, rho, u = cases.block_case("urban", shape)
+    w = cases.relaxation_rate(1e-6)
+    feat = H.FEATURE_SETS["luw"]
+    zones = dict(downstream_face=2, buffer_N=16, buffer_inv_tau=0.01, buffer_nudge_vertical=1, sponge_N=20, sponge_inv_tau=0.02)
+    ref = H.run_cpu(O.Oracle(), O, shape, precision, feat, flags, rho, u, 6, w, zones=zones)
+    got = H.run_cuda(shape, precision, feat, flags, rho, u, 6, w, arith=arith, zones=zones, batched=True, expect_tiles=True)
+    if arith == 0:
+        assert np.array_equal(H.decode(O, None, got[0], precision), H.decode(O, None, ref[0], precision)), "DDFs differ"
+        assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2]), "rho / u differ"
+    else:
+        e = H.errors(got, ref)
+        assert e[0] <= 1e-3 and e[1] <= 2e-4, e
 
 
 def test_c1_sized_case_equals_oracle(oracle_lib):

@@ -10,6 +10,8 @@ import subprocess
 import numpy as np
 import pytest
 
+from tests import helpers as H
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DRIVER = os.path.join(ROOT, "baseline", "_ref", "luw_reference_driver")
 CASE = os.path.join(ROOT, "baseline", "_ref", "case_profile")
@@ -49,3 +51,49 @@ def test_reference_case_driver_runs_its_example_deck(tmp_path):
             assert 1.0 < float(speed.max()) < 40.0, (p, float(speed.max()))
             checked += 1
     assert checked >= 1, [os.path.basename(p) for p in vtks]
+
+
+def test_deck_driven_path_equals_oracle(tmp_path, oracle_lib):
+    """Parity of the deck-driven path: the same binary, STRICT arithmetic, von Karman inlet off (its per-step update is covered by test_vk_inlet_matches_oracle),
+    20 steps. The host layer's LUW_DUMP_DIR hook writes what the case driver handed it -- the triangles of its voxelisation call, the host images at initialize(),
+    the kernel constants -- and rho / u after step 20. (a) the flags after voxelising CaseE_PF.stl equal the oracle voxeliser's on the same triangles, bit for bit;
+    (b) rho / u after 20 steps equal the oracle's from the same initial images, bit for bit; (c) the 253-wide lattice ran on the TMA tile kernel."""
+    O = oracle_lib
+    case, dump = str(tmp_path / "case"), str(tmp_path / "dump")
+    shutil.copytree(CASE, case)
+    os.makedirs(dump)
+    deck = open(os.path.join(case, "conf.luwpf")).read()
+    deck = re.sub(r"(?m)^run_nstep\s*=.*$", "run_nstep = 20", deck) + "\nvk_inlet_enable = false\n"
+    open(os.path.join(case, "conf.luwpf"), "w").write(deck)
+    env = dict(os.environ, LUW_ARITH="0", LUW_DUMP_DIR=dump, LUW_DUMP_STEP="20", LUW_VERBOSE="1")
+    r = subprocess.run([DRIVER, os.path.join(case, "conf.luwpf")], capture_output=True, text=True, timeout=600, cwd=case, env=env, stdin=subprocess.DEVNULL)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    assert "tile kernel" in r.stderr, "the example deck's 253 x 250 x 59 lattice did not reach the TMA tile kernel:\n" + r.stderr[-2000:]
+    prm = dict(line.split() for line in open(os.path.join(dump, "params.txt")))
+    shape = (int(prm["Nx"]), int(prm["Ny"]), int(prm["Nz"]))
+    N = shape[0] * shape[1] * shape[2]
+    precision, features = int(prm["precision"]), int(prm["features"])
+    assert shape[:2] == (253, 250) and int(prm["arith"]) == 0
+    zones = dict(downstream_face=int(prm["downstream_face"]), buffer_N=int(prm["buffer_N"]), buffer_inv_tau=float(prm["buffer_inv_tau"]),
+                 buffer_nudge_vertical=int(prm["buffer_nudge_vertical"]), sponge_N=int(prm["sponge_N"]), sponge_inv_tau=float(prm["sponge_inv_tau"]))
+    p = O.make_params(*shape, precision, features, w=float(prm["w"]), **zones)
+    rd = lambda name, dt: np.fromfile(os.path.join(dump, name + ".bin"), dt)
+    # (a) voxelisation
+    ntri, direction, flag, _ = (int(v) for v in rd("vox_head", np.uint32))
+    tri = rd("vox_tri", np.float32)
+    bbu, p0, p1, p2 = tri[:16].copy(), tri[16:16 + 3 * ntri].copy(), tri[16 + 3 * ntri:16 + 6 * ntri].copy(), tri[16 + 6 * ntri:16 + 9 * ntri].copy()
+    assert ntri > 1000 and tri.size == 16 + 9 * ntri
+    flags, uu = rd("vox_flags_before", np.uint8), rd("vox_u_before", np.float32)
+    O.Oracle().bind(p).voxelize_mesh(direction, uu, flags, flag, p0, p1, p2, bbu)
+    got = rd("vox_flags_after", np.uint8)
+    assert np.array_equal(got, flags), f"voxelised flags differ from the oracle in {int((got != flags).sum())} cells"
+    assert int(((got & 3) == 1).sum()) > 10000
+    # (b) 20 steps from the driver's initial images
+    f = (float(prm["fx"]), float(prm["fy"]), float(prm["fz"]))
+    omega = (float(prm["omega_x"]), float(prm["omega_y"]), float(prm["omega_z"]))
+    ref = H.run_cpu(O.Oracle(), O, shape, precision, features, rd("init_flags", np.uint8), rd("init_rho", np.float32), rd("init_u", np.float32), 20,
+                    float(prm["w"]), f=f, omega=omega, zones=zones, update_at_end=not (features & 1))
+    rho, u = rd("step_rho", np.float32), rd("step_u", np.float32)
+    assert rho.size == N and u.size == 3 * N
+    assert np.array_equal(rho, ref[1]), f"rho differs in {int((rho != ref[1]).sum())} cells"
+    assert np.array_equal(u, ref[2]), f"u differs in {int((u != ref[2]).sum())} values"
