@@ -258,6 +258,7 @@ def main():
     ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    args.also_default = args.also is None
     if args.also is None:
         args.also = "urban_fp16s_uf,channel512_fp16s,channel512_fp32,channel512_fp16c" if args.workload == "urban_fp16s" and args.gpus == 1 else ""
     if args.impl == "reference":
@@ -507,60 +508,79 @@ def bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src):
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    D = tuple(int(v) for v in args.decomp.split(",")) if args.decomp else DECOMP[case][world]
-    assert len(D) == 3 and D[0] * D[1] * D[2] == world, "--decomp must multiply to the number of ranks"
-    H = tuple(1 if v > 1 else 0 for v in D)
-    Ng = tuple((n - 2 * h) * v for n, h, v in zip(shape, H, D))  # global lattice whose blocks have exactly the workload's local size incl. halos
-    zones = ZONES if features & (F_NUDGE | F_SPONGE) else {}
-    lbm = DistributedLBM(Ng, D, device=local, nu=nu, precision=precision, features=features, arith=arith,
-                         omega=OMEGA if features & F_VF else (0.0, 0.0, 0.0), transport=args.transport,
-                         **(dict(alpha=THERMAL_ALPHA) if features & F_TEMPERATURE else {}), **zones)
-    assert tuple(lbm.Nl) == tuple(shape)
-    flags, rho, u = cases.block_case(case, Ng, lbm.O, shape)
-    T = thermal_fields(flags, shape) if features & F_TEMPERATURE else None  # per-block stratification: a benchmark input, not a physical profile across blocks
-    dist.barrier()  # host-side case generation takes seconds and not the same number on every rank: start the first halo exchange together
-    lbm.initialize(flags, rho, u, T)
+    D0 = tuple(int(v) for v in args.decomp.split(",")) if args.decomp else DECOMP[case][world]
+    assert len(D0) == 3 and D0[0] * D0[1] * D0[2] == world, "--decomp must multiply to the number of ranks"
     K, W = args.steps, args.warmup
-    lbm.run(W)
-    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+
+    def run_decomp(D):
+        """One weak-scaling measurement: every rank owns a block of the workload's local size (halo layers included) of a lattice decomposed as D."""
+        H = tuple(1 if v > 1 else 0 for v in D)
+        Ng = tuple((n - 2 * h) * v for n, h, v in zip(shape, H, D))  # global lattice whose blocks have exactly the workload's local size incl. halos
+        zones = ZONES if features & (F_NUDGE | F_SPONGE) else {}
+        lbm = DistributedLBM(Ng, D, device=local, nu=nu, precision=precision, features=features, arith=arith,
+                             omega=OMEGA if features & F_VF else (0.0, 0.0, 0.0), transport=args.transport,
+                             **(dict(alpha=THERMAL_ALPHA) if features & F_TEMPERATURE else {}), **zones)
+        assert tuple(lbm.Nl) == tuple(shape)
+        flags, rho, u = cases.block_case(case, Ng, lbm.O, shape)
+        T = thermal_fields(flags, shape) if features & F_TEMPERATURE else None  # per-block stratification: a benchmark input, not a physical profile across blocks
+        dist.barrier()  # host-side case generation takes seconds and not the same number on every rank: start the first halo exchange together
+        lbm.initialize(flags, rho, u, T)
+        lbm.run(W)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        launches0, over0 = lbm.domain.launch_count(), lbm.domain.overlapped_steps()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(lbm._stream); lbm.run(K); e1.record(lbm._stream)  # on the stream the step is enqueued on; it waits for the halo stream's insert at the end of every step
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        dist.barrier(); torch.cuda.synchronize()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        launches, overlapped = lbm.domain.launch_count() - launches0, lbm.domain.overlapped_steps() - over0
+        # roofline pass for the step kernel of this rank
+        lbm.domain.kernel_timing(True); lbm.run(K); kms, kn = lbm.domain.kernel_timing_read(); lbm.domain.kernel_timing(False)
+        kern = torch.tensor([kms / max(kn, 1)], device="cuda")
+        dist.all_reduce(kern, op=dist.ReduceOp.MAX)
+        out = None
+        if rank == 0:
+            ms, kern_ms = float(ms.item()), float(kern.item())
+            Nglob, Nloc = int(np.prod(Ng)), int(np.prod(shape))
+            mlups = Nglob * K / ms / 1e3
+            achieved = Nloc * alg_bytes(precision, features) / (kern_ms * 1e-3) / 1e9
+            halo_bytes = sum(2 * lbm.halo_bytes(A.HALO_FI, a) for a in range(3) if D[a] > 1)
+            out = dict(mlups=mlups, ms=ms, kern_ms=kern_ms, achieved=achieved, halo_bytes=int(halo_bytes), launches=int(launches), overlapped=int(overlapped), Ng=Ng, D=D)
+        lbm.close()
+        return out
+
     clk = ClockSampler(local)
     if rank == 0:
         clk.start()
-    launches0 = lbm.domain.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(lbm._stream); lbm.run(K); e1.record(lbm._stream)  # on the stream the step and the halo exchange are enqueued on
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    dist.barrier(); torch.cuda.synchronize()
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    launches = lbm.domain.launch_count() - launches0
-    # roofline pass for the step kernel of this rank
-    lbm.domain.kernel_timing(True); lbm.run(K); kms, kn = lbm.domain.kernel_timing_read(); lbm.domain.kernel_timing(False)
-    kern = torch.tensor([kms / max(kn, 1)], device="cuda")
-    dist.all_reduce(kern, op=dist.ReduceOp.MAX)
+    r0 = run_decomp(D0)
     clocks = clk.stop() if rank == 0 else None
+    # the reference README's layouts at 8 GPUs (FX/lbm.cpp:1066-1073: d = x + (y + z*Dy)*Dx), reported beside the default one
+    extra = [d for d in ((8, 1, 1), (2, 2, 2)) if world == 8 and not args.decomp and d != D0 and args.also_default]
+    also = [run_decomp(d) for d in extra]
     if rank == 0:
-        ms, kern_ms = float(ms.item()), float(kern.item())
-        Nglob = int(np.prod(Ng))
+        def halo_of(r):
+            return {"nvlink_bytes_out_per_gpu_per_step": r["halo_bytes"], "exposed_ms_per_step": r["ms"] / K - r["kern_ms"],
+                    "overlapped_with_the_step": r["overlapped"] == K, "note": "y / z exchanges run on a second stream while the interior strips are collided (luw_step_halo_ipc); x faces involve every strip and follow the step"}
+        mlups, ms, kern_ms, achieved, Ng, D = r0["mlups"], r0["ms"], r0["kern_ms"], r0["achieved"], r0["Ng"], r0["D"]
         Nloc = int(np.prod(shape))
-        mlups = Nglob * K / ms / 1e3
-        achieved = Nloc * alg_bytes(precision, features) / (kern_ms * 1e-3) / 1e9
-        halo_bytes = sum(2 * lbm.halo_bytes(A.HALO_FI, a) for a in range(3) if D[a] > 1)
         res = {"metric": "D3Q19 MLUP/s", "value": mlups, "unit": "MLUP/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[precision], "data": "synthetic",
                "config": dict(config_of(args.workload, args.arith, D, Ng), block_per_gpu_incl_halo=list(shape), halo_transport=args.transport),
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                             "kernel": "k_stream_collide_thermal" if features & F_TEMPERATURE else "k_stream_collide_tile", "kernel_ms": kern_ms, "share_of_step": kern_ms / (ms / K), "alg_bytes_per_cell": alg_bytes(precision, features),
                             "cells_per_launch": Nloc, "peak_source": peak_src},
-               "halo": {"nvlink_bytes_out_per_gpu_per_step": int(halo_bytes), "exposed_ms_per_step": ms / K - kern_ms},
+               "halo": halo_of(r0),
                "e2e": {"value": mlups, "unit": "MLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                        "note": "N>1: the multi-rank loop IS the host-API loop (DistributedLBM.run); per-step boundary upload / probe read-back are measured at N=1"},
-               "clocks": clocks, "gpu_launches": int(launches)}
+               "clocks": clocks, "gpu_launches": r0["launches"]}
+        if also:
+            res["also"] = [{"decomposition": list(r["D"]), "lattice": list(r["Ng"]), "value": r["mlups"], "unit": "MLUP/s", "ms_per_step": r["ms"] / K, "kernel_ms": r["kern_ms"],
+                            "halo": halo_of(r)} for r in also]
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(res), flush=True)
         os.dup2(2, 1)
-    lbm.close()
     dist.destroy_process_group()
     return 0
 

@@ -141,6 +141,14 @@ int luw_halo_exchange(luw_domain* const* doms, uint32_t count, int payload, uint
 int luw_halo_ipc_export(luw_domain* dom, uint32_t axis, void* handle_out);
 int luw_halo_ipc_connect(luw_domain* dom, uint32_t axis, const void* handle_up, const void* handle_dn);
 int luw_halo_ipc_exchange(luw_domain* dom, int payload, uint32_t axis, uint64_t t);
+/* One time step of a rank of the one-process-per-GPU driver: stream_collide + the fi (and gi) exchanges of every decomposed axis, x -> y -> z (do_time_step +
+ * communicate_fi, FX/lbm.cpp:1262-1290, 1907-1935) -- with the exchange OVERLAPPED with the interior of the step where the decomposition allows it (y / z splits of a
+ * TMA-tiled domain): the step kernel collides the strips that hold the halo / boundary layers first and counts them as they reach global memory; a second stream waits
+ * for that count and runs extract -> remote store -> flag -> wait -> insert while the interior strips are still being collided; the domain's stream waits for the
+ * insert before anything else. Same results, bit for bit, as luw_stream_collide followed by luw_halo_ipc_exchange per axis (which is what it does when x is
+ * decomposed -- x faces involve every strip --, for thermal domains, or with LUW_HALO_OVERLAP=0). */
+int luw_step_halo_ipc(luw_domain* dom, uint64_t t, float fx, float fy, float fz, float omega_x, float omega_y, float omega_z);
+int luw_overlapped_steps(const luw_domain* dom, uint64_t* steps); /* how many luw_step_halo_ipc calls ran their exchange overlapped with the step (diagnostics, tests) */
 /* LBM::do_time_step for `k` steps t0..t0+k-1 on all domains of a decomposition (FX/lbm.cpp:1262-1290): stream_collide on every domain, then
  * luw_halo_exchange(HALO_FI) for x, y, z. The reference's per-step finish_queue / barriers are gone: everything is stream-ordered. */
 int luw_run_steps_multi(luw_domain* const* doms, uint32_t count, uint64_t t0, uint64_t k, float fx, float fy, float fz, float omega_x, float omega_y, float omega_z);

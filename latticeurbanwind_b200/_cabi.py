@@ -60,6 +60,8 @@ EXPORTS = {  # name -> argtypes; every symbol include/luw_cuda.h declares
     "luw_halo_ipc_export": [C.c_void_p, C.c_uint32, C.c_void_p],
     "luw_halo_ipc_connect": [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p],
     "luw_halo_ipc_exchange": [C.c_void_p, C.c_int, C.c_uint32, C.c_uint64],
+    "luw_step_halo_ipc": [C.c_void_p, C.c_uint64] + [C.c_float] * 6,
+    "luw_overlapped_steps": [C.c_void_p, C.POINTER(C.c_uint64)],
     "luw_run_steps_multi": [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64] + [C.c_float] * 6,
     "luw_vk_inlet_create": [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)],
     "luw_vk_inlet_apply": [C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_float],

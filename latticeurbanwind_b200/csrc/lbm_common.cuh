@@ -41,8 +41,23 @@ struct DomainConst { // the def_* constants of FX/lbm.cpp:612-783 as kernel para
 	// thermal D3Q7 extension (F_TEMPERATURE; FX/lbm.cpp:322-323, 750-752): 7 x N DDFs in the storage type of fi, N floats, def_w_T / def_beta / def_T_avg
 	void* gi; float* T;
 	float w_T, beta, T_avg;
+	// Strip order of the tiled step when the halo exchange overlaps it (luw_step_halo_ipc; 0 everywhere = natural order, nothing signalled): the strips that hold the
+	// halo / boundary layers of the decomposed y and z axes (so_ylo / so_yhi tile rows at the low / high end of y, so_zlo / so_zhi tile planes in z; so_nb strips in
+	// all) are handed out first, and every finished boundary strip is counted in *bdone once its DDFs are in global memory.
+	uint32_t so_ylo, so_yhi, so_zlo, so_zhi, so_nb;
+	uint32_t* bdone;
 };
 struct StepArgs { uint64_t t; float fx, fy, fz, ox, oy, oz; }; // per-step kernel arguments, FX/lbm.cpp:345
+// i-th strip handed out by the counter -> strip id ty + tz*Ty: the so_nb boundary strips first (whole tile planes at the z ends, then the y-end tile rows of the inner planes), then the interior
+__host__ __device__ inline uint32_t strip_of(const DomainConst& c, const uint32_t i, const uint32_t Ty, const uint32_t Tz) {
+	if(c.so_nb==0u) return i;
+	const uint32_t Bz = (c.so_zlo+c.so_zhi)*Ty, per = c.so_ylo+c.so_yhi;
+	uint32_t ty, tz;
+	if(i<Bz) { const uint32_t k = i/Ty; tz = k<c.so_zlo ? k : Tz-c.so_zhi+(k-c.so_zlo); ty = i%Ty; }
+	else if(i<c.so_nb) { const uint32_t j = i-Bz, k = j%per; tz = c.so_zlo+j/per; ty = k<c.so_ylo ? k : Ty-c.so_yhi+(k-c.so_ylo); }
+	else { const uint32_t j = i-c.so_nb, Iy = Ty-per; ty = c.so_ylo+j%Iy; tz = c.so_zlo+j/Iy; }
+	return ty+tz*Ty;
+}
 
 namespace { // internal linkage: this header is compiled into two translation units with different arithmetic flags
 

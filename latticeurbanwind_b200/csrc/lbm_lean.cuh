@@ -141,15 +141,9 @@ template<> struct SmemPair<P_FP16C> : SmemPair<P_FP16S> {
 	static __device__ __forceinline__ R enc(const f2 v) { return PairCodec<P_FP16C>::enc_fast(v); }
 };
 
-// rho/u of TYPE_E cells: into L2 one tile ahead (`fn`: the pair's flags in the NEXT stage; `ns`: the strip id published for it, possibly a stale one -- this is only a hint)
-template<class CFG> __device__ __noinline__ void lean_prefetch_e(const DomainConst& c, const bool last, const uint32_t fn, const uint32_t ns, const uint32_t nstrips, const uint32_t tiles_y,
-	const uint32_t lx, const uint32_t ly, const uint32_t lz, const uint64_t n) {
-	if(!last) {
-		if((fn&0x0003u)==TYPE_E||(fn&0x0300u)==(TYPE_E<<8)) { const uint64_t m = n+(uint64_t)CFG::TX; prefetch_l2(c.rho+m); prefetch_l2(c.u+m); prefetch_l2(c.u+c.N+m); prefetch_l2(c.u+2ull*c.N+m); }
-	} else if(lx==0u) { // the next strip starts at the west face: its x = 0 cells
-		const uint64_t m = (uint64_t)((ns%tiles_y)*(uint32_t)CFG::TY+ly)*c.Px+(uint64_t)((ns/tiles_y)*(uint32_t)CFG::TZ+lz)*((uint64_t)c.Px*c.Ny);
-		if(ns<nstrips&&m<c.N) { prefetch_l2(c.rho+m); prefetch_l2(c.u+m); prefetch_l2(c.u+c.N+m); prefetch_l2(c.u+2ull*c.N+m); }
-	}
+// rho/u of TYPE_E cells: into L2 one tile ahead (`fn`: the pair's flags in the NEXT stage)
+template<class CFG> __device__ __noinline__ void lean_prefetch_e(const DomainConst& c, const uint32_t fn, const uint64_t n) {
+	if((fn&0x0003u)==TYPE_E||(fn&0x0300u)==(TYPE_E<<8)) { const uint64_t m = n+(uint64_t)CFG::TX; prefetch_l2(c.rho+m); prefetch_l2(c.u+m); prefetch_l2(c.u+c.N+m); prefetch_l2(c.u+2ull*c.N+m); }
 }
 
 // The general body of the lean loop: run masks (solid / gas cells, halo columns, columns beyond the lattice), TYPE_E cells, relaxation zones. Out of line: about a
@@ -294,14 +288,14 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 	__syncthreads();
 
 	const uint32_t nstrips = tiles_y*tiles_z;
-	constexpr uint32_t END = 0xFFFFFFFFu;
+	constexpr uint32_t END = 0xFFFFFFFFu, STRIP_BND = 0x80000000u; // tile_strip[s]: strip id | STRIP_BND for a boundary strip of an overlapped halo exchange (DomainConst::so_nb)
 	const uint32_t odd = (uint32_t)(a.t&1ull);
 	const bool wrap_x = (lc.flags&LC_WRAP_X)!=0u;
 	const bool park = (lc.flags&LC_PARK)!=0u;
 
 	if(tid>=(uint32_t)NC) { // ---------------------------------------------------------------- producer warp (protocol of k_stream_collide_tile)
 		const bool leader = (tid&31u)==0u;
-		uint32_t lstrip = 0u, lxt = 0u, issued = 0u;
+		uint32_t lstrip = 0u, lxt = 0u, issued = 0u, lbnd = 0u;
 		bool ended = false;
 		const bool lag = (lc.flags&LC_LAG)!=0u;
 		const auto issue_loads = [&]() {
@@ -315,11 +309,14 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 					if(leader) { tile_strip[s] = END; mbar_arrive(bar_full+s); }
 					return;
 				}
+				lbnd = lstrip<c.so_nb ? STRIP_BND : 0u; // boundary strips come first (strip_of) and are counted in *c.bdone when they are in global memory
+				lstrip = strip_of(c, lstrip, tiles_y, tiles_z);
 			}
 			const int x0 = (int)lxt*TX, y0 = (int)(lstrip%tiles_y)*TY, z0 = (int)(lstrip/tiles_y)*TZ;
 			uint8_t* st = stage0+(size_t)s*CFG::STAGE_BYTES;
+			if(EQ&&lxt==0u) prefetch_west_face<CFG>(c, tid&31u, y0, z0);
 			if(leader) {
-				tile_strip[s] = lstrip;
+				tile_strip[s] = lstrip|lbnd;
 				tile_yz[2*s] = y0; tile_yz[2*s+1] = z0;
 				mbar_expect_tx(bar_full+s, (uint32_t)CFG::LOAD_BYTES);
 				tma_load_3d(st+CFG::FLAG_OFF, &maps.flags, bar_full+s, x0, y0, z0);
@@ -378,6 +375,7 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 					}
 				}
 				tma_commit();
+				if(last_of_strip&&(tile_strip[s]&STRIP_BND)!=0u) { tma_wait_all0(); __threadfence(); atomicAdd(c.bdone, 1u); } // a boundary strip is in global memory: the halo exchange may read it
 				// refill: the stage just stored may be overwritten once TMA has read it. LC_LAG: do not wait for that here -- refill the stage of the PREVIOUS tile instead, whose
 				// stores were committed a tile-time ago (the wait then returns at once; the ring is one tile shallower)
 				if(!ended) { if(lag) { if(q>0u) tma_wait_read1(); } else tma_wait_read0(); }
@@ -406,16 +404,18 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 	int y0 = 0, z0 = 0, py0 = 0, pz0 = 0;
 	uint32_t y = 0u, z = 0u, park_off = 0u;
 	uint32_t sf = 0u; // strip state in one register: the strip touches the y/z boundary (uniform in the CTA) | the cells of this row execute | the row lies in a relaxation zone through its y / z position (both uniform in the warp)
-	constexpr uint32_t SF_BND = 1u, SF_IN = 2u, SF_ZONE = 4u;
+	constexpr uint32_t SF_BND = 1u, SF_IN = 2u, SF_ZONE = 4u, SF_HB = 8u; // SF_HB: a boundary strip of an overlapped halo exchange (carried to the flush of its parked column in bit 30 of py0)
+	constexpr int PY_HB = 1<<30;
 	for(;;) { // ---- tiles: strips as published by the producer, inside a strip x ascending
 		mbar_wait_a(bar0+8u*s, ph);
 		const bool first = xt==0u, last = xt+1u==tiles_x;
 		if(first) { // ---- a new strip
-			const uint32_t strip = tile_strip[s];
-			if(strip==END) break;
+			const uint32_t raw = tile_strip[s];
+			if(raw==END) break;
+			const uint32_t strip = raw&~STRIP_BND;
 			y0 = (int)(strip%tiles_y)*TY; z0 = (int)(strip/tiles_y)*TZ;
 			y = (uint32_t)y0+ly; z = (uint32_t)z0+lz;
-			sf = (y0==0||y0+TY>=(int)c.Ny||z0==0||z0+TZ>=(int)c.Nz) ? SF_BND : 0u;
+			sf = ((y0==0||y0+TY>=(int)c.Ny||z0==0||z0+TZ>=(int)c.Nz) ? SF_BND : 0u)|((raw&STRIP_BND) ? SF_HB : 0u);
 			if(y<c.Ny&&z<c.Nz&&!((c.Dy>1u&&(y==0u||y>=c.Ny-1u))||(c.Dz>1u&&(z==0u||z>=c.Nz-1u)))) sf |= SF_IN;
 			if(has_zones&&zone_row_hit(c, y, z)) sf |= SF_ZONE;
 			park_off = (uint32_t)CFG::BOX_BYTES+((kstrip&1u)*(uint32_t)CFG::ROWS+row)*(uint32_t)CFG::ES; // in stage 0, + box_off(b): this row's parked element of shifted box b
@@ -434,7 +434,8 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 			if(park&&lx==lc.rowend_last) { // the thread that holds the row's last pair in the strip's last tile owns the periodic-x column of its row
 				if(kstrip>0u&&xt==1u) { // the previous strip's column goes to global memory (its first tile has been written back: bar_head)
 					mbar_wait_a(bar0+16u*(uint32_t)S, (kstrip-1u)&1u);
-					flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd);
+					flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0&~PY_HB, pz0, odd);
+					if(py0&PY_HB) { __threadfence(); atomicAdd(c.bdone, 1u); } // one count per row of a boundary strip's parked column
 				}
 				if(first) { // park column 0 of the x-shifted boxes (pre-collision values; nothing else touches them before the strip's last tile)
 #pragma unroll
@@ -454,8 +455,7 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 			if(lx==(last ? lc.rowend_last : (uint32_t)(TX-2))) nxt = !last ? st1+row*(uint32_t)(TX*CFG::ES) : park ? sm0+park_off : wrap_x ? st+row*(uint32_t)(TX*CFG::ES) : bb;
 			const int xw = (int)(xt*(uint32_t)TX+(lx&~63u));
 			const bool zone_warp = zone_yz||xw<=lc.zone_xw||xw>=lc.zone_xe;
-			if(EQ&&(xt+2u>=tiles_x||__any_sync(0xFFFFFFFFu, fl2!=0u))) lean_prefetch_e<CFG>(c, last, last ? 0u : lds_u16(st1+(uint32_t)CFG::FLAG_OFF+2u*tid), tile_strip[s1], nstrips, tiles_y, lx, ly, lz,
-				(uint64_t)x+(uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny));
+			if(EQ&&!last&&(xt+2u>=tiles_x||__any_sync(0xFFFFFFFFu, fl2!=0u))) lean_prefetch_e<CFG>(c, lds_u16(st1+(uint32_t)CFG::FLAG_OFF+2u*tid), (uint64_t)x+(uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny));
 			if(!slow) { // ---------------- fast body: 64 cells that all execute
 				PairIn in;
 				in.zones = false;
@@ -530,11 +530,12 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 		__syncwarp();
 		if((tid&31u)==0u) mbar_arrive_a(bar0+8u*((uint32_t)S+s)); // one arrival per warp
 		s = s1; ph = ph1; st = st1;
-		if(last) { xt = 0u; py0 = y0; pz0 = z0; kstrip++; } else xt++;
+		if(last) { xt = 0u; py0 = y0|((sf&SF_HB) ? PY_HB : 0); pz0 = z0; kstrip++; } else xt++;
 	}
 	if(park&&kstrip>0u&&lx==lc.rowend_last) { // the last strip's periodic-x column
 		mbar_wait_a(bar0+16u*(uint32_t)S, (kstrip-1u)&1u);
-		flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd);
+		flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0&~PY_HB, pz0, odd);
+		if(py0&PY_HB) { __threadfence(); atomicAdd(c.bdone, 1u); }
 	}
 }
 

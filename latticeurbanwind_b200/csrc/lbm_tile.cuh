@@ -315,6 +315,16 @@ template<class CFG, uint32_t FEAT> __device__ __noinline__ void fix_equilibrium(
 	}
 }
 
+// rho / u of a strip's west-face cells (x = 0; TYPE_E in every open-boundary case) into L2: by the producer warp when it issues the loads of the strip's first tile (it is
+// the one that knows the strip; the consumers used to peek at the next stage's strip id for this, which the race checker rightly flags). One sector per lane.
+template<class CFG> __device__ __forceinline__ void prefetch_west_face(const DomainConst& c, const uint32_t lane, const int y0, const int z0) {
+	const uint32_t r = lane>>2, a = lane&3u;
+	if(r<(uint32_t)CFG::ROWS) {
+		const uint32_t y = (uint32_t)y0+r%(uint32_t)CFG::TY, z = (uint32_t)z0+r/(uint32_t)CFG::TY;
+		if(y<c.Ny&&z<c.Nz) { const uint64_t m = (uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny); prefetch_l2(a==0u ? c.rho+m : c.u+(uint64_t)(a-1u)*c.N+m); }
+	}
+}
+
 // ------------------------------------------------------------------ the kernel
 template<class CFG, uint32_t FEAT, bool FAST> __global__ void __maxnreg__(((FAST&&CFG::TWOPASS) ? tile_max_regs(CFG::THREADS/32, CFG::CTAS_PER_SM) : 128)) // the single-pass paths hold all 19 DDF pairs: 128 registers, residency as it comes
 k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_constant__ StepArgs a, const __grid_constant__ TileMaps maps, const uint32_t tiles_x, const uint32_t tiles_y, const uint32_t tiles_z, const uint32_t opts) {
@@ -344,7 +354,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 
 	// tile sequence of this CTA: strips (one (y,z) tile row each) drawn from the counter c.sched[t&1] (zeroed by the previous step's launch, or by the host when the parity repeats); inside a strip x ascending
 	const uint32_t nstrips = tiles_y*tiles_z;
-	constexpr uint32_t END = 0xFFFFFFFFu;
+	constexpr uint32_t END = 0xFFFFFFFFu, STRIP_BND = 0x80000000u; // tile_strip[s]: strip id | STRIP_BND for a boundary strip of an overlapped halo exchange (DomainConst::so_nb)
 	const uint32_t odd = (uint32_t)(a.t&1ull);
 	const bool wrap_x = c.Dx==1u; // the lattice is periodic in x inside this domain
 	const bool park = wrap_x&&tiles_x>=2u; // ... and the wrapped column lives in another tile than the last one
@@ -352,7 +362,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 	if(tid>=(uint32_t)NC) { // ---------------------------------------------------------------- producer warp: TMA loads and stores
 		// The whole warp walks the loops (uniform control flow keeps coordinates and addresses in uniform registers); lane 0 issues.
 		const bool leader = (tid&31u)==0u;
-		uint32_t lstrip = 0u, lxt = 0u, issued = 0u; // tile the next load belongs to; tiles whose loads have been issued
+		uint32_t lstrip = 0u, lxt = 0u, issued = 0u, lbnd = 0u; // tile the next load belongs to; tiles whose loads have been issued
 		bool ended = false;
 		const bool lag = (opts&1u)!=0u; // refill the stage of the PREVIOUS tile (its stores were committed a tile-time ago) instead of waiting for this tile's stores to be read
 		const auto issue_loads = [&]() {
@@ -366,11 +376,14 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 					if(leader) { tile_strip[s] = END; mbar_arrive(bar_full+s); }
 					return;
 				}
+				lbnd = lstrip<c.so_nb ? STRIP_BND : 0u; // boundary strips come first (strip_of) and are counted in *c.bdone when they are in global memory
+				lstrip = strip_of(c, lstrip, tiles_y, tiles_z);
 			}
 			const int x0 = (int)lxt*TX, y0 = (int)(lstrip%tiles_y)*TY, z0 = (int)(lstrip/tiles_y)*TZ;
 			uint8_t* st = stage0+(size_t)s*CFG::STAGE_BYTES;
+			if(EQ&&lxt==0u) prefetch_west_face<CFG>(c, tid&31u, y0, z0);
 			if(leader) {
-				tile_strip[s] = lstrip; // published by the barrier's release / acquire
+				tile_strip[s] = lstrip|lbnd; // published by the barrier's release / acquire
 				tile_yz[2*s] = y0; tile_yz[2*s+1] = z0;
 				mbar_expect_tx(bar_full+s, (uint32_t)CFG::LOAD_BYTES);
 				tma_load_3d(st+CFG::FLAG_OFF, &maps.flags, bar_full+s, x0, y0, z0);
@@ -410,6 +423,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 					if(inner||!box_by_threads<CFG>(c, cy, cz, y0, z0)) tma_store_4d(&maps.fi, st+CFG::box_off(2+2*k), x0, y0+cy, z0+cz, odd ? i+1 : i);
 				}
 				tma_commit();
+				if(last_of_strip&&(tile_strip[s]&STRIP_BND)!=0u) { tma_wait_all0(); __threadfence(); atomicAdd(c.bdone, 1u); } // a boundary strip is in global memory: the halo exchange may read it
 				TRACE(1, q);
 				if(!ended) { if(lag) { if(q>0u) tma_wait_read1(); } else tma_wait_read0(); } // the stage may be refilled once TMA has read it
 				TRACE(2, q);
@@ -435,6 +449,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 	// walk: strips as published by the producer; inside a strip xt = 0..tiles_x-1; ring slot s and its phase advance with every tile
 	uint32_t xt = 0u, s = 0u, ph = 0u, kstrip = 0u;
 	int y0 = 0, z0 = 0, py0 = 0, pz0 = 0;
+	uint32_t hb = 0u, phb = 0u; // this / the previous strip is a boundary strip of an overlapped halo exchange
 	bool zone_yz = false; // this thread's row lies in a relaxation zone through its y / z position (decided once per strip)
 	const int zone_xe = Nb>=0 ? (int)c.Nxg-1-Nb-63-c.Ox : 0x7FFFFFFF; // a warp (64 x-consecutive cells from local x = xw) reaches the east shell iff xw >= zone_xe, the west shell iff xw + Ox <= Nb
 	for(uint32_t q=0u; ; q++) {
@@ -445,8 +460,10 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 		const bool first = xt==0u, last = xt+1u==tiles_x; // the next tile of the strip holds the +x slots of this tile's last column
 		if(first) { // a new strip: which one?
 			mbar_wait(bar_full+s, ph);
-			const uint32_t strip = tile_strip[s];
-			if(strip==END) break;
+			const uint32_t raw = tile_strip[s];
+			if(raw==END) break;
+			const uint32_t strip = raw&~STRIP_BND;
+			hb = raw&STRIP_BND;
 			y0 = (int)(strip%tiles_y)*TY; z0 = (int)(strip/tiles_y)*TZ;
 			if(has_zones) { const int yg = y0+(int)ly+c.Oy, zg = z0+(int)lz+c.Oz; zone_yz = yg<=Nb||yg>=(int)c.Nyg-1-Nb||zg>=(int)c.Nzg-1-Nb||zg>=(int)c.Nzg-2-Ns; }
 		}
@@ -458,7 +475,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 		if(park&&kstrip>0u&&xt==1u) { // write the previous strip's periodic-x column
 			mbar_wait(bar_head, (kstrip-1u)&1u);
 			__syncwarp();
-			if(lx==rowend_last) flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd); // the thread that wrote the parked elements last
+			if(lx==rowend_last) { flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd); if(phb!=0u) { __threadfence(); atomicAdd(c.bdone, 1u); } } // the thread that wrote the parked elements last; one count per row of a boundary strip
 		}
 
 		if(tid==0u) TRACE(4, q);
@@ -473,13 +490,9 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 			run1 = run1&&in_yz&&x+1u<c.Nx&&!(c.Dx>1u&&(x+1u>=c.Nx-1u));
 		}
 		if(EQ) { // rho/u of TYPE_E cells: into L2 one tile ahead
-			if(!last) {
+			if(!last) { // (the next strip's west face: prefetch_west_face, by the producer)
 				const uint32_t fn = ((const uint16_t*)(st1+CFG::FLAG_OFF))[tid];
 				if((fn&0x0003u)==TYPE_E||(fn&0x0300u)==(TYPE_E<<8)) { const uint64_t m = n+(uint64_t)TX; prefetch_l2(c.rho+m); prefetch_l2(c.u+m); prefetch_l2(c.u+c.N+m); prefetch_l2(c.u+2ull*c.N+m); }
-			} else if(lx==0u) { // the next strip starts at the west face: its x = 0 cells (the id may still be a stale one: this is only a hint)
-				const uint32_t ns = tile_strip[s1];
-				const uint64_t m = (uint64_t)((ns%tiles_y)*(uint32_t)TY+ly)*rowN+(uint64_t)((ns/tiles_y)*(uint32_t)TZ+lz)*planeN;
-				if(ns<nstrips&&m<c.N) { prefetch_l2(c.rho+m); prefetch_l2(c.u+m); prefetch_l2(c.u+c.N+m); prefetch_l2(c.u+2ull*c.N+m); }
 			}
 		}
 		R* const box = (R*)st+tid; // the pair's word in box b is at byte offset box_off(b)
@@ -657,12 +670,12 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 		bar_arrive_id(2u+s, (uint32_t)CFG::THREADS);
 #endif
 		s = s1; ph = ph1;
-		if(last) { xt = 0u; py0 = y0; pz0 = z0; kstrip++; } else xt++;
+		if(last) { xt = 0u; py0 = y0; pz0 = z0; phb = hb; kstrip++; } else xt++;
 	}
 	TRACE_CLK(2);
 	if(park&&kstrip>0u) { // the last strip's periodic-x column
 		mbar_wait(bar_head, (kstrip-1u)&1u);
-		if(lx==rowend_last) flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd);
+		if(lx==rowend_last) { flush_wrap<CFG>(c, stage0, (kstrip-1u)&1u, row, py0, pz0, odd); if(phb!=0u) { __threadfence(); atomicAdd(c.bdone, 1u); } }
 	}
 }
 

@@ -59,6 +59,11 @@ struct luw_domain {
 		uint32_t seq = 0u; // exchanges issued on this axis
 		bool same = false; // up and dn are one mapping
 	} ipc[3];
+	// overlapped halo exchange (luw_step_halo_ipc): second stream, "boundary strips are in global memory" counter of the step kernel and its running target
+	cudaStream_t halo_stream = nullptr;
+	cudaEvent_t halo_done = nullptr;
+	uint32_t bdone_target = 0u;
+	uint64_t overlapped_steps = 0ull;
 	bool ktiming = false; // bracket every main step kernel with events (luw_kernel_timing)
 	std::vector<cudaEvent_t> kev; // event pairs
 	size_t kev_used = 0u;
@@ -165,8 +170,10 @@ void setup_tiles(luw_domain* d) {
 	const char* off = getenv("LUW_NO_TILE");
 	if(off&&off[0]=='1') return;
 	const char* var = getenv("LUW_TILE_VARIANT");
-	// default: two-pass kernel; 5 CTAs/SM where the collision fits 72 registers (no LES), else 128x4 tiles with 8 consumer warps per producer (measured, profiles/)
-	const int want = (var&&var[0]) ? atoi(var) : d->c.precision==luw::P_FP16C ? 3 : (d->c.precision==luw::P_FP16S&&(d->c.features&luw::F_SUBGRID)) ? 4 : 0; // FP16C: the software codec makes decoding twice dearer than the registers (single pass)
+	// default (measured, profiles/r2_variant_sweeps.txt): FP16S -> the lean-loop two-pass kernel, 128x4 tiles with 8 consumer warps per producer for the LES step (V5), 128x2 tiles and
+	// 5 CTAs/SM without LES (V6); FP16C -> single pass (V3: the software codec makes decoding twice dearer than the registers); FP32 -> single pass (V0). STRICT arithmetic runs
+	// k_stream_collide_tile on the same tile shapes.
+	const int want = (var&&var[0]) ? atoi(var) : d->c.precision==luw::P_FP16C ? 3 : d->c.precision==luw::P_FP16S ? ((d->c.features&luw::F_SUBGRID) ? 5 : 6) : 0;
 	const luw::DomainConst& c = d->c;
 	// odd Nx: the row's last pair holds one cell (rows are padded to Px, a multiple of 16 elements); lbm_tile.cuh `odd_end`
 	encode_tiled_fn enc = get_encode_tiled();
@@ -196,7 +203,7 @@ void setup_tiles(luw_domain* d) {
 		CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)!=CUDA_SUCCESS) return;
 	d->tiled = true;
 }
-cudaError_t enqueue_step(luw_domain* d, const luw::StepArgs& a) {
+cudaError_t enqueue_step(luw_domain* d, const luw::StepArgs& a, const luw::DomainConst* order = nullptr) { // order: d->c with the so_* strip order of an overlapped halo exchange
 	cudaError_t e = cudaSuccess;
 	if(d->tiled) { // strip counters of the persistent kernel: step parity p uses sched[p] and zeroes sched[p^1]; a memset is only needed when a parity repeats
 		const int par = (int)(a.t&1ull);
@@ -207,7 +214,7 @@ cudaError_t enqueue_step(luw_domain* d, const luw::StepArgs& a) {
 		if(d->kev_used+2u>d->kev.size()) for(int k=0; k<2; k++) { cudaEvent_t ev; e = cudaEventCreate(&ev); if(e!=cudaSuccess) return e; d->kev.push_back(ev); }
 		e = cudaEventRecord(d->kev[d->kev_used], d->stream); if(e!=cudaSuccess) return e;
 	}
-	if(d->tiled) e = d->ks->stream_collide_tile(d->c, a, d->maps, d->tile_variant, d->sm_count, d->stream);
+	if(d->tiled) e = d->ks->stream_collide_tile(order ? *order : d->c, a, d->maps, d->tile_variant, d->sm_count, d->stream);
 	else if(d->c.features&luw::F_TEMPERATURE) e = d->ks->stream_collide_thermal(d->c, a, d->stream);
 	else e = d->ks->stream_collide(d->c, a, d->stream);
 	d->launches++;
@@ -369,7 +376,7 @@ int luw_domain_create(const luw_domain_params* p, luw_domain** out) {
 	if(rc==LUW_OK) rc = dev_alloc(d, &c.rho, N);
 	if(rc==LUW_OK) rc = dev_alloc(d, &c.u, 3ull*N);
 	if(rc==LUW_OK) rc = dev_alloc(d, &c.flags, N);
-	if(rc==LUW_OK) rc = dev_alloc(d, &c.sched, 2u);
+	if(rc==LUW_OK) rc = dev_alloc(d, &c.sched, 4u); // [0], [1]: strip counters of the two step parities; [2]: boundary-strip counter of the overlapped halo exchange (c.bdone)
 	const bool thermal = (p->features&LUW_TEMPERATURE)!=0u;
 	if(rc==LUW_OK&&thermal) rc = dev_alloc(d, (uint8_t**)&c.gi, 7ull*N*d->ddf_size); // gi = Memory<fpxx>(N, 7), T = Memory<float>(N, 1, .., 1.0f): FX/lbm.cpp:322-323
 	if(rc==LUW_OK&&thermal) rc = dev_alloc(d, &c.T, N);
@@ -377,7 +384,7 @@ int luw_domain_create(const luw_domain_params* p, luw_domain** out) {
 		e = cudaMemsetAsync(c.fi, 0, 19ull*N*d->ddf_size, d->stream);
 		if(e==cudaSuccess) e = cudaMemsetAsync(c.u, 0, 3ull*N*4ull, d->stream);
 		if(e==cudaSuccess) e = cudaMemsetAsync(c.flags, 0, N, d->stream);
-		if(e==cudaSuccess) e = cudaMemsetAsync(c.sched, 0, 8u, d->stream);
+		if(e==cudaSuccess) e = cudaMemsetAsync(c.sched, 0, 16u, d->stream);
 		if(e==cudaSuccess) { k_fill_f32<<<1184, 256, 0, d->stream>>>(c.rho, N, 1.0f); e = cudaGetLastError(); d->launches++; }
 		if(e==cudaSuccess&&thermal) e = cudaMemsetAsync(c.gi, 0, 7ull*N*d->ddf_size, d->stream);
 		if(e==cudaSuccess&&thermal) { k_fill_f32<<<1184, 256, 0, d->stream>>>(c.T, N, 1.0f); e = cudaGetLastError(); d->launches++; }
@@ -397,6 +404,7 @@ int luw_domain_create(const luw_domain_params* p, luw_domain** out) {
 		if(rc==LUW_OK) { e = cudaMemcpyAsync(d->sigma, t.data(), t.size()*4u, cudaMemcpyHostToDevice, d->stream); if(e==cudaSuccess) e = cudaStreamSynchronize(d->stream); if(e!=cudaSuccess) rc = cuda_fail(e, "upload sponge table"); }
 	}
 	c.wbuf = d->wbuf; c.sigma = d->sigma;
+	c.bdone = c.sched ? c.sched+2 : nullptr;
 	if(rc==LUW_OK) {
 		cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, p->device);
 		setup_tiles(d);
@@ -411,6 +419,8 @@ int luw_domain_destroy(luw_domain* d) {
 	DeviceGuard guard(d->p.device);
 	if(d->own_stream) cudaStreamSynchronize(d->own_stream);
 	cudaFree(d->c.fi); cudaFree(d->c.rho); cudaFree(d->c.u); cudaFree(d->c.flags); cudaFree(d->c.sched); cudaFree(d->wbuf); cudaFree(d->sigma); cudaFree(d->c.gi); cudaFree(d->c.T);
+	if(d->halo_stream) { cudaStreamSynchronize(d->halo_stream); cudaStreamDestroy(d->halo_stream); }
+	if(d->halo_done) cudaEventDestroy(d->halo_done);
 	if(d->ev0) cudaEventDestroy(d->ev0);
 	if(d->ev1) cudaEventDestroy(d->ev1);
 	for(cudaEvent_t ev : d->kev) cudaEventDestroy(ev);
@@ -679,6 +689,75 @@ int luw_halo_ipc_exchange(luw_domain* d, int payload, uint32_t axis, uint64_t t)
 	char* const recv_m = h->block+256ull+(2ull*par+1ull)*bb;
 	CU(halo_kernel(d, payload, axis, t, true, true, recv_p, recv_m));
 	d->launches += 4ull;
+	return LUW_OK;
+}
+// the step kernel counts finished boundary strips in *ctr (DomainConst::bdone); the halo stream starts its exchange when all of this step's are in. Bounded like k_halo_wait.
+__global__ void k_boundary_wait(const uint32_t* ctr, const uint32_t target) {
+	const long long t0 = clock64();
+	uint32_t v;
+	for(;;) {
+		asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+		if((int32_t)(v-target)>=0) break;
+		__nanosleep(100u);
+		if(clock64()-t0>120000000000ll) __trap();
+	}
+}
+// Strip order of an overlapped step (DomainConst::so_*): the tile rows / planes that hold layers 0, 1, N-2, N-1 of the decomposed y / z axes. false: no interior left to overlap with.
+static bool halo_strip_order(const luw_domain* d, luw::DomainConst* o, uint32_t* per_strip) {
+	luw::TileShape sh;
+	if(!d->tiled||!d->ks->tile_shape(d->c.precision, d->c.features, d->tile_variant, &sh)) return false;
+	const luw::DomainConst& c = d->c;
+	const uint32_t TY = (uint32_t)sh.ty, TZ = (uint32_t)sh.tz, Ty = (c.Ny+TY-1u)/TY, Tz = (c.Nz+TZ-1u)/TZ, Tx = (c.Nx+(uint32_t)sh.tx-1u)/(uint32_t)sh.tx;
+	*o = c;
+	o->so_ylo = c.Dy>1u ? 1u/TY+1u : 0u; o->so_yhi = c.Dy>1u ? Ty-(c.Ny-2u)/TY : 0u;
+	o->so_zlo = c.Dz>1u ? 1u/TZ+1u : 0u; o->so_zhi = c.Dz>1u ? Tz-(c.Nz-2u)/TZ : 0u;
+	if(o->so_ylo+o->so_yhi>=Ty||o->so_zlo+o->so_zhi>=Tz) return false;
+	o->so_nb = (o->so_zlo+o->so_zhi)*Ty+(o->so_ylo+o->so_yhi)*(Tz-o->so_zlo-o->so_zhi);
+	if(o->so_nb==0u) return false;
+	const bool park = c.Dx==1u&&Tx>=2u; // the periodic-x column of a strip is flushed by one thread per tile row, a strip later: counted too (lbm_tile.cuh)
+	*per_strip = 1u+(park ? TY*TZ : 0u);
+	return true;
+}
+int luw_step_halo_ipc(luw_domain* d, uint64_t t, float fx, float fy, float fz, float ox, float oy, float oz) {
+	if(!d) return fail(LUW_ERR_INVALID, "null domain");
+	DeviceGuard guard(d->p.device);
+	const luw::StepArgs a = { t, fx, fy, fz, ox, oy, oz };
+	const bool thermal = (d->c.features&luw::F_TEMPERATURE)!=0u;
+	luw::DomainConst order;
+	uint32_t per_strip = 0u;
+	static const bool allowed = []{ const char* e = getenv("LUW_HALO_OVERLAP"); return !(e&&e[0]=='0'); }();
+	const bool overlap = allowed&&!thermal&&d->c.Dx==1u&&(d->c.Dy>1u||d->c.Dz>1u)&&halo_strip_order(d, &order, &per_strip);
+	if(!overlap) { // x faces involve every strip, thermal domains run the one-cell-per-thread kernel: exchange behind the step, on the domain's stream
+		CU(enqueue_step(d, a));
+		for(uint32_t axis=0u; axis<3u; axis++) if((axis==0u ? d->c.Dx : axis==1u ? d->c.Dy : d->c.Dz)>1u) { if(const int rc = luw_halo_ipc_exchange(d, LUW_HALO_FI, axis, t)) return rc; }
+		if(thermal) for(uint32_t axis=0u; axis<3u; axis++) if((axis==0u ? d->c.Dx : axis==1u ? d->c.Dy : d->c.Dz)>1u) { if(const int rc = luw_halo_ipc_exchange(d, LUW_HALO_GI, axis, t)) return rc; }
+		return LUW_OK;
+	}
+	if(!d->halo_stream) {
+		int lo = 0, hi = 0;
+		CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		CU(cudaStreamCreateWithPriority(&d->halo_stream, cudaStreamNonBlocking, hi)); // its small kernels go ahead of the step kernel's remaining CTAs... which are resident anyway: they only need free thread slots
+		CU(cudaEventCreateWithFlags(&d->halo_done, cudaEventDisableTiming));
+	}
+	CU(enqueue_step(d, a, &order)); // boundary strips first, counted in *c.bdone
+	d->bdone_target += order.so_nb*per_strip;
+	k_boundary_wait<<<1, 1, 0, d->halo_stream>>>(d->c.bdone, d->bdone_target);
+	CU(cudaGetLastError());
+	d->launches++;
+	cudaStream_t const main_stream = d->stream;
+	d->stream = d->halo_stream; // the exchange kernels of luw_halo_ipc_exchange go to the halo stream: they run while the interior strips are still being collided
+	int rc = LUW_OK;
+	for(uint32_t axis=1u; axis<3u&&rc==LUW_OK; axis++) if((axis==1u ? d->c.Dy : d->c.Dz)>1u) rc = luw_halo_ipc_exchange(d, LUW_HALO_FI, axis, t);
+	d->stream = main_stream;
+	if(rc!=LUW_OK) return rc;
+	CU(cudaEventRecord(d->halo_done, d->halo_stream));
+	CU(cudaStreamWaitEvent(d->stream, d->halo_done, 0)); // whatever follows on the domain's stream (the next step, copies, statistics) sees the exchanged lattice
+	d->overlapped_steps++;
+	return LUW_OK;
+}
+int luw_overlapped_steps(const luw_domain* d, uint64_t* steps) {
+	if(!d||!steps) return fail(LUW_ERR_INVALID, "null argument");
+	*steps = d->overlapped_steps;
 	return LUW_OK;
 }
 int luw_run_steps_multi(luw_domain* const* doms, uint32_t count, uint64_t t0, uint64_t k, float fx, float fy, float fz, float ox, float oy, float oz) {

@@ -165,6 +165,15 @@ class Domain:
     def halo_ipc_exchange(self, payload, axis):
         A.check(A.lib().luw_halo_ipc_exchange(self._h, payload, axis, self.t))
 
+    def step_halo_ipc(self):
+        """stream_collide + the fi (gi) exchanges of all decomposed axes, overlapped with the interior of the step where the decomposition allows it (luw_step_halo_ipc)."""
+        A.check(A.lib().luw_step_halo_ipc(self._h, self.t, *map(float, self.f), *map(float, self.omega)))
+
+    def overlapped_steps(self):
+        n = C.c_uint64()
+        A.check(A.lib().luw_overlapped_steps(self._h, C.byref(n)))
+        return n.value
+
     # ---- measurement helpers
     def timer_begin(self):
         A.check(A.lib().luw_timer_begin(self._h))

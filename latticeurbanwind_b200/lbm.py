@@ -316,10 +316,13 @@ class DistributedLBM(_Base):
 
     def do_time_step(self):
         dom = self.domain
-        dom.enqueue_stream_collide()
-        self.communicate(A.HALO_FI, self._extract, self._insert)
-        if self.thermal:
-            self.communicate(A.HALO_GI, self._extract, self._insert)
+        if not self.routing_only and self.transport == "ipc":  # one call: step + exchanges, the y / z exchanges overlapped with the interior strips (luw_step_halo_ipc)
+            dom.step_halo_ipc()
+        else:
+            dom.enqueue_stream_collide()
+            self.communicate(A.HALO_FI, self._extract, self._insert)
+            if self.thermal:
+                self.communicate(A.HALO_GI, self._extract, self._insert)
         dom.increment_time_step()
         self.t += 1
 

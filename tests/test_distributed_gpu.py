@@ -1,4 +1,5 @@
-"""GPU, world_size 2 (needs two devices; skipped elsewhere): the one-process-per-GPU driver (DistributedLBM: step kernel, halo extract, payload over
+"""GPU, world_size 2 (two devices; on a one-GPU box both ranks share device 0 and rendezvous over gloo -- CUDA IPC works between processes on one device, NCCL does
+not, so only the IPC transport runs there): the one-process-per-GPU driver (DistributedLBM: step kernel, halo extract, payload over
 NVLink -- remote stores into the neighbour's IPC-mapped receive block, or NCCL send/recv -- halo insert, all ordered on one stream) reproduces the
 single-domain run of the same kernels bit for bit."""
 import os
@@ -26,17 +27,22 @@ def _worker(rank, world, port, D, precision, arith, transport, out):
     import torch.distributed as dist
     from latticeurbanwind_b200.lbm import DistributedLBM
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    shared = torch.cuda.device_count() < world  # both ranks on one GPU: the contexts time-slice; every device-side wait is bounded
+    dev = 0 if shared else rank
+    torch.cuda.set_device(dev)
+    if shared:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    else:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", dev))
     try:
         flags, rho, u = cases.urban(*SHAPE, seed=21, edge=4, pitch=8)
-        lbm = DistributedLBM(SHAPE, D, device=rank, nu=1e-6, precision=precision, features=H.FEATURE_SETS["luw"], arith=arith, f=H.FORCE, omega=H.OMEGA, transport=transport, **ZONES)
+        lbm = DistributedLBM(SHAPE, D, device=dev, nu=1e-6, precision=precision, features=H.FEATURE_SETS["luw"], arith=arith, f=H.FORCE, omega=H.OMEGA, transport=transport, **ZONES)
         shape, Ov, fl, rh, uu = H.cut_block(SHAPE, D, lbm.d, flags, rho, u)
         assert shape == lbm.Nl and Ov == lbm.O
         lbm.initialize(fl, rh, uu)
         lbm.run(STEPS)
         lbm.domain.download_all()
-        np.savez(os.path.join(out, f"rank{rank}.npz"), rho=lbm.domain.rho, u=lbm.domain.u, gidx=lbm.gidx, Nl=np.array(lbm.Nl))
+        np.savez(os.path.join(out, f"rank{rank}.npz"), rho=lbm.domain.rho, u=lbm.domain.u, gidx=lbm.gidx, Nl=np.array(lbm.Nl), overlapped=np.array(lbm.domain.overlapped_steps()))
         lbm.close()
     finally:
         dist.destroy_process_group()
@@ -47,8 +53,10 @@ def _worker(rank, world, port, D, precision, arith, transport, out):
 def test_two_ranks_nccl_reproduce_single_domain(tmp_path, D, arith, transport):
     import torch
     import torch.multiprocessing as mp
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
+    if torch.cuda.device_count() < 1:
+        pytest.skip("needs a GPU")
+    if torch.cuda.device_count() < 2 and transport == "nccl":
+        pytest.skip("NCCL needs one device per rank")
     from latticeurbanwind_b200.lbm import LBM
     precision = 1
     mp.spawn(_worker, args=(2, _free_port(), D, precision, arith, transport, str(tmp_path)), nprocs=2, join=True)
@@ -60,6 +68,8 @@ def test_two_ranks_nccl_reproduce_single_domain(tmp_path, D, arith, transport):
     N = int(np.prod(SHAPE))
     for r in range(2):
         z = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
+        if transport == "ipc":  # y / z splits: every step's exchange ran on the halo stream, overlapped with the interior strips (luw_step_halo_ipc); x faces involve every strip
+            assert int(z["overlapped"]) == (STEPS if D[0] == 1 else 0), int(z["overlapped"])
         Nl = tuple(int(v) for v in z["Nl"])
         keep = np.ones(Nl[::-1], bool)
         for a in range(3):
