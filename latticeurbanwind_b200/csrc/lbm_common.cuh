@@ -46,6 +46,9 @@ struct DomainConst { // the def_* constants of FX/lbm.cpp:612-783 as kernel para
 	// all) are handed out first, and every finished boundary strip is counted in *bdone once its DDFs are in global memory.
 	uint32_t so_ylo, so_yhi, so_zlo, so_zhi, so_nb;
 	uint32_t* bdone;
+	// Thermal step in two kernels (luw_cabi.cu enqueue_step): the TMA-tiled momentum kernel leaves the velocity BEFORE the force half-step here (3 x N floats, the
+	// one input of the g collision that is never stored otherwise, FX/kernel.cpp:1664), k_thermal_g consumes it. nullptr on domains without TEMPERATURE.
+	float* upre;
 };
 struct StepArgs { uint64_t t; float fx, fy, fz, ox, oy, oz; }; // per-step kernel arguments, FX/lbm.cpp:345
 // i-th strip handed out by the counter -> strip id ty + tz*Ty: the so_nb boundary strips first (whole tile planes at the z ends, then the y-end tile rows of the inner planes), then the interior

@@ -299,6 +299,48 @@ template<int P, uint32_t FEAT> __global__ void __launch_bounds__(128) k_stream_c
 	collide_cell_thermal<P, FEAT>(c, a, j, x, y, z, fl, odd, f);
 	store_f<P>((T*)c.fi, c.N, j, odd, f);
 }
+// The TEMPERATURE block alone (FX/kernel.cpp:1639-1684), second kernel of the two-kernel thermal step: the TMA-tiled momentum kernel has left every executing
+// non-TYPE_E cell's velocity before the force half-step in c.upre (TYPE_E cells keep theirs in the boundary field c.u); the arithmetic is collide_cell_thermal's, line by
+// line. Only legal while the buoyancy term vanishes (f = 0 or beta = 0, as in every LUW mode): with buoyancy the momentum step depends on this step's T, and
+// enqueue_step runs the fused one-cell-per-thread kernel instead. FEAT: UPDATE_FIELDS (T is stored) and EQUILIBRIUM_BOUNDARIES matter.
+template<int P, uint32_t FEAT> __global__ void __launch_bounds__(128) k_thermal_g(const __grid_constant__ DomainConst c, const __grid_constant__ StepArgs a) {
+	typedef typename Ddf<P>::T S;
+	constexpr bool UF = (FEAT&F_UPDATE_FIELDS)!=0u, EQ = (FEAT&F_EQUILIBRIUM)!=0u;
+	const uint32_t x = blockIdx.x*blockDim.x+threadIdx.x, y = blockIdx.y, z = blockIdx.z;
+	if(x>=c.Nx||is_halo(c, x, y, z)) return;
+	uint64_t j[Q];
+	neighbors(c, x, y, z, j); // the first seven entries are neighbors_temperature()'s j7
+	const uint64_t n = j[0];
+	const uint32_t fl = c.flags[n], bo = fl&TYPE_BO;
+	if(bo==TYPE_S||(fl&TYPE_SU)==TYPE_G) return;
+	const uint32_t odd = (uint32_t)(a.t&1ull);
+	const bool is_e = EQ&&bo==TYPE_E, is_t = (fl&TYPE_T)!=0u;
+	const float* const us = is_e ? c.u : c.upre;
+	const float uxn = us[n], uyn = us[c.N+n], uzn = us[2ull*c.N+n];
+	float g[7];
+	load_g<P>((const S*)c.gi, c.N, j, odd, g);
+	float Tn = temperature_of(c, n, is_t, g);
+	if((c.features&F_SPONGE)&&!is_t&&bo!=TYPE_E&&c.has_t) {
+		const int dt = (int)(c.Nzg-2u)-((int)z+c.Oz);
+		if(dt>=0&&dt<(int)c.sponge_N) {
+			const float sg = __ldg(c.sigma+dt);
+			const uint64_t nref = (uint64_t)x+((uint64_t)y+(uint64_t)c.tz*c.Ny)*c.Px;
+			Tn = fmaf(sg, c.T[nref]-Tn, Tn);
+		}
+	}
+	float geq[7];
+	g_eq(Tn, uxn, uyn, uzn, geq);
+	if(is_t) {
+#pragma unroll
+		for(int i=0; i<7; i++) g[i] = geq[i];
+	} else {
+		if(UF) c.T[n] = Tn;
+		const float omw_T = 1.0f-c.w_T;
+#pragma unroll
+		for(int i=0; i<7; i++) g[i] = fmaf(omw_T, g[i], c.w_T*geq[i]);
+	}
+	store_g<P>((S*)c.gi, c.N, j, odd, g);
+}
 // initialize with the TEMPERATURE block (FX/kernel.cpp:1442-1450): g starts at g_eq(T, u)
 template<int P> __global__ void __launch_bounds__(128) k_initialize_thermal(const __grid_constant__ DomainConst c) {
 	typedef typename Ddf<P>::T T;

@@ -155,7 +155,7 @@ template<class CFG, uint32_t FEAT> __device__ __noinline__ void lean_general_pai
 	typedef SmemPair<P> SP;
 	typedef typename SP::R R;
 	typedef PairCodec<P> PC;
-	constexpr bool UF = (FEAT&F_UPDATE_FIELDS)!=0u, EQ = (FEAT&F_EQUILIBRIUM)!=0u, SG = (FEAT&F_SUBGRID)!=0u;
+	constexpr bool UF = (FEAT&F_UPDATE_FIELDS)!=0u, EQ = (FEAT&F_EQUILIBRIUM)!=0u, SG = (FEAT&F_SUBGRID)!=0u, TH = (FEAT&F_TEMPERATURE)!=0u;
 	const float scale = (P==P_FP16S) ? 32768.0f : 1.0f, inv = (P==P_FP16S) ? 3.0517578E-5f : 1.0f;
 	const uint32_t fl0 = fl2&0xFFu, fl1 = fl2>>8;
 	bool run0 = !((fl0&TYPE_BO)==TYPE_S||(fl0&TYPE_SU)==TYPE_G), run1 = !((fl1&TYPE_BO)==TYPE_S||(fl1&TYPE_SU)==TYPE_G);
@@ -186,6 +186,7 @@ template<class CFG, uint32_t FEAT> __device__ __noinline__ void lean_general_pai
 	FastK K;
 	PairOut out;
 	fast_prepare<FEAT>(c, a, in, M, scale, inv, K, out);
+	if(TH) store_upre(c, n, run0&&!e0, run1&&!e1, out);
 	if(UF) { // rho / u of the non-TYPE_E cells (UPDATE_FIELDS, FX/kernel.cpp:1709-1715)
 		const bool w0 = run0&&!e0, w1 = run1&&!e1;
 		if(w0&&w1) {
@@ -267,7 +268,7 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 	typedef PairCodec<P> PC;
 	typedef typename PC::R R;
 	typedef typename PC::E E;
-	constexpr bool UF = (FEAT&F_UPDATE_FIELDS)!=0u, EQ = (FEAT&F_EQUILIBRIUM)!=0u, VF = (FEAT&F_VOLUME_FORCE)!=0u, SG = (FEAT&F_SUBGRID)!=0u;
+	constexpr bool UF = (FEAT&F_UPDATE_FIELDS)!=0u, EQ = (FEAT&F_EQUILIBRIUM)!=0u, VF = (FEAT&F_VOLUME_FORCE)!=0u, SG = (FEAT&F_SUBGRID)!=0u, TH = (FEAT&F_TEMPERATURE)!=0u;
 	static_assert(TX/2>=32, "a consumer warp must lie inside one lattice row");
 
 	extern __shared__ uint8_t smem_raw[];
@@ -482,6 +483,7 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 				FastK K;
 				PairOut out;
 				fast_prepare<FEAT>(c, a, in, M, scale, inv, K, out);
+				if(TH) store_upre(c, (uint64_t)x+(uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny), (e2&0x00FFu)==0u, (e2&0xFF00u)==0u, out);
 				if(UF) { // rho / u of the non-TYPE_E cells (UPDATE_FIELDS, FX/kernel.cpp:1709-1715)
 					const uint64_t n = (uint64_t)x+(uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny);
 					if(e2==0u) {

@@ -166,6 +166,8 @@ template<> struct PairCodec<P_FP32> { // two floats
 	static __device__ __forceinline__ void shift_out_both(uint8_t* own, uint8_t* next, const R n) { ((float*)own)[1] = n.x; *(float*)next = n.y; }
 	// odd Nx, the row's last pair: cell 0 IS the last column (its +x element is `next`), cell 1 does not exist
 	static __device__ __forceinline__ R shift_in_odd(const uint8_t* next) { return make_float2(*(const float*)next, 0.0f); }
+	// ... by element loads: the FIRST element of the pair's word belongs to the pair on the left, which may be writing it (a whole-word load is a data race, if a harmless one)
+	static __device__ __forceinline__ R shift_in_e(const uint8_t* own, const uint8_t* next) { return make_float2(((const float*)own)[1], *(const float*)next); }
 	static __device__ __forceinline__ void shift_out_odd(uint8_t* next, const R n) { *(float*)next = n.x; }
 	typedef uint32_t M; // lane mask of a pair: bit 0 / bit 1 = cell 0 / 1 takes the new value
 	static __device__ __forceinline__ M mask(const bool k0, const bool k1) { return (k0 ? 1u : 0u)|(k1 ? 2u : 0u); }
@@ -184,6 +186,7 @@ template<> struct PairCodec<P_FP16S> { // half2 holding 2^15 f; the 2^15 is fold
 	static __device__ __forceinline__ void shift_out(uint8_t* own, uint8_t* next, const R n, const bool k0, const bool k1) { if(k0) ((uint16_t*)own)[1] = (uint16_t)(n&0xFFFFu); if(k1) *(uint16_t*)next = (uint16_t)(n>>16); }
 	static __device__ __forceinline__ void shift_out_both(uint8_t* own, uint8_t* next, const R n) { ((uint16_t*)own)[1] = (uint16_t)(n&0xFFFFu); *(uint16_t*)next = (uint16_t)(n>>16); }
 	static __device__ __forceinline__ R shift_in_odd(const uint8_t* next) { return (uint32_t)*(const uint16_t*)next; }
+	static __device__ __forceinline__ R shift_in_e(const uint8_t* own, const uint8_t* next) { return (uint32_t)((const uint16_t*)own)[1]|((uint32_t)*(const uint16_t*)next<<16); }
 	static __device__ __forceinline__ void shift_out_odd(uint8_t* next, const R n) { *(uint16_t*)next = (uint16_t)(n&0xFFFFu); }
 	typedef uint32_t M; // bit mask of a pair: the halves that take the new value
 	static __device__ __forceinline__ M mask(const bool k0, const bool k1) { return (k0 ? 0x0000FFFFu : 0u)|(k1 ? 0xFFFF0000u : 0u); }
@@ -215,6 +218,7 @@ template<> struct PairCodec<P_FP16C> {
 	static __device__ __forceinline__ void shift_out(uint8_t* own, uint8_t* next, const R n, const bool k0, const bool k1) { if(k0) ((uint16_t*)own)[1] = (uint16_t)(n&0xFFFFu); if(k1) *(uint16_t*)next = (uint16_t)(n>>16); }
 	static __device__ __forceinline__ void shift_out_both(uint8_t* own, uint8_t* next, const R n) { ((uint16_t*)own)[1] = (uint16_t)(n&0xFFFFu); *(uint16_t*)next = (uint16_t)(n>>16); }
 	static __device__ __forceinline__ R shift_in_odd(const uint8_t* next) { return (uint32_t)*(const uint16_t*)next; }
+	static __device__ __forceinline__ R shift_in_e(const uint8_t* own, const uint8_t* next) { return (uint32_t)((const uint16_t*)own)[1]|((uint32_t)*(const uint16_t*)next<<16); }
 	static __device__ __forceinline__ void shift_out_odd(uint8_t* next, const R n) { *(uint16_t*)next = (uint16_t)(n&0xFFFFu); }
 	typedef uint32_t M; // bit mask of a pair: the halves that take the new value
 	static __device__ __forceinline__ M mask(const bool k0, const bool k1) { return (k0 ? 0x0000FFFFu : 0u)|(k1 ? 0xFFFF0000u : 0u); }
@@ -315,6 +319,14 @@ template<class CFG, uint32_t FEAT> __device__ __noinline__ void fix_equilibrium(
 	}
 }
 
+// thermal step in two kernels (DomainConst::upre): the pair's velocity before the force half-step; w0 / w1: the cell executes and is not TYPE_E (k_thermal_g takes u of TYPE_E cells from the boundary field)
+__device__ __forceinline__ void store_upre(const DomainConst& c, const uint64_t n, const bool w0, const bool w1, const PairOut& o) {
+	if(w0&&w1) { *(float2*)(c.upre+n) = o.upx.v; *(float2*)(c.upre+c.N+n) = o.upy.v; *(float2*)(c.upre+2ull*c.N+n) = o.upz.v; }
+	else {
+		if(w0) { c.upre[n] = o.upx.v.x; c.upre[c.N+n] = o.upy.v.x; c.upre[2ull*c.N+n] = o.upz.v.x; }
+		if(w1) { c.upre[n+1ull] = o.upx.v.y; c.upre[c.N+n+1ull] = o.upy.v.y; c.upre[2ull*c.N+n+1ull] = o.upz.v.y; }
+	}
+}
 // rho / u of a strip's west-face cells (x = 0; TYPE_E in every open-boundary case) into L2: by the producer warp when it issues the loads of the strip's first tile (it is
 // the one that knows the strip; the consumers used to peek at the next stage's strip id for this, which the race checker rightly flags). One sector per lane.
 template<class CFG> __device__ __forceinline__ void prefetch_west_face(const DomainConst& c, const uint32_t lane, const int y0, const int z0) {
@@ -332,7 +344,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 	typedef PairCodec<P> PC;
 	typedef typename PC::R R;
 	typedef typename PC::E E;
-	constexpr bool UF = (FEAT&F_UPDATE_FIELDS)!=0u, EQ = (FEAT&F_EQUILIBRIUM)!=0u, VF = (FEAT&F_VOLUME_FORCE)!=0u;
+	constexpr bool UF = (FEAT&F_UPDATE_FIELDS)!=0u, EQ = (FEAT&F_EQUILIBRIUM)!=0u, VF = (FEAT&F_VOLUME_FORCE)!=0u, TH = (FEAT&F_TEMPERATURE)!=0u;
 
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t* const stage0 = smem_raw+((128u-(smem_u32(smem_raw)&127u))&127u); // 128 B aligned; derived from the __shared__ symbol so that LDS/STS are emitted
@@ -500,7 +512,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 		uint8_t* const park_row = stage0+CFG::BOX_BYTES+(par*(uint32_t)CFG::ROWS+row)*(uint32_t)CFG::ES; // + box_off(b): this row's parked element of shifted box b
 		if(park&&first&&lx==0u) { // park column 0 of the x-shifted boxes (pre-collision values; only the strip's last tile touches them)
 #pragma unroll
-			for(int b=0; b<Q; b++) if(box_shifted(b)) *(E*)(park_row+CFG::box_off(b)) = PC::low(*(const R*)((const uint8_t*)box+CFG::box_off(b)));
+			for(int b=0; b<Q; b++) if(box_shifted(b)) *(E*)(park_row+CFG::box_off(b)) = *(const E*)((const uint8_t*)box+CFG::box_off(b));
 		}
 		// the row-end lane (possibly in another warp) reads what the row's first lane parked. (It does so in the strip's last tile, and the stage ring keeps the warps
 		// within STAGES tiles of each other, so for strips longer than the ring the barrier is not strictly needed; dropping it gained nothing: 49.2 vs 50.5 GLUP/s.)
@@ -525,8 +537,8 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 				}
 			}
 			const auto store_fields = [&](const PairOut& o) { // rho / u of the non-TYPE_E cells (UPDATE_FIELDS, FX/kernel.cpp:1709-1715)
+				const bool w0 = run0&&!e0, w1 = run1&&!e1;
 				if(UF) {
-					const bool w0 = run0&&!e0, w1 = run1&&!e1;
 					if(w0&&w1) {
 						*(float2*)(c.rho+n) = o.rho.v; *(float2*)(c.u+n) = o.ux.v; *(float2*)(c.u+c.N+n) = o.uy.v; *(float2*)(c.u+2ull*c.N+n) = o.uz.v;
 					} else {
@@ -534,6 +546,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 						if(w1) { c.rho[n+1ull] = o.rho.v.y; c.u[n+1ull] = o.ux.v.y; c.u[c.N+n+1ull] = o.uy.v.y; c.u[2ull*c.N+n+1ull] = o.uz.v.y; }
 					}
 				}
+				if(TH) store_upre(c, n, w0, w1, o); // thermal step: the velocity before the force half-step, for k_thermal_g
 			};
 			PairOut out;
 			if constexpr (FAST&&CFG::TWOPASS) { // ---- two passes over the shared-memory boxes: moments, then relax + store (see lbm_vec.cuh)
@@ -545,8 +558,9 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 				const f2 g0 = dec_in(*(const R*)bb);
 				const auto ld1 = [&](const int k, f2& gi, f2& gj) {
 					const R wa = *(const R*)(bb+CFG::box_off(1+2*k));
-					R wb = *(const R*)(bb+CFG::box_off(2+2*k));
-					if(pair_shifted(k)) wb = odd_end ? PC::shift_in_odd(nxt+CFG::box_off(2+2*k)) : PC::shift_in(wb, nxt+CFG::box_off(2+2*k));
+					R wb;
+					if(pair_shifted(k)) wb = odd_end ? PC::shift_in_odd(nxt+CFG::box_off(2+2*k)) : PC::shift_in_e(bb+CFG::box_off(2+2*k), nxt+CFG::box_off(2+2*k));
+					else wb = *(const R*)(bb+CFG::box_off(2+2*k));
 					gi = dec_in(wa); gj = dec_in(wb);
 				};
 				moments_of<SG>(g0, ld1, M);
@@ -558,9 +572,10 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 				*(R*)bb = PC::mixm(msk, enc_out(fma2(K.omw, g0, K.g0add)), *(const R*)bb);
 				struct Raw { R wa, wb0; };
 				const auto ld2 = [&](const int k, Raw& r, f2& gi, f2& gj) {
-					r.wa = *(const R*)(bb+CFG::box_off(1+2*k)); r.wb0 = *(const R*)(bb+CFG::box_off(2+2*k));
-					R wb = r.wb0;
-					if(pair_shifted(k)) wb = odd_end ? PC::shift_in_odd(nxt+CFG::box_off(2+2*k)) : PC::shift_in(r.wb0, nxt+CFG::box_off(2+2*k));
+					r.wa = *(const R*)(bb+CFG::box_off(1+2*k));
+					R wb;
+					if(pair_shifted(k)) { wb = odd_end ? PC::shift_in_odd(nxt+CFG::box_off(2+2*k)) : PC::shift_in_e(bb+CFG::box_off(2+2*k), nxt+CFG::box_off(2+2*k)); r.wb0 = wb; }
+					else wb = r.wb0 = *(const R*)(bb+CFG::box_off(2+2*k));
 					gi = dec_in(r.wa); gj = dec_in(wb);
 				};
 				const auto st2 = [&](const int k, const Raw& r, const f2 gi, const f2 gj) { // f_i' goes to slot B, f_i+1' to slot A
@@ -590,8 +605,9 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 			f2 f[Q];
 #pragma unroll
 			for(int b=0; b<Q; b++) {
-				R w = *(const R*)((const uint8_t*)box+CFG::box_off(b));
-				if(box_shifted(b)) w = odd_end ? PC::shift_in_odd(nxt+CFG::box_off(b)) : PC::shift_in(w, nxt+CFG::box_off(b));
+				R w;
+				if(box_shifted(b)) w = odd_end ? PC::shift_in_odd(nxt+CFG::box_off(b)) : PC::shift_in_e((const uint8_t*)box+CFG::box_off(b), nxt+CFG::box_off(b));
+				else w = *(const R*)((const uint8_t*)box+CFG::box_off(b));
 				if(FAST&&P==P_FP16S) f[b] = PairCodec<P_FP16S>::dec_raw(*(const uint32_t*)&w); else f[b] = PC::dec(w);
 			}
 			float4 eb0 = make_float4(1.0f, 0.0f, 0.0f, 0.0f), eb1 = eb0; // boundary rho/u of TYPE_E lanes (prefetched into L2 one tile ago)

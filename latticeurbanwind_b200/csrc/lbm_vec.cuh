@@ -108,7 +108,7 @@ struct PairIn { // what the step needs to know about the two cells besides their
 	int nudge_vertical;
 	ZoneRef zr0, zr1;
 };
-struct PairOut { f2 rho, ux, uy, uz; }; // the rho/u the reference writes with UPDATE_FIELDS (for non-TYPE_E cells)
+struct PairOut { f2 rho, ux, uy, uz; f2 upx, upy, upz; }; // the rho/u the reference writes with UPDATE_FIELDS (for non-TYPE_E cells); up*: the velocity before the force half-step (thermal step, DomainConst::upre)
 
 __device__ __forceinline__ void zone_force2(const PairIn& in, const f2 rho, const f2 ux, const f2 uy, const f2 uz, f2& Fx, f2& Fy, f2& Fz) {
 	zone_apply(in.zr0, in.nudge_vertical, rho.v.x, ux.v.x, uy.v.x, uz.v.x, Fx.v.x, Fy.v.x, Fz.v.x);
@@ -175,6 +175,7 @@ template<uint32_t FEAT> __device__ __forceinline__ void collide_strict2(const Do
 	constexpr bool VF = (FEAT&F_VOLUME_FORCE)!=0u, SG = (FEAT&F_SUBGRID)!=0u;
 	f2 rho, ux, uy, uz;
 	rho_u_strict2(f, rho, ux, uy, uz);
+	out.upx = ux; out.upy = uy; out.upz = uz;
 	f2 Fin[Q];
 	if(VF) {
 		const f2 m2rho = sm(-2.0f, rho);
@@ -256,6 +257,7 @@ template<uint32_t FEAT, bool HAS_E> __device__ __forceinline__ void collide_fast
 		rhom1 = sel2(in.e0, in.e1, rho-bc(1.0f), rhom1); // the non-TYPE_E partner of a mixed pair keeps its own rho-1: its result must not depend on who it is paired with
 		ir = rcp2(rho); ir = fma2(ir, fma2(-rho, ir, bc(1.0f)), ir);
 	}
+	out.upx = ux; out.upy = uy; out.upz = uz;
 	Proj F; f2 uF3 = bc(0.0f);
 	if(VF) {
 		const f2 m2rho = -2.0f*rho;
@@ -360,6 +362,7 @@ template<uint32_t FEAT> __device__ __forceinline__ void fast_prepare(const Domai
 	ir = fma2(ir, fma2(-rho, ir, bc(1.0f)), ir); // one Newton step: full single precision
 	const f2 iri = inv*ir;
 	f2 ux = M.mx*iri, uy = M.my*iri, uz = M.mz*iri;
+	out.upx = ux; out.upy = uy; out.upz = uz;
 	Proj F; F.x = F.y = F.z = bc(0.0f);
 	f2 uF = bc(0.0f);
 	if(VF) {

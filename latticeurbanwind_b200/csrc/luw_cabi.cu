@@ -166,7 +166,6 @@ encode_tiled_fn get_encode_tiled() {
 // described (row pitch not a multiple of 16 bytes for every array) -- the per-cell kernels are used then.
 void setup_tiles(luw_domain* d) {
 	d->tiled = false;
-	if(d->c.features&luw::F_TEMPERATURE) return; // the TEMPERATURE blocks exist in the one-cell-per-thread kernels only
 	const char* off = getenv("LUW_NO_TILE");
 	if(off&&off[0]=='1') return;
 	const char* var = getenv("LUW_TILE_VARIANT");
@@ -180,7 +179,8 @@ void setup_tiles(luw_domain* d) {
 	if(!enc) return;
 	luw::TileShape sh;
 	bool found = false;
-	for(int v : { want, 0, 2 }) { // 2: 64-wide tiles for narrow lattices // the requested variant, else one whose tile is not wider than the lattice
+	const int fallback = d->c.precision==luw::P_FP16C ? 3 : d->c.precision==luw::P_FP16S ? 5 : 0; // thermal domains: the one variant per precision their momentum kernel is built for
+	for(int v : { want, fallback, 0, 2 }) { // 2: 64-wide tiles for narrow lattices // the requested variant, else one whose tile is not wider than the lattice
 		if(d->ks->tile_shape(c.precision, c.features, v, &sh)&&c.Nx>=(uint32_t)sh.tx) { d->tile_variant = v; found = true; break; }
 	}
 	if(!found) return;
@@ -214,8 +214,15 @@ cudaError_t enqueue_step(luw_domain* d, const luw::StepArgs& a, const luw::Domai
 		if(d->kev_used+2u>d->kev.size()) for(int k=0; k<2; k++) { cudaEvent_t ev; e = cudaEventCreate(&ev); if(e!=cudaSuccess) return e; d->kev.push_back(ev); }
 		e = cudaEventRecord(d->kev[d->kev_used], d->stream); if(e!=cudaSuccess) return e;
 	}
-	if(d->tiled) e = d->ks->stream_collide_tile(order ? *order : d->c, a, d->maps, d->tile_variant, d->sm_count, d->stream);
-	else if(d->c.features&luw::F_TEMPERATURE) e = d->ks->stream_collide_thermal(d->c, a, d->stream);
+	// thermal domains: momentum in the tiled kernel (which leaves the pre-force velocity in c.upre) + the TEMPERATURE block as a second kernel -- unless the buoyancy
+	// term is live (f != 0 and beta != 0: the momentum step then depends on this step's T), which takes the fused one-cell-per-thread kernel
+	const bool thermal = (d->c.features&luw::F_TEMPERATURE)!=0u;
+	const bool buoyant = thermal&&d->c.beta!=0.0f&&(a.fx!=0.0f||a.fy!=0.0f||a.fz!=0.0f);
+	if(d->tiled&&!buoyant) {
+		e = d->ks->stream_collide_tile(order ? *order : d->c, a, d->maps, d->tile_variant, d->sm_count, d->stream);
+		if(e==cudaSuccess&&thermal) { e = d->ks->thermal_g(d->c, a, d->stream); d->launches++; }
+	}
+	else if(thermal) e = d->ks->stream_collide_thermal(d->c, a, d->stream);
 	else e = d->ks->stream_collide(d->c, a, d->stream);
 	d->launches++;
 	if(e!=cudaSuccess) return e;
@@ -380,6 +387,7 @@ int luw_domain_create(const luw_domain_params* p, luw_domain** out) {
 	const bool thermal = (p->features&LUW_TEMPERATURE)!=0u;
 	if(rc==LUW_OK&&thermal) rc = dev_alloc(d, (uint8_t**)&c.gi, 7ull*N*d->ddf_size); // gi = Memory<fpxx>(N, 7), T = Memory<float>(N, 1, .., 1.0f): FX/lbm.cpp:322-323
 	if(rc==LUW_OK&&thermal) rc = dev_alloc(d, &c.T, N);
+	if(rc==LUW_OK&&thermal) rc = dev_alloc(d, &c.upre, 3ull*N); // two-kernel thermal step: the pre-force velocity handed from the momentum kernel to k_thermal_g (+12 B per cell)
 	if(rc==LUW_OK) { // Memory<> zero-fills; rho starts at 1 (FX/lbm.cpp:283-288)
 		e = cudaMemsetAsync(c.fi, 0, 19ull*N*d->ddf_size, d->stream);
 		if(e==cudaSuccess) e = cudaMemsetAsync(c.u, 0, 3ull*N*4ull, d->stream);
@@ -418,7 +426,7 @@ int luw_domain_destroy(luw_domain* d) {
 	if(!d) return LUW_OK;
 	DeviceGuard guard(d->p.device);
 	if(d->own_stream) cudaStreamSynchronize(d->own_stream);
-	cudaFree(d->c.fi); cudaFree(d->c.rho); cudaFree(d->c.u); cudaFree(d->c.flags); cudaFree(d->c.sched); cudaFree(d->wbuf); cudaFree(d->sigma); cudaFree(d->c.gi); cudaFree(d->c.T);
+	cudaFree(d->c.fi); cudaFree(d->c.rho); cudaFree(d->c.u); cudaFree(d->c.flags); cudaFree(d->c.sched); cudaFree(d->wbuf); cudaFree(d->sigma); cudaFree(d->c.gi); cudaFree(d->c.T); cudaFree(d->c.upre);
 	if(d->halo_stream) { cudaStreamSynchronize(d->halo_stream); cudaStreamDestroy(d->halo_stream); }
 	if(d->halo_done) cudaEventDestroy(d->halo_done);
 	if(d->ev0) cudaEventDestroy(d->ev0);

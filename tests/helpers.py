@@ -336,12 +336,15 @@ def golden_thermal_halo(engine, O, precision):
 
 
 def run_cuda_thermal(shape, precision, features, flags, rho, u, T, steps, w, arith, f=FORCE, omega=OMEGA, zones=ZONES, thermal=THERMAL, update_at_end=False,
-                     batched=False, D=(1, 1, 1), O=(0, 0, 0)):
-    """run_cpu_thermal's script on the CUDA path (Domain over the C ABI): returns (fi, rho, u, gi, T)."""
+                     batched=False, D=(1, 1, 1), O=(0, 0, 0), expect_tiles=None):
+    """run_cpu_thermal's script on the CUDA path (Domain over the C ABI): returns (fi, rho, u, gi, T). A tiled thermal domain runs the two-kernel step (TMA-tiled
+    momentum kernel + k_thermal_g) while the buoyancy term vanishes (f = 0 or beta = 0) and the fused one-cell-per-thread kernel otherwise."""
     from latticeurbanwind_b200.domain import Domain
     Nx, Ny, Nz = shape
     with Domain(Nx, Ny, Nz, D=D, O=O, precision=precision, features=features, w=w, arith=arith, **zones) as d:
-        assert d.thermal and not d.uses_tiles()
+        assert d.thermal
+        if expect_tiles is not None:
+            assert d.uses_tiles() == expect_tiles
         d.set_thermal(**thermal)
         d.rho[:], d.u[:], d.flags[:], d.T[:] = rho, u, flags, T
         d.f, d.omega = f, omega

@@ -46,6 +46,48 @@ def test_fast_within_tolerance(oracle_lib, precision):
     assert H.rel_l2(got[2], want[2]) <= 2 * TOL_FAST[precision]["rel_l2_u"]
 
 
+NO_BUOYANCY = dict(H.THERMAL, beta=0.0)  # every LUW mode builds its LBM with f = 0: the buoyancy term vanishes and the thermal step runs as two kernels
+
+
+@PRECS
+@pytest.mark.parametrize("arith", [0, 1], ids=["strict", "fast"])
+@pytest.mark.parametrize("shape", [(128, 12, 10), (253, 9, 7)], ids=["128x12x10", "253x9x7-oddNx"])
+def test_two_kernel_thermal_step_equals_oracle(oracle_lib, precision, arith, shape):
+    """LUW's shipped switches (FX/defines.hpp:14-24: UPDATE_FIELDS, VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, SUBGRID, TEMPERATURE, + nudging and sponge) on a lattice the
+    TMA tile kernel takes: momentum in the tiled kernel, which hands the velocity before the force half-step to k_thermal_g (csrc/lbm_kernels.cuh). STRICT: every
+    DDF, rho, u, g and T value equals the oracle's; FAST: within the tolerances of the fused kernel. With a live buoyancy term the same domain must fall back to the
+    fused kernel and still equal the oracle."""
+    from tests.test_gpu_parity import TOL_FAST
+    O = oracle_lib
+    flags, rho, u, T = H.thermal_case(shape, seed=5)
+    w = cases.relaxation_rate(1e-6)
+    for thermal, f in ((NO_BUOYANCY, H.FORCE), (H.THERMAL, (0.0, 0.0, 0.0)), (H.THERMAL, H.FORCE)):  # beta = 0 / f = 0: two kernels; both live: fused
+        if arith == 1 and thermal is H.THERMAL and f == H.FORCE:
+            continue
+        want = H.run_cpu_thermal(O.Oracle(), O, shape, precision, O.FEATURE_SETS["luwT"], flags, rho, u, T, 8, w, f=f, thermal=thermal)
+        got = H.run_cuda_thermal(shape, precision, H.FEATURE_SETS["luwT"], flags, rho, u, T, 8, w, arith, f=f, thermal=thermal, expect_tiles=True)
+        if arith == 0:
+            for g, r, name in zip(got, want, NAMES):
+                assert np.array_equal(g, r), (name, thermal["beta"], f)
+        else:
+            tol = TOL_FAST_T[precision]
+            assert float(np.abs(got[4] - want[4]).max()) <= tol["max_abs"] and H.rel_l2(got[4], want[4]) <= tol["rel_l2"]
+            assert H.rel_l2(got[2], want[2]) <= 2 * TOL_FAST[precision]["rel_l2_u"]
+
+
+def test_two_kernel_thermal_step_without_update_fields(oracle_lib):
+    """FEAT = 14 | TEMPERATURE: rho / u / T are not stored per step (update_fields on demand), the pre-force velocity still reaches k_thermal_g."""
+    O = oracle_lib
+    shape = (128, 12, 10)
+    flags, rho, u, T = H.thermal_case(shape, seed=6)
+    w = cases.relaxation_rate(1e-6)
+    feat = H.FEATURE_SETS["luwnf"] | 64
+    want = H.run_cpu_thermal(O.Oracle(), O, shape, 1, feat, flags, rho, u, T, 7, w, thermal=NO_BUOYANCY, update_at_end=True)
+    got = H.run_cuda_thermal(shape, 1, feat, flags, rho, u, T, 7, w, 0, thermal=NO_BUOYANCY, update_at_end=True, expect_tiles=True)
+    for g, r, name in zip(got, want, NAMES):
+        assert np.array_equal(g, r), name
+
+
 def test_wide_lattice_and_batched_steps(oracle_lib):
     """Rows wider than one thread block, padded pitch (Nx = 150 -> 160), luw_run_steps."""
     O = oracle_lib
