@@ -412,12 +412,32 @@ def bench_single(args, workload, arith, A, cases, Domain, CellSet, pinned_empty,
         # ---- e2e: one host-API call per step, with that step's boundary field going up and a probe plane coming back
         if not args.no_e2e:
             res["e2e"] = e2e_steps(d, CellSet, pinned_empty, A, shape, min(K, 100), t_up, N)
+        if headline and not args.no_e2e:
+            res["e2e"]["cpp_host"] = cpp_host_e2e(case, shape, precision, features, min(K, 60))
         if headline and not args.no_cpu:
             c_mlups, cores, kind, sample, c_ms, c_steps = cpu_run(workload, 8, 1, budget_s=15.0)
             res["cpu_baseline"] = {"value": c_mlups, "unit": "MLUP/s", "cores": cores, "kind": kind, "sample": sample}
         return res
     finally:
         d.close()
+
+
+def cpp_host_e2e(case, shape, precision, features, K):
+    """The same metric through the reference's C++ API (latticeurbanwind_b200/host: class LBM over the C ABI), driven like FX/setup.cpp drives it: boundary
+    conditions through lbm.flags / lbm.u, run(0), then one run(1) per step with a per-step upload of the top boundary plane's velocity from the host mirror and a
+    read-back of rho / u on a probe plane into it (host buffers; one synchronisation per step). Separate process: lib/luw_host_bench (host/host_bench.cpp)."""
+    exe = os.path.join(ROOT, "latticeurbanwind_b200", "lib", "luw_host_bench")
+    if case not in ("urban", "channel") or not os.path.isfile(exe) or features & F_TEMPERATURE:
+        return {"unavailable": "luw_host_bench not built or no C++ twin of this case"}
+    try:
+        r = subprocess.run([exe, case, *map(str, shape), str(precision), str(features), str(K), "5"], capture_output=True, text=True, timeout=600)
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+        return {"value": out["mlups"], "unit": "MLUP/s", "ms_per_step": out["ms_per_step"], "steps": K, "h2d_bytes_per_step": out["h2d_bytes_per_step"],
+                "d2h_bytes_per_step": out["d2h_bytes_per_step"], "probe_mean_ux": out["probe_mean_ux"], "build_and_initialize_s": out["build_and_initialize_s"],
+                "api": "LBM::run(1) per step, LBM_Domain::u.enqueue_write_to_device / enqueue_read_from_device(offset, length) (host/lbm.hpp), finish_queue every step",
+                "note": "the case is this workload's C++ twin (same lattice, feature set and boundary types; cubes from the same pitch / edge rule)"}
+    except Exception as exc:
+        return {"unavailable": f"luw_host_bench failed: {exc}"}
 
 
 def e2e_steps(d, CellSet, pinned_empty, A, shape, K, t_upload_init, N):
@@ -442,9 +462,31 @@ def e2e_steps(d, CellSet, pinned_empty, A, shape, K, t_upload_init, N):
     uprs = [pinned_empty(3 * cpr.count, np.float32) for _ in range(RING)]
     rprs = [pinned_empty(cpr.count, np.float32) for _ in range(RING)]
     upr, rpr = uprs[0], rprs[0]
+    # von Karman inlet (on in every default deck): 256 modes on the TYPE_E cells of the x = 0 face, applied before every step like the reference's pre-step update
+    # (FX/setup.cpp:538-558, 4897) -- INSIDE the timed loop
+    vk, vk_info = None, None
+    try:
+        from latticeurbanwind_b200.domain import VkInlet
+        P, M = int(inlet.size), 256
+        rng = np.random.default_rng(5)
+        pdv = np.zeros(7 * P, np.float32)
+        pdv[0:P] = 0.0; pdv[P:2 * P] = ((inlet // np.uint64(Nx)) % np.uint64(Ny)).astype(np.float32); pdv[2 * P:3 * P] = (inlet // np.uint64(Nx * Ny)).astype(np.float32)
+        for c in range(3):
+            pdv[(3 + c) * P:(4 + c) * P] = d.u[c * d.N + inlet.astype(np.int64)]
+        pdv[6 * P:7 * P] = 0.004
+        V = 5 * M
+        mdv = np.concatenate([rng.normal(0, 0.3, 3 * V), rng.normal(0, 0.05, V), rng.normal(0, 1.0, 3 * V), rng.uniform(0, 2 * np.pi, 3 * V)]).astype(np.float32)
+        vk = VkInlet(d, inlet, np.zeros(P, np.uint8), pdv, mdv, M, V)
+        vk.apply(0, 100.0, 101.0, 0.0); d.finish_queue()
+        d.timer_begin(); vk.apply(0, 101.0, 102.0, 0.0); vk.apply(0, 102.0, 103.0, 0.0); vk.apply(0, 103.0, 104.0, 0.0); vms = d.timer_end() / 3.0
+        vk_info = {"points": P, "modes": M, "apply_ms": vms, "inside_the_timed_loop": True}
+    except Exception as exc:  # the loop then runs without it, and says so
+        vk, vk_info = None, f"failed: {exc}"
     def step(k):
         r = k % RING
         cin.upload(A.FIELD_U, uins[r])
+        if vk is not None:
+            vk.apply(0, float(200 + k), float(201 + k), 0.0)
         d.enqueue_stream_collide(); d.increment_time_step()
         cpr.download(A.FIELD_U, uprs[r]); cpr.download(A.FIELD_RHO, rprs[r])
         if r == RING - 1:
@@ -461,29 +503,16 @@ def e2e_steps(d, CellSet, pinned_empty, A, shape, K, t_upload_init, N):
     d.read_from_device(A.FIELD_RHO); d.read_from_device(A.FIELD_U); d.finish_queue()
     t_down = time.perf_counter() - t1
     out = {"value": N * K / dt / 1e6, "unit": "MLUP/s", "h2d_bytes_per_step": int(uin.nbytes), "d2h_bytes_per_step": int(upr.nbytes + rpr.nbytes),
-           "steps": K, "ms_per_step": dt / K * 1e3, "timer": "host wall clock around K x (upload, step, read-back), host sync every 4th step (ring of 4 pinned buffer sets) and at the end",
+           "steps": K, "ms_per_step": dt / K * 1e3, "timer": "host wall clock around K x (boundary upload, von Karman inlet update, step, probe read-back), host sync every 4th step (ring of 4 pinned buffer sets) and at the end",
            "probe_mean_ux": float(upr[:cpr.count].mean()),
            "job": {"upload_init_s": t_upload_init, "h2d_bytes": int(17 * N), "readback_s": t_down, "d2h_bytes": int(16 * N),
                    "note": "one-off per case: full rho/u/flags images up (17 B/cell, pinned), rho/u down (16 B/cell)"}}
     cin.close(); cpr.close()
-    try:  # von Karman inlet (on in every default deck): 256 modes on the TYPE_E cells of the x = 0 face, once per step in the reference's loop (FX/setup.cpp:538-558)
-        from latticeurbanwind_b200.domain import VkInlet
-        P, M = int(inlet.size), 256
-        rng = np.random.default_rng(5)
-        pdv = np.zeros(7 * P, np.float32)
-        pdv[0:P] = 0.0; pdv[P:2 * P] = ((inlet // np.uint64(Nx)) % np.uint64(Ny)).astype(np.float32); pdv[2 * P:3 * P] = (inlet // np.uint64(Nx * Ny)).astype(np.float32)
-        for c in range(3):
-            pdv[(3 + c) * P:(4 + c) * P] = d.u[c * d.N + inlet.astype(np.int64)]
-        pdv[6 * P:7 * P] = 0.004
-        V = 5 * M
-        mdv = np.concatenate([rng.normal(0, 0.3, 3 * V), rng.normal(0, 0.05, V), rng.normal(0, 1.0, 3 * V), rng.uniform(0, 2 * np.pi, 3 * V)]).astype(np.float32)
-        vk = VkInlet(d, inlet, np.zeros(P, np.uint8), pdv, mdv, M, V)
-        vk.apply(0, 100.0, 101.0, 0.0); d.finish_queue()
-        d.timer_begin(); vk.apply(0, 101.0, 102.0, 0.0); vk.apply(0, 102.0, 103.0, 0.0); vk.apply(0, 103.0, 104.0, 0.0); vms = d.timer_end() / 3.0
-        out["job"]["vk_inlet"] = {"points": P, "modes": M, "apply_ms": vms, "share_of_step": vms / (dt / K * 1e3)}
+    if isinstance(vk_info, dict):
+        vk_info["share_of_step"] = vk_info["apply_ms"] / (dt / K * 1e3)
+    out["job"]["vk_inlet"] = vk_info
+    if vk is not None:
         vk.close()
-    except Exception as exc:  # not part of the metric
-        out["job"]["vk_inlet"] = f"failed: {exc}"
     try:  # one sample of the device-side running statistics (mean / M2 of u, mean of rho: 72 B per cell) next to what it replaces: the read-back above
         from latticeurbanwind_b200.domain import Stats
         st = Stats(d)

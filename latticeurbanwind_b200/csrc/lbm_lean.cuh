@@ -254,7 +254,7 @@ template<class CFG> inline LeanConst lean_const(const DomainConst& c, const bool
 	l.zone_xw = west ? (int)c.buffer_N-c.Ox : -0x7FFFFFFF;
 	l.zone_xe = east ? (int)c.Nxg-1-(int)c.buffer_N-63-c.Ox : 0x7FFFFFFF;
 	l.flags = (c.Dx==1u ? LC_WRAP_X : 0u)|((c.Dx==1u&&l.tiles_x>=2u) ? LC_PARK : 0u)|((c.Dx>1u||l.last_tx!=(uint32_t)CFG::TX) ? LC_EDGE_X_SLOW : 0u)|(zones ? LC_ZONES : 0u)|(prefetch ? LC_PREFETCH : 0u)
-		|((c.features&F_UPDATE_FIELDS) ? LC_UF : 0u)|((c.features&F_EQUILIBRIUM) ? LC_EQ : 0u)|((lag&&CFG::STAGES>=3) ? LC_LAG : 0u)|((c.Nx&1u) ? LC_ODD_X : 0u);
+		|((c.features&F_UPDATE_FIELDS) ? LC_UF : 0u)|((c.features&F_EQUILIBRIUM) ? LC_EQ : 0u)|((lag&&CFG::STAGES>=5) ? LC_LAG : 0u)|((c.Nx&1u) ? LC_ODD_X : 0u);
 	return l;
 }
 __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, const int c0, const int c1, const int c2, const int c3) {

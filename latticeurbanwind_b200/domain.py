@@ -29,13 +29,40 @@ class Domain:
         self.omega = (0.0, 0.0, 0.0)
         self._h = C.c_void_p()
         A.check(A.lib().luw_domain_create(C.byref(self.params), C.byref(self._h)))
-        # host mirrors, initialised like the reference's Memory<> objects (rho=1, u=0, flags=0; FX/lbm.cpp:283-288)
-        self.rho = np.ones(self.N, np.float32)
-        self.u = np.zeros(3 * self.N, np.float32)
-        self.flags = np.zeros(self.N, np.uint8)
+        # host mirrors, initialised like the reference's Memory<> objects (rho=1, u=0, flags=0; FX/lbm.cpp:283-288) -- LAZILY: a mirror is allocated when the host
+        # first touches it. The device fields hold the same values from luw_domain_create on, so an untouched mirror has nothing to upload; a case that moves its
+        # boundary data through cell sets never owns a host image of the lattice (17 B per cell in the reference, FX/lbm.cpp:95-106).
+        self._mirror = {}
         # thermal D3Q7 extension (features & TEMPERATURE): host mirror of T, 1 everywhere like Memory<float>(N, 1, .., 1.0f) (FX/lbm.cpp:323)
         self.thermal = bool(features & A.TEMPERATURE)
-        self.T = np.ones(self.N, np.float32) if self.thermal else None
+
+    _MIRRORS = {"rho": (A.FIELD_RHO, 1, np.float32, 1.0), "u": (A.FIELD_U, 3, np.float32, 0.0), "flags": (A.FIELD_FLAGS, 1, np.uint8, 0), "T": (A.FIELD_T, 1, np.float32, 1.0)}
+
+    def _get_mirror(self, name):
+        if name == "T" and not self.thermal:
+            return None
+        a = self._mirror.get(name)
+        if a is None:
+            _, comps, dtype, value = self._MIRRORS[name]
+            a = np.full(comps * self.N, value, dtype) if value else np.zeros(comps * self.N, dtype)
+            self._mirror[name] = a
+        return a
+
+    def _set_mirror(self, name, value):
+        _, comps, dtype, _ = self._MIRRORS[name]
+        if isinstance(value, np.ndarray) and value.dtype == dtype and value.size == comps * self.N and value.flags.c_contiguous:
+            self._mirror[name] = value.reshape(-1)  # adopt the caller's buffer (e.g. page-locked memory) as the mirror
+        else:
+            self._get_mirror(name)[:] = value
+
+    rho = property(lambda self: self._get_mirror("rho"), lambda self, v: self._set_mirror("rho", v))
+    u = property(lambda self: self._get_mirror("u"), lambda self, v: self._set_mirror("u", v))
+    flags = property(lambda self: self._get_mirror("flags"), lambda self, v: self._set_mirror("flags", v))
+    T = property(lambda self: self._get_mirror("T"), lambda self, v: self._set_mirror("T", v))
+
+    def host_mirror_bytes(self):
+        """Bytes of host memory held by the mirrors that have been touched so far."""
+        return sum(a.nbytes for a in self._mirror.values())
 
     def set_thermal(self, w_T, beta=0.0, T_avg=1.0):
         """def_w_T = 1/(2 alpha + 1/2), def_beta, def_T_avg (FX/lbm.cpp:750-752) for the launches that follow."""
@@ -84,8 +111,10 @@ class Domain:
         return (A.FIELD_RHO, A.FIELD_U, A.FIELD_FLAGS) + ((A.FIELD_T,) if self.thermal else ())
 
     def upload_all(self):
+        names = {A.FIELD_RHO: "rho", A.FIELD_U: "u", A.FIELD_FLAGS: "flags", A.FIELD_T: "T"}
         for f in self._mirrored_fields():
-            self.write_to_device(f)
+            if names[f] in self._mirror:  # an untouched mirror equals what the device field was created with
+                self.write_to_device(f)
 
     def download_all(self):
         for f in self._mirrored_fields():

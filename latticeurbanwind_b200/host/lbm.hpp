@@ -83,31 +83,42 @@ float lbm_kernel_literal(const float x); // the float the reference's kernel see
 inline void luw_check(const int rc) { if(rc!=LUW_OK) print_error(std::string("CUDA layer: ")+luw_last_error_string()); } // reference: any device error -> print_error (FX/opencl.hpp:613-618)
 
 // ---------------------------------------------------------------------------------------------------------------- Memory<T> (FX/opencl.hpp:331-603)
-// Host mirror (page-locked) + the device field of ONE domain. `d` dimensions, SoA: data()[n + c*N].
+// Host mirror + the device field of ONE domain. `d` dimensions, SoA: data()[n + c*N].
+// The mirror is LAZY: nothing is allocated until the host touches it (data(), operator[], reset, a read from the device). The device field holds the construction
+// value from luw_domain_create on, so an untouched mirror has nothing to upload: enqueue_write_to_device() of such a mirror is a no-op. A case that feeds its
+// boundary through cell sets (luw_cellset_*) and reads probes the same way therefore never owns a host image of the lattice -- the reference's 17 B per cell of
+// host memory (FX/lbm.cpp:95-106; 171 GB for the 10 G-cell configuration) are only paid by code that really indexes the whole field, like the case driver.
+// Mirrors up to LUW_PIN_LIMIT_MB (default 4096 MB per field) are page-locked; larger ones are pageable, zero pages committed on first touch.
+inline ulong luw_pin_limit_bytes() { static const ulong v = []{ const char* e = getenv("LUW_PIN_LIMIT_MB"); return (ulong)(e ? atol(e) : 4096l)*1048576ull; }(); return v; }
 template<typename T> class Memory {
 private:
 	luw_domain* dom = nullptr;
 	int field = 0;
 	ulong N = 0ull; uint d = 1u;
-	T* host = nullptr;
+	mutable T* host = nullptr;
+	mutable bool pinned = false;
+	T fill = (T)0; // value of an untouched mirror (= what the device field was created with)
 	bool loose = false; // host-only buffer that is not a field of the lattice (see below)
-	void release() { if(host) { if(loose) delete[] host; else luw_host_free(host); } host = nullptr; }
-public:
-	T* x = nullptr; T* y = nullptr; T* z = nullptr; // host pointers of the components (FX/opencl.hpp:343-349)
-	Memory() {}
-	Memory(luw_domain* dom, const int field, const ulong N, const uint dimensions, const T value) : dom(dom), field(field), N(N), d(dimensions) {
-		if(N*(ulong)d==0ull) print_error("Memory size must be larger than 0.");
-		void* p = nullptr;
-		luw_check(luw_host_alloc(&p, N*(ulong)d*sizeof(T)));
-		host = (T*)p;
+	void release() { if(host) { if(loose) delete[] host; else if(pinned) luw_host_free(host); else free(host); } host = nullptr; x = y = z = nullptr; }
+	void materialize() const {
+		if(host||N*(ulong)d==0ull) return;
+		const ulong bytes = N*(ulong)d*sizeof(T);
+		if(bytes<=luw_pin_limit_bytes()) { void* p = nullptr; luw_check(luw_host_alloc(&p, bytes)); host = (T*)p; pinned = true; }
+		else { host = (T*)calloc((size_t)(N*(ulong)d), sizeof(T)); pinned = false; if(!host) print_error("Host allocation of "+std::to_string(bytes/1048576ull)+" MB failed."); }
 		x = host; if(d>1u) y = host+N; if(d>2u) z = host+2ull*N;
-		reset(value);
+		if(pinned||fill!=(T)0) for(ulong i=0ull; i<N*(ulong)d; i++) host[i] = fill; // calloc'ed zero pages stay uncommitted until they are written
+	}
+public:
+	mutable T* x = nullptr; mutable T* y = nullptr; mutable T* z = nullptr; // host pointers of the components (FX/opencl.hpp:343-349); valid once the mirror has been touched (data())
+	Memory() {}
+	Memory(luw_domain* dom, const int field, const ulong N, const uint dimensions, const T value) : dom(dom), field(field), N(N), d(dimensions), fill(value) {
+		if(N*(ulong)d==0ull) print_error("Memory size must be larger than 0.");
 	}
 	Memory(const Memory&) = delete;
 	Memory& operator=(const Memory&) = delete;
 	Memory(Memory&& o) noexcept { *this = std::move(o); }
 	Memory& operator=(Memory&& o) noexcept {
-		if(this!=&o) { release(); dom = o.dom; field = o.field; N = o.N; d = o.d; host = o.host; loose = o.loose; x = o.x; y = o.y; z = o.z; o.host = nullptr; o.x = o.y = o.z = nullptr; o.N = 0ull; }
+		if(this!=&o) { release(); dom = o.dom; field = o.field; N = o.N; d = o.d; host = o.host; pinned = o.pinned; fill = o.fill; loose = o.loose; x = o.x; y = o.y; z = o.z; o.host = nullptr; o.x = o.y = o.z = nullptr; o.N = 0ull; }
 		return *this;
 	}
 	~Memory() { release(); }
@@ -122,21 +133,22 @@ public:
 		reset(value);
 	}
 #endif
-	void reset(const T value=(T)0) { for(ulong i=0ull; i<range(); i++) host[i] = value; }
+	bool materialized() const { return host!=nullptr; } // has the host ever touched this mirror?
+	void reset(const T value=(T)0) { if(!host&&!loose) { fill = value; materialize(); return; } for(ulong i=0ull; i<range(); i++) host[i] = value; }
 	ulong length() const { return N; }
 	uint dimensions() const { return d; }
 	ulong range() const { return N*(ulong)d; }
 	ulong capacity() const { return N*(ulong)d*sizeof(T); }
-	T* data() { return host; }
-	const T* data() const { return host; }
-	T& operator[](const ulong i) { return host[i]; }
-	const T& operator[](const ulong i) const { return host[i]; }
-	T operator()(const ulong i) const { return host[i]; }
-	T operator()(const ulong i, const uint dimension) const { return host[i+(ulong)dimension*N]; }
-	void enqueue_read_from_device() { if(!loose) luw_check(luw_download(dom, field, host, 0ull, range())); }
-	void enqueue_write_to_device() { if(!loose) luw_check(luw_upload(dom, field, host, 0ull, range())); }
-	void enqueue_read_from_device(const ulong offset, const ulong length) { if(!loose) luw_check(luw_download(dom, field, host+offset, offset, length)); }
-	void enqueue_write_to_device(const ulong offset, const ulong length) { if(!loose) luw_check(luw_upload(dom, field, host+offset, offset, length)); }
+	T* data() { materialize(); return host; }
+	const T* data() const { materialize(); return host; }
+	T& operator[](const ulong i) { materialize(); return host[i]; }
+	const T& operator[](const ulong i) const { materialize(); return host[i]; }
+	T operator()(const ulong i) const { materialize(); return host[i]; }
+	T operator()(const ulong i, const uint dimension) const { materialize(); return host[i+(ulong)dimension*N]; }
+	void enqueue_read_from_device() { if(!loose) { materialize(); luw_check(luw_download(dom, field, host, 0ull, range())); } }
+	void enqueue_write_to_device() { if(!loose&&host) luw_check(luw_upload(dom, field, host, 0ull, range())); } // untouched mirror: the device already holds its value
+	void enqueue_read_from_device(const ulong offset, const ulong length) { if(!loose) { materialize(); luw_check(luw_download(dom, field, host+offset, offset, length)); } }
+	void enqueue_write_to_device(const ulong offset, const ulong length) { if(!loose&&host) luw_check(luw_upload(dom, field, host+offset, offset, length)); }
 	void finish_queue() { if(!loose) luw_check(luw_sync(dom)); }
 	void read_from_device() { enqueue_read_from_device(); finish_queue(); }
 	void write_to_device() { enqueue_write_to_device(); finish_queue(); }
@@ -250,6 +262,7 @@ public:
 #ifdef LUW_USE_REFERENCE_UTILITIES
 	void voxelize_mesh_on_device(const Mesh* mesh, const uchar flag=TYPE_S) { voxelize_triangles_on_device((const float*)mesh->p0, (const float*)mesh->p1, (const float*)mesh->p2, mesh->triangle_number, mesh->pmin, mesh->pmax, flag); }
 #endif
+	bool uses_tiles() const { int t = 0; luw_check(luw_domain_step_kernel(handle, &t)); return t!=0; } // does stream_collide run the TMA-tiled kernel on this domain?
 	luw_domain* get_handle() const { return handle; } // reference: get_device() hands out the OpenCL Device; here the C-ABI handle
 	int get_device_ordinal() const { return device; }
 #ifdef LUW_USE_REFERENCE_UTILITIES

@@ -122,3 +122,39 @@ def test_cpp_statistics_match_the_oracle_loop(oracle_lib, tmp_path):
         orc.accumulate(ref[1], ref[2], u_avg, rho_avg, *m2)
     assert np.array_equal(one[2], u_avg) and np.array_equal(one[3], rho_avg)
     assert np.array_equal(one[4], m2[0]) and np.array_equal(one[5], m2[1]) and np.array_equal(one[6], m2[2])
+
+
+BENCH = os.path.join(LIB, "luw_host_bench")
+
+
+def _host_bench(*args, env=None):
+    import json
+    build()
+    r = subprocess.run([BENCH, *map(str, args)], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.gpu
+def test_cpp_api_end_to_end_loop():
+    """bench.py's e2e.cpp_host leg in miniature: LBM built through the global accessors, one run(1) per step, per-step boundary upload and probe read-back
+    through Memory<T>'s ranged transfers (host buffers)."""
+    res = _host_bench("urban", 256, 128, 64, 1, 62, 20, 5)
+    assert res["tiled"] == 1 and res["mlups"] > 100.0 and res["h2d_bytes_per_step"] == 12 * 256 * 128 and res["d2h_bytes_per_step"] == 16 * 256 * 128
+    assert 0.01 < res["probe_mean_ux"] < 0.2 and res["host_mirror_u"] == 1 and res["host_mirror_flags"] == 1
+
+
+@pytest.mark.gpu
+def test_one_gigacell_domain_without_host_mirrors():
+    """1024^3 = 1.07 G cells FP16S (59 GB of HBM): the reference would hold 17 B per cell on the host (FX/lbm.cpp:95-106, 18 GB here, 171 GB for the 10 G-cell
+    configuration). Memory<T>'s mirrors are lazy: a case that does not index whole fields on the host never allocates them; a ranged read of a > 4 GB field lands in
+    pageable memory whose untouched pages stay uncommitted."""
+    import torch
+    if torch.cuda.mem_get_info(0)[0] < 70 * 2 ** 30:
+        pytest.skip("needs 70 GB of free device memory")
+    res = _host_bench("rest", 1024, 1024, 1024, 1, 0, 3, 1)
+    assert res["cells"] == 1024 ** 3 and res["tiled"] == 1 and res["mlups"] > 1000.0
+    assert res["host_mirror_rho"] == 0 and res["host_mirror_flags"] == 0, res
+    assert res["probe_mean_ux"] == 0.0  # a fluid at rest stays at rest
+    assert res["peak_rss_mb"] < 3000, res  # no 18 GB host image (the u mirror exists after the ranged read, 16 KB of it committed)
+    assert res["device_mb"] > 50000
