@@ -3,6 +3,11 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_distributed_gpu.py -m gpu -q -rfEs -p no:cacheprovider 2>&1 | tail -12 > gpurun_out/r2i_pytest.log
 tail -4 gpurun_out/r2i_pytest.log
+# the reference API's multi-GPU path on physical devices: the C++ LBM (one thread, D domains, device d % ndev) with the direct (remote-store) in-process exchange
+timeout 900 python -m pytest tests/test_cpp_host.py tests/test_gpu_parity.py tests/test_voxelize.py tests/test_thermal_gpu.py tests/test_stats.py -m gpu -q -rfEs -p no:cacheprovider -k "decomposed or domains or cpp or 2x" 2>&1 | tail -12 > gpurun_out/r2i_pytest_inprocess.log
+tail -4 gpurun_out/r2i_pytest_inprocess.log
+LUW_HALO_DIRECT=0 timeout 900 python -m pytest tests/test_cpp_host.py -m gpu -q -rfEs -p no:cacheprovider -k "decomposed or domains or 2x" 2>&1 | tail -4 > gpurun_out/r2i_pytest_inprocess_staged.log
+tail -2 gpurun_out/r2i_pytest_inprocess_staged.log
 run() { # name, env, args
   env $2 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 100 --warmup 10 $3 > gpurun_out/r2i_$1.json 2> gpurun_out/r2i_$1.err
   python - <<PY

@@ -50,6 +50,7 @@ struct luw_domain {
 		char* send_p = nullptr; char* send_m = nullptr; char* recv_p = nullptr; char* recv_m = nullptr;
 		uint64_t bytes = 0ull;
 		cudaEvent_t extracted = nullptr, got_p = nullptr, got_m = nullptr; // my payloads are packed / I have copied the (+) and the (-) neighbour's payload out of ITS send buffer
+		cudaEvent_t inserted = nullptr; // direct exchange (remote stores into the neighbours' receive buffers): I have unpacked my receive buffers, they may be overwritten
 		// (an event can only be recorded on a stream of its own device: every event here is recorded by its owner and waited for by the neighbours)
 		bool in_use = false;
 	} halo[3];
@@ -436,6 +437,7 @@ int luw_domain_destroy(luw_domain* d) {
 		luw_domain::HaloAxis& h = d->halo[a];
 		cudaFree(h.send_p); cudaFree(h.send_m); cudaFree(h.recv_p); cudaFree(h.recv_m);
 		if(h.extracted) cudaEventDestroy(h.extracted);
+		if(h.inserted) cudaEventDestroy(h.inserted);
 		if(h.got_p) cudaEventDestroy(h.got_p);
 		if(h.got_m) cudaEventDestroy(h.got_m);
 	}
@@ -587,7 +589,18 @@ static int halo_axis_setup(luw_domain* d, const uint32_t axis) { // buffers size
 	CU(cudaEventCreateWithFlags(&h.extracted, cudaEventDisableTiming));
 	CU(cudaEventCreateWithFlags(&h.got_p, cudaEventDisableTiming));
 	CU(cudaEventCreateWithFlags(&h.got_m, cudaEventDisableTiming));
+	CU(cudaEventCreateWithFlags(&h.inserted, cudaEventDisableTiming));
 	return LUW_OK;
+}
+// can a kernel on device `a` store into memory of device `b`? (peer access is switched on by luw_domain_create for every pair that allows it)
+static bool peer_stores_ok(const int a, const int b) {
+	if(a==b) return true;
+	int can = 0;
+	if(cudaDeviceCanAccessPeer(&can, a, b)!=cudaSuccess||!can) { cudaGetLastError(); return false; }
+	DeviceGuard guard(a);
+	const cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+	if(e!=cudaSuccess) cudaGetLastError(); // "already enabled" is the expected answer
+	return e==cudaSuccess||e==cudaErrorPeerAccessAlreadyEnabled;
 }
 int luw_halo_exchange(luw_domain* const* doms, uint32_t count, int payload, uint32_t axis, uint64_t t) {
 	if(!doms||count==0u||axis>2u) return fail(LUW_ERR_INVALID, "bad argument");
@@ -604,6 +617,37 @@ int luw_halo_exchange(luw_domain* const* doms, uint32_t count, int payload, uint
 	luw_halo_bytes(doms[0], payload, axis, &bytes);
 	const uint32_t stride = axis==0u ? 1u : axis==1u ? D[0] : D[0]*D[1];
 	const auto neighbour = [&](const uint32_t i, const uint32_t step) { const uint32_t di = (i/stride)%D[axis]; return doms[i-di*stride+((di+step)%D[axis])*stride]; }; // periodic
+	// Direct exchange (all neighbour pairs on one device or with peer access; LUW_HALO_DIRECT=0 keeps the staged copies): like the one-process-per-GPU driver's IPC path,
+	// the extract kernel of a domain STORES its two payloads straight into the neighbours' receive buffers over NVLink; events -- all domains live in this process --
+	// take the place of the flags. No send buffers, no cudaMemcpyPeerAsync.
+	static const bool direct_allowed = []{ const char* e = getenv("LUW_HALO_DIRECT"); return !(e&&e[0]=='0'); }();
+	bool direct = direct_allowed;
+	for(uint32_t i=0u; i<count&&direct; i++) direct = peer_stores_ok(doms[i]->p.device, neighbour(i, 1u)->p.device)&&peer_stores_ok(doms[i]->p.device, neighbour(i, D[axis]-1u)->p.device);
+	if(direct) {
+		for(uint32_t i=0u; i<count; i++) { // 1. pack into the neighbours' receive buffers, once they have unpacked the previous exchange of this axis
+			luw_domain* d = doms[i];
+			luw_domain* up = neighbour(i, 1u);
+			luw_domain* dn = neighbour(i, D[axis]-1u);
+			DeviceGuard guard(d->p.device);
+			if(up->halo[axis].in_use) CU(cudaStreamWaitEvent(d->stream, up->halo[axis].inserted, 0));
+			if(dn->halo[axis].in_use) CU(cudaStreamWaitEvent(d->stream, dn->halo[axis].inserted, 0));
+			CU(halo_kernel(d, payload, axis, t, false, true, up->halo[axis].recv_m, dn->halo[axis].recv_p)); // my + face -> the (+) neighbour's - halo, my - face -> the (-) neighbour's + halo
+			d->launches++;
+			CU(cudaEventRecord(d->halo[axis].extracted, d->stream));
+		}
+		for(uint32_t i=0u; i<count; i++) { // 2. unpack what the two neighbours stored
+			luw_domain* d = doms[i];
+			luw_domain::HaloAxis& h = d->halo[axis];
+			DeviceGuard guard(d->p.device);
+			CU(cudaStreamWaitEvent(d->stream, neighbour(i, D[axis]-1u)->halo[axis].extracted, 0));
+			CU(cudaStreamWaitEvent(d->stream, neighbour(i, 1u)->halo[axis].extracted, 0));
+			CU(halo_kernel(d, payload, axis, t, true, true, h.recv_p, h.recv_m));
+			d->launches++;
+			CU(cudaEventRecord(h.inserted, d->stream));
+			h.in_use = true;
+		}
+		return LUW_OK;
+	}
 	// 1. every domain packs its two boundary layers (after its neighbours have taken the previous payloads out of the send buffers)
 	for(uint32_t i=0u; i<count; i++) {
 		luw_domain* d = doms[i];
