@@ -70,7 +70,24 @@ def build(reference_root="/root/reference"):
     deck = re.sub(r"(?m)^cell_size\s*=.*$", "cell_size = 8.0", deck)
     deck = re.sub(r"(?m)^angle\s*=.*$", "angle = [270]", deck)
     open(os.path.join(dst, "conf.luwpf"), "w").write(deck + "\nrun_nstep = 60\n")
-    print("built", exe, "and staged", dst)
+    # the same project with the deck's n_gpu = [2, 2, 2] (the reference's own multi-GPU path: one thread, eight domains, FX/lbm.cpp:1057-1112): a cell size that makes
+    # every extent even (250 x 246 x 58)
+    deck222 = re.sub(r"(?m)^n_gpu\s*=.*$", "n_gpu = [2, 2, 2]", re.sub(r"(?m)^cell_size\s*=.*$", "cell_size = 8.1", deck))
+    open(os.path.join(dst, "conf_222.luwpf"), "w").write(deck222 + "\nrun_nstep = 60\n")
+    # the dataset-generation example (BASELINE configs[4], FX/setup.cpp:5690-5753): 16 inflow directions on a fixed 2.5 m grid (400 x 400 x 200), short runs
+    src = os.path.join(reference_root, "examples", "example_DatasetGen")
+    dst_dg = os.path.join(OUT, "case_dataset")
+    shutil.rmtree(dst_dg, ignore_errors=True)
+    os.makedirs(os.path.join(dst_dg, "proj_temp"))
+    shutil.copy(os.path.join(src, "proj_temp", "DLUTcase_DG.stl"), os.path.join(dst_dg, "proj_temp", "DLUTcase_DG.stl"))
+    os.chmod(os.path.join(dst_dg, "proj_temp", "DLUTcase_DG.stl"), 0o644)
+    dg = open(os.path.join(src, "conf.luwdg")).read()
+    dg = re.sub(r"(?m)^n_gpu\s*=.*$", "n_gpu = [1, 1, 1]", dg)
+    dg = re.sub(r"(?m)^mesh_control\s*=.*$", 'mesh_control = "cell_size"', dg)
+    dg = re.sub(r"(?m)^cell_size\s*=.*$", "cell_size = 2.5", dg)
+    dg = re.sub(r"(?m)^angle\s*=.*$", "angle = [" + ", ".join(str(22.5 * k).rstrip("0").rstrip(".") for k in range(16)) + "]", dg)
+    open(os.path.join(dst_dg, "conf.luwdg"), "w").write(dg + "\nrun_nstep = 300\n")
+    print("built", exe, "and staged", dst, "and", dst_dg)
     return True
 
 

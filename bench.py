@@ -44,6 +44,9 @@ WORKLOADS = {
     "channel512_fp16c": ("channel", (512, 512, 512), 2, F_EQ, "chan", 1.0 / 6.0, "C2 empty channel 512^3 FP16C (LUW's shipped DDF format), SRT nu=1/6"),
     "urban_fp16s": ("urban", (1024, 1024, 256), 1, F_VF | F_EQ | F_SG | F_NUDGE | F_SPONGE, "luwnf", 1e-6,
                     "C3 staggered cube array 1024x1024x256 FP16S, TYPE_E inflow, bounce-back, Coriolis, nudging N=16, sponge N=20, Smagorinsky; rho/u on demand"),
+    # BASELINE configs[3] scale: 1.26 G cells per GPU (69 GB of HBM), 10.07 G cells on 8 GPUs; generated and uploaded slab by slab (no host image of the block)
+    "city10g_fp16s": ("urban", (1024, 1024, 1200), 1, F_VF | F_EQ | F_SG | F_NUDGE | F_SPONGE, "luwnf", 1e-6,
+                      "C4 city-sized domain: staggered cube array, 1024x1024x1200 cells per GPU (10.07 G cells on 8 GPUs) FP16S, TYPE_E inflow, bounce-back, Coriolis, nudging, sponge, Smagorinsky"),
     "urban_fp16s_nz": ("urban", (1024, 1024, 256), 1, F_VF | F_EQ | F_SG, "core", 1e-6,
                        "C3 staggered cube array 1024x1024x256 FP16S without the relaxation zones (cost attribution only)"),
     "urban_fp16s_uf": ("urban", (1024, 1024, 256), 1, F_UF | F_VF | F_EQ | F_SG | F_NUDGE | F_SPONGE, "luw", 1e-6,
@@ -550,10 +553,20 @@ def bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src):
                              omega=OMEGA if features & F_VF else (0.0, 0.0, 0.0), transport=args.transport,
                              **(dict(alpha=THERMAL_ALPHA) if features & F_TEMPERATURE else {}), **zones)
         assert tuple(lbm.Nl) == tuple(shape)
-        flags, rho, u = cases.block_case(case, Ng, lbm.O, shape)
-        T = thermal_fields(flags, shape) if features & F_TEMPERATURE else None  # per-block stratification: a benchmark input, not a physical profile across blocks
-        dist.barrier()  # host-side case generation takes seconds and not the same number on every rank: start the first halo exchange together
-        lbm.initialize(flags, rho, u, T)
+        if int(np.prod(shape)) > 600_000_000:  # C4-sized block: generate and upload 32 planes at a time, the block never exists on the host
+            def slabs():
+                for z0 in range(0, shape[2], 32):
+                    nz = min(32, shape[2] - z0)
+                    fl, rh, uu = cases.block_case(case, Ng, (lbm.O[0], lbm.O[1], lbm.O[2] + z0), (shape[0], shape[1], nz))
+                    yield z0, fl, rh, uu
+            lbm.upload_slabs(slabs())
+            dist.barrier()
+            lbm.initialize()
+        else:
+            flags, rho, u = cases.block_case(case, Ng, lbm.O, shape)
+            T = thermal_fields(flags, shape) if features & F_TEMPERATURE else None  # per-block stratification: a benchmark input, not a physical profile across blocks
+            dist.barrier()  # host-side case generation takes seconds and not the same number on every rank: start the first halo exchange together
+            lbm.initialize(flags, rho, u, T)
         lbm.run(W)
         torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
         launches0, over0 = lbm.domain.launch_count(), lbm.domain.overlapped_steps()

@@ -107,6 +107,12 @@ class Domain:
         count = host.size - offset if count is None else count
         A.check(A.lib().luw_download(self._h, field, _ptr(host[offset:offset + count]), offset, count))
 
+    def upload_range(self, field, values, offset):
+        """Elements [offset, offset + len(values)) of a field's dense host image, from a caller-owned array: lets a case that is generated slab by slab reach the
+        device without a whole-field host image (luw_upload; pageable memory is staged before the call returns)."""
+        values = np.ascontiguousarray(values)
+        A.check(A.lib().luw_upload(self._h, field, _ptr(values), int(offset), int(values.size)))
+
     def _mirrored_fields(self):
         return (A.FIELD_RHO, A.FIELD_U, A.FIELD_FLAGS) + ((A.FIELD_T,) if self.thermal else ())
 

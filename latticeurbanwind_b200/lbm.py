@@ -291,16 +291,32 @@ class DistributedLBM(_Base):
     def _insert(self, payload, axis, rp, rm):
         self.domain.halo_insert(payload, axis, rp.data_ptr(), rm.data_ptr())
 
-    def initialize(self, flags, rho, u, T=None):
-        """flags / rho / u (/ T with TEMPERATURE): LOCAL host images of this rank's domain (halo layers included)."""
+    def upload_slabs(self, slabs):
+        """`slabs`: an iterable of (z0, flags, rho, u) pieces covering the local lattice plane range by plane range (z0 = first local z plane of the piece), uploaded
+        as they come, so that a block of 10^9 cells never needs its 17 B per cell on the host. Follow with initialize() without images."""
+        dom = self.domain
+        plane, N = self.Nl[0] * self.Nl[1], dom.N
+        for z0, fl, rh, uu in slabs:
+            n = fl.size
+            dom.upload_range(A.FIELD_FLAGS, fl, z0 * plane)
+            dom.upload_range(A.FIELD_RHO, rh, z0 * plane)
+            for c in range(3):
+                dom.upload_range(A.FIELD_U, uu[c * n:(c + 1) * n], c * N + z0 * plane)
+            dom.finish_queue()
+
+    def initialize(self, flags=None, rho=None, u=None, T=None):
+        """flags / rho / u (/ T with TEMPERATURE): LOCAL host images of this rank's domain (halo layers included); none at all after upload_slabs()."""
         if self.domain is None:
             raise RuntimeError("DistributedLBM(routing_only=True) has no device domain: the LBM step has no CPU fallback")
         dom = self.domain
-        dom.rho[:], dom.u[:], dom.flags[:] = rho, u, flags
-        if self.thermal and T is not None:
-            dom.T[:] = T
         dom.f, dom.omega = self.f, self.omega
-        dom.upload_all()
+        if flags is None:
+            pass  # the device fields are in place (upload_slabs)
+        else:
+            dom.rho[:], dom.u[:], dom.flags[:] = rho, u, flags
+            if self.thermal and T is not None:
+                dom.T[:] = T
+            dom.upload_all()
         dom.t = 1
         self.communicate(A.HALO_RHO_U_FLAGS, self._extract, self._insert)
         dom.enqueue_initialize()
