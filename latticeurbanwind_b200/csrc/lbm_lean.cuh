@@ -167,6 +167,7 @@ template<class CFG, uint32_t FEAT> __device__ __noinline__ void lean_general_pai
 	const bool e0 = EQ&&run0&&bo0==TYPE_E, e1 = EQ&&run1&&bo1==TYPE_E;
 	PairIn in;
 	in.zones = false;
+	in.e0 = e0; in.e1 = e1; in.any_e = e0||e1; in.n = n; // TYPE_E lanes: rho / u are the boundary fields' (loaded in fast_prepare; prefetched into L2 a tile ago)
 	if(zone_warp) {
 		const ZoneRow zr = zone_row(c, y, z);
 		in.nudge_vertical = c.nudge_vertical;
@@ -225,11 +226,6 @@ template<class CFG, uint32_t FEAT> __device__ __noinline__ void lean_general_pai
 		ld2(3+pl, rp, gip, gjp); ld2(6+pl, rm, gim, gjm);
 		fast_relax_diag(K, pl, gip, gjp, gim, gjm);
 		st2(3+pl, rp, gip, gjp); st2(6+pl, rm, gim, gjm);
-	}
-	if(EQ&&(e0||e1)) { // generic pointers for the out-of-line equilibrium (shared with k_stream_collide_tile)
-		uint8_t* const gb = (uint8_t*)__cvta_shared_to_generic((size_t)bb);
-		uint8_t* const gn = (uint8_t*)__cvta_shared_to_generic((size_t)nxt);
-		fix_equilibrium<CFG, FEAT>(c, a, n, e0, e1, scale, gb, gn, odd_end);
 	}
 }
 
@@ -460,6 +456,8 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 			if(!slow) { // ---------------- fast body: 64 cells that all execute
 				PairIn in;
 				in.zones = false;
+				in.any_e = EQ&&__any_sync(0xFFFFFFFFu, e2!=0u); // warp-uniform: the selects of the TYPE_E lanes stay out of the common path
+				in.e0 = (e2&0x00FFu)!=0u; in.e1 = (e2&0xFF00u)!=0u; in.n = (uint64_t)x+(uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny); // pure functions of live values: rematerialised where fast_prepare needs them. The TYPE_E lanes' rho / u are the boundary fields, loaded there (prefetched into L2 a tile ago)
 				if(zone_warp) { // relaxation-zone data first: its global loads are in flight while the moments are accumulated
 					const uint64_t n_row = (uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny);
 					const ZoneRow zr = zone_row(c, y, z);
@@ -518,10 +516,6 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 				const Raw r5 = fetch(5), r8 = fetch(8);
 				diag(1, r4, r7);
 				diag(2, r5, r8);
-				if(e2!=0u) { // TYPE_E lanes: f := feq of the boundary fields, element by element (out of line; generic pointers, shared with k_stream_collide_tile)
-					const uint64_t n = (uint64_t)x+(uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny);
-					fix_equilibrium<CFG, FEAT>(c, a, n, (e2&0x00FFu)!=0u, (e2&0xFF00u)!=0u, scale, (uint8_t*)__cvta_shared_to_generic((size_t)bb), (uint8_t*)__cvta_shared_to_generic((size_t)nxt));
-				}
 			} else lean_general_pair<CFG, FEAT>(c, a, bb, nxt, fl2, x, y, z, zone_warp, last&&(lc.flags&LC_ODD_X)!=0u&&lx==lc.rowend_last);
 		}
 		if(bnd_yz) { // write the wrapped elements back to their real addresses (TMA clips them)

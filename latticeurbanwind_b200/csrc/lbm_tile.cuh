@@ -291,34 +291,6 @@ template<uint32_t FEAT> __device__ __forceinline__ void equilibrium_cell(const D
 	}
 }
 
-// Two-pass FAST path: TYPE_E lanes run through the packed collision like any other cell and are overwritten afterwards, element by element, with
-// f := feq(boundary rho, u) (FX/kernel.cpp:1503-1515,1747). Out of line: it runs in the few warps that touch an open face, and keeping it (and a
-// second, select-carrying copy of the collision) out of the loop body keeps the loop inside the instruction cache (profiles/r1_ncu_urban_fp16s.md).
-// `raw16`: FP16S values are stored as the half of the already scaled number (scale = 2^15).
-// `odd_end`: odd Nx, the row's last pair -- cell 0's +x element is `nxt` (see PairCodec::shift_in_odd).
-template<class CFG, uint32_t FEAT> __device__ __noinline__ void fix_equilibrium(const DomainConst& c, const StepArgs& a, const uint64_t n, const bool e0, const bool e1, const float scale, uint8_t* bb, uint8_t* nxt, const bool odd_end = false) {
-	typedef typename PairCodec<CFG::P>::E E;
-	const auto enc1 = [&](const float v) -> E {
-		if constexpr (CFG::P==P_FP32) return v;
-		else if constexpr (CFG::P==P_FP16S) return __half_as_ushort(__float2half_rn(v)); // v carries the 2^15
-		else return Ddf<P_FP16C>::enc(v);
-	};
-#pragma unroll 1
-	for(uint32_t l=0u; l<2u; l++) {
-		if(!(l==0u ? e0 : e1)) continue;
-		const uint64_t m = n+(uint64_t)l;
-		float feq[Q];
-		equilibrium_cell<FEAT>(c, a, c.rho[m], c.u[m], c.u[c.N+m], c.u[2ull*c.N+m], scale, feq);
-		((E*)bb)[l] = enc1(feq[0]);
-#pragma unroll
-		for(int k=0; k<9; k++) {
-			((E*)(bb+CFG::box_off(1+2*k)))[l] = enc1(feq[2*k+2]); // slot A receives f_i+1
-			if(pair_shifted(k)) { if(l==0u&&!odd_end) ((E*)(bb+CFG::box_off(2+2*k)))[1] = enc1(feq[2*k+1]); else *(E*)(nxt+CFG::box_off(2+2*k)) = enc1(feq[2*k+1]); }
-			else ((E*)(bb+CFG::box_off(2+2*k)))[l] = enc1(feq[2*k+1]); // slot B receives f_i
-		}
-	}
-}
-
 // thermal step in two kernels (DomainConst::upre): the pair's velocity before the force half-step; w0 / w1: the cell executes and is not TYPE_E (k_thermal_g takes u of TYPE_E cells from the boundary field)
 __device__ __forceinline__ void store_upre(const DomainConst& c, const uint64_t n, const bool w0, const bool w1, const PairOut& o) {
 	if(w0&&w1) { *(float2*)(c.upre+n) = o.upx.v; *(float2*)(c.upre+c.N+n) = o.upy.v; *(float2*)(c.upre+2ull*c.N+n) = o.upz.v; }
@@ -554,6 +526,7 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 				uint8_t* const bb = (uint8_t*)box;
 				const auto dec_in = [](const R w) -> f2 { if constexpr (P==P_FP16S) return PairCodec<P_FP16S>::dec_raw(w); else return PC::dec(w); };
 				const auto enc_out = [](const f2 v) -> R { if constexpr (P==P_FP16S) return PairCodec<P_FP16S>::enc_raw(v); else if constexpr (P==P_FP16C) return PairCodec<P_FP16C>::enc_fast(v); else return PC::enc(v); };
+				in.e0 = e0; in.e1 = e1; in.any_e = e0||e1; in.n = n; // TYPE_E lanes: rho / u are the boundary fields' (loaded in fast_prepare; prefetched into L2 a tile ago)
 				Moments M;
 				const f2 g0 = dec_in(*(const R*)bb);
 				const auto ld1 = [&](const int k, f2& gi, f2& gj) {
@@ -599,7 +572,6 @@ k_stream_collide_tile(const __grid_constant__ DomainConst c, const __grid_consta
 					fast_relax_diag(K, pl, gip, gjp, gim, gjm);
 					st2(3+pl, rp, gip, gjp); st2(6+pl, rm, gim, gjm);
 				}
-				if(EQ&&(e0||e1)) fix_equilibrium<CFG, FEAT>(c, a, n, e0, e1, scale, bb, nxt, odd_end);
 			} else {
 			// load_f: box 0 -> f0, box 1+2k -> f_(2k+1), box 2+2k -> f_(2k+2)
 			f2 f[Q];

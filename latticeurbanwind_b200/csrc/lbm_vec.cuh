@@ -102,6 +102,8 @@ __device__ __forceinline__ void zone_apply(const ZoneRef& r, const int nudge_ver
 }
 
 struct PairIn { // what the step needs to know about the two cells besides their DDFs
+	uint64_t n; // FAST two-pass, any_e: device index of the pair's first cell (the TYPE_E lanes' rho / u are loaded where they are needed: no registers are held across the moment pass)
+	bool any_e; // FAST two-pass: e0 || e1 -- or, where the caller can afford a vote, "some lane of the warp holds a TYPE_E cell" (a warp-uniform branch then keeps the selects out of the common path)
 	bool e0, e1; // FAST only: lane holds a TYPE_E cell -> rho/u are the boundary values below and f := feq (STRICT redoes such lanes in scalar code, lbm_tile.cuh)
 	f2 rho_e, ux_e, uy_e, uz_e;
 	bool zones; // some lane lies in a relaxation zone
@@ -356,12 +358,24 @@ template<bool SG, class LD> __device__ __forceinline__ void moments_of(const f2 
 struct FastK { f2 omw, g0add, UA[3], B[3], E[3], X[3]; }; // see the derivation above; planes: 0 = (x,y), 1 = (x,z), 2 = (y,z)
 template<uint32_t FEAT> __device__ __forceinline__ void fast_prepare(const DomainConst& c, const StepArgs& a, const PairIn& in, const Moments& M, const float scale, const float inv, FastK& K, PairOut& out) {
 	constexpr bool VF = (FEAT&F_VOLUME_FORCE)!=0u, SG = (FEAT&F_SUBGRID)!=0u;
-	const f2 rhom1 = inv*M.R;
-	const f2 rho = rhom1+bc(1.0f);
+	constexpr bool EQ = (FEAT&F_EQUILIBRIUM)!=0u;
+	// TYPE_E lanes (FX/kernel.cpp:1503-1515, 1747): rho / u are the boundary fields' values, the force half-step and the clamp apply, f := feq -- which is this relaxation
+	// with rate 1 and without the forcing term: (1-w) = 0 wipes the streamed-in DDFs, U +- V is the equilibrium. A handful of selects instead of a scalar f_eq per cell.
+	const bool any_e = EQ&&in.any_e;
+	f2 rhom1 = inv*M.R;
+	f2 rho = rhom1+bc(1.0f);
+	if(any_e) { // a non-TYPE_E partner keeps its own values: its result must not depend on who it is paired with
+		const f2 rho_e = mk2(in.e0 ? c.rho[in.n] : 1.0f, in.e1 ? c.rho[in.n+1ull] : 1.0f);
+		rho = sel2(in.e0, in.e1, rho_e, rho); rhom1 = sel2(in.e0, in.e1, rho_e-bc(1.0f), rhom1);
+	}
 	f2 ir = rcp2(rho);
 	ir = fma2(ir, fma2(-rho, ir, bc(1.0f)), ir); // one Newton step: full single precision
 	const f2 iri = inv*ir;
 	f2 ux = M.mx*iri, uy = M.my*iri, uz = M.mz*iri;
+	if(any_e) {
+		if(in.e0) { ux.v.x = c.u[in.n]; uy.v.x = c.u[c.N+in.n]; uz.v.x = c.u[2ull*c.N+in.n]; }
+		if(in.e1) { ux.v.y = c.u[in.n+1ull]; uy.v.y = c.u[c.N+in.n+1ull]; uz.v.y = c.u[2ull*c.N+in.n+1ull]; }
+	}
 	out.upx = ux; out.upy = uy; out.upz = uz;
 	Proj F; F.x = F.y = F.z = bc(0.0f);
 	f2 uF = bc(0.0f);
@@ -389,6 +403,7 @@ template<uint32_t FEAT> __device__ __forceinline__ void fast_prepare(const Domai
 		id = fma2(id, fma2(-den, id, bc(1.0f)), id);
 		w = 2.0f*id;
 	}
+	if(any_e) w = sel2(in.e0, in.e1, bc(1.0f), w);
 	K.omw = bc(1.0f)-w;
 	const float swe = scale*WE;
 	const f2 wr = w*rho;
@@ -397,7 +412,8 @@ template<uint32_t FEAT> __device__ __forceinline__ void fast_prepare(const Domai
 	Proj G, H;
 	f2 K0;
 	if(VF) {
-		const f2 ct = fma2(w, -0.5f, bc(1.0f));
+		f2 ct = fma2(w, -0.5f, bc(1.0f));
+		if(any_e) ct = sel2(in.e0, in.e1, bc(0.0f), ct);
 		const f2 cfx = ct*F.x, cfy = ct*F.y, cfz = ct*F.z;
 		G.x = fma2(wr, ux, cfx); G.y = fma2(wr, uy, cfy); G.z = fma2(wr, uz, cfz);
 		H.x = G.x+cfx; H.y = G.y+cfy; H.z = G.z+cfz;

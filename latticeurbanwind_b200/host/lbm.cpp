@@ -41,19 +41,6 @@ static void settings_from_case_driver() {
 #endif
 }
 float3 vtk_origin_shift = float3(0.0f, 0.0f, 0.0f); // FX/lbm.cpp:18-20
-// Device memory of THIS build per domain: DDFs (19 fpxx) + rho, u (16 B) + flags (1 B) per cell of the padded local lattice, + halo buffers. The reference's
-// estimator (FX/lbm.cpp:143-232) counts its own buffer set (F, gi, T, graphics, transfer buffers): a deck with mesh_control="gpu_memory" therefore resolves to a
-// finer grid here than there for the same number of MB -- use mesh_control="cell_size" where the grid must be identical (SURVEY.md Appendix C).
-uint vram_required_mb_per_device(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz) {
-	const ulong lx = (ulong)(Nx/Dx+2u*(Dx>1u)), ly = (ulong)(Ny/Dy+2u*(Dy>1u)), lz = (ulong)(Nz/Dz+2u*(Dz>1u));
-	const ulong px = (lx+15ull)&~15ull;
-	const ulong ddf = (env_uint("LUW_PRECISION", lbm_settings.precision)==LUW_FP32) ? 4ull : 2ull;
-	const ulong cells = px*ly*lz;
-	const ulong halo = 8ull*(ddf==4ull ? 20ull : 17ull)*((Dx>1u ? ly*lz : 0ull)+(Dy>1u ? lz*lx : 0ull)+(Dz>1u ? lx*ly : 0ull));
-	const ulong thermal = (lbm_settings.features&LUW_TEMPERATURE) ? 7ull*ddf+4ull : 0ull; // gi + T (FX/lbm.cpp:124-126)
-	return (uint)((cells*(19ull*ddf+17ull+thermal)+halo)/1048576ull)+1u;
-}
-uint vram_required_mb_total(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz) { return Dx*Dy*Dz*vram_required_mb_per_device(Nx, Ny, Nz, Dx, Dy, Dz); }
 string default_filename(const string& path, const string& name, const string& extension, const ulong t) { // FX/lbm.cpp:235-239: <path or exe/export/><name>-<9-digit step><extension>
 	string time = "00000000"+to_string(t);
 	time = substring(time, length(time)-9u, 9u);
@@ -67,6 +54,19 @@ uint bytes_per_cell_host() { return 17u+(thermal_on() ? 4u : 0u); }
 uint bytes_per_cell_device() { return 19u*ddf_bytes()+17u+(thermal_on() ? 7u*ddf_bytes()+4u : 0u); }
 uint bandwidth_bytes_per_cell_device() { return 38u*ddf_bytes()+1u+((lbm_settings.features&LUW_UPDATE_FIELDS) ? 16u : 0u)+(thermal_on() ? 14u*ddf_bytes()+((lbm_settings.features&LUW_UPDATE_FIELDS) ? 4u : 0u) : 0u); } // + 7 g loads + 7 g stores (+ T), FX/lbm.cpp:127-128
 #endif // LUW_USE_REFERENCE_UTILITIES
+// Device memory of THIS build per domain: DDFs (19 fpxx) + rho, u (16 B) + flags (1 B) per cell of the padded local lattice, + halo buffers. The reference's
+// estimator (FX/lbm.cpp:143-232) counts its own buffer set (F, gi, T, graphics, transfer buffers): a deck with mesh_control="gpu_memory" therefore resolves to a
+// finer grid here than there for the same number of MB -- use mesh_control="cell_size" where the grid must be identical (SURVEY.md Appendix C).
+uint vram_required_mb_per_device(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz) {
+	const ulong lx = (ulong)(Nx/Dx+2u*(Dx>1u)), ly = (ulong)(Ny/Dy+2u*(Dy>1u)), lz = (ulong)(Nz/Dz+2u*(Dz>1u));
+	const ulong px = (lx+15ull)&~15ull;
+	const ulong ddf = (env_uint("LUW_PRECISION", lbm_settings.precision)==LUW_FP32) ? 4ull : 2ull;
+	const ulong cells = px*ly*lz;
+	const ulong halo = 8ull*(ddf==4ull ? 20ull : 17ull)*((Dx>1u ? ly*lz : 0ull)+(Dy>1u ? lz*lx : 0ull)+(Dz>1u ? lx*ly : 0ull));
+	const ulong thermal = (lbm_settings.features&LUW_TEMPERATURE) ? 7ull*ddf+4ull+12ull : 0ull; // gi + T (FX/lbm.cpp:124-126) + the pre-force velocity of the two-kernel thermal step
+	return (uint)((cells*(19ull*ddf+17ull+thermal)+halo)/1048576ull)+1u;
+}
+uint vram_required_mb_total(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz) { return Dx*Dy*Dz*vram_required_mb_per_device(Nx, Ny, Nz, Dx, Dy, Dz); }
 
 uint LBM_Domain::lbm_features() { return lbm_settings.features; }
 
@@ -188,10 +188,46 @@ void LBM::construct(const uint Nx_, const uint Ny_, const uint Nz_, const uint D
 	luw_check(luw_device_count(&ndev));
 	if(ndev<1) print_error("No CUDA device is available; this build of the LBM has no CPU fallback.");
 	const uint Hx = Dx>1u, Hy = Dy>1u, Hz = Dz>1u; // halo offsets, FX/lbm.cpp:1062-1064
+	// Device assignment, smart_device_selection of FX/lbm.cpp:947-1034: D cards of ONE model, the fastest model that has D of them, never two domains on one card --
+	// except that a box with fewer cards than domains is not an error here but a warning (several domains then share a device round robin; the parity tests run
+	// 2 x 2 x 2 decompositions on one GPU that way; LUW_STRICT_DEVICES=1 restores the reference's error). lbm_settings.devices overrides the selection.
+	std::vector<int> chosen(D, 0);
+	{
+		std::vector<luw_device_info> info((size_t)ndev);
+		for(int i=0; i<ndev; i++) luw_check(luw_get_device_info(i, &info[(size_t)i]));
+		if((int)D>ndev) {
+			const std::string msg = "Domain partition count ("+std::to_string(D)+") exceeds available physical cards ("+std::to_string((uint)ndev)+").";
+			if(env_uint("LUW_STRICT_DEVICES", 0u)) print_error(msg+" Reduce Dx*Dy*Dz to <= "+std::to_string((uint)ndev)+".");
+			fprintf(stderr, "[luw] warning: %s Domains share devices round robin.\n", msg.c_str());
+			for(uint d=0u; d<D; d++) chosen[d] = (int)(d%(uint)ndev);
+		} else {
+			int best = -1; double best_value = -1.0; // "tflops" of a card: SMs x clock (all models here have the same lanes per SM)
+			for(int i=0; i<ndev; i++) {
+				int same = 0;
+				for(int k=0; k<ndev; k++) same += std::string(info[(size_t)k].name)==std::string(info[(size_t)i].name);
+				const double value = (double)info[(size_t)i].compute_units*(double)info[(size_t)i].clock_mhz;
+				if(same>=(int)D&&value>best_value) { best_value = value; best = i; }
+			}
+			uint d = 0u;
+			if(best>=0) { for(int i=0; i<ndev&&d<D; i++) if(std::string(info[(size_t)i].name)==std::string(info[(size_t)best].name)) chosen[d++] = i; }
+			else for(int i=0; i<ndev&&d<D; i++) chosen[d++] = i; // mixed models without oversubscription
+		}
+		// VRAM preflight, sanity_checks_constructor of FX/lbm.cpp:1123-1140: the message of the reference, before anything is allocated
+		uint memory_available = 0xFFFFFFFFu;
+		std::vector<uint> share((size_t)ndev, 0u);
+		for(uint d=0u; d<D; d++) { const int dev = d<lbm_settings.devices.size() ? lbm_settings.devices[d] : chosen[d]; if(dev>=0&&dev<ndev) share[(size_t)dev]++; }
+		for(int i=0; i<ndev; i++) if(share[(size_t)i]>0u) memory_available = std::min(memory_available, (uint)(info[(size_t)i].memory_bytes/1048576ull)/share[(size_t)i]);
+		const uint memory_required = vram_required_mb_per_device(Nx, Ny, Nz, Dx, Dy, Dz);
+		if(memory_required>memory_available) {
+			const float factor = cbrtf((float)memory_available/(float)memory_required);
+			print_error("Grid resolution ("+std::to_string(Nx)+", "+std::to_string(Ny)+", "+std::to_string(Nz)+") is too large: "+std::to_string(D)+"x "+std::to_string(memory_required)+" MB required, "+std::to_string(D)+"x "+std::to_string(memory_available)
+				+" MB available. Largest possible resolution is ("+std::to_string((uint)(factor*(float)Nx))+", "+std::to_string((uint)(factor*(float)Ny))+", "+std::to_string((uint)(factor*(float)Nz))+"). Restart the simulation with lower resolution or on different device(s) with more memory.");
+		}
+	}
 	lbm_domain = new LBM_Domain*[D];
 	for(uint d=0u; d<D; d++) {
 		const uint x = (d%(Dx*Dy))%Dx, y = (d%(Dx*Dy))/Dx, z = d/(Dx*Dy); // d = x+(y+z*Dy)*Dx, FX/lbm.cpp:1066-1073
-		const int device = d<lbm_settings.devices.size() ? lbm_settings.devices[d] : (int)(d%(uint)ndev);
+		const int device = d<lbm_settings.devices.size() ? lbm_settings.devices[d] : chosen[d];
 		lbm_domain[d] = new LBM_Domain(device, Nx/Dx+2u*Hx, Ny/Dy+2u*Hy, Nz/Dz+2u*Hz, Dx, Dy, Dz, (int)(x*Nx/Dx)-(int)Hx, (int)(y*Ny/Dy)-(int)Hy, (int)(z*Nz/Dz)-(int)Hz, nu, fx, fy, fz, alpha, beta);
 		handles.push_back(lbm_domain[d]->get_handle());
 		if(LBM_Domain::thermal()) T_buffers.push_back(&lbm_domain[d]->T);

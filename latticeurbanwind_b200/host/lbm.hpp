@@ -53,8 +53,6 @@ constexpr ulong max_ulong = 18446744073709551615ull;
 #include <fstream>
 #include <thread>
 extern float3 vtk_origin_shift; // VTK origin shift in SI units (FX/lbm.hpp:10, set by the case driver FX/setup.cpp:4083)
-uint vram_required_mb_per_device(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz); // FX/lbm.hpp:17-18 -- for THIS build's buffers
-uint vram_required_mb_total(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz);
 string default_filename(const string& path, const string& name, const string& extension, const ulong t); // FX/lbm.cpp:235-242
 string default_filename(const string& name, const string& extension, const ulong t);
 uint bytes_per_cell_host(); // FX/lbm.hpp:13-15, for THIS build's buffers and the precision in use
@@ -64,6 +62,8 @@ struct LBM_Device_Info { uint id = 0u; string name = ""; uint memory = 0u, memor
 struct Device { LBM_Device_Info info; luw_domain* dom = nullptr; }; // what LBM_Domain::get_device() hands out (reference: the OpenCL Device, FX/opencl.hpp:274): its info block + the C-ABI handle
 #endif // LUW_USE_REFERENCE_UTILITIES
 
+uint vram_required_mb_per_device(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz); // FX/lbm.hpp:17-18 -- for THIS build's buffers
+uint vram_required_mb_total(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz);
 // Run-time replacement of FX/defines.hpp + the constants of FX/lbm.cpp:612-783. Set the global `lbm_settings` before constructing an LBM
 // (the case driver does that where the reference's update_coriolis / update_buffer_nudging / update_top_sponge set their globals, FX/setup.cpp:3800-3903).
 struct LBM_Settings {

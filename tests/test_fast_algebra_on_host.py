@@ -24,6 +24,8 @@ def vec_lib():
     L = C.CDLL(os.path.join(HERE, "host_emulation", "libluw_vec_on_host.so"))
     L.emu_fast_vs_strict.argtypes = [C.c_uint32, C.c_uint64, C.c_void_p, C.c_float, C.c_void_p, C.c_float] + [C.c_void_p] * 4
     L.emu_fast_vs_strict.restype = C.c_int
+    L.emu_fast_equilibrium.argtypes = [C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p]
+    L.emu_fast_equilibrium.restype = C.c_int
     return L
 
 
@@ -58,3 +60,30 @@ def test_fast_two_pass_algebra_matches_the_as_written_collision(vec_lib, feat, s
         ref = float(np.abs(strict).max())
         assert 0.01 < ref < 1.0 and err <= 3e-7, (feat, w, err, ref)
         assert float(np.abs(ru_f.astype(np.float64) - ru_s).max()) <= 4e-7, (feat, w)
+
+
+@pytest.mark.parametrize("scale", [1.0, 32768.0], ids=["S1", "S2^15"])
+@pytest.mark.parametrize("feat", [4, 14, 15])
+def test_type_e_lanes_relax_to_the_equilibrium_of_the_boundary_fields(vec_lib, feat, scale):
+    """FX/kernel.cpp:1503-1522, 1747: a TYPE_E cell takes rho / u from the boundary fields, applies the force half-step (Coriolis) and the clamp, and sets f := feq.
+    The FAST two-pass path does that as the relaxation with rate 1 and without forcing term (fast_prepare, `any_e`): whatever was streamed in must be wiped."""
+    npairs = 3000
+    rng = np.random.default_rng(77 + feat)
+    f = seeded_ddfs(npairs, 5000 + feat) * np.float32(3.0)  # what the TYPE_E cells' slots hold does not matter
+    bnd = np.zeros((2 * npairs, 4), np.float32)
+    bnd[:, 0] = 1.0 + 1e-2 * rng.standard_normal(2 * npairs)
+    bnd[:, 1:] = 0.12 * (2.0 * rng.random((2 * npairs, 3)) - 1.0)
+    fo = np.array([1e-5, -2e-5, 3e-5, 0.0, 5.6e-6, 4.7e-6], np.float32)
+    out = np.zeros(npairs * 2 * Q, np.float32)
+    rc = vec_lib.emu_fast_equilibrium(feat, npairs, f.ctypes.data, bnd.ctypes.data, C.c_float(1.9999992), fo.ctypes.data, C.c_float(scale), out.ctypes.data)
+    assert rc == 0 and np.isfinite(out).all()
+    rho, u = bnd[:, 0].astype(np.float64), bnd[:, 1:].astype(np.float64)
+    if feat & 2:  # VOLUME_FORCE: F = f - 2 rho Omega x u, u += F / (2 rho), clamp to +-c
+        om = fo[3:].astype(np.float64)
+        F = fo[:3].astype(np.float64) - 2.0 * rho[:, None] * np.cross(np.broadcast_to(om, u.shape), u)
+        u = u + F / (2.0 * rho[:, None])
+    u = np.clip(u, -0.57735027, 0.57735027)
+    cu = 3.0 * (u[:, :1] * CX + u[:, 1:2] * CY + u[:, 2:3] * CZ)
+    feq = W * rho[:, None] * (1.0 + cu + 0.5 * cu * cu - 1.5 * (u ** 2).sum(1, keepdims=True)) - W
+    err = float(np.abs(out.reshape(-1, Q).astype(np.float64) - feq).max())
+    assert err <= 3e-7, (feat, scale, err)
