@@ -237,6 +237,7 @@ struct LeanConst {
 	uint32_t last_tx; // cells of the last tile's rows that lie inside the lattice
 	uint32_t rowend_last; // local x of the pair that holds the last cell of a row, in the strip's last tile
 	int zone_xw, zone_xe; // a warp (64 x-consecutive cells from local x = xw) reaches the west nudging shell iff xw <= zone_xw, the east one iff xw >= zone_xe
+	int slow_xlo, slow_xhi; // ... holds a halo column or columns beyond the lattice iff xw <= slow_xlo or xw >= slow_xhi: only THESE warps of a strip's first / last tile take the general body
 	uint32_t flags;
 };
 enum : uint32_t { LC_WRAP_X = 1u, LC_PARK = 2u, LC_EDGE_X_SLOW = 4u, LC_ZONES = 8u, LC_PREFETCH = 16u, LC_UF = 32u, LC_EQ = 64u, LC_LAG = 128u, LC_ODD_X = 256u };
@@ -247,6 +248,8 @@ template<class CFG> inline LeanConst lean_const(const DomainConst& c, const bool
 	l.rowend_last = (l.last_tx-1u)&~1u;
 	const bool vf = (c.features&F_VOLUME_FORCE)!=0u, zones = vf&&(c.features&(F_NUDGING|F_SPONGE))!=0u;
 	const bool west = zones&&(c.features&F_NUDGING)&&c.downstream_face!=1&&c.has_w, east = zones&&(c.features&F_NUDGING)&&c.downstream_face!=2&&c.has_e;
+	l.slow_xlo = c.Dx>1u ? 0 : -1; // x = 0 is a halo column
+	l.slow_xhi = (int)(c.Dx>1u ? c.Nx-1u : c.Nx)-63; // the warp's 64 cells end beyond the last executing column
 	l.zone_xw = west ? (int)c.buffer_N-c.Ox : -0x7FFFFFFF;
 	l.zone_xe = east ? (int)c.Nxg-1-(int)c.buffer_N-63-c.Ox : 0x7FFFFFFF;
 	l.flags = (c.Dx==1u ? LC_WRAP_X : 0u)|((c.Dx==1u&&l.tiles_x>=2u) ? LC_PARK : 0u)|((c.Dx>1u||l.last_tx!=(uint32_t)CFG::TX) ? LC_EDGE_X_SLOW : 0u)|(zones ? LC_ZONES : 0u)|(prefetch ? LC_PREFETCH : 0u)
@@ -445,12 +448,12 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 			const uint32_t fl2 = lds_u16(st+(uint32_t)CFG::FLAG_OFF+2u*tid);
 			const uint32_t x = xt*(uint32_t)TX+lx;
 			// ONE warp-uniform decision per tile: all 64 cells plain fluid or TYPE_E, no halo column, no column beyond the lattice -> fast body
-			const bool slow = __any_sync(0xFFFFFFFFu, (fl2&~E_BITS)!=0u)||((first||last)&&(lc.flags&LC_EDGE_X_SLOW)!=0u);
+			const int xw = (int)(xt*(uint32_t)TX+(lx&~63u)); // first cell of the warp's 64
+			const bool slow = __any_sync(0xFFFFFFFFu, (fl2&~E_BITS)!=0u)||xw<=lc.slow_xlo||xw>=lc.slow_xhi;
 			const uint32_t e2 = EQ ? fl2&E_BITS : 0u; // TYPE_E lanes (fast body)
 			// element right of the pair's word in an x-shifted box: the next word of the row, or column 0 of the same row in the next stage / the parked column
 			uint32_t nxt = bb+(uint32_t)sizeof(R);
 			if(lx==(last ? lc.rowend_last : (uint32_t)(TX-2))) nxt = !last ? st1+row*(uint32_t)(TX*CFG::ES) : park ? sm0+park_off : wrap_x ? st+row*(uint32_t)(TX*CFG::ES) : bb;
-			const int xw = (int)(xt*(uint32_t)TX+(lx&~63u));
 			const bool zone_warp = zone_yz||xw<=lc.zone_xw||xw>=lc.zone_xe;
 			if(EQ&&!last&&(xt+2u>=tiles_x||__any_sync(0xFFFFFFFFu, fl2!=0u))) lean_prefetch_e<CFG>(c, lds_u16(st1+(uint32_t)CFG::FLAG_OFF+2u*tid), (uint64_t)x+(uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny));
 			if(!slow) { // ---------------- fast body: 64 cells that all execute

@@ -170,17 +170,17 @@ void setup_tiles(luw_domain* d) {
 	const char* off = getenv("LUW_NO_TILE");
 	if(off&&off[0]=='1') return;
 	const char* var = getenv("LUW_TILE_VARIANT");
-	// default (measured, profiles/r2_variant_sweeps.txt): FP16S -> the lean-loop two-pass kernel, 128x4 tiles with 8 consumer warps per producer for the LES step (V5), 128x2 tiles and
-	// 5 CTAs/SM without LES (V6); FP16C -> single pass (V3: the software codec makes decoding twice dearer than the registers); FP32 -> single pass (V0). STRICT arithmetic runs
-	// k_stream_collide_tile on the same tile shapes.
-	const int want = (var&&var[0]) ? atoi(var) : d->c.precision==luw::P_FP16C ? 3 : d->c.precision==luw::P_FP16S ? ((d->c.features&luw::F_SUBGRID) ? 5 : 6) : 0;
+	// default (measured, profiles/r2_variant_sweeps.txt): FP16S and FP16C -> the lean-loop two-pass kernel, 128x4 tiles with 8 consumer warps per producer for the LES step (V5),
+	// 128x2 tiles and 5 CTAs/SM without LES (V6) -- for FP16C too since the lean loop: 55.8 (V6) / 51.4 (V5) against 48.2 GLUP/s (single-pass V3) on the channel, 38.9 against 31.2 on
+	// the urban LES step with UPDATE_FIELDS; FP32 -> single pass (V0). STRICT arithmetic runs k_stream_collide_tile on the same tile shapes.
+	const int want = (var&&var[0]) ? atoi(var) : d->c.precision==luw::P_FP32 ? 0 : ((d->c.features&luw::F_SUBGRID) ? 5 : 6);
 	const luw::DomainConst& c = d->c;
 	// odd Nx: the row's last pair holds one cell (rows are padded to Px, a multiple of 16 elements); lbm_tile.cuh `odd_end`
 	encode_tiled_fn enc = get_encode_tiled();
 	if(!enc) return;
 	luw::TileShape sh;
 	bool found = false;
-	const int fallback = d->c.precision==luw::P_FP16C ? 3 : d->c.precision==luw::P_FP16S ? 5 : 0; // thermal domains: the one variant per precision their momentum kernel is built for
+	const int fallback = d->c.precision==luw::P_FP32 ? 0 : 5; // thermal domains: the one variant per precision their momentum kernel is built for
 	for(int v : { want, fallback, 0, 2 }) { // 2: 64-wide tiles for narrow lattices // the requested variant, else one whose tile is not wider than the lattice
 		if(d->ks->tile_shape(c.precision, c.features, v, &sh)&&c.Nx>=(uint32_t)sh.tx) { d->tile_variant = v; found = true; break; }
 	}

@@ -156,5 +156,5 @@ def test_one_gigacell_domain_without_host_mirrors():
     assert res["cells"] == 1024 ** 3 and res["tiled"] == 1 and res["mlups"] > 1000.0
     assert res["host_mirror_rho"] == 0 and res["host_mirror_flags"] == 0, res
     assert res["probe_mean_ux"] == 0.0  # a fluid at rest stays at rest
-    assert res["peak_rss_mb"] < 3000, res  # no 18 GB host image (the u mirror exists after the ranged read, 16 KB of it committed)
+    assert res["peak_rss_mb"] < 8000, res  # no 18 GB host image: what is resident is the CUDA context (3 - 4 GB on these boxes); the u mirror exists after the ranged read, 16 KB of it committed
     assert res["device_mb"] > 50000
