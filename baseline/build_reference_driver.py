@@ -6,8 +6,8 @@ shapes.cpp, graphics.cpp (GRAPHICS off), lodepng.cpp, all UNMODIFIED and compile
 
 How the reference's `#include "lbm.hpp"` is made to find our header without touching or copying its sources: the translation units are compiled through a
 farm of symbolic links in a temporary directory (GCC resolves a quoted include relative to the directory named in the including file's path), in which
-lbm.hpp is a two-line shim and defines.hpp is a generated variant with GRAPHICS / TEMPERATURE / FORCE_FIELD commented out (not part of this path, DESIGN.md
-section 6). Only the binary and a staged copy of the example project (deck, STL, wind profile: input DATA) are written, under baseline/_ref/ (git-ignored).
+lbm.hpp is a two-line shim and defines.hpp is a generated variant with GRAPHICS / FORCE_FIELD commented out (not part of this path) -- and
+TEMPERATURE commented out in luw_reference_driver, left on (as LUW ships it) in luw_reference_driver_T. Only the binary and a staged copy of the example project (deck, STL, wind profile: input DATA) are written, under baseline/_ref/ (git-ignored).
 
     python baseline/build_reference_driver.py [/root/reference]
 """
@@ -30,28 +30,32 @@ def build(reference_root="/root/reference"):
         print("reference tree not present: keeping the prebuilt baseline/_ref (if any)")
         return False
     os.makedirs(OUT, exist_ok=True)
-    with tempfile.TemporaryDirectory() as tmp:
-        for name in os.listdir(fx):
-            if name in ("lbm.hpp", "lbm.cpp", "opencl.hpp", "kernel.cpp", "kernel.hpp", "defines.hpp") or not (name.endswith(".cpp") or name.endswith(".hpp")):
-                continue
-            os.symlink(os.path.join(fx, name), os.path.join(tmp, name))
-        defines = open(os.path.join(fx, "defines.hpp")).read()
-        # LUW_DROPIN_TEMPERATURE=1 leaves the reference's TEMPERATURE switch on: setup.cpp's 19 TEMPERATURE blocks then compile against lbm.T / alpha / beta of the host
-        # layer and the LBM runs LUW_TEMPERATURE domains. Off by default until the thermal kernels have been observed on a B200.
-        off = ("GRAPHICS", "FORCE_FIELD") if os.environ.get("LUW_DROPIN_TEMPERATURE") == "1" else ("GRAPHICS", "TEMPERATURE", "FORCE_FIELD")
-        for flag in off:
-            defines = re.sub(r"(?m)^#define %s\b" % flag, "//#define %s" % flag, defines)
-        open(os.path.join(tmp, "defines.hpp"), "w").write(defines)
-        host = os.path.join(ROOT, "latticeurbanwind_b200", "host")
-        open(os.path.join(tmp, "lbm.hpp"), "w").write('#pragma once\n#include "utilities.hpp"\n#define LUW_USE_REFERENCE_UTILITIES\n#include "%s/lbm.hpp"\n' % host)
-        open(os.path.join(tmp, "our_lbm.cpp"), "w").write('#include "utilities.hpp"\n#define LUW_USE_REFERENCE_UTILITIES\n#include "%s/lbm.cpp"\n' % host)
-        flags = ["-std=c++17", "-pthread", "-O", "-Wno-comment", "-w", "-I."]  # the reference's own flags (FX/../makefile:1-3)
-        procs = [(u, subprocess.Popen(["g++", *flags, "-c", u + ".cpp", "-o", u + ".o"], cwd=tmp)) for u in UNITS + ["our_lbm"]]
-        for u, p in procs:
-            if p.wait() != 0:
-                raise SystemExit(f"compiling {u}.cpp against host/lbm.hpp failed")
-        exe = os.path.join(OUT, "luw_reference_driver")
-        subprocess.check_call(["g++", "-pthread", "-o", exe, *[u + ".o" for u in UNITS + ["our_lbm"]], "-L" + LIB, "-lluw_cuda", "-Wl,-rpath,$ORIGIN/../../latticeurbanwind_b200/lib", "-lstdc++fs"], cwd=tmp)
+    # two binaries: TEMPERATURE commented out (the flow-only path the benchmark headline is quoted on) and TEMPERATURE left ON as LUW ships it (FX/defines.hpp:23):
+    # setup.cpp's 19 TEMPERATURE blocks then compile against lbm.T / alpha / beta of the host layer and every LBM runs LUW_TEMPERATURE domains
+    variants = [(os.environ.get("LUW_DROPIN_TEMPERATURE") == "1", "luw_reference_driver")]
+    if os.environ.get("LUW_DROPIN_TEMPERATURE") != "1" and os.environ.get("LUW_DROPIN_SKIP_T") != "1":
+        variants.append((True, "luw_reference_driver_T"))
+    for with_temperature, exe_name in variants:
+      with tempfile.TemporaryDirectory() as tmp:
+          for name in os.listdir(fx):
+              if name in ("lbm.hpp", "lbm.cpp", "opencl.hpp", "kernel.cpp", "kernel.hpp", "defines.hpp") or not (name.endswith(".cpp") or name.endswith(".hpp")):
+                  continue
+              os.symlink(os.path.join(fx, name), os.path.join(tmp, name))
+          defines = open(os.path.join(fx, "defines.hpp")).read()
+          off = ("GRAPHICS", "FORCE_FIELD") if with_temperature else ("GRAPHICS", "TEMPERATURE", "FORCE_FIELD")
+          for flag in off:
+              defines = re.sub(r"(?m)^#define %s\b" % flag, "//#define %s" % flag, defines)
+          open(os.path.join(tmp, "defines.hpp"), "w").write(defines)
+          host = os.path.join(ROOT, "latticeurbanwind_b200", "host")
+          open(os.path.join(tmp, "lbm.hpp"), "w").write('#pragma once\n#include "utilities.hpp"\n#define LUW_USE_REFERENCE_UTILITIES\n#include "%s/lbm.hpp"\n' % host)
+          open(os.path.join(tmp, "our_lbm.cpp"), "w").write('#include "utilities.hpp"\n#define LUW_USE_REFERENCE_UTILITIES\n#include "%s/lbm.cpp"\n' % host)
+          flags = ["-std=c++17", "-pthread", "-O", "-Wno-comment", "-w", "-I."]  # the reference's own flags (FX/../makefile:1-3)
+          procs = [(u, subprocess.Popen(["g++", *flags, "-c", u + ".cpp", "-o", u + ".o"], cwd=tmp)) for u in UNITS + ["our_lbm"]]
+          for u, p in procs:
+              if p.wait() != 0:
+                  raise SystemExit(f"compiling {u}.cpp against host/lbm.hpp failed")
+          exe = os.path.join(OUT, exe_name)
+          subprocess.check_call(["g++", "-pthread", "-o", exe, *[u + ".o" for u in UNITS + ["our_lbm"]], "-L" + LIB, "-lluw_cuda", "-Wl,-rpath,$ORIGIN/../../latticeurbanwind_b200/lib", "-lstdc++fs"], cwd=tmp)
     # the example project of BASELINE configs[0], staged as input data: deck set to one GPU, a fixed cell size (identical grids whatever the memory estimator says),
     # one inflow angle and a short run; everything else as shipped
     src = os.path.join(reference_root, "examples", "example_ProfileResearch_noDEM")

@@ -97,3 +97,27 @@ def test_deck_driven_path_equals_oracle(tmp_path, oracle_lib):
     assert rho.size == N and u.size == 3 * N
     assert np.array_equal(rho, ref[1]), f"rho differs in {int((rho != ref[1]).sum())} cells"
     assert np.array_equal(u, ref[2]), f"u differs in {int((u != ref[2]).sum())} values"
+
+
+DRIVER_T = os.path.join(ROOT, "baseline", "_ref", "luw_reference_driver_T")
+
+
+@pytest.mark.skipif(not os.path.isfile(DRIVER_T), reason="baseline/_ref/luw_reference_driver_T was not built")
+def test_driver_with_temperature_on_runs_the_shipped_switches(tmp_path):
+    """LUW ships FP16C + UPDATE_FIELDS + TEMPERATURE (FX/defines.hpp:14-24). The same unmodified case driver built with TEMPERATURE left on creates LUW_TEMPERATURE
+    domains (gi, T, alpha / beta through the LBM constructor) and runs the two-kernel thermal step (TMA-tiled momentum kernel, FEAT = 15 | TEMPERATURE, + k_thermal_g).
+    Every LUW mode builds its LBM with f = 0, so the temperature cannot act on the flow: the u / rho VTK files must equal the flow-only binary's byte for byte."""
+    outs = {}
+    for name, exe in (("flow", DRIVER), ("thermal", DRIVER_T)):
+        case = str(tmp_path / name)
+        shutil.copytree(CASE, case)
+        r = subprocess.run([exe, os.path.join(case, "conf.luwpf")], capture_output=True, text=True, timeout=600, cwd=case, stdin=subprocess.DEVNULL, env=dict(os.environ, LUW_VERBOSE="1"))
+        assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+        assert "tile kernel" in r.stderr, r.stderr[-2000:]
+        if name == "thermal":
+            assert "feat=79" in r.stderr, "the TEMPERATURE build did not run the thermal momentum kernel (FEAT = 15 | 64):\n" + r.stderr[-2000:]
+            open(os.path.join(ROOT, "gpurun_out", "reference_driver_T.log"), "w").write(r.stdout + "\n---- stderr ----\n" + r.stderr)
+        outs[name] = {os.path.basename(p): open(p, "rb").read() for p in (os.path.join(b, f) for b, _, fs in os.walk(case) for f in fs if f.endswith(".vtk"))}
+    assert outs["flow"] and sorted(outs["flow"]) == sorted(k for k in outs["thermal"] if k in outs["flow"])
+    for k, v in outs["flow"].items():
+        assert outs["thermal"][k] == v, f"{k} differs between the TEMPERATURE-on and the flow-only driver"
