@@ -89,6 +89,15 @@ DECOMP = {"channel": {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (1, 2, 4)},
           "urban": {1: (1, 1, 1), 2: (1, 2, 1), 4: (1, 4, 1), 8: (1, 8, 1)}}
 
 
+def kernel_name(tiled, precision, features, arith):
+    """The step kernel(s) of a workload (csrc/luw_cabi.cu setup_tiles / enqueue_step): FAST FP16 storage runs the lean-loop TMA kernel, FP32 and STRICT the single-pass TMA
+    kernel; thermal domains add k_thermal_g behind the momentum kernel (buoyancy-free steps)."""
+    if not tiled:
+        return "k_stream_collide_thermal" if features & F_TEMPERATURE else "k_stream_collide"
+    k = "k_stream_collide_lean" if (precision != 0 and arith == "fast") else "k_stream_collide_tile"
+    return k + " + k_thermal_g" if features & F_TEMPERATURE else k
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -387,7 +396,7 @@ def bench_single(args, workload, arith, A, cases, Domain, CellSet, pinned_empty,
         kern_ms = ms / K
         achieved = N * alg_bytes(precision, features) / (kern_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "k_stream_collide_tile" if d.uses_tiles() else "k_stream_collide_thermal" if features & F_TEMPERATURE else "k_stream_collide",
+                "kernel": kernel_name(d.uses_tiles(), precision, features, args.arith),
                 "kernel_ms": kern_ms, "kernel_ms_isolated": kms / max(kn, 1),
                 "share_of_step": 1.0,
                 "alg_bytes_per_cell": alg_bytes(precision, features), "cells_per_launch": N, "peak_source": peak_src,
@@ -610,7 +619,7 @@ def bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src):
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[precision], "data": "synthetic",
                "config": dict(config_of(args.workload, args.arith, D, Ng), block_per_gpu_incl_halo=list(shape), halo_transport=args.transport),
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                            "kernel": "k_stream_collide_thermal" if features & F_TEMPERATURE else "k_stream_collide_tile", "kernel_ms": kern_ms, "share_of_step": kern_ms / (ms / K), "alg_bytes_per_cell": alg_bytes(precision, features),
+                            "kernel": kernel_name(True, precision, features, args.arith), "kernel_ms": kern_ms, "share_of_step": kern_ms / (ms / K), "alg_bytes_per_cell": alg_bytes(precision, features),
                             "cells_per_launch": Nloc, "peak_source": peak_src},
                "halo": halo_of(r0),
                "e2e": {"value": mlups, "unit": "MLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
