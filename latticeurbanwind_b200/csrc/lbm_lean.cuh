@@ -106,6 +106,12 @@ __device__ __forceinline__ void mbar_wait_a(const uint32_t bar, const uint32_t p
 	uint32_t spins = 0u;
 	while(!mbar_try_a(bar, parity)) if(++spins>(1u<<24)) __trap(); // a lost arrival must abort the launch, not hang the device
 }
+// ... yielding: a consumer that has run ahead of its CTA to the end of the ring polls while the warps it waits for need the issue slots (experiment: LC_YIELD)
+__device__ __forceinline__ void mbar_wait_y(const uint32_t bar, const uint32_t parity, const bool yield) {
+	if(mbar_try_a(bar, parity)) return;
+	uint32_t spins = 0u;
+	while(!mbar_try_a(bar, parity)) { if(yield) __nanosleep(128u); if(++spins>(1u<<24)) __trap(); }
+}
 __device__ __forceinline__ void mbar_arrive_a(const uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
 
 // the pair's word of a box (R), one element of it (E), and the FAST codecs (FP16S: the stored half IS the scaled value)
@@ -240,8 +246,8 @@ struct LeanConst {
 	int slow_xlo, slow_xhi; // ... holds a halo column or columns beyond the lattice iff xw <= slow_xlo or xw >= slow_xhi: only THESE warps of a strip's first / last tile take the general body
 	uint32_t flags;
 };
-enum : uint32_t { LC_WRAP_X = 1u, LC_PARK = 2u, LC_EDGE_X_SLOW = 4u, LC_ZONES = 8u, LC_PREFETCH = 16u, LC_UF = 32u, LC_EQ = 64u, LC_LAG = 128u, LC_ODD_X = 256u };
-template<class CFG> inline LeanConst lean_const(const DomainConst& c, const bool prefetch, const bool lag) {
+enum : uint32_t { LC_WRAP_X = 1u, LC_PARK = 2u, LC_EDGE_X_SLOW = 4u, LC_ZONES = 8u, LC_PREFETCH = 16u, LC_UF = 32u, LC_EQ = 64u, LC_LAG = 128u, LC_ODD_X = 256u, LC_YIELD = 512u };
+template<class CFG> inline LeanConst lean_const(const DomainConst& c, const bool prefetch, const bool lag, const bool yield = false) {
 	LeanConst l;
 	l.tiles_x = (c.Nx+CFG::TX-1u)/CFG::TX; l.tiles_y = (c.Ny+CFG::TY-1u)/CFG::TY; l.tiles_z = (c.Nz+CFG::TZ-1u)/CFG::TZ;
 	l.last_tx = c.Nx-(l.tiles_x-1u)*(uint32_t)CFG::TX;
@@ -253,7 +259,7 @@ template<class CFG> inline LeanConst lean_const(const DomainConst& c, const bool
 	l.zone_xw = west ? (int)c.buffer_N-c.Ox : -0x7FFFFFFF;
 	l.zone_xe = east ? (int)c.Nxg-1-(int)c.buffer_N-63-c.Ox : 0x7FFFFFFF;
 	l.flags = (c.Dx==1u ? LC_WRAP_X : 0u)|((c.Dx==1u&&l.tiles_x>=2u) ? LC_PARK : 0u)|((c.Dx>1u||l.last_tx!=(uint32_t)CFG::TX) ? LC_EDGE_X_SLOW : 0u)|(zones ? LC_ZONES : 0u)|(prefetch ? LC_PREFETCH : 0u)
-		|((c.features&F_UPDATE_FIELDS) ? LC_UF : 0u)|((c.features&F_EQUILIBRIUM) ? LC_EQ : 0u)|((lag&&CFG::STAGES>=5) ? LC_LAG : 0u)|((c.Nx&1u) ? LC_ODD_X : 0u);
+		|((c.features&F_UPDATE_FIELDS) ? LC_UF : 0u)|((c.features&F_EQUILIBRIUM) ? LC_EQ : 0u)|((lag&&CFG::STAGES>=5) ? LC_LAG : 0u)|((c.Nx&1u) ? LC_ODD_X : 0u)|(yield ? LC_YIELD : 0u);
 	return l;
 }
 __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, const int c0, const int c1, const int c2, const int c3) {
@@ -407,7 +413,7 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 	constexpr uint32_t SF_BND = 1u, SF_IN = 2u, SF_ZONE = 4u, SF_HB = 8u; // SF_HB: a boundary strip of an overlapped halo exchange (carried to the flush of its parked column in bit 30 of py0)
 	constexpr int PY_HB = 1<<30;
 	for(;;) { // ---- tiles: strips as published by the producer, inside a strip x ascending
-		mbar_wait_a(bar0+8u*s, ph);
+		mbar_wait_y(bar0+8u*s, ph, (lc.flags&LC_YIELD)!=0u);
 		const bool first = xt==0u, last = xt+1u==tiles_x;
 		if(first) { // ---- a new strip
 			const uint32_t raw = tile_strip[s];
