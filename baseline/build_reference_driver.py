@@ -55,7 +55,19 @@ def build(reference_root="/root/reference"):
               if p.wait() != 0:
                   raise SystemExit(f"compiling {u}.cpp against host/lbm.hpp failed")
           exe = os.path.join(OUT, exe_name)
-          subprocess.check_call(["g++", "-pthread", "-o", exe, *[u + ".o" for u in UNITS + ["our_lbm"]], "-L" + LIB, "-lluw_cuda", "-Wl,-rpath,$ORIGIN/../../latticeurbanwind_b200/lib", "-lstdc++fs"], cwd=tmp)
+          # fluxcorrection.cpp is one of the subsystems that change: the driver links this repo's O(surface) apply_flux_correction (same signature, bit-identical
+          # results) in its place; the reference's unmodified one is compiled too, under another name, as the oracle of baseline/_ref/luw_flux_parity
+          open(os.path.join(tmp, "our_flux.cpp"), "w").write('#include "%s/fluxcorrection_surface.cpp"\n' % host)
+          subprocess.check_call(["g++", *flags, "-c", "our_flux.cpp", "-o", "our_flux.o"], cwd=tmp)
+          objs = [u + ".o" for u in UNITS if u != "fluxcorrection"] + ["our_flux.o", "our_lbm.o"]
+          subprocess.check_call(["g++", "-pthread", "-o", exe, *objs, "-L" + LIB, "-lluw_cuda", "-Wl,-rpath,$ORIGIN/../../latticeurbanwind_b200/lib", "-lstdc++fs"], cwd=tmp)
+          if not with_temperature:  # the parity harness: everything the driver is made of except its main(), + the reference's flux correction under another name
+              subprocess.check_call(["g++", *flags, "-Dapply_flux_correction=ref_apply_flux_correction", "-c", "fluxcorrection.cpp", "-o", "ref_flux.o"], cwd=tmp)
+              subprocess.check_call(["g++", *flags, "-Dmain=reference_main_unused", "-c", "main.cpp", "-o", "main_renamed.o"], cwd=tmp)
+              open(os.path.join(tmp, "flux_parity.cpp"), "w").write('#include "%s/baseline/flux_parity.cpp"\nint main() { return luw_flux_parity_main(); }\n' % ROOT)
+              subprocess.check_call(["g++", *flags, "-c", "flux_parity.cpp", "-o", "flux_parity.o"], cwd=tmp)
+              objs = [u + ".o" for u in UNITS if u not in ("fluxcorrection", "main")] + ["main_renamed.o", "our_flux.o", "ref_flux.o", "flux_parity.o", "our_lbm.o"]
+              subprocess.check_call(["g++", "-pthread", "-o", os.path.join(OUT, "luw_flux_parity"), *objs, "-L" + LIB, "-lluw_cuda", "-Wl,-rpath,$ORIGIN/../../latticeurbanwind_b200/lib", "-lstdc++fs"], cwd=tmp)
     # the example project of BASELINE configs[0], staged as input data: deck set to one GPU, a fixed cell size (identical grids whatever the memory estimator says),
     # one inflow angle and a short run; everything else as shipped
     src = os.path.join(reference_root, "examples", "example_ProfileResearch_noDEM")

@@ -404,7 +404,7 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 	const float scale = (P==P_FP16S) ? 32768.0f : 1.0f, inv = (P==P_FP16S) ? 3.0517578E-5f : 1.0f;
 	const bool has_zones = VF&&(lc.flags&LC_ZONES)!=0u;
 	const bool next_warp = (lx&~63u)==(uint32_t)(TX-64); // this warp holds the last pair of its row in a full tile: it reads column 0 of the NEXT tile
-	constexpr uint32_t E_BITS = TYPE_E|(TYPE_E<<8);
+	constexpr uint32_t E_BITS = TYPE_E|(TYPE_E<<8), T_BITS = TYPE_T|(TYPE_T<<8); // TYPE_T (temperature boundary) means nothing to the momentum step: a thermal deck flags every TYPE_E cell TYPE_T as well
 
 	uint32_t s = 0u, ph = 0u, kstrip = 0u, st = sm0, xt = 0u; // ring slot, its phase, strips done, shared address of stage s, x tile inside the strip
 	int y0 = 0, z0 = 0, py0 = 0, pz0 = 0;
@@ -455,13 +455,13 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 			const uint32_t x = xt*(uint32_t)TX+lx;
 			// ONE warp-uniform decision per tile: all 64 cells plain fluid or TYPE_E, no halo column, no column beyond the lattice -> fast body
 			const int xw = (int)(xt*(uint32_t)TX+(lx&~63u)); // first cell of the warp's 64
-			const bool slow = __any_sync(0xFFFFFFFFu, (fl2&~E_BITS)!=0u)||xw<=lc.slow_xlo||xw>=lc.slow_xhi;
+			const bool slow = __any_sync(0xFFFFFFFFu, (fl2&~(E_BITS|T_BITS))!=0u)||xw<=lc.slow_xlo||xw>=lc.slow_xhi;
 			const uint32_t e2 = EQ ? fl2&E_BITS : 0u; // TYPE_E lanes (fast body)
 			// element right of the pair's word in an x-shifted box: the next word of the row, or column 0 of the same row in the next stage / the parked column
 			uint32_t nxt = bb+(uint32_t)sizeof(R);
 			if(lx==(last ? lc.rowend_last : (uint32_t)(TX-2))) nxt = !last ? st1+row*(uint32_t)(TX*CFG::ES) : park ? sm0+park_off : wrap_x ? st+row*(uint32_t)(TX*CFG::ES) : bb;
 			const bool zone_warp = zone_yz||xw<=lc.zone_xw||xw>=lc.zone_xe;
-			if(EQ&&!last&&(xt+2u>=tiles_x||__any_sync(0xFFFFFFFFu, fl2!=0u))) lean_prefetch_e<CFG>(c, lds_u16(st1+(uint32_t)CFG::FLAG_OFF+2u*tid), (uint64_t)x+(uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny));
+			if(EQ&&!last&&(xt+2u>=tiles_x||__any_sync(0xFFFFFFFFu, (fl2&~T_BITS)!=0u))) lean_prefetch_e<CFG>(c, lds_u16(st1+(uint32_t)CFG::FLAG_OFF+2u*tid), (uint64_t)x+(uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny));
 			if(!slow) { // ---------------- fast body: 64 cells that all execute
 				PairIn in;
 				in.zones = false;
@@ -471,8 +471,8 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 					const uint64_t n_row = (uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny);
 					const ZoneRow zr = zone_row(c, y, z);
 					in.nudge_vertical = c.nudge_vertical;
-					in.zr0 = zone_cell(c, zr, x, n_row, (fl2&0x00FFu)==0u); // not for TYPE_E cells (FX/kernel.cpp:1524); the fast body only sees flag bytes 0x00 / 0x02
-					in.zr1 = zone_cell(c, zr, x+1u, n_row, (fl2&0xFF00u)==0u);
+					in.zr0 = zone_cell(c, zr, x, n_row, (fl2&E_BITS&0x00FFu)==0u); // not for TYPE_E cells (FX/kernel.cpp:1524); the fast body only sees plain fluid and TYPE_E cells (+ TYPE_T on either)
+					in.zr1 = zone_cell(c, zr, x+1u, n_row, (fl2&E_BITS&0xFF00u)==0u);
 					in.zones = in.zr0.nudge||in.zr0.sponge||in.zr1.nudge||in.zr1.sponge;
 				}
 				Moments M;

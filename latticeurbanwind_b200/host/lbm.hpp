@@ -306,7 +306,7 @@ public:
 		uint Nx=1u, Ny=1u, Nz=1u, Dx=1u, Dy=1u, Dz=1u, D=1u, NxDx=1u, NyDy=1u, NzDz=1u, Hx=0u, Hy=0u, Hz=0u;
 		ulong NxNy=1ull, local_Nx=1ull, local_Ny=1ull, local_Nz=1ull, local_N=1ull;
 		T& reference(const ulong i, const uint dimension) { // FX/lbm.hpp:274-297: global index -> (domain, local index with halo offsets)
-			if(D==1u) return buffers[0]->data()[i%N+(ulong)std::max((ulong)dimension, i/N)*N];
+			if(D==1u) return buffers[0]->data()[i<N ? i+(ulong)dimension*N : i%N+(ulong)std::max((ulong)dimension, i/N)*N]; // same element; the common case (i < N) without the two 64-bit divisions -- the case driver calls this a few times per cell of the lattice
 			const ulong global_i = i%N, tt = global_i%NxNy;
 			const uint x = (uint)(tt%(ulong)Nx), y = (uint)(tt/(ulong)Nx), z = (uint)(global_i/NxNy);
 			const uint px = x%NxDx, py = y%NyDy, pz = z%NzDz, dx = x/NxDx, dy = y/NyDy, dz = z/NzDz, domain = dx+(dy+dz*Dy)*Dx;

@@ -121,3 +121,16 @@ def test_driver_with_temperature_on_runs_the_shipped_switches(tmp_path):
     assert outs["flow"] and sorted(outs["flow"]) == sorted(k for k in outs["thermal"] if k in outs["flow"])
     for k, v in outs["flow"].items():
         assert outs["thermal"][k] == v, f"{k} differs between the TEMPERATURE-on and the flow-only driver"
+
+
+FLUX_PARITY = os.path.join(ROOT, "baseline", "_ref", "luw_flux_parity")
+
+
+@pytest.mark.skipif(not os.path.isfile(FLUX_PARITY), reason="baseline/_ref/luw_flux_parity was not built")
+def test_surface_flux_correction_equals_the_reference_function():
+    """SURVEY 8-f2, first piece: apply_flux_correction in O(surface) host time (latticeurbanwind_b200/host/fluxcorrection_surface.cpp, linked into the drop-in driver in place of
+    FX/fluxcorrection.cpp) against the reference's own, unmodified function compiled under another name: three lattices x five downstream settings x with / without the
+    inflow re-evaluation -> flags, u and the reported sums bit-identical (baseline/flux_parity.cpp)."""
+    r = subprocess.run([FLUX_PARITY], capture_output=True, text=True, timeout=600, stdin=subprocess.DEVNULL)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert "30 of 30 runs identical" in r.stdout, r.stdout[-3000:]
