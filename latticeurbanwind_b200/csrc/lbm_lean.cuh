@@ -406,6 +406,16 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 	const bool next_warp = (lx&~63u)==(uint32_t)(TX-64); // this warp holds the last pair of its row in a full tile: it reads column 0 of the NEXT tile
 	constexpr uint32_t E_BITS = TYPE_E|(TYPE_E<<8), T_BITS = TYPE_T|(TYPE_T<<8); // TYPE_T (temperature boundary) means nothing to the momentum step: a thermal deck flags every TYPE_E cell TYPE_T as well
 
+	// per x tile of a strip (bit min(xt, 31)): does this warp hold a halo column / columns beyond the lattice (-> general body), does it reach the west / east nudging shell?
+	// Decided once per launch instead of per tile (four constant-bank loads and compares per tile otherwise); past 32 tiles bit 31 answers conservatively.
+	const bool end_full = lx==(uint32_t)(TX-2), end_last = lx==lc.rowend_last; // this thread holds the last pair of its row in a full tile / in the strip's last tile
+	uint32_t edge_bits = 0u, zonex_bits = 0u;
+	for(uint32_t t=0u; t<tiles_x; t++) {
+		const int xw = (int)(t*(uint32_t)TX+(lx&~63u));
+		const uint32_t bit = 1u<<(t<31u ? t : 31u);
+		if(xw<=lc.slow_xlo||xw>=lc.slow_xhi) edge_bits |= bit;
+		if(xw<=lc.zone_xw||xw>=lc.zone_xe) zonex_bits |= bit;
+	}
 	uint32_t s = 0u, ph = 0u, kstrip = 0u, st = sm0, xt = 0u; // ring slot, its phase, strips done, shared address of stage s, x tile inside the strip
 	int y0 = 0, z0 = 0, py0 = 0, pz0 = 0;
 	uint32_t y = 0u, z = 0u, park_off = 0u;
@@ -454,18 +464,19 @@ k_stream_collide_lean(const __grid_constant__ DomainConst c, const __grid_consta
 			const uint32_t fl2 = lds_u16(st+(uint32_t)CFG::FLAG_OFF+2u*tid);
 			const uint32_t x = xt*(uint32_t)TX+lx;
 			// ONE warp-uniform decision per tile: all 64 cells plain fluid or TYPE_E, no halo column, no column beyond the lattice -> fast body
-			const int xw = (int)(xt*(uint32_t)TX+(lx&~63u)); // first cell of the warp's 64
-			const bool slow = __any_sync(0xFFFFFFFFu, (fl2&~(E_BITS|T_BITS))!=0u)||xw<=lc.slow_xlo||xw>=lc.slow_xhi;
+			const uint32_t orfl = __reduce_or_sync(0xFFFFFFFFu, fl2); // every flag bit some cell of the warp carries: one reduction answers the three warp-uniform questions of a tile
+			const uint32_t xbit = 1u<<(xt<31u ? xt : 31u);
+			const bool slow = (orfl&~(E_BITS|T_BITS))!=0u||(edge_bits&xbit)!=0u;
 			const uint32_t e2 = EQ ? fl2&E_BITS : 0u; // TYPE_E lanes (fast body)
 			// element right of the pair's word in an x-shifted box: the next word of the row, or column 0 of the same row in the next stage / the parked column
 			uint32_t nxt = bb+(uint32_t)sizeof(R);
-			if(lx==(last ? lc.rowend_last : (uint32_t)(TX-2))) nxt = !last ? st1+row*(uint32_t)(TX*CFG::ES) : park ? sm0+park_off : wrap_x ? st+row*(uint32_t)(TX*CFG::ES) : bb;
-			const bool zone_warp = zone_yz||xw<=lc.zone_xw||xw>=lc.zone_xe;
-			if(EQ&&!last&&(xt+2u>=tiles_x||__any_sync(0xFFFFFFFFu, (fl2&~T_BITS)!=0u))) lean_prefetch_e<CFG>(c, lds_u16(st1+(uint32_t)CFG::FLAG_OFF+2u*tid), (uint64_t)x+(uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny));
+			if(last ? end_last : end_full) nxt = !last ? st1+row*(uint32_t)(TX*CFG::ES) : park ? sm0+park_off : wrap_x ? st+row*(uint32_t)(TX*CFG::ES) : bb;
+			const bool zone_warp = zone_yz||(zonex_bits&xbit)!=0u;
+			if(EQ&&!last&&(xt+2u>=tiles_x||(orfl&~T_BITS)!=0u)) lean_prefetch_e<CFG>(c, lds_u16(st1+(uint32_t)CFG::FLAG_OFF+2u*tid), (uint64_t)x+(uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny));
 			if(!slow) { // ---------------- fast body: 64 cells that all execute
 				PairIn in;
 				in.zones = false;
-				in.any_e = EQ&&__any_sync(0xFFFFFFFFu, e2!=0u); // warp-uniform: the selects of the TYPE_E lanes stay out of the common path
+				in.any_e = EQ&&(orfl&E_BITS)!=0u; // warp-uniform: the selects of the TYPE_E lanes stay out of the common path
 				in.e0 = (e2&0x00FFu)!=0u; in.e1 = (e2&0xFF00u)!=0u; in.n = (uint64_t)x+(uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny); // pure functions of live values: rematerialised where fast_prepare needs them. The TYPE_E lanes' rho / u are the boundary fields, loaded there (prefetched into L2 a tile ago)
 				if(zone_warp) { // relaxation-zone data first: its global loads are in flight while the moments are accumulated
 					const uint64_t n_row = (uint64_t)y*c.Px+(uint64_t)z*((uint64_t)c.Px*c.Ny);
