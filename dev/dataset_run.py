@@ -10,11 +10,15 @@ from latticeurbanwind_b200 import dataset_replicas as R
 ap = argparse.ArgumentParser()
 ap.add_argument("--gpus", type=int, default=8)
 ap.add_argument("--seq-cases", type=int, default=4)
+ap.add_argument("--steps", type=int, default=0, help="override the deck's run_nstep (0: keep)")
+ap.add_argument("--stagger", type=float, default=1.1, help="seconds between replica starts (the driver's console log name has one-second resolution)")
 a = ap.parse_args()
 driver = os.path.join(ROOT, "baseline", "_ref", "luw_reference_driver")
 src = os.path.join(ROOT, "baseline", "_ref", "case_dataset")
 work = tempfile.mkdtemp(prefix="luw_dg_")
 deck = open(os.path.join(src, "conf.luwdg")).read()
+if a.steps > 0:
+    deck = re.sub(r"(?m)^run_nstep\s*=.*$", f"run_nstep = {a.steps}", deck)
 angles = R.parse_list(deck, "angle")
 
 
@@ -39,8 +43,9 @@ assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 seq_out = outputs(seq)
 # (b) replicas, one process per GPU
 rep = os.path.join(work, "rep"); shutil.copytree(src, rep)
+open(os.path.join(rep, "conf.luwdg"), "w").write(deck)
 t0 = time.time()
-res = R.launch(os.path.join(rep, "conf.luwdg"), driver, a.gpus)
+res = R.launch(os.path.join(rep, "conf.luwdg"), driver, a.gpus, stagger_s=a.stagger)
 t_rep = time.time() - t0
 assert all(rc == 0 for _, _, rc, _ in res), [(d, rc, open(log).read()[-1500:]) for d, _, rc, log in res if rc != 0]
 rep_out = outputs(rep)
@@ -53,6 +58,7 @@ line = {"cases": len(angles), "gpus": a.gpus, "sequential": {"cases": a.seq_case
         "speedup_in_cases_per_hour": (len(angles) / t_rep) / (a.seq_cases / t_seq),
         "files": {"sequential": len(seq_out), "replicas": len(rep_out), "case_tags_replicas": len({tag(k) for k in rep_out}), "compared": len(common), "missing_in_replicas": missing[:8],
                   "byte_identical": len(common) - len(differing), "differing": differing[:8]},
-        "deck": "baseline/_ref/case_dataset/conf.luwdg (example_DatasetGen: 16 inflow directions, 400 x 400 x 200 cells at 2.5 m, 300 steps per case, VTK output)"}
+        "stagger_s": a.stagger, "steps_per_case": a.steps if a.steps > 0 else 300,
+        "deck": "baseline/_ref/case_dataset/conf.luwdg (example_DatasetGen: 16 inflow directions, 400 x 400 x 200 cells at 2.5 m, VTK output)"}
 print(json.dumps(line))
 shutil.rmtree(work, ignore_errors=True)

@@ -49,24 +49,25 @@ def _worker(rank, world, port, D, precision, arith, transport, out):
 
 
 @pytest.mark.parametrize("transport", ["ipc", "nccl"])
-@pytest.mark.parametrize("D,arith", [((1, 2, 1), 1), ((1, 1, 2), 0), ((2, 1, 1), 0)], ids=["1x2x1-fast", "1x1x2-strict", "2x1x1-strict"])
+@pytest.mark.parametrize("D,arith", [((1, 2, 1), 1), ((1, 1, 2), 0), ((2, 1, 1), 0), ((1, 2, 2), 1)], ids=["1x2x1-fast", "1x1x2-strict", "2x1x1-strict", "1x2x2-fast-4ranks"])
 def test_two_ranks_nccl_reproduce_single_domain(tmp_path, D, arith, transport):
     import torch
     import torch.multiprocessing as mp
+    world = D[0] * D[1] * D[2]
     if torch.cuda.device_count() < 1:
         pytest.skip("needs a GPU")
-    if torch.cuda.device_count() < 2 and transport == "nccl":
+    if torch.cuda.device_count() < world and transport == "nccl":
         pytest.skip("NCCL needs one device per rank")
     from latticeurbanwind_b200.lbm import LBM
     precision = 1
-    mp.spawn(_worker, args=(2, _free_port(), D, precision, arith, transport, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), D, precision, arith, transport, str(tmp_path)), nprocs=world, join=True)
     flags, rho, u = cases.urban(*SHAPE, seed=21, edge=4, pitch=8)
     one = LBM(SHAPE, D=(1, 1, 1), nu=1e-6, precision=precision, features=H.FEATURE_SETS["luw"], arith=arith, f=H.FORCE, omega=H.OMEGA, **ZONES)
     one.flags[:], one.rho[:], one.u[:] = flags, rho, u
     one.run(STEPS)
     one.read_from_device()
     N = int(np.prod(SHAPE))
-    for r in range(2):
+    for r in range(world):
         z = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
         if transport == "ipc":  # y / z splits: every step's exchange ran on the halo stream, overlapped with the interior strips (luw_step_halo_ipc); x faces involve every strip
             assert int(z["overlapped"]) == (STEPS if D[0] == 1 else 0), int(z["overlapped"])
