@@ -51,6 +51,17 @@ struct DomainConst { // the def_* constants of FX/lbm.cpp:612-783 as kernel para
 	float* upre;
 };
 struct StepArgs { uint64_t t; float fx, fy, fz, ox, oy, oz; }; // per-step kernel arguments, FX/lbm.cpp:345
+// Strip order of an overlapped step for tiles of TY x TZ rows / planes: the tile rows / planes that hold layers 0, 1, N-2, N-1 of the decomposed y / z axes come first.
+// false (so_nb = 0: natural order) when nothing would be left to overlap with.
+inline bool strip_order_fill(DomainConst& o, const uint32_t TY, const uint32_t TZ) {
+	const uint32_t Ty = (o.Ny+TY-1u)/TY, Tz = (o.Nz+TZ-1u)/TZ;
+	o.so_ylo = o.Dy>1u ? 1u/TY+1u : 0u; o.so_yhi = o.Dy>1u ? Ty-(o.Ny-2u)/TY : 0u;
+	o.so_zlo = o.Dz>1u ? 1u/TZ+1u : 0u; o.so_zhi = o.Dz>1u ? Tz-(o.Nz-2u)/TZ : 0u;
+	o.so_nb = 0u;
+	if(o.so_ylo+o.so_yhi>=Ty||o.so_zlo+o.so_zhi>=Tz) return false;
+	o.so_nb = (o.so_zlo+o.so_zhi)*Ty+(o.so_ylo+o.so_yhi)*(Tz-o.so_zlo-o.so_zhi);
+	return o.so_nb>0u;
+}
 // i-th strip handed out by the counter -> strip id ty + tz*Ty: the so_nb boundary strips first (whole tile planes at the z ends, then the y-end tile rows of the inner planes), then the interior
 __host__ __device__ inline uint32_t strip_of(const DomainConst& c, const uint32_t i, const uint32_t Ty, const uint32_t Tz) {
 	if(c.so_nb==0u) return i;

@@ -759,13 +759,9 @@ static bool halo_strip_order(const luw_domain* d, luw::DomainConst* o, uint32_t*
 	luw::TileShape sh;
 	if(!d->tiled||!d->ks->tile_shape(d->c.precision, d->c.features, d->tile_variant, &sh)) return false;
 	const luw::DomainConst& c = d->c;
-	const uint32_t TY = (uint32_t)sh.ty, TZ = (uint32_t)sh.tz, Ty = (c.Ny+TY-1u)/TY, Tz = (c.Nz+TZ-1u)/TZ, Tx = (c.Nx+(uint32_t)sh.tx-1u)/(uint32_t)sh.tx;
+	const uint32_t TY = (uint32_t)sh.ty, TZ = (uint32_t)sh.tz, Tx = (c.Nx+(uint32_t)sh.tx-1u)/(uint32_t)sh.tx;
 	*o = c;
-	o->so_ylo = c.Dy>1u ? 1u/TY+1u : 0u; o->so_yhi = c.Dy>1u ? Ty-(c.Ny-2u)/TY : 0u;
-	o->so_zlo = c.Dz>1u ? 1u/TZ+1u : 0u; o->so_zhi = c.Dz>1u ? Tz-(c.Nz-2u)/TZ : 0u;
-	if(o->so_ylo+o->so_yhi>=Ty||o->so_zlo+o->so_zhi>=Tz) return false;
-	o->so_nb = (o->so_zlo+o->so_zhi)*Ty+(o->so_ylo+o->so_yhi)*(Tz-o->so_zlo-o->so_zhi);
-	if(o->so_nb==0u) return false;
+	if(!luw::strip_order_fill(*o, TY, TZ)) return false;
 	const bool park = c.Dx==1u&&Tx>=2u; // the periodic-x column of a strip is flushed by one thread per tile row, a strip later: counted too (lbm_tile.cuh)
 	*per_strip = 1u+(park ? TY*TZ : 0u);
 	return true;

@@ -26,6 +26,16 @@ template<class K> static void for_face(const uint32_t A, K kernel) {
 
 extern "C" {
 uint64_t emu_sizeof_domain_const() { return sizeof(DomainConst); }
+// the strip order of an overlapped halo exchange (csrc/lbm_common.cuh strip_order_fill / strip_of): out[0..4] = so_ylo, so_yhi, so_zlo, so_zhi, so_nb; order[i] = strip id of the i-th strip handed out
+int emu_strip_order(uint32_t Ny, uint32_t Nz, uint32_t Dy, uint32_t Dz, uint32_t TY, uint32_t TZ, uint32_t* out, uint32_t* order) {
+	DomainConst c; memset(&c, 0, sizeof(c));
+	c.Ny = Ny; c.Nz = Nz; c.Dy = Dy; c.Dz = Dz;
+	const bool ok = strip_order_fill(c, TY, TZ);
+	out[0] = c.so_ylo; out[1] = c.so_yhi; out[2] = c.so_zlo; out[3] = c.so_zhi; out[4] = c.so_nb;
+	const uint32_t Ty = (Ny+TY-1u)/TY, Tz = (Nz+TZ-1u)/TZ;
+	for(uint32_t i=0u; i<Ty*Tz; i++) order[i] = strip_of(c, i, Ty, Tz);
+	return ok ? 1 : 0;
+}
 // the caller fills a DomainConst through this (same derivations as luw_domain_create) so that the struct layout stays private to C++
 int emu_make_domain(DomainConst* c, uint32_t Nx, uint32_t Ny, uint32_t Nz, uint32_t Dx, uint32_t Dy, uint32_t Dz, int Ox, int Oy, int Oz, int precision, uint32_t features, float w,
 	int downstream_face, uint32_t buffer_N, float buffer_inv_tau, int nudge_vertical, uint32_t sponge_N, const float* wbuf, const float* sigma,

@@ -179,3 +179,29 @@ def test_thermal_kernels_on_a_wide_padded_lattice(emu, oracle_lib):
         assert np.array_equal(g, r), name
     pad = d.T.reshape(shape[2], shape[1], d.Px)[..., shape[0]:]
     assert np.all(pad == 1.0)  # the padding columns are never written
+
+
+@pytest.mark.parametrize("Ny,Nz,Dy,Dz,TY,TZ", [(1024, 256, 8, 1, 4, 1), (512, 512, 2, 4, 2, 1), (14, 10, 2, 2, 4, 1), (13, 9, 2, 2, 4, 1), (40, 24, 1, 2, 2, 1), (40, 24, 2, 1, 2, 1),
+                                               (9, 7, 2, 2, 4, 1), (33, 18, 2, 2, 1, 1), (6, 4, 2, 2, 4, 1), (20, 16, 1, 1, 4, 1)])
+def test_boundary_first_strip_order(emu, Ny, Nz, Dy, Dz, TY, TZ):
+    """luw_step_halo_ipc overlaps the halo exchange with the interior of the step: the step kernel hands out the strips that hold layers 0, 1, N-2, N-1 of the decomposed
+    y / z axes first (csrc/lbm_common.cuh strip_of) and counts them. The order must be a permutation of all strips, the first so_nb of it must be exactly the strips that
+    touch those layers, and no interior strip may touch them -- whatever the tile shape, partial tiles included."""
+    Ty, Tz = -(-Ny // TY), -(-Nz // TZ)
+    out, order = np.zeros(5, np.uint32), np.zeros(Ty * Tz, np.uint32)
+    emu.emu_strip_order.argtypes = [C.c_uint32] * 6 + [C.c_void_p, C.c_void_p]
+    ok = emu.emu_strip_order(Ny, Nz, Dy, Dz, TY, TZ, out.ctypes.data, order.ctypes.data)
+    nb = int(out[4])
+    assert sorted(order.tolist()) == list(range(Ty * Tz)), "not a permutation"
+
+    def touches(strip):
+        ty, tz = strip % Ty, strip // Ty
+        rows = set(range(ty * TY, min((ty + 1) * TY, Ny)))
+        planes = set(range(tz * TZ, min((tz + 1) * TZ, Nz)))
+        return (Dy > 1 and bool(rows & {0, 1, Ny - 2, Ny - 1})) or (Dz > 1 and bool(planes & {0, 1, Nz - 2, Nz - 1}))
+    boundary = {s for s in range(Ty * Tz) if touches(s)}
+    if not ok:  # nothing decomposed, or no interior left: natural order, nothing signalled
+        assert nb == 0 and order.tolist() == list(range(Ty * Tz))
+        return
+    assert set(order[:nb].tolist()) == boundary, (sorted(set(order[:nb].tolist()) ^ boundary))
+    assert not (set(order[nb:].tolist()) & boundary)
