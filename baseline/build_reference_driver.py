@@ -22,6 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "baseline", "_ref")
 LIB = os.path.join(ROOT, "latticeurbanwind_b200", "lib")
 UNITS = ["setup", "main", "info", "interpolation", "interpolation_hd", "fluxcorrection", "shapes", "graphics", "lodepng"]
+RENAMED = {"interpolation": ["-Dapply_inlet_outlet=ref_apply_inlet_outlet"], "interpolation_hd": ["-Dapply_inlet_outlet_hd=ref_apply_inlet_outlet_hd"]}
 
 
 def build(reference_root="/root/reference"):
@@ -50,7 +51,11 @@ def build(reference_root="/root/reference"):
           open(os.path.join(tmp, "lbm.hpp"), "w").write('#pragma once\n#include "utilities.hpp"\n#define LUW_USE_REFERENCE_UTILITIES\n#include "%s/lbm.hpp"\n' % host)
           open(os.path.join(tmp, "our_lbm.cpp"), "w").write('#include "utilities.hpp"\n#define LUW_USE_REFERENCE_UTILITIES\n#include "%s/lbm.cpp"\n' % host)
           flags = ["-std=c++17", "-pthread", "-O", "-Wno-comment", "-w", "-I."]  # the reference's own flags (FX/../makefile:1-3)
-          procs = [(u, subprocess.Popen(["g++", *flags, "-c", u + ".cpp", "-o", u + ".o"], cwd=tmp)) for u in UNITS + ["our_lbm"]]
+          # interpolation.cpp / interpolation_hd.cpp: the interpolator classes stay the reference's; their two apply_* drivers are compiled under other names
+          # (the oracle of baseline/_ref/luw_inlet_parity) and this repo's surface-only, GPU-searching ones take the names (host/inlet_outlet_surface.cpp)
+          procs = [(u, subprocess.Popen(["g++", *flags, *RENAMED.get(u, []), "-c", u + ".cpp", "-o", u + ".o"], cwd=tmp)) for u in UNITS + ["our_lbm"]]
+          open(os.path.join(tmp, "our_inlet.cpp"), "w").write('#include "%s/inlet_outlet_surface.cpp"\n' % host)
+          procs.append(("our_inlet", subprocess.Popen(["g++", *flags, "-c", "our_inlet.cpp", "-o", "our_inlet.o"], cwd=tmp)))
           for u, p in procs:
               if p.wait() != 0:
                   raise SystemExit(f"compiling {u}.cpp against host/lbm.hpp failed")
@@ -59,15 +64,26 @@ def build(reference_root="/root/reference"):
           # results) in its place; the reference's unmodified one is compiled too, under another name, as the oracle of baseline/_ref/luw_flux_parity
           open(os.path.join(tmp, "our_flux.cpp"), "w").write('#include "%s/fluxcorrection_surface.cpp"\n' % host)
           subprocess.check_call(["g++", *flags, "-c", "our_flux.cpp", "-o", "our_flux.o"], cwd=tmp)
-          objs = [u + ".o" for u in UNITS if u != "fluxcorrection"] + ["our_flux.o", "our_lbm.o"]
+          objs = [u + ".o" for u in UNITS if u != "fluxcorrection"] + ["our_flux.o", "our_inlet.o", "our_lbm.o"]
           subprocess.check_call(["g++", "-pthread", "-o", exe, *objs, "-L" + LIB, "-lluw_cuda", "-Wl,-rpath,$ORIGIN/../../latticeurbanwind_b200/lib", "-lstdc++fs"], cwd=tmp)
           if not with_temperature:  # the parity harness: everything the driver is made of except its main(), + the reference's flux correction under another name
               subprocess.check_call(["g++", *flags, "-Dapply_flux_correction=ref_apply_flux_correction", "-c", "fluxcorrection.cpp", "-o", "ref_flux.o"], cwd=tmp)
               subprocess.check_call(["g++", *flags, "-Dmain=reference_main_unused", "-c", "main.cpp", "-o", "main_renamed.o"], cwd=tmp)
               open(os.path.join(tmp, "flux_parity.cpp"), "w").write('#include "%s/baseline/flux_parity.cpp"\nint main() { return luw_flux_parity_main(); }\n' % ROOT)
               subprocess.check_call(["g++", *flags, "-c", "flux_parity.cpp", "-o", "flux_parity.o"], cwd=tmp)
-              objs = [u + ".o" for u in UNITS if u not in ("fluxcorrection", "main")] + ["main_renamed.o", "our_flux.o", "ref_flux.o", "flux_parity.o", "our_lbm.o"]
+              objs = [u + ".o" for u in UNITS if u not in ("fluxcorrection", "main")] + ["main_renamed.o", "our_flux.o", "our_inlet.o", "ref_flux.o", "flux_parity.o", "our_lbm.o"]
               subprocess.check_call(["g++", "-pthread", "-o", os.path.join(OUT, "luw_flux_parity"), *objs, "-L" + LIB, "-lluw_cuda", "-Wl,-rpath,$ORIGIN/../../latticeurbanwind_b200/lib", "-lstdc++fs"], cwd=tmp)
+              # the same for apply_inlet_outlet / apply_inlet_outlet_hd: on the GPU (luw_inlet_parity), and with the search kernels' SOURCE compiled for the host
+              # (luw_inlet_parity_on_host: positions only, runs in the GPU-less container; tests/test_inlet_surface_on_host.py)
+              base = [u + ".o" for u in UNITS if u not in ("fluxcorrection", "main")] + ["main_renamed.o", "our_flux.o", "our_inlet.o", "our_lbm.o"]
+              for name, extra in (("luw_inlet_parity", []), ("luw_inlet_parity_on_host", ["-DLUW_INLET_ON_HOST"])):
+                  open(os.path.join(tmp, name + ".cpp"), "w").write('#include "%s/baseline/inlet_parity.cpp"\nint main() { return luw_inlet_parity_main(0, true); }\n' % ROOT)
+                  subprocess.check_call(["g++", *flags, *extra, "-c", name + ".cpp", "-o", name + ".o"], cwd=tmp)
+                  more = [name + ".o"]
+                  if extra:
+                      subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-w", "-I/usr/local/cuda/include", "-c", os.path.join(ROOT, "tests", "host_emulation", "inlet_on_host.cpp"), "-o", "inlet_on_host.o"], cwd=tmp)
+                      more.append("inlet_on_host.o")
+                  subprocess.check_call(["g++", "-pthread", "-o", os.path.join(OUT, name), *more, *base, "-L" + LIB, "-lluw_cuda", "-Wl,-rpath,$ORIGIN/../../latticeurbanwind_b200/lib", "-lstdc++fs"], cwd=tmp)
     # the example project of BASELINE configs[0], staged as input data: deck set to one GPU, a fixed cell size (identical grids whatever the memory estimator says),
     # one inflow angle and a short run; everything else as shipped
     src = os.path.join(reference_root, "examples", "example_ProfileResearch_noDEM")

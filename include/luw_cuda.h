@@ -168,6 +168,22 @@ int luw_vk_inlet_destroy(luw_vk_inlet* vk);
  * otherwise LUW_ERR_INVALID. Works on the device flags / u in place (upload the host images first if they were edited); bit-exact with the reference. */
 int luw_voxelize_mesh(luw_domain* dom, uint32_t direction, uint8_t flag, const float* host_p0, const float* host_p1, const float* host_p2, uint32_t triangle_count, const float* host_bbu);
 
+/* Boundary-field evaluation: the sample searches of the reference's inflow interpolators, one open-face cell per GPU thread; bit-exact with the
+ * host code (same sequential algorithm per cell, individually rounded float operations). Host buffers in and out; synchronous. The cells are the TYPE_E cells of the five
+ * open faces the reference finds by visiting every lattice cell (apply_inlet_outlet, FX/interpolation.cpp:66-210; apply_inlet_outlet_hd, FX/interpolation_hd.cpp:443-750).
+ * luw_inlet_nearest: NearestNeighborInterpolator::eval (FX/interpolation.cpp:53-62). host_cell_xyz: x[n] y[n] z[n] (SoA); host_point_xyz: x, y, z per sample;
+ *   host_nearest[c] = index of the first sample at the smallest squared distance, 0xFFFFFFFF if there is none (the reference then leaves u = 0).
+ * luw_inlet_knn: the K = 64 selection loop of KNNInterpolatorHD::eval (FX/interpolation_hd.cpp:232-296) for cells that lie on one face plane. host_point_ab: the
+ *   in-plane coordinates (a, b) of the samples on that plane, in sample order; host_cell_ab: a[n] b[n]. Per cell: host_exact[c] = first sample within 1e-16 (squared)
+ *   of the cell, else -1; host_used[c] <= 64 samples kept, host_kept[64*c + k] their indices in the reference's slot order (the order of its double-precision sums),
+ *   host_max_r2[c] = max_r2_kept. The weighted quadratic fit over the kept samples (FX/interpolation_hd.cpp:298-410) is the caller's, on the host: its weights are
+ *   exp() in double and must come from the host's libm to reproduce the reference's bits (latticeurbanwind_b200/host/inlet_outlet_surface.cpp). */
+#define LUW_INLET_KNN_K 64
+int luw_inlet_nearest(int device, uint64_t cell_count, const float* host_cell_xyz, uint32_t point_count, const float* host_point_xyz, uint32_t* host_nearest);
+int luw_inlet_knn(int device, uint64_t cell_count, const float* host_cell_ab, uint32_t point_count, const float* host_point_ab,
+	uint32_t* host_kept, uint32_t* host_used, float* host_max_r2, int32_t* host_exact);
+int luw_inlet_launch_count(uint64_t* launches); /* kernels launched by the two calls above in this process (diagnostics, tests) */
+
 /* Boundary-field upload and probe read-back without moving whole fields. The reference writes boundary values into the full host mirrors and
  * uploads / downloads ALL N cells (LBM::initialize FX/lbm.cpp:1226-1237; probes and sampling read the whole u field back, FX/setup.cpp:4411-4425,
  * 4498-4509). A cell set is a fixed list of local cell indices (e.g. the TYPE_E inflow faces, a probe plane); upload scatters host values

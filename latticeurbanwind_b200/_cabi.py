@@ -67,6 +67,9 @@ EXPORTS = {  # name -> argtypes; every symbol include/luw_cuda.h declares
     "luw_vk_inlet_apply": [C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_float],
     "luw_vk_inlet_destroy": [C.c_void_p],
     "luw_voxelize_mesh": [C.c_void_p, C.c_uint32, C.c_uint8, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p],
+    "luw_inlet_nearest": [C.c_int, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p],
+    "luw_inlet_knn": [C.c_int, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    "luw_inlet_launch_count": [C.POINTER(C.c_uint64)],
     "luw_cellset_create": [C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p)],
     "luw_cellset_upload": [C.c_void_p, C.c_int, C.c_void_p],
     "luw_cellset_download": [C.c_void_p, C.c_int, C.c_void_p],

@@ -2,6 +2,7 @@
 // Replaces the Device / Memory<T> / Kernel layer of the reference (FX/opencl.hpp:274-683) for LBM_Domain (FX/lbm.cpp:246-433).
 #include "../../include/luw_cuda.h"
 #include "lbm_launch.h"
+#include "lbm_inlet.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -305,6 +306,17 @@ __global__ void k_fill_f32(float* p, const uint64_t n, const float v) {
 	for(uint64_t i=(uint64_t)blockIdx.x*blockDim.x+threadIdx.x; i<n; i+=(uint64_t)gridDim.x*blockDim.x) p[i] = v;
 }
 
+} // namespace
+
+// Inflow-sample searches (lbm_inlet.cuh): host buffers in, host buffers out, cells in batches so that the kept-sample table (256 B per cell) stays bounded.
+namespace {
+struct DeviceBuffers { // released on every exit path
+	std::vector<void*> p;
+	~DeviceBuffers() { for(void* q : p) cudaFree(q); }
+	template<typename T> cudaError_t get(T** out, const uint64_t count) { *out = nullptr; const cudaError_t e = cudaMalloc((void**)out, (count>0ull ? count : 1ull)*sizeof(T)); if(e==cudaSuccess) p.push_back((void*)*out); return e; }
+};
+constexpr uint64_t kInletBatch = 1ull<<20;
+uint64_t g_inlet_launches = 0ull;
 } // namespace
 
 extern "C" {
@@ -889,6 +901,57 @@ int luw_voxelize_mesh(luw_domain* d, uint32_t direction, uint8_t flag, const flo
 	if(e==cudaSuccess) { d->launches++; e = cudaStreamSynchronize(d->stream); } // kernel.run() is synchronous in the reference, and the triangle buffers are released below
 	cudaFree(tri);
 	if(e!=cudaSuccess) return cuda_fail(e, "voxelize_mesh");
+	return LUW_OK;
+}
+
+int luw_inlet_nearest(int device, uint64_t ncells, const float* cell_xyz, uint32_t npts, const float* point_xyz, uint32_t* nearest) {
+	if((ncells>0ull&&(!cell_xyz||!nearest))||(npts>0u&&!point_xyz)) return fail(LUW_ERR_INVALID, "null argument");
+	if(ncells==0ull) return LUW_OK;
+	DeviceGuard guard(device);
+	if(guard.err!=cudaSuccess) return cuda_fail(guard.err, "cudaSetDevice");
+	DeviceBuffers mem;
+	const uint64_t B = ncells<kInletBatch ? ncells : kInletBatch;
+	float* dp = nullptr; float* dc = nullptr; uint32_t* dn = nullptr;
+	CU(mem.get(&dp, 3ull*npts)); CU(mem.get(&dc, 3ull*B)); CU(mem.get(&dn, B));
+	CU(cudaMemcpy(dp, point_xyz, 3ull*npts*sizeof(float), cudaMemcpyHostToDevice));
+	for(uint64_t c0=0ull; c0<ncells; c0+=B) {
+		const uint64_t n = ncells-c0<B ? ncells-c0 : B;
+		for(int k=0; k<3; k++) CU(cudaMemcpy(dc+(uint64_t)k*n, cell_xyz+(uint64_t)k*ncells+c0, n*sizeof(float), cudaMemcpyHostToDevice));
+		luw::k_inlet_nearest<<<(unsigned)((n+127ull)/128ull), 128>>>((uint32_t)n, dc, npts, dp, dn);
+		CU(cudaGetLastError());
+		g_inlet_launches++;
+		CU(cudaMemcpy(nearest+c0, dn, n*sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	}
+	return LUW_OK;
+}
+
+int luw_inlet_knn(int device, uint64_t ncells, const float* cell_ab, uint32_t npts, const float* point_ab, uint32_t* kept, uint32_t* used, float* max_r2, int32_t* exact) {
+	if((ncells>0ull&&(!cell_ab||!kept||!used||!max_r2||!exact))||(npts>0u&&!point_ab)) return fail(LUW_ERR_INVALID, "null argument");
+	if(ncells==0ull) return LUW_OK;
+	DeviceGuard guard(device);
+	if(guard.err!=cudaSuccess) return cuda_fail(guard.err, "cudaSetDevice");
+	DeviceBuffers mem;
+	const uint64_t B = ncells<kInletBatch ? ncells : kInletBatch, K = (uint64_t)luw::INLET_KNN_K;
+	float2* dp = nullptr; float* dc = nullptr; uint32_t* dk = nullptr; uint32_t* du = nullptr; float* dm = nullptr; int32_t* de = nullptr;
+	CU(mem.get(&dp, (uint64_t)npts)); CU(mem.get(&dc, 2ull*B)); CU(mem.get(&dk, K*B)); CU(mem.get(&du, B)); CU(mem.get(&dm, B)); CU(mem.get(&de, B));
+	CU(cudaMemcpy(dp, point_ab, 2ull*npts*sizeof(float), cudaMemcpyHostToDevice));
+	for(uint64_t c0=0ull; c0<ncells; c0+=B) {
+		const uint64_t n = ncells-c0<B ? ncells-c0 : B;
+		for(int k=0; k<2; k++) CU(cudaMemcpy(dc+(uint64_t)k*n, cell_ab+(uint64_t)k*ncells+c0, n*sizeof(float), cudaMemcpyHostToDevice));
+		CU(cudaMemset(dk, 0, K*n*sizeof(uint32_t))); // slots beyond used[c] read as 0
+		luw::k_inlet_knn<<<(unsigned)((n+127ull)/128ull), 128>>>((uint32_t)n, dc, npts, dp, dk, du, dm, de);
+		CU(cudaGetLastError());
+		g_inlet_launches++;
+		CU(cudaMemcpy(kept+K*c0, dk, K*n*sizeof(uint32_t), cudaMemcpyDeviceToHost));
+		CU(cudaMemcpy(used+c0, du, n*sizeof(uint32_t), cudaMemcpyDeviceToHost));
+		CU(cudaMemcpy(max_r2+c0, dm, n*sizeof(float), cudaMemcpyDeviceToHost));
+		CU(cudaMemcpy(exact+c0, de, n*sizeof(int32_t), cudaMemcpyDeviceToHost));
+	}
+	return LUW_OK;
+}
+int luw_inlet_launch_count(uint64_t* launches) {
+	if(!launches) return fail(LUW_ERR_INVALID, "null argument");
+	*launches = g_inlet_launches;
 	return LUW_OK;
 }
 

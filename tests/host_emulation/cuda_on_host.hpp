@@ -29,6 +29,7 @@ static inline float __fmul_rn(float a, float b) { return a*b; }
 static inline void emu_sincosf(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }
 // packed / explicitly rounded FP32 intrinsics used by csrc/lbm_vec.cuh (each lane rounded like the scalar operation; g++ -ffp-contract=off keeps a*b+c unfused)
 static inline float __fadd_rn(float a, float b) { return a+b; }
+static inline float __fsub_rn(float a, float b) { return a-b; }
 static inline float __fdiv_rn(float a, float b) { return a/b; }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
 static inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(a.x+b.x, a.y+b.y); }

@@ -134,3 +134,20 @@ def test_surface_flux_correction_equals_the_reference_function():
     r = subprocess.run([FLUX_PARITY], capture_output=True, text=True, timeout=600, stdin=subprocess.DEVNULL)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
     assert "30 of 30 runs identical" in r.stdout, r.stdout[-3000:]
+
+
+INLET_PARITY = os.path.join(ROOT, "baseline", "_ref", "luw_inlet_parity")
+
+
+@pytest.mark.skipif(not os.path.isfile(INLET_PARITY), reason="baseline/_ref/luw_inlet_parity was not built")
+def test_surface_inlet_outlet_mapping_equals_the_reference_functions():
+    """apply_inlet_outlet / apply_inlet_outlet_hd with the face cells enumerated directly and the sample searches on the GPU (csrc/lbm_inlet.cuh through
+    luw_inlet_nearest / luw_inlet_knn; latticeurbanwind_b200/host/inlet_outlet_surface.cpp, linked into the drop-in driver under the reference's names) against the
+    reference's own, unmodified functions compiled under other names: 20 position-level runs (5 sample clouds x threshold x nearest / K = 64 fit) and 60 lattice-level
+    runs (3 lattices x 5 downstream settings x open / closed x nearest / HD, with and without the side z cap) -> every flag and velocity bit-identical
+    (baseline/inlet_parity.cpp)."""
+    r = subprocess.run([INLET_PARITY], capture_output=True, text=True, timeout=900, stdin=subprocess.DEVNULL)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-1000:]
+    assert "80 of 80 runs identical" in r.stdout, r.stdout[-4000:]
+    launches = int(r.stdout.strip().rsplit("search kernels launched:", 1)[1])
+    assert launches >= 80, "the sample searches did not run on the device"
