@@ -67,6 +67,19 @@ ulong differing(const std::vector<float3>& a, const std::vector<float3>& b) {
 
 int luw_inlet_parity_main(const int device, const bool with_lattices) {
 	int bad = 0, runs = 0;
+	if(getenv("LUW_INLET_TIMING")) { // how long the reference's own per-cell evaluation takes on one host thread: 100 000 samples (20 000 per face), 512 positions
+		Cloud c; c.name = "timing";
+		std::mt19937 rng(1u); std::uniform_real_distribution<float> unit(-512.0f, 512.0f);
+		for(int f=0; f<5; f++) for(int i=0; i<20000; i++) { const float a = unit(rng), b = 0.25f*unit(rng); c.P.push_back(f==0 ? float3(-512.0f, a, b) : f==1 ? float3(512.0f, a, b) : f==2 ? float3(a, -512.0f, b) : f==3 ? float3(a, 512.0f, b) : float3(a, unit(rng), 128.0f)); c.U.push_back(float3(0.05f)); }
+		std::vector<float3> p; for(int i=0; i<512; i++) p.push_back(float3(unit(rng), unit(rng), 127.5f));
+		KNNInterpolatorHD knn(c.P, c.U); InletVelocityFieldHD hd(knn, -1.0E9f);
+		NearestNeighborInterpolator nn(c.P, c.U); InletVelocityField lo(nn, -1.0E9f, 0.0f);
+		float sink = 0.0f;
+		Clock clock; for(const float3& q : p) sink += hd(q).x; const double t_hd = clock.stop();
+		clock.start(); for(const float3& q : p) sink += lo(q).x; const double t_lo = clock.stop();
+		printf("reference evaluation on one host thread, 100000 samples: KNN-HD %.1f us per cell, nearest %.1f us per cell (%g)\n", 1.0E6*t_hd/512.0, 1.0E6*t_lo/512.0, sink);
+		return 0;
+	}
 	const uint Nx = 41u, Ny = 34u, Nz = 27u;
 	const std::vector<float3> pos = face_positions(Nx, Ny, Nz);
 	const char* kinds[5] = { "regular grid", "jittered", "sparse faces", "collinear", "no samples" };
