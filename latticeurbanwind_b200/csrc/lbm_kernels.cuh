@@ -469,48 +469,47 @@ __global__ void __launch_bounds__(128) k_vk_inlet_apply(const uint64_t Ncells, c
 // (the reference reads all of them from global memory per work-item). Ray/triangle arithmetic in the reference's operation order; this kernel is always
 // taken from the STRICT translation unit (-fmad=false, IEEE division), because the flags must be bit-exact and a contracted product flips grazing rays.
 struct VoxBox { uint32_t ntri; float x0, y0, z0, x1, y1, z1; };
-__global__ void __launch_bounds__(128) k_voxelize_mesh(const __grid_constant__ DomainConst c, const uint32_t direction, const uint32_t A, const uint8_t flag, const VoxBox bb,
-	const float* __restrict__ p0, const float* __restrict__ p1, const float* __restrict__ p2) {
-	__shared__ float tri[128][9];
-	const uint32_t a = blockIdx.x*blockDim.x+threadIdx.x;
+struct VoxColumn { // one ray: the column it runs along, its origin, and what it has crossed so far
+	uint32_t X, Y, Z;
+	float rox, roy, roz, dx, dy, dz;
+	bool out_of_box;
+	uint32_t intersections, intersections_check;
+	uint16_t distances[64];
+};
+// column (c0, c1) of the face normal to `direction`: (y, z) for x-rays, (z, x) for y-rays, (x, y) for z-rays -- the reference's a % n0, a / n0 (FX/kernel.cpp:2386-2393)
+__device__ __forceinline__ void vox_column(const DomainConst& c, const uint32_t direction, const uint32_t c0, const uint32_t c1, const VoxBox& bb, VoxColumn& col) {
 	const int Nx = (int)c.Nx, Ny = (int)c.Ny, Nz = (int)c.Nz;
 	const auto clampi = [](const int x, const int lo, const int hi) { return x<lo ? lo : (x>hi ? hi : x); };
-	uint32_t X = 0u, Y = 0u, Z = 0u;
-	if(direction==0u) { X = (uint32_t)clampi((int)bb.x0-c.Ox, 0, Nx-1); Y = a%c.Ny; Z = a/c.Ny; }
-	else if(direction==1u) { X = a/c.Nz; Y = (uint32_t)clampi((int)bb.y0-c.Oy, 0, Ny-1); Z = a%c.Nz; }
-	else { X = a%c.Nx; Y = a/c.Nx; Z = (uint32_t)clampi((int)bb.z0-c.Oz, 0, Nz-1); }
+	if(direction==0u) { col.X = (uint32_t)clampi((int)bb.x0-c.Ox, 0, Nx-1); col.Y = c0; col.Z = c1; }
+	else if(direction==1u) { col.X = c1; col.Y = (uint32_t)clampi((int)bb.y0-c.Oy, 0, Ny-1); col.Z = c0; }
+	else { col.X = c0; col.Y = c1; col.Z = (uint32_t)clampi((int)bb.z0-c.Oz, 0, Nz-1); }
 	const float offx = 0.5f*(float)(Nx+2*c.Ox)-0.5f, offy = 0.5f*(float)(Ny+2*c.Oy)-0.5f, offz = 0.5f*(float)(Nz+2*c.Oz)-0.5f;
-	const float rox = ((float)X+0.5f-0.5f*(float)Nx)+offx, roy = ((float)Y+0.5f-0.5f*(float)Ny)+offy, roz = ((float)Z+0.5f-0.5f*(float)Nz)+offz;
-	const float dx = (float)(direction==0u), dy = (float)(direction==1u), dz = (float)(direction==2u);
-	const bool out_of_box = direction==0u ? (roy<bb.y0||roz<bb.z0||roy>=bb.y1||roz>=bb.z1) : direction==1u ? (rox<bb.x0||roz<bb.z0||rox>=bb.x1||roz>=bb.z1) : (rox<bb.x0||roy<bb.y0||rox>=bb.x1||roy>=bb.y1);
-	const bool active = a<A&&!out_of_box;
-	uint32_t intersections = 0u, intersections_check = 0u;
-	uint16_t distances[64];
-	for(uint32_t base=0u; base<bb.ntri; base+=128u) {
-		__syncthreads();
-		const uint32_t i = base+threadIdx.x;
-		if(i<bb.ntri) {
-#pragma unroll
-			for(int k=0; k<3; k++) { tri[threadIdx.x][k] = p0[3u*i+k]; tri[threadIdx.x][3+k] = p1[3u*i+k]; tri[threadIdx.x][6+k] = p2[3u*i+k]; }
-		}
-		__syncthreads();
-		if(!active) continue;
-		const uint32_t cnt = bb.ntri-base<128u ? bb.ntri-base : 128u;
-		for(uint32_t k=0u; k<cnt; k++) {
-			const float ax = tri[k][0], ay = tri[k][1], az = tri[k][2];
-			const float ux = tri[k][3]-ax, uy = tri[k][4]-ay, uz = tri[k][5]-az;
-			const float vx = tri[k][6]-ax, vy = tri[k][7]-ay, vz = tri[k][8]-az;
-			const float wx = rox-ax, wy = roy-ay, wz = roz-az;
-			const float hx = dy*vz-dz*vy, hy = dz*vx-dx*vz, hz = dx*vy-dy*vx; // cross(r_direction, v)
-			const float qx = wy*uz-wz*uy, qy = wz*ux-wx*uz, qz = wx*uy-wy*ux; // cross(w, u)
-			const float g = ux*hx+uy*hy+uz*hz, f = 1.0f/g, s = f*(wx*hx+wy*hy+wz*hz), t = f*(dx*qx+dy*qy+dz*qz), d = f*(vx*qx+vy*qy+vz*qz);
-			if(g!=0.0f&&s>=0.0f&&s<1.0f&&t>=0.0f&&s+t<1.0f) {
-				if(d>0.0f) { if(intersections<64u&&d<65536.0f) distances[intersections] = (uint16_t)d; intersections++; }
-				else intersections_check++;
-			}
-		}
+	col.rox = ((float)col.X+0.5f-0.5f*(float)Nx)+offx; col.roy = ((float)col.Y+0.5f-0.5f*(float)Ny)+offy; col.roz = ((float)col.Z+0.5f-0.5f*(float)Nz)+offz;
+	col.dx = (float)(direction==0u); col.dy = (float)(direction==1u); col.dz = (float)(direction==2u);
+	const float rox = col.rox, roy = col.roy, roz = col.roz;
+	col.out_of_box = direction==0u ? (roy<bb.y0||roz<bb.z0||roy>=bb.y1||roz>=bb.z1) : direction==1u ? (rox<bb.x0||roz<bb.z0||rox>=bb.x1||roz>=bb.z1) : (rox<bb.x0||roy<bb.y0||rox>=bb.x1||roy>=bb.y1);
+	col.intersections = 0u; col.intersections_check = 0u;
+}
+// ray against the triangle (a, a+u.., a+v..) given as p0, p1, p2 (FX/kernel.cpp:2404-2423)
+__device__ __forceinline__ void vox_cross(VoxColumn& col, const float ax, const float ay, const float az, const float bx, const float by, const float bz, const float cx, const float cy, const float cz) {
+	const float dx = col.dx, dy = col.dy, dz = col.dz;
+	const float ux = bx-ax, uy = by-ay, uz = bz-az;
+	const float vx = cx-ax, vy = cy-ay, vz = cz-az;
+	const float wx = col.rox-ax, wy = col.roy-ay, wz = col.roz-az;
+	const float hx = dy*vz-dz*vy, hy = dz*vx-dx*vz, hz = dx*vy-dy*vx; // cross(r_direction, v)
+	const float qx = wy*uz-wz*uy, qy = wz*ux-wx*uz, qz = wx*uy-wy*ux; // cross(w, u)
+	const float g = ux*hx+uy*hy+uz*hz, f = 1.0f/g, s = f*(wx*hx+wy*hy+wz*hz), t = f*(dx*qx+dy*qy+dz*qz), d = f*(vx*qx+vy*qy+vz*qz);
+	if(g!=0.0f&&s>=0.0f&&s<1.0f&&t>=0.0f&&s+t<1.0f) {
+		if(d>0.0f) { if(col.intersections<64u&&d<65536.0f) col.distances[col.intersections] = (uint16_t)d; col.intersections++; }
+		else col.intersections_check++;
 	}
-	if(!active) return;
+}
+// the crossings sorted, the cells of the column between them flagged (FX/kernel.cpp:2425-2470)
+__device__ __forceinline__ void vox_fill(const DomainConst& c, const uint32_t direction, const uint8_t flag, const VoxBox& bb, VoxColumn& col) {
+	const int Nx = (int)c.Nx, Ny = (int)c.Ny, Nz = (int)c.Nz;
+	const auto clampi = [](const int x, const int lo, const int hi) { return x<lo ? lo : (x>hi ? hi : x); };
+	const uint32_t intersections = col.intersections, intersections_check = col.intersections_check, X = col.X, Y = col.Y, Z = col.Z;
+	uint16_t* distances = col.distances;
 	const uint32_t nsort = intersections<64u ? intersections : 64u;
 	for(uint32_t i=1u; i<nsort; i++) { const uint16_t t = distances[i]; int j = (int)i-1; while(j>=0&&distances[j]>t) { distances[j+1] = distances[j]; j--; } distances[j+1] = t; }
 	bool inside = (intersections%2u)&&(intersections_check%2u);
@@ -529,6 +528,49 @@ __global__ void __launch_bounds__(128) k_voxelize_mesh(const __grid_constant__ D
 		}
 		c.flags[n] = fl;
 	}
+}
+__global__ void __launch_bounds__(128) k_voxelize_mesh(const __grid_constant__ DomainConst c, const uint32_t direction, const uint32_t A, const uint8_t flag, const VoxBox bb,
+	const float* __restrict__ p0, const float* __restrict__ p1, const float* __restrict__ p2) {
+	__shared__ float tri[128][9];
+	const uint32_t a = blockIdx.x*blockDim.x+threadIdx.x;
+	const uint32_t n0 = direction==0u ? c.Ny : direction==1u ? c.Nz : c.Nx;
+	VoxColumn col;
+	vox_column(c, direction, a%n0, a/n0, bb, col);
+	const bool active = a<A&&!col.out_of_box;
+	for(uint32_t base=0u; base<bb.ntri; base+=128u) {
+		__syncthreads();
+		const uint32_t i = base+threadIdx.x;
+		if(i<bb.ntri) {
+#pragma unroll
+			for(int k=0; k<3; k++) { tri[threadIdx.x][k] = p0[3u*i+k]; tri[threadIdx.x][3+k] = p1[3u*i+k]; tri[threadIdx.x][6+k] = p2[3u*i+k]; }
+		}
+		__syncthreads();
+		if(!active) continue;
+		const uint32_t cnt = bb.ntri-base<128u ? bb.ntri-base : 128u;
+		for(uint32_t k=0u; k<cnt; k++) vox_cross(col, tri[k][0], tri[k][1], tri[k][2], tri[k][3], tri[k][4], tri[k][5], tri[k][6], tri[k][7], tri[k][8]);
+	}
+	if(!active) return;
+	vox_fill(c, direction, flag, bb, col);
+}
+// The same with a bin grid over the face (csrc/vox_bins.h): one block per bin of 32 x 4 columns, which walks the bin's triangle list only -- the triangles whose
+// projected bounding box, padded by one cell, reaches one of its columns, in ascending triangle order. A ray meets the triangles that can cross it in the order the
+// kernel above meets them, so the crossings (and which 64 are kept when there are more) and the flags are the same; the work drops from columns x triangles to
+// columns x (triangles near the column). The pad is the reference's own margin for handing a domain only "its" triangles (FX/lbm.cpp:41-90). All threads of a block
+// read the same triangle at the same time: one broadcast transaction per warp and load.
+__global__ void __launch_bounds__(128) k_voxelize_mesh_binned(const __grid_constant__ DomainConst c, const uint32_t direction, const uint8_t flag, const VoxBox bb, const uint32_t bins0,
+	const uint32_t* __restrict__ bin_start, const uint32_t* __restrict__ bin_ids, const float* __restrict__ p0, const float* __restrict__ p1, const float* __restrict__ p2) {
+	const uint32_t n0 = direction==0u ? c.Ny : direction==1u ? c.Nz : c.Nx, n1 = direction==0u ? c.Nz : direction==1u ? c.Nx : c.Ny;
+	const uint32_t c0 = (blockIdx.x%bins0)*32u+(threadIdx.x&31u), c1 = (blockIdx.x/bins0)*4u+(threadIdx.x>>5);
+	if(c0>=n0||c1>=n1) return;
+	VoxColumn col;
+	vox_column(c, direction, c0, c1, bb, col);
+	if(col.out_of_box) return;
+	const uint32_t end = __ldg(bin_start+blockIdx.x+1u);
+	for(uint32_t k=__ldg(bin_start+blockIdx.x); k<end; k++) {
+		const uint32_t i = __ldg(bin_ids+k);
+		vox_cross(col, __ldg(p0+3u*i), __ldg(p0+3u*i+1u), __ldg(p0+3u*i+2u), __ldg(p1+3u*i), __ldg(p1+3u*i+1u), __ldg(p1+3u*i+2u), __ldg(p2+3u*i), __ldg(p2+3u*i+1u), __ldg(p2+3u*i+2u));
+	}
+	vox_fill(c, direction, flag, bb, col);
 }
 
 // FAST variant: cos(phase + phi) = cos(phase) cos(phi) - sin(phase) sin(phi). The per-mode products A*cos(phi), A*sin(phi) come from a table built once on

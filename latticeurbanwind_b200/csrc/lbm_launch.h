@@ -19,6 +19,9 @@ struct KernelSet { // one per arithmetic mode; every function enqueues exactly o
 	bool (*tile_shape)(int precision, uint32_t features, int variant, TileShape* shape);
 	cudaError_t (*stream_collide_tile)(const DomainConst& c, const StepArgs& a, const TileMaps& maps, int variant, int sm_count, cudaStream_t s);
 	cudaError_t (*voxelize)(const DomainConst& c, uint32_t direction, uint8_t flag, uint32_t ntri, const float* box6, const float* p0, const float* p1, const float* p2, cudaStream_t s); // p0..p2: device
+	// the same through a bin grid over the face (csrc/vox_bins.h): bin_start[bins0*bins1 + 1], bin_ids[]: device
+	cudaError_t (*voxelize_binned)(const DomainConst& c, uint32_t direction, uint8_t flag, uint32_t ntri, const float* box6, uint32_t bins0, uint32_t bins1, const uint32_t* bin_start, const uint32_t* bin_ids,
+		const float* p0, const float* p1, const float* p2, cudaStream_t s);
 	// thermal D3Q7 extension (domains created with LUW_TEMPERATURE): the three LBM kernels with the reference's TEMPERATURE blocks, halos of gi and T
 	cudaError_t (*initialize_thermal)(const DomainConst& c, cudaStream_t s);
 	cudaError_t (*stream_collide_thermal)(const DomainConst& c, const StepArgs& a, cudaStream_t s);

@@ -3,6 +3,7 @@
 #include "../../include/luw_cuda.h"
 #include "lbm_launch.h"
 #include "lbm_inlet.cuh"
+#include "vox_bins.h"
 
 #include <cmath>
 #include <cstdio>
@@ -892,14 +893,24 @@ int luw_voxelize_mesh(luw_domain* d, uint32_t direction, uint8_t flag, const flo
 	for(int k=10; k<16; k++) if(bbu[k]!=0.0f) return fail(LUW_ERR_INVALID, "moving geometry (non-zero linear / rotational velocity) is not supported: LUW voxelises resting meshes only");
 	if(ntri==0u) return LUW_OK; // run_voxelize_pass returns early, FX/lbm.cpp:505
 	DeviceGuard guard(d->p.device);
-	float* tri = nullptr;
-	CU(cudaMalloc((void**)&tri, 9ull*ntri*sizeof(float))); // Memory<float3> p0, p1, p2 of FX/lbm.cpp:525-527: live for this call only
+	// bin grid over the face (vox_bins.h): every block walks only the triangles near its 32 x 4 columns. LUW_VOXELIZE_BINS=0 keeps the all-triangles kernel (A/B, tests).
+	const char* env = getenv("LUW_VOXELIZE_BINS");
+	luw::VoxBins bins;
+	if(!(env&&env[0]=='0')) bins = luw::vox_build_bins(direction, d->c.Nx, d->c.Ny, d->c.Nz, d->c.Ox, d->c.Oy, d->c.Oz, p0, p1, p2, ntri);
+	const bool binned = bins.bins0>0u;
+	DeviceBuffers mem;
+	float* tri = nullptr; uint32_t* bin_start = nullptr; uint32_t* bin_ids = nullptr;
+	CU(mem.get(&tri, 9ull*ntri)); // Memory<float3> p0, p1, p2 of FX/lbm.cpp:525-527: live for this call only
+	if(binned) { CU(mem.get(&bin_start, (uint64_t)bins.start.size())); CU(mem.get(&bin_ids, (uint64_t)bins.ids.size())); }
 	cudaError_t e = cudaMemcpyAsync(tri, p0, 3ull*ntri*4ull, cudaMemcpyHostToDevice, d->stream);
 	if(e==cudaSuccess) e = cudaMemcpyAsync(tri+3ull*ntri, p1, 3ull*ntri*4ull, cudaMemcpyHostToDevice, d->stream);
 	if(e==cudaSuccess) e = cudaMemcpyAsync(tri+6ull*ntri, p2, 3ull*ntri*4ull, cudaMemcpyHostToDevice, d->stream);
-	if(e==cudaSuccess) e = luw::kernels_strict().voxelize(d->c, direction, flag, ntri, bbu+1, tri, tri+3ull*ntri, tri+6ull*ntri, d->stream); // always the as-written arithmetic: flags are bit-exact
-	if(e==cudaSuccess) { d->launches++; e = cudaStreamSynchronize(d->stream); } // kernel.run() is synchronous in the reference, and the triangle buffers are released below
-	cudaFree(tri);
+	if(binned) {
+		if(e==cudaSuccess) e = cudaMemcpyAsync(bin_start, bins.start.data(), bins.start.size()*4ull, cudaMemcpyHostToDevice, d->stream);
+		if(e==cudaSuccess&&!bins.ids.empty()) e = cudaMemcpyAsync(bin_ids, bins.ids.data(), bins.ids.size()*4ull, cudaMemcpyHostToDevice, d->stream);
+		if(e==cudaSuccess) e = luw::kernels_strict().voxelize_binned(d->c, direction, flag, ntri, bbu+1, bins.bins0, bins.bins1, bin_start, bin_ids, tri, tri+3ull*ntri, tri+6ull*ntri, d->stream);
+	} else if(e==cudaSuccess) e = luw::kernels_strict().voxelize(d->c, direction, flag, ntri, bbu+1, tri, tri+3ull*ntri, tri+6ull*ntri, d->stream); // always the as-written arithmetic: flags are bit-exact
+	if(e==cudaSuccess) { d->launches++; e = cudaStreamSynchronize(d->stream); } // kernel.run() is synchronous in the reference, and the buffers are released on return
 	if(e!=cudaSuccess) return cuda_fail(e, "voxelize_mesh");
 	return LUW_OK;
 }

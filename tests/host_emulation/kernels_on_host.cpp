@@ -2,6 +2,7 @@
 // Build: g++ -std=c++17 -O2 -ffp-contract=off -fopenmp -shared -fPIC -w -I/usr/local/cuda/include kernels_on_host.cpp -o libluw_kernels_on_host.so
 #include "cuda_on_host.hpp"
 #include "../../latticeurbanwind_b200/csrc/lbm_kernels.cuh"
+#include "../../latticeurbanwind_b200/csrc/vox_bins.h"
 using namespace luw;
 
 // one "launch": grid (ceil(Nx/tx), Ny, Nz) x block tx, as cell_grid() / pick_tx() of lbm_launch.inc
@@ -70,6 +71,20 @@ int emu_halo_gi(const DomainConst* c, uint32_t axis, uint32_t odd, int insert, i
 	const uint32_t A = axis==0u ? c->Ny*c->Nz : axis==1u ? c->Nz*c->Nx : c->Nx*c->Ny;
 	if(c->precision==P_FP32) { if(insert) for_face(A, [&]{ k_halo_gi<float, true>(*c, axis, A, odd, xfast!=0, (float*)bp, (float*)bm); }); else for_face(A, [&]{ k_halo_gi<float, false>(*c, axis, A, odd, xfast!=0, (float*)bp, (float*)bm); }); }
 	else { if(insert) for_face(A, [&]{ k_halo_gi<uint16_t, true>(*c, axis, A, odd, xfast!=0, (uint16_t*)bp, (uint16_t*)bm); }); else for_face(A, [&]{ k_halo_gi<uint16_t, false>(*c, axis, A, odd, xfast!=0, (uint16_t*)bp, (uint16_t*)bm); }); }
+	return 0;
+}
+// the binned voxeliser as luw_voxelize_mesh runs it: bin grid from vox_build_bins, one 128-thread block per bin. stats[0..2] = bins, list entries, longest list
+int emu_voxelize_binned(const DomainConst* c, uint32_t direction, uint8_t flag, const float* p0, const float* p1, const float* p2, uint32_t ntri, const float* bbu, uint64_t* stats) {
+	const VoxBins bins = vox_build_bins(direction, c->Nx, c->Ny, c->Nz, c->Ox, c->Oy, c->Oz, p0, p1, p2, ntri);
+	if(bins.bins0==0u) return 1;
+	const VoxBox bb = { ntri, bbu[1], bbu[2], bbu[3], bbu[4], bbu[5], bbu[6] };
+	const unsigned nb = bins.bins0*bins.bins1;
+	if(stats) { stats[0] = nb; stats[1] = bins.ids.size(); stats[2] = 0ull; for(unsigned b=0u; b<nb; b++) if(bins.start[b+1u]-bins.start[b]>stats[2]) stats[2] = bins.start[b+1u]-bins.start[b]; }
+#pragma omp parallel for schedule(dynamic)
+	for(long long b=0; b<(long long)nb; b++) {
+		emu_blockDim = {128u, 1u, 1u}; emu_gridDim = {nb, 1u, 1u};
+		for(unsigned t=0u; t<128u; t++) { emu_blockIdx = {(unsigned)b, 0u, 0u}; emu_threadIdx = {t, 0u, 0u}; k_voxelize_mesh_binned(*c, direction, flag, bb, bins.bins0, bins.start.data(), bins.ids.data(), p0, p1, p2); }
+	}
 	return 0;
 }
 int emu_halo_T(const DomainConst* c, uint32_t axis, int insert, int xfast, float* bp, float* bm) {

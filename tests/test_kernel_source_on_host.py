@@ -205,3 +205,87 @@ def test_boundary_first_strip_order(emu, Ny, Nz, Dy, Dz, TY, TZ):
         return
     assert set(order[:nb].tolist()) == boundary, (sorted(set(order[:nb].tolist()) ^ boundary))
     assert not (set(order[nb:].tolist()) & boundary)
+
+
+# ---------------------------------------------------------------------------------------------- binned mesh voxeliser (csrc/vox_bins.h + k_voxelize_mesh_binned)
+def _city_mesh(shape, boxes, seed):
+    """Many small closed boxes at fractional positions over a base slab: most triangles reach one or two bins only."""
+    rng = np.random.default_rng(seed)
+    Nx, Ny, Nz = shape
+    tris = H._box_tris((1.0, 1.0, 1.0), (Nx - 1.0, Ny - 1.0, 2.3))
+    for _ in range(boxes):
+        cx, cy = rng.uniform(4, Nx - 4), rng.uniform(4, Ny - 4)
+        w, d, h = rng.uniform(1.2, 5.5), rng.uniform(1.2, 5.5), rng.uniform(2.0, Nz - 5.0)
+        tris += H._box_tris((cx - w / 2, cy - d / 2, 1.7), (cx + w / 2, cy + d / 2, 1.7 + h))
+    P = np.array(tris, np.float32)
+    p0, p1, p2 = (np.ascontiguousarray(P[:, k, :]).reshape(-1) for k in range(3))
+    return p0, p1, p2, P.reshape(-1, 3).min(0), P.reshape(-1, 3).max(0)
+
+
+def _voxelize_both(emu, oracle_lib, shape, mesh, direction, D=(1, 1, 1), Ov=(0, 0, 0), preset=False):
+    p0, p1, p2, pmin, pmax = mesh
+    ntri = p0.size // 3
+    bbu = H.vox_bbu(ntri, pmin, pmax)
+    N = int(np.prod(shape))
+    flags, u = np.zeros(N, np.uint8), np.zeros(3 * N, np.float32)
+    if preset:
+        rng = np.random.default_rng(1)
+        flags[:] = rng.choice(np.array([0, 1, 2, 0x40, 0x81], np.uint8), N)
+        u[rng.integers(0, 3 * N, 500)] = 0.01
+    p = oracle_lib.make_params(*shape, oracle_lib.FP16S, oracle_lib.FEATURE_SETS["luw"], D=D, O=Ov, **H.ZONES)
+    want = flags.copy()
+    oracle_lib.Oracle().bind(p).voxelize_mesh(direction, u.copy(), want, 1, p0, p1, p2, bbu)
+    d = HostDomain(emu, shape, 1, H.FEATURE_SETS["luw"], 1.0, H.ZONES, D=D, Ov=Ov)
+    d.put(d.flags, flags, 1); d.put(d.u, u, 3)
+    stats = np.zeros(3, np.uint64)
+    emu.emu_voxelize_binned.argtypes = [C.c_void_p, C.c_uint32, C.c_uint8] + [C.c_void_p] * 3 + [C.c_uint32, C.c_void_p, C.c_void_p]
+    assert emu.emu_voxelize_binned(d.c, direction, 1, _p(p0), _p(p1), _p(p2), ntri, _p(bbu), _p(stats)) == 0
+    return d.get(d.flags, 1), want, stats, ntri
+
+
+@pytest.mark.parametrize("direction", [2, 0, 1], ids=["z-rays", "x-rays", "y-rays"])
+@pytest.mark.parametrize("preset", [False, True], ids=["empty", "preset"])
+def test_binned_voxelizer_source_equals_the_oracle(emu, oracle_lib, direction, preset):
+    """Each block walks only the triangles whose padded projected box reaches its 32 x 4 columns: the flags must be those of the all-triangles voxeliser (the oracle,
+    pinned to the reference's kernel text in test_voxelize.py), on the mesh with grazing rays and on lattices with pre-set flags."""
+    got, want, stats, ntri = _voxelize_both(emu, oracle_lib, H.VOX_SHAPE, H.vox_mesh(), direction, preset=preset)
+    assert np.array_equal(got, want)
+    assert 500 < int(((got & 3) == 1).sum()) < got.size // 2
+
+
+def test_binned_voxelizer_in_a_decomposed_block(emu, oracle_lib):
+    Nx, Ny, Nz = H.VOX_SHAPE
+    shape, D, Ov = (Nx // 2 + 2, Ny, Nz // 2 + 2), (2, 1, 2), (Nx // 2 - 1, 0, Nz // 2 - 1)
+    got, want, _, _ = _voxelize_both(emu, oracle_lib, shape, H.vox_mesh(), 2, D=D, Ov=Ov)
+    assert np.array_equal(got, want) and ((got & 3) == 1).sum() > 50
+
+
+@pytest.mark.parametrize("direction", [2, 1], ids=["z-rays", "y-rays"])
+def test_binned_voxelizer_on_a_city_of_small_boxes(emu, oracle_lib, direction):
+    """400 boxes on a 210 x 150 x 30 lattice (odd extents: partial bins on both axes): identical flags, and the lists are a small fraction of columns x triangles."""
+    shape = (210, 150, 30)
+    got, want, stats, ntri = _voxelize_both(emu, oracle_lib, shape, _city_mesh(shape, 400, 5), direction)
+    assert np.array_equal(got, want)
+    assert int(((got & 3) == 1).sum()) > 20000
+    bins, entries, longest = (int(v) for v in stats)
+    assert entries * 128 < 0.2 * ntri * bins * 128 and longest < ntri  # work in ray/triangle tests: bins x 128 x list length vs columns x all triangles
+
+
+STL = os.path.join(os.path.dirname(HERE), os.pardir, "baseline", "_ref", "case_profile", "proj_temp", "CaseE_PF.stl")
+
+
+@pytest.mark.skipif(not os.path.isfile(STL), reason="baseline/_ref/case_profile (the reference's example project, staged by baseline/build_reference_driver.py) is not here")
+def test_binned_voxelizer_on_the_reference_example_mesh(emu, oracle_lib):
+    """The example project's building mesh (9 210 triangles) scaled onto the example's 253 x 250 x 59 lattice: identical flags with ~300 times fewer ray / triangle tests."""
+    raw = open(STL, "rb").read()
+    n = int(np.frombuffer(raw[80:84], np.uint32)[0])
+    rec = np.frombuffer(raw[84:84 + 50 * n], dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]))
+    V = rec["v"].astype(np.float32)
+    lo, hi = V.reshape(-1, 3).min(0), V.reshape(-1, 3).max(0)
+    shape = (253, 250, 59)
+    scale = np.float32(0.8 * min(shape[0] / (hi[0] - lo[0]), shape[1] / (hi[1] - lo[1])))
+    V = ((V - lo) * scale + np.array([shape[0] * 0.1, shape[1] * 0.1, 0.7], np.float32)).astype(np.float32)
+    mesh = tuple(np.ascontiguousarray(V[:, k, :]).reshape(-1) for k in range(3)) + (V.reshape(-1, 3).min(0), V.reshape(-1, 3).max(0))
+    got, want, stats, ntri = _voxelize_both(emu, oracle_lib, shape, mesh, 2)
+    assert np.array_equal(got, want) and int(((got & 3) == 1).sum()) > 10000
+    assert int(stats[1]) * 128 * 100 < ntri * shape[0] * shape[1]

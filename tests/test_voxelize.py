@@ -51,7 +51,10 @@ def test_oracle_voxelizer_in_a_decomposed_block(oracle_lib):
 @pytest.mark.gpu
 @pytest.mark.parametrize("direction", [2, 0, 1], ids=["z-rays", "x-rays", "y-rays"])
 @pytest.mark.parametrize("preset", [False, True], ids=["empty", "preset"])
-def test_cuda_voxelizer_equals_oracle(oracle_lib, direction, preset):
+@pytest.mark.parametrize("bins", ["1", "0"], ids=["binned", "all-triangles"])
+def test_cuda_voxelizer_equals_oracle(oracle_lib, direction, preset, bins, monkeypatch):
+    """Both device voxelisers: the bin-grid kernel luw_voxelize_mesh takes by default (csrc/vox_bins.h) and the all-triangles kernel behind LUW_VOXELIZE_BINS=0."""
+    monkeypatch.setenv("LUW_VOXELIZE_BINS", bins)
     from latticeurbanwind_b200 import _cabi as A
     from latticeurbanwind_b200.domain import Domain
     O = oracle_lib
