@@ -55,7 +55,7 @@ def build(reference_root="/root/reference"):
           # (the oracle of baseline/_ref/luw_inlet_parity) and this repo's surface-only, GPU-searching ones take the names (host/inlet_outlet_surface.cpp)
           procs = [(u, subprocess.Popen(["g++", *flags, *RENAMED.get(u, []), "-c", u + ".cpp", "-o", u + ".o"], cwd=tmp)) for u in UNITS + ["our_lbm"]]
           open(os.path.join(tmp, "our_inlet.cpp"), "w").write('#include "%s/inlet_outlet_surface.cpp"\n' % host)
-          procs.append(("our_inlet", subprocess.Popen(["g++", *flags, "-c", "our_inlet.cpp", "-o", "our_inlet.o"], cwd=tmp)))
+          procs.append(("our_inlet", subprocess.Popen(["g++", *flags, "-DLUW_INLET_AB_HOOK", "-c", "our_inlet.cpp", "-o", "our_inlet.o"], cwd=tmp)))  # the hook: LUW_INLET_AB=reference, see the file
           for u, p in procs:
               if p.wait() != 0:
                   raise SystemExit(f"compiling {u}.cpp against host/lbm.hpp failed")
@@ -106,6 +106,38 @@ def build(reference_root="/root/reference"):
     # every extent even (250 x 246 x 58)
     deck222 = re.sub(r"(?m)^n_gpu\s*=.*$", "n_gpu = [2, 2, 2]", re.sub(r"(?m)^cell_size\s*=.*$", "cell_size = 8.1", deck))
     open(os.path.join(dst, "conf_222.luwpf"), "w").write(deck222 + "\nrun_nstep = 60\n")
+    # a WRF-style case (.luw deck: boundary values from proj_temp/SurfData_<datetime>.csv, FX/setup.cpp:3600-3610, mapped by apply_inlet_outlet_hd / apply_inlet_outlet):
+    # the reference ships no SurfData (its example_NWP-LBM holds the deck only), so the samples are synthetic -- a log-law wind with a slow horizontal variation on the
+    # five open faces of the example's domain, 50 m x 10 m apart -- over the example's building mesh. Two decks: high_order on (K = 64 fit) and off (nearest sample).
+    dst_nwp = os.path.join(OUT, "case_nwp")
+    shutil.rmtree(dst_nwp, ignore_errors=True)
+    os.makedirs(os.path.join(dst_nwp, "proj_temp"))
+    shutil.copy(os.path.join(reference_root, "examples", "example_ProfileResearch_noDEM", "proj_temp", "CaseE_PF.stl"), os.path.join(dst_nwp, "proj_temp", "CaseE.stl"))
+    os.chmod(os.path.join(dst_nwp, "proj_temp", "CaseE.stl"), 0o644)
+    import math
+    Lx, Ly, Lz = 2022.500153, 1996.500092, 270.0
+    rows = ["X,Y,Z,u,v,w"]
+    def wind(x, y, z):
+        s = 7.8 * math.log(max(z, 1.0) / 0.5) / math.log(Lz / 0.5) * (1.0 + 0.05 * math.sin(x / 311.0) * math.cos(y / 273.0))
+        return s * math.cos(0.2), s * math.sin(0.2), 0.02 * s * math.sin(x / 150.0)
+    def frange(hi, step):
+        n = int(hi / step)
+        return [hi * k / n for k in range(n + 1)]
+    for z in frange(Lz, 10.0):
+        for y in frange(Ly, 50.0):
+            for x in (0.0, Lx):
+                rows.append("%.6f,%.6f,%.6f,%.6f,%.6f,%.6f" % (x, y, z, *wind(x, y, z)))
+        for x in frange(Lx, 50.0)[1:-1]:
+            for y in (0.0, Ly):
+                rows.append("%.6f,%.6f,%.6f,%.6f,%.6f,%.6f" % (x, y, z, *wind(x, y, z)))
+    for y in frange(Ly, 50.0)[1:-1]:
+        for x in frange(Lx, 50.0)[1:-1]:
+            rows.append("%.6f,%.6f,%.6f,%.6f,%.6f,%.6f" % (x, y, Lz, *wind(x, y, Lz)))
+    open(os.path.join(dst_nwp, "proj_temp", "SurfData_20251222120000.csv"), "w").write("\n".join(rows) + "\n")
+    nwp = re.sub(r"(?m)^(x_exp_rat|y_exp_rat|angle)\s*=.*\n", "", deck)
+    nwp = re.sub(r"(?m)^flux_correction\s*=.*$", "flux_correction = true", nwp)
+    open(os.path.join(dst_nwp, "conf.luw"), "w").write(nwp + "\nrun_nstep = 20\n")
+    open(os.path.join(dst_nwp, "conf_nearest.luw"), "w").write(re.sub(r"(?m)^high_order\s*=.*$", "high_order = false", nwp) + "\nrun_nstep = 20\n")
     # the dataset-generation example (BASELINE configs[4], FX/setup.cpp:5690-5753): 16 inflow directions on a fixed 2.5 m grid (400 x 400 x 200), short runs
     src = os.path.join(reference_root, "examples", "example_DatasetGen")
     dst_dg = os.path.join(OUT, "case_dataset")

@@ -37,14 +37,33 @@ __global__ void __launch_bounds__(128) k_inlet_nearest(const uint32_t ncells, co
 // The K-nearest selection of KNNInterpolatorHD::eval for cells that share a face plane. q: the in-plane coordinates (a, b) of the samples ON that plane, in the
 // reference's sample order; cell: SoA a[ncells] b[ncells]. Per cell: exact[c] = first sample with r2 <= 1e-16 (the reference returns that sample's velocity) or -1;
 // otherwise used[c] = number of kept samples (<= 64), kept[64*c + k] = their indices into q in the reference's slot order, max_r2[c] = `max_r2_kept`.
-__global__ void __launch_bounds__(128) k_inlet_knn(const uint32_t ncells, const float* __restrict__ cell, const uint32_t npts, const float2* __restrict__ q,
+constexpr int INLET_KNN_THREADS = 64; // threads per block of k_inlet_knn: 64 slots x (r2, index) + 8 group maxima, x 64 threads = 34 KB of shared memory
+__global__ void __launch_bounds__(INLET_KNN_THREADS) k_inlet_knn(const uint32_t ncells, const float* __restrict__ cell, const uint32_t npts, const float2* __restrict__ q,
 	uint32_t* __restrict__ kept, uint32_t* __restrict__ used, float* __restrict__ max_r2, int32_t* __restrict__ exact) {
-	constexpr int K = INLET_KNN_K;
+	constexpr int K = INLET_KNN_K, T = INLET_KNN_THREADS, G = 8; // G groups of K/G slots
+	// the kept samples of every thread, slot-major: slot k of thread t at [k*T + t] (consecutive threads, consecutive banks). In registers the slots could not be
+	// indexed, in local memory every re-scan for the worst sample went through L1 / L2 to DRAM (first cut of this kernel: 31 GB of DRAM traffic per million cells).
+	__shared__ float s_r2[K*T];
+	__shared__ uint32_t s_i[K*T];
+	__shared__ float s_gmax[G*T]; // largest r2 of each group of 8 slots (-inf if it holds NaN only): the worst sample is found in 8 + 8 loads instead of 64
 	const uint32_t c = blockIdx.x*blockDim.x+threadIdx.x;
 	if(c>=ncells) return;
+	float* best_r2 = s_r2+threadIdx.x;
+	uint32_t* best_i = s_i+threadIdx.x;
+	float* gmax = s_gmax+threadIdx.x;
+	const float ninf = __uint_as_float(0xFF800000u);
+	// The reference's scan `worst = best[0]; for k = 1..63: if(best[k] > worst) ...` picks the FIRST slot that holds the largest value (a NaN in slot 0 stays the worst
+	// for ever, NaN elsewhere is never picked). Same pick, in two levels: first group whose maximum is the largest, first slot of that group that holds it.
+	const auto group_max = [&](const int g) { float m = ninf; for(int k=g*(K/G); k<(g+1)*(K/G); k++) { const float v = best_r2[k*T]; if(v>m) m = v; } gmax[g*T] = m; };
+	const auto find_worst = [&](int& worst_k, float& worst_r2) {
+		const float first = best_r2[0];
+		if(first!=first) { worst_k = 0; worst_r2 = first; return; }
+		int g = 0; float m = gmax[0];
+		for(int j=1; j<G; j++) { const float v = gmax[j*T]; if(v>m) { m = v; g = j; } }
+		worst_k = g*(K/G); worst_r2 = m; // m is a value some slot of group g holds (slot 0 is no NaN here, so group 0's maximum is no -inf and m neither)
+		for(int k=g*(K/G); k<(g+1)*(K/G); k++) if(best_r2[k*T]==m) { worst_k = k; break; }
+	};
 	const float ca = cell[c], cb = cell[(uint64_t)ncells+c];
-	float best_r2[K];
-	uint32_t best_i[K];
 	int filled = 0, worst_k = -1, hit = -1;
 	float max_r2_kept = 0.0f, worst_r2 = 0.0f;
 	for(uint32_t i=0u; i<npts; i++) {
@@ -53,18 +72,18 @@ __global__ void __launch_bounds__(128) k_inlet_knn(const uint32_t ncells, const 
 		const float r2 = __fadd_rn(__fmul_rn(s1, s1), __fmul_rn(s2, s2));
 		if(r2<=1.0E-16f) { hit = (int)i; break; } // `eps2`
 		if(filled<K) {
-			best_r2[filled] = r2; best_i[filled] = i;
+			best_r2[filled*T] = r2; best_i[filled*T] = i;
 			if(r2>max_r2_kept) max_r2_kept = r2;
 			filled++;
 		} else {
 			if(worst_k<0) { // the reference finds the worst kept sample anew for every candidate; it only changes when a sample is replaced
-				worst_k = 0; worst_r2 = best_r2[0];
-				for(int k=1; k<K; k++) if(best_r2[k]>worst_r2) { worst_r2 = best_r2[k]; worst_k = k; }
+				for(int g=0; g<G; g++) group_max(g);
+				find_worst(worst_k, worst_r2);
 			}
 			if(r2<worst_r2) {
-				best_r2[worst_k] = r2; best_i[worst_k] = i;
-				worst_k = 0; worst_r2 = best_r2[0];
-				for(int k=1; k<K; k++) if(best_r2[k]>worst_r2) { worst_r2 = best_r2[k]; worst_k = k; }
+				best_r2[worst_k*T] = r2; best_i[worst_k*T] = i;
+				group_max(worst_k/(K/G));
+				find_worst(worst_k, worst_r2);
 				max_r2_kept = worst_r2;
 			}
 		}
@@ -72,7 +91,7 @@ __global__ void __launch_bounds__(128) k_inlet_knn(const uint32_t ncells, const 
 	exact[c] = hit;
 	used[c] = (uint32_t)filled;
 	max_r2[c] = max_r2_kept;
-	for(int k=0; k<filled; k++) kept[(uint64_t)K*c+(uint64_t)k] = best_i[k];
+	for(int k=0; k<filled; k++) kept[(uint64_t)K*c+(uint64_t)k] = best_i[k*T];
 }
 
 } // namespace luw

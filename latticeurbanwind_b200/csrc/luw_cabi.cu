@@ -950,7 +950,7 @@ int luw_inlet_knn(int device, uint64_t ncells, const float* cell_ab, uint32_t np
 		const uint64_t n = ncells-c0<B ? ncells-c0 : B;
 		for(int k=0; k<2; k++) CU(cudaMemcpy(dc+(uint64_t)k*n, cell_ab+(uint64_t)k*ncells+c0, n*sizeof(float), cudaMemcpyHostToDevice));
 		CU(cudaMemset(dk, 0, K*n*sizeof(uint32_t))); // slots beyond used[c] read as 0
-		luw::k_inlet_knn<<<(unsigned)((n+127ull)/128ull), 128>>>((uint32_t)n, dc, npts, dp, dk, du, dm, de);
+		luw::k_inlet_knn<<<(unsigned)((n+(uint64_t)luw::INLET_KNN_THREADS-1ull)/(uint64_t)luw::INLET_KNN_THREADS), luw::INLET_KNN_THREADS>>>((uint32_t)n, dc, npts, dp, dk, du, dm, de);
 		CU(cudaGetLastError());
 		g_inlet_launches++;
 		CU(cudaMemcpy(kept+K*c0, dk, K*n*sizeof(uint32_t), cudaMemcpyDeviceToHost));

@@ -210,8 +210,21 @@ void luw_inlet_eval_knn(const int device, const KNNInterpolatorHD& knn, const fl
 	}
 }
 
-void apply_inlet_outlet(LBM& lbm, const std::string& downstream_bc, const InletVelocityField& inlet, bool downstream_open_face, unsigned long /*min_work_per_thread*/,
+#ifdef LUW_INLET_AB_HOOK
+// TEST HOOK of the drop-in driver build (baseline/build_reference_driver.py defines the macro): with LUW_INLET_AB=reference in the environment the two functions below hand
+// over to the reference's own, unmodified ones -- linked into the same binary under other names -- so that tests/test_reference_driver.py can run one deck both ways and
+// compare the boundary images byte for byte. Both ways are host-side case set-up; the LBM step is not involved.
+void ref_apply_inlet_outlet(LBM& lbm, const std::string& downstream_bc, const InletVelocityField& inlet, bool downstream_open_face, unsigned long min_work_per_thread, bool show_progress, int side_ref_z_cap_index);
+void ref_apply_inlet_outlet_hd(LBM& lbm, const std::string& downstream_bc, const InletVelocityFieldHD& inlet, bool downstream_open_face, unsigned long min_work_per_thread, bool show_progress, int side_ref_z_cap_index);
+static bool ab_reference() { const char* e = std::getenv("LUW_INLET_AB"); return e&&std::string(e)=="reference"; }
+#endif
+
+void apply_inlet_outlet(LBM& lbm, const std::string& downstream_bc, const InletVelocityField& inlet, bool downstream_open_face, unsigned long min_work_per_thread,
 	bool show_progress, int side_ref_z_cap_index) {
+#ifdef LUW_INLET_AB_HOOK
+	if(ab_reference()) { println("| inlet/outlet init: LUW_INLET_AB=reference -> the reference's own apply_inlet_outlet"); ref_apply_inlet_outlet(lbm, downstream_bc, inlet, downstream_open_face, min_work_per_thread, show_progress, side_ref_z_cap_index); return; }
+#endif
+	(void)min_work_per_thread;
 	const std::vector<SurfaceCell> cells = mark_boundary(lbm, downstream_bc, downstream_open_face, side_ref_z_cap_index);
 	std::vector<float3> pos(cells.size()), u(cells.size());
 	for(size_t i=0u; i<cells.size(); i++) pos[i] = cells[i].pos;
@@ -225,8 +238,12 @@ void apply_inlet_outlet(LBM& lbm, const std::string& downstream_bc, const InletV
 	}
 }
 
-void apply_inlet_outlet_hd(LBM& lbm, const std::string& downstream_bc, const InletVelocityFieldHD& inlet, bool downstream_open_face, unsigned long /*min_work_per_thread*/,
+void apply_inlet_outlet_hd(LBM& lbm, const std::string& downstream_bc, const InletVelocityFieldHD& inlet, bool downstream_open_face, unsigned long min_work_per_thread,
 	bool show_progress, int side_ref_z_cap_index) {
+#ifdef LUW_INLET_AB_HOOK
+	if(ab_reference()) { println("| inlet/outlet init (HD): LUW_INLET_AB=reference -> the reference's own apply_inlet_outlet_hd"); ref_apply_inlet_outlet_hd(lbm, downstream_bc, inlet, downstream_open_face, min_work_per_thread, show_progress, side_ref_z_cap_index); return; }
+#endif
+	(void)min_work_per_thread;
 	const std::vector<SurfaceCell> cells = mark_boundary(lbm, downstream_bc, downstream_open_face, side_ref_z_cap_index);
 	std::vector<float3> pos(cells.size()), u(cells.size());
 	for(size_t i=0u; i<cells.size(); i++) pos[i] = cells[i].pos;

@@ -151,3 +151,34 @@ def test_surface_inlet_outlet_mapping_equals_the_reference_functions():
     assert "80 of 80 runs identical" in r.stdout, r.stdout[-4000:]
     launches = int(r.stdout.strip().rsplit("search kernels launched:", 1)[1])
     assert launches >= 80, "the sample searches did not run on the device"
+
+
+CASE_NWP = os.path.join(ROOT, "baseline", "_ref", "case_nwp")
+
+
+@pytest.mark.skipif(not os.path.isdir(CASE_NWP), reason="baseline/_ref/case_nwp was not staged")
+@pytest.mark.parametrize("deck,marker", [("conf.luw", "K-nearest search on the GPU"), ("conf_nearest.luw", "sample search on the GPU")], ids=["high-order", "nearest"])
+def test_wrf_style_deck_maps_its_boundary_like_the_reference_functions(tmp_path, deck, marker):
+    """SURVEY 8-f2 in place: a .luw deck (boundary values from proj_temp/SurfData_<datetime>.csv: 5 906 synthetic samples on the five open faces, the example's building
+    mesh) through the reference's unmodified case driver, once with this repo's apply_inlet_outlet(_hd) (face cells enumerated, sample searches on the GPU) and once with
+    LUW_INLET_AB=reference, which makes the same binary call the reference's own functions instead. The host images the driver hands to LBM::initialize -- flags, u, rho
+    after boundary mapping AND flux correction -- must be byte-identical, and both runs must finish their 20 steps."""
+    images = {}
+    for mode in ("ours", "reference"):
+        case, dump = str(tmp_path / mode), str(tmp_path / (mode + "_dump"))
+        shutil.copytree(CASE_NWP, case)
+        os.makedirs(dump)
+        env = dict(os.environ, LUW_DUMP_DIR=dump, LUW_DUMP_STEP="20", LUW_VERBOSE="1")
+        if mode == "reference":
+            env["LUW_INLET_AB"] = "reference"
+        r = subprocess.run([DRIVER, os.path.join(case, deck)], capture_output=True, text=True, timeout=900, cwd=case, env=env, stdin=subprocess.DEVNULL)
+        open(os.path.join(ROOT, "gpurun_out", f"reference_driver_nwp_{deck.split('.')[0]}_{mode}.log"), "w").write(r.stdout + "\n---- stderr ----\n" + r.stderr)
+        assert r.returncode == 0, r.stdout[-5000:] + r.stderr[-2000:]
+        assert (marker in r.stdout) == (mode == "ours") and ("LUW_INLET_AB=reference" in r.stdout) == (mode == "reference"), r.stdout[-5000:]
+        images[mode] = {name: open(os.path.join(dump, name + ".bin"), "rb").read() for name in ("init_flags", "init_u", "init_rho", "step_u")}
+    flags = np.frombuffer(images["ours"]["init_flags"], np.uint8)
+    u = np.frombuffer(images["ours"]["init_u"], np.float32)
+    assert int(((flags & 3) == 2).sum()) > 50000 and float(np.abs(u).max()) > 0.01, "the boundary was not mapped"
+    for name in ("init_flags", "init_u", "init_rho"):
+        assert images["ours"][name] == images["reference"][name], f"{name} differs between this repo's boundary mapping and the reference's"
+    assert images["ours"]["step_u"] == images["reference"]["step_u"]
