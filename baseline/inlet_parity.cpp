@@ -108,7 +108,7 @@ int luw_inlet_parity_main(const int device, const bool with_lattices) {
 		}
 	}
 #ifndef LUW_INLET_ON_HOST
-	if(with_lattices) {
+	if(with_lattices&&!getenv("LUW_INLET_PARITY_POSITIONS_ONLY")) { // (the sanitizer runs use the position level only)
 		const uint shapes[3][3] = { { 37u, 29u, 23u }, { 64u, 3u, 17u }, { 5u, 41u, 9u } };
 		const char* downs[5] = { "+x", "-x", "+y", "-y", "none" };
 		for(int s=0; s<3; s++) for(int d=0; d<5; d++) for(int open=0; open<2; open++) for(int hd=0; hd<2; hd++) {

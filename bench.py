@@ -56,6 +56,9 @@ WORKLOADS = {
                             "C3 staggered cube array 1024x1024x256 FP16S, full LUW step with UPDATE_FIELDS and thermal D3Q7 transport (TYPE_E cells carry TYPE_T, alpha = 2e-3)"),
     "urban_fp16c_thermal": ("urban", (1024, 1024, 256), 2, F_UF | F_VF | F_EQ | F_SG | F_NUDGE | F_SPONGE | F_TEMPERATURE, "luwT", 1e-6,
                             "C3 staggered cube array 1024x1024x256 FP16C + UPDATE_FIELDS + TEMPERATURE: the switches LUW ships (FX/defines.hpp:14-24)"),
+    # BASELINE configs[0] size: the example project coarsened to 256 x 256 x 128 (8.4 M cells, 1.3 GB of FP32 DDFs): a launch-latency-sensitive lattice, not a headline
+    "profile256_fp32": ("urban", (256, 256, 128), 0, F_UF | F_VF | F_EQ | F_SG | F_NUDGE | F_SPONGE, "luw", 1e-6,
+                        "C1-sized staggered cube array 256x256x128 FP32, full LUW step with UPDATE_FIELDS (the reference's CPU-runnable configuration)"),
     "urban_fp16c_uf": ("urban", (1024, 1024, 256), 2, F_UF | F_VF | F_EQ | F_SG | F_NUDGE | F_SPONGE, "luw", 1e-6,
                        "C3 staggered cube array 1024x1024x256 FP16C, full LUW step with UPDATE_FIELDS"),
 }
