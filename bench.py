@@ -59,6 +59,12 @@ WORKLOADS = {
     # BASELINE configs[0] size: the example project coarsened to 256 x 256 x 128 (8.4 M cells, 1.3 GB of FP32 DDFs): a launch-latency-sensitive lattice, not a headline
     "profile256_fp32": ("urban", (256, 256, 128), 0, F_UF | F_VF | F_EQ | F_SG | F_NUDGE | F_SPONGE, "luw", 1e-6,
                         "C1-sized staggered cube array 256x256x128 FP32, full LUW step with UPDATE_FIELDS (the reference's CPU-runnable configuration)"),
+    "profile256_fp16c": ("urban", (256, 256, 128), 2, F_UF | F_VF | F_EQ | F_SG | F_NUDGE | F_SPONGE, "luw", 1e-6,
+                         "C1-sized staggered cube array 256x256x128 FP16C, full LUW step with UPDATE_FIELDS (the drop-in driver's default precision on an example-sized lattice)"),
+    "profile256_fp16s": ("urban", (256, 256, 128), 1, F_UF | F_VF | F_EQ | F_SG | F_NUDGE | F_SPONGE, "luw", 1e-6,
+                         "C1-sized staggered cube array 256x256x128 FP16S, full LUW step with UPDATE_FIELDS"),
+    "urban512_fp32": ("urban", (512, 512, 256), 0, F_UF | F_VF | F_EQ | F_SG | F_NUDGE | F_SPONGE, "luw", 1e-6,
+                      "staggered cube array 512x512x256 FP32 (10.2 GB of DDFs), full LUW step with UPDATE_FIELDS"),
     "urban_fp16c_uf": ("urban", (1024, 1024, 256), 2, F_UF | F_VF | F_EQ | F_SG | F_NUDGE | F_SPONGE, "luw", 1e-6,
                        "C3 staggered cube array 1024x1024x256 FP16C, full LUW step with UPDATE_FIELDS"),
 }
@@ -92,12 +98,14 @@ DECOMP = {"channel": {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (1, 2, 4)},
           "urban": {1: (1, 1, 1), 2: (1, 2, 1), 4: (1, 4, 1), 8: (1, 8, 1)}}
 
 
-def kernel_name(tiled, precision, features, arith):
-    """The step kernel(s) of a workload (csrc/luw_cabi.cu setup_tiles / enqueue_step): FAST FP16 storage runs the lean-loop TMA kernel, FP32 and STRICT the single-pass TMA
-    kernel; thermal domains add k_thermal_g behind the momentum kernel (buoyancy-free steps)."""
+def kernel_name(tiled, precision, features, arith, cells=0):
+    """The step kernel(s) of a workload (csrc/luw_cabi.cu setup_tiles / enqueue_step): FAST FP16 storage runs the lean-loop TMA kernel, and so does the FAST FP32 LES step
+    on lattices of 2^25 cells and more; otherwise FP32 and STRICT run the general-loop TMA kernel; thermal domains add k_thermal_g behind the momentum kernel
+    (buoyancy-free steps)."""
     if not tiled:
         return "k_stream_collide_thermal" if features & F_TEMPERATURE else "k_stream_collide"
-    k = "k_stream_collide_lean" if (precision != 0 and arith == "fast") else "k_stream_collide_tile"
+    lean = arith == "fast" and (precision != 0 or (bool(features & F_SG) and not features & F_TEMPERATURE and cells >= 1 << 25))
+    k = "k_stream_collide_lean" if lean else "k_stream_collide_tile"
     return k + " + k_thermal_g" if features & F_TEMPERATURE else k
 
 
@@ -399,7 +407,7 @@ def bench_single(args, workload, arith, A, cases, Domain, CellSet, pinned_empty,
         kern_ms = ms / K
         achieved = N * alg_bytes(precision, features) / (kern_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": kernel_name(d.uses_tiles(), precision, features, args.arith),
+                "kernel": kernel_name(d.uses_tiles(), precision, features, args.arith, N),
                 "kernel_ms": kern_ms, "kernel_ms_isolated": kms / max(kn, 1),
                 "share_of_step": 1.0,
                 "alg_bytes_per_cell": alg_bytes(precision, features), "cells_per_launch": N, "peak_source": peak_src,
@@ -622,7 +630,7 @@ def bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src):
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[precision], "data": "synthetic",
                "config": dict(config_of(args.workload, args.arith, D, Ng), block_per_gpu_incl_halo=list(shape), halo_transport=args.transport),
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                            "kernel": kernel_name(True, precision, features, args.arith), "kernel_ms": kern_ms, "share_of_step": kern_ms / (ms / K), "alg_bytes_per_cell": alg_bytes(precision, features),
+                            "kernel": kernel_name(True, precision, features, args.arith, Nloc), "kernel_ms": kern_ms, "share_of_step": kern_ms / (ms / K), "alg_bytes_per_cell": alg_bytes(precision, features),
                             "cells_per_launch": Nloc, "peak_source": peak_src},
                "halo": halo_of(r0),
                "e2e": {"value": mlups, "unit": "MLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,

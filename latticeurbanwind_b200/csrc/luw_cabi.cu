@@ -174,10 +174,12 @@ void setup_tiles(luw_domain* d) {
 	const char* var = getenv("LUW_TILE_VARIANT");
 	// default (measured, profiles/r2_variant_sweeps.txt): FP16S and FP16C -> the lean-loop two-pass kernel, 128x4 tiles with 8 consumer warps per producer for the LES step (V5),
 	// 128x2 tiles and 5 CTAs/SM without LES (V6) -- for FP16C too since the lean loop: 55.8 (V6) / 51.4 (V5) against 48.2 GLUP/s (single-pass V3) on the channel, 38.9 against 31.2 on
-	// the urban LES step with UPDATE_FIELDS; FP32 -> single pass (V0) without LES (HBM-bound: 0.98 of the copy peak on the channel), its two-pass twin (V1) for the LES step
-	// (C1-sized 256 x 256 x 128 lattice with UPDATE_FIELDS: 27.7 against 24.5 GLUP/s; lean loop V5 27.3; profiles/r2_variant_sweeps.txt call Z).
+	// the urban LES step with UPDATE_FIELDS; FP32 -> single pass (V0) without LES (HBM-bound: 0.98 of the copy peak on the channel); for the LES step the two-pass kernels:
+	// the lean loop (V5) on large lattices (512 x 512 x 256 with UPDATE_FIELDS: 35.8 GLUP/s = 0.84 of the copy peak at 153 B per cell, V1 34.9, V0 30.0), its general-loop twin (V1)
+	// on small ones (C1-sized 256 x 256 x 128: 27.7, V5 27.3, V0 24.5; profiles/r2_variant_sweeps.txt calls Z / ZA).
 	// STRICT arithmetic runs k_stream_collide_tile on the same tile shapes.
-	const int want = (var&&var[0]) ? atoi(var) : d->c.precision==luw::P_FP32 ? ((d->c.features&luw::F_SUBGRID) ? 1 : 0) : ((d->c.features&luw::F_SUBGRID) ? 5 : 6);
+	const bool large = (uint64_t)d->c.Nx*d->c.Ny*d->c.Nz>=(1ull<<25);
+	const int want = (var&&var[0]) ? atoi(var) : d->c.precision==luw::P_FP32 ? ((d->c.features&luw::F_SUBGRID) ? (large ? 5 : 1) : 0) : ((d->c.features&luw::F_SUBGRID) ? 5 : 6);
 	const luw::DomainConst& c = d->c;
 	// odd Nx: the row's last pair holds one cell (rows are padded to Px, a multiple of 16 elements); lbm_tile.cuh `odd_end`
 	encode_tiled_fn enc = get_encode_tiled();
