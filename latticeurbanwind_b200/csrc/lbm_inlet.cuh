@@ -66,11 +66,10 @@ __global__ void __launch_bounds__(INLET_KNN_THREADS) k_inlet_knn(const uint32_t 
 	const float ca = cell[c], cb = cell[(uint64_t)ncells+c];
 	int filled = 0, worst_k = -1, hit = -1;
 	float max_r2_kept = 0.0f, worst_r2 = 0.0f;
-	for(uint32_t i=0u; i<npts; i++) {
-		const float2 p = __ldg(q+i);
-		const float s1 = __fsub_rn(p.x, ca), s2 = __fsub_rn(p.y, cb);
-		const float r2 = __fadd_rn(__fmul_rn(s1, s1), __fmul_rn(s2, s2));
-		if(r2<=1.0E-16f) { hit = (int)i; break; } // `eps2`
+	const auto dist2 = [&](const float a, const float b) { const float s1 = __fsub_rn(a, ca), s2 = __fsub_rn(b, cb); return __fadd_rn(__fmul_rn(s1, s1), __fmul_rn(s2, s2)); };
+	// one sample of the reference's loop body; true: the sample coincides with the cell (`r2 <= eps2`), the scan ends
+	const auto consider = [&](const uint32_t i, const float r2) {
+		if(r2<=1.0E-16f) { hit = (int)i; return true; }
 		if(filled<K) {
 			best_r2[filled*T] = r2; best_i[filled*T] = i;
 			if(r2>max_r2_kept) max_r2_kept = r2;
@@ -87,7 +86,18 @@ __global__ void __launch_bounds__(INLET_KNN_THREADS) k_inlet_knn(const uint32_t 
 				max_r2_kept = worst_r2;
 			}
 		}
+		return false;
+	};
+	uint32_t i = 0u;
+	// four samples per trip: their distances are independent of each other (the loop is latency-bound otherwise: three resident warps per scheduler); once the slots are
+	// full almost every trip ends at the first test -- none of the four is nearer than the worst kept sample. Candidates go through the reference's body in sample order.
+	for(; i+4u<=npts&&hit<0; i+=4u) {
+		const float4 pa = __ldg((const float4*)(q+i)), pb = __ldg((const float4*)(q+i+2u));
+		const float r0 = dist2(pa.x, pa.y), r1 = dist2(pa.z, pa.w), r2 = dist2(pb.x, pb.y), r3 = dist2(pb.z, pb.w);
+		if(worst_k>=0&&!(r0<worst_r2||r1<worst_r2||r2<worst_r2||r3<worst_r2)&&r0>1.0E-16f&&r1>1.0E-16f&&r2>1.0E-16f&&r3>1.0E-16f) continue;
+		if(consider(i, r0)||consider(i+1u, r1)||consider(i+2u, r2)||consider(i+3u, r3)) break;
 	}
+	for(; i<npts&&hit<0; i++) { const float2 p = __ldg(q+i); if(consider(i, dist2(p.x, p.y))) break; }
 	exact[c] = hit;
 	used[c] = (uint32_t)filled;
 	max_r2[c] = max_r2_kept;

@@ -187,7 +187,10 @@ void setup_tiles(luw_domain* d) {
 	luw::TileShape sh;
 	bool found = false;
 	const int fallback = d->c.precision==luw::P_FP32 ? 0 : 5; // thermal domains: the one variant per precision their momentum kernel is built for
-	for(int v : { want, fallback, 0, 2 }) { // 2: 64-wide tiles for narrow lattices // the requested variant, else one whose tile is not wider than the lattice
+	// FP32 LES: the single-pass and the two-pass kernels differ in their FAST roundings, so a narrow block of a decomposition must not drop to single pass (V0 / V2) while the
+	// others run two-pass: its fallbacks are the two-pass variants (V1, 64-wide V7) first. Thermal FP32 domains have V0 only and take it on every block alike.
+	const bool fp32_les = !(var&&var[0])&&d->c.precision==luw::P_FP32&&(d->c.features&luw::F_SUBGRID)&&!(d->c.features&luw::F_TEMPERATURE);
+	for(int v : { want, fp32_les ? 1 : fallback, fp32_les ? 7 : 0, fp32_les ? 0 : 2, 2 }) { // 2: 64-wide tiles for narrow lattices // the requested variant, else one whose tile is not wider than the lattice
 		if(d->ks->tile_shape(c.precision, c.features, v, &sh)&&c.Nx>=(uint32_t)sh.tx) { d->tile_variant = v; found = true; break; }
 	}
 	if(!found) return;

@@ -198,6 +198,36 @@ def test_fast_result_does_not_depend_on_the_tile_variant(monkeypatch, variant, s
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
 
 
+@pytest.mark.parametrize("variant,shape", [(5, (256, 24, 12)), (7, (256, 24, 12))], ids=["V5-lean", "V7-64wide"])
+def test_fp32_two_pass_variants_agree(monkeypatch, variant, shape):
+    """The FP32 LES step runs two-pass by default (V1; the lean loop V5 on large lattices; V7 = two-pass on 64-wide tiles for blocks narrower than 128 cells,
+    csrc/luw_cabi.cu setup_tiles): all three must produce V1's bits, or a decomposed FP32 run would depend on how wide its blocks are."""
+    flags, rho, u, w = _bench_case("luw", shape)
+    res = []
+    for v in (1, variant):
+        monkeypatch.setenv("LUW_TILE_VARIANT", str(v))
+        res.append(H.run_cuda(shape, 0, H.FEATURE_SETS["luw"], flags, rho, u, 11, w, arith=1, zones=BENCH_ZONES, expect_tiles=True))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+
+
+@pytest.mark.parametrize("arith", [0, 1], ids=["strict", "fast"])
+def test_fp32_les_on_a_narrow_lattice_takes_the_64_wide_two_pass_tiles(oracle_lib, monkeypatch, arith):
+    """66 cells wide (a block of a 128-cell lattice split in x): no explicit variant, so setup_tiles falls through V1 to V7. STRICT equals the oracle bit for bit, FAST within tolerance."""
+    O = oracle_lib
+    monkeypatch.delenv("LUW_TILE_VARIANT", raising=False)
+    shape = (66, 24, 12)
+    flags, rho, u, w = _bench_case("luw", shape)
+    feat = H.FEATURE_SETS["luw"]
+    ref = H.run_cpu(O.Oracle(), O, shape, 0, feat, flags, rho, u, 9, w, zones=BENCH_ZONES)
+    got = H.run_cuda(shape, 0, feat, flags, rho, u, 9, w, arith=arith, zones=BENCH_ZONES, expect_tiles=True)
+    if arith == 0:
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+    else:
+        e = H.errors(got, ref)
+        tol = TOL_TILED_FAST[0]
+        assert e[0] <= tol["rel_l2_u"] and e[1] <= tol["max_abs_u"] and e[2] <= tol["rel_l2_rho"], e
+
+
 # 100 steps at BASELINE configs[0] size (SURVEY 8c: "FP16S: CUDA-FP16S vs oracle-FP16S, rel-L2(u) <= 1e-4 after 100 steps" was a proposal to be calibrated).
 # Measured values are printed and recorded (gpurun_out/parity_measured.jsonl -> profiles/); the bars are <= 3x measured. For the 16-bit formats the floor
 # is the storage format itself: a FAST value that differs from the STRICT one in its last float bits rounds to the neighbouring 16-bit code with
