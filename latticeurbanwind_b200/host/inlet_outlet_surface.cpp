@@ -18,6 +18,7 @@
 // (tests/test_reference_driver.py, on the GPU); tests/test_inlet_surface_on_host.py checks the same code against the reference's eval() in the GPU-less container, with
 // the kernel source compiled for the host.
 #include "setup.hpp" // everything the two headers below include, before `private` is redefined
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
@@ -191,22 +192,27 @@ void luw_inlet_eval_knn(const int device, const KNNInterpolatorHD& knn, const fl
 			const float dist = plane==0 ? std::fabs(P[i].x-xmin) : plane==1 ? std::fabs(P[i].x-xmax) : plane==2 ? std::fabs(P[i].y-ymin) : plane==3 ? std::fabs(P[i].y-ymax) : std::fabs(P[i].z-zmax);
 			if(dist<=plane_tol) { on_plane.push_back(i); q.push_back(a_of(P[i])); q.push_back(b_of(P[i])); }
 		}
-		std::vector<float> cell(2u*n);
-		for(size_t k=0u; k<n; k++) { cell[k] = a_of(pos[cells[k]]); cell[n+k] = b_of(pos[cells[k]]); }
-		std::vector<uint> kept((size_t)LUW_INLET_KNN_K*n), used(n); std::vector<float> max_r2(n); std::vector<int> exact(n);
-		check(luw_inlet_knn(device, (uint64_t)n, cell.data(), (uint32_t)on_plane.size(), q.data(), kept.data(), used.data(), max_r2.data(), exact.data()));
-		parallel_over(n, [&](const size_t k) {
-			float3& out = u[cells[k]];
-			if(exact[k]>=0) { out = U[on_plane[exact[k]]]; return; }
-			KeptSample s[LUW_INLET_KNN_K];
-			const float ca = cell[k], cb = cell[n+k];
-			for(uint j=0u; j<used[k]; j++) {
-				const uint slot = kept[(size_t)LUW_INLET_KNN_K*k+j];
-				const float s1 = q[2u*slot]-ca, s2 = q[2u*slot+1u]-cb;
-				s[j] = KeptSample{ (double)s1, (double)s2, U[on_plane[slot]] };
-			}
-			out = fit_kept(s, (int)used[k], max_r2[k]);
-		});
+		// in batches, so that the table of kept samples (256 B per cell) stays bounded on the host as well (LUW_INLET_BATCH: test hook for the batching itself)
+		static const size_t batch = []{ const char* e = std::getenv("LUW_INLET_BATCH"); const long v = e ? std::atol(e) : 0l; return v>0l ? (size_t)v : (size_t)1u<<20; }();
+		std::vector<float> cell(2u*std::min(n, batch));
+		std::vector<uint> kept((size_t)LUW_INLET_KNN_K*std::min(n, batch)), used(std::min(n, batch)); std::vector<float> max_r2(std::min(n, batch)); std::vector<int> exact(std::min(n, batch));
+		for(size_t c0=0u; c0<n; c0+=batch) {
+			const size_t m = std::min(batch, n-c0);
+			for(size_t k=0u; k<m; k++) { cell[k] = a_of(pos[cells[c0+k]]); cell[m+k] = b_of(pos[cells[c0+k]]); }
+			check(luw_inlet_knn(device, (uint64_t)m, cell.data(), (uint32_t)on_plane.size(), q.data(), kept.data(), used.data(), max_r2.data(), exact.data()));
+			parallel_over(m, [&](const size_t k) {
+				float3& out = u[cells[c0+k]];
+				if(exact[k]>=0) { out = U[on_plane[exact[k]]]; return; }
+				KeptSample s[LUW_INLET_KNN_K];
+				const float ca = cell[k], cb = cell[m+k];
+				for(uint j=0u; j<used[k]; j++) {
+					const uint slot = kept[(size_t)LUW_INLET_KNN_K*k+j];
+					const float s1 = q[2u*slot]-ca, s2 = q[2u*slot+1u]-cb;
+					s[j] = KeptSample{ (double)s1, (double)s2, U[on_plane[slot]] };
+				}
+				out = fit_kept(s, (int)used[k], max_r2[k]);
+			});
+		}
 	}
 }
 

@@ -24,7 +24,10 @@ def test_inlet_mapping_equals_the_reference_functors_on_host():
         if not os.path.isdir("/root/reference"):
             pytest.skip("baseline/_ref/luw_inlet_parity_on_host is missing or stale and the reference tree is not here to rebuild it")
         subprocess.check_call([sys.executable, os.path.join(ROOT, "baseline", "build_reference_driver.py")], env=dict(os.environ, LUW_DROPIN_SKIP_T="1"), stdout=subprocess.DEVNULL)
-    r = subprocess.run([EXE], capture_output=True, text=True, timeout=600, stdin=subprocess.DEVNULL)
-    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-1000:]
-    assert "20 of 20 runs identical" in r.stdout, r.stdout[-4000:]
-    assert r.stdout.count("IDENTICAL") == 20
+    for batch in ("", "777"):  # default batching (one batch here) and 777 cells per call of the K-nearest search
+        r = subprocess.run([EXE], capture_output=True, text=True, timeout=600, stdin=subprocess.DEVNULL, env=dict(os.environ, LUW_INLET_BATCH=batch))
+        assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-1000:]
+        assert "20 of 20 runs identical" in r.stdout, r.stdout[-4000:]
+        assert r.stdout.count("IDENTICAL") == 20
+        launches = int(r.stdout.strip().rsplit("search kernels launched:", 1)[1])
+        assert (launches > 50) if batch else (launches == 50), launches
