@@ -273,6 +273,7 @@ def main():
     ap.add_argument("--decomp", default="", help="N>1: Dx,Dy,Dz (product = N); default: see DECOMP")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-multi", type=int, default=1, help="N>1: 1 = measure the end-to-end leg on all ranks (per-step boundary upload and probe read-back on every rank), 0 = skip it")
     ap.add_argument("--also", default=None, help="comma-separated extra workloads measured after the headline one (N=1) and reported under `also`; "
                                                  "default: urban_fp16s_uf and the channel workloads when the headline is the default one")
     ap.add_argument("--sustain", type=float, default=2.0, help="seconds of back-to-back steps for the `sustained` figure (0: skip)")
@@ -564,7 +565,7 @@ def bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src):
     assert len(D0) == 3 and D0[0] * D0[1] * D0[2] == world, "--decomp must multiply to the number of ranks"
     K, W = args.steps, args.warmup
 
-    def run_decomp(D):
+    def run_decomp(D, with_e2e=False):
         """One weak-scaling measurement: every rank owns a block of the workload's local size (halo layers included) of a lattice decomposed as D."""
         H = tuple(1 if v > 1 else 0 for v in D)
         Ng = tuple((n - 2 * h) * v for n, h, v in zip(shape, H, D))  # global lattice whose blocks have exactly the workload's local size incl. halos
@@ -582,11 +583,13 @@ def bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src):
             lbm.upload_slabs(slabs())
             dist.barrier()
             lbm.initialize()
+            flags_local = None
         else:
             flags, rho, u = cases.block_case(case, Ng, lbm.O, shape)
             T = thermal_fields(flags, shape) if features & F_TEMPERATURE else None  # per-block stratification: a benchmark input, not a physical profile across blocks
             dist.barrier()  # host-side case generation takes seconds and not the same number on every rank: start the first halo exchange together
             lbm.initialize(flags, rho, u, T)
+            flags_local = flags
         lbm.run(W)
         torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
         launches0, over0 = lbm.domain.launch_count(), lbm.domain.overlapped_steps()
@@ -601,6 +604,7 @@ def bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src):
         lbm.domain.kernel_timing(True); lbm.run(K); kms, kn = lbm.domain.kernel_timing_read(); lbm.domain.kernel_timing(False)
         kern = torch.tensor([kms / max(kn, 1)], device="cuda")
         dist.all_reduce(kern, op=dist.ReduceOp.MAX)
+        e2e = multi_e2e(lbm, flags_local, min(K, 100)) if with_e2e and args.e2e_multi and not args.no_e2e else None
         out = None
         if rank == 0:
             ms, kern_ms = float(ms.item()), float(kern.item())
@@ -609,13 +613,69 @@ def bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src):
             achieved = Nloc * alg_bytes(precision, features) / (kern_ms * 1e-3) / 1e9
             halo_bytes = sum(2 * lbm.halo_bytes(A.HALO_FI, a) for a in range(3) if D[a] > 1)
             out = dict(mlups=mlups, ms=ms, kern_ms=kern_ms, achieved=achieved, halo_bytes=int(halo_bytes), launches=int(launches), overlapped=int(overlapped), Ng=Ng, D=D)
+            if isinstance(e2e, dict) and "seconds" in e2e:
+                e2e = dict(e2e, value=Nglob * e2e["steps"] / e2e.pop("seconds") / 1e6, unit="MLUP/s")
+            out["e2e"] = e2e
         lbm.close()
         return out
+
+    def multi_e2e(lbm, flags_local, Ke):
+        """The same metric end to end at N ranks: every step, every rank uploads the velocity of its block's TYPE_E cells (the boundary values a case driver refreshes) from
+        pinned host memory, all ranks step together (halo exchange included), every rank reads rho / u of a probe plane of its block back. Wall clock between two barriers,
+        MAX over ranks; the byte counts are sums over the ranks. Everything that can fail (cell sets, pinned buffers, one upload and one read-back) happens BEFORE the ranks
+        agree, through an all-reduce, to run the loop -- a rank must not drop out of a collective step loop."""
+        ok, why, cin = 1, "", None
+        try:
+            if flags_local is None:
+                raise RuntimeError("the block was uploaded slab by slab and has no host image to take the boundary cells from")
+            from latticeurbanwind_b200.domain import CellSet, pinned_empty
+            dom = lbm.domain
+            Nx, Ny, Nz = shape
+            bc = np.flatnonzero((flags_local & 3) == 2).astype(np.uint64)
+            yz = (np.arange(Ny, dtype=np.uint64)[None, :] + np.arange(Nz, dtype=np.uint64)[:, None] * np.uint64(Ny)).reshape(-1) * np.uint64(Nx)
+            if bc.size == 0:
+                bc = yz + np.uint64(1)
+            probe = yz + np.uint64(Nx - 2)
+            cin, cpr = CellSet(dom, bc), CellSet(dom, probe)
+            RING = 4
+            uins = [pinned_empty(3 * cin.count, np.float32) for _ in range(RING)]
+            uprs = [pinned_empty(3 * cpr.count, np.float32) for _ in range(RING)]
+            rprs = [pinned_empty(cpr.count, np.float32) for _ in range(RING)]
+            cin.download(A.FIELD_U, uins[0]); dom.finish_queue()  # the values that are there: the loop re-uploads them (the flow is not disturbed)
+            for b in uins[1:]:
+                b[:] = uins[0]
+            cin.upload(A.FIELD_U, uins[1]); cpr.download(A.FIELD_U, uprs[0]); cpr.download(A.FIELD_RHO, rprs[0]); dom.finish_queue()
+        except Exception as exc:
+            ok, why = 0, str(exc)
+        agree = torch.tensor([ok], device="cuda", dtype=torch.int32)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        if int(agree.item()) != 1:
+            return {"unavailable": why or "another rank could not set the loop up"}
+        dom = lbm.domain
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(Ke):
+            r = k % RING
+            cin.upload(A.FIELD_U, uins[r])
+            lbm.run(1)
+            cpr.download(A.FIELD_U, uprs[r]); cpr.download(A.FIELD_RHO, rprs[r])
+            if r == RING - 1:
+                dom.finish_queue()
+        dom.finish_queue(); torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        nbytes = torch.tensor([uins[0].nbytes, uprs[0].nbytes + rprs[0].nbytes], device="cuda", dtype=torch.int64)
+        dist.all_reduce(nbytes, op=dist.ReduceOp.SUM)
+        probe_mean = float(uprs[(Ke - 1) % RING][:cpr.count].mean())
+        cin.close(); cpr.close()
+        return {"seconds": float(dt.item()), "steps": Ke, "h2d_bytes_per_step": int(nbytes[0].item()), "d2h_bytes_per_step": int(nbytes[1].item()), "ms_per_step": float(dt.item()) / Ke * 1e3,
+                "probe_mean_ux_rank0": probe_mean,
+                "timer": "host wall clock between two barriers around K x (every rank: boundary-cell velocity upload from pinned memory, one step with its halo exchange, probe-plane rho / u read-back), host sync every 4th step, MAX over ranks; bytes summed over ranks"}
 
     clk = ClockSampler(local)
     if rank == 0:
         clk.start()
-    r0 = run_decomp(D0)
+    r0 = run_decomp(D0, True)
     clocks = clk.stop() if rank == 0 else None
     # the reference README's layouts at 8 GPUs (FX/lbm.cpp:1066-1073: d = x + (y + z*Dy)*Dx), reported beside the default one
     extra = [d for d in ((8, 1, 1), (2, 2, 2)) if world == 8 and not args.decomp and d != D0 and args.also_default]
@@ -633,8 +693,9 @@ def bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src):
                             "kernel": kernel_name(True, precision, features, args.arith, Nloc), "kernel_ms": kern_ms, "share_of_step": kern_ms / (ms / K), "alg_bytes_per_cell": alg_bytes(precision, features),
                             "cells_per_launch": Nloc, "peak_source": peak_src},
                "halo": halo_of(r0),
-               "e2e": {"value": mlups, "unit": "MLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                       "note": "N>1: the multi-rank loop IS the host-API loop (DistributedLBM.run); per-step boundary upload / probe read-back are measured at N=1"},
+               "e2e": r0["e2e"] if isinstance(r0.get("e2e"), dict) and "value" in r0["e2e"] else
+                      {"value": mlups, "unit": "MLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                       "note": "N>1: the multi-rank loop IS the host-API loop (DistributedLBM.run); the per-step boundary upload / probe read-back leg did not run here: " + str((r0.get("e2e") or {}).get("unavailable", "switched off"))},
                "clocks": clocks, "gpu_launches": r0["launches"]}
         if also:
             res["also"] = [{"decomposition": list(r["D"]), "lattice": list(r["Ng"]), "value": r["mlups"], "unit": "MLUP/s", "ms_per_step": r["ms"] / K, "kernel_ms": r["kern_ms"],
