@@ -620,8 +620,8 @@ def bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src):
         return out
 
     def multi_e2e(lbm, flags_local, Ke):
-        """The same metric end to end at N ranks: every step, every rank uploads the velocity of its block's TYPE_E cells (the boundary values a case driver refreshes) from
-        pinned host memory, all ranks step together (halo exchange included), every rank reads rho / u of a probe plane of its block back. Wall clock between two barriers,
+        """The same metric end to end at N ranks: every step, every rank uploads the velocity of its block's inflow-face cells (x = 0 plane, TYPE_E; the x = 1 plane for blocks away from the
+        inflow face) from pinned host memory, all ranks step together (halo exchange included), every rank reads rho / u of a probe plane of its block back. Wall clock between two barriers,
         MAX over ranks; the byte counts are sums over the ranks. Everything that can fail (cell sets, pinned buffers, one upload and one read-back) happens BEFORE the ranks
         agree, through an all-reduce, to run the loop -- a rank must not drop out of a collective step loop."""
         ok, why, cin = 1, "", None
@@ -631,10 +631,10 @@ def bench_multi(args, arith, A, cases, rank, world, local, peak, peak_src):
             from latticeurbanwind_b200.domain import CellSet, pinned_empty
             dom = lbm.domain
             Nx, Ny, Nz = shape
-            bc = np.flatnonzero((flags_local & 3) == 2).astype(np.uint64)
             yz = (np.arange(Ny, dtype=np.uint64)[None, :] + np.arange(Nz, dtype=np.uint64)[:, None] * np.uint64(Ny)).reshape(-1) * np.uint64(Nx)
+            bc = yz[flags_local[yz.astype(np.int64)] == 2]  # TYPE_E cells of the block's x = 0 plane: the inflow face, as in the N = 1 loop (e2e_steps)
             if bc.size == 0:
-                bc = yz + np.uint64(1)
+                bc = yz + np.uint64(1)  # a block away from the inflow face refreshes its x = 1 plane instead (same bytes, same kernels; the values are the ones already there)
             probe = yz + np.uint64(Nx - 2)
             cin, cpr = CellSet(dom, bc), CellSet(dom, probe)
             RING = 4
