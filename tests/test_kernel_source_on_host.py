@@ -289,3 +289,37 @@ def test_binned_voxelizer_on_the_reference_example_mesh(emu, oracle_lib):
     got, want, stats, ntri = _voxelize_both(emu, oracle_lib, shape, mesh, 2)
     assert np.array_equal(got, want) and int(((got & 3) == 1).sum()) > 10000
     assert int(stats[1]) * 128 * 100 < ntri * shape[0] * shape[1]
+
+
+def _rotated_prisms(shape, count, seed):
+    """Extruded buildings with oblique walls (footprints rotated by arbitrary angles, one of them by exactly 45 degrees through lattice points) and a tilted roof each:
+    vertical triangles whose projection along z is a line segment (zero projected area), the case in which a barycentric ray test is at its most fragile."""
+    rng = np.random.default_rng(seed)
+    Nx, Ny, Nz = shape
+    tris = H._box_tris((1.0, 1.0, 1.0), (Nx - 1.0, Ny - 1.0, 2.3))
+    for k in range(count):
+        cx, cy = rng.uniform(10, Nx - 10), rng.uniform(10, Ny - 10)
+        w, d, h = rng.uniform(2.5, 7.5), rng.uniform(2.5, 7.5), rng.uniform(3.0, Nz - 6.0)
+        ang = np.pi / 4 if k == 0 else rng.uniform(0, np.pi)
+        if k == 0:
+            cx, cy, w, d = 20.5, 20.5, 8.0 * np.sqrt(2.0), 4.0 * np.sqrt(2.0)  # corners on lattice points, walls along the diagonals through cell centres
+        c, s = np.cos(ang), np.sin(ang)
+        corners = [(cx + c * a - s * b, cy + s * a + c * b) for a, b in ((-w / 2, -d / 2), (w / 2, -d / 2), (w / 2, d / 2), (-w / 2, d / 2))]
+        z0, top = 1.7, [1.7 + h, 1.7 + h + 0.8, 1.7 + h + 1.1, 1.7 + h + 0.3]
+        lo = [np.array([x, y, z0], np.float32) for x, y in corners]
+        hi = [np.array([x, y, z], np.float32) for (x, y), z in zip(corners, top)]
+        tris += [(lo[0], lo[2], lo[1]), (lo[0], lo[3], lo[2]), (hi[0], hi[1], hi[2]), (hi[0], hi[2], hi[3])]
+        for i in range(4):
+            j = (i + 1) % 4
+            tris += [(lo[i], lo[j], hi[j]), (lo[i], hi[j], hi[i])]
+    P = np.array(tris, np.float32)
+    p0, p1, p2 = (np.ascontiguousarray(P[:, k, :]).reshape(-1) for k in range(3))
+    return p0, p1, p2, P.reshape(-1, 3).min(0), P.reshape(-1, 3).max(0)
+
+
+@pytest.mark.parametrize("direction", [2, 0], ids=["z-rays", "x-rays"])
+def test_binned_voxelizer_with_oblique_vertical_walls(emu, oracle_lib, direction):
+    shape = (96, 80, 28)
+    got, want, stats, ntri = _voxelize_both(emu, oracle_lib, shape, _rotated_prisms(shape, 40, 17), direction)
+    assert np.array_equal(got, want), f"{int((got != want).sum())} cells differ"
+    assert int(((got & 3) == 1).sum()) > 5000
