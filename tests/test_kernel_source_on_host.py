@@ -276,7 +276,8 @@ STL = os.path.join(os.path.dirname(HERE), os.pardir, "baseline", "_ref", "case_p
 
 @pytest.mark.skipif(not os.path.isfile(STL), reason="baseline/_ref/case_profile (the reference's example project, staged by baseline/build_reference_driver.py) is not here")
 def test_binned_voxelizer_on_the_reference_example_mesh(emu, oracle_lib):
-    """The example project's building mesh (9 210 triangles) scaled onto the example's 253 x 250 x 59 lattice: identical flags with ~300 times fewer ray / triangle tests."""
+    """The example project's building mesh (9 210 triangles) scaled onto the example's 253 x 250 x 59 lattice: identical flags with ~70 times fewer ray / triangle tests
+    (about 1 % of its triangles are ill-conditioned in projection and are tested by every column, csrc/vox_bins.h "Conditioning")."""
     raw = open(STL, "rb").read()
     n = int(np.frombuffer(raw[80:84], np.uint32)[0])
     rec = np.frombuffer(raw[84:84 + 50 * n], dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]))
@@ -288,7 +289,7 @@ def test_binned_voxelizer_on_the_reference_example_mesh(emu, oracle_lib):
     mesh = tuple(np.ascontiguousarray(V[:, k, :]).reshape(-1) for k in range(3)) + (V.reshape(-1, 3).min(0), V.reshape(-1, 3).max(0))
     got, want, stats, ntri = _voxelize_both(emu, oracle_lib, shape, mesh, 2)
     assert np.array_equal(got, want) and int(((got & 3) == 1).sum()) > 10000
-    assert int(stats[1]) * 128 * 100 < ntri * shape[0] * shape[1]
+    assert int(stats[1]) * 128 * 30 < ntri * shape[0] * shape[1]
 
 
 def _rotated_prisms(shape, count, seed):
@@ -323,3 +324,25 @@ def test_binned_voxelizer_with_oblique_vertical_walls(emu, oracle_lib, direction
     got, want, stats, ntri = _voxelize_both(emu, oracle_lib, shape, _rotated_prisms(shape, 40, 17), direction)
     assert np.array_equal(got, want), f"{int((got != want).sum())} cells differ"
     assert int(((got & 3) == 1).sum()) > 5000
+
+
+def test_binned_voxelizer_with_degenerate_slivers(emu, oracle_lib):
+    """1 500 vertical slivers whose three corners project onto one line up to rounding (half of them through lattice points): the reference's barycentric test answers
+    with rounding noise for rays near such a line, several sliver lengths away -- and those answers are its flags. The bin grid hands such triangles to every column
+    (csrc/vox_bins.h "Conditioning"; without that rule this mesh differs from the all-triangles result in ~100 cells), so the flags stay identical."""
+    shape = (96, 80, 28)
+    rng = np.random.default_rng(3)
+    tris = H._box_tris((1.0, 1.0, 1.0), (95.0, 79.0, 2.3))
+    for k in range(1500):
+        if k % 2 == 0:
+            ax, ay, dx, dy = rng.integers(5, 60) + 0.0, rng.integers(5, 50) + 0.0, rng.integers(1, 4) * 1.0, rng.integers(1, 4) * 1.0
+        else:
+            ax, ay, dx, dy = rng.uniform(5, 60), rng.uniform(5, 50), rng.uniform(-3, 3), rng.uniform(-3, 3)
+        t1, t2 = rng.uniform(0.5, 6), rng.uniform(0.5, 6)
+        tris.append((np.array([ax, ay, rng.uniform(2, 10)], np.float32), np.array([ax + t1 * dx, ay + t1 * dy, rng.uniform(2, 10)], np.float32),
+                     np.array([ax + t2 * dx, ay + t2 * dy, rng.uniform(10, 20)], np.float32)))
+    P = np.array(tris, np.float32)
+    mesh = tuple(np.ascontiguousarray(P[:, k, :]).reshape(-1) for k in range(3)) + (P.reshape(-1, 3).min(0), P.reshape(-1, 3).max(0))
+    for direction in (2, 0):
+        got, want, stats, ntri = _voxelize_both(emu, oracle_lib, shape, mesh, direction)
+        assert np.array_equal(got, want), f"direction {direction}: {int((got != want).sum())} cells differ"
