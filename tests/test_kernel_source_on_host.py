@@ -346,3 +346,13 @@ def test_binned_voxelizer_with_degenerate_slivers(emu, oracle_lib):
     for direction in (2, 0):
         got, want, stats, ntri = _voxelize_both(emu, oracle_lib, shape, mesh, direction)
         assert np.array_equal(got, want), f"direction {direction}: {int((got != want).sum())} cells differ"
+
+
+@pytest.mark.parametrize("D", [(2, 2, 1), (2, 1, 2)], ids=["2x2x1", "2x1x2"])
+def test_binned_voxelizer_in_every_block_of_a_decomposition(emu, oracle_lib, D):
+    """Blocks with halo layers start one cell outside the lattice (offset -1): the bin grid follows the block's offset like the ray origins do."""
+    from latticeurbanwind_b200.lbm import split
+    Ng, Nl, doms = split(H.VOX_SHAPE, D)
+    for d, Ov in doms:
+        got, want, _, _ = _voxelize_both(emu, oracle_lib, tuple(Nl), H.vox_mesh(), 2, D=D, Ov=tuple(Ov))
+        assert np.array_equal(got, want), (d, Ov)
