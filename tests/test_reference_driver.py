@@ -116,6 +116,7 @@ def test_driver_with_temperature_on_runs_the_shipped_switches(tmp_path):
         assert "tile kernel" in r.stderr, r.stderr[-2000:]
         if name == "thermal":
             assert "feat=79" in r.stderr, "the TEMPERATURE build did not run the thermal momentum kernel (FEAT = 15 | 64):\n" + r.stderr[-2000:]
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             open(os.path.join(ROOT, "gpurun_out", "reference_driver_T.log"), "w").write(r.stdout + "\n---- stderr ----\n" + r.stderr)
         outs[name] = {os.path.basename(p): open(p, "rb").read() for p in (os.path.join(b, f) for b, _, fs in os.walk(case) for f in fs if f.endswith(".vtk"))}
     assert outs["flow"] and sorted(outs["flow"]) == sorted(k for k in outs["thermal"] if k in outs["flow"])
@@ -164,6 +165,7 @@ def test_wrf_style_deck_maps_its_boundary_like_the_reference_functions(tmp_path,
     LUW_INLET_AB=reference, which makes the same binary call the reference's own functions instead. The host images the driver hands to LBM::initialize -- flags, u, rho
     after boundary mapping AND flux correction -- must be byte-identical, and both runs must finish their 20 steps."""
     images = {}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     for mode in ("ours", "reference"):
         case, dump = str(tmp_path / mode), str(tmp_path / (mode + "_dump"))
         shutil.copytree(CASE_NWP, case)
