@@ -78,6 +78,14 @@ int luw_inlet_parity_main(const int device, const bool with_lattices) {
 		Clock clock; for(const float3& q : p) sink += hd(q).x; const double t_hd = clock.stop();
 		clock.start(); for(const float3& q : p) sink += lo(q).x; const double t_lo = clock.stop();
 		printf("reference evaluation on one host thread, 100000 samples: KNN-HD %.1f us per cell, nearest %.1f us per cell (%g)\n", 1.0E6*t_hd/512.0, 1.0E6*t_lo/512.0, sink);
+		// the host part of this repo's K = 64 path (the fit over the kept samples): 64 samples on the top face, so that the search is trivial; LBM_NUM_THREADS=1 for a per-thread figure
+		Cloud small; small.name = "fit";
+		for(int i=0; i<64; i++) { small.P.push_back(float3(unit(rng), unit(rng), 128.0f)); small.U.push_back(float3(0.05f, 0.01f, 0.0f)); }
+		small.P.push_back(float3(-512.0f, -512.0f, -64.0f)); small.U.push_back(float3(0.0f)); small.P.push_back(float3(512.0f, 512.0f, -64.0f)); small.U.push_back(float3(0.0f)); // the cloud's bounding box
+		std::vector<float3> many, out(200000); for(int i=0; i<200000; i++) many.push_back(float3(0.9f*unit(rng), 0.9f*unit(rng), 127.5f));
+		KNNInterpolatorHD knn64(small.P, small.U);
+		clock.start(); luw_inlet_eval_knn(device, knn64, -1.0E9f, many.data(), many.size(), out.data()); const double t_fit = clock.stop();
+		printf("this repo, 200000 cells x 64 samples (search trivial): %.2f us per cell wall clock with LBM_NUM_THREADS=%s\n", 1.0E6*t_fit/200000.0, getenv("LBM_NUM_THREADS") ? getenv("LBM_NUM_THREADS") : "(all)");
 		return 0;
 	}
 	const uint Nx = 41u, Ny = 34u, Nz = 27u;
