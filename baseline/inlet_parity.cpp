@@ -67,6 +67,31 @@ ulong differing(const std::vector<float3>& a, const std::vector<float3>& b) {
 
 int luw_inlet_parity_main(const int device, const bool with_lattices) {
 	int bad = 0, runs = 0;
+	if(const char* golden = getenv("LUW_INLET_GOLDEN")) { // tests/golden/make_golden_inlet.py: the REFERENCE's velocities for small clouds, as a fixture for oracle/inlet_oracle.py
+		FILE* f = fopen(golden, "wb");
+		if(!f) return 1;
+		const uint Gx = 23u, Gy = 19u, Gz = 13u;
+		const std::vector<float3> gp = face_positions(Gx, Gy, Gz);
+		const uint kinds[4] = { 0u, 1u, 2u, 3u };
+		const uint head[2] = { 4u, (uint)gp.size() };
+		fwrite(head, sizeof(uint), 2u, f);
+		fwrite(gp.data(), sizeof(float3), gp.size(), f);
+		for(int k=0; k<4; k++) {
+			const Cloud c = make_cloud("golden", 0.5f*(float)Gx, 0.5f*(float)Gy, 0.5f*(float)Gz, (int)kinds[k], 91u+(uint)k);
+			const float z_threshold = k%2 ? -3.25f : -1.0E9f;
+			std::vector<float3> hd(gp.size()), lo(gp.size());
+			KNNInterpolatorHD knn(c.P, c.U); InletVelocityFieldHD fhd(knn, z_threshold);
+			NearestNeighborInterpolator nn(c.P, c.U); InletVelocityField flo(nn, z_threshold, 0.0f);
+			for(size_t i=0u; i<gp.size(); i++) { hd[i] = fhd(gp[i]); lo[i] = flo(gp[i]); }
+			const uint n = (uint)c.P.size();
+			fwrite(&n, sizeof(uint), 1u, f); fwrite(&z_threshold, sizeof(float), 1u, f);
+			fwrite(c.P.data(), sizeof(float3), c.P.size(), f); fwrite(c.U.data(), sizeof(float3), c.U.size(), f);
+			fwrite(hd.data(), sizeof(float3), hd.size(), f); fwrite(lo.data(), sizeof(float3), lo.size(), f);
+		}
+		fclose(f);
+		printf("golden inlet fixture: %u positions x 4 clouds -> %s\n", (uint)gp.size(), golden);
+		return 0;
+	}
 	if(getenv("LUW_INLET_TIMING")) { // how long the reference's own per-cell evaluation takes on one host thread: 100 000 samples (20 000 per face), 512 positions
 		Cloud c; c.name = "timing";
 		std::mt19937 rng(1u); std::uniform_real_distribution<float> unit(-512.0f, 512.0f);
