@@ -51,6 +51,23 @@ def test_no_device_means_error_not_fallback():
     assert A.device_count() == 0
 
 
+def test_inlet_searches_need_a_device_too():
+    """SURVEY 8-f2 entry points: without a CUDA device the sample searches return an error (no host fallback inside the library)."""
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    from latticeurbanwind_b200 import _cabi as A
+    L = A.lib()
+    cell, pts = np.zeros(6, np.float32), np.zeros(6, np.float32)
+    near, kept, used, mr, ex = np.zeros(2, np.uint32), np.zeros(128, np.uint32), np.zeros(2, np.uint32), np.zeros(2, np.float32), np.zeros(2, np.int32)
+    assert L.luw_inlet_nearest(0, 2, cell.ctypes.data, 2, pts.ctypes.data, near.ctypes.data) != 0
+    assert L.luw_last_error_string()
+    assert L.luw_inlet_knn(0, 2, cell.ctypes.data, 2, pts.ctypes.data, kept.ctypes.data, used.ctypes.data, mr.ctypes.data, ex.ctypes.data) != 0
+    with pytest.raises(A.LuwError):
+        A.check(L.luw_inlet_knn(0, 2, cell.ctypes.data, 2, pts.ctypes.data, kept.ctypes.data, used.ctypes.data, mr.ctypes.data, ex.ctypes.data))
+
+
 def test_header_is_plain_c():
     """The boundary is a C ABI: the header must compile as C99 on its own (no C++ or torch types in the signatures)."""
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", HEADER], capture_output=True, text=True)
