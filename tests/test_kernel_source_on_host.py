@@ -356,3 +356,23 @@ def test_binned_voxelizer_in_every_block_of_a_decomposition(emu, oracle_lib, D):
     for d, Ov in doms:
         got, want, _, _ = _voxelize_both(emu, oracle_lib, tuple(Nl), H.vox_mesh(), 2, D=D, Ov=tuple(Ov))
         assert np.array_equal(got, want), (d, Ov)
+
+
+@pytest.mark.parametrize("trial", [0, 1, 2, 3])
+def test_binned_voxelizer_on_triangle_soup(emu, oracle_lib, trial):
+    """800 unrelated triangles from a third of a cell to several lattice widths in size, some horizontal, some vertical, some with coinciding or lattice-point corners,
+    over lattices with and without pre-set flags, three ray directions: the flags of the all-triangles voxeliser, cell for cell."""
+    shape = (70, 45, 33)
+    rng = np.random.default_rng(100 + trial)
+    n = 800
+    scale = rng.choice([0.3, 2.0, 8.0, 40.0], n)[:, None, None]
+    centre = rng.uniform(-5, 75, (n, 1, 3)) * np.array([1, 0.7, 0.5])
+    P = (centre + rng.normal(0, 1, (n, 3, 3)) * scale).astype(np.float32)
+    P[:50, :, 2] = P[:50, :1, 2]
+    P[50:100, 1, :2] = P[50:100, 0, :2]
+    P[100:120, 2] = P[100:120, 1]
+    P[120:140] = np.round(P[120:140])
+    mesh = tuple(np.ascontiguousarray(P[:, k, :]).reshape(-1) for k in range(3)) + (P.reshape(-1, 3).min(0), P.reshape(-1, 3).max(0))
+    for direction in (2, 0, 1):
+        got, want, _, _ = _voxelize_both(emu, oracle_lib, shape, mesh, direction, preset=bool(trial % 2))
+        assert np.array_equal(got, want), f"direction {direction}: {int((got != want).sum())} cells differ"
