@@ -76,3 +76,41 @@ def test_cuda_searches_equal_the_oracle_and_reproduce_the_reference(k):
     if k != 3:
         want = GOLD[f"hd_{k}"][::STRIDE]
         assert float(np.abs(hd - want).max()) <= 1e-6, float(np.abs(hd - want).max())
+
+
+def test_kernel_source_selection_equals_the_oracle_on_adversarial_orders(tmp_path):
+    """CPU: csrc/lbm_inlet.cuh compiled for the host (tests/host_emulation) against the oracle's selection loop on sample orders that stress the slot bookkeeping:
+    heavy ties (lattice coordinates), samples that approach the cell monotonically (a replacement at every sample), duplicates, a NaN sample; 1 to 500 samples,
+    around the K = 64 boundary and the kernel's four-samples-per-trip loop. exact / used / slot order / max_r2_kept must be identical."""
+    import ctypes as C
+    import subprocess
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emulation")
+    if not os.path.isfile("/usr/local/cuda/include/cuda_fp16.h"):
+        pytest.skip("CUDA headers not installed")
+    so = str(tmp_path / "libinlet_emu.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-w", "-I/usr/local/cuda/include", os.path.join(here, "inlet_on_host.cpp"), "-o", so])
+    L = C.CDLL(so)
+    L.luw_inlet_knn.argtypes = [C.c_int, C.c_uint64, C.c_void_p, C.c_uint32] + [C.c_void_p] * 5
+    rng = np.random.default_rng(5)
+    for case in range(40):
+        npts, kind = int(rng.choice([1, 3, 63, 64, 65, 66, 67, 130, 257, 500])), case % 5
+        if kind == 0:
+            q = rng.uniform(-10, 10, (npts, 2))
+        elif kind == 1:
+            q = rng.integers(-4, 5, (npts, 2)).astype(float)
+        elif kind == 2:
+            q = np.stack([np.linspace(30, 0.5, npts), np.zeros(npts)], 1)
+        elif kind == 3:
+            q = np.repeat(rng.uniform(-3, 3, (max(npts // 4, 1), 2)), 4, 0)[:npts]
+        else:
+            q = rng.uniform(-10, 10, (npts, 2)); q[rng.integers(0, npts)] = [np.nan, 1.0]
+        q = np.ascontiguousarray(q, np.float32)
+        ncells = 24
+        cell = np.ascontiguousarray(rng.integers(-3, 4, (2, ncells)).astype(np.float32) + np.float32(0.0 if kind == 1 else 0.5))
+        kept = np.zeros((ncells, 64), np.uint32); used = np.zeros(ncells, np.uint32); mr = np.zeros(ncells, np.float32); ex = np.zeros(ncells, np.int32)
+        assert L.luw_inlet_knn(0, ncells, cell.ctypes.data, len(q), q.ctypes.data, kept.ctypes.data, used.ctypes.data, mr.ctypes.data, ex.ctypes.data) == 0
+        for c in range(ncells):
+            e, k, m = IO.knn_select(q, cell[0, c], cell[1, c])
+            assert ex[c] == e, (case, c)
+            if e < 0:
+                assert used[c] == len(k) and kept[c, :used[c]].tolist() == k and (mr[c] == m or (np.isnan(mr[c]) and np.isnan(m))), (case, kind, c)
